@@ -1,0 +1,89 @@
+"""Seeded synthetic matching primitives and panoramas.
+
+The reference ships no data (datasets/checkpoints are download-only,
+README.md:24-28), so the benchmark, the oracle and the parity tests all draw
+from this generator.  A *record* uses the wire format of the reference's
+primitive cache (trainRelativePoseModuleRecFD.py:207-208).
+"""
+import os
+
+import numpy as np
+
+_DATA = os.path.join(os.path.dirname(os.path.abspath(__file__)), "data")
+
+FEAT_DIM = 32  # descriptor width (model/mymodel.py:228, rpmodule.py:323)
+
+
+def shipped_params(dataset="suncg"):
+    """Rows [sigmaAngle1, sigmaAngle2, sigmaDist, sigmaFeat] of the parameter file
+    the reference ships (data/relativePoseModule/final_param_<ds>_rlevel_3.txt,
+    read by evaluation.py:95-101)."""
+    path = os.path.join(_DATA, "final_param_%s_rlevel_3.txt" % dataset)
+    return np.loadtxt(path).reshape(-1, 4)
+
+
+def random_rigid(rs):
+    axis = rs.randn(3)
+    axis /= np.linalg.norm(axis)
+    ang = rs.uniform(0.3, 2.5)
+    K = np.array([[0, -axis[2], axis[1]], [axis[2], 0, -axis[0]], [-axis[1], axis[0], 0]])
+    R = np.eye(3) + np.sin(ang) * K + (1 - np.cos(ang)) * (K @ K)
+    t = rs.randn(3) * 0.5
+    T = np.eye(4)
+    T[:3, :3] = R
+    T[:3, 3] = t
+    return T
+
+
+def _unit(v):
+    return v / np.linalg.norm(v, axis=1, keepdims=True)
+
+
+def make_pair(seed, n_s, n_t=None, inlier_frac=0.5, pos_noise=0.005, feat_noise=0.02):
+    """One scan pair's matching primitives.
+
+    source points U(-3,3)^3 m, unit normals, descriptors tanh(N(0,1)) float32
+    (SCNet's f-head is tanh bounded, model/mymodel.py:374-375); the first
+    floor(inlier_frac*min(n_s,n_t)) target rows are the rigidly moved source rows
+    plus noise, the rest are independent draws; weights are 1.0 (observed) w.p.
+    0.5, else 0.99 (rputil.py:229-235).
+    """
+    if n_t is None:
+        n_t = n_s
+    rs = np.random.RandomState(seed)
+    T = random_rigid(rs)
+    R, t = T[:3, :3], T[:3, 3]
+    pc_s = rs.uniform(-3, 3, size=(n_s, 3))
+    nrm_s = _unit(rs.randn(n_s, 3))
+    feat_s = np.tanh(rs.randn(n_s, FEAT_DIM))
+    pc_t = rs.uniform(-3, 3, size=(n_t, 3))
+    nrm_t = _unit(rs.randn(n_t, 3))
+    feat_t = np.tanh(rs.randn(n_t, FEAT_DIM))
+    n_in = int(np.floor(inlier_frac * min(n_s, n_t)))
+    if n_in > 0:
+        pc_t[:n_in] = pc_s[:n_in] @ R.T + t + rs.randn(n_in, 3) * pos_noise
+        nrm_t[:n_in] = nrm_s[:n_in] @ R.T
+        feat_t[:n_in] = feat_s[:n_in] + rs.randn(n_in, FEAT_DIM) * feat_noise
+    w_s = np.where(rs.rand(n_s) < 0.5, 1.0, 0.99)
+    w_t = np.where(rs.rand(n_t) < 0.5, 1.0, 0.99)
+    return {
+        "pc_src": pc_s, "normal_src": nrm_s, "feat_src": feat_s.astype(np.float32), "weight_src": w_s,
+        "pc_tgt": pc_t, "normal_tgt": nrm_t, "feat_tgt": feat_t.astype(np.float32), "weight_tgt": w_t,
+        "R_gt": T,
+    }
+
+
+def record_to_dicts(rec):
+    """(dataS, dataT) in the layout RelativePoseEstimation_helper takes (rpmodule.py:317-325)."""
+    s = {"pc": rec["pc_src"], "normal": rec["normal_src"], "feat": rec["feat_src"], "weight": rec["weight_src"]}
+    t = {"pc": rec["pc_tgt"], "normal": rec["normal_tgt"], "feat": rec["feat_tgt"], "weight": rec["weight_tgt"]}
+    return s, t
+
+
+def keypoints_for_nominal_N(N, topk=5):
+    """n_s = n_t = ceil(N/topK): nominal 64..2048 -> N_actual 65,130,260,515,1025,2050."""
+    return -(-N // topk)
+
+
+def make_batch(first_seed, count, n_s, n_t=None, **kw):
+    return [make_pair(first_seed + i, n_s, n_t, **kw) for i in range(count)]

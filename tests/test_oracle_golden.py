@@ -1,0 +1,57 @@
+"""The oracle (oracle/rp_oracle.py) against outputs of the reference itself.
+
+Golden vectors: tests/golden/rp_golden.npz, produced by running the unmodified
+reference (tests/golden/make_golden.py).  Bars: top-k index sets and surviving
+pair sets identical, pair weights to 1e-12 relative, poses to 1e-10 Frobenius
+(the two sides run the same LAPACK/ARPACK calls; what differs is summation
+order only)."""
+import numpy as np
+import pytest
+
+from oracle import rp_oracle
+from oracle.ref_loader import reference_available
+from tests.golden_util import load_cases
+
+CASES = load_cases()
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c.name for c in CASES])
+def test_oracle_matches_golden(case):
+    para = case.apply(rp_oracle.Params())
+    s, t = case.dicts()
+    trace = {}
+    T = rp_oracle.solve_pair(s, t, para, trace)
+    assert T.shape == (4, 4) and T.dtype == np.float64
+    if case.topk_sets is not None:
+        assert np.array_equal(trace['topk'], case.topk_sets), "top-k index sets differ"
+    if case.row is not None:
+        n_t = s['pc'].shape[0] * 0 + t['pc'].shape[0]
+        cor = trace['corres']
+        flat = cor[0] * n_t + cor[1]
+        got = np.stack((flat[trace['pairs'][:, 0]], flat[trace['pairs'][:, 1]]), 1)
+        assert np.array_equal(got, case.pair_keys()), "surviving pair sets differ"
+        assert np.allclose(trace['w'], case.w, rtol=1e-12, atol=0)
+    assert np.linalg.norm(T - case.T) <= 1e-10, np.linalg.norm(T - case.T)
+
+
+def test_oracle_unknown_method_raises():
+    case = CASES[0]
+    para = case.apply(rp_oracle.Params())
+    para.method = 'nope'
+    s, t = case.dicts()
+    with pytest.raises(Exception):
+        rp_oracle.solve_pair(s, t, para)
+
+
+@pytest.mark.skipif(not reference_available(), reason="/root/reference not present (GPU box)")
+def test_oracle_matches_live_reference():
+    from oracle.ref_loader import load_reference_rpmodule, reference_opts
+    from relativepose_b200 import synth
+    ref = load_reference_rpmodule()
+    P = synth.shipped_params('suncg')
+    for seed, n in ((100, 20), (101, 37), (102, 64)):
+        rec = synth.make_pair(seed, n)
+        s, t = synth.record_to_dicts(rec)
+        Tr = ref.RelativePoseEstimation_helper(s, t, reference_opts(*P[0]))
+        To = rp_oracle.solve_pair(s, t, rp_oracle.Params(*P[0]))
+        assert np.linalg.norm(Tr - To) <= 1e-10
