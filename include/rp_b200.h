@@ -1,0 +1,167 @@
+/* rp_b200.h -- C ABI of the B200-native relative-pose hot path.
+ *
+ * The reference (zhenpeiyang/RelativePose @ 2e9fdf5) has no FFI/plugin layer; its
+ * boundary is a Python call surface.  This header is the
+ * C-ABI a maintainer would bind underneath that surface (ctypes stub shown in
+ * INTEGRATION.md).  Every entry point cites the reference function it replaces.
+ *
+ * Conventions: plain pointers and sizes only; all data pointers are DEVICE
+ * pointers unless the name ends in _host; `stream` is a cudaStream_t passed as
+ * void*; every function returns 0 on success or a negative RP_ERR_* code and
+ * never throws; no allocation happens in the steady state (caller-owned
+ * workspace, size from the *_workspace_bytes query); calls are asynchronous on
+ * `stream` and re-entrant as long as concurrent calls use disjoint workspaces.
+ *
+ * Ragged batches: pair b owns source keypoints [off_s[b], off_s[b+1]) and target
+ * keypoints [off_t[b], off_t[b+1]) of the concatenated keypoint arrays.
+ */
+#ifndef RP_B200_H
+#define RP_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RP_ABI_VERSION 1
+
+/* error codes (function return values) */
+#define RP_OK 0
+#define RP_ERR_INVALID_ARG (-1)
+#define RP_ERR_WORKSPACE_TOO_SMALL (-2)
+#define RP_ERR_UNSUPPORTED (-3)   /* topK > RP_MAX_TOPK, feature dim > 128, n_t too large for shared memory */
+#define RP_ERR_CUDA (-4)
+#define RP_ERR_NO_DEVICE (-5)
+
+/* per-pair status (status[b]); 1..5 are the reference's identity early exits */
+#define RP_STATUS_OK 0
+#define RP_STATUS_FEW_KEYPOINTS 1   /* rpmodule.py:346-348 */
+#define RP_STATUS_FEW_CORRES 2      /* rpmodule.py:377-379 */
+#define RP_STATUS_FEW_DIST 3        /* rpmodule.py:406-408 */
+#define RP_STATUS_FEW_ANGLE 4       /* rpmodule.py:440-443 */
+#define RP_STATUS_ZERO_WEIGHT 5     /* rpmodule.py:469-472 */
+#define RP_STATUS_EDGE_OVERFLOW (-2) /* pair needs a larger edge capacity; re-run with a bigger workspace */
+#define RP_STATUS_UNSUPPORTED (-3)
+
+#define RP_MAX_TOPK 8
+#define RP_MAX_FEAT_DIM 128
+
+/* para.method (rputil.py:22, dispatch rpmodule.py:491-508) */
+#define RP_METHOD_HORN87 0
+#define RP_METHOD_SPECTRAL 1
+#define RP_METHOD_IRLS 2
+#define RP_METHOD_IRLS_SM 3
+
+/* stages for rp_solve_batch_ex(stop_after) */
+#define RP_STAGE_TOPK 1      /* rpmodule.py:342-375 */
+#define RP_STAGE_AFFINITY 2  /* rpmodule.py:382-472 */
+#define RP_STAGE_SOLVE 3     /* rpmodule.py:484-508 */
+
+/* Solver parameters: `rputil.opts` (RPModule/rputil.py:11-22) reduced on the HOST, with
+ * numpy arithmetic, to the scalars the reference actually uses, so thresholds are the
+ * reference's bit patterns:
+ *   feat_den      = 2*np.power(sigmaFeat/5, 2)              rpmodule.py:356,358
+ *   feat_den_obs  = 2*np.power((sigmaFeat/1.2)/5, 2)        rpmodule.py:357,358
+ *   dist_thre_sq  = np.power(distThre, 2)                   rpmodule.py:404
+ *   sep_thre      = 1.5*np.power(distSepThre, 2)            rpmodule.py:404
+ *   angle_thre_sq = np.power(angleThre, 2)                  rpmodule.py:434-436
+ *   den_dist      = 2*sigmaDist**2, den_a1 = 2*sigmaAngle1**2, den_a2 = 2*sigmaAngle2**2   rpmodule.py:457-460
+ */
+typedef struct rp_params {
+    double feat_den;
+    double feat_den_obs;
+    double dist_thre_sq;
+    double sep_thre;
+    double angle_thre_sq;
+    double den_dist;
+    double den_a1;
+    double den_a2;
+    double mu;          /* rputil.py:20 */
+    double power_tol;   /* stop power iteration when ||u_k - u_{k-1}||_2 <= power_tol (reference: ARPACK tol=0) */
+    int32_t topk;       /* rputil.py:21; effective K = min(topk, n_t-1), rpmodule.py:368 */
+    int32_t method;     /* RP_METHOD_* */
+    int32_t max_power_iters;
+    int32_t reserved;
+} rp_params;
+
+#define RP_STATS_STRIDE 8
+/* stats[b*8 + k]: 0 N (=n_s*K), 1 pairs after distance test, 2 pairs after angle test,
+ * 3 pairs with non-zero weight, 4 power iterations (sum over alternations),
+ * 5 max power iterations in one alternation, 6 1 if some alternation hit max_power_iters, 7 K */
+
+/* Optional stage-boundary outputs (device pointers; any may be NULL).  Used by the parity tests. */
+typedef struct rp_debug {
+    int32_t* topk_idx;   /* [sum n_s, max_topk] target index of each candidate, -1 padded; order = descending weight */
+    double* topk_f;      /* [sum n_s, max_topk] normalised weight wij of each candidate (rpmodule.py:362,453-454) */
+    float* dij;          /* per pair n_s*n_t float32 descriptor distances at dij_off[b] (rpmodule.py:355) */
+    const int64_t* dij_off; /* [B] element offsets into dij */
+    int32_t* edge_rc;    /* [B, edge_cap, 2] surviving (first,second) correspondence ids, row-major order NOT guaranteed */
+    double* edge_w;      /* [B, edge_cap] pair weight w (rpmodule.py:457-467) */
+    int64_t edge_cap;
+    double* u;           /* [B, 5, u_stride] leading eigenvector per alternation (irls+sm / spectral) */
+    int64_t u_stride;
+} rp_debug;
+
+int rp_abi_version(void);
+
+/* Number of SMs / device name of the current CUDA device (host utility). */
+int rp_device_info(int* sm_count, int* cc_major, int* cc_minor, size_t* total_mem);
+
+/* Workspace for rp_solve_batch*: `n_slots` resident CTAs (0 = default: one or two per SM),
+ * each able to hold a pair with n_s <= max_ns, n_t <= max_nt, K <= max_topk and up to
+ * `edge_cap` pairs passing the distance test (0 = worst case N(N-1)/2). */
+int rp_solve_workspace_bytes(int n_slots, int max_ns, int max_nt, int max_topk, int feat_dim,
+                             int64_t edge_cap, size_t* bytes);
+
+/* Replaces RelativePoseEstimation_helper (RPModule/rpmodule.py:317-508) for a ragged batch of B
+ * scan pairs -- descriptor distance + soft match + top-k, pairwise consistency affinity,
+ * spectral/IRLS solve -- one fused launch.
+ *   pc_*   [sum n, 3] float64   'pc'      nrm_* [sum n, 3] float64 'normal'
+ *   feat_* [sum n, feat_dim] float32 'feat' (before /100)   w_* [sum n] float64 'weight'
+ *   params [n_params] (device), param_idx [B] (device) or NULL (all pairs use params[0])
+ *   zero_row_topk [B, max_topk] (device) or NULL: the candidate set to use for a source keypoint whose
+ *     soft-match row underflows to all zeros (rpmodule.py:359-363 zeroes the row; np.argpartition then
+ *     returns an order-of-introselect set that depends only on (n_t, K)).  The host fills it with
+ *     np.argpartition(-np.zeros(n_t), K)[:K] so ties resolve exactly like the reference; NULL = by distance.
+ *   T_out [B,16] row-major 4x4 float64; status [B]; stats [B,8] (may be NULL)
+ */
+int rp_solve_batch(int B, const int32_t* off_s, const int32_t* off_t,
+                   const double* pc_s, const double* nrm_s, const float* feat_s, const double* w_s,
+                   const double* pc_t, const double* nrm_t, const float* feat_t, const double* w_t,
+                   int feat_dim, const rp_params* params, const int32_t* param_idx,
+                   const int32_t* zero_row_topk,
+                   int max_ns, int max_nt, int max_topk,
+                   int n_slots, int64_t edge_cap, void* workspace, size_t workspace_bytes,
+                   double* T_out, int32_t* status, int32_t* stats, void* stream);
+
+/* Same, stopping after a stage (RP_STAGE_*) and filling the stage-boundary outputs in `dbg`
+ * (host struct holding device pointers).  rp_match_topk / rp_affinity_build are this call with
+ * stop_after = RP_STAGE_TOPK / RP_STAGE_AFFINITY. */
+int rp_solve_batch_ex(int B, const int32_t* off_s, const int32_t* off_t,
+                      const double* pc_s, const double* nrm_s, const float* feat_s, const double* w_s,
+                      const double* pc_t, const double* nrm_t, const float* feat_t, const double* w_t,
+                      int feat_dim, const rp_params* params, const int32_t* param_idx,
+                      const int32_t* zero_row_topk,
+                      int max_ns, int max_nt, int max_topk,
+                      int n_slots, int64_t edge_cap, void* workspace, size_t workspace_bytes,
+                      double* T_out, int32_t* status, int32_t* stats,
+                      int stop_after, const rp_debug* dbg, void* stream);
+
+/* Stage entry: rpmodule.py:342-375 only (dij -> wij -> row-normalise -> top-k). */
+int rp_match_topk(int B, const int32_t* off_s, const int32_t* off_t,
+                  const float* feat_s, const double* w_s, const float* feat_t, const double* w_t,
+                  int feat_dim, const rp_params* params, const int32_t* param_idx,
+                  const int32_t* zero_row_topk,
+                  int max_ns, int max_nt, int max_topk,
+                  int n_slots, void* workspace, size_t workspace_bytes,
+                  int32_t* topk_idx, double* topk_f, int32_t* status, void* stream);
+
+/* Kernel launch counter (number of kernels this library launched since load); bench.py reports it. */
+int64_t rp_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RP_B200_H */

@@ -1,0 +1,86 @@
+"""ctypes binding of librp_b200.so (the C ABI in include/rp_b200.h).
+
+There is NO CPU fallback: if the library is missing or no CUDA device is usable,
+the product path raises.  (The numpy oracle under oracle/ is test infrastructure
+and is never imported from here.)
+"""
+import ctypes
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.environ.get("RP_B200_LIB", os.path.join(HERE, "librp_b200.so"))   # env override: tuning variants only
+
+RP_OK = 0
+ERRORS = {-1: "RP_ERR_INVALID_ARG", -2: "RP_ERR_WORKSPACE_TOO_SMALL", -3: "RP_ERR_UNSUPPORTED",
+          -4: "RP_ERR_CUDA", -5: "RP_ERR_NO_DEVICE"}
+
+STAGE_TOPK, STAGE_AFFINITY, STAGE_SOLVE = 1, 2, 3
+METHODS = {"horn87": 0, "spectral": 1, "irls": 2, "irls+sm": 3}
+MAX_TOPK = 8
+STATS_STRIDE = 8
+STATUS_EDGE_OVERFLOW = -2
+STATUS_UNSUPPORTED = -3
+
+
+class RpParams(ctypes.Structure):
+    _fields_ = [("feat_den", ctypes.c_double), ("feat_den_obs", ctypes.c_double),
+                ("dist_thre_sq", ctypes.c_double), ("sep_thre", ctypes.c_double),
+                ("angle_thre_sq", ctypes.c_double), ("den_dist", ctypes.c_double),
+                ("den_a1", ctypes.c_double), ("den_a2", ctypes.c_double),
+                ("mu", ctypes.c_double), ("power_tol", ctypes.c_double),
+                ("topk", ctypes.c_int32), ("method", ctypes.c_int32),
+                ("max_power_iters", ctypes.c_int32), ("reserved", ctypes.c_int32)]
+
+
+class RpDebug(ctypes.Structure):
+    _fields_ = [("topk_idx", ctypes.c_void_p), ("topk_f", ctypes.c_void_p),
+                ("dij", ctypes.c_void_p), ("dij_off", ctypes.c_void_p),
+                ("edge_rc", ctypes.c_void_p), ("edge_w", ctypes.c_void_p), ("edge_cap", ctypes.c_int64),
+                ("u", ctypes.c_void_p), ("u_stride", ctypes.c_int64)]
+
+
+EXPORTS = ("rp_abi_version", "rp_device_info", "rp_solve_workspace_bytes", "rp_solve_batch",
+           "rp_solve_batch_ex", "rp_match_topk", "rp_launch_count")
+
+_lib = None
+
+
+class NativeLibraryMissing(RuntimeError):
+    pass
+
+
+def load():
+    """Load the CUDA library or raise (no fallback)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise NativeLibraryMissing(
+            "%s not found: build it with `python -m relativepose_b200.build` (nvcc, sm_100a). "
+            "relativepose_b200 has no CPU fallback." % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH)
+    vp, i32, i64 = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64
+    lib.rp_abi_version.restype = i32
+    lib.rp_launch_count.restype = i64
+    lib.rp_device_info.restype = i32
+    lib.rp_device_info.argtypes = [ctypes.POINTER(ctypes.c_int)] * 3 + [ctypes.POINTER(ctypes.c_size_t)]
+    lib.rp_solve_workspace_bytes.restype = i32
+    lib.rp_solve_workspace_bytes.argtypes = [i32, i32, i32, i32, i32, i64, ctypes.POINTER(ctypes.c_size_t)]
+    common = [i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, vp, vp, vp, i32, i32, i32, i32, i64, vp,
+              ctypes.c_size_t, vp, vp, vp]
+    lib.rp_solve_batch.restype = i32
+    lib.rp_solve_batch.argtypes = common + [vp]
+    lib.rp_solve_batch_ex.restype = i32
+    lib.rp_solve_batch_ex.argtypes = common + [i32, ctypes.POINTER(RpDebug), vp]
+    lib.rp_match_topk.restype = i32
+    lib.rp_match_topk.argtypes = [i32, vp, vp, vp, vp, vp, vp, i32, vp, vp, vp, i32, i32, i32, i32, vp,
+                                  ctypes.c_size_t, vp, vp, vp, vp]
+    if lib.rp_abi_version() != 1:
+        raise RuntimeError("librp_b200.so ABI mismatch")
+    _lib = lib
+    return lib
+
+
+def check(rc, what):
+    if rc != RP_OK:
+        raise RuntimeError("%s failed: %s (%d)" % (what, ERRORS.get(rc, "?"), rc))

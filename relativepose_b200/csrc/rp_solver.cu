@@ -1,0 +1,1157 @@
+// rp_solver.cu -- B200 (sm_100a) relative-pose solver: small persistent CTAs, one scan pair at a time each.
+//
+// Replaces the reference's RelativePoseEstimation_helper (RPModule/rpmodule.py:317-508) and the four
+// fitters it dispatches to (fit_horn87 :60, fit_spectral :86, fit_irls :169, fit_irls_sm :212,
+// horn87_np :17).  Nothing here is translated from the reference: the NumPy code enumerates all
+// N(N-1)/2 correspondence pairs with fancy indexing, stacks 4M rows and calls ARPACK on an
+// (n_s*n_t)^2 sparse matrix; this kernel
+//   A. forms the n_s x n_t float32 descriptor distances with NumPy's exact summation order (so the
+//      top-k index sets are bit-identical), soft-match weights, per-row top-k         (:342-375)
+//   B. gathers per-correspondence geometry (float64 in the slot's workspace, float32 copy in smem)
+//   C. runs a conservative float32 pre-test of the distance-consistency condition over every
+//      correspondence pair and emits a compact candidate list (never rejects a pair the float64
+//      test would accept: margins scale with the coordinate magnitude)               (:382-404)
+//   D. per candidate: exact float64 distance test in NumPy's operation order, angle consistency,
+//      pair weight; survivors set two bits of a symmetric bit mask                   (:399-472)
+//   E. builds a deterministic CSR (both directions, columns ascending) of the compact N x N affinity W
+//   F. runs the fitters on per-correspondence quantities: every stacked-row sum of the reference
+//      factors as sum_rows = sum_c (row-degree of c) * (per-correspondence term), the spectral
+//      affinity is A = diag(h) W + W diag(h), and x = u_p u_q w_pq has degrees u .* (W u) -- so each
+//      IRLS round is an O(N) reduction and each power-iteration step one CSR pass with two
+//      right-hand sides and a single barrier.
+// All arithmetic that decides anything (filters) or feeds the pose is float64, like the reference.
+//
+// Determinism: every reduction has a fixed order; atomics are used only for bit-mask OR and for slot
+// allocation in the candidate list (which changes the order candidates are *processed* in, never a value
+// or the position a value is stored at).  Results do not depend on which CTA/SM/GPU runs a pair.
+#include <cuda_runtime.h>
+#include <math_constants.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/rp_b200.h"
+
+namespace {
+
+#ifndef RP_THREADS
+#define RP_THREADS 128
+#endif
+#ifndef RP_MIN_BLOCKS
+#define RP_MIN_BLOCKS 4
+#endif
+constexpr int T = RP_THREADS;       // threads per CTA: small CTAs, several per SM, so the serial 4x4 eigen
+constexpr int NWARP = T / 32;       // section of one pair overlaps the parallel phases of the others
+constexpr int STAGE = 64;           // per-warp candidate staging entries
+constexpr int KMAX = RP_MAX_TOPK;
+constexpr int NSUM = 25;            // sums per Horn fit
+constexpr int NUM_ALTER = 5;        // rpmodule.py:229
+constexpr int NUM_REWEIGHT = 5;     // rpmodule.py:228
+constexpr double OFFSET = 50.0;     // rpmodule.py:231
+constexpr double EPS = 1e-12;       // rpmodule.py:232
+constexpr double UNOBS_DAMP = 0.6;  // rpmodule.py:467
+constexpr float FEAT_SCALING = 100.0f;  // rpmodule.py:327
+
+static long long g_launches = 0;
+
+struct SolveArgs {
+    int B;
+    const int32_t* off_s;
+    const int32_t* off_t;
+    const double* pc_s; const double* nrm_s; const float* feat_s; const double* w_s;
+    const double* pc_t; const double* nrm_t; const float* feat_t; const double* w_t;
+    int feat_dim;
+    const rp_params* params;
+    const int32_t* param_idx;
+    const int32_t* zero_row_topk;
+    int max_topk;
+    long long edge_cap;
+    char* ws;               // workspace base; first 256 bytes = header (work counter)
+    size_t slot_bytes;
+    size_t o_geo, o_cj, o_mask, o_edges, o_ew, o_rowstart, o_cols, o_vals;
+    int Nmax, NWmax;
+    double* T_out; int32_t* status; int32_t* stats;
+    int stop_after;
+    int has_dbg;
+    rp_debug dbg;
+    int mask_in_smem;
+    int tfeat_stride;       // odd stride (floats) of the staged target descriptors
+    size_t sm_mask_off;     // byte offset of the bit mask in dynamic shared memory (when mask_in_smem)
+};
+
+// ----------------------------------------------------------------------------------------------
+// small device helpers
+__device__ __forceinline__ double shfl_xor_d(double v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += shfl_xor_d(v, o);
+    return v;
+}
+
+// NumPy's float32 add.reduce over a contiguous axis (pairwise_sum, 8 accumulators for 8<=n<=128;
+// numpy/_core/src/umath/loops_utils.h.src) applied to (s-t)^2.  No FMA contraction anywhere.
+__device__ __forceinline__ float sq_diff(const float* __restrict__ s, const float* __restrict__ t, int c) {
+    float d = __fsub_rn(s[c], t[c]);
+    return __fmul_rn(d, d);
+}
+__device__ float numpy_sqdist_f32(const float* __restrict__ s, const float* __restrict__ t, int n) {
+    if (n < 8) {
+        float res = 0.f;
+        for (int i = 0; i < n; ++i) res = __fadd_rn(res, sq_diff(s, t, i));
+        return res;
+    }
+    float r[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) r[j] = sq_diff(s, t, j);
+    int i;
+    for (i = 8; i < n - (n % 8); i += 8) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) r[j] = __fadd_rn(r[j], sq_diff(s, t, i + j));
+    }
+    float res = __fadd_rn(__fadd_rn(__fadd_rn(r[0], r[1]), __fadd_rn(r[2], r[3])),
+                          __fadd_rn(__fadd_rn(r[4], r[5]), __fadd_rn(r[6], r[7])));
+    for (; i < n; ++i) res = __fadd_rn(res, sq_diff(s, t, i));
+    return res;
+}
+
+// (a0*b0 + a1*b1) + a2*b2 with separately rounded products: NumPy's (a*b).sum(1) on [P,3].
+__device__ __forceinline__ double dot3_np(double a0, double a1, double a2, double b0, double b1, double b2) {
+    return __dadd_rn(__dadd_rn(__dmul_rn(a0, b0), __dmul_rn(a1, b1)), __dmul_rn(a2, b2));
+}
+__device__ __forceinline__ double clip1(double x) { return fmin(fmax(x, -1.0), 1.0); }
+
+// ----------------------------------------------------------------------------------------------
+// 4x4 symmetric eigen: eigenvector of the largest eigenvalue of Horn's N (rpmodule.py:46-53).
+// Cyclic Jacobi -- robust path (used when the fast path declines).
+__device__ void jacobi4_max(const double A_in[4][4], double q[4]) {
+    double A[4][4], V[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { A[i][j] = A_in[i][j]; V[i][j] = (i == j) ? 1.0 : 0.0; }
+    for (int sweep = 0; sweep < 30; ++sweep) {
+        double off = 0.0, diag = 0.0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            diag += A[i][i] * A[i][i];
+#pragma unroll
+            for (int j = i + 1; j < 4; ++j) off += A[i][j] * A[i][j];
+        }
+        if (off <= 1e-32 * (diag + off) || off == 0.0) break;
+#pragma unroll
+        for (int p = 0; p < 3; ++p) {
+#pragma unroll
+            for (int qq = p + 1; qq < 4; ++qq) {
+                double apq = A[p][qq];
+                if (apq == 0.0) continue;
+                double theta = (A[qq][qq] - A[p][p]) / (2.0 * apq);
+                double t = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+                double c = rsqrt(t * t + 1.0);
+                double s = t * c;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {      // A <- A J
+                    double akp = A[k][p], akq = A[k][qq];
+                    A[k][p] = c * akp - s * akq;
+                    A[k][qq] = s * akp + c * akq;
+                }
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {      // A <- J^T A
+                    double apk = A[p][k], aqk = A[qq][k];
+                    A[p][k] = c * apk - s * aqk;
+                    A[qq][k] = s * apk + c * aqk;
+                }
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    double vkp = V[k][p], vkq = V[k][qq];
+                    V[k][p] = c * vkp - s * vkq;
+                    V[k][qq] = s * vkp + c * vkq;
+                }
+            }
+        }
+    }
+    int best = 0;
+    double bv = A[0][0];
+#pragma unroll
+    for (int i = 1; i < 4; ++i) if (A[i][i] > bv) { bv = A[i][i]; best = i; }
+    double nn = 0.0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { q[k] = (best == 0 ? V[k][0] : best == 1 ? V[k][1] : best == 2 ? V[k][2] : V[k][3]); nn += q[k] * q[k]; }
+    nn = rsqrt(nn);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) q[k] *= nn;
+}
+
+__device__ __forceinline__ double det3(double a, double b, double c, double d, double e, double f,
+                                       double g, double h, double i) {
+    return a * (e * i - f * h) - b * (d * i - f * g) + c * (d * h - e * g);
+}
+
+// Column `col` of adj(B) for symmetric 4x4 B.  adj(B) = alpha v v^T when B is singular of rank 3.
+__device__ __forceinline__ void adj_col(const double B[4][4], int col, double v[4]) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        int r0 = (k == 0) ? 1 : 0, r1 = (k <= 1) ? 2 : 1, r2 = (k <= 2) ? 3 : 2;
+        int c0 = (col == 0) ? 1 : 0, c1 = (col <= 1) ? 2 : 1, c2 = (col <= 2) ? 3 : 2;
+        double d = det3(B[r0][c0], B[r0][c1], B[r0][c2], B[r1][c0], B[r1][c1], B[r1][c2],
+                        B[r2][c0], B[r2][c1], B[r2][c2]);
+        v[k] = ((k + col) & 1) ? -d : d;
+    }
+}
+
+// Fast path: lambda_max by Newton on the characteristic polynomial, eigenvector from the adjugate, Rayleigh
+// polish.  lam_hint > 0 warm-starts Newton at the previous fit's eigenvalue; the result is accepted only with
+// a certificate that it is the LARGEST root (first and second derivative of the real-rooted quartic positive;
+// the third is 24*lam) and a small eigen-residual.  Otherwise Newton restarts from the safe upper bound, and
+// if that declines too (near-degenerate top eigenvalue) the caller falls back to Jacobi.
+__device__ bool horn_eig_fast(const double N[4][4], double q[4], double lam_hint, double* lam_out) {
+    double fro = 0.0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) fro += N[i][j] * N[i][j];
+    if (!(fro > 0.0) || !isfinite(fro)) return false;
+    // characteristic polynomial  l^4 + c2 l^2 + c1 l + c0  (trace N == 0)
+    double c2 = -0.5 * fro;
+    double m0 = det3(N[1][1], N[1][2], N[1][3], N[2][1], N[2][2], N[2][3], N[3][1], N[3][2], N[3][3]);
+    double m1 = det3(N[0][0], N[0][2], N[0][3], N[2][0], N[2][2], N[2][3], N[3][0], N[3][2], N[3][3]);
+    double m2 = det3(N[0][0], N[0][1], N[0][3], N[1][0], N[1][1], N[1][3], N[3][0], N[3][1], N[3][3]);
+    double m3 = det3(N[0][0], N[0][1], N[0][2], N[1][0], N[1][1], N[1][2], N[2][0], N[2][1], N[2][2]);
+    double c1 = -(m0 + m1 + m2 + m3);
+    double k0 = det3(N[1][0], N[1][2], N[1][3], N[2][0], N[2][2], N[2][3], N[3][0], N[3][2], N[3][3]);
+    double k1 = det3(N[1][0], N[1][1], N[1][3], N[2][0], N[2][1], N[2][3], N[3][0], N[3][1], N[3][3]);
+    double k2 = det3(N[1][0], N[1][1], N[1][2], N[2][0], N[2][1], N[2][2], N[3][0], N[3][1], N[3][2]);
+    double c0 = N[0][0] * m0 - N[0][1] * k0 + N[0][2] * k1 - N[0][3] * k2;
+    const double scale = sqrt(fro);
+    const double bound = 0.8660254037844387 * scale * (1.0 + 1e-12);   // >= lambda_max (traceless symmetric 4x4)
+    const bool have_hint = (lam_hint > 0.0) && (lam_hint < bound);
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        double lam = (attempt == 0 && have_hint) ? lam_hint : bound;
+        bool ok = false;
+        for (int it = 0; it < 60; ++it) {
+            double l2 = lam * lam;
+            double p = (l2 + c2) * l2 + c1 * lam + c0;
+            double dp = (4.0 * l2 + 2.0 * c2) * lam + c1;
+            if (!(dp > 0.0)) break;
+            double step = p / dp;
+            lam -= step;
+            if (fabs(step) <= 4.0e-16 * fabs(lam)) { ok = true; break; }
+            if (!(lam > 0.0) || !(lam <= 2.0 * bound)) break;
+        }
+        if (ok) {   // largest-root certificate
+            double dp = (4.0 * lam * lam + 2.0 * c2) * lam + c1;
+            double ddp = 12.0 * lam * lam + 2.0 * c2;
+            ok = (dp > 0.0) && (ddp > 0.0) && (lam > 0.0);
+        }
+        if (ok) {
+            double v[4];
+            bool good = true;
+            for (int polish = 0; polish < 2 && good; ++polish) {
+                double Bm[4][4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) Bm[i][j] = N[i][j] - (i == j ? lam : 0.0);
+                // diagonal of adj(B) = alpha v_i^2: take the column with the largest diagonal cofactor
+                double d0 = det3(Bm[1][1], Bm[1][2], Bm[1][3], Bm[2][1], Bm[2][2], Bm[2][3], Bm[3][1], Bm[3][2], Bm[3][3]);
+                double d1 = det3(Bm[0][0], Bm[0][2], Bm[0][3], Bm[2][0], Bm[2][2], Bm[2][3], Bm[3][0], Bm[3][2], Bm[3][3]);
+                double d2 = det3(Bm[0][0], Bm[0][1], Bm[0][3], Bm[1][0], Bm[1][1], Bm[1][3], Bm[3][0], Bm[3][1], Bm[3][3]);
+                double d3 = det3(Bm[0][0], Bm[0][1], Bm[0][2], Bm[1][0], Bm[1][1], Bm[1][2], Bm[2][0], Bm[2][1], Bm[2][2]);
+                int col = 0; double dm = fabs(d0);
+                if (fabs(d1) > dm) { dm = fabs(d1); col = 1; }
+                if (fabs(d2) > dm) { dm = fabs(d2); col = 2; }
+                if (fabs(d3) > dm) { dm = fabs(d3); col = 3; }
+                // |adj| ~ prod(lambda_max - lambda_i): tiny => (near-)degenerate top eigenvalue
+                if (!(dm > 1e-9 * scale * scale * scale)) { good = false; break; }
+                if (col == 0) adj_col(Bm, 0, v); else if (col == 1) adj_col(Bm, 1, v);
+                else if (col == 2) adj_col(Bm, 2, v); else adj_col(Bm, 3, v);
+                double nn = rsqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2] + v[3] * v[3]);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) v[k] *= nn;
+                double rq = 0.0;                 // Rayleigh quotient refines lambda (cubic convergence)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    double sx = 0.0;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) sx += N[i][j] * v[j];
+                    rq += v[i] * sx;
+                }
+                lam = rq;
+            }
+            if (good) {
+                double res = 0.0;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    double sx = -lam * v[i];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) sx += N[i][j] * v[j];
+                    res += sx * sx;
+                }
+                if (res <= 1e-22 * fro) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) q[k] = v[k];
+                    *lam_out = lam;
+                    return true;
+                }
+            }
+        }
+        if (!have_hint) break;   // the bound start was the first attempt
+    }
+    return false;
+}
+
+// ----------------------------------------------------------------------------------------------
+struct Pose { double R[9]; double t[3]; double sm[3]; double tm[3]; };
+
+struct Shared {
+    double red[2][NWARP][NSUM];
+    double fin[32];
+    Pose pose;
+    double scal[8];      // 0: lambda warm start, 1: prefilter margin
+    int cnt[8];          // 0 candidate count, 1 M1, 2 M2, 3 scan carry, 4 pair id, 5 nnz
+    int warp_tot[NWARP];
+    unsigned stage[NWARP][STAGE];
+    float sfeat[NWARP][RP_MAX_FEAT_DIM];
+};
+
+// Per-correspondence geometry, SoA in the slot's global workspace (stride = Nmax doubles).
+enum { G_PX = 0, G_PY, G_PZ, G_QX, G_QY, G_QZ, G_NX, G_NY, G_NZ, G_MX, G_MY, G_MZ, G_WS, G_WT, G_F, G_DEG, G_COUNT };
+
+struct PairView {
+    int ns, nt, K, N, NW;
+    double* geo; int gstride;
+    int* cj;
+    unsigned* mask;
+    unsigned* edges; double* ew;
+    int* rowstart; uint16_t* cols; double* vals;
+    // shared-memory vectors
+    double *aP, *aN, *res, *ua, *ub, *sv;
+    float* f32pos;       // [6][N] float32 copy of the positions (phase C only; aliases the vectors)
+};
+
+// One weighted Horn fit from per-correspondence weights aP (positions, incl. mu) / aN (normals):
+// centroids (rpmodule.py:240-243), 3x3 cross-covariance (:245-249,39-43), Horn N (:46-49), eigen, R (:54-56),
+// t (:250).  `mean_div`: centroid weights are aP/mean_div (fit_horn87 / fit_spectral's first fit use the
+// un-scaled pair weights for the centroids, rpmodule.py:72-75,107-110).
+__device__ void horn_fit(Shared& sh, const PairView& pv, double mean_div, int& red_buf) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    double acc[NSUM];
+#pragma unroll
+    for (int k = 0; k < NSUM; ++k) acc[k] = 0.0;
+    const double* geo = pv.geo; const int gs = pv.gstride;
+    for (int c = tid; c < pv.N; c += T) {
+        double wp = pv.aP[c], wn = pv.aN[c];
+        double px = geo[G_PX * gs + c], py = geo[G_PY * gs + c], pz = geo[G_PZ * gs + c];
+        double qx = geo[G_QX * gs + c], qy = geo[G_QY * gs + c], qz = geo[G_QZ * gs + c];
+        double nx = geo[G_NX * gs + c], ny = geo[G_NY * gs + c], nz = geo[G_NZ * gs + c];
+        double mx = geo[G_MX * gs + c], my = geo[G_MY * gs + c], mz = geo[G_MZ * gs + c];
+        acc[0] += wp;
+        double wpx = wp * px, wpy = wp * py, wpz = wp * pz;
+        acc[1] += wpx; acc[2] += wpy; acc[3] += wpz;
+        acc[4] += wp * qx; acc[5] += wp * qy; acc[6] += wp * qz;
+        acc[7] += wpx * qx; acc[8] += wpx * qy; acc[9] += wpx * qz;
+        acc[10] += wpy * qx; acc[11] += wpy * qy; acc[12] += wpy * qz;
+        acc[13] += wpz * qx; acc[14] += wpz * qy; acc[15] += wpz * qz;
+        double wnx = wn * nx, wny = wn * ny, wnz = wn * nz;
+        acc[16] += wnx * mx; acc[17] += wnx * my; acc[18] += wnx * mz;
+        acc[19] += wny * mx; acc[20] += wny * my; acc[21] += wny * mz;
+        acc[22] += wnz * mx; acc[23] += wnz * my; acc[24] += wnz * mz;
+    }
+#pragma unroll
+    for (int k = 0; k < NSUM; ++k) acc[k] = warp_sum(acc[k]);
+    if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < NSUM; ++k) sh.red[red_buf][warp][k] = acc[k];
+    }
+    __syncthreads();
+    if (warp == 0) {
+        if (lane < NSUM) {
+            double s = 0.0;
+#pragma unroll
+            for (int w = 0; w < NWARP; ++w) s += sh.red[red_buf][w][lane];
+            sh.fin[lane] = s;
+        }
+        __syncwarp();
+        if (lane == 0) {
+            const double* f = sh.fin;
+            double W = f[0];
+            double Wm = W / mean_div;
+            double inv = 1.0 / (Wm + EPS);                       // centroids  sum(w p) / (sum(w) + EPS)
+            double sm[3], tm[3];
+#pragma unroll
+            for (int a = 0; a < 3; ++a) { sm[a] = (f[1 + a] / mean_div) * inv; tm[a] = (f[4 + a] / mean_div) * inv; }
+            // M_ab = sum wp (p_a - sm_a)(q_b - tm_b) + sum wn n_a m_b
+            double M[3][3];
+#pragma unroll
+            for (int a = 0; a < 3; ++a)
+#pragma unroll
+                for (int b = 0; b < 3; ++b)
+                    M[a][b] = f[7 + 3 * a + b] - sm[a] * f[4 + b] - f[1 + a] * tm[b] + W * sm[a] * tm[b] + f[16 + 3 * a + b];
+            double Nm[4][4];
+            Nm[0][0] = M[0][0] + M[1][1] + M[2][2];
+            Nm[0][1] = M[1][2] - M[2][1]; Nm[0][2] = M[2][0] - M[0][2]; Nm[0][3] = M[0][1] - M[1][0];
+            Nm[1][1] = M[0][0] - M[1][1] - M[2][2];
+            Nm[1][2] = M[0][1] + M[1][0]; Nm[1][3] = M[0][2] + M[2][0];
+            Nm[2][2] = M[1][1] - M[0][0] - M[2][2];
+            Nm[2][3] = M[1][2] + M[2][1];
+            Nm[3][3] = M[2][2] - M[0][0] - M[1][1];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < i; ++j) Nm[i][j] = Nm[j][i];
+            double q[4];
+            double lam_new = 0.0;
+            if (!horn_eig_fast(Nm, q, sh.scal[0], &lam_new)) { jacobi4_max(Nm, q); lam_new = 0.0; }
+            sh.scal[0] = lam_new;                                // warm start for this pair's next fit
+            double a = q[0], b = q[1], c = q[2], d = q[3];
+            Pose& P = sh.pose;
+            P.R[0] = a * a + b * b - c * c - d * d; P.R[1] = 2 * (b * c - a * d); P.R[2] = 2 * (b * d + a * c);
+            P.R[3] = 2 * (c * b + a * d); P.R[4] = a * a - b * b + c * c - d * d; P.R[5] = 2 * (c * d - a * b);
+            P.R[6] = 2 * (d * b - a * c); P.R[7] = 2 * (d * c + a * b); P.R[8] = a * a - b * b - c * c + d * d;
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+                P.t[r] = -(P.R[3 * r] * sm[0] + P.R[3 * r + 1] * sm[1] + P.R[3 * r + 2] * sm[2]) + tm[r];
+                P.sm[r] = sm[r]; P.tm[r] = tm[r];
+            }
+        }
+    }
+    __syncthreads();
+    red_buf ^= 1;
+}
+
+// Per-correspondence residuals w.r.t. the current pose (rpmodule.py:252-253); optionally reweight (:255).
+// res[c] = mu*||R(p-sm)-(q-tm)||^2 + ||R n - m||^2  (the r of :262-263).
+__device__ void residual_pass(const Shared& sh, const PairView& pv, double mu, bool reweight) {
+    const Pose& P = sh.pose;
+    const double* geo = pv.geo; const int gs = pv.gstride;
+    for (int c = threadIdx.x; c < pv.N; c += T) {
+        double px = geo[G_PX * gs + c] - P.sm[0], py = geo[G_PY * gs + c] - P.sm[1], pz = geo[G_PZ * gs + c] - P.sm[2];
+        double qx = geo[G_QX * gs + c] - P.tm[0], qy = geo[G_QY * gs + c] - P.tm[1], qz = geo[G_QZ * gs + c] - P.tm[2];
+        double dx = P.R[0] * px + P.R[1] * py + P.R[2] * pz - qx;
+        double dy = P.R[3] * px + P.R[4] * py + P.R[5] * pz - qy;
+        double dz = P.R[6] * px + P.R[7] * py + P.R[8] * pz - qz;
+        double rp = mu * (dx * dx + dy * dy + dz * dz);
+        double nx = geo[G_NX * gs + c], ny = geo[G_NY * gs + c], nz = geo[G_NZ * gs + c];
+        double ex = P.R[0] * nx + P.R[1] * ny + P.R[2] * nz - geo[G_MX * gs + c];
+        double ey = P.R[3] * nx + P.R[4] * ny + P.R[5] * nz - geo[G_MY * gs + c];
+        double ez = P.R[6] * nx + P.R[7] * ny + P.R[8] * nz - geo[G_MZ * gs + c];
+        double rn = ex * ex + ey * ey + ez * ez;
+        pv.res[c] = rp + rn;
+        if (reweight) {
+            pv.aP[c] = pv.aP[c] / (1.0 + rp);
+            pv.aN[c] = pv.aN[c] / (1.0 + rn);
+        }
+    }
+    __syncthreads();
+}
+
+__device__ void irls_rounds(Shared& sh, const PairView& pv, double mu, int& red_buf) {
+    for (int it = 0; it < NUM_REWEIGHT; ++it) {
+        horn_fit(sh, pv, 1.0, red_buf);
+        residual_pass(sh, pv, mu, true);
+    }
+}
+
+// Block reduction of NV values, result broadcast to every thread (one __syncthreads, double buffered).
+template <int NV>
+__device__ void block_sum(Shared& sh, double (&v)[NV], int& red_buf) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) v[k] = warp_sum(v[k]);
+    if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < NV; ++k) sh.red[red_buf][warp][k] = v[k];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+        double s = 0.0;
+#pragma unroll
+        for (int w = 0; w < NWARP; ++w) s += sh.red[red_buf][w][k];
+        v[k] = s;
+    }
+    red_buf ^= 1;
+}
+
+// Leading eigenvector of A = S (diag(h) W + W diag(h)) S (S = diag(sv) or identity; h lives in pv.res) by power
+// iteration -- the compact-matrix equivalent of csc_matrix + eigs(k=1) (rpmodule.py:270-276, :131-136).
+// One barrier per step: the iterate is kept un-normalised (y_k = A u_k, u_{k+1} = y_k/||y_k||), and the step's
+// reduction carries both ||y_k||^2 and the residual ||y_k - lambda_{k-1} u_k||^2, i.e. lambda^2 ||u_{k+1}-u_k||^2
+// with a one-step-stale lambda.  On return pv.ua holds the unit eigenvector (non-negative).
+template <bool USE_SV>
+__device__ int power_iteration(Shared& sh, const PairView& pv, double tol, int max_it, bool warm,
+                               int& red_buf, int* converged) {
+    const int tid = threadIdx.x;
+    const int N = pv.N;
+    if (!warm) {
+        double v[1] = {0.0};
+        for (int c = tid; c < N; c += T) { double d = pv.geo[G_DEG * pv.gstride + c]; pv.ua[c] = d; v[0] += d * d; }
+        block_sum<1>(sh, v, red_buf);
+        double inv0 = v[0] > 0.0 ? rsqrt(v[0]) : 0.0;
+        for (int c = tid; c < N; c += T) pv.ua[c] *= inv0;
+    }
+    __syncthreads();
+    double* cur = pv.ua;    // y_{k-1} (or the unit start vector)
+    double* nxt = pv.ub;
+    double inv = 1.0;       // 1/||cur||
+    double lam_prev = 0.0;
+    int it = 0;
+    *converged = 0;
+    double res_prev = CUDART_INF;
+    for (it = 0; it < max_it; ++it) {
+        double v[2] = {0.0, 0.0};
+        for (int p = tid; p < N; p += T) {
+            int b = pv.rowstart[p], e = pv.rowstart[p + 1];
+            double s1 = 0.0, s2 = 0.0;
+            for (int k = b; k < e; ++k) {
+                int c = pv.cols[k]; double w = pv.vals[k];
+                double gc = cur[c];
+                if (USE_SV) gc *= pv.sv[c];
+                s1 += w * gc; s2 += w * (pv.res[c] * gc);
+            }
+            double y = (pv.res[p] * s1 + s2) * inv;      // (A u_k)_p
+            if (USE_SV) y *= pv.sv[p];
+            nxt[p] = y;
+            double r = y - lam_prev * (cur[p] * inv);    // residual against the previous eigenvalue estimate
+            v[0] += y * y; v[1] += r * r;
+        }
+        block_sum<2>(sh, v, red_buf);                    // barrier: nxt complete, cur no longer read
+        double nrm2 = v[0];
+        double* t = cur; cur = nxt; nxt = t;
+        if (!(nrm2 > 0.0)) { inv = 0.0; ++it; break; }
+        double lam = sqrt(nrm2);
+        inv = 1.0 / lam;
+        if (it > 0) {
+            double rel2 = v[1] / nrm2;                   // ~ ||u_{k+1} - u_k||^2
+            if (rel2 <= tol * tol) { ++it; *converged = 1; break; }
+            if (rel2 >= res_prev && rel2 < 1e-26) { ++it; *converged = 1; break; }   // stagnation at rounding level
+            res_prev = rel2;
+        }
+        lam_prev = lam;
+    }
+    // leave the unit vector in pv.ua
+    if (cur == pv.ua) {
+        for (int p = tid; p < N; p += T) pv.ua[p] = cur[p] * inv;
+    } else {
+        for (int p = tid; p < N; p += T) pv.ua[p] = cur[p] * inv;
+    }
+    __syncthreads();
+    return it;
+}
+
+// xdeg_c = u_c (W u)_c : degrees of x = max(0,u_p u_q) w_pq (rpmodule.py:277-285; u >= 0 for a Perron vector).
+__device__ void x_degrees(const PairView& pv, double mu) {
+    for (int p = threadIdx.x; p < pv.N; p += T) {
+        int b = pv.rowstart[p], e = pv.rowstart[p + 1];
+        double s = 0.0;
+        for (int k = b; k < e; ++k) s += pv.vals[k] * pv.ua[pv.cols[k]];
+        double xd = pv.ua[p] * s;
+        pv.aP[p] = mu * xd; pv.aN[p] = xd;
+    }
+    __syncthreads();
+}
+
+// res <- h = max(0, OFFSET - res)   (rpmodule.py:265-266: a = w*(offset - r), clipped at 0)
+__device__ void residual_to_h(const PairView& pv) {
+    for (int c = threadIdx.x; c < pv.N; c += T) pv.res[c] = fmax(0.0, OFFSET - pv.res[c]);
+    __syncthreads();
+}
+
+__device__ __forceinline__ void write_identity(double* T_out) {
+    if (T_out && threadIdx.x < 16) T_out[threadIdx.x] = ((threadIdx.x % 5) == 0) ? 1.0 : 0.0;
+}
+
+__global__ void __launch_bounds__(T, RP_MIN_BLOCKS) rp_solve_kernel(const SolveArgs A) {
+    extern __shared__ __align__(16) unsigned char dyn_smem[];
+    __shared__ Shared sh;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    int* work_counter = reinterpret_cast<int*>(A.ws);
+    char* slot = A.ws + 256 + (size_t)blockIdx.x * A.slot_bytes;
+
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) sh.cnt[4] = atomicAdd(work_counter, 1);
+        __syncthreads();
+        const int b = sh.cnt[4];
+        if (b >= A.B) break;
+
+        const rp_params par = A.params[A.param_idx ? A.param_idx[b] : 0];
+        const int s0 = A.off_s[b], t0 = A.off_t[b];
+        const int ns = A.off_s[b + 1] - s0, nt = A.off_t[b + 1] - t0;
+        double* Tout = A.T_out ? A.T_out + (size_t)b * 16 : nullptr;
+        int* st = A.stats ? A.stats + (size_t)b * RP_STATS_STRIDE : nullptr;
+        if (st && tid < RP_STATS_STRIDE) st[tid] = 0;
+        const int D = A.feat_dim;
+
+        if (ns < 3 || nt < 3) {                                   // rpmodule.py:346-348
+            write_identity(Tout);
+            if (tid == 0) A.status[b] = RP_STATUS_FEW_KEYPOINTS;
+            continue;
+        }
+        int K = par.topk < nt - 1 ? par.topk : nt - 1;           // rpmodule.py:368
+        if (K > KMAX || K > A.max_topk || K < 1 || ns * K > A.Nmax) {
+            write_identity(Tout);
+            if (tid == 0) A.status[b] = RP_STATUS_UNSUPPORTED;
+            continue;
+        }
+        PairView pv;
+        pv.ns = ns; pv.nt = nt; pv.K = K; pv.N = ns * K; pv.NW = (pv.N + 31) >> 5;
+        pv.geo = reinterpret_cast<double*>(slot + A.o_geo); pv.gstride = A.Nmax;
+        pv.cj = reinterpret_cast<int*>(slot + A.o_cj);
+        pv.edges = reinterpret_cast<unsigned*>(slot + A.o_edges);
+        pv.ew = reinterpret_cast<double*>(slot + A.o_ew);
+        pv.rowstart = reinterpret_cast<int*>(slot + A.o_rowstart);
+        pv.cols = reinterpret_cast<uint16_t*>(slot + A.o_cols);
+        pv.vals = reinterpret_cast<double*>(slot + A.o_vals);
+        {
+            double* v = reinterpret_cast<double*>(dyn_smem);
+            pv.aP = v; pv.aN = v + A.Nmax; pv.res = v + 2 * A.Nmax; pv.ua = v + 3 * A.Nmax;
+            pv.ub = v + 4 * A.Nmax; pv.sv = v + 5 * A.Nmax;
+            pv.f32pos = reinterpret_cast<float*>(dyn_smem);
+            pv.mask = A.mask_in_smem ? reinterpret_cast<unsigned*>(dyn_smem + A.sm_mask_off)
+                                     : reinterpret_cast<unsigned*>(slot + A.o_mask);
+        }
+        const int N = pv.N, NW = pv.NW;
+        if (st && tid == 0) { st[0] = N; st[7] = K; }
+
+        // ------------------------------------------------------------------ A. descriptor front end
+        {
+            float* tfeat = reinterpret_cast<float*>(dyn_smem);       // aliases the vectors (not yet live)
+            const int ts = A.tfeat_stride;
+            const float* ft = A.feat_t + (size_t)t0 * D;
+            for (int e = tid; e < nt * D; e += T) {
+                int j = e / D, c = e - j * D;
+                tfeat[j * ts + c] = __fdiv_rn(ft[e], FEAT_SCALING);    // rpmodule.py:343
+            }
+            __syncthreads();
+            for (int i = warp; i < ns; i += NWARP) {
+                const float* fs = A.feat_s + (size_t)(s0 + i) * D;
+                for (int c = lane; c < D; c += 32) sh.sfeat[warp][c] = __fdiv_rn(fs[c], FEAT_SCALING);   // :342
+                __syncwarp();
+                const double wsi = A.w_s[s0 + i];
+                double lk[KMAX]; int li[KMAX];
+#pragma unroll
+                for (int k = 0; k < KMAX; ++k) { lk[k] = -CUDART_INF; li[k] = 0x7fffffff; }
+                double ss = 0.0;
+                for (int j = lane; j < nt; j += 32) {
+                    float dij = numpy_sqdist_f32(sh.sfeat[warp], tfeat + j * ts, D);            // :355
+                    if (A.has_dbg && A.dbg.dij) A.dbg.dij[A.dbg.dij_off[b] + (int64_t)i * nt + j] = dij;
+                    double both = __dmul_rn(wsi, A.w_t[t0 + j]);                                   // :354
+                    double den = (both == 1.0) ? par.feat_den_obs : par.feat_den;                 // :356-357
+                    double key = (double)(-dij) / den;                                            // :358 (argument of exp)
+                    double e = exp(key);
+                    ss += e * e;
+                    if (key > lk[KMAX - 1]) {
+                        double ck = key; int ci = j;
+#pragma unroll
+                        for (int k = 0; k < KMAX; ++k) {
+                            if (ck > lk[k]) { double tk = lk[k]; int ti = li[k]; lk[k] = ck; li[k] = ci; ck = tk; ci = ti; }
+                        }
+                    }
+                }
+                ss = warp_sum(ss);
+                double nm = sqrt(ss);                                                              // :359
+                double mykey = 0.0; int myidx = -1;
+                for (int r = 0; r < K; ++r) {
+                    double bk = lk[0]; int bi = li[0];
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) {
+                        double ok = shfl_xor_d(bk, o); int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                        if (ok > bk || (ok == bk && oi < bi)) { bk = ok; bi = oi; }
+                    }
+                    if (li[0] == bi && bi != 0x7fffffff) {      // this lane owned the winner: pop it
+#pragma unroll
+                        for (int k = 0; k < KMAX - 1; ++k) { lk[k] = lk[k + 1]; li[k] = li[k + 1]; }
+                        lk[KMAX - 1] = -CUDART_INF; li[KMAX - 1] = 0x7fffffff;
+                    }
+                    if (lane == r) { mykey = bk; myidx = bi; }
+                }
+                if (lane < K) {
+                    if (myidx == 0x7fffffff || myidx < 0) myidx = lane < nt ? lane : 0;   // NaN descriptors: arbitrary but valid
+                    double f = (nm == 0.0) ? 0.0 : exp(mykey) / nm;                               // :360-363
+                    if (nm == 0.0 && A.zero_row_topk) {         // all-zero row: numpy's tie order (host supplied)
+                        int z = A.zero_row_topk[(size_t)b * A.max_topk + lane];
+                        if (z >= 0 && z < nt) myidx = z;
+                    }
+                    int c = i * K + lane;
+                    pv.cj[c] = myidx;
+                    pv.geo[G_F * pv.gstride + c] = f;
+                    if (A.has_dbg && A.dbg.topk_idx) A.dbg.topk_idx[(size_t)(s0 + i) * A.max_topk + lane] = myidx;
+                    if (A.has_dbg && A.dbg.topk_f) A.dbg.topk_f[(size_t)(s0 + i) * A.max_topk + lane] = f;
+                } else if (lane < A.max_topk) {
+                    if (A.has_dbg && A.dbg.topk_idx) A.dbg.topk_idx[(size_t)(s0 + i) * A.max_topk + lane] = -1;
+                    if (A.has_dbg && A.dbg.topk_f) A.dbg.topk_f[(size_t)(s0 + i) * A.max_topk + lane] = 0.0;
+                }
+                __syncwarp();
+            }
+            __syncthreads();
+        }
+        if (A.stop_after == RP_STAGE_TOPK) {
+            write_identity(Tout);
+            if (tid == 0) A.status[b] = RP_STATUS_OK;
+            continue;
+        }
+        if (N < 3) {                                                 // rpmodule.py:377-379
+            write_identity(Tout);
+            if (tid == 0) A.status[b] = RP_STATUS_FEW_CORRES;
+            continue;
+        }
+
+        // ------------------------------------------------------------------ B. per-correspondence geometry
+        int red_buf = 0;
+        {
+            const int gs = pv.gstride;
+            float* fp = pv.f32pos;
+            double amax = 0.0;
+            for (int c = tid; c < N; c += T) {
+                int i = c / K, j = pv.cj[c];
+                const double* p = A.pc_s + (size_t)(s0 + i) * 3; const double* q = A.pc_t + (size_t)(t0 + j) * 3;
+                const double* n = A.nrm_s + (size_t)(s0 + i) * 3; const double* m = A.nrm_t + (size_t)(t0 + j) * 3;
+                double p0 = p[0], p1 = p[1], p2 = p[2], q0 = q[0], q1 = q[1], q2 = q[2];
+                pv.geo[G_PX * gs + c] = p0; pv.geo[G_PY * gs + c] = p1; pv.geo[G_PZ * gs + c] = p2;
+                pv.geo[G_QX * gs + c] = q0; pv.geo[G_QY * gs + c] = q1; pv.geo[G_QZ * gs + c] = q2;
+                pv.geo[G_NX * gs + c] = n[0]; pv.geo[G_NY * gs + c] = n[1]; pv.geo[G_NZ * gs + c] = n[2];
+                pv.geo[G_MX * gs + c] = m[0]; pv.geo[G_MY * gs + c] = m[1]; pv.geo[G_MZ * gs + c] = m[2];
+                pv.geo[G_WS * gs + c] = A.w_s[s0 + i]; pv.geo[G_WT * gs + c] = A.w_t[t0 + j];
+                fp[0 * N + c] = (float)p0; fp[1 * N + c] = (float)p1; fp[2 * N + c] = (float)p2;
+                fp[3 * N + c] = (float)q0; fp[4 * N + c] = (float)q1; fp[5 * N + c] = (float)q2;
+                amax = fmax(amax, fmax(fmax(fabs(p0), fabs(p1)), fmax(fabs(p2), fmax(fabs(q0), fmax(fabs(q1), fabs(q2))))));
+            }
+            for (int e = tid; e < N * NW; e += T) pv.mask[e] = 0u;
+            if (tid < 8) sh.cnt[tid] = (tid == 4) ? b : 0;
+            if (tid == 0) sh.scal[0] = 0.0;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) amax = fmax(amax, shfl_xor_d(amax, o));
+            if (lane == 0) sh.red[red_buf][warp][0] = amax;
+            __syncthreads();
+            if (tid == 0) {
+                double m = 0.0;
+                for (int w = 0; w < NWARP; ++w) m = fmax(m, sh.red[red_buf][w][0]);
+                // float32 pre-test margin: coordinates rounded to f32 (rel 2^-24), differences, squares, sqrt --
+                // absolute distance error < ~8 * 2^-24 * max|coord| ~ 5e-7 * max|coord|; 1e-3 floor.  See DESIGN.md.
+                sh.scal[1] = 1.0e-3 + 4.0e-6 * m;
+            }
+            red_buf ^= 1;
+            __syncthreads();
+        }
+
+        // ------------------------------------------------------------------ C. float32 pre-test -> candidates  (:389-404)
+        {
+            const float* fp = pv.f32pos;
+            const float margin = (float)sh.scal[1];
+            const float tau = (float)sqrt(par.dist_thre_sq) + margin;       // |ds - dt| < distThre (+margin)
+            const float sep = (float)par.sep_thre - margin;                 // min(ds,dt) > 1.5*distSepThre^2 (-margin)
+            unsigned* stg = sh.stage[warp];
+            int nst = 0;                                                     // staged entries (warp-uniform)
+            for (int r = warp; r < N - 1; r += NWARP) {
+                float p1x = fp[0 * N + r], p1y = fp[1 * N + r], p1z = fp[2 * N + r];
+                float q1x = fp[3 * N + r], q1y = fp[4 * N + r], q1z = fp[5 * N + r];
+                for (int cw = r >> 5; cw < NW; ++cw) {
+                    int c = (cw << 5) + lane;
+                    bool keep = false;
+                    if (c > r && c < N) {
+                        float ax = p1x - fp[0 * N + c], ay = p1y - fp[1 * N + c], az = p1z - fp[2 * N + c];
+                        float bx = q1x - fp[3 * N + c], by = q1y - fp[4 * N + c], bz = q1z - fp[5 * N + c];
+                        float ds = sqrtf(ax * ax + ay * ay + az * az);
+                        float dt = sqrtf(bx * bx + by * by + bz * bz);
+                        keep = (fabsf(ds - dt) < tau) && (fminf(ds, dt) > sep);
+                    }
+                    unsigned bal = __ballot_sync(0xffffffffu, keep);
+                    if (bal) {
+                        if (keep) stg[nst + __popc(bal & ((1u << lane) - 1u))] = ((unsigned)r << 16) | (unsigned)c;
+                        nst += __popc(bal);
+                        __syncwarp();
+                        if (nst >= 32) {                                     // flush 32 entries, coalesced
+                            int base = 0;
+                            if (lane == 0) base = atomicAdd(&sh.cnt[0], 32);
+                            base = __shfl_sync(0xffffffffu, base, 0);
+                            unsigned v = stg[lane];
+                            if ((long long)base + lane < A.edge_cap) pv.edges[base + lane] = v;
+                            __syncwarp();
+                            unsigned mv = (lane < nst - 32) ? stg[32 + lane] : 0u;
+                            __syncwarp();
+                            if (lane < nst - 32) stg[lane] = mv;
+                            nst -= 32;
+                            __syncwarp();
+                        }
+                    }
+                }
+            }
+            if (nst > 0) {
+                int base = 0;
+                if (lane == 0) base = atomicAdd(&sh.cnt[0], nst);
+                base = __shfl_sync(0xffffffffu, base, 0);
+                if (lane < nst && (long long)base + lane < A.edge_cap) pv.edges[base + lane] = stg[lane];
+            }
+            __syncthreads();
+        }
+        const int MC = sh.cnt[0];
+        if ((long long)MC > A.edge_cap) {
+            write_identity(Tout);
+            if (tid == 0) A.status[b] = RP_STATUS_EDGE_OVERFLOW;
+            continue;
+        }
+
+        // ------------------------------------------------------------------ D. exact tests + pair weight (:399-467)
+        {
+            const int gs = pv.gstride; const double* geo = pv.geo;
+            int m1 = 0, m2 = 0, nz = 0;
+            for (int e = tid; e < MC; e += T) {
+                unsigned rc = pv.edges[e];
+                int r = rc >> 16, c = rc & 0xffffu;
+                double ax = geo[G_PX * gs + r] - geo[G_PX * gs + c], ay = geo[G_PY * gs + r] - geo[G_PY * gs + c], az = geo[G_PZ * gs + r] - geo[G_PZ * gs + c];
+                double bx = geo[G_QX * gs + r] - geo[G_QX * gs + c], by = geo[G_QY * gs + r] - geo[G_QY * gs + c], bz = geo[G_QZ * gs + r] - geo[G_QZ * gs + c];
+                double dis_s = sqrt(dot3_np(ax, ay, az, ax, ay, az));                // :399
+                double dis_t = sqrt(dot3_np(bx, by, bz, bx, by, bz));                // :400
+                double df = dis_s - dis_t;
+                double dd = __dmul_rn(df, df);                                       // :401
+                double w = -1.0;
+                if ((dd < par.dist_thre_sq) && (fmin(dis_s, dis_t) > par.sep_thre)) {   // :404
+                    ++m1;
+                    double e1x = ax / dis_s, e1y = ay / dis_s, e1z = az / dis_s;     // :424-427
+                    double e2x = bx / dis_t, e2y = by / dis_t, e2z = bz / dis_t;
+                    double n1x = geo[G_NX * gs + r], n1y = geo[G_NY * gs + r], n1z = geo[G_NZ * gs + r];
+                    double n2x = geo[G_NX * gs + c], n2y = geo[G_NY * gs + c], n2z = geo[G_NZ * gs + c];
+                    double m1x = geo[G_MX * gs + r], m1y = geo[G_MY * gs + r], m1z = geo[G_MZ * gs + r];
+                    double m2x = geo[G_MX * gs + c], m2y = geo[G_MY * gs + c], m2z = geo[G_MZ * gs + c];
+                    double a1 = acos(clip1(dot3_np(n1x, n1y, n1z, n2x, n2y, n2z))) - acos(clip1(dot3_np(m1x, m1y, m1z, m2x, m2y, m2z)));
+                    double b1 = acos(clip1(dot3_np(n1x, n1y, n1z, e1x, e1y, e1z))) - acos(clip1(dot3_np(m1x, m1y, m1z, e2x, e2y, e2z)));
+                    double g1 = acos(clip1(dot3_np(n2x, n2y, n2z, e1x, e1y, e1z))) - acos(clip1(dot3_np(m2x, m2y, m2z, e2x, e2y, e2z)));
+                    double alpha = __dmul_rn(a1, a1), beta = __dmul_rn(b1, b1), gamma = __dmul_rn(g1, g1);   // :430-432
+                    if ((alpha < par.angle_thre_sq) && (beta < par.angle_thre_sq) && (gamma < par.angle_thre_sq)) {   // :434-436
+                        double ex = ((-dd / par.den_dist - alpha / par.den_a1) - beta / par.den_a2) - gamma / par.den_a2;   // :457-460
+                        w = (geo[G_F * gs + r] * geo[G_F * gs + c]) * exp(ex);
+                        double seen = __dmul_rn(__dmul_rn(__dmul_rn(geo[G_WS * gs + r], geo[G_WS * gs + c]), geo[G_WT * gs + r]), geo[G_WT * gs + c]);   // :462-466
+                        if (seen != 1.0) w *= UNOBS_DAMP;                                                                      // :467
+                        ++m2; if (w != 0.0) ++nz;
+                        atomicOr(&pv.mask[(size_t)r * NW + (c >> 5)], 1u << (c & 31));
+                        atomicOr(&pv.mask[(size_t)c * NW + (r >> 5)], 1u << (r & 31));
+                    }
+                }
+                pv.ew[e] = w;
+            }
+            m1 = __reduce_add_sync(0xffffffffu, m1); m2 = __reduce_add_sync(0xffffffffu, m2); nz = __reduce_add_sync(0xffffffffu, nz);
+            if (lane == 0) { atomicAdd(&sh.cnt[1], m1); atomicAdd(&sh.cnt[2], m2); atomicAdd(&sh.cnt[5], nz); }
+            __syncthreads();
+        }
+        const int M1 = sh.cnt[1], M2 = sh.cnt[2], NZ = sh.cnt[5];
+        if (st && tid == 0) { st[1] = M1; st[2] = M2; st[3] = NZ; }
+        if (A.has_dbg && A.dbg.edge_rc) {
+            // compacted dump of the surviving pairs (test hook; order follows the candidate list)
+            if (tid == 0) {
+                long long o = 0;
+                for (int e = 0; e < MC; ++e) {
+                    if (pv.ew[e] >= 0.0 && o < A.dbg.edge_cap) {
+                        unsigned rc = pv.edges[e];
+                        A.dbg.edge_rc[((size_t)b * A.dbg.edge_cap + o) * 2 + 0] = rc >> 16;
+                        A.dbg.edge_rc[((size_t)b * A.dbg.edge_cap + o) * 2 + 1] = rc & 0xffffu;
+                        if (A.dbg.edge_w) A.dbg.edge_w[(size_t)b * A.dbg.edge_cap + o] = pv.ew[e];
+                        ++o;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+        if (M1 < 3) {                                                // rpmodule.py:406-408
+            write_identity(Tout);
+            if (tid == 0) A.status[b] = RP_STATUS_FEW_DIST;
+            continue;
+        }
+        if (M2 < 3) {                                                // rpmodule.py:440-443
+            write_identity(Tout);
+            if (tid == 0) A.status[b] = RP_STATUS_FEW_ANGLE;
+            continue;
+        }
+        if (NZ < 1) {                                                // rpmodule.py:469-472
+            write_identity(Tout);
+            if (tid == 0) A.status[b] = RP_STATUS_ZERO_WEIGHT;
+            continue;
+        }
+        if (A.stop_after == RP_STAGE_AFFINITY) {
+            write_identity(Tout);
+            if (tid == 0) A.status[b] = RP_STATUS_OK;
+            continue;
+        }
+
+        // ------------------------------------------------------------------ E. CSR of W (both directions)
+        {
+            if (tid == 0) sh.cnt[3] = 0;
+            __syncthreads();
+            for (int base = 0; base < N; base += T) {                 // exclusive scan of the row populations
+                int r = base + tid;
+                int cnt = 0;
+                if (r < N) for (int w = 0; w < NW; ++w) cnt += __popc(pv.mask[(size_t)r * NW + w]);
+                int inc = cnt;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { int v = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += v; }
+                if (lane == 31) sh.warp_tot[warp] = inc;
+                __syncthreads();
+                int woff = 0;
+#pragma unroll
+                for (int w = 0; w < NWARP; ++w) if (w < warp) woff += sh.warp_tot[w];
+                int carry = sh.cnt[3];
+                if (r < N) pv.rowstart[r] = carry + woff + inc - cnt;
+                __syncthreads();
+                if (tid == T - 1) sh.cnt[3] = carry + woff + inc;
+                __syncthreads();
+            }
+            if (tid == 0) pv.rowstart[N] = sh.cnt[3];
+            __syncthreads();
+            for (int e = tid; e < MC; e += T) {
+                double w = pv.ew[e];
+                if (w < 0.0) continue;
+                unsigned rc = pv.edges[e];
+                int r = rc >> 16, c = rc & 0xffffu;
+                int pr = pv.rowstart[r], pc = pv.rowstart[c];
+                const unsigned* mr = pv.mask + (size_t)r * NW; const unsigned* mc = pv.mask + (size_t)c * NW;
+                for (int ww = 0; ww < (c >> 5); ++ww) pr += __popc(mr[ww]);
+                pr += __popc(mr[c >> 5] & ((1u << (c & 31)) - 1u));
+                for (int ww = 0; ww < (r >> 5); ++ww) pc += __popc(mc[ww]);
+                pc += __popc(mc[r >> 5] & ((1u << (r & 31)) - 1u));
+                pv.cols[pr] = (uint16_t)c; pv.vals[pr] = w;
+                pv.cols[pc] = (uint16_t)r; pv.vals[pc] = w;
+            }
+            __syncthreads();
+            for (int p = tid; p < N; p += T) {                        // row degrees of W
+                int bb = pv.rowstart[p], ee = pv.rowstart[p + 1];
+                double s = 0.0;
+                for (int k = bb; k < ee; ++k) s += pv.vals[k];
+                pv.geo[G_DEG * pv.gstride + p] = s;
+            }
+            __syncthreads();
+        }
+
+        // ------------------------------------------------------------------ F. fitters
+        const double mu = par.mu;
+        int tot_it = 0, max_it_seen = 0, not_conv = 0;
+        for (int c = tid; c < N; c += T) {
+            double d = pv.geo[G_DEG * pv.gstride + c];
+            pv.aP[c] = mu * d; pv.aN[c] = d;
+        }
+        __syncthreads();
+        if (par.method == RP_METHOD_HORN87) {                         // rpmodule.py:60-84
+            horn_fit(sh, pv, mu, red_buf);
+        } else if (par.method == RP_METHOD_IRLS) {                    // rpmodule.py:169-210
+            irls_rounds(sh, pv, mu, red_buf);
+        } else if (par.method == RP_METHOD_IRLS_SM) {                 // rpmodule.py:212-315
+            irls_rounds(sh, pv, mu, red_buf);
+            for (int alt = 0; alt < NUM_ALTER; ++alt) {
+                residual_to_h(pv);
+                int conv = 0;
+                int it = power_iteration<false>(sh, pv, par.power_tol, par.max_power_iters, alt > 0, red_buf, &conv);
+                tot_it += it; max_it_seen = it > max_it_seen ? it : max_it_seen; not_conv |= !conv;
+                if (A.has_dbg && A.dbg.u) for (int c = tid; c < N; c += T) A.dbg.u[((size_t)b * NUM_ALTER + alt) * A.dbg.u_stride + c] = pv.ua[c];
+                x_degrees(pv, mu);
+                irls_rounds(sh, pv, mu, red_buf);
+            }
+        } else if (par.method == RP_METHOD_SPECTRAL) {                // rpmodule.py:86-167
+            horn_fit(sh, pv, mu, red_buf);
+            for (int c = tid; c < N; c += T) pv.sv[c] = 1.0;
+            __syncthreads();
+            for (int alt = 0; alt < NUM_ALTER; ++alt) {
+                residual_pass(sh, pv, mu, false);
+                residual_to_h(pv);
+                int conv = 0;
+                int it = power_iteration<true>(sh, pv, par.power_tol, par.max_power_iters, false, red_buf, &conv);
+                tot_it += it; max_it_seen = it > max_it_seen ? it : max_it_seen; not_conv |= !conv;
+                if (A.has_dbg && A.dbg.u) for (int c = tid; c < N; c += T) A.dbg.u[((size_t)b * NUM_ALTER + alt) * A.dbg.u_stride + c] = pv.ua[c];
+                x_degrees(pv, mu);
+                for (int c = tid; c < N; c += T) pv.sv[c] = pv.ua[c];     // next affinity uses allWP = mu*x (:126,148)
+                __syncthreads();
+                horn_fit(sh, pv, 1.0, red_buf);
+            }
+        } else {
+            write_identity(Tout);
+            if (tid == 0) A.status[b] = RP_STATUS_UNSUPPORTED;
+            continue;
+        }
+        if (tid < 16) {
+            int r = tid >> 2, c = tid & 3;
+            double v;
+            if (r < 3) v = (c < 3) ? sh.pose.R[3 * r + c] : sh.pose.t[r];
+            else v = (c == 3) ? 1.0 : 0.0;
+            Tout[tid] = v;
+        }
+        if (tid == 0) {
+            A.status[b] = RP_STATUS_OK;
+            if (st) { st[4] = tot_it; st[5] = max_it_seen; st[6] = not_conv; }
+        }
+    }
+}
+
+// ----------------------------------------------------------------------------------------------
+struct Layout {
+    size_t o_geo, o_cj, o_mask, o_edges, o_ew, o_rowstart, o_cols, o_vals, slot_bytes;
+    int Nmax, NWmax;
+    long long edge_cap;
+};
+
+inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+bool make_layout(int max_ns, int max_topk, long long edge_cap, Layout* L) {
+    long long Nmax = (long long)max_ns * max_topk;
+    if (Nmax < 1 || Nmax > 65535) return false;
+    long long P = Nmax * (Nmax - 1) / 2;
+    if (edge_cap <= 0 || edge_cap > P) edge_cap = P;
+    if (edge_cap < 3) edge_cap = 3;
+    L->Nmax = (int)Nmax; L->NWmax = (int)((Nmax + 31) / 32); L->edge_cap = edge_cap;
+    size_t o = 0;
+    L->o_geo = o; o = align_up(o + sizeof(double) * G_COUNT * Nmax, 256);
+    L->o_cj = o; o = align_up(o + sizeof(int) * Nmax, 256);
+    L->o_mask = o; o = align_up(o + sizeof(unsigned) * Nmax * L->NWmax, 256);
+    L->o_edges = o; o = align_up(o + sizeof(unsigned) * edge_cap, 256);
+    L->o_ew = o; o = align_up(o + sizeof(double) * edge_cap, 256);
+    L->o_rowstart = o; o = align_up(o + sizeof(int) * (Nmax + 1), 256);
+    L->o_cols = o; o = align_up(o + sizeof(uint16_t) * 2 * edge_cap, 256);
+    L->o_vals = o; o = align_up(o + sizeof(double) * 2 * edge_cap, 256);
+    L->slot_bytes = o;
+    return true;
+}
+
+struct SmemPlan { size_t bytes; int mask_in_smem; int tfeat_stride; size_t mask_off; };
+
+bool make_smem_plan(const Layout& L, int max_nt, int feat_dim, SmemPlan* S) {
+    // ~227 KB per SM shared by RP_MIN_BLOCKS CTAs; the static part (struct Shared) is ~3-8 KB
+    const size_t budget = (size_t)(220 * 1024) / RP_MIN_BLOCKS - 9 * 1024;
+    const size_t hard = 200 * 1024;
+    int ts = feat_dim | 1;
+    size_t fe = (size_t)max_nt * ts * sizeof(float);
+    size_t vec = align_up((size_t)6 * L.Nmax * sizeof(double), 16);
+    size_t mask = (size_t)L.Nmax * L.NWmax * sizeof(unsigned);
+    size_t base = fe > vec ? fe : vec;
+    base = align_up(base, 16);
+    int in_smem = (base + mask <= budget) ? 1 : 0;
+    size_t need = base + (in_smem ? mask : 0);
+    if (need > hard) return false;
+    S->bytes = need; S->mask_in_smem = in_smem; S->tfeat_stride = ts; S->mask_off = base;
+    return true;
+}
+
+int default_slots(size_t smem_bytes) {
+    int dev = 0, sms = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return -1;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return -1;
+    int per = 0;
+    cudaFuncSetAttribute(rp_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, rp_solve_kernel, T, smem_bytes) != cudaSuccess) return -1;
+    if (per < 1) per = 1;
+    return sms * per;
+}
+
+}  // namespace
+
+extern "C" {
+
+int rp_abi_version(void) { return RP_ABI_VERSION; }
+
+int64_t rp_launch_count(void) { return g_launches; }
+
+int rp_device_info(int* sm_count, int* cc_major, int* cc_minor, size_t* total_mem) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); return RP_ERR_NO_DEVICE; }
+    cudaDeviceProp p;
+    if (cudaGetDeviceProperties(&p, dev) != cudaSuccess) { cudaGetLastError(); return RP_ERR_NO_DEVICE; }
+    if (sm_count) *sm_count = p.multiProcessorCount;
+    if (cc_major) *cc_major = p.major;
+    if (cc_minor) *cc_minor = p.minor;
+    if (total_mem) *total_mem = p.totalGlobalMem;
+    return RP_OK;
+}
+
+int rp_solve_workspace_bytes(int n_slots, int max_ns, int max_nt, int max_topk, int feat_dim,
+                             int64_t edge_cap, size_t* bytes) {
+    if (!bytes || max_ns < 1 || max_nt < 1 || max_topk < 1) return RP_ERR_INVALID_ARG;
+    if (max_topk > RP_MAX_TOPK || feat_dim < 1 || feat_dim > RP_MAX_FEAT_DIM) return RP_ERR_UNSUPPORTED;
+    Layout L;
+    if (!make_layout(max_ns, max_topk, edge_cap, &L)) return RP_ERR_UNSUPPORTED;
+    SmemPlan S;
+    if (!make_smem_plan(L, max_nt, feat_dim, &S)) return RP_ERR_UNSUPPORTED;
+    if (n_slots <= 0) {
+        n_slots = default_slots(S.bytes);
+        if (n_slots < 0) { cudaGetLastError(); return RP_ERR_NO_DEVICE; }
+    }
+    *bytes = 256 + (size_t)n_slots * L.slot_bytes;
+    return RP_OK;
+}
+
+int rp_solve_batch_ex(int B, const int32_t* off_s, const int32_t* off_t,
+                      const double* pc_s, const double* nrm_s, const float* feat_s, const double* w_s,
+                      const double* pc_t, const double* nrm_t, const float* feat_t, const double* w_t,
+                      int feat_dim, const rp_params* params, const int32_t* param_idx,
+                      const int32_t* zero_row_topk,
+                      int max_ns, int max_nt, int max_topk,
+                      int n_slots, int64_t edge_cap, void* workspace, size_t workspace_bytes,
+                      double* T_out, int32_t* status, int32_t* stats,
+                      int stop_after, const rp_debug* dbg, void* stream_) {
+    if (B < 0 || !off_s || !off_t || !feat_s || !feat_t || !w_s || !w_t || !params || !workspace || !status)
+        return RP_ERR_INVALID_ARG;
+    if (stop_after != RP_STAGE_TOPK && !T_out) return RP_ERR_INVALID_ARG;
+    if (stop_after != RP_STAGE_TOPK && (!pc_s || !pc_t || !nrm_s || !nrm_t)) return RP_ERR_INVALID_ARG;
+    if (stop_after < RP_STAGE_TOPK || stop_after > RP_STAGE_SOLVE) return RP_ERR_INVALID_ARG;
+    if (max_topk > RP_MAX_TOPK || max_topk < 1 || feat_dim < 1 || feat_dim > RP_MAX_FEAT_DIM) return RP_ERR_UNSUPPORTED;
+    if (B == 0) return RP_OK;
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    Layout L;
+    if (!make_layout(max_ns, max_topk, edge_cap, &L)) return RP_ERR_UNSUPPORTED;
+    SmemPlan S;
+    if (!make_smem_plan(L, max_nt, feat_dim, &S)) return RP_ERR_UNSUPPORTED;
+    if (cudaFuncSetAttribute(rp_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S.bytes) != cudaSuccess) {
+        cudaGetLastError();
+        return RP_ERR_CUDA;
+    }
+    if (n_slots <= 0) {
+        n_slots = default_slots(S.bytes);
+        if (n_slots < 0) { cudaGetLastError(); return RP_ERR_NO_DEVICE; }
+    }
+    if (workspace_bytes < 256 + (size_t)n_slots * L.slot_bytes) return RP_ERR_WORKSPACE_TOO_SMALL;
+    SolveArgs a;
+    a.B = B; a.off_s = off_s; a.off_t = off_t;
+    a.pc_s = pc_s; a.nrm_s = nrm_s; a.feat_s = feat_s; a.w_s = w_s;
+    a.pc_t = pc_t; a.nrm_t = nrm_t; a.feat_t = feat_t; a.w_t = w_t;
+    a.feat_dim = feat_dim; a.params = params; a.param_idx = param_idx; a.zero_row_topk = zero_row_topk;
+    a.max_topk = max_topk; a.edge_cap = L.edge_cap;
+    a.ws = static_cast<char*>(workspace); a.slot_bytes = L.slot_bytes;
+    a.o_geo = L.o_geo; a.o_cj = L.o_cj; a.o_mask = L.o_mask; a.o_edges = L.o_edges; a.o_ew = L.o_ew;
+    a.o_rowstart = L.o_rowstart; a.o_cols = L.o_cols; a.o_vals = L.o_vals;
+    a.Nmax = L.Nmax; a.NWmax = L.NWmax;
+    a.T_out = T_out; a.status = status; a.stats = stats;
+    a.stop_after = stop_after;
+    a.has_dbg = dbg ? 1 : 0;
+    if (dbg) a.dbg = *dbg; else { rp_debug z = {}; a.dbg = z; }
+    a.mask_in_smem = S.mask_in_smem; a.tfeat_stride = S.tfeat_stride; a.sm_mask_off = S.mask_off;
+    if (cudaMemsetAsync(workspace, 0, 256, stream) != cudaSuccess) { cudaGetLastError(); return RP_ERR_CUDA; }
+    int grid = B < n_slots ? B : n_slots;
+    rp_solve_kernel<<<grid, T, S.bytes, stream>>>(a);
+    ++g_launches;
+    if (cudaGetLastError() != cudaSuccess) return RP_ERR_CUDA;
+    return RP_OK;
+}
+
+int rp_solve_batch(int B, const int32_t* off_s, const int32_t* off_t,
+                   const double* pc_s, const double* nrm_s, const float* feat_s, const double* w_s,
+                   const double* pc_t, const double* nrm_t, const float* feat_t, const double* w_t,
+                   int feat_dim, const rp_params* params, const int32_t* param_idx,
+                   const int32_t* zero_row_topk,
+                   int max_ns, int max_nt, int max_topk,
+                   int n_slots, int64_t edge_cap, void* workspace, size_t workspace_bytes,
+                   double* T_out, int32_t* status, int32_t* stats, void* stream) {
+    return rp_solve_batch_ex(B, off_s, off_t, pc_s, nrm_s, feat_s, w_s, pc_t, nrm_t, feat_t, w_t, feat_dim, params,
+                             param_idx, zero_row_topk, max_ns, max_nt, max_topk, n_slots, edge_cap, workspace,
+                             workspace_bytes, T_out, status, stats, RP_STAGE_SOLVE, nullptr, stream);
+}
+
+int rp_match_topk(int B, const int32_t* off_s, const int32_t* off_t,
+                  const float* feat_s, const double* w_s, const float* feat_t, const double* w_t,
+                  int feat_dim, const rp_params* params, const int32_t* param_idx,
+                  const int32_t* zero_row_topk,
+                  int max_ns, int max_nt, int max_topk,
+                  int n_slots, void* workspace, size_t workspace_bytes,
+                  int32_t* topk_idx, double* topk_f, int32_t* status, void* stream) {
+    if (!topk_idx || !status) return RP_ERR_INVALID_ARG;
+    rp_debug d = {};
+    d.topk_idx = topk_idx; d.topk_f = topk_f;
+    return rp_solve_batch_ex(B, off_s, off_t, nullptr, nullptr, feat_s, w_s, nullptr, nullptr, feat_t, w_t, feat_dim,
+                             params, param_idx, zero_row_topk, max_ns, max_nt, max_topk, n_slots, 0, workspace,
+                             workspace_bytes, nullptr, status, nullptr, RP_STAGE_TOPK, &d, stream);
+}
+
+}  // extern "C"

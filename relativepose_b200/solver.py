@@ -1,0 +1,264 @@
+"""Host side of the batched relative-pose solver (Python/torch plumbing over the C ABI).
+
+`PoseSolver.solve_records` / `solve_packed` replace loops over the reference's
+``RelativePoseEstimation_helper`` (RPModule/rpmodule.py:317-508); the batch wire
+format is the reference's primitive-cache record
+(trainRelativePoseModuleRecFD.py:207-208).  torch is used only for device
+memory, pinned staging buffers and the CUDA stream.
+"""
+import ctypes
+
+import numpy as np
+
+from . import _lib
+
+FEAT_DIM_DEFAULT = 32
+
+
+def params_from_opts(para, power_tol=1e-13, max_power_iters=4000):
+    """Reduce a reference-style ``opts`` (RPModule/rputil.py:11-22) to the scalars the kernel takes,
+    with the reference's own numpy expressions so thresholds carry identical bit patterns."""
+    method = para.method
+    if method not in _lib.METHODS:
+        raise Exception("unknown method!")                              # rpmodule.py:507-508
+    OBS_W = 1.2                                                         # rpmodule.py:328
+    sig = np.ones([2]) * para.sigmaFeat                                 # rpmodule.py:356
+    sig[1] = para.sigmaFeat / OBS_W                                     # rpmodule.py:357
+    den = 2 * np.power(sig / 5, 2)                                      # rpmodule.py:358
+    p = _lib.RpParams()
+    p.feat_den = float(den[0])
+    p.feat_den_obs = float(den[1])
+    p.dist_thre_sq = float(np.power(para.distThre, 2))                  # rpmodule.py:404
+    p.sep_thre = float(1.5 * np.power(para.distSepThre, 2))             # rpmodule.py:404
+    p.angle_thre_sq = float(np.power(para.angleThre, 2))                # rpmodule.py:434
+    p.den_dist = float(2 * para.sigmaDist ** 2)                         # rpmodule.py:457
+    p.den_a1 = float(2 * para.sigmaAngle1 ** 2)                         # rpmodule.py:458
+    p.den_a2 = float(2 * para.sigmaAngle2 ** 2)                         # rpmodule.py:459-460
+    p.mu = float(para.mu)
+    p.power_tol = float(power_tol)
+    p.topk = int(para.topK)
+    p.method = _lib.METHODS[method]
+    p.max_power_iters = int(max_power_iters)
+    return p
+
+
+_ZERO_ROW_CACHE = {}
+
+
+def zero_row_topk(n_t, K):
+    """Index set numpy's introselect returns for an all-equal row: what the reference's
+    ``np.argpartition(-wij, topK)[:, :topK]`` (rpmodule.py:369) yields for a keypoint whose soft-match row
+    was zeroed (rpmodule.py:359-363).  Depends only on (n_t, K); computed with numpy itself."""
+    key = (int(n_t), int(K))
+    if key not in _ZERO_ROW_CACHE:
+        if K < 1 or n_t < 2:
+            _ZERO_ROW_CACHE[key] = np.zeros([0], dtype=np.int32)
+        else:
+            _ZERO_ROW_CACHE[key] = np.argpartition(-np.zeros([1, n_t]), K, axis=1)[0, :K].astype(np.int32)
+    return _ZERO_ROW_CACHE[key]
+
+
+class PackedBatch(object):
+    """A ragged batch of scan pairs as concatenated host arrays (pinned torch tensors)."""
+
+    FIELDS = ("pc_s", "nrm_s", "feat_s", "w_s", "pc_t", "nrm_t", "feat_t", "w_t")
+
+    def __init__(self, records=None, pin=True):
+        import torch
+        self.B = 0
+        if records is None:
+            return
+        B = len(records)
+        ns = np.array([r["pc_src"].shape[0] for r in records], dtype=np.int64)
+        nt = np.array([r["pc_tgt"].shape[0] for r in records], dtype=np.int64)
+        self.B = B
+        self.off_s = np.zeros(B + 1, dtype=np.int32)
+        self.off_t = np.zeros(B + 1, dtype=np.int32)
+        np.cumsum(ns, out=self.off_s[1:])
+        np.cumsum(nt, out=self.off_t[1:])
+        self.max_ns = int(ns.max()) if B else 0
+        self.max_nt = int(nt.max()) if B else 0
+        D = records[0]["feat_src"].shape[1] if B and records[0]["feat_src"].ndim == 2 else FEAT_DIM_DEFAULT
+        self.feat_dim = int(D)
+
+        def cat(key, dtype, cols):
+            parts = [np.asarray(r[key], dtype=dtype).reshape(-1, cols) if cols else np.asarray(r[key], dtype=dtype).reshape(-1)
+                     for r in records]
+            a = np.ascontiguousarray(np.concatenate(parts, 0)) if parts else np.zeros((0,), dtype)
+            t = torch.from_numpy(a)
+            return t.pin_memory() if (pin and torch.cuda.is_available()) else t
+
+        self.pc_s = cat("pc_src", np.float64, 3)
+        self.nrm_s = cat("normal_src", np.float64, 3)
+        self.feat_s = cat("feat_src", np.float32, D)
+        self.w_s = cat("weight_src", np.float64, 0)
+        self.pc_t = cat("pc_tgt", np.float64, 3)
+        self.nrm_t = cat("normal_tgt", np.float64, 3)
+        self.feat_t = cat("feat_tgt", np.float32, D)
+        self.w_t = cat("weight_tgt", np.float64, 0)
+        self.off_s_t = torch.from_numpy(self.off_s)
+        self.off_t_t = torch.from_numpy(self.off_t)
+        self.nt_list = nt
+        self._zero_rows = {}
+        if pin and torch.cuda.is_available():
+            self.off_s_t = self.off_s_t.pin_memory()
+            self.off_t_t = self.off_t_t.pin_memory()
+
+    def zero_rows(self, topk, stride):
+        """[B, stride] int32 table of numpy tie-order candidate sets (see zero_row_topk)."""
+        import torch
+        key = (int(topk), int(stride))
+        if key not in self._zero_rows:
+            tab = np.full([self.B, stride], -1, dtype=np.int32)
+            for n_t in np.unique(self.nt_list):
+                K = min(int(topk), int(n_t) - 1)
+                if K >= 1:
+                    tab[self.nt_list == n_t, :K] = zero_row_topk(n_t, K)
+            t = torch.from_numpy(tab)
+            self._zero_rows[key] = t.pin_memory() if torch.cuda.is_available() else t
+        return self._zero_rows[key]
+
+    def h2d_bytes(self):
+        n = self.off_s_t.numel() * 4 + self.off_t_t.numel() * 4
+        for f in self.FIELDS:
+            t = getattr(self, f)
+            n += t.numel() * t.element_size()
+        return n
+
+    def to_device(self, device, non_blocking=True):
+        d = DeviceBatch()
+        d.B, d.max_ns, d.max_nt, d.feat_dim = self.B, self.max_ns, self.max_nt, self.feat_dim
+        for f in self.FIELDS + ("off_s_t", "off_t_t"):
+            setattr(d, f, getattr(self, f).to(device, non_blocking=non_blocking))
+        d.host = self
+        d._zero_dev = {}
+        return d
+
+
+class DeviceBatch(object):
+    """Same arrays, resident in HBM."""
+
+    def zero_rows(self, topk, stride, device):
+        key = (int(topk), int(stride))
+        if key not in self._zero_dev:
+            self._zero_dev[key] = self.host.zero_rows(topk, stride).to(device, non_blocking=True)
+        return self._zero_dev[key]
+
+
+class SolveResult(object):
+    def __init__(self, T, status, stats):
+        self.T, self.status, self.stats = T, status, stats
+
+
+class PoseSolver(object):
+    """Owns the device workspace and parameter block for one GPU/stream."""
+
+    def __init__(self, device=None, n_slots=0, edge_frac=1.0):
+        import torch
+        self.torch = torch
+        self.lib = _lib.load()
+        if not torch.cuda.is_available():
+            raise RuntimeError("relativepose_b200 needs a CUDA device (no CPU fallback)")
+        self.device = torch.device(device if device is not None else "cuda:%d" % torch.cuda.current_device())
+        self.n_slots = n_slots
+        self.edge_frac = edge_frac
+        self._ws = None
+        self._ws_key = None
+        self._par_dev = None
+        self._par_key = None
+
+    # ------------------------------------------------------------------ helpers
+    def _params_device(self, plist):
+        key = b"".join(bytes(p) for p in plist)
+        if key != self._par_key:
+            arr = (_lib.RpParams * len(plist))(*plist)
+            host = np.frombuffer(bytes(arr), dtype=np.uint8).copy()
+            self._par_dev = self.torch.from_numpy(host).to(self.device)
+            self._par_key = key
+        return self._par_dev
+
+    def _edge_cap(self, max_ns, topk):
+        N = max_ns * topk
+        P = N * (N - 1) // 2
+        return max(3, int(P * self.edge_frac)) if self.edge_frac < 1.0 else 0
+
+    def _workspace(self, max_ns, max_nt, topk, feat_dim, edge_cap):
+        key = (max_ns, max_nt, topk, feat_dim, edge_cap, self.n_slots)
+        if self._ws_key is not None and self._ws is not None:
+            k = self._ws_key
+            if k[0] >= max_ns and k[1] >= max_nt and k[2] == topk and k[3] == feat_dim and k[4] == edge_cap:
+                return self._ws, k
+        nbytes = ctypes.c_size_t(0)
+        with self.torch.cuda.device(self.device):
+            _lib.check(self.lib.rp_solve_workspace_bytes(self.n_slots, max_ns, max_nt, topk, feat_dim, edge_cap,
+                                                         ctypes.byref(nbytes)), "rp_solve_workspace_bytes")
+        self._ws = self.torch.empty(nbytes.value, dtype=self.torch.uint8, device=self.device)
+        self._ws_key = key
+        return self._ws, key
+
+    # ------------------------------------------------------------------ main entry
+    def solve_device(self, dbatch, plist, param_idx=None, stop_after=_lib.STAGE_SOLVE, debug=None, edge_cap=None):
+        """Launch on a DeviceBatch.  Returns device tensors (T [B,4,4] f64, status [B] i32, stats [B,8] i32)."""
+        torch = self.torch
+        B = dbatch.B
+        T = torch.empty((B, 4, 4), dtype=torch.float64, device=self.device)
+        status = torch.empty((B,), dtype=torch.int32, device=self.device)
+        stats = torch.empty((B, _lib.STATS_STRIDE), dtype=torch.int32, device=self.device)
+        if B == 0:
+            return T, status, stats
+        topk = max(min(int(p.topk), _lib.MAX_TOPK + 1) for p in plist)
+        topk = max(1, min(topk, max(dbatch.max_nt - 1, 1)))
+        if topk > _lib.MAX_TOPK:
+            raise RuntimeError("topK=%d > %d is not supported by the CUDA solver" % (topk, _lib.MAX_TOPK))
+        if edge_cap is None:
+            edge_cap = self._edge_cap(dbatch.max_ns, topk)
+        ws, key = self._workspace(dbatch.max_ns, dbatch.max_nt, topk, dbatch.feat_dim, edge_cap)
+        par = self._params_device(plist)
+        pidx = param_idx.data_ptr() if param_idx is not None else None
+        zrows = dbatch.zero_rows(max(int(p.topk) for p in plist), topk, self.device)
+        dbg = None
+        if debug is not None:
+            dbg = ctypes.byref(debug)
+        with torch.cuda.device(self.device):
+            stream = torch.cuda.current_stream().cuda_stream
+            rc = self.lib.rp_solve_batch_ex(
+                B, dbatch.off_s_t.data_ptr(), dbatch.off_t_t.data_ptr(),
+                dbatch.pc_s.data_ptr(), dbatch.nrm_s.data_ptr(), dbatch.feat_s.data_ptr(), dbatch.w_s.data_ptr(),
+                dbatch.pc_t.data_ptr(), dbatch.nrm_t.data_ptr(), dbatch.feat_t.data_ptr(), dbatch.w_t.data_ptr(),
+                dbatch.feat_dim, par.data_ptr(), pidx, zrows.data_ptr(), key[0], key[1], topk,
+                self.n_slots, edge_cap, ws.data_ptr(), ws.numel(),
+                T.data_ptr(), status.data_ptr(), stats.data_ptr(), stop_after, dbg, stream)
+        _lib.check(rc, "rp_solve_batch_ex")
+        return T, status, stats
+
+    def solve_packed(self, packed, para, return_stats=False):
+        """Host buffers in -> host poses out ([B,4,4] float64): H2D, one fused launch, D2H."""
+        plist = [params_from_opts(para)]
+        d = packed.to_device(self.device)
+        T, status, stats = self.solve_device(d, plist)
+        Th = T.cpu().numpy()
+        sth = status.cpu().numpy()
+        if (sth == _lib.STATUS_EDGE_OVERFLOW).any():        # only with edge_frac < 1: redo with full capacity
+            T, status, stats = self.solve_device(d, plist, edge_cap=0)
+            Th, sth = T.cpu().numpy(), status.cpu().numpy()
+        if (sth == _lib.STATUS_UNSUPPORTED).any():
+            raise RuntimeError("pair outside the CUDA solver's supported range (topK>%d?)" % _lib.MAX_TOPK)
+        if return_stats:
+            return Th, sth, stats.cpu().numpy()
+        return Th
+
+    def solve_records(self, records, para, return_stats=False):
+        return self.solve_packed(PackedBatch(records), para, return_stats=return_stats)
+
+
+_default_solver = {}
+
+
+def default_solver(device=None):
+    import torch
+    if device is None:
+        device = "cuda:%d" % torch.cuda.current_device()
+    key = str(device)
+    if key not in _default_solver:
+        _default_solver[key] = PoseSolver(device)
+    return _default_solver[key]
