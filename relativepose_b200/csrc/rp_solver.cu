@@ -299,6 +299,12 @@ __device__ bool horn_eig_fast(const double N[4][4], double q[4], double lam_hint
     return false;
 }
 
+__device__ __forceinline__ float rsqrt_approx(float x) {
+    float r;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));     // one MUFU.RSQ, ~2 ulp: far inside the pre-test margin
+    return r;
+}
+
 // ----------------------------------------------------------------------------------------------
 struct Pose { double R[9]; double t[3]; double sm[3]; double tm[3]; };
 
@@ -309,6 +315,10 @@ struct Shared {
     double scal[8];      // 0: lambda warm start, 1: prefilter margin
     int cnt[8];          // 0 candidate count, 1 M1, 2 M2, 3 scan carry, 4 pair id, 5 nnz
     int warp_tot[NWARP];
+    int warp_tot2[NWARP];
+    int crow0[T];        // merge-path: compact (non-empty) row index of the first non-zero of thread t's chunk
+    double part[T][4];   // merge-path partial sums: [0..1] leading piece of a row begun in an earlier chunk,
+                         //                          [2..3] trailing piece of a row that continues in later chunks
     unsigned stage[NWARP][STAGE];
     float sfeat[NWARP][RP_MAX_FEAT_DIM];
 };
@@ -322,10 +332,16 @@ struct PairView {
     int* cj;
     unsigned* mask;
     unsigned* edges; double* ew;
-    int* rowstart; uint16_t* cols; double* vals;
+    int* rowstart;       // [N+1] shared memory
+    uint16_t* cols; double* vals;   // lane-interleaved: logical entry k lives at (k % E) * T + k / E
+                         // cols word: column (14 bits) | bit 15 = first entry of its row | bit 14 = last entry
+    int E, nnz, nrows;   // non-zeros per thread chunk, total directed non-zeros, rows with non-zeros
+    unsigned* rowmap;    // [nrows] shared: row id | first chunk << 16 | last chunk << 24
+    double* S;           // [2*nrows] shared: row sums (s1,s2) of rows lying inside one chunk
     // shared-memory vectors
     double *aP, *aN, *res, *ua, *ub, *sv;
-    float* f32pos;       // [6][N] float32 copy of the positions (phase C only; aliases the vectors)
+    float4* sp4;         // [ns] float32 source keypoint positions   (phase C only; aliases the vectors)
+    float4* tq4;         // [N]  float32 target position of each correspondence
 };
 
 // One weighted Horn fit from per-correspondence weights aP (positions, incl. mu) / aN (normals):
@@ -334,10 +350,55 @@ struct PairView {
 // un-scaled pair weights for the centroids, rpmodule.py:72-75,107-110).
 __device__ void horn_fit(Shared& sh, const PairView& pv, double mean_div, int& red_buf) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const double* geo = pv.geo; const int gs = pv.gstride;
+    if (NWARP == 4) {
+        // warp-specialised: each warp owns 6-7 of the 25 sums over ALL correspondences, so the only
+        // cross-lane traffic is one butterfly per owned sum and there is no cross-warp combine.
+        double a0 = 0, a1 = 0, a2 = 0, a3 = 0, a4 = 0, a5 = 0, a6 = 0;
+        if (warp == 0) {
+            for (int c = lane; c < pv.N; c += 32) {
+                double wp = pv.aP[c];
+                a0 += wp;
+                a1 += wp * geo[G_PX * gs + c]; a2 += wp * geo[G_PY * gs + c]; a3 += wp * geo[G_PZ * gs + c];
+                a4 += wp * geo[G_QX * gs + c]; a5 += wp * geo[G_QY * gs + c]; a6 += wp * geo[G_QZ * gs + c];
+            }
+        } else if (warp == 1) {
+            for (int c = lane; c < pv.N; c += 32) {
+                double wp = pv.aP[c];
+                double qx = geo[G_QX * gs + c], qy = geo[G_QY * gs + c], qz = geo[G_QZ * gs + c];
+                double wpx = wp * geo[G_PX * gs + c], wpy = wp * geo[G_PY * gs + c];
+                a0 += wpx * qx; a1 += wpx * qy; a2 += wpx * qz; a3 += wpy * qx; a4 += wpy * qy; a5 += wpy * qz;
+            }
+        } else if (warp == 2) {
+            for (int c = lane; c < pv.N; c += 32) {
+                double wpz = pv.aP[c] * geo[G_PZ * gs + c];
+                double wnx = pv.aN[c] * geo[G_NX * gs + c];
+                double mx = geo[G_MX * gs + c], my = geo[G_MY * gs + c], mz = geo[G_MZ * gs + c];
+                a0 += wpz * geo[G_QX * gs + c]; a1 += wpz * geo[G_QY * gs + c]; a2 += wpz * geo[G_QZ * gs + c];
+                a3 += wnx * mx; a4 += wnx * my; a5 += wnx * mz;
+            }
+        } else {
+            for (int c = lane; c < pv.N; c += 32) {
+                double wn = pv.aN[c];
+                double wny = wn * geo[G_NY * gs + c], wnz = wn * geo[G_NZ * gs + c];
+                double mx = geo[G_MX * gs + c], my = geo[G_MY * gs + c], mz = geo[G_MZ * gs + c];
+                a0 += wny * mx; a1 += wny * my; a2 += wny * mz; a3 += wnz * mx; a4 += wnz * my; a5 += wnz * mz;
+            }
+        }
+        a0 = warp_sum(a0); a1 = warp_sum(a1); a2 = warp_sum(a2); a3 = warp_sum(a3); a4 = warp_sum(a4); a5 = warp_sum(a5);
+        if (warp == 0) a6 = warp_sum(a6);
+        if (lane == 0) {
+            // fin layout: 0 W | 1-3 sum wp p | 4-6 sum wp q | 7-15 sum wp p q^T | 16-24 sum wn n m^T
+            const int base = (warp == 0) ? 0 : (warp == 1) ? 7 : (warp == 2) ? 13 : 19;
+            sh.fin[base + 0] = a0; sh.fin[base + 1] = a1; sh.fin[base + 2] = a2;
+            sh.fin[base + 3] = a3; sh.fin[base + 4] = a4; sh.fin[base + 5] = a5;
+            if (warp == 0) sh.fin[6] = a6;
+        }
+        __syncthreads();
+    } else {
     double acc[NSUM];
 #pragma unroll
     for (int k = 0; k < NSUM; ++k) acc[k] = 0.0;
-    const double* geo = pv.geo; const int gs = pv.gstride;
     for (int c = tid; c < pv.N; c += T) {
         double wp = pv.aP[c], wn = pv.aN[c];
         double px = geo[G_PX * gs + c], py = geo[G_PY * gs + c], pz = geo[G_PZ * gs + c];
@@ -363,14 +424,15 @@ __device__ void horn_fit(Shared& sh, const PairView& pv, double mean_div, int& r
         for (int k = 0; k < NSUM; ++k) sh.red[red_buf][warp][k] = acc[k];
     }
     __syncthreads();
-    if (warp == 0) {
-        if (lane < NSUM) {
-            double s = 0.0;
+    if (warp == 0 && lane < NSUM) {
+        double s = 0.0;
 #pragma unroll
-            for (int w = 0; w < NWARP; ++w) s += sh.red[red_buf][w][lane];
-            sh.fin[lane] = s;
-        }
-        __syncwarp();
+        for (int w = 0; w < NWARP; ++w) s += sh.red[red_buf][w][lane];
+        sh.fin[lane] = s;
+    }
+    __syncthreads();
+    }
+    if (warp == 0) {
         if (lane == 0) {
             const double* f = sh.fin;
             double W = f[0];
@@ -437,8 +499,10 @@ __device__ void residual_pass(const Shared& sh, const PairView& pv, double mu, b
         double rn = ex * ex + ey * ey + ez * ez;
         pv.res[c] = rp + rn;
         if (reweight) {
-            pv.aP[c] = pv.aP[c] / (1.0 + rp);
-            pv.aN[c] = pv.aN[c] / (1.0 + rn);
+            // w/(1+r) as w * (1/(1+r)): the weights reach the denormal range (e^-400-ish products), which would send
+            // every division down the slow path; 1+r is always a normal number >= 1.  (<= 1 ulp from the quotient.)
+            pv.aP[c] = pv.aP[c] * (1.0 / (1.0 + rp));
+            pv.aN[c] = pv.aN[c] * (1.0 / (1.0 + rn));
         }
     }
     __syncthreads();
@@ -472,16 +536,97 @@ __device__ void block_sum(Shared& sh, double (&v)[NV], int& red_buf) {
     red_buf ^= 1;
 }
 
+// Merge-path walk over the CSR of W: every thread owns E consecutive logical non-zeros (perfect balance no
+// matter how skewed the row lengths are -- inlier correspondences have ~10x the degree of outliers).
+// The chunk loop is branch-free (row boundaries are flag bits in the column word: reset / store are selects and
+// predicated stores), so it unrolls and its loads batch.  F::term(c, w, s1, s2) accumulates one non-zero;
+// after a barrier F::fin(row, s1, s2) runs once per non-empty row, one thread per row.  A row split across
+// chunks is summed trailing piece + leading pieces in chunk order, so the summation order is fixed.
+// Rows without non-zeros are never visited.  Contains one __syncthreads.
+template <class F>
+__device__ __forceinline__ void csr_walk(Shared& sh, const PairView& pv, F& f) {
+    const int t = threadIdx.x;
+    const int E = pv.E;
+    int n = pv.nnz - t * E;
+    n = n < 0 ? 0 : (n > E ? E : n);                      // non-zeros in this thread's chunk
+    if (n > 0) {
+        const uint16_t* __restrict__ cp = pv.cols + t;
+        const double* __restrict__ vp = pv.vals + t;
+        double* __restrict__ S = pv.S;
+        double* mypart = sh.part[t];
+        int cr = sh.crow0[t];
+        bool headless = true;                             // current row began in an earlier chunk
+        double s1 = 0.0, s2 = 0.0;
+        unsigned cw = 0;
+#pragma unroll 4
+        for (int i = 0; i < n; ++i) {
+            cw = cp[(size_t)i * T];
+            const double w = vp[(size_t)i * T];
+            const bool st = (cw & 0x8000u) != 0, en = (cw & 0x4000u) != 0;
+            s1 = st ? 0.0 : s1; s2 = st ? 0.0 : s2;
+            cr += (st && i > 0) ? 1 : 0;
+            headless = headless && !st;
+            f.term((int)(cw & 0x3fffu), w, s1, s2);
+            if (en) { double* d = headless ? mypart : (S + 2 * cr); d[0] = s1; d[1] = s2; }
+        }
+        if (!(cw & 0x4000u)) { double* d = headless ? mypart : (mypart + 2); d[0] = s1; d[1] = s2; }
+    }
+    __syncthreads();
+    for (int cr = t; cr < pv.nrows; cr += T) {
+        const unsigned info = pv.rowmap[cr];
+        const int p = info & 0xffffu, t0 = (info >> 16) & 0xffu, t1 = info >> 24;
+        double s1, s2;
+        if (t0 == t1) { s1 = pv.S[2 * cr]; s2 = pv.S[2 * cr + 1]; }
+        else {
+            s1 = sh.part[t0][2]; s2 = sh.part[t0][3];
+            for (int tt = t0 + 1; tt <= t1; ++tt) { s1 += sh.part[tt][0]; s2 += sh.part[tt][1]; }
+        }
+        f.fin(p, s1, s2);
+    }
+}
+
+template <bool USE_SV>
+struct PowerStep {            // y = S (diag(h) W + W diag(h)) S u ; accumulates ||y||^2 and ||y - lam_prev u||^2
+    const double* __restrict__ cur; double* __restrict__ nxt;
+    const double* __restrict__ h; const double* __restrict__ sv;
+    double inv, lam_prev, acc0, acc1;
+    __device__ __forceinline__ void term(int c, double w, double& s1, double& s2) const {
+        double gc = cur[c];
+        if (USE_SV) gc *= sv[c];
+        s1 += w * gc; s2 += w * (h[c] * gc);
+    }
+    __device__ __forceinline__ void fin(int p, double s1, double s2) {
+        double y = (h[p] * s1 + s2) * inv;           // (A u_k)_p
+        if (USE_SV) y *= sv[p];
+        nxt[p] = y;
+        double r = y - lam_prev * (cur[p] * inv);    // residual against the previous eigenvalue estimate
+        acc0 += y * y; acc1 += r * r;
+    }
+};
+
+struct XDegStep {             // xdeg_p = u_p (W u)_p
+    const double* __restrict__ u; double* __restrict__ aP; double* __restrict__ aN; double mu;
+    __device__ __forceinline__ void term(int c, double w, double& s1, double&) const { s1 += w * u[c]; }
+    __device__ __forceinline__ void fin(int p, double s1, double) const { double xd = u[p] * s1; aP[p] = mu * xd; aN[p] = xd; }
+};
+
+struct DegStep {              // row sums of W
+    double* __restrict__ deg;
+    __device__ __forceinline__ void term(int, double w, double& s1, double&) const { s1 += w; }
+    __device__ __forceinline__ void fin(int p, double s1, double) const { deg[p] = s1; }
+};
+
 // Leading eigenvector of A = S (diag(h) W + W diag(h)) S (S = diag(sv) or identity; h lives in pv.res) by power
 // iteration -- the compact-matrix equivalent of csc_matrix + eigs(k=1) (rpmodule.py:270-276, :131-136).
-// One barrier per step: the iterate is kept un-normalised (y_k = A u_k, u_{k+1} = y_k/||y_k||), and the step's
-// reduction carries both ||y_k||^2 and the residual ||y_k - lambda_{k-1} u_k||^2, i.e. lambda^2 ||u_{k+1}-u_k||^2
-// with a one-step-stale lambda.  On return pv.ua holds the unit eigenvector (non-negative).
+// The iterate is kept un-normalised (y_k = A u_k, u_{k+1} = y_k/||y_k||) and the step's single reduction
+// carries both ||y_k||^2 and the residual ||y_k - lambda_{k-1} u_k||^2, i.e. lambda^2 ||u_{k+1}-u_k||^2 with a
+// one-step-stale lambda.  On return pv.ua holds the unit eigenvector (non-negative).
 template <bool USE_SV>
 __device__ int power_iteration(Shared& sh, const PairView& pv, double tol, int max_it, bool warm,
                                int& red_buf, int* converged) {
     const int tid = threadIdx.x;
     const int N = pv.N;
+    for (int c = tid; c < N; c += T) pv.ub[c] = 0.0;     // rows without non-zeros stay 0 in both buffers
     if (!warm) {
         double v[1] = {0.0};
         for (int c = tid; c < N; c += T) { double d = pv.geo[G_DEG * pv.gstride + c]; pv.ua[c] = d; v[0] += d * d; }
@@ -490,63 +635,42 @@ __device__ int power_iteration(Shared& sh, const PairView& pv, double tol, int m
         for (int c = tid; c < N; c += T) pv.ua[c] *= inv0;
     }
     __syncthreads();
-    double* cur = pv.ua;    // y_{k-1} (or the unit start vector)
-    double* nxt = pv.ub;
-    double inv = 1.0;       // 1/||cur||
-    double lam_prev = 0.0;
+    PowerStep<USE_SV> st;
+    st.cur = pv.ua; st.nxt = pv.ub; st.h = pv.res; st.sv = pv.sv;
+    st.inv = 1.0; st.lam_prev = 0.0;
     int it = 0;
     *converged = 0;
     double res_prev = CUDART_INF;
     for (it = 0; it < max_it; ++it) {
-        double v[2] = {0.0, 0.0};
-        for (int p = tid; p < N; p += T) {
-            int b = pv.rowstart[p], e = pv.rowstart[p + 1];
-            double s1 = 0.0, s2 = 0.0;
-            for (int k = b; k < e; ++k) {
-                int c = pv.cols[k]; double w = pv.vals[k];
-                double gc = cur[c];
-                if (USE_SV) gc *= pv.sv[c];
-                s1 += w * gc; s2 += w * (pv.res[c] * gc);
-            }
-            double y = (pv.res[p] * s1 + s2) * inv;      // (A u_k)_p
-            if (USE_SV) y *= pv.sv[p];
-            nxt[p] = y;
-            double r = y - lam_prev * (cur[p] * inv);    // residual against the previous eigenvalue estimate
-            v[0] += y * y; v[1] += r * r;
-        }
+        st.acc0 = 0.0; st.acc1 = 0.0;
+        csr_walk(sh, pv, st);
+        double v[2] = {st.acc0, st.acc1};
         block_sum<2>(sh, v, red_buf);                    // barrier: nxt complete, cur no longer read
         double nrm2 = v[0];
-        double* t = cur; cur = nxt; nxt = t;
-        if (!(nrm2 > 0.0)) { inv = 0.0; ++it; break; }
+        { const double* t = st.cur; st.cur = st.nxt; st.nxt = const_cast<double*>(t); }
+        if (!(nrm2 > 0.0)) { st.inv = 0.0; ++it; break; }
         double lam = sqrt(nrm2);
-        inv = 1.0 / lam;
+        st.inv = 1.0 / lam;
         if (it > 0) {
             double rel2 = v[1] / nrm2;                   // ~ ||u_{k+1} - u_k||^2
             if (rel2 <= tol * tol) { ++it; *converged = 1; break; }
             if (rel2 >= res_prev && rel2 < 1e-26) { ++it; *converged = 1; break; }   // stagnation at rounding level
             res_prev = rel2;
         }
-        lam_prev = lam;
+        st.lam_prev = lam;
     }
-    // leave the unit vector in pv.ua
-    if (cur == pv.ua) {
-        for (int p = tid; p < N; p += T) pv.ua[p] = cur[p] * inv;
-    } else {
-        for (int p = tid; p < N; p += T) pv.ua[p] = cur[p] * inv;
-    }
+    { const double* cur = st.cur; const double inv = st.inv;
+      for (int p = tid; p < N; p += T) pv.ua[p] = cur[p] * inv; }   // leave the unit vector in pv.ua
     __syncthreads();
     return it;
 }
 
 // xdeg_c = u_c (W u)_c : degrees of x = max(0,u_p u_q) w_pq (rpmodule.py:277-285; u >= 0 for a Perron vector).
-__device__ void x_degrees(const PairView& pv, double mu) {
-    for (int p = threadIdx.x; p < pv.N; p += T) {
-        int b = pv.rowstart[p], e = pv.rowstart[p + 1];
-        double s = 0.0;
-        for (int k = b; k < e; ++k) s += pv.vals[k] * pv.ua[pv.cols[k]];
-        double xd = pv.ua[p] * s;
-        pv.aP[p] = mu * xd; pv.aN[p] = xd;
-    }
+__device__ void x_degrees(Shared& sh, const PairView& pv, double mu) {
+    for (int p = threadIdx.x; p < pv.N; p += T)
+        if (pv.rowstart[p] == pv.rowstart[p + 1]) { pv.aP[p] = 0.0; pv.aN[p] = 0.0; }
+    XDegStep st; st.u = pv.ua; st.aP = pv.aP; st.aN = pv.aN; st.mu = mu;
+    csr_walk(sh, pv, st);
     __syncthreads();
 }
 
@@ -554,6 +678,112 @@ __device__ void x_degrees(const PairView& pv, double mu) {
 __device__ void residual_to_h(const PairView& pv) {
     for (int c = threadIdx.x; c < pv.N; c += T) pv.res[c] = fmax(0.0, OFFSET - pv.res[c]);
     __syncthreads();
+}
+
+// Phase C: conservative float32 pre-test of the distance-consistency condition (rpmodule.py:399-404).
+// The source distance depends only on the source keypoint pair (i1,i2) and is shared by the KK*KK
+// correspondence pairs built on it: lanes hold i2 (and the KK target points of its correspondences in
+// registers), i1 is broadcast, and each (k1,k2) costs one 3-d distance.  Each lane records its keeps in a
+// KK*KK-bit mask; one warp scan per (i1, 32 x i2) cell then appends them to the per-warp stage buffer,
+// which is flushed 32 entries at a time into the candidate list.
+template <int KK>
+__device__ void pretest_pairs(Shared& sh, const PairView& pv, float tau, float sep2, long long edge_cap) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int ns = pv.ns;
+    const float4* sp4 = pv.sp4; const float4* tq4 = pv.tq4;
+    unsigned* stg = sh.stage[warp];
+    int nst = 0;                                                     // staged entries (warp-uniform)
+    const int nchunk = (ns + 31) >> 5;
+    // (i2-chunk, i1) cells, i1 <= last i2 of the chunk; cells are dealt round-robin to the warps
+    for (int ch = 0; ch < nchunk; ++ch) {
+        const int i2 = (ch << 5) + lane;
+        const bool v2 = i2 < ns;
+        const int i2c = v2 ? i2 : ns - 1;
+        const float4 p2 = sp4[i2c];
+        float4 q2[KK];
+#pragma unroll
+        for (int k = 0; k < KK; ++k) q2[k] = tq4[i2c * KK + k];
+        const int i1_end = min(ns - 1, (ch << 5) + 31);              // i1 < i2 <= chunk end
+        for (int i1 = warp; i1 < i1_end; i1 += NWARP) {
+            const float4 p1 = sp4[i1];
+            float ax = p1.x - p2.x, ay = p1.y - p2.y, az = p1.z - p2.z;
+            float S = ax * ax + ay * ay + az * az;
+            float ds = S * rsqrt_approx(S + 1e-30f);
+            const bool vs = v2 && (i2 > i1) && (S > sep2);          // min(ds,dt) > sep  =>  ds > sep
+            unsigned long long keepm = 0ull;
+#pragma unroll
+            for (int k1 = 0; k1 < KK; ++k1) {
+                const float4 q1 = tq4[i1 * KK + k1];
+#pragma unroll
+                for (int k2 = 0; k2 < KK; ++k2) {
+                    float bx = q1.x - q2[k2].x, by = q1.y - q2[k2].y, bz = q1.z - q2[k2].z;
+                    float Tq = bx * bx + by * by + bz * bz;
+                    float dt = Tq * rsqrt_approx(Tq + 1e-30f);
+                    bool keep = (fabsf(ds - dt) < tau) && (Tq > sep2);
+                    keepm |= keep ? (1ull << (k1 * KK + k2)) : 0ull;
+                }
+            }
+            if (!vs) keepm = 0ull;
+            const int cntl = __popcll(keepm);
+            if (__any_sync(0xffffffffu, cntl != 0)) {
+                int inc = cntl;                                      // inclusive warp scan of the per-lane counts
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { int v = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += v; }
+                const int total = __shfl_sync(0xffffffffu, inc, 31);
+                int pos = nst + inc - cntl;
+                // stage buffer holds 64: flush first if this cell could overflow it
+                if (nst + total > STAGE) {
+                    // emit what is staged (nst < 32 entries) to keep the buffer bounded
+                    int base = 0;
+                    if (lane == 0) base = atomicAdd(&sh.cnt[0], nst);
+                    base = __shfl_sync(0xffffffffu, base, 0);
+                    if (lane < nst && (long long)base + lane < edge_cap) pv.edges[base + lane] = stg[lane];
+                    __syncwarp();
+                    pos -= nst; nst = 0;
+                }
+                if (total <= STAGE) {
+                    while (keepm) {
+                        int bit = __ffsll((long long)keepm) - 1; keepm &= keepm - 1;
+                        int k1 = bit / KK, k2 = bit - k1 * KK;
+                        stg[pos++] = ((unsigned)(i1 * KK + k1) << 16) | (unsigned)(i2 * KK + k2);
+                    }
+                    nst += total;
+                    __syncwarp();
+                    while (nst >= 32) {                              // flush 32 entries, coalesced
+                        int base = 0;
+                        if (lane == 0) base = atomicAdd(&sh.cnt[0], 32);
+                        base = __shfl_sync(0xffffffffu, base, 0);
+                        unsigned v = stg[lane];
+                        if ((long long)base + lane < edge_cap) pv.edges[base + lane] = v;
+                        __syncwarp();
+                        unsigned mv = (lane < nst - 32) ? stg[32 + lane] : 0u;
+                        __syncwarp();
+                        if (lane < nst - 32) stg[lane] = mv;
+                        nst -= 32;
+                        __syncwarp();
+                    }
+                } else {
+                    // dense cell (more than 64 keeps among 32*KK*KK tests): write straight to the candidate list
+                    int base = 0;
+                    if (lane == 0) base = atomicAdd(&sh.cnt[0], total);
+                    base = __shfl_sync(0xffffffffu, base, 0);
+                    long long o = (long long)base + (pos - nst);
+                    while (keepm) {
+                        int bit = __ffsll((long long)keepm) - 1; keepm &= keepm - 1;
+                        int k1 = bit / KK, k2 = bit - k1 * KK;
+                        if (o < edge_cap) pv.edges[o] = ((unsigned)(i1 * KK + k1) << 16) | (unsigned)(i2 * KK + k2);
+                        ++o;
+                    }
+                }
+            }
+        }
+    }
+    if (nst > 0) {
+        int base = 0;
+        if (lane == 0) base = atomicAdd(&sh.cnt[0], nst);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (lane < nst && (long long)base + lane < edge_cap) pv.edges[base + lane] = stg[lane];
+    }
 }
 
 __device__ __forceinline__ void write_identity(double* T_out) {
@@ -599,14 +829,18 @@ __global__ void __launch_bounds__(T, RP_MIN_BLOCKS) rp_solve_kernel(const SolveA
         pv.cj = reinterpret_cast<int*>(slot + A.o_cj);
         pv.edges = reinterpret_cast<unsigned*>(slot + A.o_edges);
         pv.ew = reinterpret_cast<double*>(slot + A.o_ew);
-        pv.rowstart = reinterpret_cast<int*>(slot + A.o_rowstart);
         pv.cols = reinterpret_cast<uint16_t*>(slot + A.o_cols);
         pv.vals = reinterpret_cast<double*>(slot + A.o_vals);
         {
             double* v = reinterpret_cast<double*>(dyn_smem);
             pv.aP = v; pv.aN = v + A.Nmax; pv.res = v + 2 * A.Nmax; pv.ua = v + 3 * A.Nmax;
             pv.ub = v + 4 * A.Nmax; pv.sv = v + 5 * A.Nmax;
-            pv.f32pos = reinterpret_cast<float*>(dyn_smem);
+            pv.S = v + 6 * A.Nmax;                                   // 2*Nmax doubles
+            pv.rowstart = reinterpret_cast<int*>(v + 8 * A.Nmax);    // Nmax+1 ints
+            pv.rowmap = reinterpret_cast<unsigned*>(pv.rowstart + (A.Nmax + 1));   // Nmax words
+            pv.E = 1; pv.nnz = 0; pv.nrows = 0;
+            pv.sp4 = reinterpret_cast<float4*>(dyn_smem);
+            pv.tq4 = pv.sp4 + ns;
             pv.mask = A.mask_in_smem ? reinterpret_cast<unsigned*>(dyn_smem + A.sm_mask_off)
                                      : reinterpret_cast<unsigned*>(slot + A.o_mask);
         }
@@ -638,8 +872,10 @@ __global__ void __launch_bounds__(T, RP_MIN_BLOCKS) rp_solve_kernel(const SolveA
                     double both = __dmul_rn(wsi, A.w_t[t0 + j]);                                   // :354
                     double den = (both == 1.0) ? par.feat_den_obs : par.feat_den;                 // :356-357
                     double key = (double)(-dij) / den;                                            // :358 (argument of exp)
-                    double e = exp(key);
-                    ss += e * e;
+                    if (key > -372.6) {          // below this exp(key)^2 < 2^-1075 rounds to +0: adding it is a no-op
+                        double e = exp(key);
+                        ss += e * e;
+                    }
                     if (key > lk[KMAX - 1]) {
                         double ck = key; int ci = j;
 #pragma unroll
@@ -700,7 +936,6 @@ __global__ void __launch_bounds__(T, RP_MIN_BLOCKS) rp_solve_kernel(const SolveA
         int red_buf = 0;
         {
             const int gs = pv.gstride;
-            float* fp = pv.f32pos;
             double amax = 0.0;
             for (int c = tid; c < N; c += T) {
                 int i = c / K, j = pv.cj[c];
@@ -712,8 +947,8 @@ __global__ void __launch_bounds__(T, RP_MIN_BLOCKS) rp_solve_kernel(const SolveA
                 pv.geo[G_NX * gs + c] = n[0]; pv.geo[G_NY * gs + c] = n[1]; pv.geo[G_NZ * gs + c] = n[2];
                 pv.geo[G_MX * gs + c] = m[0]; pv.geo[G_MY * gs + c] = m[1]; pv.geo[G_MZ * gs + c] = m[2];
                 pv.geo[G_WS * gs + c] = A.w_s[s0 + i]; pv.geo[G_WT * gs + c] = A.w_t[t0 + j];
-                fp[0 * N + c] = (float)p0; fp[1 * N + c] = (float)p1; fp[2 * N + c] = (float)p2;
-                fp[3 * N + c] = (float)q0; fp[4 * N + c] = (float)q1; fp[5 * N + c] = (float)q2;
+                pv.tq4[c] = make_float4((float)q0, (float)q1, (float)q2, 0.f);
+                if (c - i * K == 0) pv.sp4[i] = make_float4((float)p0, (float)p1, (float)p2, 0.f);
                 amax = fmax(amax, fmax(fmax(fabs(p0), fabs(p1)), fmax(fabs(p2), fmax(fabs(q0), fmax(fabs(q1), fabs(q2))))));
             }
             for (int e = tid; e < N * NW; e += T) pv.mask[e] = 0u;
@@ -736,51 +971,19 @@ __global__ void __launch_bounds__(T, RP_MIN_BLOCKS) rp_solve_kernel(const SolveA
 
         // ------------------------------------------------------------------ C. float32 pre-test -> candidates  (:389-404)
         {
-            const float* fp = pv.f32pos;
             const float margin = (float)sh.scal[1];
             const float tau = (float)sqrt(par.dist_thre_sq) + margin;       // |ds - dt| < distThre (+margin)
-            const float sep = (float)par.sep_thre - margin;                 // min(ds,dt) > 1.5*distSepThre^2 (-margin)
-            unsigned* stg = sh.stage[warp];
-            int nst = 0;                                                     // staged entries (warp-uniform)
-            for (int r = warp; r < N - 1; r += NWARP) {
-                float p1x = fp[0 * N + r], p1y = fp[1 * N + r], p1z = fp[2 * N + r];
-                float q1x = fp[3 * N + r], q1y = fp[4 * N + r], q1z = fp[5 * N + r];
-                for (int cw = r >> 5; cw < NW; ++cw) {
-                    int c = (cw << 5) + lane;
-                    bool keep = false;
-                    if (c > r && c < N) {
-                        float ax = p1x - fp[0 * N + c], ay = p1y - fp[1 * N + c], az = p1z - fp[2 * N + c];
-                        float bx = q1x - fp[3 * N + c], by = q1y - fp[4 * N + c], bz = q1z - fp[5 * N + c];
-                        float ds = sqrtf(ax * ax + ay * ay + az * az);
-                        float dt = sqrtf(bx * bx + by * by + bz * bz);
-                        keep = (fabsf(ds - dt) < tau) && (fminf(ds, dt) > sep);
-                    }
-                    unsigned bal = __ballot_sync(0xffffffffu, keep);
-                    if (bal) {
-                        if (keep) stg[nst + __popc(bal & ((1u << lane) - 1u))] = ((unsigned)r << 16) | (unsigned)c;
-                        nst += __popc(bal);
-                        __syncwarp();
-                        if (nst >= 32) {                                     // flush 32 entries, coalesced
-                            int base = 0;
-                            if (lane == 0) base = atomicAdd(&sh.cnt[0], 32);
-                            base = __shfl_sync(0xffffffffu, base, 0);
-                            unsigned v = stg[lane];
-                            if ((long long)base + lane < A.edge_cap) pv.edges[base + lane] = v;
-                            __syncwarp();
-                            unsigned mv = (lane < nst - 32) ? stg[32 + lane] : 0u;
-                            __syncwarp();
-                            if (lane < nst - 32) stg[lane] = mv;
-                            nst -= 32;
-                            __syncwarp();
-                        }
-                    }
-                }
-            }
-            if (nst > 0) {
-                int base = 0;
-                if (lane == 0) base = atomicAdd(&sh.cnt[0], nst);
-                base = __shfl_sync(0xffffffffu, base, 0);
-                if (lane < nst && (long long)base + lane < A.edge_cap) pv.edges[base + lane] = stg[lane];
+            float sep = (float)par.sep_thre - margin;                       // min(ds,dt) > 1.5*distSepThre^2 (-margin)
+            const float sep2 = sep > 0.f ? sep * sep : -1.f;                // compared against squared distances
+            switch (K) {
+                case 1: pretest_pairs<1>(sh, pv, tau, sep2, A.edge_cap); break;
+                case 2: pretest_pairs<2>(sh, pv, tau, sep2, A.edge_cap); break;
+                case 3: pretest_pairs<3>(sh, pv, tau, sep2, A.edge_cap); break;
+                case 4: pretest_pairs<4>(sh, pv, tau, sep2, A.edge_cap); break;
+                case 5: pretest_pairs<5>(sh, pv, tau, sep2, A.edge_cap); break;
+                case 6: pretest_pairs<6>(sh, pv, tau, sep2, A.edge_cap); break;
+                case 7: pretest_pairs<7>(sh, pv, tau, sep2, A.edge_cap); break;
+                default: pretest_pairs<8>(sh, pv, tau, sep2, A.edge_cap); break;
             }
             __syncthreads();
         }
@@ -807,8 +1010,9 @@ __global__ void __launch_bounds__(T, RP_MIN_BLOCKS) rp_solve_kernel(const SolveA
                 double w = -1.0;
                 if ((dd < par.dist_thre_sq) && (fmin(dis_s, dis_t) > par.sep_thre)) {   // :404
                     ++m1;
-                    double e1x = ax / dis_s, e1y = ay / dis_s, e1z = az / dis_s;     // :424-427
-                    double e2x = bx / dis_t, e2y = by / dis_t, e2z = bz / dis_t;
+                    const double is = 1.0 / dis_s, it = 1.0 / dis_t;                    // :424-427 (a * (1/|a|), <= 1 ulp from a/|a|)
+                    double e1x = ax * is, e1y = ay * is, e1z = az * is;
+                    double e2x = bx * it, e2y = by * it, e2z = bz * it;
                     double n1x = geo[G_NX * gs + r], n1y = geo[G_NY * gs + r], n1z = geo[G_NZ * gs + r];
                     double n2x = geo[G_NX * gs + c], n2y = geo[G_NY * gs + c], n2z = geo[G_NZ * gs + c];
                     double m1x = geo[G_MX * gs + r], m1y = geo[G_MY * gs + r], m1z = geo[G_MZ * gs + r];
@@ -874,49 +1078,69 @@ __global__ void __launch_bounds__(T, RP_MIN_BLOCKS) rp_solve_kernel(const SolveA
 
         // ------------------------------------------------------------------ E. CSR of W (both directions)
         {
-            if (tid == 0) sh.cnt[3] = 0;
+            int* cidx = reinterpret_cast<int*>(pv.S);                 // compact index of every row (temporary)
+            if (tid == 0) { sh.cnt[3] = 0; sh.cnt[6] = 0; }
             __syncthreads();
-            for (int base = 0; base < N; base += T) {                 // exclusive scan of the row populations
+            for (int base = 0; base < N; base += T) {                 // exclusive scans: row populations, non-empty rows
                 int r = base + tid;
                 int cnt = 0;
                 if (r < N) for (int w = 0; w < NW; ++w) cnt += __popc(pv.mask[(size_t)r * NW + w]);
-                int inc = cnt;
+                int ne = cnt > 0 ? 1 : 0;
+                int inc = cnt, inc2 = ne;
 #pragma unroll
-                for (int o = 1; o < 32; o <<= 1) { int v = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += v; }
-                if (lane == 31) sh.warp_tot[warp] = inc;
+                for (int o = 1; o < 32; o <<= 1) {
+                    int v = __shfl_up_sync(0xffffffffu, inc, o), v2 = __shfl_up_sync(0xffffffffu, inc2, o);
+                    if (lane >= o) { inc += v; inc2 += v2; }
+                }
+                if (lane == 31) { sh.warp_tot[warp] = inc; sh.warp_tot2[warp] = inc2; }
                 __syncthreads();
-                int woff = 0;
+                int woff = 0, woff2 = 0;
 #pragma unroll
-                for (int w = 0; w < NWARP; ++w) if (w < warp) woff += sh.warp_tot[w];
-                int carry = sh.cnt[3];
-                if (r < N) pv.rowstart[r] = carry + woff + inc - cnt;
+                for (int w = 0; w < NWARP; ++w) if (w < warp) { woff += sh.warp_tot[w]; woff2 += sh.warp_tot2[w]; }
+                int carry = sh.cnt[3], carry2 = sh.cnt[6];
+                if (r < N) { pv.rowstart[r] = carry + woff + inc - cnt; cidx[r] = carry2 + woff2 + inc2 - ne; }
                 __syncthreads();
-                if (tid == T - 1) sh.cnt[3] = carry + woff + inc;
+                if (tid == T - 1) { sh.cnt[3] = carry + woff + inc; sh.cnt[6] = carry2 + woff2 + inc2; }
                 __syncthreads();
             }
             if (tid == 0) pv.rowstart[N] = sh.cnt[3];
             __syncthreads();
+            pv.nnz = pv.rowstart[N];
+            pv.nrows = sh.cnt[6];
+            pv.E = (pv.nnz + T - 1) / T; if (pv.E < 1) pv.E = 1;
+            const int E = pv.E;
+            {   // compact row of this thread's first logical non-zero (upper_bound - 1 over rowstart)
+                int k0 = tid * E, lo_r = 0, hi_r = N;                 // invariant: rowstart[lo_r] <= k0 < rowstart[hi_r]
+                if (k0 < pv.nnz) {
+                    while (hi_r - lo_r > 1) { int mid = (lo_r + hi_r) >> 1; if (pv.rowstart[mid] <= k0) lo_r = mid; else hi_r = mid; }
+                    sh.crow0[tid] = cidx[lo_r];
+                } else sh.crow0[tid] = 0;
+            }
+            for (int r = tid; r < N; r += T) {
+                int rs = pv.rowstart[r], re = pv.rowstart[r + 1];
+                if (re > rs) pv.rowmap[cidx[r]] = (unsigned)r | ((unsigned)(rs / E) << 16) | ((unsigned)((re - 1) / E) << 24);
+                else pv.geo[G_DEG * pv.gstride + r] = 0.0;
+            }
             for (int e = tid; e < MC; e += T) {
                 double w = pv.ew[e];
                 if (w < 0.0) continue;
                 unsigned rc = pv.edges[e];
                 int r = rc >> 16, c = rc & 0xffffu;
-                int pr = pv.rowstart[r], pc = pv.rowstart[c];
+                const int rs_r = pv.rowstart[r], rs_c = pv.rowstart[c];
+                int pr = rs_r, pc = rs_c;
                 const unsigned* mr = pv.mask + (size_t)r * NW; const unsigned* mc = pv.mask + (size_t)c * NW;
                 for (int ww = 0; ww < (c >> 5); ++ww) pr += __popc(mr[ww]);
                 pr += __popc(mr[c >> 5] & ((1u << (c & 31)) - 1u));
                 for (int ww = 0; ww < (r >> 5); ++ww) pc += __popc(mc[ww]);
                 pc += __popc(mc[r >> 5] & ((1u << (r & 31)) - 1u));
-                pv.cols[pr] = (uint16_t)c; pv.vals[pr] = w;
-                pv.cols[pc] = (uint16_t)r; pv.vals[pc] = w;
+                unsigned fr_flags = (pr == rs_r ? 0x8000u : 0u) | (pr == pv.rowstart[r + 1] - 1 ? 0x4000u : 0u);
+                unsigned fc_flags = (pc == rs_c ? 0x8000u : 0u) | (pc == pv.rowstart[c + 1] - 1 ? 0x4000u : 0u);
+                size_t fr = (size_t)(pr % E) * T + pr / E, fc = (size_t)(pc % E) * T + pc / E;   // lane-interleaved layout
+                pv.cols[fr] = (uint16_t)((unsigned)c | fr_flags); pv.vals[fr] = w;
+                pv.cols[fc] = (uint16_t)((unsigned)r | fc_flags); pv.vals[fc] = w;
             }
             __syncthreads();
-            for (int p = tid; p < N; p += T) {                        // row degrees of W
-                int bb = pv.rowstart[p], ee = pv.rowstart[p + 1];
-                double s = 0.0;
-                for (int k = bb; k < ee; ++k) s += pv.vals[k];
-                pv.geo[G_DEG * pv.gstride + p] = s;
-            }
+            { DegStep dg; dg.deg = pv.geo + (size_t)G_DEG * pv.gstride; csr_walk(sh, pv, dg); }   // row degrees of W
             __syncthreads();
         }
 
@@ -940,7 +1164,7 @@ __global__ void __launch_bounds__(T, RP_MIN_BLOCKS) rp_solve_kernel(const SolveA
                 int it = power_iteration<false>(sh, pv, par.power_tol, par.max_power_iters, alt > 0, red_buf, &conv);
                 tot_it += it; max_it_seen = it > max_it_seen ? it : max_it_seen; not_conv |= !conv;
                 if (A.has_dbg && A.dbg.u) for (int c = tid; c < N; c += T) A.dbg.u[((size_t)b * NUM_ALTER + alt) * A.dbg.u_stride + c] = pv.ua[c];
-                x_degrees(pv, mu);
+                x_degrees(sh, pv, mu);
                 irls_rounds(sh, pv, mu, red_buf);
             }
         } else if (par.method == RP_METHOD_SPECTRAL) {                // rpmodule.py:86-167
@@ -954,7 +1178,7 @@ __global__ void __launch_bounds__(T, RP_MIN_BLOCKS) rp_solve_kernel(const SolveA
                 int it = power_iteration<true>(sh, pv, par.power_tol, par.max_power_iters, false, red_buf, &conv);
                 tot_it += it; max_it_seen = it > max_it_seen ? it : max_it_seen; not_conv |= !conv;
                 if (A.has_dbg && A.dbg.u) for (int c = tid; c < N; c += T) A.dbg.u[((size_t)b * NUM_ALTER + alt) * A.dbg.u_stride + c] = pv.ua[c];
-                x_degrees(pv, mu);
+                x_degrees(sh, pv, mu);
                 for (int c = tid; c < N; c += T) pv.sv[c] = pv.ua[c];     // next affinity uses allWP = mu*x (:126,148)
                 __syncthreads();
                 horn_fit(sh, pv, 1.0, red_buf);
@@ -989,7 +1213,7 @@ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 bool make_layout(int max_ns, int max_topk, long long edge_cap, Layout* L) {
     long long Nmax = (long long)max_ns * max_topk;
-    if (Nmax < 1 || Nmax > 65535) return false;
+    if (Nmax < 1 || Nmax > 16383) return false;     // 14-bit column field in the CSR word
     long long P = Nmax * (Nmax - 1) / 2;
     if (edge_cap <= 0 || edge_cap > P) edge_cap = P;
     if (edge_cap < 3) edge_cap = 3;
@@ -1001,8 +1225,8 @@ bool make_layout(int max_ns, int max_topk, long long edge_cap, Layout* L) {
     L->o_edges = o; o = align_up(o + sizeof(unsigned) * edge_cap, 256);
     L->o_ew = o; o = align_up(o + sizeof(double) * edge_cap, 256);
     L->o_rowstart = o; o = align_up(o + sizeof(int) * (Nmax + 1), 256);
-    L->o_cols = o; o = align_up(o + sizeof(uint16_t) * 2 * edge_cap, 256);
-    L->o_vals = o; o = align_up(o + sizeof(double) * 2 * edge_cap, 256);
+    L->o_cols = o; o = align_up(o + sizeof(uint16_t) * (2 * edge_cap + 2 * T), 256);     // lane-interleaved: up to T-1 pad
+    L->o_vals = o; o = align_up(o + sizeof(double) * (2 * edge_cap + 2 * T), 256);
     L->slot_bytes = o;
     return true;
 }
@@ -1015,7 +1239,7 @@ bool make_smem_plan(const Layout& L, int max_nt, int feat_dim, SmemPlan* S) {
     const size_t hard = 200 * 1024;
     int ts = feat_dim | 1;
     size_t fe = (size_t)max_nt * ts * sizeof(float);
-    size_t vec = align_up((size_t)6 * L.Nmax * sizeof(double), 16);
+    size_t vec = align_up((size_t)8 * L.Nmax * sizeof(double) + (size_t)(2 * L.Nmax + 1) * sizeof(int), 16);   // 6 vectors + S + rowstart + rowmap
     size_t mask = (size_t)L.Nmax * L.NWmax * sizeof(unsigned);
     size_t base = fe > vec ? fe : vec;
     base = align_up(base, 16);

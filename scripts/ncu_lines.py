@@ -24,6 +24,7 @@ def sass_lines(so, kernel_sub):
             continue
         txt = subprocess.run(["nvdisasm", "-gi", "-c", os.path.join(tmp, f)], stdout=subprocess.PIPE, text=True).stdout
         cur_fn, cur = None, None
+        prev_was_file = False
         for line in txt.splitlines():
             m = re.match(r"\s*\.section\s+\.text\.(\S+?),", line)
             if m:
@@ -35,11 +36,19 @@ def sass_lines(so, kernel_sub):
                 chain = [(m.group(1), int(m.group(2)))]
                 for mm in re.finditer(r'inlined at "([^"]+)", line (\d+)', m.group(3)):
                     chain.append((mm.group(1), int(mm.group(2))))
-                cur = chain
+                # consecutive "//## File" lines spell one inline chain, innermost first
+                if prev_was_file and cur:
+                    for fr in chain:
+                        if cur[-1] != fr:
+                            cur.append(fr)
+                else:
+                    cur = chain
+                prev_was_file = True
                 continue
             m = re.match(r"\s*/\*([0-9a-f]{4,})\*/\s+(.*?);", line)
             if m and cur_fn is not None:
-                out[cur_fn][int(m.group(1), 16)] = (cur, m.group(2).strip())
+                out[cur_fn][int(m.group(1), 16)] = (list(cur) if cur else [("?", 0)], m.group(2).strip())
+                prev_was_file = False
     for fn, d in out.items():
         if kernel_sub in fn:
             return d
