@@ -67,7 +67,7 @@ struct SolveArgs {
     long long edge_cap;
     char* ws;               // workspace base; first 256 bytes = header (work counter)
     size_t slot_bytes;
-    size_t o_geo, o_cj, o_mask, o_edges, o_ew, o_rowstart, o_cols, o_vals;
+    size_t o_geo, o_cj, o_mask, o_edges, o_ew, o_rowstart, o_cols, o_vals;     // o_rowstart: uint16 [Nmax][NWmax] word-prefix counts
     int Nmax, NWmax;
     double* T_out; int32_t* status; int32_t* stats;
     int stop_after;
@@ -93,6 +93,30 @@ __device__ __forceinline__ double warp_sum(double v) {
 __device__ __forceinline__ float sq_diff(const float* __restrict__ s, const float* __restrict__ t, int c) {
     float d = __fsub_rn(s[c], t[c]);
     return __fmul_rn(d, d);
+}
+// Same arithmetic, 128-bit shared-memory loads: requires n % 8 == 0, n <= 128 and 16-byte aligned rows.
+__device__ __forceinline__ float numpy_sqdist_f32_v4(const float* __restrict__ s, const float* __restrict__ t, int n) {
+    const float4* s4 = reinterpret_cast<const float4*>(s);
+    const float4* t4 = reinterpret_cast<const float4*>(t);
+    float r[8];
+    {
+        float4 a = s4[0], b = t4[0], c = s4[1], d = t4[1];
+        float e;
+        e = __fsub_rn(a.x, b.x); r[0] = __fmul_rn(e, e); e = __fsub_rn(a.y, b.y); r[1] = __fmul_rn(e, e);
+        e = __fsub_rn(a.z, b.z); r[2] = __fmul_rn(e, e); e = __fsub_rn(a.w, b.w); r[3] = __fmul_rn(e, e);
+        e = __fsub_rn(c.x, d.x); r[4] = __fmul_rn(e, e); e = __fsub_rn(c.y, d.y); r[5] = __fmul_rn(e, e);
+        e = __fsub_rn(c.z, d.z); r[6] = __fmul_rn(e, e); e = __fsub_rn(c.w, d.w); r[7] = __fmul_rn(e, e);
+    }
+    for (int i = 2; i < (n >> 2); i += 2) {
+        float4 a = s4[i], b = t4[i], c = s4[i + 1], d = t4[i + 1];
+        float e;
+        e = __fsub_rn(a.x, b.x); r[0] = __fadd_rn(r[0], __fmul_rn(e, e)); e = __fsub_rn(a.y, b.y); r[1] = __fadd_rn(r[1], __fmul_rn(e, e));
+        e = __fsub_rn(a.z, b.z); r[2] = __fadd_rn(r[2], __fmul_rn(e, e)); e = __fsub_rn(a.w, b.w); r[3] = __fadd_rn(r[3], __fmul_rn(e, e));
+        e = __fsub_rn(c.x, d.x); r[4] = __fadd_rn(r[4], __fmul_rn(e, e)); e = __fsub_rn(c.y, d.y); r[5] = __fadd_rn(r[5], __fmul_rn(e, e));
+        e = __fsub_rn(c.z, d.z); r[6] = __fadd_rn(r[6], __fmul_rn(e, e)); e = __fsub_rn(c.w, d.w); r[7] = __fadd_rn(r[7], __fmul_rn(e, e));
+    }
+    return __fadd_rn(__fadd_rn(__fadd_rn(r[0], r[1]), __fadd_rn(r[2], r[3])),
+                     __fadd_rn(__fadd_rn(r[4], r[5]), __fadd_rn(r[6], r[7])));
 }
 __device__ float numpy_sqdist_f32(const float* __restrict__ s, const float* __restrict__ t, int n) {
     if (n < 8) {
@@ -320,7 +344,7 @@ struct Shared {
     double part[T][4];   // merge-path partial sums: [0..1] leading piece of a row begun in an earlier chunk,
                          //                          [2..3] trailing piece of a row that continues in later chunks
     unsigned stage[NWARP][STAGE];
-    float sfeat[NWARP][RP_MAX_FEAT_DIM];
+    __align__(16) float sfeat[NWARP][RP_MAX_FEAT_DIM];
 };
 
 // Per-correspondence geometry, SoA in the slot's global workspace (stride = Nmax doubles).
@@ -851,6 +875,7 @@ __global__ void __launch_bounds__(T, RP_MIN_BLOCKS) rp_solve_kernel(const SolveA
         {
             float* tfeat = reinterpret_cast<float*>(dyn_smem);       // aliases the vectors (not yet live)
             const int ts = A.tfeat_stride;
+            const bool vec4 = ((D & 7) == 0) && ((ts & 3) == 0);
             const float* ft = A.feat_t + (size_t)t0 * D;
             for (int e = tid; e < nt * D; e += T) {
                 int j = e / D, c = e - j * D;
@@ -867,7 +892,8 @@ __global__ void __launch_bounds__(T, RP_MIN_BLOCKS) rp_solve_kernel(const SolveA
                 for (int k = 0; k < KMAX; ++k) { lk[k] = -CUDART_INF; li[k] = 0x7fffffff; }
                 double ss = 0.0;
                 for (int j = lane; j < nt; j += 32) {
-                    float dij = numpy_sqdist_f32(sh.sfeat[warp], tfeat + j * ts, D);            // :355
+                    float dij = vec4 ? numpy_sqdist_f32_v4(sh.sfeat[warp], tfeat + j * ts, D)
+                                     : numpy_sqdist_f32(sh.sfeat[warp], tfeat + j * ts, D);        // :355
                     if (A.has_dbg && A.dbg.dij) A.dbg.dij[A.dbg.dij_off[b] + (int64_t)i * nt + j] = dij;
                     double both = __dmul_rn(wsi, A.w_t[t0 + j]);                                   // :354
                     double den = (both == 1.0) ? par.feat_den_obs : par.feat_den;                 // :356-357
@@ -1079,12 +1105,16 @@ __global__ void __launch_bounds__(T, RP_MIN_BLOCKS) rp_solve_kernel(const SolveA
         // ------------------------------------------------------------------ E. CSR of W (both directions)
         {
             int* cidx = reinterpret_cast<int*>(pv.S);                 // compact index of every row (temporary)
+            uint16_t* wpre = reinterpret_cast<uint16_t*>(slot + A.o_rowstart);   // popcount of the mask words before word w of row r
             if (tid == 0) { sh.cnt[3] = 0; sh.cnt[6] = 0; }
             __syncthreads();
             for (int base = 0; base < N; base += T) {                 // exclusive scans: row populations, non-empty rows
                 int r = base + tid;
                 int cnt = 0;
-                if (r < N) for (int w = 0; w < NW; ++w) cnt += __popc(pv.mask[(size_t)r * NW + w]);
+                if (r < N) {
+                    uint16_t* wp = wpre + (size_t)r * NW;
+                    for (int w = 0; w < NW; ++w) { wp[w] = (uint16_t)cnt; cnt += __popc(pv.mask[(size_t)r * NW + w]); }
+                }
                 int ne = cnt > 0 ? 1 : 0;
                 int inc = cnt, inc2 = ne;
 #pragma unroll
@@ -1127,12 +1157,8 @@ __global__ void __launch_bounds__(T, RP_MIN_BLOCKS) rp_solve_kernel(const SolveA
                 unsigned rc = pv.edges[e];
                 int r = rc >> 16, c = rc & 0xffffu;
                 const int rs_r = pv.rowstart[r], rs_c = pv.rowstart[c];
-                int pr = rs_r, pc = rs_c;
-                const unsigned* mr = pv.mask + (size_t)r * NW; const unsigned* mc = pv.mask + (size_t)c * NW;
-                for (int ww = 0; ww < (c >> 5); ++ww) pr += __popc(mr[ww]);
-                pr += __popc(mr[c >> 5] & ((1u << (c & 31)) - 1u));
-                for (int ww = 0; ww < (r >> 5); ++ww) pc += __popc(mc[ww]);
-                pc += __popc(mc[r >> 5] & ((1u << (r & 31)) - 1u));
+                const int pr = rs_r + wpre[(size_t)r * NW + (c >> 5)] + __popc(pv.mask[(size_t)r * NW + (c >> 5)] & ((1u << (c & 31)) - 1u));
+                const int pc = rs_c + wpre[(size_t)c * NW + (r >> 5)] + __popc(pv.mask[(size_t)c * NW + (r >> 5)] & ((1u << (r & 31)) - 1u));
                 unsigned fr_flags = (pr == rs_r ? 0x8000u : 0u) | (pr == pv.rowstart[r + 1] - 1 ? 0x4000u : 0u);
                 unsigned fc_flags = (pc == rs_c ? 0x8000u : 0u) | (pc == pv.rowstart[c + 1] - 1 ? 0x4000u : 0u);
                 size_t fr = (size_t)(pr % E) * T + pr / E, fc = (size_t)(pc % E) * T + pc / E;   // lane-interleaved layout
@@ -1224,7 +1250,7 @@ bool make_layout(int max_ns, int max_topk, long long edge_cap, Layout* L) {
     L->o_mask = o; o = align_up(o + sizeof(unsigned) * Nmax * L->NWmax, 256);
     L->o_edges = o; o = align_up(o + sizeof(unsigned) * edge_cap, 256);
     L->o_ew = o; o = align_up(o + sizeof(double) * edge_cap, 256);
-    L->o_rowstart = o; o = align_up(o + sizeof(int) * (Nmax + 1), 256);
+    L->o_rowstart = o; o = align_up(o + sizeof(uint16_t) * Nmax * L->NWmax, 256);
     L->o_cols = o; o = align_up(o + sizeof(uint16_t) * (2 * edge_cap + 2 * T), 256);     // lane-interleaved: up to T-1 pad
     L->o_vals = o; o = align_up(o + sizeof(double) * (2 * edge_cap + 2 * T), 256);
     L->slot_bytes = o;
@@ -1237,7 +1263,7 @@ bool make_smem_plan(const Layout& L, int max_nt, int feat_dim, SmemPlan* S) {
     // ~227 KB per SM shared by RP_MIN_BLOCKS CTAs; the static part (struct Shared) is ~3-8 KB
     const size_t budget = (size_t)(220 * 1024) / RP_MIN_BLOCKS - 9 * 1024;
     const size_t hard = 200 * 1024;
-    int ts = feat_dim | 1;
+    int ts = (feat_dim % 8 == 0) ? (feat_dim + 4) : (feat_dim | 1);   // 16-B aligned rows, (ts/4) odd -> conflict-free LDS.128
     size_t fe = (size_t)max_nt * ts * sizeof(float);
     size_t vec = align_up((size_t)8 * L.Nmax * sizeof(double) + (size_t)(2 * L.Nmax + 1) * sizeof(int), 16);   // 6 vectors + S + rowstart + rowmap
     size_t mask = (size_t)L.Nmax * L.NWmax * sizeof(unsigned);
