@@ -158,8 +158,62 @@ int rp_match_topk(int B, const int32_t* off_s, const int32_t* off_t,
                   int n_slots, void* workspace, size_t workspace_bytes,
                   int32_t* topk_idx, double* topk_f, int32_t* status, void* stream);
 
+
+/* ------------------------------------------------------------------------------------------------------------
+ * SCNet / Resnet18_8s layer ABI (model/mymodel.py).  The reference runs these through torch.nn / cuDNN
+ * (nn.Conv2d, nn.ConvTranspose2d, BatchNorm2d(track_running_stats=False), LeakyReLU(0.1), F.upsample); here one
+ * kernel family does "conv block" = [normalise + LeakyReLU of the producer's raw output while loading] ->
+ * conv / transposed conv -> raw output + per-(pair, channel) partial batch statistics.  Activations are float32
+ * NHWC with an explicit channel pitch/offset, so torch.cat (mymodel.py:266-325) never materialises.
+ * A "group" is one scan pair = 2 consecutive images = one forward call of the reference = one BN batch.
+ */
+typedef struct rp_conv_src {
+    const float* ptr;     /* [2G, Hin, Win, pitch] raw (pre-BN) activations */
+    int32_t pitch;        /* channels per pixel in memory */
+    int32_t ch_off;       /* first channel of this view */
+    int32_t C;            /* channels used */
+    int32_t act;          /* 0: use as is; 1: x*scale+shift then LeakyReLU(0.1) (mymodel.py:19-20,32-33) */
+    const float* scale;   /* [G, sstride] per-(group, channel) BN scale  gamma/sqrt(var+eps)   (act=1) */
+    const float* shift;   /* [G, sstride] per-(group, channel) BN shift  beta - mean*scale */
+    int32_t sstride;
+    int32_t s_off;
+} rp_conv_src;
+
+typedef struct rp_conv_desc {
+    rp_conv_src src[2];   /* channel-concatenated inputs (torch.cat((a,b),1)) */
+    int32_t nsrc;
+    int32_t transposed;   /* 0 nn.Conv2d, 1 nn.ConvTranspose2d */
+    int32_t k, s, p;      /* kernel, stride, padding (square) */
+    int32_t G;            /* scan pairs */
+    int32_t Hin, Win, Hout, Wout;
+    int32_t Cout;
+    const float* W;       /* packed [k*k][Cin_total][Cout]: conv w[co,ci,ky,kx], transposed w[ci,co,ky,kx] */
+    float* out;           /* [2G, Hout, Wout, out_pitch] raw output */
+    int32_t out_pitch, out_ch_off;
+    float* psum;          /* [G, nparts, Cout] partial sums for the batch statistics, or NULL */
+    float* psq;
+    const float* bias;    /* [Cout] or NULL (the 1x1 heads, mymodel.py:188,196,204,220,228) */
+    int32_t tanh_out;     /* mymodel.py:374-375 */
+    int32_t reserved;
+} rp_conv_desc;
+
+/* number of partial-statistics rows per group the layer writes (psum/psq are [G, nparts, Cout]) */
+int rp_conv_nparts(const rp_conv_desc* d, int* nparts);
+int rp_conv_layer(const rp_conv_desc* d, void* stream);
+/* scale/shift [G, sstride] (+s_off) from the partials: batch mean / biased variance over the 2*Hout*Wout
+ * pixels of a pair, eps 1e-5 (nn.BatchNorm2d, mymodel.py:19,32) */
+int rp_bn_finalize(const float* psum, const float* psq, int G, int nparts, int Cout, int count,
+                   const float* gamma, const float* beta, float* scale, float* shift, int sstride, int s_off,
+                   void* stream);
+/* F.upsample(x,[224,224],'bilinear',align_corners=False) (mymodel.py:261) fused with the channel regrouping of
+ * mymodel.py:264-286: in [n,16,H,W] NCHW -> out [n,224,224,20] NHWC = (rgb,mask | normal,mask | depth,mask) x (own, warped) */
+int rp_scnet_resize_in(const float* x, int n, int H, int W, float* out, void* stream);
+/* F.upsample(xout,inShape,'bilinear',align_corners=False) (mymodel.py:379): in [n,224,224,C] NHWC -> out [n,C,H,W] NCHW */
+int rp_scnet_resize_out(const float* in, int n, int C, int H, int W, float* out, void* stream);
+
 /* Kernel launch counter (number of kernels this library launched since load); bench.py reports it. */
 int64_t rp_launch_count(void);
+int64_t rp_conv_launch_count(void);
 
 #ifdef __cplusplus
 }

@@ -39,8 +39,25 @@ class RpDebug(ctypes.Structure):
                 ("u", ctypes.c_void_p), ("u_stride", ctypes.c_int64)]
 
 
+class RpConvSrc(ctypes.Structure):
+    _fields_ = [("ptr", ctypes.c_void_p), ("pitch", ctypes.c_int32), ("ch_off", ctypes.c_int32),
+                ("C", ctypes.c_int32), ("act", ctypes.c_int32), ("scale", ctypes.c_void_p),
+                ("shift", ctypes.c_void_p), ("sstride", ctypes.c_int32), ("s_off", ctypes.c_int32)]
+
+
+class RpConvDesc(ctypes.Structure):
+    _fields_ = [("src", RpConvSrc * 2), ("nsrc", ctypes.c_int32), ("transposed", ctypes.c_int32),
+                ("k", ctypes.c_int32), ("s", ctypes.c_int32), ("p", ctypes.c_int32), ("G", ctypes.c_int32),
+                ("Hin", ctypes.c_int32), ("Win", ctypes.c_int32), ("Hout", ctypes.c_int32), ("Wout", ctypes.c_int32),
+                ("Cout", ctypes.c_int32), ("W", ctypes.c_void_p), ("out", ctypes.c_void_p),
+                ("out_pitch", ctypes.c_int32), ("out_ch_off", ctypes.c_int32), ("psum", ctypes.c_void_p),
+                ("psq", ctypes.c_void_p), ("bias", ctypes.c_void_p), ("tanh_out", ctypes.c_int32),
+                ("reserved", ctypes.c_int32)]
+
+
 EXPORTS = ("rp_abi_version", "rp_device_info", "rp_solve_workspace_bytes", "rp_solve_batch",
-           "rp_solve_batch_ex", "rp_match_topk", "rp_launch_count")
+           "rp_solve_batch_ex", "rp_match_topk", "rp_launch_count",
+           "rp_conv_nparts", "rp_conv_layer", "rp_bn_finalize", "rp_scnet_resize_in", "rp_scnet_resize_out")
 
 _lib = None
 
@@ -75,6 +92,17 @@ def load():
     lib.rp_match_topk.restype = i32
     lib.rp_match_topk.argtypes = [i32, vp, vp, vp, vp, vp, vp, i32, vp, vp, vp, i32, i32, i32, i32, vp,
                                   ctypes.c_size_t, vp, vp, vp, vp]
+    lib.rp_conv_nparts.restype = i32
+    lib.rp_conv_nparts.argtypes = [ctypes.POINTER(RpConvDesc), ctypes.POINTER(ctypes.c_int)]
+    lib.rp_conv_layer.restype = i32
+    lib.rp_conv_layer.argtypes = [ctypes.POINTER(RpConvDesc), vp]
+    lib.rp_bn_finalize.restype = i32
+    lib.rp_bn_finalize.argtypes = [vp, vp, i32, i32, i32, i32, vp, vp, vp, vp, i32, i32, vp]
+    lib.rp_scnet_resize_in.restype = i32
+    lib.rp_scnet_resize_in.argtypes = [vp, i32, i32, i32, vp, vp]
+    lib.rp_scnet_resize_out.restype = i32
+    lib.rp_scnet_resize_out.argtypes = [vp, i32, i32, i32, i32, vp, vp]
+    lib.rp_conv_launch_count.restype = i64
     if lib.rp_abi_version() != 1:
         raise RuntimeError("librp_b200.so ABI mismatch")
     _lib = lib

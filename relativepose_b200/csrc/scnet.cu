@@ -1,0 +1,345 @@
+// scnet.cu -- SCNet / Resnet18_8s layers for sm_100a (model/mymodel.py of the reference).
+//
+// The reference runs nn.Conv2d / nn.ConvTranspose2d + BatchNorm2d(track_running_stats=False) + LeakyReLU(0.1)
+// through cuDNN/ATen, materialising every torch.cat (mymodel.py:15-39, 266-325).  Here a "conv block" is one
+// kernel: while loading its inputs it applies the PRODUCER's batch-norm + LeakyReLU (per scan pair and per
+// channel: the reference's BN batch is the 2 images of one forward call), convolves, writes the raw output and
+// the partial batch statistics of its own output.  Concatenations are two-source K loops over NHWC views with
+// a channel pitch/offset; stride-2 transposed convolutions are decomposed into their 4 sub-pixel classes so no
+// multiply-by-zero work is issued.
+//
+// This file: float32 CUDA-core implicit GEMM (exact-parity path, tolerance 1e-4 max-abs vs the reference
+// module) + resize / BN-finalise kernels.  The tcgen05 core for the large layers lives in scnet_tc.cu (round 2).
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+#include "../../include/rp_b200.h"
+
+namespace {
+
+constexpr int BM = 64, BN_ = 64, BK = 16, CT = 256;
+constexpr int MAXTAP = 16;
+constexpr float LEAKY = 0.1f;
+constexpr double BN_EPS = 1e-5;
+
+struct Tap { int dy, dx, widx; };
+struct ConvClass { int py, px, Ha, Wb, ntap; Tap taps[MAXTAP]; };
+
+struct ConvArgs {
+    rp_conv_src src[2];
+    int nsrc;
+    int G, Hin, Win, Hout, Wout, Cout, Cin_total;
+    int istr, ostr, nclass, tiles_m;
+    ConvClass cls[4];
+    const float* W;
+    float* out; int out_pitch, out_ch_off;
+    float* psum; float* psq;
+    const float* bias; int tanh_out;
+};
+
+// One (group, class, m-tile, n-tile) per CTA.  256 threads: loaders (64 pixels x 4 channel quads / 16 k x 16 n quads),
+// compute 16x16 threads x (4 pixels x 4 channels).
+__global__ void __launch_bounds__(CT) conv_igemm_f32(const ConvArgs A) {
+    __shared__ __align__(16) float As[BK][BM + 4];
+    __shared__ __align__(16) float Bs[BK][BN_ + 4];
+    __shared__ float red_s[16][BN_];
+    __shared__ float red_q[16][BN_];
+    const int tid = threadIdx.x;
+    const int tile_m = blockIdx.x, tile_n = blockIdx.y;
+    const int g = blockIdx.z / A.nclass, ci = blockIdx.z - g * A.nclass;
+    const ConvClass& C = A.cls[ci];
+    const int HW = C.Ha * C.Wb;
+    const int Mc = 2 * HW;
+    const int tx = tid & 15, ty = tid >> 4;
+    const int part_row = (g * A.nclass + ci) * A.tiles_m + tile_m;
+    if (tile_m * BM >= Mc) {             // padded tile of a smaller class: contributes zeros to the statistics
+        if (A.psum && tid < BN_) {
+            int co = tile_n * BN_ + tid;
+            if (co < A.Cout) { A.psum[(size_t)part_row * A.Cout + co] = 0.f; A.psq[(size_t)part_row * A.Cout + co] = 0.f; }
+        }
+        return;
+    }
+    // loader coordinates (A): pixel pm, channel quad q
+    const int pm = tid >> 2, q = tid & 3;
+    const int m_l = tile_m * BM + pm;
+    const bool mval = m_l < Mc;
+    int img_l = 0, a_l = 0, b_l = 0;
+    if (mval) { int im = m_l / HW; int rem = m_l - im * HW; img_l = g * 2 + im; a_l = rem / C.Wb; b_l = rem - a_l * C.Wb; }
+    // loader coordinates (B): k row kb, n quad
+    const int kb = tid >> 4, nq = tid & 15;
+    const int co_l = tile_n * BN_ + nq * 4;
+
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+    for (int t = 0; t < C.ntap; ++t) {
+        const Tap tp = C.taps[t];
+        const int iy = a_l * A.istr + tp.dy, ix = b_l * A.istr + tp.dx;
+        const bool inb = mval && iy >= 0 && iy < A.Hin && ix >= 0 && ix < A.Win;
+        const size_t pix = ((size_t)img_l * A.Hin + iy) * A.Win + ix;
+        int cbase = 0;
+        for (int s = 0; s < A.nsrc; ++s) {
+            const rp_conv_src& S = A.src[s];
+            for (int c0 = 0; c0 < S.C; c0 += BK) {
+                // ---- A tile: 4 channels of one pixel per thread, producer BN + LeakyReLU applied on the fly
+                float v[4] = {0.f, 0.f, 0.f, 0.f};
+                const int ch = c0 + q * 4;
+                if (inb && ch < S.C) {
+                    const float* p = S.ptr + pix * S.pitch + S.ch_off + ch;
+                    const bool full = (ch + 3 < S.C);
+                    if (full && ((((size_t)p) & 15) == 0)) {
+                        float4 x = *reinterpret_cast<const float4*>(p);
+                        v[0] = x.x; v[1] = x.y; v[2] = x.z; v[3] = x.w;
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) if (ch + j < S.C) v[j] = p[j];
+                    }
+                    if (S.act) {
+                        const float* sc = S.scale + (size_t)g * S.sstride + S.s_off + ch;
+                        const float* sh = S.shift + (size_t)g * S.sstride + S.s_off + ch;
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) if (ch + j < S.C) {
+                            float y = fmaf(v[j], sc[j], sh[j]);
+                            v[j] = y > 0.f ? y : LEAKY * y;
+                        }
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) As[q * 4 + j][pm] = v[j];
+                // ---- B tile: packed weights [tap][Cin_total][Cout]
+                {
+                    float w[4] = {0.f, 0.f, 0.f, 0.f};
+                    const int kc = c0 + kb;
+                    if (kc < S.C) {
+                        const float* wp = A.W + ((size_t)tp.widx * A.Cin_total + cbase + kc) * A.Cout + co_l;
+                        if (co_l + 3 < A.Cout && ((((size_t)wp) & 15) == 0)) {
+                            float4 x = *reinterpret_cast<const float4*>(wp);
+                            w[0] = x.x; w[1] = x.y; w[2] = x.z; w[3] = x.w;
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) if (co_l + j < A.Cout) w[j] = wp[j];
+                        }
+                    }
+                    *reinterpret_cast<float4*>(&Bs[kb][nq * 4]) = make_float4(w[0], w[1], w[2], w[3]);
+                }
+                __syncthreads();
+#pragma unroll
+                for (int k = 0; k < BK; ++k) {
+                    const float4 a = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
+                    const float4 b = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+                    acc[0][0] = fmaf(a.x, b.x, acc[0][0]); acc[0][1] = fmaf(a.x, b.y, acc[0][1]); acc[0][2] = fmaf(a.x, b.z, acc[0][2]); acc[0][3] = fmaf(a.x, b.w, acc[0][3]);
+                    acc[1][0] = fmaf(a.y, b.x, acc[1][0]); acc[1][1] = fmaf(a.y, b.y, acc[1][1]); acc[1][2] = fmaf(a.y, b.z, acc[1][2]); acc[1][3] = fmaf(a.y, b.w, acc[1][3]);
+                    acc[2][0] = fmaf(a.z, b.x, acc[2][0]); acc[2][1] = fmaf(a.z, b.y, acc[2][1]); acc[2][2] = fmaf(a.z, b.z, acc[2][2]); acc[2][3] = fmaf(a.z, b.w, acc[2][3]);
+                    acc[3][0] = fmaf(a.w, b.x, acc[3][0]); acc[3][1] = fmaf(a.w, b.y, acc[3][1]); acc[3][2] = fmaf(a.w, b.z, acc[3][2]); acc[3][3] = fmaf(a.w, b.w, acc[3][3]);
+                }
+                __syncthreads();
+            }
+            cbase += S.C;
+        }
+    }
+
+    // ---- epilogue: bias / tanh, store raw output, per-channel partial statistics of this tile
+    float ps[4] = {0.f, 0.f, 0.f, 0.f}, pq[4] = {0.f, 0.f, 0.f, 0.f};
+    const int co0 = tile_n * BN_ + tx * 4;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int m = tile_m * BM + ty * 4 + i;
+        if (m >= Mc) continue;
+        const int im = m / HW; const int rem = m - im * HW; const int a = rem / C.Wb, b = rem - a * C.Wb;
+        const int oy = a * A.ostr + C.py, ox = b * A.ostr + C.px;
+        float* op = A.out + (((size_t)(g * 2 + im) * A.Hout + oy) * A.Wout + ox) * A.out_pitch + A.out_ch_off + co0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if (co0 + j >= A.Cout) continue;
+            float y = acc[i][j];
+            if (A.bias) y += A.bias[co0 + j];
+            if (A.tanh_out) y = tanhf(y);
+            op[j] = y;
+            ps[j] += y; pq[j] += y * y;
+        }
+    }
+    if (A.psum) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { red_s[ty][tx * 4 + j] = ps[j]; red_q[ty][tx * 4 + j] = pq[j]; }
+        __syncthreads();
+        if (tid < BN_) {
+            float s = 0.f, qq = 0.f;
+#pragma unroll
+            for (int r = 0; r < 16; ++r) { s += red_s[r][tid]; qq += red_q[r][tid]; }
+            const int co = tile_n * BN_ + tid;
+            if (co < A.Cout) { A.psum[(size_t)part_row * A.Cout + co] = s; A.psq[(size_t)part_row * A.Cout + co] = qq; }
+        }
+    }
+}
+
+__global__ void bn_finalize_kernel(const float* __restrict__ psum, const float* __restrict__ psq, int nparts, int Cout,
+                                   int count, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                   float* __restrict__ scale, float* __restrict__ shift, int sstride, int s_off) {
+    const int g = blockIdx.y;
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= Cout) return;
+    double s = 0.0, q = 0.0;
+    const float* ps = psum + (size_t)g * nparts * Cout + c;
+    const float* pq = psq + (size_t)g * nparts * Cout + c;
+    for (int r = 0; r < nparts; ++r) { s += (double)ps[(size_t)r * Cout]; q += (double)pq[(size_t)r * Cout]; }
+    const double mean = s / count;
+    double var = q / count - mean * mean;          // biased variance, as nn.BatchNorm2d normalises with
+    if (var < 0.0) var = 0.0;
+    const double sc = (double)gamma[c] / sqrt(var + BN_EPS);
+    scale[(size_t)g * sstride + s_off + c] = (float)sc;
+    shift[(size_t)g * sstride + s_off + c] = (float)((double)beta[c] - mean * sc);
+}
+
+// ATen upsample_bilinear2d, align_corners=False: src = (dst+0.5)*scale-0.5 clamped at 0, scale = in/out in float.
+__device__ __forceinline__ void bilin_coord(int d, float scale, int in_size, int& i0, int& i1, float& l0, float& l1) {
+    float r = scale * ((float)d + 0.5f) - 0.5f;
+    if (r < 0.f) r = 0.f;
+    i0 = (int)r;
+    if (i0 > in_size - 1) i0 = in_size - 1;
+    i1 = i0 + ((i0 < in_size - 1) ? 1 : 0);
+    l1 = r - (float)i0;
+    l0 = 1.f - l1;
+}
+
+__global__ void scnet_resize_in_kernel(const float* __restrict__ x, int n, int H, int W, float* __restrict__ out) {
+    // out [n,224,224,20]; one thread per output pixel
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n * 224 * 224) return;
+    const int ox = idx % 224, oy = (idx / 224) % 224, im = idx / (224 * 224);
+    int y0, y1, x0, x1; float ly0, ly1, lx0, lx1;
+    bilin_coord(oy, (float)H / 224.f, H, y0, y1, ly0, ly1);
+    bilin_coord(ox, (float)W / 224.f, W, x0, x1, lx0, lx1);
+    float v[16];
+#pragma unroll
+    for (int c = 0; c < 16; ++c) {
+        const float* p = x + ((size_t)im * 16 + c) * H * W;
+        float p00 = p[(size_t)y0 * W + x0], p01 = p[(size_t)y0 * W + x1], p10 = p[(size_t)y1 * W + x0], p11 = p[(size_t)y1 * W + x1];
+        v[c] = ly0 * (lx0 * p00 + lx1 * p01) + ly1 * (lx0 * p10 + lx1 * p11);
+    }
+    float* o = out + (size_t)idx * 20;
+    // (rgb,mask) (normal,mask) (depth,mask) for the view, then for the warped other view (mymodel.py:264-286)
+    o[0] = v[0]; o[1] = v[1]; o[2] = v[2]; o[3] = v[7];
+    o[4] = v[3]; o[5] = v[4]; o[6] = v[5]; o[7] = v[7];
+    o[8] = v[6]; o[9] = v[7];
+    o[10] = v[8]; o[11] = v[9]; o[12] = v[10]; o[13] = v[15];
+    o[14] = v[11]; o[15] = v[12]; o[16] = v[13]; o[17] = v[15];
+    o[18] = v[14]; o[19] = v[15];
+}
+
+__global__ void scnet_resize_out_kernel(const float* __restrict__ in, int n, int C, int H, int W, float* __restrict__ out) {
+    // in [n,224,224,C] NHWC -> out [n,C,H,W]; one thread per (pixel, 4 channels... ) keep simple: per (n,c,y,x)
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t total = (size_t)n * C * H * W;
+    if (idx >= total) return;
+    const int ox = (int)(idx % W); const int oy = (int)((idx / W) % H); const int c = (int)((idx / ((size_t)W * H)) % C);
+    const int im = (int)(idx / ((size_t)W * H * C));
+    int y0, y1, x0, x1; float ly0, ly1, lx0, lx1;
+    bilin_coord(oy, 224.f / (float)H, 224, y0, y1, ly0, ly1);
+    bilin_coord(ox, 224.f / (float)W, 224, x0, x1, lx0, lx1);
+    const float* p = in + (size_t)im * 224 * 224 * C + c;
+    float p00 = p[((size_t)y0 * 224 + x0) * C], p01 = p[((size_t)y0 * 224 + x1) * C];
+    float p10 = p[((size_t)y1 * 224 + x0) * C], p11 = p[((size_t)y1 * 224 + x1) * C];
+    out[idx] = ly0 * (lx0 * p00 + lx1 * p01) + ly1 * (lx0 * p10 + lx1 * p11);
+}
+
+bool build_args(const rp_conv_desc* d, ConvArgs* A) {
+    if (!d || d->nsrc < 1 || d->nsrc > 2 || d->k < 1 || d->k > 4 || d->s < 1 || d->s > 2 || d->G < 1) return false;
+    A->nsrc = d->nsrc;
+    A->Cin_total = 0;
+    for (int i = 0; i < d->nsrc; ++i) { A->src[i] = d->src[i]; A->Cin_total += d->src[i].C; }
+    A->G = d->G; A->Hin = d->Hin; A->Win = d->Win; A->Hout = d->Hout; A->Wout = d->Wout; A->Cout = d->Cout;
+    A->W = d->W; A->out = d->out; A->out_pitch = d->out_pitch; A->out_ch_off = d->out_ch_off;
+    A->psum = d->psum; A->psq = d->psq; A->bias = d->bias; A->tanh_out = d->tanh_out;
+    const int k = d->k, s = d->s, p = d->p;
+    if (!d->transposed) {
+        // iy = oy*s - p + ky
+        A->istr = s; A->ostr = 1; A->nclass = 1;
+        ConvClass& c = A->cls[0];
+        c.py = 0; c.px = 0; c.Ha = d->Hout; c.Wb = d->Wout; c.ntap = 0;
+        for (int ky = 0; ky < k; ++ky) for (int kx = 0; kx < k; ++kx) { c.taps[c.ntap].dy = ky - p; c.taps[c.ntap].dx = kx - p; c.taps[c.ntap].widx = ky * k + kx; ++c.ntap; }
+    } else {
+        // oy = iy*s - p + ky  ->  for output parity class py: ky with (py + p - ky) % s == 0, iy = a + (py + p - ky)/s
+        A->istr = 1; A->ostr = s; A->nclass = s * s;
+        for (int py = 0; py < s; ++py) for (int px = 0; px < s; ++px) {
+            ConvClass& c = A->cls[py * s + px];
+            c.py = py; c.px = px; c.ntap = 0;
+            c.Ha = (d->Hout - py + s - 1) / s; c.Wb = (d->Wout - px + s - 1) / s;
+            if (c.Ha < 0) c.Ha = 0; if (c.Wb < 0) c.Wb = 0;
+            for (int ky = 0; ky < k; ++ky) {
+                if (((py + p - ky) % s + s) % s != 0) continue;
+                for (int kx = 0; kx < k; ++kx) {
+                    if (((px + p - kx) % s + s) % s != 0) continue;
+                    int dy = (py + p - ky) / s, dx = (px + p - kx) / s;     // exact (divisible); may be negative
+                    if ((py + p - ky) < 0) dy = -((ky - py - p) / s);
+                    if ((px + p - kx) < 0) dx = -((kx - px - p) / s);
+                    c.taps[c.ntap].dy = dy; c.taps[c.ntap].dx = dx; c.taps[c.ntap].widx = ky * k + kx; ++c.ntap;
+                }
+            }
+        }
+    }
+    int tm = 1;
+    for (int i = 0; i < A->nclass; ++i) { int t = (2 * A->cls[i].Ha * A->cls[i].Wb + BM - 1) / BM; if (t > tm) tm = t; }
+    A->tiles_m = tm;
+    return true;
+}
+
+long long g_conv_launches = 0;
+
+}  // namespace
+
+extern "C" {
+
+int rp_conv_nparts(const rp_conv_desc* d, int* nparts) {
+    ConvArgs A;
+    if (!nparts || !build_args(d, &A)) return RP_ERR_INVALID_ARG;
+    *nparts = A.nclass * A.tiles_m;
+    return RP_OK;
+}
+
+int rp_conv_layer(const rp_conv_desc* d, void* stream_) {
+    ConvArgs A;
+    if (!build_args(d, &A)) return RP_ERR_INVALID_ARG;
+    if (!d->W || !d->out || !d->src[0].ptr) return RP_ERR_INVALID_ARG;
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    dim3 grid(A.tiles_m, (A.Cout + BN_ - 1) / BN_, A.G * A.nclass);
+    conv_igemm_f32<<<grid, CT, 0, stream>>>(A);
+    ++g_conv_launches;
+    return cudaGetLastError() == cudaSuccess ? RP_OK : RP_ERR_CUDA;
+}
+
+int rp_bn_finalize(const float* psum, const float* psq, int G, int nparts, int Cout, int count,
+                   const float* gamma, const float* beta, float* scale, float* shift, int sstride, int s_off,
+                   void* stream_) {
+    if (!psum || !psq || !gamma || !beta || !scale || !shift || G < 1 || nparts < 1 || Cout < 1) return RP_ERR_INVALID_ARG;
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    dim3 grid((Cout + 127) / 128, G);
+    bn_finalize_kernel<<<grid, 128, 0, stream>>>(psum, psq, nparts, Cout, count, gamma, beta, scale, shift, sstride, s_off);
+    ++g_conv_launches;
+    return cudaGetLastError() == cudaSuccess ? RP_OK : RP_ERR_CUDA;
+}
+
+int rp_scnet_resize_in(const float* x, int n, int H, int W, float* out, void* stream_) {
+    if (!x || !out || n < 1) return RP_ERR_INVALID_ARG;
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    int total = n * 224 * 224;
+    scnet_resize_in_kernel<<<(total + 255) / 256, 256, 0, stream>>>(x, n, H, W, out);
+    ++g_conv_launches;
+    return cudaGetLastError() == cudaSuccess ? RP_OK : RP_ERR_CUDA;
+}
+
+int rp_scnet_resize_out(const float* in, int n, int C, int H, int W, float* out, void* stream_) {
+    if (!in || !out || n < 1) return RP_ERR_INVALID_ARG;
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    size_t total = (size_t)n * C * H * W;
+    scnet_resize_out_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(in, n, C, H, W, out);
+    ++g_conv_launches;
+    return cudaGetLastError() == cudaSuccess ? RP_OK : RP_ERR_CUDA;
+}
+
+int64_t rp_conv_launch_count(void) { return g_conv_launches; }
+
+}  // extern "C"

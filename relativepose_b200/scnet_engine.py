@@ -1,0 +1,222 @@
+"""Host-side sequencing of the SCNet forward (model/mymodel.py:259-380) over the C-ABI layer kernels.
+
+torch is plumbing here: parameter storage, device buffers, the CUDA stream.  Every arithmetic op of the forward
+runs in relativepose_b200/csrc/scnet.cu.  Activations are float32 NHWC "raw" conv outputs; each carries per-(pair,
+channel) BN scale/shift that the consumer applies while loading (so BatchNorm + LeakyReLU + torch.cat never make
+a pass over memory of their own).
+"""
+import ctypes
+
+from . import _lib
+
+NGF = 64
+
+
+class _Act(object):
+    """A raw NHWC activation view: buffer [2P,H,W,pitch], channel window, BN scale/shift [P,pitch]."""
+
+    def __init__(self, buf, H, W, pitch, ch_off, C, scale=None, shift=None):
+        self.buf, self.H, self.W, self.pitch, self.ch_off, self.C = buf, H, W, pitch, ch_off, C
+        self.scale, self.shift = scale, shift
+
+    def view(self, ch_off, C):
+        return _Act(self.buf, self.H, self.W, self.pitch, self.ch_off + ch_off, C, self.scale, self.shift)
+
+
+class ScnetEngine(object):
+    def __init__(self, net):
+        import torch
+        self.torch = torch
+        self.net = net
+        self.lib = _lib.load()
+        self._packed_key = None
+        self._packed = {}
+        self._bufs = {}
+        self._P = 0
+        self._dev = None
+
+    # ---------------------------------------------------------------- weights
+    def _pack(self):
+        torch = self.torch
+        key = tuple((p.data_ptr(), p._version) for p in self.net.parameters())
+        if key == self._packed_key:
+            return
+        W = {}
+        sd = dict(self.net.named_parameters())
+        for name, p in sd.items():
+            if name.endswith('.0.weight'):
+                base = name[:-9]
+                mod = getattr(self.net, base)[0]
+                tr = isinstance(mod, torch.nn.ConvTranspose2d)
+                w = p.detach()
+                w = w.permute(2, 3, 0, 1) if tr else w.permute(2, 3, 1, 0)       # -> [k,k,Cin,Cout]
+                W[base] = w.contiguous().float()
+            elif name.startswith('deconv1') and name.endswith('.weight'):
+                W[name[:-7]] = p.detach().permute(2, 3, 1, 0).contiguous().float()   # 1x1 heads
+        self._packed = W
+        self._packed_key = key
+
+    # ---------------------------------------------------------------- buffers
+    def _alloc(self, P, device, cout_total):
+        torch = self.torch
+        if self._P == P and self._dev == device and self._bufs.get('ctot') == cout_total:
+            return
+        n = 2 * P
+        f = dict(dtype=torch.float32, device=device)
+        B = {}
+
+        def act(name, H, W, C):
+            B[name] = _Act(torch.empty((n, H, W, C), **f), H, W, C, 0, C,
+                           torch.empty((P, C), **f), torch.empty((P, C), **f))
+
+        B['in20'] = _Act(torch.empty((n, 224, 224, 20), **f), 224, 224, 20, 0, 20)
+        for st in ('rgb', 'n', 'd'):
+            for wh in ('', '_t2s'):
+                act('e1' + st + wh, 224, 224, 32)
+                act('e2' + st + wh, 112, 112, 64)
+        act('xin', 56, 56, 768)
+        act('x4', 28, 28, 256); act('x5', 14, 14, 512); act('x6', 7, 7, 512)
+        act('x7', 3, 3, 512); act('x8', 3, 3, 512); act('x9', 1, 1, 1024)
+        act('dx9', 3, 3, 512); act('dx8', 3, 3, 512); act('dx7', 7, 7, 512)
+        act('dx6', 14, 14, 512); act('dx5', 28, 28, 256); act('dx4', 56, 56, 128)
+        for st in ('rgb', 'n', 'd', 's', 'f'):
+            act('d3' + st, 112, 112, 64)
+            act('d2' + st, 224, 224, 32 if st in ('rgb', 'n', 'd') else 64)
+        B['out224'] = _Act(torch.empty((n, 224, 224, cout_total), **f), 224, 224, cout_total, 0, cout_total)
+        B['ctot'] = cout_total
+        B['partials'] = None
+        self._bufs, self._P, self._dev = B, P, device
+
+    # ---------------------------------------------------------------- one conv block
+    def _conv(self, name, srcs, out, transposed, k, s, p, bn=True, bias=None, tanh=False, stream=None):
+        torch = self.torch
+        d = _lib.RpConvDesc()
+        d.nsrc = len(srcs)
+        for i, a in enumerate(srcs):
+            d.src[i].ptr = a.buf.data_ptr()
+            d.src[i].pitch, d.src[i].ch_off, d.src[i].C = a.pitch, a.ch_off, a.C
+            if a.scale is not None:
+                d.src[i].act = 1
+                d.src[i].scale, d.src[i].shift = a.scale.data_ptr(), a.shift.data_ptr()
+                d.src[i].sstride, d.src[i].s_off = a.pitch, a.ch_off
+            else:
+                d.src[i].act = 0
+        d.transposed, d.k, d.s, d.p = int(transposed), k, s, p
+        d.G = self._P
+        d.Hin, d.Win, d.Hout, d.Wout = srcs[0].H, srcs[0].W, out.H, out.W
+        d.Cout = out.C
+        d.W = self._packed[name].data_ptr()
+        d.out, d.out_pitch, d.out_ch_off = out.buf.data_ptr(), out.pitch, out.ch_off
+        d.bias = bias.data_ptr() if bias is not None else None
+        d.tanh_out = int(tanh)
+        nparts = ctypes.c_int(0)
+        if bn:
+            _lib.check(self.lib.rp_conv_nparts(ctypes.byref(d), ctypes.byref(nparts)), "rp_conv_nparts")
+            need = self._P * nparts.value * out.C
+            pt = self._bufs['partials']
+            if pt is None or pt.numel() < 2 * need:
+                pt = torch.empty((2 * need,), dtype=torch.float32, device=self._dev)
+                self._bufs['partials'] = pt
+            d.psum, d.psq = pt.data_ptr(), pt.data_ptr() + 4 * need
+        else:
+            d.psum, d.psq = None, None
+        _lib.check(self.lib.rp_conv_layer(ctypes.byref(d), stream), "rp_conv_layer(%s)" % name)
+        if bn:
+            bnm = getattr(self.net, name)[1]
+            _lib.check(self.lib.rp_bn_finalize(d.psum, d.psq, self._P, nparts.value, out.C, 2 * out.H * out.W,
+                                               bnm.weight.data_ptr(), bnm.bias.data_ptr(),
+                                               out.scale.data_ptr(), out.shift.data_ptr(), out.pitch, out.ch_off, stream),
+                       "rp_bn_finalize(%s)" % name)
+
+    # ---------------------------------------------------------------- forward
+    def forward(self, x, trace=None):
+        torch = self.torch
+        if not x.is_cuda:
+            raise RuntimeError("relativepose_b200.SCNet.forward needs a CUDA tensor (no CPU fallback)")
+        if x.dim() != 4 or x.shape[1] != 16 or x.shape[0] % 2 != 0:
+            raise ValueError("expected [2P,16,H,W]")
+        x = x.contiguous().float()
+        n, _, H, W = x.shape
+        P = n // 2
+        net = self.net
+        snum = net.snumclass
+        ctot = 7 + snum + 32
+        with torch.cuda.device(x.device), torch.no_grad():
+            self._pack()
+            self._alloc(P, x.device, ctot)
+            B = self._bufs
+            stream = torch.cuda.current_stream().cuda_stream
+            _lib.check(self.lib.rp_scnet_resize_in(x.data_ptr(), n, H, W, B['in20'].buf.data_ptr(), stream), "resize_in")
+            chan = {'rgb': (0, 4), 'n': (4, 4), 'd': (8, 2)}
+            xin_slot = {'rgb': 0, 'rgb_t2s': 128, 'n': 256, 'n_t2s': 384, 'd': 512, 'd_t2s': 640}
+            for wh, base in (('', 0), ('_t2s', 10)):
+                for st in ('rgb', 'n', 'd'):
+                    off, c = chan[st]
+                    self._conv('conv1' + st, [B['in20'].view(base + off, c)], B['e1' + st + wh], False, 3, 1, 1, stream=stream)
+                    self._conv('conv2' + st, [B['e1' + st + wh]], B['e2' + st + wh], False, 4, 2, 1, stream=stream)
+                    self._conv('conv3' + st, [B['e2' + st + wh]], B['xin'].view(xin_slot[st + wh], 128), False, 4, 2, 1, stream=stream)
+            self._conv('conv4', [B['xin']], B['x4'], False, 4, 2, 1, stream=stream)
+            self._conv('conv5', [B['x4']], B['x5'], False, 4, 2, 1, stream=stream)
+            self._conv('conv6', [B['x5']], B['x6'], False, 4, 2, 1, stream=stream)
+            self._conv('conv7', [B['x6']], B['x7'], False, 3, 2, 0, stream=stream)
+            self._conv('conv8', [B['x7']], B['x8'], False, 3, 1, 1, stream=stream)
+            self._conv('conv9', [B['x8']], B['x9'], False, 3, 1, 0, stream=stream)
+            self._conv('deconv9', [B['x9']], B['dx9'], True, 3, 1, 0, stream=stream)
+            self._conv('deconv8', [B['dx9'], B['x8']], B['dx8'], True, 3, 1, 1, stream=stream)
+            self._conv('deconv7', [B['dx8'], B['x7']], B['dx7'], True, 3, 2, 0, stream=stream)
+            self._conv('deconv6', [B['dx7'], B['x6']], B['dx6'], True, 4, 2, 1, stream=stream)
+            self._conv('deconv5', [B['dx6'], B['x5']], B['dx5'], True, 4, 2, 1, stream=stream)
+            self._conv('deconv4', [B['dx5'], B['x4']], B['dx4'], True, 4, 2, 1, stream=stream)
+            head_off = {'rgb': (0, 3), 'n': (3, 3), 'd': (6, 1), 's': (7, snum), 'f': (7 + snum, 32)}
+            for st in ('rgb', 'n', 'd'):
+                self._conv('deconv3' + st, [B['dx4'], B['xin'].view(xin_slot[st], 128)], B['d3' + st], True, 4, 2, 1, stream=stream)
+                self._conv('deconv2' + st, [B['d3' + st], B['e2' + st]], B['d2' + st], True, 4, 2, 1, stream=stream)
+                o, c = head_off[st]
+                self._conv('deconv1' + st, [B['d2' + st], B['e1' + st]], B['out224'].view(o, c), False, 1, 1, 0, bn=False,
+                           bias=getattr(net, 'deconv1' + st).bias, stream=stream)
+            for st in ('s', 'f'):
+                self._conv('deconv3' + st, [B['dx4']], B['d3' + st], True, 4, 2, 1, stream=stream)
+                self._conv('deconv2' + st, [B['d3' + st]], B['d2' + st], True, 4, 2, 1, stream=stream)
+                o, c = head_off[st]
+                self._conv('deconv1' + st, [B['d2' + st]], B['out224'].view(o, c), False, 1, 1, 0, bn=False,
+                           bias=getattr(net, 'deconv1' + st).bias, tanh=(st == 'f' and bool(net.useTanh)), stream=stream)
+            out = torch.empty((n, ctot, H, W), dtype=torch.float32, device=x.device)
+            _lib.check(self.lib.rp_scnet_resize_out(B['out224'].buf.data_ptr(), n, ctot, H, W, out.data_ptr(), stream), "resize_out")
+            if trace is not None:
+                self._dump(trace)
+        return out
+
+    def _dump(self, trace):
+        """Test hook: every intermediate as NCHW tensors (raw and BN+LeakyReLU'd), named like the oracle's trace."""
+        torch = self.torch
+        B = self._bufs
+
+        def grab(a):
+            raw = a.buf[..., a.ch_off:a.ch_off + a.C]
+            out = {'raw': raw.permute(0, 3, 1, 2).contiguous()}
+            if a.scale is not None:
+                sc = a.scale[:, a.ch_off:a.ch_off + a.C].repeat_interleave(2, 0)[:, None, None, :]
+                sh = a.shift[:, a.ch_off:a.ch_off + a.C].repeat_interleave(2, 0)[:, None, None, :]
+                out['act'] = torch.nn.functional.leaky_relu(raw * sc + sh, 0.1).permute(0, 3, 1, 2).contiguous()
+            return out
+
+        slot = {'rgb': 0, 'rgb_t2s': 128, 'n': 256, 'n_t2s': 384, 'd': 512, 'd_t2s': 640}
+        names = {}
+        for st in ('rgb', 'n', 'd'):
+            for wh in ('', '_t2s'):
+                names['conv1' + st + wh] = B['e1' + st + wh]
+                names['conv2' + st + wh] = B['e2' + st + wh]
+                names['conv3' + st + wh] = B['xin'].view(slot[st + wh], 128)
+        for a, b in (('conv4', 'x4'), ('conv5', 'x5'), ('conv6', 'x6'), ('conv7', 'x7'), ('conv8', 'x8'), ('conv9', 'x9'),
+                     ('deconv9', 'dx9'), ('deconv8', 'dx8'), ('deconv7', 'dx7'), ('deconv6', 'dx6'), ('deconv5', 'dx5'),
+                     ('deconv4', 'dx4')):
+            names[a] = B[b]
+        for st in ('rgb', 'n', 'd', 's', 'f'):
+            names['deconv3' + st] = B['d3' + st]
+            names['deconv2' + st] = B['d2' + st]
+        for k, a in names.items():
+            g = grab(a)
+            trace[k + ':raw'] = g['raw']
+            trace[k + ':act'] = g['act']
+        trace['out224'] = B['out224'].buf.permute(0, 3, 1, 2).contiguous()
+        trace['in20'] = B['in20'].buf.permute(0, 3, 1, 2).contiguous()

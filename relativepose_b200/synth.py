@@ -87,3 +87,31 @@ def keypoints_for_nominal_N(N, topk=5):
 
 def make_batch(first_seed, count, n_s, n_t=None, **kw):
     return [make_pair(first_seed + i, n_s, n_t, **kw) for i in range(count)]
+
+
+def make_panorama_pair(seed, dataset="suncg", H=160, W=640):
+    """Synthetic RGB-D skybox pair assembled like evaluation.py:217-239: per scan
+    [rgb U(0,1), unit normals, depth U(0.5,5) with 5% invalid zeros] masked to the observed face(s)
+    (util.py:209-232: 'second' = columns h..2h for suncg/matterport, 'kinect' = 66x88 window for scannet),
+    plus the validity mask channel; the warped-other-view half is zero on the first alternation step
+    (util.py:95-96).  Returns float32 [2,16,H,W]."""
+    rs = np.random.RandomState(seed)
+    out = np.zeros([2, 16, H, W], dtype=np.float32)
+    for v in range(2):
+        rgb = rs.uniform(0, 1, size=(3, H, W))
+        nrm = rs.randn(3, H, W)
+        nrm /= np.linalg.norm(nrm, axis=0, keepdims=True)
+        depth = rs.uniform(0.5, 5.0, size=(1, H, W))
+        depth[rs.rand(1, H, W) < 0.05] = 0.0
+        full = np.concatenate((rgb, nrm, depth), 0)
+        mask = np.zeros([1, H, W])
+        if "scannet" in dataset:
+            dw, dh = int(89.67 // 2), int(67.25 // 2)
+            mask[:, 80 - dh:80 + dh, 160 + 80 - dw:160 + 80 + dw] = 1
+        else:
+            mask[:, :H, H:2 * H] = 1
+        view = full * mask
+        valid = (view[6:7] != 0).astype(np.float64)          # evaluation.py:225-228 / rpmodule.py:609-612
+        out[v, 0:7] = view
+        out[v, 7:8] = valid
+    return out

@@ -1,0 +1,93 @@
+"""GPU parity for SCNet.forward: CUDA layers vs the oracle layer by layer, and the final
+output vs the golden produced by the reference nn.Module itself (tests/golden/scnet_golden.npz).
+
+Tolerance (float32 CUDA-core path): max-abs 2e-4 on every BN+LeakyReLU'd activation and on the output
+(values are O(1..10); the reference's own cuDNN/CPU fp32 paths differ from each other at this level)."""
+import types
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+TOL = 2e-4
+
+
+def _args(snum, tanh):
+    a = types.SimpleNamespace()
+    a.batchnorm, a.useTanh, a.skipLayer, a.outputType, a.snumclass = 1, tanh, 1, 'rgbdnsf', snum
+    return a
+
+
+def _golden():
+    import os
+    return np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "scnet_golden.npz"))
+
+
+@pytest.mark.parametrize("name", ["suncg", "scannet"])
+def test_scnet_forward_matches_reference_golden(name):
+    import torch
+    from oracle import scnet_oracle
+    from relativepose_b200 import synth
+    from relativepose_b200.model.mymodel import SCNet
+    from relativepose_b200.scnet_engine import ScnetEngine
+    G = _golden()
+    snum, tanh, seed, chk = G[name + '/meta']
+    snum, tanh, seed = int(snum), int(tanh), int(seed)
+    torch.manual_seed(0)
+    net = SCNet(_args(snum, tanh))
+    sd = {k: v.detach().clone() for k, v in net.state_dict().items()}
+    got_chk = float(sum(v.double().abs().sum().item() for v in sd.values()))
+    assert abs(got_chk - chk) <= 1e-6 * chk, "seeded weights differ from the ones the golden was made with"
+    x = torch.from_numpy(synth.make_panorama_pair(seed, str(G[name + '/dataset'])))
+    net = net.cuda()
+    eng = ScnetEngine(net)
+    tr = {}
+    y = eng.forward(x.cuda(), trace=tr)
+    torch.cuda.synchronize()
+    # layer-by-layer against the oracle (CPU fp32)
+    otr = {}
+    with torch.no_grad():
+        yo = scnet_oracle.forward_pair(sd, x, snum, bool(tanh), trace=otr)
+    worst = 0.0
+    rows = []
+    for k in otr:
+        if k.endswith(':act') and k in tr:
+            e = (tr[k].cpu() - otr[k]).abs().max().item()
+            rows.append((k, e, otr[k].abs().max().item()))
+            worst = max(worst, e)
+    e224 = (tr['out224'].cpu() - otr['out224']).abs().max().item()
+    rows.append(('out224', e224, otr['out224'].abs().max().item()))
+    for r in rows:
+        print("%-22s err %.3e  (|ref|max %.3f)" % r)
+    yc = y.cpu().numpy()
+    err_or = float(np.abs(yc - yo.numpy()).max())
+    err_gold = float(np.abs(yc[:, :, ::4, ::8] - G[name + '/sub']).max())
+    print("final: vs oracle %.3e, vs reference golden %.3e" % (err_or, err_gold))
+    assert worst <= TOL and e224 <= TOL
+    assert err_or <= TOL and err_gold <= TOL
+    assert np.abs(yc.mean(axis=(2, 3)) - G[name + '/mean']).max() <= TOL
+
+
+def test_scnet_pairs_are_independent_bn_groups():
+    """A batch of P pairs equals P separate forwards (the reference always forwards one pair: its BN batch)."""
+    import torch
+    from relativepose_b200 import synth
+    from relativepose_b200.model.mymodel import SCNet
+    torch.manual_seed(0)
+    net = SCNet(_args(15, 1)).cuda()
+    xs = [torch.from_numpy(synth.make_panorama_pair(s, "suncg", 64, 256)).cuda() for s in (3, 4, 5)]
+    yb = net(torch.cat(xs, 0))
+    for i, x in enumerate(xs):
+        yi = net(x)
+        assert torch.equal(yb[2 * i:2 * i + 2], yi)
+
+
+def test_scnet_module_surface():
+    import torch
+    from model.mymodel import SCNet
+    torch.manual_seed(0)
+    net = SCNet(_args(15, 1))
+    keys = list(net.state_dict().keys())
+    assert len(keys) == 103 and keys[0] == 'conv1rgb.0.weight' and 'deconv1f.bias' in keys
+    with pytest.raises(RuntimeError):
+        net(torch.zeros(2, 16, 32, 128))          # CPU tensor: no fallback
