@@ -215,6 +215,10 @@ int rp_scnet_resize_out(const float* in, int n, int C, int H, int W, float* out,
 int64_t rp_launch_count(void);
 int64_t rp_conv_launch_count(void);
 
+/* Unit-test hook for the tcgen05/TMEM building blocks: C[M,N] = A[M,K] * B[N,K]^T (device pointers, float32 in/out,
+ * bf16-rounded operands, fp32 accumulation in TMEM).  M % 128 == 0, K % 64 == 0, bn in {64,128}, N % bn == 0. */
+int rp_tc_gemm_test(const float* A, const float* B, float* C, int M, int N, int K, int bn, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

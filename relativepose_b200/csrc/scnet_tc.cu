@@ -1,0 +1,189 @@
+// scnet_tc.cu -- tcgen05 (5th-gen tensor core) building blocks for the SCNet convolutions, sm_100a only.
+//
+// Operands are staged in shared memory by ordinary threads (the A operand of an implicit-GEMM convolution is a
+// gather with the producer's BatchNorm + LeakyReLU applied on the fly, so it cannot come from TMA) in the
+// canonical K-major, no-swizzle UMMA layout: 8-row x 16-byte "core matrices", 128 contiguous bytes each;
+//   core(kc, mc) of a [rows][BK] bf16 tile lives at ((kc * rows/8) + mc) * 128 bytes
+//   -> stride between cores along M/N (SBO) = 128 B, along K (LBO) = rows/8 * 128 B.
+// One elected thread issues tcgen05.mma (M=128, N=BN, K=16 per instruction, bf16 x bf16 -> fp32 in TMEM),
+// tcgen05.commit signals an mbarrier, the epilogue reads the accumulator with tcgen05.ld (32 lanes x 32 columns
+// per warp and instruction).  Descriptor bit layouts follow cute/arch/mma_sm100_desc.hpp (UMMA::SmemDescriptor,
+// UMMA::InstrDescriptor).
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/rp_b200.h"
+
+namespace tc {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// UMMA shared-memory descriptor, K-major, SWIZZLE_NONE, version 1 (Blackwell).
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3fffu);              // start address  [0,14)
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3fffu) << 16;     // leading (K) byte offset  [16,30)
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3fffu) << 32;     // stride (M/N) byte offset [32,46)
+    d |= (uint64_t)1 << 46;                                // version = 1
+    return d;                                              // base_offset 0, lbo_mode 0, layout_type 0 (no swizzle)
+}
+
+// UMMA instruction descriptor: D=f32, A=B=bf16, both K-major, dense, M x N.
+__host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t done = 0;
+    const uint32_t a = smem_u32(bar);
+    while (!done) {
+        asm volatile("{\n\t.reg .pred p;\n\t"
+                     "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                     "selp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(a), "r"(parity) : "memory");
+    }
+}
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* slot, uint32_t ncols) {      // whole warp
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {     // whole warp
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\t"
+                 "setp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// 32 lanes x 32 columns of 32-bit: thread <-> TMEM lane (row of the accumulator), registers <-> columns
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
+    uint32_t* r = reinterpret_cast<uint32_t*>(v);
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                 "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                 "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+                   "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+                   "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                 : "r"(taddr) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// 8 consecutive K elements of one row -> one 16-byte unit of the canonical layout
+__device__ __forceinline__ void store_core_row(unsigned char* tile, int rows, int row, int kc, const float* v8) {
+    __nv_bfloat162 p0 = __floats2bfloat162_rn(v8[0], v8[1]);
+    __nv_bfloat162 p1 = __floats2bfloat162_rn(v8[2], v8[3]);
+    __nv_bfloat162 p2 = __floats2bfloat162_rn(v8[4], v8[5]);
+    __nv_bfloat162 p3 = __floats2bfloat162_rn(v8[6], v8[7]);
+    uint4 u;
+    u.x = *reinterpret_cast<uint32_t*>(&p0); u.y = *reinterpret_cast<uint32_t*>(&p1);
+    u.z = *reinterpret_cast<uint32_t*>(&p2); u.w = *reinterpret_cast<uint32_t*>(&p3);
+    const int off = ((kc * (rows >> 3) + (row >> 3)) * 8 + (row & 7)) * 16;
+    *reinterpret_cast<uint4*>(tile + off) = u;
+}
+
+constexpr int TM = 128;     // UMMA M
+constexpr int TK = 64;      // K per pipeline stage (4 MMAs)
+
+// ---------------------------------------------------------------------------------------------------
+// Bring-up / unit-test kernel: C[M,N] = A[M,K] * B[N,K]^T, fp32 in/out, bf16 operands, fp32 accumulate.
+// One CTA (128 threads) per 128 x BN tile; synchronous single-stage K loop.  M % 128 == 0, N % BN == 0, K % 64 == 0.
+template <int BN>
+__global__ void __launch_bounds__(128) gemm_bf16_test(const float* __restrict__ A, const float* __restrict__ B,
+                                                      float* __restrict__ C, int M, int N, int K) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    unsigned char* sA = smem;                       // 128 x 64 bf16 = 16 KB
+    unsigned char* sB = smem + TM * TK * 2;         // BN  x 64 bf16
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ uint32_t tmem_slot;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int m0 = blockIdx.x * TM, n0 = blockIdx.y * BN;
+    if (tid == 0) { mbar_init(&bar, 1); fence_mbar_init(); }
+    if (warp == 0) tmem_alloc(&tmem_slot, BN);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_d = tmem_slot;
+    const uint32_t idesc = make_idesc_bf16(TM, BN);
+    uint32_t parity = 0;
+    for (int k0 = 0; k0 < K; k0 += TK) {
+        // stage A: thread = row
+        {
+            const float* ap = A + (size_t)(m0 + tid) * K + k0;
+#pragma unroll
+            for (int kc = 0; kc < TK / 8; ++kc) {
+                float4 x = *reinterpret_cast<const float4*>(ap + kc * 8);
+                float4 y = *reinterpret_cast<const float4*>(ap + kc * 8 + 4);
+                float v[8] = {x.x, x.y, x.z, x.w, y.x, y.y, y.z, y.w};
+                store_core_row(sA, TM, tid, kc, v);
+            }
+        }
+        for (int r = tid; r < BN; r += 128) {
+            const float* bp = B + (size_t)(n0 + r) * K + k0;
+#pragma unroll
+            for (int kc = 0; kc < TK / 8; ++kc) {
+                float4 x = *reinterpret_cast<const float4*>(bp + kc * 8);
+                float4 y = *reinterpret_cast<const float4*>(bp + kc * 8 + 4);
+                float v[8] = {x.x, x.y, x.z, x.w, y.x, y.y, y.z, y.w};
+                store_core_row(sB, BN, r, kc, v);
+            }
+        }
+        fence_async_smem();          // generic-proxy smem writes -> visible to the tensor core (async proxy)
+        __syncthreads();
+        if (tid == 0) {
+            tc_fence_after();
+            const uint32_t a0 = smem_u32(sA), b0 = smem_u32(sB);
+#pragma unroll
+            for (int j = 0; j < TK / 16; ++j) {
+                uint64_t ad = make_smem_desc(a0 + j * 2 * (TM / 8) * 128, (TM / 8) * 128, 128);
+                uint64_t bd = make_smem_desc(b0 + j * 2 * (BN / 8) * 128, (BN / 8) * 128, 128);
+                umma_bf16(tmem_d, ad, bd, idesc, (k0 > 0 || j > 0) ? 1u : 0u);
+            }
+            umma_commit(&bar);       // arrives when the MMAs above have finished reading smem / writing TMEM
+        }
+        mbar_wait(&bar, parity);
+        parity ^= 1;
+    }
+    tc_fence_after();
+    // epilogue: warp w reads TMEM lanes 32w..32w+31 (= rows), 32 columns at a time
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+        float v[32];
+        tmem_ld32(tmem_d + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);
+        float* cp = C + (size_t)(m0 + tid) * N + n0 + c0;
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(cp + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem_d, BN);
+}
+
+}  // namespace tc
+
+extern "C" {
+
+// Unit-test hook for the tcgen05 building blocks: C = A * B^T with bf16-rounded operands (device pointers).
+int rp_tc_gemm_test(const float* A, const float* B, float* C, int M, int N, int K, int bn, void* stream_) {
+    if (!A || !B || !C || M % 128 || K % 64 || (bn != 64 && bn != 128) || N % bn) return RP_ERR_INVALID_ARG;
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    dim3 grid(M / 128, N / bn);
+    size_t smem = (size_t)(128 + bn) * 64 * 2;
+    if (bn == 64) tc::gemm_bf16_test<64><<<grid, 128, smem, stream>>>(A, B, C, M, N, K);
+    else tc::gemm_bf16_test<128><<<grid, 128, smem, stream>>>(A, B, C, M, N, K);
+    return cudaGetLastError() == cudaSuccess ? RP_OK : RP_ERR_CUDA;
+}
+
+}  // extern "C"
