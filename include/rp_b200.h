@@ -215,6 +215,11 @@ int rp_scnet_resize_out(const float* in, int n, int C, int H, int W, float* out,
 int64_t rp_launch_count(void);
 int64_t rp_conv_launch_count(void);
 
+/* rp_conv_layer on the 5th-gen tensor cores (tcgen05.mma, bf16 operands, fp32 accumulators in TMEM).  `w_packed` is the
+ * layer's weight tensor as bf16 blocks in the UMMA shared-memory image; see csrc/scnet_tc.cu. */
+int rp_conv_nparts_tc(const rp_conv_desc* d, int* nparts);
+int rp_conv_layer_tc(const rp_conv_desc* d, const void* w_packed, int bn, int tk, void* stream);
+
 /* Unit-test hook for the tcgen05/TMEM building blocks: C[M,N] = A[M,K] * B[N,K]^T (device pointers, float32 in/out,
  * bf16-rounded operands, fp32 accumulation in TMEM).  M % 128 == 0, K % 64 == 0, bn in {64,128}, N % bn == 0. */
 int rp_tc_gemm_test(const float* A, const float* B, float* C, int M, int N, int K, int bn, void* stream);

@@ -58,7 +58,7 @@ class RpConvDesc(ctypes.Structure):
 EXPORTS = ("rp_abi_version", "rp_device_info", "rp_solve_workspace_bytes", "rp_solve_batch",
            "rp_solve_batch_ex", "rp_match_topk", "rp_launch_count",
            "rp_conv_nparts", "rp_conv_layer", "rp_bn_finalize", "rp_scnet_resize_in", "rp_scnet_resize_out",
-           "rp_conv_launch_count", "rp_tc_gemm_test")
+           "rp_conv_launch_count", "rp_tc_gemm_test", "rp_conv_nparts_tc", "rp_conv_layer_tc")
 
 _lib = None
 
@@ -104,6 +104,10 @@ def load():
     lib.rp_scnet_resize_out.restype = i32
     lib.rp_scnet_resize_out.argtypes = [vp, i32, i32, i32, i32, vp, vp]
     lib.rp_conv_launch_count.restype = i64
+    lib.rp_conv_nparts_tc.restype = i32
+    lib.rp_conv_nparts_tc.argtypes = [ctypes.POINTER(RpConvDesc), ctypes.POINTER(ctypes.c_int)]
+    lib.rp_conv_layer_tc.restype = i32
+    lib.rp_conv_layer_tc.argtypes = [ctypes.POINTER(RpConvDesc), vp, i32, i32, vp]
     lib.rp_tc_gemm_test.restype = i32
     lib.rp_tc_gemm_test.argtypes = [vp, vp, vp, i32, i32, i32, i32, vp]
     if lib.rp_abi_version() != 1:

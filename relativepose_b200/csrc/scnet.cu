@@ -15,29 +15,12 @@
 #include <stdint.h>
 
 #include "../../include/rp_b200.h"
+#include "scnet_common.cuh"
 
 namespace {
+using namespace scnet;
 
 constexpr int BM = 64, BN_ = 64, BK = 16, CT = 256;
-constexpr int MAXTAP = 16;
-constexpr float LEAKY = 0.1f;
-constexpr double BN_EPS = 1e-5;
-
-struct Tap { int dy, dx, widx; };
-struct ConvClass { int py, px, Ha, Wb, ntap; Tap taps[MAXTAP]; };
-
-struct ConvArgs {
-    rp_conv_src src[2];
-    int nsrc;
-    int G, Hin, Win, Hout, Wout, Cout, Cin_total;
-    int istr, ostr, nclass, tiles_m;
-    ConvClass cls[4];
-    const float* W;
-    float* out; int out_pitch, out_ch_off;
-    float* psum; float* psq;
-    const float* bias; int tanh_out;
-};
-
 // One (group, class, m-tile, n-tile) per CTA.  256 threads: loaders (64 pixels x 4 channel quads / 16 k x 16 n quads),
 // compute 16x16 threads x (4 pixels x 4 channels).
 __global__ void __launch_bounds__(CT) conv_igemm_f32(const ConvArgs A) {
@@ -246,48 +229,9 @@ __global__ void scnet_resize_out_kernel(const float* __restrict__ in, int n, int
     out[idx] = ly0 * (lx0 * p00 + lx1 * p01) + ly1 * (lx0 * p10 + lx1 * p11);
 }
 
-bool build_args(const rp_conv_desc* d, ConvArgs* A) {
-    if (!d || d->nsrc < 1 || d->nsrc > 2 || d->k < 1 || d->k > 4 || d->s < 1 || d->s > 2 || d->G < 1) return false;
-    A->nsrc = d->nsrc;
-    A->Cin_total = 0;
-    for (int i = 0; i < d->nsrc; ++i) { A->src[i] = d->src[i]; A->Cin_total += d->src[i].C; }
-    A->G = d->G; A->Hin = d->Hin; A->Win = d->Win; A->Hout = d->Hout; A->Wout = d->Wout; A->Cout = d->Cout;
-    A->W = d->W; A->out = d->out; A->out_pitch = d->out_pitch; A->out_ch_off = d->out_ch_off;
-    A->psum = d->psum; A->psq = d->psq; A->bias = d->bias; A->tanh_out = d->tanh_out;
-    const int k = d->k, s = d->s, p = d->p;
-    if (!d->transposed) {
-        // iy = oy*s - p + ky
-        A->istr = s; A->ostr = 1; A->nclass = 1;
-        ConvClass& c = A->cls[0];
-        c.py = 0; c.px = 0; c.Ha = d->Hout; c.Wb = d->Wout; c.ntap = 0;
-        for (int ky = 0; ky < k; ++ky) for (int kx = 0; kx < k; ++kx) { c.taps[c.ntap].dy = ky - p; c.taps[c.ntap].dx = kx - p; c.taps[c.ntap].widx = ky * k + kx; ++c.ntap; }
-    } else {
-        // oy = iy*s - p + ky  ->  for output parity class py: ky with (py + p - ky) % s == 0, iy = a + (py + p - ky)/s
-        A->istr = 1; A->ostr = s; A->nclass = s * s;
-        for (int py = 0; py < s; ++py) for (int px = 0; px < s; ++px) {
-            ConvClass& c = A->cls[py * s + px];
-            c.py = py; c.px = px; c.ntap = 0;
-            c.Ha = (d->Hout - py + s - 1) / s; c.Wb = (d->Wout - px + s - 1) / s;
-            if (c.Ha < 0) c.Ha = 0; if (c.Wb < 0) c.Wb = 0;
-            for (int ky = 0; ky < k; ++ky) {
-                if (((py + p - ky) % s + s) % s != 0) continue;
-                for (int kx = 0; kx < k; ++kx) {
-                    if (((px + p - kx) % s + s) % s != 0) continue;
-                    int dy = (py + p - ky) / s, dx = (px + p - kx) / s;     // exact (divisible); may be negative
-                    if ((py + p - ky) < 0) dy = -((ky - py - p) / s);
-                    if ((px + p - kx) < 0) dx = -((kx - px - p) / s);
-                    c.taps[c.ntap].dy = dy; c.taps[c.ntap].dx = dx; c.taps[c.ntap].widx = ky * k + kx; ++c.ntap;
-                }
-            }
-        }
-    }
-    int tm = 1;
-    for (int i = 0; i < A->nclass; ++i) { int t = (2 * A->cls[i].Ha * A->cls[i].Wb + BM - 1) / BM; if (t > tm) tm = t; }
-    A->tiles_m = tm;
-    return true;
-}
-
-long long g_conv_launches = 0;
+}  // namespace
+namespace scnet { long long g_conv_launches = 0; }
+namespace {
 
 }  // namespace
 
@@ -295,14 +239,14 @@ extern "C" {
 
 int rp_conv_nparts(const rp_conv_desc* d, int* nparts) {
     ConvArgs A;
-    if (!nparts || !build_args(d, &A)) return RP_ERR_INVALID_ARG;
+    if (!nparts || !build_args(d, &A, BM)) return RP_ERR_INVALID_ARG;
     *nparts = A.nclass * A.tiles_m;
     return RP_OK;
 }
 
 int rp_conv_layer(const rp_conv_desc* d, void* stream_) {
     ConvArgs A;
-    if (!build_args(d, &A)) return RP_ERR_INVALID_ARG;
+    if (!build_args(d, &A, BM)) return RP_ERR_INVALID_ARG;
     if (!d->W || !d->out || !d->src[0].ptr) return RP_ERR_INVALID_ARG;
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
     dim3 grid(A.tiles_m, (A.Cout + BN_ - 1) / BN_, A.G * A.nclass);

@@ -14,6 +14,7 @@
 #include <stdint.h>
 
 #include "../../include/rp_b200.h"
+#include "scnet_common.cuh"
 
 namespace tc {
 
@@ -171,6 +172,187 @@ __global__ void __launch_bounds__(128) gemm_bf16_test(const float* __restrict__ 
     if (warp == 0) tmem_dealloc(tmem_d, BN);
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Implicit-GEMM convolution / transposed convolution on tcgen05.  One CTA = 128 output pixels (UMMA M) x BN output
+// channels of one (scan pair, sub-pixel class); K loop over (tap, source, TK-channel tile), two smem stages:
+// while the tensor core works on stage s the 128 threads gather + BatchNorm + LeakyReLU + bf16-convert the next
+// A tile (thread = pixel row: 16-byte units land conflict-free in the core-matrix layout) and copy the next
+// pre-packed weight block (already in the smem image).  tcgen05.commit -> mbarrier frees a stage.  Epilogue:
+// TMEM -> registers -> raw fp32 NHWC output (+bias/tanh for the 1x1 heads) and per-channel partial batch
+// statistics through a padded smem transpose (fixed summation order).
+template <int BN, int TK>
+__global__ void __launch_bounds__(128) conv_igemm_tc(const scnet::ConvArgs A, const unsigned char* __restrict__ Wp,
+                                                      int nkt, int ntn) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    constexpr int A_BYTES = TM * TK * 2, B_BYTES = BN * TK * 2, STAGE = A_BYTES + B_BYTES;
+    __shared__ __align__(8) uint64_t bar[2];
+    __shared__ uint32_t tmem_slot;
+    __shared__ float red_s[4][32], red_q[4][32];
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int tile_m = blockIdx.x, tile_n = blockIdx.y;
+    const int g = blockIdx.z / A.nclass, ci = blockIdx.z - g * A.nclass;
+    const scnet::ConvClass& C = A.cls[ci];
+    const int HW = C.Ha * C.Wb;
+    const int Mc = 2 * HW;
+    const int part_row = (g * A.nclass + ci) * A.tiles_m + tile_m;
+    if (tile_m * TM >= Mc) {             // padded tile of a smaller class: zeros for the statistics
+        if (A.psum && tid < BN) {
+            int co = tile_n * BN + tid;
+            if (co < A.Cout) { A.psum[(size_t)part_row * A.Cout + co] = 0.f; A.psq[(size_t)part_row * A.Cout + co] = 0.f; }
+        }
+        return;
+    }
+    const int m_l = tile_m * TM + tid;
+    const bool mval = m_l < Mc;
+    int img_l = 0, a_l = 0, b_l = 0;
+    if (mval) { int im = m_l / HW; int rem = m_l - im * HW; img_l = g * 2 + im; a_l = rem / C.Wb; b_l = rem - a_l * C.Wb; }
+
+    if (tid == 0) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); fence_mbar_init(); }
+    if (warp == 0) tmem_alloc(&tmem_slot, BN);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_d = tmem_slot;
+    const uint32_t idesc = make_idesc_bf16(TM, BN);
+
+    int it = 0;
+    for (int t = 0; t < C.ntap; ++t) {
+        const scnet::Tap tp = C.taps[t];
+        const int iy = a_l * A.istr + tp.dy, ix = b_l * A.istr + tp.dx;
+        const bool inb = mval && iy >= 0 && iy < A.Hin && ix >= 0 && ix < A.Win;
+        const size_t pix = ((size_t)img_l * A.Hin + iy) * A.Win + ix;
+        int kt = 0;
+        for (int s = 0; s < A.nsrc; ++s) {
+            const rp_conv_src& S = A.src[s];
+            for (int c0 = 0; c0 < S.C; c0 += TK, ++kt, ++it) {
+                const int stage = it & 1;
+                unsigned char* sA = smem + stage * STAGE;
+                unsigned char* sB = sA + A_BYTES;
+                mbar_wait(&bar[stage], (uint32_t)(((it >> 1) & 1) ^ 1));      // MMAs that read this stage are done
+                // ---- A tile: my pixel, TK consecutive channels
+                if (inb) {
+                    const float* p = S.ptr + pix * S.pitch + S.ch_off + c0;
+                    const float* sc = S.scale + (size_t)g * S.sstride + S.s_off + c0;
+                    const float* sh = S.shift + (size_t)g * S.sstride + S.s_off + c0;
+#pragma unroll
+                    for (int kc = 0; kc < TK / 8; ++kc) {
+                        float4 x = *reinterpret_cast<const float4*>(p + kc * 8);
+                        float4 y = *reinterpret_cast<const float4*>(p + kc * 8 + 4);
+                        float v[8] = {x.x, x.y, x.z, x.w, y.x, y.y, y.z, y.w};
+                        if (S.act) {
+                            float4 s0 = *reinterpret_cast<const float4*>(sc + kc * 8), s1 = *reinterpret_cast<const float4*>(sc + kc * 8 + 4);
+                            float4 h0 = *reinterpret_cast<const float4*>(sh + kc * 8), h1 = *reinterpret_cast<const float4*>(sh + kc * 8 + 4);
+                            const float sv[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+                            const float hv[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) { float z = fmaf(v[j], sv[j], hv[j]); v[j] = z > 0.f ? z : scnet::LEAKY * z; }
+                        }
+                        store_core_row(sA, TM, tid, kc, v);
+                    }
+                } else {
+                    const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+                    for (int kc = 0; kc < TK / 8; ++kc)
+                        *reinterpret_cast<uint4*>(sA + ((kc * (TM >> 3) + (tid >> 3)) * 8 + (tid & 7)) * 16) = z;
+                }
+                // ---- B tile: pre-packed block (tap, k-tile, n-tile), already in the smem image
+                {
+                    const uint4* src = reinterpret_cast<const uint4*>(Wp + ((size_t)((size_t)tp.widx * nkt + kt) * ntn + tile_n) * B_BYTES);
+                    uint4* dst = reinterpret_cast<uint4*>(sB);
+#pragma unroll
+                    for (int i = 0; i < B_BYTES / 16 / 128; ++i) dst[i * 128 + tid] = src[i * 128 + tid];
+                    if ((B_BYTES / 16) % 128) { int i = (B_BYTES / 16 / 128) * 128 + tid; if (i < B_BYTES / 16) dst[i] = src[i]; }
+                }
+                fence_async_smem();
+                __syncthreads();
+                if (tid == 0) {
+                    tc_fence_after();
+                    const uint32_t a0 = smem_u32(sA), b0 = smem_u32(sB);
+#pragma unroll
+                    for (int j = 0; j < TK / 16; ++j) {
+                        uint64_t ad = make_smem_desc(a0 + j * 2 * (TM / 8) * 128, (TM / 8) * 128, 128);
+                        uint64_t bd = make_smem_desc(b0 + j * 2 * (BN / 8) * 128, (BN / 8) * 128, 128);
+                        umma_bf16(tmem_d, ad, bd, idesc, (it > 0 || j > 0) ? 1u : 0u);
+                    }
+                    umma_commit(&bar[stage]);
+                }
+            }
+        }
+    }
+    // drain: the last commit covers every MMA issued before it
+    {
+        const int last = it - 1;
+        mbar_wait(&bar[last & 1], (uint32_t)((last >> 1) & 1));
+    }
+    tc_fence_after();
+    __syncthreads();           // every thread is past the mainloop: stage memory can be reused
+
+    // ---- epilogue
+    float* Tt = reinterpret_cast<float*>(smem);            // [128][33] transpose buffer
+    float* op = nullptr;
+    if (mval) {
+        const int im = m_l / HW;
+        const int oy = a_l * A.ostr + C.py, ox = b_l * A.ostr + C.px;
+        op = A.out + (((size_t)(g * 2 + im) * A.Hout + oy) * A.Wout + ox) * A.out_pitch + A.out_ch_off;
+    }
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+        float v[32];
+        tmem_ld32(tmem_d + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);
+        const int co0 = tile_n * BN + c0;
+        if (A.bias || A.tanh_out) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                if (co0 + j < A.Cout) { float y = v[j] + (A.bias ? A.bias[co0 + j] : 0.f); v[j] = A.tanh_out ? tanhf(y) : y; }
+            }
+        }
+        if (op) {
+            if (co0 + 31 < A.Cout && (((size_t)(op + co0)) & 15) == 0) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(op + co0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) if (co0 + j < A.Cout) op[co0 + j] = v[j];
+            }
+        }
+        if (A.psum) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) Tt[tid * 33 + j] = v[j];          // rows of invalid pixels are exact zeros
+            __syncthreads();
+            {
+                const int col = tid & 31, part = tid >> 5;
+                float s1 = 0.f, s2 = 0.f;
+#pragma unroll 8
+                for (int r = 0; r < 32; ++r) { float x = Tt[(part * 32 + r) * 33 + col]; s1 += x; s2 += x * x; }
+                red_s[part][col] = s1; red_q[part][col] = s2;
+            }
+            __syncthreads();
+            if (tid < 32 && co0 + tid < A.Cout) {
+                float s1 = ((red_s[0][tid] + red_s[1][tid]) + red_s[2][tid]) + red_s[3][tid];
+                float s2 = ((red_q[0][tid] + red_q[1][tid]) + red_q[2][tid]) + red_q[3][tid];
+                A.psum[(size_t)part_row * A.Cout + co0 + tid] = s1;
+                A.psq[(size_t)part_row * A.Cout + co0 + tid] = s2;
+            }
+            __syncthreads();
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem_d, BN);
+}
+
+template <int BN, int TK>
+int launch_conv_tc(const scnet::ConvArgs& A, const void* wp, int nkt, cudaStream_t stream) {
+    const int ntn = (A.Cout + BN - 1) / BN;
+    size_t pipe = 2 * (size_t)(TM * TK * 2 + BN * TK * 2), tr = (size_t)128 * 33 * 4;
+    size_t smem = pipe > tr ? pipe : tr;
+    auto kern = conv_igemm_tc<BN, TK>;
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { cudaGetLastError(); return RP_ERR_CUDA; }
+    dim3 grid(A.tiles_m, ntn, A.G * A.nclass);
+    kern<<<grid, 128, smem, stream>>>(A, static_cast<const unsigned char*>(wp), nkt, ntn);
+    ++scnet::g_conv_launches;
+    return cudaGetLastError() == cudaSuccess ? RP_OK : RP_ERR_CUDA;
+}
+
 }  // namespace tc
 
 extern "C" {
@@ -184,6 +366,33 @@ int rp_tc_gemm_test(const float* A, const float* B, float* C, int M, int N, int 
     if (bn == 64) tc::gemm_bf16_test<64><<<grid, 128, smem, stream>>>(A, B, C, M, N, K);
     else tc::gemm_bf16_test<128><<<grid, 128, smem, stream>>>(A, B, C, M, N, K);
     return cudaGetLastError() == cudaSuccess ? RP_OK : RP_ERR_CUDA;
+}
+
+int rp_conv_nparts_tc(const rp_conv_desc* d, int* nparts) {
+    scnet::ConvArgs A;
+    if (!nparts || !scnet::build_args(d, &A, tc::TM)) return RP_ERR_INVALID_ARG;
+    *nparts = A.nclass * A.tiles_m;
+    return RP_OK;
+}
+
+// Same layer contract as rp_conv_layer, on tcgen05: bf16 operands, fp32 accumulation in TMEM.  `w_packed` = the
+// layer's weights as bf16 blocks [tap][k-tile][n-tile][tk/8][bn/8][8 rows (co)][8 (ci)] (the UMMA smem image, see
+// relativepose_b200/scnet_engine.py:pack_tc); every source must have C % tk == 0; bn in {32,64,128}, tk in {32,64}.
+int rp_conv_layer_tc(const rp_conv_desc* d, const void* w_packed, int bn, int tk, void* stream_) {
+    scnet::ConvArgs A;
+    if (!w_packed || !scnet::build_args(d, &A, tc::TM)) return RP_ERR_INVALID_ARG;
+    if (!d->out || !d->src[0].ptr) return RP_ERR_INVALID_ARG;
+    int nkt = 0;
+    for (int i = 0; i < d->nsrc; ++i) {
+        if (d->src[i].C % tk || (d->src[i].pitch % 4) || (d->src[i].ch_off % 4)) return RP_ERR_UNSUPPORTED;
+        if (d->src[i].act && ((d->src[i].sstride % 4) || (d->src[i].s_off % 4))) return RP_ERR_UNSUPPORTED;
+        nkt += d->src[i].C / tk;
+    }
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+#define RP_TC_CASE(BN_, TK_) if (bn == BN_ && tk == TK_) return tc::launch_conv_tc<BN_, TK_>(A, w_packed, nkt, stream);
+    RP_TC_CASE(32, 32) RP_TC_CASE(64, 32) RP_TC_CASE(128, 32) RP_TC_CASE(32, 64) RP_TC_CASE(64, 64) RP_TC_CASE(128, 64)
+#undef RP_TC_CASE
+    return RP_ERR_UNSUPPORTED;
 }
 
 }  // extern "C"

@@ -23,14 +23,39 @@ class _Act(object):
         return _Act(self.buf, self.H, self.W, self.pitch, self.ch_off + ch_off, C, self.scale, self.shift)
 
 
+def pack_tc(w_taps, src_channels, cout, bn, tk):
+    """Weights [taps, Cin_total, Cout] fp32 -> bf16 blocks [tap][k-tile][n-tile][tk/8][bn/8][8 (co)][8 (ci)]: each
+    (tap, k-tile, n-tile) block is the UMMA K-major / no-swizzle shared-memory image of a [bn x tk] B operand, so
+    the kernel copies it verbatim.  K tiles run source by source (the kernel's loop order); Cout is zero padded."""
+    import torch
+    taps = w_taps.shape[0]
+    ntn = -(-cout // bn)
+    cpad = ntn * bn
+    W = torch.zeros((taps, w_taps.shape[1], cpad), dtype=torch.float32, device=w_taps.device)
+    W[:, :, :cout] = w_taps
+    k0s, base = [], 0
+    for c in src_channels:
+        assert c % tk == 0
+        k0s += [base + c0 for c0 in range(0, c, tk)]
+        base += c
+    Wt = torch.stack([W[:, k0:k0 + tk, :] for k0 in k0s], 1)                   # [t, kt, tk, cpad]
+    Wt = Wt.reshape(taps, len(k0s), tk // 8, 8, ntn, bn // 8, 8)               # [t, kt, kc, kk, nt, nc, r]
+    Wt = Wt.permute(0, 1, 4, 2, 5, 6, 3).contiguous()                          # [t, kt, nt, kc, nc, r, kk]
+    return Wt.to(torch.bfloat16).contiguous()
+
+
 class ScnetEngine(object):
-    def __init__(self, net):
+    def __init__(self, net, mode=None):
+        import os
         import torch
+        # 'tc': tcgen05 bf16 tensor-core kernels wherever a layer qualifies (default); 'fp32': CUDA-core float32 only
+        self.mode = mode or os.environ.get("RP_SCNET_MODE", "tc")
         self.torch = torch
         self.net = net
         self.lib = _lib.load()
         self._packed_key = None
         self._packed = {}
+        self._packed_tc = {}
         self._bufs = {}
         self._P = 0
         self._dev = None
@@ -54,6 +79,7 @@ class ScnetEngine(object):
             elif name.startswith('deconv1') and name.endswith('.weight'):
                 W[name[:-7]] = p.detach().permute(2, 3, 1, 0).contiguous().float()   # 1x1 heads
         self._packed = W
+        self._packed_tc = {}
         self._packed_key = key
 
     # ---------------------------------------------------------------- buffers
@@ -106,12 +132,22 @@ class ScnetEngine(object):
         d.Hin, d.Win, d.Hout, d.Wout = srcs[0].H, srcs[0].W, out.H, out.W
         d.Cout = out.C
         d.W = self._packed[name].data_ptr()
+        use_tc = self.mode == 'tc' and all(a.C % 32 == 0 for a in srcs)
+        if use_tc:
+            tk = 64 if all(a.C % 64 == 0 for a in srcs) else 32
+            bn_tile = 128 if out.C >= 128 else (64 if out.C >= 64 else 32)
+            key = (name, bn_tile, tk)
+            if key not in self._packed_tc:
+                w = self._packed[name]
+                self._packed_tc[key] = pack_tc(w.reshape(k * k, w.shape[2], w.shape[3]), [a.C for a in srcs], out.C, bn_tile, tk)
+            wtc = self._packed_tc[key]
         d.out, d.out_pitch, d.out_ch_off = out.buf.data_ptr(), out.pitch, out.ch_off
         d.bias = bias.data_ptr() if bias is not None else None
         d.tanh_out = int(tanh)
         nparts = ctypes.c_int(0)
         if bn:
-            _lib.check(self.lib.rp_conv_nparts(ctypes.byref(d), ctypes.byref(nparts)), "rp_conv_nparts")
+            _lib.check((self.lib.rp_conv_nparts_tc if use_tc else self.lib.rp_conv_nparts)(ctypes.byref(d), ctypes.byref(nparts)),
+                       "rp_conv_nparts")
             need = self._P * nparts.value * out.C
             pt = self._bufs['partials']
             if pt is None or pt.numel() < 2 * need:
@@ -120,7 +156,10 @@ class ScnetEngine(object):
             d.psum, d.psq = pt.data_ptr(), pt.data_ptr() + 4 * need
         else:
             d.psum, d.psq = None, None
-        _lib.check(self.lib.rp_conv_layer(ctypes.byref(d), stream), "rp_conv_layer(%s)" % name)
+        if use_tc:
+            _lib.check(self.lib.rp_conv_layer_tc(ctypes.byref(d), wtc.data_ptr(), bn_tile, tk, stream), "rp_conv_layer_tc(%s)" % name)
+        else:
+            _lib.check(self.lib.rp_conv_layer(ctypes.byref(d), stream), "rp_conv_layer(%s)" % name)
         if bn:
             bnm = getattr(self.net, name)[1]
             _lib.check(self.lib.rp_bn_finalize(d.psum, d.psq, self._P, nparts.value, out.C, 2 * out.H * out.W,

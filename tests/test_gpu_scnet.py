@@ -30,6 +30,42 @@ def _golden():
 
 
 @pytest.mark.parametrize("name", ["suncg", "scannet"])
+def test_scnet_tensor_core_path(name):
+    """tcgen05 path (bf16 operands, fp32 accumulate): same forward, documented looser tolerance.  bf16 has an 8-bit
+    mantissa (2^-9 relative rounding per operand); through ~20 conv blocks with re-normalising BatchNorm the output
+    differs from the float32 reference by ~1e-2 of its range.  Asserted: max-abs <= 0.25 and RMS <= 0.03 on outputs
+    of magnitude ~10 (the bottleneck layers are excluded from any max-abs statement, see the fp32 test)."""
+    import torch
+    from oracle import scnet_oracle
+    from relativepose_b200 import synth
+    from relativepose_b200.model.mymodel import SCNet
+    from relativepose_b200.scnet_engine import ScnetEngine
+    G = _golden()
+    snum, tanh, seed, chk = G[name + '/meta']
+    snum, tanh, seed = int(snum), int(tanh), int(seed)
+    torch.manual_seed(0)
+    net = SCNet(_args(snum, tanh))
+    sd = {k: v.detach().clone() for k, v in net.state_dict().items()}
+    x = torch.from_numpy(synth.make_panorama_pair(seed, str(G[name + '/dataset'])))
+    net = net.cuda()
+    tr = {}
+    y = ScnetEngine(net, mode='tc').forward(x.cuda(), trace=tr)
+    torch.cuda.synchronize()
+    otr = {}
+    with torch.no_grad():
+        yo = scnet_oracle.forward_pair(sd, x, snum, bool(tanh), trace=otr)
+    for k in otr:
+        if k.endswith(':act') and k in tr:
+            d = (tr[k].cpu() - otr[k])
+            print("%-22s max %.3e rms %.3e (|ref|max %.3f)" % (k, d.abs().max().item(), d.pow(2).mean().sqrt().item(), otr[k].abs().max().item()))
+    d = (y.cpu() - yo)
+    emax, erms = d.abs().max().item(), d.pow(2).mean().sqrt().item()
+    gsub = float(np.abs(y.cpu().numpy()[:, :, ::4, ::8] - G[name + '/sub']).max())
+    print("tc final: max %.3e rms %.3e, vs reference golden (subsampled) max %.3e, |y|max %.2f" % (emax, erms, gsub, yo.abs().max().item()))
+    assert emax <= 0.25 and erms <= 0.03 and gsub <= 0.25
+
+
+@pytest.mark.parametrize("name", ["suncg", "scannet"])
 def test_scnet_forward_matches_reference_golden(name):
     import torch
     from oracle import scnet_oracle
@@ -46,7 +82,7 @@ def test_scnet_forward_matches_reference_golden(name):
     assert abs(got_chk - chk) <= 1e-6 * chk, "seeded weights differ from the ones the golden was made with"
     x = torch.from_numpy(synth.make_panorama_pair(seed, str(G[name + '/dataset'])))
     net = net.cuda()
-    eng = ScnetEngine(net)
+    eng = ScnetEngine(net, mode='fp32')
     tr = {}
     y = eng.forward(x.cuda(), trace=tr)
     torch.cuda.synchronize()
@@ -83,7 +119,7 @@ def test_scnet_pairs_are_independent_bn_groups():
     from relativepose_b200 import synth
     from relativepose_b200.model.mymodel import SCNet
     torch.manual_seed(0)
-    net = SCNet(_args(15, 1)).cuda()
+    net = SCNet(_args(15, 1)).cuda()          # default mode (tensor cores)
     xs = [torch.from_numpy(synth.make_panorama_pair(s, "suncg", 64, 256)).cuda() for s in (3, 4, 5)]
     yb = net(torch.cat(xs, 0))
     for i, x in enumerate(xs):
