@@ -159,22 +159,29 @@ __global__ void __launch_bounds__(CT) conv_igemm_f32(const ConvArgs A) {
     }
 }
 
+// One warp per (group, channel): lanes stride over the partial rows (each lane sums its rows in order, then a
+// fixed butterfly) -- deterministic, and 32x less serial than one thread per channel for the 1568-row layers.
 __global__ void bn_finalize_kernel(const float* __restrict__ psum, const float* __restrict__ psq, int nparts, int Cout,
                                    int count, const float* __restrict__ gamma, const float* __restrict__ beta,
                                    float* __restrict__ scale, float* __restrict__ shift, int sstride, int s_off) {
     const int g = blockIdx.y;
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (c >= Cout) return;
     double s = 0.0, q = 0.0;
     const float* ps = psum + (size_t)g * nparts * Cout + c;
     const float* pq = psq + (size_t)g * nparts * Cout + c;
-    for (int r = 0; r < nparts; ++r) { s += (double)ps[(size_t)r * Cout]; q += (double)pq[(size_t)r * Cout]; }
-    const double mean = s / count;
-    double var = q / count - mean * mean;          // biased variance, as nn.BatchNorm2d normalises with
-    if (var < 0.0) var = 0.0;
-    const double sc = (double)gamma[c] / sqrt(var + BN_EPS);
-    scale[(size_t)g * sstride + s_off + c] = (float)sc;
-    shift[(size_t)g * sstride + s_off + c] = (float)((double)beta[c] - mean * sc);
+    for (int r = lane; r < nparts; r += 32) { s += (double)ps[(size_t)r * Cout]; q += (double)pq[(size_t)r * Cout]; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); q += __shfl_xor_sync(0xffffffffu, q, o); }
+    if (lane == 0) {
+        const double mean = s / count;
+        double var = q / count - mean * mean;          // biased variance, as nn.BatchNorm2d normalises with
+        if (var < 0.0) var = 0.0;
+        const double sc = (double)gamma[c] / sqrt(var + BN_EPS);
+        scale[(size_t)g * sstride + s_off + c] = (float)sc;
+        shift[(size_t)g * sstride + s_off + c] = (float)((double)beta[c] - mean * sc);
+    }
 }
 
 // ATen upsample_bilinear2d, align_corners=False: src = (dst+0.5)*scale-0.5 clamped at 0, scale = in/out in float.
@@ -214,19 +221,89 @@ __global__ void scnet_resize_in_kernel(const float* __restrict__ x, int n, int H
 }
 
 __global__ void scnet_resize_out_kernel(const float* __restrict__ in, int n, int C, int H, int W, float* __restrict__ out) {
-    // in [n,224,224,C] NHWC -> out [n,C,H,W]; one thread per (pixel, 4 channels... ) keep simple: per (n,c,y,x)
+    // in [n,224,224,C] NHWC -> out [n,C,H,W]: one thread per output pixel; the four corner pixels are contiguous
+    // C-vectors, the per-channel stores are coalesced across the warp (consecutive ox)
     const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const size_t total = (size_t)n * C * H * W;
+    const size_t total = (size_t)n * H * W;
     if (idx >= total) return;
-    const int ox = (int)(idx % W); const int oy = (int)((idx / W) % H); const int c = (int)((idx / ((size_t)W * H)) % C);
-    const int im = (int)(idx / ((size_t)W * H * C));
+    const int ox = (int)(idx % W); const int oy = (int)((idx / W) % H); const int im = (int)(idx / ((size_t)W * H));
     int y0, y1, x0, x1; float ly0, ly1, lx0, lx1;
     bilin_coord(oy, 224.f / (float)H, 224, y0, y1, ly0, ly1);
     bilin_coord(ox, 224.f / (float)W, 224, x0, x1, lx0, lx1);
-    const float* p = in + (size_t)im * 224 * 224 * C + c;
-    float p00 = p[((size_t)y0 * 224 + x0) * C], p01 = p[((size_t)y0 * 224 + x1) * C];
-    float p10 = p[((size_t)y1 * 224 + x0) * C], p11 = p[((size_t)y1 * 224 + x1) * C];
-    out[idx] = ly0 * (lx0 * p00 + lx1 * p01) + ly1 * (lx0 * p10 + lx1 * p11);
+    const float* b = in + (size_t)im * 224 * 224 * C;
+    const float* p00 = b + ((size_t)y0 * 224 + x0) * C; const float* p01 = b + ((size_t)y0 * 224 + x1) * C;
+    const float* p10 = b + ((size_t)y1 * 224 + x0) * C; const float* p11 = b + ((size_t)y1 * 224 + x1) * C;
+    float* o = out + (size_t)im * C * H * W + (size_t)oy * W + ox;
+    for (int c = 0; c < C; ++c)
+        o[(size_t)c * H * W] = ly0 * (lx0 * p00[c] + lx1 * p01[c]) + ly1 * (lx0 * p10[c] + lx1 * p11[c]);
+}
+
+// Direct 3x3/s1/p1 convolution for the tiny-Cin encoder stems (conv1rgb/conv1n: Cin=4, conv1d: Cin=2 -> 32 channels,
+// mymodel.py:151,155,159): one thread per output pixel x 32 channels, weights + nothing else in smem.  The implicit
+// GEMM kernel would spend 75-88 % of every 16-wide K tile on padding here.
+template <int CIN>
+__global__ void __launch_bounds__(128) conv3x3_small_cin(const ConvArgs A) {
+    __shared__ float Ws[9 * CIN * 32];
+    __shared__ float red_s[4][32], red_q[4][32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int i = tid; i < 9 * CIN * 32; i += 128) Ws[i] = A.W[i];          // packed [tap][ci][co], Cout == 32
+    __syncthreads();
+    const int g = blockIdx.y;
+    const int HW = A.Hout * A.Wout;
+    const int m = blockIdx.x * 128 + tid;                                   // pixel within the pair (2 images)
+    const bool val = m < 2 * HW;
+    float acc[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) acc[j] = 0.f;
+    int im = 0, oy = 0, ox = 0;
+    if (val) {
+        im = m / HW; const int rem = m - im * HW; oy = rem / A.Wout; ox = rem - oy * A.Wout;
+        const rp_conv_src& S = A.src[0];
+        const float* base = S.ptr + (size_t)(g * 2 + im) * A.Hin * A.Win * S.pitch + S.ch_off;
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky) {
+            const int iy = oy + ky - 1;
+            if (iy < 0 || iy >= A.Hin) continue;
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) {
+                const int ix = ox + kx - 1;
+                if (ix < 0 || ix >= A.Win) continue;
+                const float* p = base + ((size_t)iy * A.Win + ix) * S.pitch;
+                float x[CIN];
+#pragma unroll
+                for (int c = 0; c < CIN; ++c) x[c] = p[c];
+                const float* w = Ws + (ky * 3 + kx) * CIN * 32;
+#pragma unroll
+                for (int c = 0; c < CIN; ++c)
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) acc[j] = fmaf(x[c], w[c * 32 + j], acc[j]);
+            }
+        }
+        float* op = A.out + (((size_t)(g * 2 + im) * A.Hout + oy) * A.Wout + ox) * A.out_pitch + A.out_ch_off;
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(op + j) = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
+    }
+    if (A.psum) {       // per-channel sums over the 128 pixels of this CTA: butterfly per warp, 4 warps combined in order
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            float s1 = acc[j], s2 = acc[j] * acc[j];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) { s1 += __shfl_xor_sync(0xffffffffu, s1, o); s2 += __shfl_xor_sync(0xffffffffu, s2, o); }
+            if (lane == 0) { red_s[warp][j] = s1; red_q[warp][j] = s2; }
+        }
+        __syncthreads();
+        if (tid < 32) {
+            const size_t row = (size_t)g * gridDim.x + blockIdx.x;
+            A.psum[row * 32 + tid] = ((red_s[0][tid] + red_s[1][tid]) + red_s[2][tid]) + red_s[3][tid];
+            A.psq[row * 32 + tid] = ((red_q[0][tid] + red_q[1][tid]) + red_q[2][tid]) + red_q[3][tid];
+        }
+    }
+}
+
+inline bool small_cin_eligible(const rp_conv_desc* d) {
+    return d->nsrc == 1 && !d->transposed && d->k == 3 && d->s == 1 && d->p == 1 && d->Cout == 32 && !d->bias &&
+           !d->tanh_out && d->src[0].act == 0 && (d->src[0].C == 4 || d->src[0].C == 2) &&
+           (d->out_pitch % 4 == 0) && (d->out_ch_off % 4 == 0) && d->Hin == d->Hout && d->Win == d->Wout;
 }
 
 }  // namespace
@@ -240,6 +317,7 @@ extern "C" {
 int rp_conv_nparts(const rp_conv_desc* d, int* nparts) {
     ConvArgs A;
     if (!nparts || !build_args(d, &A, BM)) return RP_ERR_INVALID_ARG;
+    if (small_cin_eligible(d)) { *nparts = (2 * d->Hout * d->Wout + 127) / 128; return RP_OK; }
     *nparts = A.nclass * A.tiles_m;
     return RP_OK;
 }
@@ -249,6 +327,13 @@ int rp_conv_layer(const rp_conv_desc* d, void* stream_) {
     if (!build_args(d, &A, BM)) return RP_ERR_INVALID_ARG;
     if (!d->W || !d->out || !d->src[0].ptr) return RP_ERR_INVALID_ARG;
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    if (small_cin_eligible(d)) {
+        dim3 grid((2 * d->Hout * d->Wout + 127) / 128, A.G);
+        if (d->src[0].C == 4) conv3x3_small_cin<4><<<grid, 128, 0, stream>>>(A);
+        else conv3x3_small_cin<2><<<grid, 128, 0, stream>>>(A);
+        ++g_conv_launches;
+        return cudaGetLastError() == cudaSuccess ? RP_OK : RP_ERR_CUDA;
+    }
     dim3 grid(A.tiles_m, (A.Cout + BN_ - 1) / BN_, A.G * A.nclass);
     conv_igemm_f32<<<grid, CT, 0, stream>>>(A);
     ++g_conv_launches;
@@ -260,8 +345,8 @@ int rp_bn_finalize(const float* psum, const float* psq, int G, int nparts, int C
                    void* stream_) {
     if (!psum || !psq || !gamma || !beta || !scale || !shift || G < 1 || nparts < 1 || Cout < 1) return RP_ERR_INVALID_ARG;
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
-    dim3 grid((Cout + 127) / 128, G);
-    bn_finalize_kernel<<<grid, 128, 0, stream>>>(psum, psq, nparts, Cout, count, gamma, beta, scale, shift, sstride, s_off);
+    dim3 grid((Cout + 7) / 8, G);                     // 8 warps per block, one warp per channel
+    bn_finalize_kernel<<<grid, 256, 0, stream>>>(psum, psq, nparts, Cout, count, gamma, beta, scale, shift, sstride, s_off);
     ++g_conv_launches;
     return cudaGetLastError() == cudaSuccess ? RP_OK : RP_ERR_CUDA;
 }
@@ -278,7 +363,7 @@ int rp_scnet_resize_in(const float* x, int n, int H, int W, float* out, void* st
 int rp_scnet_resize_out(const float* in, int n, int C, int H, int W, float* out, void* stream_) {
     if (!in || !out || n < 1) return RP_ERR_INVALID_ARG;
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
-    size_t total = (size_t)n * C * H * W;
+    size_t total = (size_t)n * H * W;
     scnet_resize_out_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(in, n, C, H, W, out);
     ++g_conv_launches;
     return cudaGetLastError() == cudaSuccess ? RP_OK : RP_ERR_CUDA;

@@ -173,22 +173,40 @@ __global__ void __launch_bounds__(128) gemm_bf16_test(const float* __restrict__ 
 }
 
 // ---------------------------------------------------------------------------------------------------
-// Implicit-GEMM convolution / transposed convolution on tcgen05.  One CTA = 128 output pixels (UMMA M) x BN output
-// channels of one (scan pair, sub-pixel class); K loop over (tap, source, TK-channel tile), two smem stages:
-// while the tensor core works on stage s the 128 threads gather + BatchNorm + LeakyReLU + bf16-convert the next
-// A tile (thread = pixel row: 16-byte units land conflict-free in the core-matrix layout) and copy the next
-// pre-packed weight block (already in the smem image).  tcgen05.commit -> mbarrier frees a stage.  Epilogue:
-// TMEM -> registers -> raw fp32 NHWC output (+bias/tanh for the 1x1 heads) and per-channel partial batch
+// Implicit-GEMM convolution / transposed convolution on tcgen05.  One CTA (256 threads) = 128 output pixels (UMMA M)
+// x BN output channels of one (scan pair, sub-pixel class); K loop over (tap, source, TK-channel tile) with NS=3
+// shared-memory stages:
+//   * B (weights): pre-packed on the host in the UMMA smem image, fetched by ONE thread with cp.async.bulk
+//     (1-D TMA, completion on an mbarrier via complete_tx), issued one iteration ahead;
+//   * A (activations): gathered by all 256 threads (2 per pixel row, TK/2 channels each) with the producer's
+//     BatchNorm + LeakyReLU applied on the fly, converted to bf16 and written as 16-byte core-matrix rows;
+//   * one thread issues tcgen05.mma; tcgen05.commit -> mbarrier frees the stage.
+// Epilogue: TMEM -> registers -> raw fp32 NHWC output (+bias/tanh for the 1x1 heads) and per-channel partial batch
 // statistics through a padded smem transpose (fixed summation order).
+constexpr int NS = 3;
+constexpr int CTA = 256;
+
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
 template <int BN, int TK>
-__global__ void __launch_bounds__(128) conv_igemm_tc(const scnet::ConvArgs A, const unsigned char* __restrict__ Wp,
+__global__ void __launch_bounds__(CTA) conv_igemm_tc(const scnet::ConvArgs A, const unsigned char* __restrict__ Wp,
                                                       int nkt, int ntn) {
     extern __shared__ __align__(128) unsigned char smem[];
     constexpr int A_BYTES = TM * TK * 2, B_BYTES = BN * TK * 2, STAGE = A_BYTES + B_BYTES;
-    __shared__ __align__(8) uint64_t bar[2];
+    constexpr int HALF_KC = TK / 16;                      // 16-byte core rows per thread and stage
+    __shared__ __align__(8) uint64_t empty_bar[NS];
+    __shared__ __align__(8) uint64_t fullb_bar[NS];
     __shared__ uint32_t tmem_slot;
-    __shared__ float red_s[4][32], red_q[4][32];
-    const int tid = threadIdx.x, warp = tid >> 5;
+    __shared__ float red_s[8][32], red_q[8][32];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int row = ((warp & 3) << 5) + lane;             // pixel row of the tile == TMEM lane
+    const int half = warp >> 2;                           // which half of the TK channels this thread stages
     const int tile_m = blockIdx.x, tile_n = blockIdx.y;
     const int g = blockIdx.z / A.nclass, ci = blockIdx.z - g * A.nclass;
     const scnet::ConvClass& C = A.cls[ci];
@@ -202,133 +220,155 @@ __global__ void __launch_bounds__(128) conv_igemm_tc(const scnet::ConvArgs A, co
         }
         return;
     }
-    const int m_l = tile_m * TM + tid;
+    const int m_l = tile_m * TM + row;
     const bool mval = m_l < Mc;
     int img_l = 0, a_l = 0, b_l = 0;
     if (mval) { int im = m_l / HW; int rem = m_l - im * HW; img_l = g * 2 + im; a_l = rem / C.Wb; b_l = rem - a_l * C.Wb; }
 
-    if (tid == 0) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); fence_mbar_init(); }
+    if (tid == 0) {
+#pragma unroll
+        for (int i = 0; i < NS; ++i) { mbar_init(&empty_bar[i], 1); mbar_init(&fullb_bar[i], 1); }
+        fence_mbar_init();
+    }
     if (warp == 0) tmem_alloc(&tmem_slot, BN);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_d = tmem_slot;
     const uint32_t idesc = make_idesc_bf16(TM, BN);
+    const int nkt0 = A.src[0].C / TK;
+    const int niter = C.ntap * nkt;
 
-    int it = 0;
-    for (int t = 0; t < C.ntap; ++t) {
-        const scnet::Tap tp = C.taps[t];
-        const int iy = a_l * A.istr + tp.dy, ix = b_l * A.istr + tp.dx;
-        const bool inb = mval && iy >= 0 && iy < A.Hin && ix >= 0 && ix < A.Win;
-        const size_t pix = ((size_t)img_l * A.Hin + iy) * A.Win + ix;
-        int kt = 0;
-        for (int s = 0; s < A.nsrc; ++s) {
-            const rp_conv_src& S = A.src[s];
-            for (int c0 = 0; c0 < S.C; c0 += TK, ++kt, ++it) {
-                const int stage = it & 1;
-                unsigned char* sA = smem + stage * STAGE;
-                unsigned char* sB = sA + A_BYTES;
-                mbar_wait(&bar[stage], (uint32_t)(((it >> 1) & 1) ^ 1));      // MMAs that read this stage are done
-                // ---- A tile: my pixel, TK consecutive channels
-                if (inb) {
-                    const float* p = S.ptr + pix * S.pitch + S.ch_off + c0;
-                    const float* sc = S.scale + (size_t)g * S.sstride + S.s_off + c0;
-                    const float* sh = S.shift + (size_t)g * S.sstride + S.s_off + c0;
+    auto weight_block = [&](int i) -> const unsigned char* {
+        const int t = i / nkt, kt = i - t * nkt;
+        return Wp + ((size_t)((size_t)C.taps[t].widx * nkt + kt) * ntn + tile_n) * B_BYTES;
+    };
+    if (tid == 0) {                                       // prologue: weights of iteration 0
+        mbar_expect_tx(&fullb_bar[0], B_BYTES);
+        bulk_g2s(smem + A_BYTES, weight_block(0), B_BYTES, &fullb_bar[0]);
+    }
+
+    int t_cur = -1;
+    bool inb = false;
+    size_t pix = 0;
+    for (int i = 0; i < niter; ++i) {
+        const int stage = i % NS, use = i / NS;
+        unsigned char* sA = smem + stage * STAGE;
+        unsigned char* sB = sA + A_BYTES;
+        if (tid == 0 && i + 1 < niter) {                  // prefetch the next iteration's weight block
+            const int s1 = (i + 1) % NS, u1 = (i + 1) / NS;
+            mbar_wait(&empty_bar[s1], (uint32_t)((u1 & 1) ^ 1));
+            mbar_expect_tx(&fullb_bar[s1], B_BYTES);
+            bulk_g2s(smem + s1 * STAGE + A_BYTES, weight_block(i + 1), B_BYTES, &fullb_bar[s1]);
+        }
+        const int t = i / nkt, kt = i - t * nkt;
+        if (t != t_cur) {
+            t_cur = t;
+            const scnet::Tap tp = C.taps[t];
+            const int iy = a_l * A.istr + tp.dy, ix = b_l * A.istr + tp.dx;
+            inb = mval && iy >= 0 && iy < A.Hin && ix >= 0 && ix < A.Win;
+            pix = ((size_t)img_l * A.Hin + iy) * A.Win + ix;
+        }
+        const int si = kt < nkt0 ? 0 : 1;
+        const rp_conv_src& S = A.src[si];
+        const int c0 = (kt - (si ? nkt0 : 0)) * TK + half * (TK / 2);
+        mbar_wait(&empty_bar[stage], (uint32_t)((use & 1) ^ 1));     // MMAs that read this stage are done
+        // ---- A: my pixel row, TK/2 consecutive channels
+        if (inb) {
+            const float* p = S.ptr + pix * S.pitch + S.ch_off + c0;
+            const float* sc = S.scale + (size_t)g * S.sstride + S.s_off + c0;
+            const float* sh = S.shift + (size_t)g * S.sstride + S.s_off + c0;
+            float4 x[HALF_KC * 2];
 #pragma unroll
-                    for (int kc = 0; kc < TK / 8; ++kc) {
-                        float4 x = *reinterpret_cast<const float4*>(p + kc * 8);
-                        float4 y = *reinterpret_cast<const float4*>(p + kc * 8 + 4);
-                        float v[8] = {x.x, x.y, x.z, x.w, y.x, y.y, y.z, y.w};
-                        if (S.act) {
-                            float4 s0 = *reinterpret_cast<const float4*>(sc + kc * 8), s1 = *reinterpret_cast<const float4*>(sc + kc * 8 + 4);
-                            float4 h0 = *reinterpret_cast<const float4*>(sh + kc * 8), h1 = *reinterpret_cast<const float4*>(sh + kc * 8 + 4);
-                            const float sv[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
-                            const float hv[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+            for (int q = 0; q < HALF_KC * 2; ++q) x[q] = *reinterpret_cast<const float4*>(p + q * 4);     // all loads first
 #pragma unroll
-                            for (int j = 0; j < 8; ++j) { float z = fmaf(v[j], sv[j], hv[j]); v[j] = z > 0.f ? z : scnet::LEAKY * z; }
-                        }
-                        store_core_row(sA, TM, tid, kc, v);
-                    }
-                } else {
-                    const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+            for (int kc = 0; kc < HALF_KC; ++kc) {
+                float v[8] = {x[2 * kc].x, x[2 * kc].y, x[2 * kc].z, x[2 * kc].w, x[2 * kc + 1].x, x[2 * kc + 1].y, x[2 * kc + 1].z, x[2 * kc + 1].w};
+                if (S.act) {
+                    float4 s0 = *reinterpret_cast<const float4*>(sc + kc * 8), s1 = *reinterpret_cast<const float4*>(sc + kc * 8 + 4);
+                    float4 h0 = *reinterpret_cast<const float4*>(sh + kc * 8), h1 = *reinterpret_cast<const float4*>(sh + kc * 8 + 4);
+                    const float sv[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+                    const float hv[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
 #pragma unroll
-                    for (int kc = 0; kc < TK / 8; ++kc)
-                        *reinterpret_cast<uint4*>(sA + ((kc * (TM >> 3) + (tid >> 3)) * 8 + (tid & 7)) * 16) = z;
+                    for (int j = 0; j < 8; ++j) { float z = fmaf(v[j], sv[j], hv[j]); v[j] = z > 0.f ? z : scnet::LEAKY * z; }
                 }
-                // ---- B tile: pre-packed block (tap, k-tile, n-tile), already in the smem image
-                {
-                    const uint4* src = reinterpret_cast<const uint4*>(Wp + ((size_t)((size_t)tp.widx * nkt + kt) * ntn + tile_n) * B_BYTES);
-                    uint4* dst = reinterpret_cast<uint4*>(sB);
-#pragma unroll
-                    for (int i = 0; i < B_BYTES / 16 / 128; ++i) dst[i * 128 + tid] = src[i * 128 + tid];
-                    if ((B_BYTES / 16) % 128) { int i = (B_BYTES / 16 / 128) * 128 + tid; if (i < B_BYTES / 16) dst[i] = src[i]; }
-                }
-                fence_async_smem();
-                __syncthreads();
-                if (tid == 0) {
-                    tc_fence_after();
-                    const uint32_t a0 = smem_u32(sA), b0 = smem_u32(sB);
-#pragma unroll
-                    for (int j = 0; j < TK / 16; ++j) {
-                        uint64_t ad = make_smem_desc(a0 + j * 2 * (TM / 8) * 128, (TM / 8) * 128, 128);
-                        uint64_t bd = make_smem_desc(b0 + j * 2 * (BN / 8) * 128, (BN / 8) * 128, 128);
-                        umma_bf16(tmem_d, ad, bd, idesc, (it > 0 || j > 0) ? 1u : 0u);
-                    }
-                    umma_commit(&bar[stage]);
-                }
+                store_core_row(sA, TM, row, half * HALF_KC + kc, v);
             }
+        } else {
+            const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+            for (int kc = 0; kc < HALF_KC; ++kc)
+                *reinterpret_cast<uint4*>(sA + (((half * HALF_KC + kc) * (TM >> 3) + (row >> 3)) * 8 + (row & 7)) * 16) = z;
+        }
+        fence_async_smem();
+        __syncthreads();
+        if (tid == 0) {
+            mbar_wait(&fullb_bar[stage], (uint32_t)(use & 1));      // this stage's weight block has landed
+            tc_fence_after();
+            const uint32_t a0 = smem_u32(sA), b0 = smem_u32(sB);
+#pragma unroll
+            for (int j = 0; j < TK / 16; ++j) {
+                uint64_t ad = make_smem_desc(a0 + j * 2 * (TM / 8) * 128, (TM / 8) * 128, 128);
+                uint64_t bd = make_smem_desc(b0 + j * 2 * (BN / 8) * 128, (BN / 8) * 128, 128);
+                umma_bf16(tmem_d, ad, bd, idesc, (i > 0 || j > 0) ? 1u : 0u);
+            }
+            umma_commit(&empty_bar[stage]);
         }
     }
-    // drain: the last commit covers every MMA issued before it
-    {
-        const int last = it - 1;
-        mbar_wait(&bar[last & 1], (uint32_t)((last >> 1) & 1));
+    {   // drain: the last commit covers every MMA issued before it
+        const int last = niter - 1;
+        mbar_wait(&empty_bar[last % NS], (uint32_t)((last / NS) & 1));
     }
     tc_fence_after();
     __syncthreads();           // every thread is past the mainloop: stage memory can be reused
 
-    // ---- epilogue
+    // ---- epilogue (warps 0-3 own the TMEM lanes; all 8 warps help with the column sums)
     float* Tt = reinterpret_cast<float*>(smem);            // [128][33] transpose buffer
     float* op = nullptr;
-    if (mval) {
+    if (warp < 4 && mval) {
         const int im = m_l / HW;
         const int oy = a_l * A.ostr + C.py, ox = b_l * A.ostr + C.px;
         op = A.out + (((size_t)(g * 2 + im) * A.Hout + oy) * A.Wout + ox) * A.out_pitch + A.out_ch_off;
     }
     for (int c0 = 0; c0 < BN; c0 += 32) {
-        float v[32];
-        tmem_ld32(tmem_d + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);
         const int co0 = tile_n * BN + c0;
-        if (A.bias || A.tanh_out) {
+        if (warp < 4) {
+            float v[32];
+            tmem_ld32(tmem_d + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);
+            if (A.bias || A.tanh_out) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-                if (co0 + j < A.Cout) { float y = v[j] + (A.bias ? A.bias[co0 + j] : 0.f); v[j] = A.tanh_out ? tanhf(y) : y; }
+                for (int j = 0; j < 32; ++j) {
+                    if (co0 + j < A.Cout) { float y = v[j] + (A.bias ? A.bias[co0 + j] : 0.f); v[j] = A.tanh_out ? tanhf(y) : y; }
+                }
             }
-        }
-        if (op) {
-            if (co0 + 31 < A.Cout && (((size_t)(op + co0)) & 15) == 0) {
+            if (op) {
+                if (co0 + 31 < A.Cout && (((size_t)(op + co0)) & 15) == 0) {
 #pragma unroll
-                for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(op + co0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-            } else {
+                    for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(op + co0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                } else {
 #pragma unroll
-                for (int j = 0; j < 32; ++j) if (co0 + j < A.Cout) op[co0 + j] = v[j];
+                    for (int j = 0; j < 32; ++j) if (co0 + j < A.Cout) op[co0 + j] = v[j];
+                }
+            }
+            if (A.psum) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) Tt[row * 33 + j] = v[j];          // rows of invalid pixels are exact zeros
             }
         }
         if (A.psum) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) Tt[tid * 33 + j] = v[j];          // rows of invalid pixels are exact zeros
             __syncthreads();
             {
-                const int col = tid & 31, part = tid >> 5;
+                const int col = tid & 31, part = tid >> 5;                      // 8 parts of 16 rows
                 float s1 = 0.f, s2 = 0.f;
-#pragma unroll 8
-                for (int r = 0; r < 32; ++r) { float x = Tt[(part * 32 + r) * 33 + col]; s1 += x; s2 += x * x; }
+#pragma unroll
+                for (int r = 0; r < 16; ++r) { float x = Tt[(part * 16 + r) * 33 + col]; s1 += x; s2 += x * x; }
                 red_s[part][col] = s1; red_q[part][col] = s2;
             }
             __syncthreads();
             if (tid < 32 && co0 + tid < A.Cout) {
-                float s1 = ((red_s[0][tid] + red_s[1][tid]) + red_s[2][tid]) + red_s[3][tid];
-                float s2 = ((red_q[0][tid] + red_q[1][tid]) + red_q[2][tid]) + red_q[3][tid];
+                float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+                for (int r = 0; r < 8; ++r) { s1 += red_s[r][tid]; s2 += red_q[r][tid]; }
                 A.psum[(size_t)part_row * A.Cout + co0 + tid] = s1;
                 A.psq[(size_t)part_row * A.Cout + co0 + tid] = s2;
             }
@@ -343,12 +383,12 @@ __global__ void __launch_bounds__(128) conv_igemm_tc(const scnet::ConvArgs A, co
 template <int BN, int TK>
 int launch_conv_tc(const scnet::ConvArgs& A, const void* wp, int nkt, cudaStream_t stream) {
     const int ntn = (A.Cout + BN - 1) / BN;
-    size_t pipe = 2 * (size_t)(TM * TK * 2 + BN * TK * 2), tr = (size_t)128 * 33 * 4;
+    size_t pipe = (size_t)NS * (size_t)(TM * TK * 2 + BN * TK * 2), tr = (size_t)128 * 33 * 4;
     size_t smem = pipe > tr ? pipe : tr;
     auto kern = conv_igemm_tc<BN, TK>;
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { cudaGetLastError(); return RP_ERR_CUDA; }
     dim3 grid(A.tiles_m, ntn, A.G * A.nclass);
-    kern<<<grid, 128, smem, stream>>>(A, static_cast<const unsigned char*>(wp), nkt, ntn);
+    kern<<<grid, CTA, smem, stream>>>(A, static_cast<const unsigned char*>(wp), nkt, ntn);
     ++scnet::g_conv_launches;
     return cudaGetLastError() == cudaSuccess ? RP_OK : RP_ERR_CUDA;
 }

@@ -50,6 +50,10 @@ class ScnetEngine(object):
         import torch
         # 'tc': tcgen05 bf16 tensor-core kernels wherever a layer qualifies (default); 'fp32': CUDA-core float32 only
         self.mode = mode or os.environ.get("RP_SCNET_MODE", "tc")
+        # replay the ~87 layer launches of a forward as one CUDA graph once a shape has been seen twice
+        self.use_graph = os.environ.get("RP_SCNET_GRAPH", "1") == "1"
+        self._graphs = {}
+        self._seen = {}
         self.torch = torch
         self.net = net
         self.lib = _lib.load()
@@ -169,6 +173,29 @@ class ScnetEngine(object):
 
     # ---------------------------------------------------------------- forward
     def forward(self, x, trace=None):
+        torch = self.torch
+        if self.use_graph and trace is None and x.is_cuda and x.dim() == 4:
+            key = (tuple(x.shape), str(x.device), self.mode, tuple((p.data_ptr(), p._version) for p in self.net.parameters()))
+            ent = self._graphs.get(key)
+            if ent is not None:
+                gph, xs, ys = ent
+                xs.copy_(x)
+                gph.replay()
+                return ys.clone()
+            self._seen[key] = self._seen.get(key, 0) + 1
+            if self._seen[key] == 3:              # two eager runs have warmed every buffer: capture the third
+                xs = x.contiguous().float().clone()
+                with torch.cuda.device(x.device):
+                    torch.cuda.synchronize()
+                    gph = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(gph):
+                        ys = self._forward_eager(xs, None)
+                self._graphs = {key: (gph, xs, ys)}       # one cached graph (buffers are shared between shapes)
+                gph.replay()
+                return ys.clone()
+        return self._forward_eager(x, trace)
+
+    def _forward_eager(self, x, trace=None):
         torch = self.torch
         if not x.is_cuda:
             raise RuntimeError("relativepose_b200.SCNet.forward needs a CUDA tensor (no CPU fallback)")
