@@ -194,19 +194,28 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
                  ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
+// A-tile geometry: K-core stride (LBO) padded by 16 bytes so that the 8 lanes that stage the 8 K-cores of one pixel
+// row hit 8 different 16-byte bank groups (conflict-free STS.128) while reading one contiguous 256-byte run of global.
+constexpr int A_LBO = (TM / 8) * 128 + 16;
+constexpr int MAX_CIN = 1536;
+
 template <int BN, int TK>
-__global__ void __launch_bounds__(CTA) conv_igemm_tc(const scnet::ConvArgs A, const unsigned char* __restrict__ Wp,
-                                                      int nkt, int ntn) {
+__global__ void __launch_bounds__(CTA, 2) conv_igemm_tc(const scnet::ConvArgs A, const unsigned char* __restrict__ Wp,
+                                                         int nkt, int ntn) {
     extern __shared__ __align__(128) unsigned char smem[];
-    constexpr int A_BYTES = TM * TK * 2, B_BYTES = BN * TK * 2, STAGE = A_BYTES + B_BYTES;
-    constexpr int HALF_KC = TK / 16;                      // 16-byte core rows per thread and stage
+    constexpr int KC = TK / 8;                            // 16-byte core rows (8 channels) per pixel row and stage
+    constexpr int A_BYTES = ((KC * A_LBO + 127) / 128) * 128, B_BYTES = BN * TK * 2, STAGE = A_BYTES + B_BYTES;
+    constexpr int NI = (TM * KC) / CTA;                   // (pixel row, core) items per thread and stage
+    constexpr int ROWS_PER_PASS = CTA / KC;
     __shared__ __align__(8) uint64_t empty_bar[NS];
     __shared__ __align__(8) uint64_t fullb_bar[NS];
     __shared__ uint32_t tmem_slot;
     __shared__ float red_s[8][32], red_q[8][32];
+    __shared__ __align__(16) float s_sc[MAX_CIN], s_sh[MAX_CIN];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int row = ((warp & 3) << 5) + lane;             // pixel row of the tile == TMEM lane
-    const int half = warp >> 2;                           // which half of the TK channels this thread stages
+    const int row = ((warp & 3) << 5) + lane;             // epilogue: pixel row of the tile == TMEM lane (warps 0-3)
+    const int kc_l = tid % KC;                            // loader: which 8-channel core of the K tile
+    const int prow0 = tid / KC;                           // loader: first pixel row (then += ROWS_PER_PASS)
     const int tile_m = blockIdx.x, tile_n = blockIdx.y;
     const int g = blockIdx.z / A.nclass, ci = blockIdx.z - g * A.nclass;
     const scnet::ConvClass& C = A.cls[ci];
@@ -220,11 +229,26 @@ __global__ void __launch_bounds__(CTA) conv_igemm_tc(const scnet::ConvArgs A, co
         }
         return;
     }
-    const int m_l = tile_m * TM + row;
-    const bool mval = m_l < Mc;
-    int img_l = 0, a_l = 0, b_l = 0;
-    if (mval) { int im = m_l / HW; int rem = m_l - im * HW; img_l = g * 2 + im; a_l = rem / C.Wb; b_l = rem - a_l * C.Wb; }
-
+    // loader pixel coordinates (NI rows per thread)
+    int l_img[NI], l_a[NI], l_b[NI]; bool l_val[NI];
+#pragma unroll
+    for (int j = 0; j < NI; ++j) {
+        const int m = tile_m * TM + prow0 + j * ROWS_PER_PASS;
+        l_val[j] = m < Mc; l_img[j] = 0; l_a[j] = 0; l_b[j] = 0;
+        if (l_val[j]) { int im = m / HW; int rem = m - im * HW; l_img[j] = g * 2 + im; l_a[j] = rem / C.Wb; l_b[j] = rem - l_a[j] * C.Wb; }
+    }
+    // producer BN scale/shift of every input channel of this group, once
+    {
+        int cb = 0;
+        for (int si = 0; si < A.nsrc; ++si) {
+            const rp_conv_src& S = A.src[si];
+            for (int c = tid; c < S.C; c += CTA) {
+                s_sc[cb + c] = S.act ? S.scale[(size_t)g * S.sstride + S.s_off + c] : 1.f;
+                s_sh[cb + c] = S.act ? S.shift[(size_t)g * S.sstride + S.s_off + c] : 0.f;
+            }
+            cb += S.C;
+        }
+    }
     if (tid == 0) {
 #pragma unroll
         for (int i = 0; i < NS; ++i) { mbar_init(&empty_bar[i], 1); mbar_init(&fullb_bar[i], 1); }
@@ -248,57 +272,63 @@ __global__ void __launch_bounds__(CTA) conv_igemm_tc(const scnet::ConvArgs A, co
         bulk_g2s(smem + A_BYTES, weight_block(0), B_BYTES, &fullb_bar[0]);
     }
 
-    int t_cur = -1;
-    bool inb = false;
-    size_t pix = 0;
+    // raw A registers for the current and the next iteration (software pipelining of the gather)
+    float4 xc[NI][2], xn[NI][2];
+    bool vc[NI], vn[NI];
+    auto issue_loads = [&](int i, float4 (&x)[NI][2], bool (&v)[NI]) {
+        const int t = i / nkt, kt = i - t * nkt;
+        const scnet::Tap tp = C.taps[t];
+        const int si = kt < nkt0 ? 0 : 1;
+        const rp_conv_src& S = A.src[si];
+        const int c0 = (kt - (si ? nkt0 : 0)) * TK + kc_l * 8;
+#pragma unroll
+        for (int j = 0; j < NI; ++j) {
+            const int iy = l_a[j] * A.istr + tp.dy, ix = l_b[j] * A.istr + tp.dx;
+            v[j] = l_val[j] && iy >= 0 && iy < A.Hin && ix >= 0 && ix < A.Win;
+            if (v[j]) {
+                const float* p = S.ptr + (((size_t)l_img[j] * A.Hin + iy) * A.Win + ix) * S.pitch + S.ch_off + c0;
+                x[j][0] = *reinterpret_cast<const float4*>(p);
+                x[j][1] = *reinterpret_cast<const float4*>(p + 4);
+            }
+        }
+    };
+    issue_loads(0, xc, vc);
+
     for (int i = 0; i < niter; ++i) {
         const int stage = i % NS, use = i / NS;
         unsigned char* sA = smem + stage * STAGE;
         unsigned char* sB = sA + A_BYTES;
-        if (tid == 0 && i + 1 < niter) {                  // prefetch the next iteration's weight block
+        if (tid == 0 && i + 1 < niter) {                  // prefetch the next iteration's weight block (bulk TMA)
             const int s1 = (i + 1) % NS, u1 = (i + 1) / NS;
             mbar_wait(&empty_bar[s1], (uint32_t)((u1 & 1) ^ 1));
             mbar_expect_tx(&fullb_bar[s1], B_BYTES);
             bulk_g2s(smem + s1 * STAGE + A_BYTES, weight_block(i + 1), B_BYTES, &fullb_bar[s1]);
         }
-        const int t = i / nkt, kt = i - t * nkt;
-        if (t != t_cur) {
-            t_cur = t;
-            const scnet::Tap tp = C.taps[t];
-            const int iy = a_l * A.istr + tp.dy, ix = b_l * A.istr + tp.dx;
-            inb = mval && iy >= 0 && iy < A.Hin && ix >= 0 && ix < A.Win;
-            pix = ((size_t)img_l * A.Hin + iy) * A.Win + ix;
-        }
-        const int si = kt < nkt0 ? 0 : 1;
-        const rp_conv_src& S = A.src[si];
-        const int c0 = (kt - (si ? nkt0 : 0)) * TK + half * (TK / 2);
+        if (i + 1 < niter) issue_loads(i + 1, xn, vn);    // next A gather in flight while this tile is transformed
+        const int kt = i % nkt;
+        const int cb = kt * TK + kc_l * 8;                // channel index into s_sc/s_sh (sources are concatenated)
+        const float4 s0 = *reinterpret_cast<const float4*>(&s_sc[cb]), s1v = *reinterpret_cast<const float4*>(&s_sc[cb + 4]);
+        const float4 h0 = *reinterpret_cast<const float4*>(&s_sh[cb]), h1 = *reinterpret_cast<const float4*>(&s_sh[cb + 4]);
+        const float sv[8] = {s0.x, s0.y, s0.z, s0.w, s1v.x, s1v.y, s1v.z, s1v.w};
+        const float hv[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+        const bool act = A.src[kt < nkt0 ? 0 : 1].act != 0;
         mbar_wait(&empty_bar[stage], (uint32_t)((use & 1) ^ 1));     // MMAs that read this stage are done
-        // ---- A: my pixel row, TK/2 consecutive channels
-        if (inb) {
-            const float* p = S.ptr + pix * S.pitch + S.ch_off + c0;
-            const float* sc = S.scale + (size_t)g * S.sstride + S.s_off + c0;
-            const float* sh = S.shift + (size_t)g * S.sstride + S.s_off + c0;
-            float4 x[HALF_KC * 2];
 #pragma unroll
-            for (int q = 0; q < HALF_KC * 2; ++q) x[q] = *reinterpret_cast<const float4*>(p + q * 4);     // all loads first
+        for (int j = 0; j < NI; ++j) {
+            const int prow = prow0 + j * ROWS_PER_PASS;
+            uint4 u = make_uint4(0u, 0u, 0u, 0u);
+            if (vc[j]) {
+                float v[8] = {xc[j][0].x, xc[j][0].y, xc[j][0].z, xc[j][0].w, xc[j][1].x, xc[j][1].y, xc[j][1].z, xc[j][1].w};
+                if (act) {
 #pragma unroll
-            for (int kc = 0; kc < HALF_KC; ++kc) {
-                float v[8] = {x[2 * kc].x, x[2 * kc].y, x[2 * kc].z, x[2 * kc].w, x[2 * kc + 1].x, x[2 * kc + 1].y, x[2 * kc + 1].z, x[2 * kc + 1].w};
-                if (S.act) {
-                    float4 s0 = *reinterpret_cast<const float4*>(sc + kc * 8), s1 = *reinterpret_cast<const float4*>(sc + kc * 8 + 4);
-                    float4 h0 = *reinterpret_cast<const float4*>(sh + kc * 8), h1 = *reinterpret_cast<const float4*>(sh + kc * 8 + 4);
-                    const float sv[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
-                    const float hv[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) { float z = fmaf(v[j], sv[j], hv[j]); v[j] = z > 0.f ? z : scnet::LEAKY * z; }
+                    for (int q = 0; q < 8; ++q) { float z = fmaf(v[q], sv[q], hv[q]); v[q] = z > 0.f ? z : scnet::LEAKY * z; }
                 }
-                store_core_row(sA, TM, row, half * HALF_KC + kc, v);
+                __nv_bfloat162 p0 = __floats2bfloat162_rn(v[0], v[1]), p1 = __floats2bfloat162_rn(v[2], v[3]);
+                __nv_bfloat162 p2 = __floats2bfloat162_rn(v[4], v[5]), p3 = __floats2bfloat162_rn(v[6], v[7]);
+                u.x = *reinterpret_cast<uint32_t*>(&p0); u.y = *reinterpret_cast<uint32_t*>(&p1);
+                u.z = *reinterpret_cast<uint32_t*>(&p2); u.w = *reinterpret_cast<uint32_t*>(&p3);
             }
-        } else {
-            const uint4 z = make_uint4(0u, 0u, 0u, 0u);
-#pragma unroll
-            for (int kc = 0; kc < HALF_KC; ++kc)
-                *reinterpret_cast<uint4*>(sA + (((half * HALF_KC + kc) * (TM >> 3) + (row >> 3)) * 8 + (row & 7)) * 16) = z;
+            *reinterpret_cast<uint4*>(sA + kc_l * A_LBO + (prow >> 3) * 128 + (prow & 7) * 16) = u;
         }
         fence_async_smem();
         __syncthreads();
@@ -308,12 +338,14 @@ __global__ void __launch_bounds__(CTA) conv_igemm_tc(const scnet::ConvArgs A, co
             const uint32_t a0 = smem_u32(sA), b0 = smem_u32(sB);
 #pragma unroll
             for (int j = 0; j < TK / 16; ++j) {
-                uint64_t ad = make_smem_desc(a0 + j * 2 * (TM / 8) * 128, (TM / 8) * 128, 128);
+                uint64_t ad = make_smem_desc(a0 + j * 2 * A_LBO, A_LBO, 128);
                 uint64_t bd = make_smem_desc(b0 + j * 2 * (BN / 8) * 128, (BN / 8) * 128, 128);
                 umma_bf16(tmem_d, ad, bd, idesc, (i > 0 || j > 0) ? 1u : 0u);
             }
             umma_commit(&empty_bar[stage]);
         }
+#pragma unroll
+        for (int j = 0; j < NI; ++j) { xc[j][0] = xn[j][0]; xc[j][1] = xn[j][1]; vc[j] = vn[j]; }
     }
     {   // drain: the last commit covers every MMA issued before it
         const int last = niter - 1;
@@ -325,10 +357,13 @@ __global__ void __launch_bounds__(CTA) conv_igemm_tc(const scnet::ConvArgs A, co
     // ---- epilogue (warps 0-3 own the TMEM lanes; all 8 warps help with the column sums)
     float* Tt = reinterpret_cast<float*>(smem);            // [128][33] transpose buffer
     float* op = nullptr;
-    if (warp < 4 && mval) {
-        const int im = m_l / HW;
-        const int oy = a_l * A.ostr + C.py, ox = b_l * A.ostr + C.px;
-        op = A.out + (((size_t)(g * 2 + im) * A.Hout + oy) * A.Wout + ox) * A.out_pitch + A.out_ch_off;
+    if (warp < 4) {
+        const int m_l = tile_m * TM + row;
+        if (m_l < Mc) {
+            const int im = m_l / HW; const int rem = m_l - im * HW; const int a_l = rem / C.Wb, b_l = rem - a_l * C.Wb;
+            const int oy = a_l * A.ostr + C.py, ox = b_l * A.ostr + C.px;
+            op = A.out + (((size_t)(g * 2 + im) * A.Hout + oy) * A.Wout + ox) * A.out_pitch + A.out_ch_off;
+        }
     }
     for (int c0 = 0; c0 < BN; c0 += 32) {
         const int co0 = tile_n * BN + c0;
@@ -383,7 +418,7 @@ __global__ void __launch_bounds__(CTA) conv_igemm_tc(const scnet::ConvArgs A, co
 template <int BN, int TK>
 int launch_conv_tc(const scnet::ConvArgs& A, const void* wp, int nkt, cudaStream_t stream) {
     const int ntn = (A.Cout + BN - 1) / BN;
-    size_t pipe = (size_t)NS * (size_t)(TM * TK * 2 + BN * TK * 2), tr = (size_t)128 * 33 * 4;
+    size_t pipe = (size_t)NS * (size_t)((((TK / 8) * A_LBO + 127) / 128) * 128 + BN * TK * 2), tr = (size_t)128 * 33 * 4;
     size_t smem = pipe > tr ? pipe : tr;
     auto kern = conv_igemm_tc<BN, TK>;
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { cudaGetLastError(); return RP_ERR_CUDA; }
@@ -423,6 +458,7 @@ int rp_conv_layer_tc(const rp_conv_desc* d, const void* w_packed, int bn, int tk
     if (!w_packed || !scnet::build_args(d, &A, tc::TM)) return RP_ERR_INVALID_ARG;
     if (!d->out || !d->src[0].ptr) return RP_ERR_INVALID_ARG;
     int nkt = 0;
+    if (A.Cin_total > tc::MAX_CIN) return RP_ERR_UNSUPPORTED;
     for (int i = 0; i < d->nsrc; ++i) {
         if (d->src[i].C % tk || (d->src[i].pitch % 4) || (d->src[i].ch_off % 4)) return RP_ERR_UNSUPPORTED;
         if (d->src[i].act && ((d->src[i].sstride % 4) || (d->src[i].s_off % 4))) return RP_ERR_UNSUPPORTED;

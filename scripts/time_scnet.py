@@ -9,11 +9,11 @@ torch.manual_seed(0)
 net = SCNet(a).cuda()
 for P in [int(v) for v in (sys.argv[1:] or ["1", "8"])]:
     x = torch.cat([torch.from_numpy(synth.make_panorama_pair(s, "suncg")) for s in range(P)], 0).cuda()
-    for _ in range(2):
+    for _ in range(5):          # includes the CUDA-graph capture on the third call
         y = net(x)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    n = 5
+    n = 10
     e0.record()
     for _ in range(n):
         y = net(x)
