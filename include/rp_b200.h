@@ -177,6 +177,8 @@ typedef struct rp_conv_src {
     const float* shift;   /* [G, sstride] per-(group, channel) BN shift  beta - mean*scale */
     int32_t sstride;
     int32_t s_off;
+    float slope;          /* negative slope of the activation applied with act=1: 0.1 = LeakyReLU (SCNet), 0 = ReLU (ResNet) */
+    int32_t reserved;
 } rp_conv_src;
 
 typedef struct rp_conv_desc {
@@ -194,14 +196,14 @@ typedef struct rp_conv_desc {
     float* psq;
     const float* bias;    /* [Cout] or NULL (the 1x1 heads, mymodel.py:188,196,204,220,228) */
     int32_t tanh_out;     /* mymodel.py:374-375 */
-    int32_t reserved;
+    int32_t imgs_per_group; /* images per BN batch: 0 or 2 = one scan pair (SCNet); Resnet18_8s uses the whole call */
 } rp_conv_desc;
 
 /* number of partial-statistics rows per group the layer writes (psum/psq are [G, nparts, Cout]) */
 int rp_conv_nparts(const rp_conv_desc* d, int* nparts);
 int rp_conv_layer(const rp_conv_desc* d, void* stream);
 /* scale/shift [G, sstride] (+s_off) from the partials: batch mean / biased variance over the 2*Hout*Wout
- * pixels of a pair, eps 1e-5 (nn.BatchNorm2d, mymodel.py:19,32) */
+ * pixels of a group (`count`), eps 1e-5 (nn.BatchNorm2d, mymodel.py:19,32) */
 int rp_bn_finalize(const float* psum, const float* psq, int G, int nparts, int Cout, int count,
                    const float* gamma, const float* beta, float* scale, float* shift, int sstride, int s_off,
                    void* stream);
@@ -212,6 +214,19 @@ int rp_scnet_resize_in(const float* x, int n, int H, int W, float* out, void* st
 int rp_scnet_resize_out(const float* in, int n, int C, int H, int W, float* out, void* stream);
 
 /* Kernel launch counter (number of kernels this library launched since load); bench.py reports it. */
+/* ---- Resnet18_8s extras (mymodel.py:82-122; stock ResNet-18 trunk) -------------------------------------------
+ * y = act(x*scale+shift) with per-(group,channel) BN scale/shift (NULL = identity), all tensors float32 NHWC. */
+/* relu(bn1(conv1)) followed by MaxPool2d(3, stride 2, padding 1): in [n,H,W,C] raw -> out [n,Ho,Wo,C] activated */
+int rp_bn_relu_maxpool(const float* in, int n, int H, int W, int C, int imgs_per_group,
+                       const float* scale, const float* shift, float* out, int Ho, int Wo, void* stream);
+/* BasicBlock tail: out = relu(a*sa+ha + (b*sb+hb)); sb/hb NULL = identity shortcut (b already activated) */
+int rp_bn_add_relu(const float* a, const float* sa, const float* ha, const float* b, const float* sb, const float* hb,
+                   float* out, int n, int HW, int C, int imgs_per_group, void* stream);
+/* F.upsample(src, size, 'bilinear', align_corners=False) on NHWC: dst = (accumulate ? dst : 0) + up(src) */
+int rp_resize_nhwc(const float* src, int n, int Hs, int Ws, int C, float* dst, int Hd, int Wd, int accumulate, void* stream);
+/* final F.upsample to the input size + optional tanh, NHWC [n,Hs,Ws,C] -> NCHW [n,C,H,W] (mymodel.py:111,120-121) */
+int rp_resize_to_nchw(const float* src, int n, int Hs, int Ws, int C, float* out, int H, int W, int tanh_out, void* stream);
+
 int64_t rp_launch_count(void);
 int64_t rp_conv_launch_count(void);
 

@@ -42,7 +42,8 @@ class RpDebug(ctypes.Structure):
 class RpConvSrc(ctypes.Structure):
     _fields_ = [("ptr", ctypes.c_void_p), ("pitch", ctypes.c_int32), ("ch_off", ctypes.c_int32),
                 ("C", ctypes.c_int32), ("act", ctypes.c_int32), ("scale", ctypes.c_void_p),
-                ("shift", ctypes.c_void_p), ("sstride", ctypes.c_int32), ("s_off", ctypes.c_int32)]
+                ("shift", ctypes.c_void_p), ("sstride", ctypes.c_int32), ("s_off", ctypes.c_int32),
+                ("slope", ctypes.c_float), ("reserved", ctypes.c_int32)]
 
 
 class RpConvDesc(ctypes.Structure):
@@ -52,13 +53,14 @@ class RpConvDesc(ctypes.Structure):
                 ("Cout", ctypes.c_int32), ("W", ctypes.c_void_p), ("out", ctypes.c_void_p),
                 ("out_pitch", ctypes.c_int32), ("out_ch_off", ctypes.c_int32), ("psum", ctypes.c_void_p),
                 ("psq", ctypes.c_void_p), ("bias", ctypes.c_void_p), ("tanh_out", ctypes.c_int32),
-                ("reserved", ctypes.c_int32)]
+                ("imgs_per_group", ctypes.c_int32)]
 
 
 EXPORTS = ("rp_abi_version", "rp_device_info", "rp_solve_workspace_bytes", "rp_solve_batch",
            "rp_solve_batch_ex", "rp_match_topk", "rp_launch_count",
            "rp_conv_nparts", "rp_conv_layer", "rp_bn_finalize", "rp_scnet_resize_in", "rp_scnet_resize_out",
-           "rp_conv_launch_count", "rp_tc_gemm_test", "rp_conv_nparts_tc", "rp_conv_layer_tc")
+           "rp_conv_launch_count", "rp_tc_gemm_test", "rp_conv_nparts_tc", "rp_conv_layer_tc",
+           "rp_bn_relu_maxpool", "rp_bn_add_relu", "rp_resize_nhwc", "rp_resize_to_nchw")
 
 _lib = None
 
@@ -108,6 +110,14 @@ def load():
     lib.rp_conv_nparts_tc.argtypes = [ctypes.POINTER(RpConvDesc), ctypes.POINTER(ctypes.c_int)]
     lib.rp_conv_layer_tc.restype = i32
     lib.rp_conv_layer_tc.argtypes = [ctypes.POINTER(RpConvDesc), vp, i32, i32, vp]
+    lib.rp_bn_relu_maxpool.restype = i32
+    lib.rp_bn_relu_maxpool.argtypes = [vp, i32, i32, i32, i32, i32, vp, vp, vp, i32, i32, vp]
+    lib.rp_bn_add_relu.restype = i32
+    lib.rp_bn_add_relu.argtypes = [vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, vp]
+    lib.rp_resize_nhwc.restype = i32
+    lib.rp_resize_nhwc.argtypes = [vp, i32, i32, i32, i32, vp, i32, i32, i32, vp]
+    lib.rp_resize_to_nchw.restype = i32
+    lib.rp_resize_to_nchw.argtypes = [vp, i32, i32, i32, i32, vp, i32, i32, i32, vp]
     lib.rp_tc_gemm_test.restype = i32
     lib.rp_tc_gemm_test.argtypes = [vp, vp, vp, i32, i32, i32, i32, vp]
     if lib.rp_abi_version() != 1:

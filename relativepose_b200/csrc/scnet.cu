@@ -33,7 +33,7 @@ __global__ void __launch_bounds__(CT) conv_igemm_f32(const ConvArgs A) {
     const int g = blockIdx.z / A.nclass, ci = blockIdx.z - g * A.nclass;
     const ConvClass& C = A.cls[ci];
     const int HW = C.Ha * C.Wb;
-    const int Mc = 2 * HW;
+    const int Mc = A.gsz * HW;
     const int tx = tid & 15, ty = tid >> 4;
     const int part_row = (g * A.nclass + ci) * A.tiles_m + tile_m;
     if (tile_m * BM >= Mc) {             // padded tile of a smaller class: contributes zeros to the statistics
@@ -48,7 +48,7 @@ __global__ void __launch_bounds__(CT) conv_igemm_f32(const ConvArgs A) {
     const int m_l = tile_m * BM + pm;
     const bool mval = m_l < Mc;
     int img_l = 0, a_l = 0, b_l = 0;
-    if (mval) { int im = m_l / HW; int rem = m_l - im * HW; img_l = g * 2 + im; a_l = rem / C.Wb; b_l = rem - a_l * C.Wb; }
+    if (mval) { int im = m_l / HW; int rem = m_l - im * HW; img_l = g * A.gsz + im; a_l = rem / C.Wb; b_l = rem - a_l * C.Wb; }
     // loader coordinates (B): k row kb, n quad
     const int kb = tid >> 4, nq = tid & 15;
     const int co_l = tile_n * BN_ + nq * 4;
@@ -87,7 +87,7 @@ __global__ void __launch_bounds__(CT) conv_igemm_f32(const ConvArgs A) {
 #pragma unroll
                         for (int j = 0; j < 4; ++j) if (ch + j < S.C) {
                             float y = fmaf(v[j], sc[j], sh[j]);
-                            v[j] = y > 0.f ? y : LEAKY * y;
+                            v[j] = y > 0.f ? y : S.slope * y;
                         }
                     }
                 }
@@ -134,7 +134,7 @@ __global__ void __launch_bounds__(CT) conv_igemm_f32(const ConvArgs A) {
         if (m >= Mc) continue;
         const int im = m / HW; const int rem = m - im * HW; const int a = rem / C.Wb, b = rem - a * C.Wb;
         const int oy = a * A.ostr + C.py, ox = b * A.ostr + C.px;
-        float* op = A.out + (((size_t)(g * 2 + im) * A.Hout + oy) * A.Wout + ox) * A.out_pitch + A.out_ch_off + co0;
+        float* op = A.out + (((size_t)(g * A.gsz + im) * A.Hout + oy) * A.Wout + ox) * A.out_pitch + A.out_ch_off + co0;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             if (co0 + j >= A.Cout) continue;
@@ -300,10 +300,86 @@ __global__ void __launch_bounds__(128) conv3x3_small_cin(const ConvArgs A) {
     }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Resnet18_8s extras (mymodel.py:82-122): all float32 NHWC, BN scale/shift per (group, channel).
+__global__ void bn_relu_maxpool_kernel(const float* __restrict__ in, int n, int H, int W, int C, int gsz,
+                                       const float* __restrict__ scale, const float* __restrict__ shift,
+                                       float* __restrict__ out, int Ho, int Wo) {
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t total = (size_t)n * Ho * Wo * C;
+    if (idx >= total) return;
+    const int c = (int)(idx % C); const int ox = (int)((idx / C) % Wo); const int oy = (int)((idx / ((size_t)C * Wo)) % Ho);
+    const int im = (int)(idx / ((size_t)C * Wo * Ho));
+    const int g = im / gsz;
+    const float sc = scale ? scale[(size_t)g * C + c] : 1.f, sh = shift ? shift[(size_t)g * C + c] : 0.f;
+    float m = -INFINITY;
+    for (int ky = 0; ky < 3; ++ky) {
+        const int iy = oy * 2 - 1 + ky;
+        if (iy < 0 || iy >= H) continue;
+        for (int kx = 0; kx < 3; ++kx) {
+            const int ix = ox * 2 - 1 + kx;
+            if (ix < 0 || ix >= W) continue;
+            float v = fmaf(in[(((size_t)im * H + iy) * W + ix) * C + c], sc, sh);
+            v = v > 0.f ? v : 0.f;
+            m = fmaxf(m, v);
+        }
+    }
+    out[idx] = m;
+}
+
+__global__ void bn_add_relu_kernel(const float* __restrict__ a, const float* __restrict__ sa, const float* __restrict__ ha,
+                                   const float* __restrict__ b, const float* __restrict__ sb, const float* __restrict__ hb,
+                                   float* __restrict__ out, int n, int HW, int C, int gsz) {
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t total = (size_t)n * HW * C;
+    if (idx >= total) return;
+    const int c = (int)(idx % C);
+    const int g = (int)(idx / ((size_t)C * HW)) / gsz;
+    float x = fmaf(a[idx], sa[(size_t)g * C + c], ha[(size_t)g * C + c]);
+    float y = sb ? fmaf(b[idx], sb[(size_t)g * C + c], hb[(size_t)g * C + c]) : b[idx];
+    float z = x + y;
+    out[idx] = z > 0.f ? z : 0.f;
+}
+
+__global__ void resize_nhwc_kernel(const float* __restrict__ src, int n, int Hs, int Ws, int C, float* __restrict__ dst,
+                                   int Hd, int Wd, int accumulate) {
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t total = (size_t)n * Hd * Wd * C;
+    if (idx >= total) return;
+    const int c = (int)(idx % C); const int ox = (int)((idx / C) % Wd); const int oy = (int)((idx / ((size_t)C * Wd)) % Hd);
+    const int im = (int)(idx / ((size_t)C * Wd * Hd));
+    int y0, y1, x0, x1; float ly0, ly1, lx0, lx1;
+    bilin_coord(oy, (float)Hs / (float)Hd, Hs, y0, y1, ly0, ly1);
+    bilin_coord(ox, (float)Ws / (float)Wd, Ws, x0, x1, lx0, lx1);
+    const float* p = src + (size_t)im * Hs * Ws * C + c;
+    float v = ly0 * (lx0 * p[((size_t)y0 * Ws + x0) * C] + lx1 * p[((size_t)y0 * Ws + x1) * C]) +
+              ly1 * (lx0 * p[((size_t)y1 * Ws + x0) * C] + lx1 * p[((size_t)y1 * Ws + x1) * C]);
+    dst[idx] = accumulate ? dst[idx] + v : v;
+}
+
+__global__ void resize_to_nchw_kernel(const float* __restrict__ src, int n, int Hs, int Ws, int C, float* __restrict__ out,
+                                      int H, int W, int tanh_out) {
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t total = (size_t)n * H * W;
+    if (idx >= total) return;
+    const int ox = (int)(idx % W); const int oy = (int)((idx / W) % H); const int im = (int)(idx / ((size_t)W * H));
+    int y0, y1, x0, x1; float ly0, ly1, lx0, lx1;
+    bilin_coord(oy, (float)Hs / (float)H, Hs, y0, y1, ly0, ly1);
+    bilin_coord(ox, (float)Ws / (float)W, Ws, x0, x1, lx0, lx1);
+    const float* b = src + (size_t)im * Hs * Ws * C;
+    const float* p00 = b + ((size_t)y0 * Ws + x0) * C; const float* p01 = b + ((size_t)y0 * Ws + x1) * C;
+    const float* p10 = b + ((size_t)y1 * Ws + x0) * C; const float* p11 = b + ((size_t)y1 * Ws + x1) * C;
+    float* o = out + (size_t)im * C * H * W + (size_t)oy * W + ox;
+    for (int c = 0; c < C; ++c) {
+        float v = ly0 * (lx0 * p00[c] + lx1 * p01[c]) + ly1 * (lx0 * p10[c] + lx1 * p11[c]);
+        o[(size_t)c * H * W] = tanh_out ? tanhf(v) : v;
+    }
+}
+
 inline bool small_cin_eligible(const rp_conv_desc* d) {
     return d->nsrc == 1 && !d->transposed && d->k == 3 && d->s == 1 && d->p == 1 && d->Cout == 32 && !d->bias &&
            !d->tanh_out && d->src[0].act == 0 && (d->src[0].C == 4 || d->src[0].C == 2) &&
-           (d->out_pitch % 4 == 0) && (d->out_ch_off % 4 == 0) && d->Hin == d->Hout && d->Win == d->Wout;
+           (d->out_pitch % 4 == 0) && (d->out_ch_off % 4 == 0) && d->Hin == d->Hout && d->Win == d->Wout && (d->imgs_per_group == 0 || d->imgs_per_group == 2);
 }
 
 }  // namespace
@@ -365,6 +441,44 @@ int rp_scnet_resize_out(const float* in, int n, int C, int H, int W, float* out,
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
     size_t total = (size_t)n * H * W;
     scnet_resize_out_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(in, n, C, H, W, out);
+    ++g_conv_launches;
+    return cudaGetLastError() == cudaSuccess ? RP_OK : RP_ERR_CUDA;
+}
+
+int rp_bn_relu_maxpool(const float* in, int n, int H, int W, int C, int imgs_per_group,
+                       const float* scale, const float* shift, float* out, int Ho, int Wo, void* stream_) {
+    if (!in || !out || n < 1 || imgs_per_group < 1) return RP_ERR_INVALID_ARG;
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    size_t total = (size_t)n * Ho * Wo * C;
+    bn_relu_maxpool_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(in, n, H, W, C, imgs_per_group, scale, shift, out, Ho, Wo);
+    ++g_conv_launches;
+    return cudaGetLastError() == cudaSuccess ? RP_OK : RP_ERR_CUDA;
+}
+
+int rp_bn_add_relu(const float* a, const float* sa, const float* ha, const float* b, const float* sb, const float* hb,
+                   float* out, int n, int HW, int C, int imgs_per_group, void* stream_) {
+    if (!a || !sa || !ha || !b || !out || n < 1 || imgs_per_group < 1) return RP_ERR_INVALID_ARG;
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    size_t total = (size_t)n * HW * C;
+    bn_add_relu_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(a, sa, ha, b, sb, hb, out, n, HW, C, imgs_per_group);
+    ++g_conv_launches;
+    return cudaGetLastError() == cudaSuccess ? RP_OK : RP_ERR_CUDA;
+}
+
+int rp_resize_nhwc(const float* src, int n, int Hs, int Ws, int C, float* dst, int Hd, int Wd, int accumulate, void* stream_) {
+    if (!src || !dst || n < 1) return RP_ERR_INVALID_ARG;
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    size_t total = (size_t)n * Hd * Wd * C;
+    resize_nhwc_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(src, n, Hs, Ws, C, dst, Hd, Wd, accumulate);
+    ++g_conv_launches;
+    return cudaGetLastError() == cudaSuccess ? RP_OK : RP_ERR_CUDA;
+}
+
+int rp_resize_to_nchw(const float* src, int n, int Hs, int Ws, int C, float* out, int H, int W, int tanh_out, void* stream_) {
+    if (!src || !out || n < 1) return RP_ERR_INVALID_ARG;
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    size_t total = (size_t)n * H * W;
+    resize_to_nchw_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(src, n, Hs, Ws, C, out, H, W, tanh_out);
     ++g_conv_launches;
     return cudaGetLastError() == cudaSuccess ? RP_OK : RP_ERR_CUDA;
 }

@@ -7,7 +7,7 @@
 namespace scnet {
 
 constexpr float LEAKY = 0.1f;       // mymodel.py:20,33
-constexpr int MAXTAP = 16;
+constexpr int MAXTAP = 49;          // 7x7 stem of Resnet18_8s
 constexpr double BN_EPS = 1e-5;
 
 struct Tap { int dy, dx, widx; };
@@ -18,6 +18,7 @@ struct ConvArgs {
     int nsrc;
     int G, Hin, Win, Hout, Wout, Cout, Cin_total;
     int istr, ostr, nclass, tiles_m;
+    int gsz;            // images per BN group
     ConvClass cls[4];
     const float* W;
     float* out; int out_pitch, out_ch_off;
@@ -29,7 +30,9 @@ struct ConvArgs {
 extern long long g_conv_launches;
 
 inline bool build_args(const rp_conv_desc* d, ConvArgs* A, int bm) {
-    if (!d || d->nsrc < 1 || d->nsrc > 2 || d->k < 1 || d->k > 4 || d->s < 1 || d->s > 2 || d->G < 1) return false;
+    if (!d || d->nsrc < 1 || d->nsrc > 2 || d->k < 1 || d->k > 7 || d->s < 1 || d->s > 2 || d->G < 1) return false;
+    if (d->transposed && d->k > 4) return false;
+    A->gsz = d->imgs_per_group > 0 ? d->imgs_per_group : 2;
     A->nsrc = d->nsrc;
     A->Cin_total = 0;
     for (int i = 0; i < d->nsrc; ++i) { A->src[i] = d->src[i]; A->Cin_total += d->src[i].C; }
@@ -64,7 +67,7 @@ inline bool build_args(const rp_conv_desc* d, ConvArgs* A, int bm) {
         }
     }
     int tm = 1;
-    for (int i = 0; i < A->nclass; ++i) { int t = (2 * A->cls[i].Ha * A->cls[i].Wb + bm - 1) / bm; if (t > tm) tm = t; }
+    for (int i = 0; i < A->nclass; ++i) { int t = (A->gsz * A->cls[i].Ha * A->cls[i].Wb + bm - 1) / bm; if (t > tm) tm = t; }
     A->tiles_m = tm;
     return true;
 }

@@ -220,7 +220,7 @@ __global__ void __launch_bounds__(CTA, 2) conv_igemm_tc(const scnet::ConvArgs A,
     const int g = blockIdx.z / A.nclass, ci = blockIdx.z - g * A.nclass;
     const scnet::ConvClass& C = A.cls[ci];
     const int HW = C.Ha * C.Wb;
-    const int Mc = 2 * HW;
+    const int Mc = A.gsz * HW;
     const int part_row = (g * A.nclass + ci) * A.tiles_m + tile_m;
     if (tile_m * TM >= Mc) {             // padded tile of a smaller class: zeros for the statistics
         if (A.psum && tid < BN) {
@@ -235,7 +235,7 @@ __global__ void __launch_bounds__(CTA, 2) conv_igemm_tc(const scnet::ConvArgs A,
     for (int j = 0; j < NI; ++j) {
         const int m = tile_m * TM + prow0 + j * ROWS_PER_PASS;
         l_val[j] = m < Mc; l_img[j] = 0; l_a[j] = 0; l_b[j] = 0;
-        if (l_val[j]) { int im = m / HW; int rem = m - im * HW; l_img[j] = g * 2 + im; l_a[j] = rem / C.Wb; l_b[j] = rem - l_a[j] * C.Wb; }
+        if (l_val[j]) { int im = m / HW; int rem = m - im * HW; l_img[j] = g * A.gsz + im; l_a[j] = rem / C.Wb; l_b[j] = rem - l_a[j] * C.Wb; }
     }
     // producer BN scale/shift of every input channel of this group, once
     {
@@ -312,6 +312,7 @@ __global__ void __launch_bounds__(CTA, 2) conv_igemm_tc(const scnet::ConvArgs A,
         const float sv[8] = {s0.x, s0.y, s0.z, s0.w, s1v.x, s1v.y, s1v.z, s1v.w};
         const float hv[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
         const bool act = A.src[kt < nkt0 ? 0 : 1].act != 0;
+        const float slope = A.src[kt < nkt0 ? 0 : 1].slope;
         mbar_wait(&empty_bar[stage], (uint32_t)((use & 1) ^ 1));     // MMAs that read this stage are done
 #pragma unroll
         for (int j = 0; j < NI; ++j) {
@@ -321,7 +322,7 @@ __global__ void __launch_bounds__(CTA, 2) conv_igemm_tc(const scnet::ConvArgs A,
                 float v[8] = {xc[j][0].x, xc[j][0].y, xc[j][0].z, xc[j][0].w, xc[j][1].x, xc[j][1].y, xc[j][1].z, xc[j][1].w};
                 if (act) {
 #pragma unroll
-                    for (int q = 0; q < 8; ++q) { float z = fmaf(v[q], sv[q], hv[q]); v[q] = z > 0.f ? z : scnet::LEAKY * z; }
+                    for (int q = 0; q < 8; ++q) { float z = fmaf(v[q], sv[q], hv[q]); v[q] = z > 0.f ? z : slope * z; }
                 }
                 __nv_bfloat162 p0 = __floats2bfloat162_rn(v[0], v[1]), p1 = __floats2bfloat162_rn(v[2], v[3]);
                 __nv_bfloat162 p2 = __floats2bfloat162_rn(v[4], v[5]), p3 = __floats2bfloat162_rn(v[6], v[7]);
@@ -362,7 +363,7 @@ __global__ void __launch_bounds__(CTA, 2) conv_igemm_tc(const scnet::ConvArgs A,
         if (m_l < Mc) {
             const int im = m_l / HW; const int rem = m_l - im * HW; const int a_l = rem / C.Wb, b_l = rem - a_l * C.Wb;
             const int oy = a_l * A.ostr + C.py, ox = b_l * A.ostr + C.px;
-            op = A.out + (((size_t)(g * 2 + im) * A.Hout + oy) * A.Wout + ox) * A.out_pitch + A.out_ch_off;
+            op = A.out + (((size_t)(g * A.gsz + im) * A.Hout + oy) * A.Wout + ox) * A.out_pitch + A.out_ch_off;
         }
     }
     for (int c0 = 0; c0 < BN; c0 += 32) {

@@ -81,3 +81,71 @@ class SCNet(nn.Module):
         if self._engine is None:
             self._engine = scnet_engine.ScnetEngine(self)
         return self._engine.forward(x)
+
+
+# --------------------------------------------------------------------------------------------------------------
+# Resnet18_8s (mymodel.py:41-122).  The reference builds its trunk from a *forked* torchvision
+# (README.md:11: warmspringwinds/vision, kwargs fully_conv/output_stride/remove_avg_pool_layer) that is not
+# vendored; its forward touches only conv1, bn1, relu, maxpool, layer1..4 of the stock ResNet-18 (mymodel.py:85-99).
+# The containers below reproduce the stock parameter/buffer names so checkpoints of the reference load
+# (``resnet18_32s.layer2.0.downsample.0.weight`` ...).  forward() runs the CUDA kernels; the torch sub-modules are
+# never called.
+class _BasicBlock(nn.Module):
+    expansion = 1
+
+    def __init__(self, cin, cout, stride):
+        super(_BasicBlock, self).__init__()
+        self.conv1 = nn.Conv2d(cin, cout, 3, stride, 1, bias=False)
+        self.bn1 = nn.BatchNorm2d(cout)
+        self.relu = nn.ReLU(inplace=True)
+        self.conv2 = nn.Conv2d(cout, cout, 3, 1, 1, bias=False)
+        self.bn2 = nn.BatchNorm2d(cout)
+        self.stride = stride
+        self.downsample = None
+        if stride != 1 or cin != cout:
+            self.downsample = nn.Sequential(nn.Conv2d(cin, cout, 1, stride, bias=False), nn.BatchNorm2d(cout))
+
+
+class _ResNet18Trunk(nn.Module):
+    def __init__(self, num_input):
+        super(_ResNet18Trunk, self).__init__()
+        self.conv1 = nn.Conv2d(num_input, 64, kernel_size=7, stride=2, padding=3, bias=False)     # mymodel.py:57
+        self.bn1 = nn.BatchNorm2d(64)
+        self.relu = nn.ReLU(inplace=True)
+        self.maxpool = nn.MaxPool2d(kernel_size=3, stride=2, padding=1)
+        self.layer1 = nn.Sequential(_BasicBlock(64, 64, 1), _BasicBlock(64, 64, 1))
+        self.layer2 = nn.Sequential(_BasicBlock(64, 128, 2), _BasicBlock(128, 128, 1))
+        self.layer3 = nn.Sequential(_BasicBlock(128, 256, 2), _BasicBlock(256, 256, 1))
+        self.layer4 = nn.Sequential(_BasicBlock(256, 512, 2), _BasicBlock(512, 512, 1))
+        self.fc = nn.Sequential()                                                               # mymodel.py:61
+
+
+class Resnet18_8s(nn.Module):
+    def __init__(self, args):
+        super(Resnet18_8s, self).__init__()
+        self.args = args
+        self.resnet18_32s = _ResNet18Trunk(args.num_input)
+        self.score_32s = nn.Conv2d(512, 32, kernel_size=1)
+        self.score_16s = nn.Conv2d(256, 32, kernel_size=1)
+        self.score_8s = nn.Conv2d(128, 32, kernel_size=1)
+        self._engine = None
+
+    def forward(self, x):
+        """x: [n,num_input,H,W] float32 CUDA -> [n,32,H,W].  BatchNorm uses the statistics of this call's n images
+        (the reference never puts the module in eval mode: mainPanoCompletion2view.py:132,268-274); running-stat
+        buffers are not updated."""
+        from .. import resnet_engine
+        if self._engine is None:
+            self._engine = resnet_engine.ResnetEngine(self)
+        return self._engine.forward(x)
+
+
+class segmentation_layer(nn.Module):
+    """mymodel.py:126-139: 1x1 head on the 32-d feature map (training-time auxiliary; plain torch)."""
+
+    def __init__(self, args):
+        super(segmentation_layer, self).__init__()
+        self.segm_layer = nn.Conv2d(32, args.snumclass, kernel_size=1)
+
+    def forward(self, featMap):
+        return self.segm_layer(featMap)

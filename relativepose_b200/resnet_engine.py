@@ -1,0 +1,101 @@
+"""Host-side sequencing of ``Resnet18_8s.forward`` (model/mymodel.py:82-122) over the C-ABI layer kernels."""
+import ctypes
+
+from . import _lib
+from .scnet_engine import ScnetEngine, _Act
+
+
+class ResnetEngine(ScnetEngine):
+    _slope = 0.0          # ReLU
+
+    def __init__(self, net, mode=None):
+        ScnetEngine.__init__(self, net, mode)
+        self.use_graph = False
+        self._key = None
+
+    def _pack(self):
+        torch = self.torch
+        key = tuple((p.data_ptr(), p._version) for p in self.net.parameters())
+        if key == self._packed_key:
+            return
+        W = {}
+        for name, p in self.net.named_parameters():
+            if p.dim() == 4:
+                W[name[:-7]] = p.detach().permute(2, 3, 1, 0).contiguous().float()       # conv w[co,ci,ky,kx] -> [k,k,Cin,Cout]
+        self._packed, self._packed_tc, self._packed_key = W, {}, key
+
+    def forward(self, x, trace=None):
+        torch = self.torch
+        if not x.is_cuda:
+            raise RuntimeError("relativepose_b200.Resnet18_8s.forward needs a CUDA tensor (no CPU fallback)")
+        x = x.contiguous().float()
+        n, cin, H, W = x.shape
+        net = self.net
+        tr = net.resnet18_32s
+        with torch.cuda.device(x.device), torch.no_grad():
+            self._pack()
+            self._dev = x.device
+            self._P, self._gsz = 1, n                      # one BatchNorm batch: all images of the call
+            if self._bufs.get('partials', None) is None:
+                self._bufs = {'partials': None}
+            stream = torch.cuda.current_stream().cuda_stream
+            f = dict(dtype=torch.float32, device=x.device)
+
+            def act(Hh, Ww, C, bn=True):
+                return _Act(torch.empty((n, Hh, Ww, C), **f), Hh, Ww, C, 0, C,
+                            torch.empty((1, C), **f) if bn else None, torch.empty((1, C), **f) if bn else None)
+
+            def co(h, k, s, p):
+                return (h + 2 * p - k) // s + 1
+
+            xin = _Act(x.permute(0, 2, 3, 1).contiguous(), H, W, cin, 0, cin)      # NCHW -> NHWC view of the input (plumbing)
+            H1, W1 = co(H, 7, 2, 3), co(W, 7, 2, 3)
+            c1 = act(H1, W1, 64)
+            self._conv('resnet18_32s.conv1', [xin], c1, False, 7, 2, 3, stream=stream, bn_params=(tr.bn1.weight, tr.bn1.bias))
+            H2, W2 = co(H1, 3, 2, 1), co(W1, 3, 2, 1)
+            cur = act(H2, W2, 64, bn=False)
+            _lib.check(self.lib.rp_bn_relu_maxpool(c1.buf.data_ptr(), n, H1, W1, 64, n, c1.scale.data_ptr(), c1.shift.data_ptr(),
+                                                   cur.buf.data_ptr(), H2, W2, stream), "rp_bn_relu_maxpool")
+            if trace is not None:
+                trace['pool'] = cur.buf.permute(0, 3, 1, 2).contiguous()
+            feats = {}
+            for li, cout, stride0 in ((1, 64, 1), (2, 128, 2), (3, 256, 2), (4, 512, 2)):
+                layer = getattr(tr, 'layer%d' % li)
+                for bi in range(2):
+                    blk = layer[bi]
+                    pre = 'resnet18_32s.layer%d.%d' % (li, bi)
+                    s = stride0 if bi == 0 else 1
+                    Ho, Wo = co(cur.H, 3, s, 1), co(cur.W, 3, s, 1)
+                    r1 = act(Ho, Wo, cout)
+                    self._conv(pre + '.conv1', [cur], r1, False, 3, s, 1, stream=stream, bn_params=(blk.bn1.weight, blk.bn1.bias))
+                    r2 = act(Ho, Wo, cout)
+                    self._conv(pre + '.conv2', [r1], r2, False, 3, 1, 1, stream=stream, bn_params=(blk.bn2.weight, blk.bn2.bias))
+                    out = act(Ho, Wo, cout, bn=False)
+                    if blk.downsample is not None:
+                        rd = act(Ho, Wo, cout)
+                        self._conv(pre + '.downsample.0', [cur], rd, False, 1, s, 0, stream=stream,
+                                   bn_params=(blk.downsample[1].weight, blk.downsample[1].bias))
+                        _lib.check(self.lib.rp_bn_add_relu(r2.buf.data_ptr(), r2.scale.data_ptr(), r2.shift.data_ptr(),
+                                                           rd.buf.data_ptr(), rd.scale.data_ptr(), rd.shift.data_ptr(),
+                                                           out.buf.data_ptr(), n, Ho * Wo, cout, n, stream), "rp_bn_add_relu")
+                    else:
+                        _lib.check(self.lib.rp_bn_add_relu(r2.buf.data_ptr(), r2.scale.data_ptr(), r2.shift.data_ptr(),
+                                                           cur.buf.data_ptr(), None, None,
+                                                           out.buf.data_ptr(), n, Ho * Wo, cout, n, stream), "rp_bn_add_relu")
+                    cur = out
+                    if trace is not None:
+                        trace[pre] = cur.buf.permute(0, 3, 1, 2).contiguous()
+                feats[li] = cur
+            scores = {}
+            for li, name in ((2, 'score_8s'), (3, 'score_16s'), (4, 'score_32s')):
+                a = feats[li]
+                sc = act(a.H, a.W, 32, bn=False)
+                self._conv(name, [a], sc, False, 1, 1, 0, bn=False, bias=getattr(net, name).bias, stream=stream)
+                scores[li] = sc
+            s8, s16, s32 = scores[2], scores[3], scores[4]
+            _lib.check(self.lib.rp_resize_nhwc(s32.buf.data_ptr(), n, s32.H, s32.W, 32, s16.buf.data_ptr(), s16.H, s16.W, 1, stream), "resize32")
+            _lib.check(self.lib.rp_resize_nhwc(s16.buf.data_ptr(), n, s16.H, s16.W, 32, s8.buf.data_ptr(), s8.H, s8.W, 1, stream), "resize16")
+            out = torch.empty((n, 32, H, W), **f)
+            _lib.check(self.lib.rp_resize_to_nchw(s8.buf.data_ptr(), n, s8.H, s8.W, 32, out.data_ptr(), H, W,
+                                                  int(bool(net.args.useTanh)), stream), "resize_out")
+        return out

@@ -118,15 +118,20 @@ class ScnetEngine(object):
         self._bufs, self._P, self._dev = B, P, device
 
     # ---------------------------------------------------------------- one conv block
-    def _conv(self, name, srcs, out, transposed, k, s, p, bn=True, bias=None, tanh=False, stream=None):
+    _slope = 0.1          # LeakyReLU(0.1) of the SCNet blocks; ResnetEngine overrides with 0 (ReLU)
+    _gsz = 2              # images per BatchNorm batch (one scan pair)
+
+    def _conv(self, name, srcs, out, transposed, k, s, p, bn=True, bias=None, tanh=False, stream=None, bn_params=None):
         torch = self.torch
         d = _lib.RpConvDesc()
+        d.imgs_per_group = self._gsz
         d.nsrc = len(srcs)
         for i, a in enumerate(srcs):
             d.src[i].ptr = a.buf.data_ptr()
             d.src[i].pitch, d.src[i].ch_off, d.src[i].C = a.pitch, a.ch_off, a.C
             if a.scale is not None:
                 d.src[i].act = 1
+                d.src[i].slope = self._slope
                 d.src[i].scale, d.src[i].shift = a.scale.data_ptr(), a.shift.data_ptr()
                 d.src[i].sstride, d.src[i].s_off = a.pitch, a.ch_off
             else:
@@ -165,9 +170,11 @@ class ScnetEngine(object):
         else:
             _lib.check(self.lib.rp_conv_layer(ctypes.byref(d), stream), "rp_conv_layer(%s)" % name)
         if bn:
-            bnm = getattr(self.net, name)[1]
-            _lib.check(self.lib.rp_bn_finalize(d.psum, d.psq, self._P, nparts.value, out.C, 2 * out.H * out.W,
-                                               bnm.weight.data_ptr(), bnm.bias.data_ptr(),
+            if bn_params is None:
+                bnm = getattr(self.net, name)[1]
+                bn_params = (bnm.weight, bnm.bias)
+            _lib.check(self.lib.rp_bn_finalize(d.psum, d.psq, self._P, nparts.value, out.C, self._gsz * out.H * out.W,
+                                               bn_params[0].data_ptr(), bn_params[1].data_ptr(),
                                                out.scale.data_ptr(), out.shift.data_ptr(), out.pitch, out.ch_off, stream),
                        "rp_bn_finalize(%s)" % name)
 
