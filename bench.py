@@ -32,6 +32,7 @@ METRIC = "scan-pairs/sec (R,t solved) at N=512 corr"
 UNIT = "pairs/s"
 N_NOMINAL = 512
 TOPK = 5
+DRAM_BYTES_PER_PAIR_NCU = 345_800      # measured, see roofline.traffic_source
 
 
 def parse():
@@ -42,7 +43,7 @@ def parse():
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--pairs", type=int, default=4096, help="scan pairs per GPU per step")
     ap.add_argument("--nominal-n", type=int, default=N_NOMINAL)
-    ap.add_argument("--cpu-sample", type=int, default=0, help="pairs in the CPU-baseline sample (0 = 2 per core)")
+    ap.add_argument("--cpu-sample", type=int, default=0, help="pairs in the CPU-baseline sample (0 = 4 per core)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--sweep", action="store_true", help="also report the N sweep {128..2048} (configs[4])")
     return ap.parse_args()
@@ -71,7 +72,7 @@ def cpu_baseline(n_kp, sample, first_seed=10_000_000):
     from relativepose_b200 import synth
     cores = os.cpu_count() or 1
     if sample <= 0:
-        sample = max(2 * cores, 8)
+        sample = max(4 * cores, 16)
     sig = tuple(float(x) for x in synth.shipped_params("suncg")[0])
     jobs = [(first_seed + i, n_kp, sig) for i in range(sample)]
     ctx = mp.get_context("fork")
@@ -279,7 +280,9 @@ def run_cuda_arm(args):
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "peak_source": peak_src, "kernel": "rp_solve_kernel",
+                     "traffic": DRAM_BYTES_PER_PAIR_NCU * B, "traffic_source": "ncu --set full dram__bytes_read+write "
+                     "per pair at N_actual=515 (profiles/r1_solver_ncu_summary.txt, v5: 409 MB / 1184 pairs) x pairs per launch",
+                     "peak_source": peak_src, "kernel": "rp_solve_kernel",
                      "kernel_ms": float(np.mean(kern_ms)),
                      "model": "SURVEY 8(d) dense-equivalent bytes: 4*N^2*(2+sum_a(It_a+1)) + 156*(n_s+n_t) per pair with the "
                               "measured It_a; the kernel keeps W as an on-chip/L2 CSR, see DESIGN.md",

@@ -231,11 +231,20 @@ class PoseSolver(object):
         _lib.check(rc, "rp_solve_batch_ex")
         return T, status, stats
 
-    def solve_packed(self, packed, para, return_stats=False):
-        """Host buffers in -> host poses out ([B,4,4] float64): H2D, one fused launch, D2H."""
+    def solve_packed(self, packed, para, return_stats=False, chunks=None):
+        """Host buffers in -> host poses out ([B,4,4] float64).  The batch is cut into `chunks` pair ranges; the
+        pinned-host -> HBM copy of range c+1 runs on a copy stream while the fused kernel works on range c
+        (ragged offsets are absolute, so a range is just a pointer offset into the same arrays)."""
+        torch = self.torch
         plist = [params_from_opts(para)]
-        d = packed.to_device(self.device)
-        T, status, stats = self.solve_device(d, plist)
+        B = packed.B
+        if chunks is None:
+            chunks = 4 if B >= 2048 else 1
+        if chunks <= 1 or B < chunks:
+            d = packed.to_device(self.device)
+            T, status, stats = self.solve_device(d, plist)
+        else:
+            d, T, status, stats = self._solve_pipelined(packed, plist, chunks)
         Th = T.cpu().numpy()
         sth = status.cpu().numpy()
         if (sth == _lib.STATUS_EDGE_OVERFLOW).any():        # only with edge_frac < 1: redo with full capacity
@@ -246,6 +255,61 @@ class PoseSolver(object):
         if return_stats:
             return Th, sth, stats.cpu().numpy()
         return Th
+
+    def _solve_pipelined(self, packed, plist, chunks):
+        torch = self.torch
+        B = packed.B
+        dev = self.device
+        with torch.cuda.device(dev):
+            main = torch.cuda.current_stream()
+            if getattr(self, "_copy_stream", None) is None:
+                self._copy_stream = torch.cuda.Stream(device=dev)
+            cs = self._copy_stream
+            d = DeviceBatch()
+            d.B, d.max_ns, d.max_nt, d.feat_dim = B, packed.max_ns, packed.max_nt, packed.feat_dim
+            d.host, d._zero_dev = packed, {}
+            for f in PackedBatch.FIELDS:
+                h = getattr(packed, f)
+                setattr(d, f, torch.empty(h.shape, dtype=h.dtype, device=dev))
+            d.off_s_t = packed.off_s_t.to(dev, non_blocking=True)
+            d.off_t_t = packed.off_t_t.to(dev, non_blocking=True)
+            T = torch.empty((B, 4, 4), dtype=torch.float64, device=dev)
+            status = torch.empty((B,), dtype=torch.int32, device=dev)
+            stats = torch.empty((B, _lib.STATS_STRIDE), dtype=torch.int32, device=dev)
+            topk = max(1, min(max(int(p.topk) for p in plist), max(packed.max_nt - 1, 1)))
+            edge_cap = self._edge_cap(packed.max_ns, topk)
+            ws, key = self._workspace(packed.max_ns, packed.max_nt, topk, packed.feat_dim, edge_cap)
+            par = self._params_device(plist)
+            zrows = d.zero_rows(max(int(p.topk) for p in plist), topk, dev)
+            cs.wait_stream(main)                          # allocations above are visible to the copy stream
+            bounds = [B * c // chunks for c in range(chunks + 1)]
+            events = []
+            with torch.cuda.stream(cs):
+                for c in range(chunks):
+                    b0, b1 = bounds[c], bounds[c + 1]
+                    s0, s1 = int(packed.off_s[b0]), int(packed.off_s[b1])
+                    t0, t1 = int(packed.off_t[b0]), int(packed.off_t[b1])
+                    for f, (lo, hi) in (("pc_s", (s0, s1)), ("nrm_s", (s0, s1)), ("feat_s", (s0, s1)), ("w_s", (s0, s1)),
+                                        ("pc_t", (t0, t1)), ("nrm_t", (t0, t1)), ("feat_t", (t0, t1)), ("w_t", (t0, t1))):
+                        getattr(d, f)[lo:hi].copy_(getattr(packed, f)[lo:hi], non_blocking=True)
+                    ev = torch.cuda.Event()
+                    ev.record(cs)
+                    events.append(ev)
+            for c in range(chunks):
+                b0, b1 = bounds[c], bounds[c + 1]
+                main.wait_event(events[c])
+                rc = self.lib.rp_solve_batch_ex(
+                    b1 - b0, d.off_s_t.data_ptr() + 4 * b0, d.off_t_t.data_ptr() + 4 * b0,
+                    d.pc_s.data_ptr(), d.nrm_s.data_ptr(), d.feat_s.data_ptr(), d.w_s.data_ptr(),
+                    d.pc_t.data_ptr(), d.nrm_t.data_ptr(), d.feat_t.data_ptr(), d.w_t.data_ptr(),
+                    d.feat_dim, par.data_ptr(), None, zrows.data_ptr() + 4 * topk * b0, key[0], key[1], topk,
+                    self.n_slots, edge_cap, ws.data_ptr(), ws.numel(),
+                    T.data_ptr() + 128 * b0, status.data_ptr() + 4 * b0, stats.data_ptr() + 4 * _lib.STATS_STRIDE * b0,
+                    _lib.STAGE_SOLVE, None, main.cuda_stream)
+                _lib.check(rc, "rp_solve_batch_ex")
+            for f in PackedBatch.FIELDS:                   # the device arrays were filled on the copy stream
+                getattr(d, f).record_stream(cs)
+        return d, T, status, stats
 
     def solve_records(self, records, para, return_stats=False):
         return self.solve_packed(PackedBatch(records), para, return_stats=return_stats)

@@ -143,3 +143,33 @@ def test_determinism_and_slot_independence(solver):
     T3 = solver.solve_records(recs, para)
     assert np.array_equal(T1, T3)
     assert np.array_equal(T1, T2)
+
+
+def test_pipelined_chunks_bitwise_equal(solver):
+    """solve_packed cuts large batches into chunks to overlap H2D with compute: same bits as one launch."""
+    from relativepose_b200 import synth
+    from relativepose_b200.solver import PackedBatch
+    from relativepose_b200.RPModule.rputil import opts
+    P = synth.shipped_params('suncg')
+    recs = [synth.make_pair(700 + i, n_s, n_t) for i, (n_s, n_t) in enumerate([(30, 41), (52, 52), (2, 9), (64, 33), (26, 26)] * 4)]
+    pk = PackedBatch(recs)
+    para = opts(*P[0])
+    T1, s1, st1 = solver.solve_packed(pk, para, return_stats=True, chunks=1)
+    T4, s4, st4 = solver.solve_packed(pk, para, return_stats=True, chunks=4)
+    assert np.array_equal(T1, T4) and np.array_equal(s1, s4) and np.array_equal(st1, st4)
+
+
+def test_large_n_sweep_end(solver):
+    """configs[4] upper end: nominal N=2048 (n_s=n_t=410, N_actual=2050) against the oracle."""
+    from relativepose_b200 import synth
+    from relativepose_b200.RPModule.rputil import opts
+    from oracle import rp_oracle
+    P = synth.shipped_params('suncg')
+    rec = synth.make_pair(4242, 410)
+    T, status, stats = solver.solve_records([rec], opts(*P[0]), return_stats=True)
+    s, t = synth.record_to_dicts(rec)
+    tr = {}
+    To = rp_oracle.solve_pair(s, t, rp_oracle.Params(*P[0]), tr)
+    assert status[0] == 0 and stats[0, 0] == 2050
+    assert stats[0, 2] == tr['pairs'].shape[0], "surviving pair count differs"
+    assert np.linalg.norm(T[0] - To) <= T_TOL
