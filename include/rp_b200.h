@@ -227,6 +227,9 @@ int rp_resize_nhwc(const float* src, int n, int Hs, int Ws, int C, float* dst, i
 /* final F.upsample to the input size + optional tanh, NHWC [n,Hs,Ws,C] -> NCHW [n,C,H,W] (mymodel.py:111,120-121) */
 int rp_resize_to_nchw(const float* src, int n, int Hs, int Ws, int C, float* out, int H, int W, int tanh_out, void* stream);
 
+/* rputil.interpolate (RPModule/rputil.py:43-58): feat [C,H,W], pt [K,2] normalised (x,y) -> out [C,K]; device float32 */
+int rp_interpolate(const float* feat, int C, int H, int W, const float* pt, int K, float* out, void* stream);
+
 int64_t rp_launch_count(void);
 int64_t rp_conv_launch_count(void);
 

@@ -41,3 +41,40 @@ def RelativePoseEstimation_helper(dataS, dataT, para):
         logger.info("stage-1: not enough!")                    # rpmodule.py:346-348 (before the method dispatch)
         return np.eye(4)
     return RelativePoseEstimation_batch([_record(dataS, dataT)], para)[0]
+
+
+def getMatchingPrimitive(dataS, dataT, dataset, representation, doCompletion, keypoint_fn=None):
+    """rpmodule.py:511-538: keypoints -> 3-D positions / normals / descriptors / observation weights.
+
+    ``keypoint_fn(dataS, dataT, dataset)`` must return the reference's 6-tuple
+    ``(pts, ptsNorm, ptsW, ptt, pttNorm, pttW)`` (rputil.getKeypoint / getKeypoint_kinect: pixel coordinates [n,2],
+    coordinates normalised by (W,H), weights 1.0 / 0.99).  The reference's own detector is OpenCV-contrib SIFT plus
+    an unseeded random augmentation (rputil.py:141-353) and sits outside this repo's parity perimeter
+    (SURVEY.md section 8f row 2), so it has to be supplied."""
+    if keypoint_fn is None:
+        raise NotImplementedError("getMatchingPrimitive needs keypoint_fn (the SIFT keypoint stage of rputil.getKeypoint is "
+                                  "outside the B200 hot path; see DESIGN.md section 8)")
+    pts, ptsNorm, ptsW, ptt, pttNorm, pttW = keypoint_fn(dataS, dataT, dataset)
+    if pts is None or ptt is None or pts.shape[1] < 2 or ptt.shape[1] < 2:
+        return None, None, None, None, None, None, None, None
+    pts3d, ptsns = getPixel(dataS['depth'], dataS['normal'], pts, dataset=dataset, representation=representation)
+    ptt3d, ptsnt = getPixel(dataT['depth'], dataT['normal'], ptt, dataset=dataset, representation=representation)
+    dess = interpolate(dataS['feat'], ptsNorm).cpu().numpy().T          # [n,32] float32, as torch_op.npy(...).T
+    dest = interpolate(dataT['feat'], pttNorm).cpu().numpy().T
+    if not doCompletion:            # keep only keypoints from the observed region (rpmodule.py:534-537)
+        ks, kt = ptsW == 1, pttW == 1
+        pts3d, ptsns, dess, ptsW = pts3d[:, ks], ptsns[ks], dess[ks], ptsW[ks]
+        ptt3d, ptsnt, dest, pttW = ptt3d[:, kt], ptsnt[kt], dest[kt], pttW[kt]
+    return pts3d, ptt3d, ptsns, ptsnt, dess, dest, ptsW, pttW
+
+
+def RelativePoseEstimation(dataS, dataT, para, dataset, representation, maskMethod, doCompletion=True, index=None,
+                           keypoint_fn=None):
+    """rpmodule.py:540-566: keypoints -> matching primitives -> RelativePoseEstimation_helper."""
+    R_hat = np.eye(4)
+    prim = getMatchingPrimitive(dataS, dataT, dataset, representation, doCompletion, keypoint_fn)
+    pts3d, ptt3d, ptsns, ptsnt, dess, dest, ptsW, pttW = prim
+    if pts3d is None or ptt3d is None or pts3d.shape[0] < 2:
+        return R_hat
+    return RelativePoseEstimation_helper({'pc': pts3d.T, 'normal': ptsns, 'feat': dess, 'weight': ptsW},
+                                         {'pc': ptt3d.T, 'normal': ptsnt, 'feat': dest, 'weight': pttW}, para)

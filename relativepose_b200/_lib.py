@@ -60,7 +60,7 @@ EXPORTS = ("rp_abi_version", "rp_device_info", "rp_solve_workspace_bytes", "rp_s
            "rp_solve_batch_ex", "rp_match_topk", "rp_launch_count",
            "rp_conv_nparts", "rp_conv_layer", "rp_bn_finalize", "rp_scnet_resize_in", "rp_scnet_resize_out",
            "rp_conv_launch_count", "rp_tc_gemm_test", "rp_conv_nparts_tc", "rp_conv_layer_tc",
-           "rp_bn_relu_maxpool", "rp_bn_add_relu", "rp_resize_nhwc", "rp_resize_to_nchw")
+           "rp_bn_relu_maxpool", "rp_bn_add_relu", "rp_resize_nhwc", "rp_resize_to_nchw", "rp_interpolate")
 
 _lib = None
 
@@ -118,6 +118,8 @@ def load():
     lib.rp_resize_nhwc.argtypes = [vp, i32, i32, i32, i32, vp, i32, i32, i32, vp]
     lib.rp_resize_to_nchw.restype = i32
     lib.rp_resize_to_nchw.argtypes = [vp, i32, i32, i32, i32, vp, i32, i32, i32, vp]
+    lib.rp_interpolate.restype = i32
+    lib.rp_interpolate.argtypes = [vp, i32, i32, i32, vp, i32, vp, vp]
     lib.rp_tc_gemm_test.restype = i32
     lib.rp_tc_gemm_test.argtypes = [vp, vp, vp, i32, i32, i32, i32, vp]
     if lib.rp_abi_version() != 1:

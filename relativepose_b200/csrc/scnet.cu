@@ -376,6 +376,30 @@ __global__ void resize_to_nchw_kernel(const float* __restrict__ src, int n, int 
     }
 }
 
+// rputil.interpolate (RPModule/rputil.py:43-58): bilinear gather of C-channel descriptors at K normalised points,
+// x = px*(W-1), y = py*(H-1), floor-based weights, float32 with the reference's operation order.
+__global__ void interpolate_kernel(const float* __restrict__ feat, int C, int H, int W, const float* __restrict__ pt, int K,
+                                   float* __restrict__ out) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= C * K) return;
+    const int k = idx % K, c = idx / K;
+    const float x = pt[2 * k] * (float)(W - 1), y = pt[2 * k + 1] * (float)(H - 1);
+    const float x0 = floorf(x), y0 = floorf(y);
+    int ix = (int)x0, iy = (int)y0;
+    ix = ix < 0 ? 0 : (ix > W - 2 ? W - 2 : ix);
+    iy = iy < 0 ? 0 : (iy > H - 2 ? H - 2 : iy);
+    const float* f = feat + (size_t)c * H * W;
+    const float v00 = f[(size_t)iy * W + ix], v10 = f[(size_t)(iy + 1) * W + ix];
+    const float v01 = f[(size_t)iy * W + ix + 1], v11 = f[(size_t)(iy + 1) * W + ix + 1];
+    const float wx0 = __fsub_rn(__fadd_rn(x0, 1.f), x), wy0 = __fsub_rn(__fadd_rn(y0, 1.f), y);
+    const float wx1 = __fsub_rn(x, x0), wy1 = __fsub_rn(y, y0);
+    float r = __fmul_rn(__fmul_rn(v00, wx0), wy0);
+    r = __fadd_rn(r, __fmul_rn(__fmul_rn(v10, wx0), wy1));
+    r = __fadd_rn(r, __fmul_rn(__fmul_rn(v01, wx1), wy0));
+    r = __fadd_rn(r, __fmul_rn(__fmul_rn(v11, wx1), wy1));
+    out[idx] = r;
+}
+
 inline bool small_cin_eligible(const rp_conv_desc* d) {
     return d->nsrc == 1 && !d->transposed && d->k == 3 && d->s == 1 && d->p == 1 && d->Cout == 32 && !d->bias &&
            !d->tanh_out && d->src[0].act == 0 && (d->src[0].C == 4 || d->src[0].C == 2) &&
@@ -479,6 +503,15 @@ int rp_resize_to_nchw(const float* src, int n, int Hs, int Ws, int C, float* out
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
     size_t total = (size_t)n * H * W;
     resize_to_nchw_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(src, n, Hs, Ws, C, out, H, W, tanh_out);
+    ++g_conv_launches;
+    return cudaGetLastError() == cudaSuccess ? RP_OK : RP_ERR_CUDA;
+}
+
+int rp_interpolate(const float* feat, int C, int H, int W, const float* pt, int K, float* out, void* stream_) {
+    if (!feat || !pt || !out || C < 1 || K < 0 || H < 2 || W < 2) return RP_ERR_INVALID_ARG;
+    if (K == 0) return RP_OK;
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    interpolate_kernel<<<(C * K + 255) / 256, 256, 0, stream>>>(feat, C, H, W, pt, K, out);
     ++g_conv_launches;
     return cudaGetLastError() == cudaSuccess ? RP_OK : RP_ERR_CUDA;
 }
