@@ -125,13 +125,17 @@ int rp_solve_workspace_bytes(int n_slots, int max_ns, int max_nt, int max_topk, 
  *     soft-match row underflows to all zeros (rpmodule.py:359-363 zeroes the row; np.argpartition then
  *     returns an order-of-introselect set that depends only on (n_t, K)).  The host fills it with
  *     np.argpartition(-np.zeros(n_t), K)[:K] so ties resolve exactly like the reference; NULL = by distance.
+ *   feat_sum_order [B] (device) or NULL (= all 0): float32 summation order of the descriptor distance, which in
+ *     NumPy depends on the memory layout of the 'feat' arrays (rpmodule.py:355): 0 = both C-contiguous (8-lane
+ *     pairwise sum), 1 = either one a transposed view, as the reference's own pipeline passes them
+ *     (rpmodule.py:531-532) -> sequential sum over the channels.  The Python layer derives it from the array flags.
  *   T_out [B,16] row-major 4x4 float64; status [B]; stats [B,8] (may be NULL)
  */
 int rp_solve_batch(int B, const int32_t* off_s, const int32_t* off_t,
                    const double* pc_s, const double* nrm_s, const float* feat_s, const double* w_s,
                    const double* pc_t, const double* nrm_t, const float* feat_t, const double* w_t,
                    int feat_dim, const rp_params* params, const int32_t* param_idx,
-                   const int32_t* zero_row_topk,
+                   const int32_t* zero_row_topk, const int32_t* feat_sum_order,
                    int max_ns, int max_nt, int max_topk,
                    int n_slots, int64_t edge_cap, void* workspace, size_t workspace_bytes,
                    double* T_out, int32_t* status, int32_t* stats, void* stream);
@@ -143,7 +147,7 @@ int rp_solve_batch_ex(int B, const int32_t* off_s, const int32_t* off_t,
                       const double* pc_s, const double* nrm_s, const float* feat_s, const double* w_s,
                       const double* pc_t, const double* nrm_t, const float* feat_t, const double* w_t,
                       int feat_dim, const rp_params* params, const int32_t* param_idx,
-                      const int32_t* zero_row_topk,
+                      const int32_t* zero_row_topk, const int32_t* feat_sum_order,
                       int max_ns, int max_nt, int max_topk,
                       int n_slots, int64_t edge_cap, void* workspace, size_t workspace_bytes,
                       double* T_out, int32_t* status, int32_t* stats,
@@ -153,7 +157,7 @@ int rp_solve_batch_ex(int B, const int32_t* off_s, const int32_t* off_t,
 int rp_match_topk(int B, const int32_t* off_s, const int32_t* off_t,
                   const float* feat_s, const double* w_s, const float* feat_t, const double* w_t,
                   int feat_dim, const rp_params* params, const int32_t* param_idx,
-                  const int32_t* zero_row_topk,
+                  const int32_t* zero_row_topk, const int32_t* feat_sum_order,
                   int max_ns, int max_nt, int max_topk,
                   int n_slots, void* workspace, size_t workspace_bytes,
                   int32_t* topk_idx, double* topk_f, int32_t* status, void* stream);

@@ -86,14 +86,14 @@ def load():
     lib.rp_device_info.argtypes = [ctypes.POINTER(ctypes.c_int)] * 3 + [ctypes.POINTER(ctypes.c_size_t)]
     lib.rp_solve_workspace_bytes.restype = i32
     lib.rp_solve_workspace_bytes.argtypes = [i32, i32, i32, i32, i32, i64, ctypes.POINTER(ctypes.c_size_t)]
-    common = [i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, vp, vp, vp, i32, i32, i32, i32, i64, vp,
+    common = [i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, vp, vp, vp, vp, i32, i32, i32, i32, i64, vp,
               ctypes.c_size_t, vp, vp, vp]
     lib.rp_solve_batch.restype = i32
     lib.rp_solve_batch.argtypes = common + [vp]
     lib.rp_solve_batch_ex.restype = i32
     lib.rp_solve_batch_ex.argtypes = common + [i32, ctypes.POINTER(RpDebug), vp]
     lib.rp_match_topk.restype = i32
-    lib.rp_match_topk.argtypes = [i32, vp, vp, vp, vp, vp, vp, i32, vp, vp, vp, i32, i32, i32, i32, vp,
+    lib.rp_match_topk.argtypes = [i32, vp, vp, vp, vp, vp, vp, i32, vp, vp, vp, vp, i32, i32, i32, i32, vp,
                                   ctypes.c_size_t, vp, vp, vp, vp]
     lib.rp_conv_nparts.restype = i32
     lib.rp_conv_nparts.argtypes = [ctypes.POINTER(RpConvDesc), ctypes.POINTER(ctypes.c_int)]

@@ -63,6 +63,7 @@ struct SolveArgs {
     const rp_params* params;
     const int32_t* param_idx;
     const int32_t* zero_row_topk;
+    const int32_t* feat_sum_order;
     int max_topk;
     long long edge_cap;
     char* ws;               // workspace base; first 256 bytes = header (work counter)
@@ -135,6 +136,15 @@ __device__ float numpy_sqdist_f32(const float* __restrict__ s, const float* __re
     float res = __fadd_rn(__fadd_rn(__fadd_rn(r[0], r[1]), __fadd_rn(r[2], r[3])),
                           __fadd_rn(__fadd_rn(r[4], r[5]), __fadd_rn(r[6], r[7])));
     for (; i < n; ++i) res = __fadd_rn(res, sq_diff(s, t, i));
+    return res;
+}
+
+// When either descriptor array is not C-contiguous (the reference's own pipeline hands over transposed views:
+// rpmodule.py:531-532 `torch_op.npy(interpolate(...)).T`), NumPy's nditer makes the channel axis an outer loop and the
+// float32 reduction degenerates to a plain sequential sum over the channels.
+__device__ float numpy_sqdist_f32_seq(const float* __restrict__ s, const float* __restrict__ t, int n) {
+    float res = sq_diff(s, t, 0);
+    for (int i = 1; i < n; ++i) res = __fadd_rn(res, sq_diff(s, t, i));
     return res;
 }
 
@@ -876,6 +886,7 @@ __global__ void __launch_bounds__(T, RP_MIN_BLOCKS) rp_solve_kernel(const SolveA
             float* tfeat = reinterpret_cast<float*>(dyn_smem);       // aliases the vectors (not yet live)
             const int ts = A.tfeat_stride;
             const bool vec4 = ((D & 7) == 0) && ((ts & 3) == 0);
+            const bool seq_sum = A.feat_sum_order && A.feat_sum_order[b] != 0;
             const float* ft = A.feat_t + (size_t)t0 * D;
             for (int e = tid; e < nt * D; e += T) {
                 int j = e / D, c = e - j * D;
@@ -892,8 +903,9 @@ __global__ void __launch_bounds__(T, RP_MIN_BLOCKS) rp_solve_kernel(const SolveA
                 for (int k = 0; k < KMAX; ++k) { lk[k] = -CUDART_INF; li[k] = 0x7fffffff; }
                 double ss = 0.0;
                 for (int j = lane; j < nt; j += 32) {
-                    float dij = vec4 ? numpy_sqdist_f32_v4(sh.sfeat[warp], tfeat + j * ts, D)
-                                     : numpy_sqdist_f32(sh.sfeat[warp], tfeat + j * ts, D);        // :355
+                    float dij = seq_sum ? numpy_sqdist_f32_seq(sh.sfeat[warp], tfeat + j * ts, D)
+                                : vec4  ? numpy_sqdist_f32_v4(sh.sfeat[warp], tfeat + j * ts, D)
+                                        : numpy_sqdist_f32(sh.sfeat[warp], tfeat + j * ts, D);     // :355
                     if (A.has_dbg && A.dbg.dij) A.dbg.dij[A.dbg.dij_off[b] + (int64_t)i * nt + j] = dij;
                     double both = __dmul_rn(wsi, A.w_t[t0 + j]);                                   // :354
                     double den = (both == 1.0) ? par.feat_den_obs : par.feat_den;                 // :356-357
@@ -1327,7 +1339,7 @@ int rp_solve_batch_ex(int B, const int32_t* off_s, const int32_t* off_t,
                       const double* pc_s, const double* nrm_s, const float* feat_s, const double* w_s,
                       const double* pc_t, const double* nrm_t, const float* feat_t, const double* w_t,
                       int feat_dim, const rp_params* params, const int32_t* param_idx,
-                      const int32_t* zero_row_topk,
+                      const int32_t* zero_row_topk, const int32_t* feat_sum_order,
                       int max_ns, int max_nt, int max_topk,
                       int n_slots, int64_t edge_cap, void* workspace, size_t workspace_bytes,
                       double* T_out, int32_t* status, int32_t* stats,
@@ -1357,7 +1369,7 @@ int rp_solve_batch_ex(int B, const int32_t* off_s, const int32_t* off_t,
     a.B = B; a.off_s = off_s; a.off_t = off_t;
     a.pc_s = pc_s; a.nrm_s = nrm_s; a.feat_s = feat_s; a.w_s = w_s;
     a.pc_t = pc_t; a.nrm_t = nrm_t; a.feat_t = feat_t; a.w_t = w_t;
-    a.feat_dim = feat_dim; a.params = params; a.param_idx = param_idx; a.zero_row_topk = zero_row_topk;
+    a.feat_dim = feat_dim; a.params = params; a.param_idx = param_idx; a.zero_row_topk = zero_row_topk; a.feat_sum_order = feat_sum_order;
     a.max_topk = max_topk; a.edge_cap = L.edge_cap;
     a.ws = static_cast<char*>(workspace); a.slot_bytes = L.slot_bytes;
     a.o_geo = L.o_geo; a.o_cj = L.o_cj; a.o_mask = L.o_mask; a.o_edges = L.o_edges; a.o_ew = L.o_ew;
@@ -1380,19 +1392,19 @@ int rp_solve_batch(int B, const int32_t* off_s, const int32_t* off_t,
                    const double* pc_s, const double* nrm_s, const float* feat_s, const double* w_s,
                    const double* pc_t, const double* nrm_t, const float* feat_t, const double* w_t,
                    int feat_dim, const rp_params* params, const int32_t* param_idx,
-                   const int32_t* zero_row_topk,
+                   const int32_t* zero_row_topk, const int32_t* feat_sum_order,
                    int max_ns, int max_nt, int max_topk,
                    int n_slots, int64_t edge_cap, void* workspace, size_t workspace_bytes,
                    double* T_out, int32_t* status, int32_t* stats, void* stream) {
     return rp_solve_batch_ex(B, off_s, off_t, pc_s, nrm_s, feat_s, w_s, pc_t, nrm_t, feat_t, w_t, feat_dim, params,
-                             param_idx, zero_row_topk, max_ns, max_nt, max_topk, n_slots, edge_cap, workspace,
+                             param_idx, zero_row_topk, feat_sum_order, max_ns, max_nt, max_topk, n_slots, edge_cap, workspace,
                              workspace_bytes, T_out, status, stats, RP_STAGE_SOLVE, nullptr, stream);
 }
 
 int rp_match_topk(int B, const int32_t* off_s, const int32_t* off_t,
                   const float* feat_s, const double* w_s, const float* feat_t, const double* w_t,
                   int feat_dim, const rp_params* params, const int32_t* param_idx,
-                  const int32_t* zero_row_topk,
+                  const int32_t* zero_row_topk, const int32_t* feat_sum_order,
                   int max_ns, int max_nt, int max_topk,
                   int n_slots, void* workspace, size_t workspace_bytes,
                   int32_t* topk_idx, double* topk_f, int32_t* status, void* stream) {
@@ -1400,7 +1412,7 @@ int rp_match_topk(int B, const int32_t* off_s, const int32_t* off_t,
     rp_debug d = {};
     d.topk_idx = topk_idx; d.topk_f = topk_f;
     return rp_solve_batch_ex(B, off_s, off_t, nullptr, nullptr, feat_s, w_s, nullptr, nullptr, feat_t, w_t, feat_dim,
-                             params, param_idx, zero_row_topk, max_ns, max_nt, max_topk, n_slots, 0, workspace,
+                             params, param_idx, zero_row_topk, feat_sum_order, max_ns, max_nt, max_topk, n_slots, 0, workspace,
                              workspace_bytes, nullptr, status, nullptr, RP_STAGE_TOPK, &d, stream);
 }
 

@@ -98,6 +98,13 @@ class PackedBatch(object):
         self.w_t = cat("weight_tgt", np.float64, 0)
         self.off_s_t = torch.from_numpy(self.off_s)
         self.off_t_t = torch.from_numpy(self.off_t)
+        # NumPy's float32 summation order for the descriptor distance depends on the layout of the caller's 'feat'
+        # arrays (see include/rp_b200.h: feat_sum_order): sequential unless both are C-contiguous
+        order = np.array([0 if (np.asarray(r["feat_src"]).flags["C_CONTIGUOUS"] and np.asarray(r["feat_tgt"]).flags["C_CONTIGUOUS"])
+                          else 1 for r in records], dtype=np.int32)
+        self.sum_order_t = torch.from_numpy(order)
+        if pin and torch.cuda.is_available():
+            self.sum_order_t = self.sum_order_t.pin_memory()
         self.nt_list = nt
         self._zero_rows = {}
         if pin and torch.cuda.is_available():
@@ -128,7 +135,7 @@ class PackedBatch(object):
     def to_device(self, device, non_blocking=True):
         d = DeviceBatch()
         d.B, d.max_ns, d.max_nt, d.feat_dim = self.B, self.max_ns, self.max_nt, self.feat_dim
-        for f in self.FIELDS + ("off_s_t", "off_t_t"):
+        for f in self.FIELDS + ("off_s_t", "off_t_t", "sum_order_t"):
             setattr(d, f, getattr(self, f).to(device, non_blocking=non_blocking))
         d.host = self
         d._zero_dev = {}
@@ -225,7 +232,7 @@ class PoseSolver(object):
                 B, dbatch.off_s_t.data_ptr(), dbatch.off_t_t.data_ptr(),
                 dbatch.pc_s.data_ptr(), dbatch.nrm_s.data_ptr(), dbatch.feat_s.data_ptr(), dbatch.w_s.data_ptr(),
                 dbatch.pc_t.data_ptr(), dbatch.nrm_t.data_ptr(), dbatch.feat_t.data_ptr(), dbatch.w_t.data_ptr(),
-                dbatch.feat_dim, par.data_ptr(), pidx, zrows.data_ptr(), key[0], key[1], topk,
+                dbatch.feat_dim, par.data_ptr(), pidx, zrows.data_ptr(), dbatch.sum_order_t.data_ptr(), key[0], key[1], topk,
                 self.n_slots, edge_cap, ws.data_ptr(), ws.numel(),
                 T.data_ptr(), status.data_ptr(), stats.data_ptr(), stop_after, dbg, stream)
         _lib.check(rc, "rp_solve_batch_ex")
@@ -273,6 +280,7 @@ class PoseSolver(object):
                 setattr(d, f, torch.empty(h.shape, dtype=h.dtype, device=dev))
             d.off_s_t = packed.off_s_t.to(dev, non_blocking=True)
             d.off_t_t = packed.off_t_t.to(dev, non_blocking=True)
+            d.sum_order_t = packed.sum_order_t.to(dev, non_blocking=True)
             T = torch.empty((B, 4, 4), dtype=torch.float64, device=dev)
             status = torch.empty((B,), dtype=torch.int32, device=dev)
             stats = torch.empty((B, _lib.STATS_STRIDE), dtype=torch.int32, device=dev)
@@ -302,7 +310,7 @@ class PoseSolver(object):
                     b1 - b0, d.off_s_t.data_ptr() + 4 * b0, d.off_t_t.data_ptr() + 4 * b0,
                     d.pc_s.data_ptr(), d.nrm_s.data_ptr(), d.feat_s.data_ptr(), d.w_s.data_ptr(),
                     d.pc_t.data_ptr(), d.nrm_t.data_ptr(), d.feat_t.data_ptr(), d.w_t.data_ptr(),
-                    d.feat_dim, par.data_ptr(), None, zrows.data_ptr() + 4 * topk * b0, key[0], key[1], topk,
+                    d.feat_dim, par.data_ptr(), None, zrows.data_ptr() + 4 * topk * b0, d.sum_order_t.data_ptr() + 4 * b0, key[0], key[1], topk,
                     self.n_slots, edge_cap, ws.data_ptr(), ws.numel(),
                     T.data_ptr() + 128 * b0, status.data_ptr() + 4 * b0, stats.data_ptr() + 4 * _lib.STATS_STRIDE * b0,
                     _lib.STAGE_SOLVE, None, main.cuda_stream)

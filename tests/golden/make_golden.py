@@ -105,6 +105,15 @@ def cases():
     # topK variants (rpmodule.py:368: topK=min(para.topK, n_t-1))
     out.append(("topk4_n64", synth.make_pair(13, 64), 'irls+sm', 0, 'suncg', 4))
     out.append(("topk_clamped", synth.make_pair(14, 30, 4), 'irls+sm', 0, 'suncg', 5))
+    # descriptor arrays as transposed views, the layout the reference's own pipeline passes (rpmodule.py:531-532):
+    # NumPy then sums the 32 squared differences sequentially instead of pairwise
+    for nm, seed, n, which in (("forder_both", 18, 52, "st"), ("forder_src", 19, 40, "s"), ("forder_tgt_n103", 20, 103, "t")):
+        r = synth.make_pair(seed, n)
+        if "s" in which:
+            r['feat_src'] = np.ascontiguousarray(r['feat_src'].T).T
+        if "t" in which:
+            r['feat_tgt'] = np.ascontiguousarray(r['feat_tgt'].T).T
+        out.append((nm, r, 'irls+sm', 0, 'suncg', 5))
     # early exits (rpmodule.py:346-348, 406-408, 440-443)
     out.append(("exit_few_kp", synth.make_pair(15, 2, 10), 'irls+sm', 0, 'suncg', 5))
     out.append(("exit_no_inlier", synth.make_pair(16, 6, inlier_frac=0.0), 'irls+sm', 0, 'suncg', 5))

