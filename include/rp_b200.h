@@ -217,6 +217,21 @@ int rp_scnet_resize_in(const float* x, int n, int H, int W, float* out, void* st
 /* F.upsample(xout,inShape,'bilinear',align_corners=False) (mymodel.py:379): in [n,224,224,C] NHWC -> out [n,C,H,W] NCHW */
 int rp_scnet_resize_out(const float* in, int n, int C, int H, int W, float* out, void* stream);
 
+/* Stage entry: the fitters only (rpmodule.py:484-508; fit_horn87 :60, fit_spectral :86, fit_irls :169, fit_irls_sm :212,
+ * horn87_np :17).  Problem b owns nodes [node_off[b], node_off[b+1]) = candidate correspondences with source/target
+ * position (sp, tp) and normal (sn, tn), and optionally edges [edge_off[b], edge_off[b+1]) = geometrically consistent
+ * pairs: two local node indices and the pair weight w (rpmodule.py:457-467).  With edges the base weights are the row
+ * degrees of W (exactly the reference's stacked rows allWP = allWN = [w, w]); with edge_off == NULL the explicit
+ * per-node weights node_wp/node_wn are used (allWP/allWN of fit_horn87 / fit_irls; horn87_np = normals only). */
+int rp_spectral_irls_workspace_bytes(int n_slots, int max_nodes, int64_t edge_cap, size_t* bytes);
+int rp_spectral_irls_solve(int B, const int32_t* node_off,
+                           const double* sp, const double* sn, const double* tp, const double* tn,
+                           const double* node_wp, const double* node_wn,
+                           const int32_t* edge_off, const int32_t* edge_rc, const double* edge_w,
+                           const rp_params* params, const int32_t* param_idx, int max_nodes,
+                           int n_slots, int64_t edge_cap, void* workspace, size_t workspace_bytes,
+                           double* T_out, int32_t* status, int32_t* stats, void* stream);
+
 /* Kernel launch counter (number of kernels this library launched since load); bench.py reports it. */
 /* ---- Resnet18_8s extras (mymodel.py:82-122; stock ResNet-18 trunk) -------------------------------------------
  * y = act(x*scale+shift) with per-(group,channel) BN scale/shift (NULL = identity), all tensors float32 NHWC. */

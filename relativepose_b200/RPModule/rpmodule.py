@@ -78,3 +78,69 @@ def RelativePoseEstimation(dataS, dataT, para, dataset, representation, maskMeth
         return R_hat
     return RelativePoseEstimation_helper({'pc': pts3d.T, 'normal': ptsns, 'feat': dess, 'weight': ptsW},
                                          {'pc': ptt3d.T, 'normal': ptsnt, 'feat': dest, 'weight': pttW}, para)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Module-level fitters with the reference's positional signatures (rpmodule.py:17,60,86,169,212), backed by the
+# rp_spectral_irls_solve stage entry.
+def horn87_np(src, tgt, weight=None):
+    """rpmodule.py:17-58.  src, tgt: [(k),3,n]; weight: [(k),n] -> R [(k),3,3]."""
+    src, tgt = np.asarray(src, dtype=np.float64), np.asarray(tgt, dtype=np.float64)
+    if src.ndim == 2 and tgt.ndim == 2:
+        src, tgt = src[np.newaxis], tgt[np.newaxis]
+    assert src.shape[2] == tgt.shape[2]
+    k, n = src.shape[0], src.shape[2]
+    w = np.ones([k, n]) if weight is None else np.asarray(weight, dtype=np.float64).reshape(k, n)
+    sn = src.transpose(0, 2, 1).reshape(-1, 3)
+    tn = tgt.transpose(0, 2, 1).reshape(-1, 3)
+    zeros = np.zeros_like(sn)
+    off = np.arange(k + 1) * n
+    T = _solver.default_solver().fit_nodes(zeros, sn, zeros, tn, off, 'horn87', 1.0,
+                                           node_w=(np.zeros(k * n), w.reshape(-1)))
+    return T[:, :3, :3].copy()
+
+
+def _fit_rows(allSP, allTP, allSN, allTN, allWP, allWN, mu, method):
+    n = allSP.shape[0]
+    return _solver.default_solver().fit_nodes(allSP, allSN, allTP, allTN, np.array([0, n]), method, mu,
+                                              node_w=(np.asarray(allWP, dtype=np.float64), np.asarray(allWN, dtype=np.float64)))[0]
+
+
+def fit_horn87(allSP, allTP, allSN, allTN, allWP, allWN, mu):
+    """rpmodule.py:60-84."""
+    return _fit_rows(allSP, allTP, allSN, allTN, allWP, allWN, mu, 'horn87')
+
+
+def fit_irls(allSP, allTP, allSN, allTN, allWP, allWN, mu):
+    """rpmodule.py:169-210."""
+    return _fit_rows(allSP, allTP, allSN, allTN, allWP, allWN, mu, 'irls')
+
+
+def _fit_graph(allSP, allTP, allSN, allTN, allWP, allWN, w, mu, row, col, method):
+    """The spectral fitters work on the compact affinity: stacked rows 0..M-1 / M..2M-1 are the first / second
+    correspondence of pair i (rpmodule.py:484-489), identified by their flat ids row[i] / col[i] (:495-496)."""
+    w = np.asarray(w, dtype=np.float64)
+    M = w.shape[0]
+    allWP, allWN = np.asarray(allWP, dtype=np.float64), np.asarray(allWN, dtype=np.float64)
+    if not (np.array_equal(allWP, np.tile(w, 2)) and np.array_equal(allWN, np.tile(w, 2))):
+        raise NotImplementedError("fit_spectral/fit_irls_sm expect allWP == allWN == [w, w], as RelativePoseEstimation_helper "
+                                  "builds them (rpmodule.py:488-489)")
+    ids = np.concatenate((np.asarray(row), np.asarray(col)))
+    uniq, first, inv = np.unique(ids, return_index=True, return_inverse=True)
+    for arr in (allSP, allTP, allSN, allTN):
+        if not np.array_equal(np.asarray(arr)[first][inv], np.asarray(arr)):
+            raise NotImplementedError("stacked rows with the same correspondence id must carry the same geometry")
+    rc = np.stack((inv[:M], inv[M:]), 1)
+    solver = _solver.default_solver()
+    return solver.fit_nodes(np.asarray(allSP)[first], np.asarray(allSN)[first], np.asarray(allTP)[first], np.asarray(allTN)[first],
+                            np.array([0, len(uniq)]), method, mu, edges=(np.array([0, M]), rc, w))[0]
+
+
+def fit_spectral(allSP, allTP, allSN, allTN, allWP, allWN, w_i1i2j1j2, mu, row, col, numFea_s, numFea_t):
+    """rpmodule.py:86-167."""
+    return _fit_graph(allSP, allTP, allSN, allTN, allWP, allWN, w_i1i2j1j2, mu, row, col, 'spectral')
+
+
+def fit_irls_sm(allSP, allTP, allSN, allTN, allWP, allWN, w_i1i2j1j2, mu, row, col, numFea_s, numFea_t):
+    """rpmodule.py:212-315 (the default method)."""
+    return _fit_graph(allSP, allTP, allSN, allTN, allWP, allWN, w_i1i2j1j2, mu, row, col, 'irls+sm')

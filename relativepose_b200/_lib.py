@@ -57,7 +57,7 @@ class RpConvDesc(ctypes.Structure):
 
 
 EXPORTS = ("rp_abi_version", "rp_device_info", "rp_solve_workspace_bytes", "rp_solve_batch",
-           "rp_solve_batch_ex", "rp_match_topk", "rp_launch_count",
+           "rp_solve_batch_ex", "rp_match_topk", "rp_launch_count", "rp_spectral_irls_solve", "rp_spectral_irls_workspace_bytes",
            "rp_conv_nparts", "rp_conv_layer", "rp_bn_finalize", "rp_scnet_resize_in", "rp_scnet_resize_out",
            "rp_conv_launch_count", "rp_tc_gemm_test", "rp_conv_nparts_tc", "rp_conv_layer_tc",
            "rp_bn_relu_maxpool", "rp_bn_add_relu", "rp_resize_nhwc", "rp_resize_to_nchw", "rp_interpolate")
@@ -95,6 +95,10 @@ def load():
     lib.rp_match_topk.restype = i32
     lib.rp_match_topk.argtypes = [i32, vp, vp, vp, vp, vp, vp, i32, vp, vp, vp, vp, i32, i32, i32, i32, vp,
                                   ctypes.c_size_t, vp, vp, vp, vp]
+    lib.rp_spectral_irls_workspace_bytes.restype = i32
+    lib.rp_spectral_irls_workspace_bytes.argtypes = [i32, i32, i64, ctypes.POINTER(ctypes.c_size_t)]
+    lib.rp_spectral_irls_solve.restype = i32
+    lib.rp_spectral_irls_solve.argtypes = [i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i64, vp, ctypes.c_size_t, vp, vp, vp, vp]
     lib.rp_conv_nparts.restype = i32
     lib.rp_conv_nparts.argtypes = [ctypes.POINTER(RpConvDesc), ctypes.POINTER(ctypes.c_int)]
     lib.rp_conv_layer.restype = i32

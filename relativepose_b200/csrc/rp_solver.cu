@@ -64,6 +64,10 @@ struct SolveArgs {
     const int32_t* param_idx;
     const int32_t* zero_row_topk;
     const int32_t* feat_sum_order;
+    // solve-only entry (rp_spectral_irls_solve): nodes = correspondences with caller geometry, edges = caller pair list
+    int solve_only;
+    const double* node_wp; const double* node_wn;      // explicit base weights (NULL: row degrees of W)
+    const int32_t* edge_off; const int32_t* edge_rc; const double* edge_w;
     int max_topk;
     long long edge_cap;
     char* ws;               // workspace base; first 256 bytes = header (work counter)
@@ -846,12 +850,13 @@ __global__ void __launch_bounds__(T, RP_MIN_BLOCKS) rp_solve_kernel(const SolveA
         if (st && tid < RP_STATS_STRIDE) st[tid] = 0;
         const int D = A.feat_dim;
 
-        if (ns < 3 || nt < 3) {                                   // rpmodule.py:346-348
+        if (!A.solve_only && (ns < 3 || nt < 3)) {                // rpmodule.py:346-348
             write_identity(Tout);
             if (tid == 0) A.status[b] = RP_STATUS_FEW_KEYPOINTS;
             continue;
         }
         int K = par.topk < nt - 1 ? par.topk : nt - 1;           // rpmodule.py:368
+        if (A.solve_only) K = 1;                                  // nodes are the correspondences themselves
         if (K > KMAX || K > A.max_topk || K < 1 || ns * K > A.Nmax) {
             write_identity(Tout);
             if (tid == 0) A.status[b] = RP_STATUS_UNSUPPORTED;
@@ -882,7 +887,7 @@ __global__ void __launch_bounds__(T, RP_MIN_BLOCKS) rp_solve_kernel(const SolveA
         if (st && tid == 0) { st[0] = N; st[7] = K; }
 
         // ------------------------------------------------------------------ A. descriptor front end
-        {
+        if (!A.solve_only) {
             float* tfeat = reinterpret_cast<float*>(dyn_smem);       // aliases the vectors (not yet live)
             const int ts = A.tfeat_stride;
             const bool vec4 = ((D & 7) == 0) && ((ts & 3) == 0);
@@ -964,7 +969,7 @@ __global__ void __launch_bounds__(T, RP_MIN_BLOCKS) rp_solve_kernel(const SolveA
             if (tid == 0) A.status[b] = RP_STATUS_OK;
             continue;
         }
-        if (N < 3) {                                                 // rpmodule.py:377-379
+        if (!A.solve_only && N < 3) {                                // rpmodule.py:377-379
             write_identity(Tout);
             if (tid == 0) A.status[b] = RP_STATUS_FEW_CORRES;
             continue;
@@ -976,7 +981,7 @@ __global__ void __launch_bounds__(T, RP_MIN_BLOCKS) rp_solve_kernel(const SolveA
             const int gs = pv.gstride;
             double amax = 0.0;
             for (int c = tid; c < N; c += T) {
-                int i = c / K, j = pv.cj[c];
+                int i = c / K, j = A.solve_only ? c : pv.cj[c];      // solve-only: node c carries both sides (t0 == s0)
                 const double* p = A.pc_s + (size_t)(s0 + i) * 3; const double* q = A.pc_t + (size_t)(t0 + j) * 3;
                 const double* n = A.nrm_s + (size_t)(s0 + i) * 3; const double* m = A.nrm_t + (size_t)(t0 + j) * 3;
                 double p0 = p[0], p1 = p[1], p2 = p[2], q0 = q[0], q1 = q[1], q2 = q[2];
@@ -984,7 +989,7 @@ __global__ void __launch_bounds__(T, RP_MIN_BLOCKS) rp_solve_kernel(const SolveA
                 pv.geo[G_QX * gs + c] = q0; pv.geo[G_QY * gs + c] = q1; pv.geo[G_QZ * gs + c] = q2;
                 pv.geo[G_NX * gs + c] = n[0]; pv.geo[G_NY * gs + c] = n[1]; pv.geo[G_NZ * gs + c] = n[2];
                 pv.geo[G_MX * gs + c] = m[0]; pv.geo[G_MY * gs + c] = m[1]; pv.geo[G_MZ * gs + c] = m[2];
-                pv.geo[G_WS * gs + c] = A.w_s[s0 + i]; pv.geo[G_WT * gs + c] = A.w_t[t0 + j];
+                if (!A.solve_only) { pv.geo[G_WS * gs + c] = A.w_s[s0 + i]; pv.geo[G_WT * gs + c] = A.w_t[t0 + j]; }
                 pv.tq4[c] = make_float4((float)q0, (float)q1, (float)q2, 0.f);
                 if (c - i * K == 0) pv.sp4[i] = make_float4((float)p0, (float)p1, (float)p2, 0.f);
                 amax = fmax(amax, fmax(fmax(fabs(p0), fabs(p1)), fmax(fabs(p2), fmax(fabs(q0), fmax(fabs(q1), fabs(q2))))));
@@ -1007,8 +1012,30 @@ __global__ void __launch_bounds__(T, RP_MIN_BLOCKS) rp_solve_kernel(const SolveA
             __syncthreads();
         }
 
+        // ------------------------------------------------------------------ C'/D'. solve-only: import the caller's pair list
+        if (A.solve_only) {
+            const int e0 = A.edge_off ? A.edge_off[b] : 0, ne = A.edge_off ? A.edge_off[b + 1] - e0 : 0;
+            if ((long long)ne > A.edge_cap) {
+                write_identity(Tout);
+                if (tid == 0) A.status[b] = RP_STATUS_EDGE_OVERFLOW;
+                continue;
+            }
+            for (int e = tid; e < ne; e += T) {
+                int r = A.edge_rc[2 * (size_t)(e0 + e)], c = A.edge_rc[2 * (size_t)(e0 + e) + 1];
+                if (r > c) { int t2 = r; r = c; c = t2; }
+                const bool ok = r >= 0 && c < N && r != c;
+                pv.edges[e] = ((unsigned)(ok ? r : 0) << 16) | (unsigned)(ok ? c : 0);
+                pv.ew[e] = ok ? A.edge_w[e0 + e] : -1.0;
+                if (ok) {
+                    atomicOr(&pv.mask[(size_t)r * NW + (c >> 5)], 1u << (c & 31));
+                    atomicOr(&pv.mask[(size_t)c * NW + (r >> 5)], 1u << (r & 31));
+                }
+            }
+            if (tid == 0) { sh.cnt[0] = ne; sh.cnt[1] = ne; sh.cnt[2] = ne; sh.cnt[5] = ne; }
+            __syncthreads();
+        }
         // ------------------------------------------------------------------ C. float32 pre-test -> candidates  (:389-404)
-        {
+        if (!A.solve_only) {
             const float margin = (float)sh.scal[1];
             const float tau = (float)sqrt(par.dist_thre_sq) + margin;       // |ds - dt| < distThre (+margin)
             float sep = (float)par.sep_thre - margin;                       // min(ds,dt) > 1.5*distSepThre^2 (-margin)
@@ -1033,7 +1060,7 @@ __global__ void __launch_bounds__(T, RP_MIN_BLOCKS) rp_solve_kernel(const SolveA
         }
 
         // ------------------------------------------------------------------ D. exact tests + pair weight (:399-467)
-        {
+        if (!A.solve_only) {
             const int gs = pv.gstride; const double* geo = pv.geo;
             int m1 = 0, m2 = 0, nz = 0;
             for (int e = tid; e < MC; e += T) {
@@ -1093,17 +1120,17 @@ __global__ void __launch_bounds__(T, RP_MIN_BLOCKS) rp_solve_kernel(const SolveA
             }
             __syncthreads();
         }
-        if (M1 < 3) {                                                // rpmodule.py:406-408
+        if (!A.solve_only && M1 < 3) {                               // rpmodule.py:406-408
             write_identity(Tout);
             if (tid == 0) A.status[b] = RP_STATUS_FEW_DIST;
             continue;
         }
-        if (M2 < 3) {                                                // rpmodule.py:440-443
+        if (!A.solve_only && M2 < 3) {                               // rpmodule.py:440-443
             write_identity(Tout);
             if (tid == 0) A.status[b] = RP_STATUS_FEW_ANGLE;
             continue;
         }
-        if (NZ < 1) {                                                // rpmodule.py:469-472
+        if (!A.solve_only && NZ < 1) {                               // rpmodule.py:469-472
             write_identity(Tout);
             if (tid == 0) A.status[b] = RP_STATUS_ZERO_WEIGHT;
             continue;
@@ -1186,8 +1213,9 @@ __global__ void __launch_bounds__(T, RP_MIN_BLOCKS) rp_solve_kernel(const SolveA
         const double mu = par.mu;
         int tot_it = 0, max_it_seen = 0, not_conv = 0;
         for (int c = tid; c < N; c += T) {
-            double d = pv.geo[G_DEG * pv.gstride + c];
-            pv.aP[c] = mu * d; pv.aN[c] = d;
+            double dP = pv.geo[G_DEG * pv.gstride + c], dN = dP;
+            if (A.solve_only && A.node_wp) { dP = A.node_wp[s0 + c]; dN = A.node_wn[s0 + c]; }   // stacked-row weights of fit_horn87 / fit_irls
+            pv.aP[c] = mu * dP; pv.aN[c] = dN;
         }
         __syncthreads();
         if (par.method == RP_METHOD_HORN87) {                         // rpmodule.py:60-84
@@ -1370,6 +1398,7 @@ int rp_solve_batch_ex(int B, const int32_t* off_s, const int32_t* off_t,
     a.pc_s = pc_s; a.nrm_s = nrm_s; a.feat_s = feat_s; a.w_s = w_s;
     a.pc_t = pc_t; a.nrm_t = nrm_t; a.feat_t = feat_t; a.w_t = w_t;
     a.feat_dim = feat_dim; a.params = params; a.param_idx = param_idx; a.zero_row_topk = zero_row_topk; a.feat_sum_order = feat_sum_order;
+    a.solve_only = 0; a.node_wp = nullptr; a.node_wn = nullptr; a.edge_off = nullptr; a.edge_rc = nullptr; a.edge_w = nullptr;
     a.max_topk = max_topk; a.edge_cap = L.edge_cap;
     a.ws = static_cast<char*>(workspace); a.slot_bytes = L.slot_bytes;
     a.o_geo = L.o_geo; a.o_cj = L.o_cj; a.o_mask = L.o_mask; a.o_edges = L.o_edges; a.o_ew = L.o_ew;
@@ -1414,6 +1443,62 @@ int rp_match_topk(int B, const int32_t* off_s, const int32_t* off_t,
     return rp_solve_batch_ex(B, off_s, off_t, nullptr, nullptr, feat_s, w_s, nullptr, nullptr, feat_t, w_t, feat_dim,
                              params, param_idx, zero_row_topk, feat_sum_order, max_ns, max_nt, max_topk, n_slots, 0, workspace,
                              workspace_bytes, nullptr, status, nullptr, RP_STAGE_TOPK, &d, stream);
+}
+
+// Stage entry rpmodule.py:484-508 (fitters only): B problems, each a set of correspondences ("nodes": source/target
+// position and normal) and an optional list of consistent pairs ("edges": two node indices and the pair weight w,
+// rpmodule.py:457-467).  With edges: base weights are the row degrees of W (fit_spectral / fit_irls_sm; also
+// fit_horn87 / fit_irls on the helper's stacked rows).  Without edges: explicit per-node weights (allWP, allWN of
+// fit_horn87 / fit_irls; horn87_np = normals only).  Replaces fit_horn87 :60, fit_spectral :86, fit_irls :169,
+// fit_irls_sm :212 and horn87_np :17.
+int rp_spectral_irls_solve(int B, const int32_t* node_off,
+                           const double* sp, const double* sn, const double* tp, const double* tn,
+                           const double* node_wp, const double* node_wn,
+                           const int32_t* edge_off, const int32_t* edge_rc, const double* edge_w,
+                           const rp_params* params, const int32_t* param_idx, int max_nodes,
+                           int n_slots, int64_t edge_cap, void* workspace, size_t workspace_bytes,
+                           double* T_out, int32_t* status, int32_t* stats, void* stream_) {
+    if (B < 0 || !node_off || !sp || !sn || !tp || !tn || !params || !workspace || !T_out || !status) return RP_ERR_INVALID_ARG;
+    if (!edge_off && !(node_wp && node_wn)) return RP_ERR_INVALID_ARG;
+    if (edge_off && (!edge_rc || !edge_w)) return RP_ERR_INVALID_ARG;
+    if (B == 0) return RP_OK;
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    Layout L;
+    if (!make_layout(max_nodes, 1, edge_cap, &L)) return RP_ERR_UNSUPPORTED;
+    SmemPlan S;
+    if (!make_smem_plan(L, 1, 8, &S)) return RP_ERR_UNSUPPORTED;
+    if (cudaFuncSetAttribute(rp_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S.bytes) != cudaSuccess) {
+        cudaGetLastError();
+        return RP_ERR_CUDA;
+    }
+    if (n_slots <= 0) {
+        n_slots = default_slots(S.bytes);
+        if (n_slots < 0) { cudaGetLastError(); return RP_ERR_NO_DEVICE; }
+    }
+    if (workspace_bytes < 256 + (size_t)n_slots * L.slot_bytes) return RP_ERR_WORKSPACE_TOO_SMALL;
+    SolveArgs a = {};
+    a.B = B; a.off_s = node_off; a.off_t = node_off;
+    a.pc_s = sp; a.nrm_s = sn; a.pc_t = tp; a.nrm_t = tn;
+    a.feat_dim = 8; a.params = params; a.param_idx = param_idx;
+    a.solve_only = 1; a.node_wp = node_wp; a.node_wn = node_wn; a.edge_off = edge_off; a.edge_rc = edge_rc; a.edge_w = edge_w;
+    a.max_topk = 1; a.edge_cap = L.edge_cap;
+    a.ws = static_cast<char*>(workspace); a.slot_bytes = L.slot_bytes;
+    a.o_geo = L.o_geo; a.o_cj = L.o_cj; a.o_mask = L.o_mask; a.o_edges = L.o_edges; a.o_ew = L.o_ew;
+    a.o_rowstart = L.o_rowstart; a.o_cols = L.o_cols; a.o_vals = L.o_vals;
+    a.Nmax = L.Nmax; a.NWmax = L.NWmax;
+    a.T_out = T_out; a.status = status; a.stats = stats;
+    a.stop_after = RP_STAGE_SOLVE; a.has_dbg = 0;
+    a.mask_in_smem = S.mask_in_smem; a.tfeat_stride = S.tfeat_stride; a.sm_mask_off = S.mask_off;
+    if (cudaMemsetAsync(workspace, 0, 256, stream) != cudaSuccess) { cudaGetLastError(); return RP_ERR_CUDA; }
+    int grid = B < n_slots ? B : n_slots;
+    rp_solve_kernel<<<grid, T, S.bytes, stream>>>(a);
+    ++g_launches;
+    if (cudaGetLastError() != cudaSuccess) return RP_ERR_CUDA;
+    return RP_OK;
+}
+
+int rp_spectral_irls_workspace_bytes(int n_slots, int max_nodes, int64_t edge_cap, size_t* bytes) {
+    return rp_solve_workspace_bytes(n_slots, max_nodes, 1, 1, 8, edge_cap, bytes);
 }
 
 }  // extern "C"

@@ -319,6 +319,51 @@ class PoseSolver(object):
                 getattr(d, f).record_stream(cs)
         return d, T, status, stats
 
+    def fit_nodes(self, sp, sn, tp, tn, node_off, method, mu, edges=None, node_w=None, power_tol=1e-13, max_power_iters=4000):
+        """Stage entry rp_spectral_irls_solve: B fitting problems over caller-built correspondences ("nodes").
+        sp/sn/tp/tn [sum N,3] float64 host arrays, node_off [B+1]; edges = (edge_off [B+1], rc [sum M,2] local node
+        indices, w [sum M]) or None; node_w = (wp [sum N], wn [sum N]) explicit base weights when there are no edges.
+        Returns poses [B,4,4] (host)."""
+        torch = self.torch
+        dev = self.device
+        node_off = np.ascontiguousarray(node_off, dtype=np.int32)
+        B = len(node_off) - 1
+        if B == 0:
+            return np.zeros([0, 4, 4])
+        p = _lib.RpParams()
+        p.mu, p.power_tol, p.method, p.max_power_iters, p.topk = float(mu), float(power_tol), _lib.METHODS[method], int(max_power_iters), 1
+        par = self._params_device([p])
+        d64 = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64)).to(dev)      # noqa: E731
+        i32 = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.int32)).to(dev)        # noqa: E731
+        t_sp, t_sn, t_tp, t_tn, t_off = d64(sp), d64(sn), d64(tp), d64(tn), i32(node_off)
+        max_nodes = int(np.diff(node_off).max())
+        t_wp = t_wn = t_eo = t_rc = t_ew = None
+        max_edges = 3
+        if edges is not None:
+            eo = np.ascontiguousarray(edges[0], dtype=np.int32)
+            t_eo, t_rc, t_ew = i32(eo), i32(edges[1]), d64(edges[2])
+            max_edges = max(3, int(np.diff(eo).max()))
+        if node_w is not None:
+            t_wp, t_wn = d64(node_w[0]), d64(node_w[1])
+        nbytes = ctypes.c_size_t(0)
+        with torch.cuda.device(dev):
+            _lib.check(self.lib.rp_spectral_irls_workspace_bytes(self.n_slots, max_nodes, max_edges, ctypes.byref(nbytes)),
+                       "rp_spectral_irls_workspace_bytes")
+            ws = torch.empty(nbytes.value, dtype=torch.uint8, device=dev)
+            T = torch.empty((B, 4, 4), dtype=torch.float64, device=dev)
+            status = torch.empty((B,), dtype=torch.int32, device=dev)
+            ptr = lambda t: t.data_ptr() if t is not None else None                              # noqa: E731
+            rc = self.lib.rp_spectral_irls_solve(B, t_off.data_ptr(), t_sp.data_ptr(), t_sn.data_ptr(), t_tp.data_ptr(),
+                                                 t_tn.data_ptr(), ptr(t_wp), ptr(t_wn), ptr(t_eo), ptr(t_rc), ptr(t_ew),
+                                                 par.data_ptr(), None, max_nodes, self.n_slots, max_edges,
+                                                 ws.data_ptr(), ws.numel(), T.data_ptr(), status.data_ptr(), None,
+                                                 torch.cuda.current_stream().cuda_stream)
+            _lib.check(rc, "rp_spectral_irls_solve")
+            st = status.cpu().numpy()
+        if (st != 0).any():
+            raise RuntimeError("rp_spectral_irls_solve: status %s" % st[st != 0][:4])
+        return T.cpu().numpy()
+
     def solve_records(self, records, para, return_stats=False):
         return self.solve_packed(PackedBatch(records), para, return_stats=return_stats)
 
