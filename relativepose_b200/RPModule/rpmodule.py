@@ -101,9 +101,15 @@ def horn87_np(src, tgt, weight=None):
 
 
 def _fit_rows(allSP, allTP, allSN, allTN, allWP, allWN, mu, method):
-    n = allSP.shape[0]
-    return _solver.default_solver().fit_nodes(allSP, allSN, allTP, allTN, np.array([0, n]), method, mu,
-                                              node_w=(np.asarray(allWP, dtype=np.float64), np.asarray(allWN, dtype=np.float64)))[0]
+    # Stacked rows with identical geometry have identical residuals, hence identical IRLS factors: they can be merged
+    # into one node whose base weight is the sum of theirs (the helper stacks every correspondence once per pair).
+    geo = np.concatenate([np.asarray(a, dtype=np.float64).reshape(-1, 3) for a in (allSP, allTP, allSN, allTN)], 1)
+    uniq, inv = np.unique(geo, axis=0, return_inverse=True)
+    inv = inv.reshape(-1)
+    wp = np.bincount(inv, weights=np.asarray(allWP, dtype=np.float64), minlength=len(uniq))
+    wn = np.bincount(inv, weights=np.asarray(allWN, dtype=np.float64), minlength=len(uniq))
+    return _solver.default_solver().fit_nodes(uniq[:, 0:3], uniq[:, 6:9], uniq[:, 3:6], uniq[:, 9:12], np.array([0, len(uniq)]),
+                                              method, mu, node_w=(wp, wn))[0]
 
 
 def fit_horn87(allSP, allTP, allSN, allTN, allWP, allWN, mu):
