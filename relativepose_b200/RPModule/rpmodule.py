@@ -150,3 +150,84 @@ def fit_spectral(allSP, allTP, allSN, allTN, allWP, allWN, w_i1i2j1j2, mu, row, 
 def fit_irls_sm(allSP, allTP, allSN, allTN, allWP, allWN, w_i1i2j1j2, mu, row, col, numFea_s, numFea_t):
     """rpmodule.py:212-315 (the default method)."""
     return _fit_graph(allSP, allTP, allSN, allTN, allWP, allWN, w_i1i2j1j2, mu, row, col, 'irls+sm')
+
+
+def apply_mask(x, maskMethod):
+    """util.apply_mask (util.py:209-232) for the two masks the pipeline uses: 'second' observes skybox face 1 (columns
+    h..2h), 'kinect' a 66x88 window of it.  x: torch [n,c,h,w].  Returns (masked x, mask [n,1,h,w])."""
+    import torch
+    h, w = x.shape[2], x.shape[3]
+    m = torch.zeros((x.shape[0], 1, h, w), dtype=x.dtype, device=x.device)
+    if maskMethod == 'second':
+        m[:, :, :h, h:2 * h] = 1
+    elif maskMethod == 'kinect':
+        assert w == 640 and h == 160
+        dw, dh = int(89.67 // 2), int(67.25 // 2)
+        m[:, :, 80 - dh:80 + dh, 160 + 80 - dw:160 + 80 + dw] = 1
+    else:
+        raise ValueError("unknown maskMethod %r" % (maskMethod,))
+    return x * m, m
+
+
+def RelativePoseEstimationViaCompletion(net, data_s, data_t, args, warping_fn=None, keypoint_fn=None):
+    """The main algorithm (rpmodule.py:569-662): alternate scan completion (``net`` = SCNet) and pairwise matching.
+
+    args: snumclass, featureDim, outputType, maskMethod, alterStep, dataset, para (per-step sigma arrays),
+    representation, completion.  ``warping_fn(view_np [1,8,h,w], R4x4, dataset) -> np [1,8,h,w]`` is util.warping
+    (util.py:94-172; identity pose -> zeros, :95-96) and ``keypoint_fn`` the keypoint stage -- both are the
+    SURVEY.md section 8f "next" rows and have to be supplied (for alterStep == 1 warping is never needed)."""
+    import copy
+    import torch
+    EPS = 1e-12
+    idx_f = 0
+    for key, n in (('rgb', 3), ('n', 3), ('d', 1), ('s', args.snumclass)):
+        if key in args.outputType:
+            idx_f += n
+    idx_f_end = idx_f + args.featureDim
+    dev = next(net.parameters()).device
+
+    def v(a):
+        return torch.as_tensor(np.asarray(a), dtype=torch.float32, device=dev)
+
+    def warp(view, R):
+        if np.linalg.norm(R - np.eye(4)) == 0:                       # util.py:95-96
+            return torch.zeros_like(view)
+        if warping_fn is None:
+            raise NotImplementedError("RelativePoseEstimationViaCompletion needs warping_fn for alterStep > 1 "
+                                      "(util.warping is a SURVEY 8f next row)")
+        return v(warping_fn(view.cpu().numpy(), R, args.dataset))
+
+    with torch.no_grad():
+        R_hat = np.eye(4)
+        full = [torch.cat((v(d['rgb']), v(d['norm']), v(d['depth']).unsqueeze(2)), 2).permute(2, 0, 1).unsqueeze(0)
+                for d in (data_s, data_t)]                           # :599-600
+        views, masks = [], []
+        for c in full:
+            vw, m = apply_mask(c.clone(), args.maskMethod)           # :603-604
+            masks.append(m[0].cpu().numpy().transpose(1, 2, 0))
+            views.append(torch.cat((vw, (vw[:, 6:7] != 0).float()), 1))   # :609-612
+        view_s, view_t = views
+        mask_s, mask_t = masks
+        for alter_ in range(args.alterStep):
+            view_t2s = warp(view_t, np.linalg.inv(R_hat))            # :616-617
+            view_s2t = warp(view_s, R_hat)
+            f = net(torch.cat((torch.cat((view_s, view_t2s), 1), torch.cat((view_t, view_s2t), 1))))   # :619-623
+            comp = []
+            for k, (d, m) in enumerate(((data_s, mask_s), (data_t, mask_t))):
+                fk = f[k].cpu().numpy()
+                nrm = (1 - m) * fk[3:6].transpose(1, 2, 0) + m * d['norm']                # :629-632
+                nrm = nrm / (np.linalg.norm(nrm, axis=2, keepdims=True) + EPS)
+                dep = (1 - m[:, :, 0]) * fk[6] + m[:, :, 0] * d['depth']                 # :633-634
+                c = {'normal': nrm, 'depth': dep, 'obs_mask': m.copy(),
+                     'rgb': (m * d['rgb'] * 255).astype('uint8'), 'feat': f[k, idx_f:idx_f_end]}   # :636-652
+                if 'scannet' in args.dataset:
+                    c['rgb_full'] = (d['rgb_full'] * 255).astype('uint8')
+                    c['depth_full'] = d['depth_full']
+                comp.append(c)
+            para_this = copy.copy(args.para)                         # :654-658
+            for name in ('sigmaAngle1', 'sigmaAngle2', 'sigmaDist', 'sigmaFeat'):
+                setattr(para_this, name, getattr(args.para, name)[alter_])
+            R_hat = RelativePoseEstimation(comp[0], comp[1], para_this, args.dataset, args.representation,
+                                           doCompletion=args.completion, maskMethod=args.maskMethod, index=None,
+                                           keypoint_fn=keypoint_fn)                       # :660
+    return R_hat

