@@ -50,6 +50,11 @@ constexpr double OFFSET = 50.0;     // rpmodule.py:231
 constexpr double EPS = 1e-12;       // rpmodule.py:232
 constexpr double UNOBS_DAMP = 0.6;  // rpmodule.py:467
 constexpr float FEAT_SCALING = 100.0f;  // rpmodule.py:327
+// Pairs whose weight is below PRUNE_REL * (largest pair weight of the scan pair) are left out of the CSR: every sum they
+// enter is dominated by terms >= 1e22 times larger, so in float64 they are exact no-ops (soft-match weights are
+// row-normalised: a keypoint's best candidate has f ~ 1, its other candidates ~ e^-400).  Filters, counts and the
+// surviving-pair set are unaffected; the fitters then only visit correspondences that still have a pair.
+constexpr double PRUNE_REL = 1e-22;
 
 static long long g_launches = 0;
 
@@ -350,7 +355,8 @@ struct Shared {
     double red[2][NWARP][NSUM];
     double fin[32];
     Pose pose;
-    double scal[8];      // 0: lambda warm start, 1: prefilter margin
+    double scal[8];      // 0: lambda warm start, 1: prefilter margin, 2: CSR weight threshold
+    unsigned long long wmax_bits;   // largest pair weight (non-negative doubles order like their bit patterns)
     int cnt[8];          // 0 candidate count, 1 M1, 2 M2, 3 scan carry, 4 pair id, 5 nnz
     int warp_tot[NWARP];
     int warp_tot2[NWARP];
@@ -394,21 +400,24 @@ __device__ void horn_fit(Shared& sh, const PairView& pv, double mean_div, int& r
         // cross-lane traffic is one butterfly per owned sum and there is no cross-warp combine.
         double a0 = 0, a1 = 0, a2 = 0, a3 = 0, a4 = 0, a5 = 0, a6 = 0;
         if (warp == 0) {
-            for (int c = lane; c < pv.N; c += 32) {
+            for (int cr = lane; cr < pv.nrows; cr += 32) {
+                const int c = pv.rowmap[cr] & 0xffffu;
                 double wp = pv.aP[c];
                 a0 += wp;
                 a1 += wp * geo[G_PX * gs + c]; a2 += wp * geo[G_PY * gs + c]; a3 += wp * geo[G_PZ * gs + c];
                 a4 += wp * geo[G_QX * gs + c]; a5 += wp * geo[G_QY * gs + c]; a6 += wp * geo[G_QZ * gs + c];
             }
         } else if (warp == 1) {
-            for (int c = lane; c < pv.N; c += 32) {
+            for (int cr = lane; cr < pv.nrows; cr += 32) {
+                const int c = pv.rowmap[cr] & 0xffffu;
                 double wp = pv.aP[c];
                 double qx = geo[G_QX * gs + c], qy = geo[G_QY * gs + c], qz = geo[G_QZ * gs + c];
                 double wpx = wp * geo[G_PX * gs + c], wpy = wp * geo[G_PY * gs + c];
                 a0 += wpx * qx; a1 += wpx * qy; a2 += wpx * qz; a3 += wpy * qx; a4 += wpy * qy; a5 += wpy * qz;
             }
         } else if (warp == 2) {
-            for (int c = lane; c < pv.N; c += 32) {
+            for (int cr = lane; cr < pv.nrows; cr += 32) {
+                const int c = pv.rowmap[cr] & 0xffffu;
                 double wpz = pv.aP[c] * geo[G_PZ * gs + c];
                 double wnx = pv.aN[c] * geo[G_NX * gs + c];
                 double mx = geo[G_MX * gs + c], my = geo[G_MY * gs + c], mz = geo[G_MZ * gs + c];
@@ -416,7 +425,8 @@ __device__ void horn_fit(Shared& sh, const PairView& pv, double mean_div, int& r
                 a3 += wnx * mx; a4 += wnx * my; a5 += wnx * mz;
             }
         } else {
-            for (int c = lane; c < pv.N; c += 32) {
+            for (int cr = lane; cr < pv.nrows; cr += 32) {
+                const int c = pv.rowmap[cr] & 0xffffu;
                 double wn = pv.aN[c];
                 double wny = wn * geo[G_NY * gs + c], wnz = wn * geo[G_NZ * gs + c];
                 double mx = geo[G_MX * gs + c], my = geo[G_MY * gs + c], mz = geo[G_MZ * gs + c];
@@ -437,7 +447,8 @@ __device__ void horn_fit(Shared& sh, const PairView& pv, double mean_div, int& r
     double acc[NSUM];
 #pragma unroll
     for (int k = 0; k < NSUM; ++k) acc[k] = 0.0;
-    for (int c = tid; c < pv.N; c += T) {
+    for (int cr = tid; cr < pv.nrows; cr += T) {
+        const int c = pv.rowmap[cr] & 0xffffu;
         double wp = pv.aP[c], wn = pv.aN[c];
         double px = geo[G_PX * gs + c], py = geo[G_PY * gs + c], pz = geo[G_PZ * gs + c];
         double qx = geo[G_QX * gs + c], qy = geo[G_QY * gs + c], qz = geo[G_QZ * gs + c];
@@ -523,7 +534,8 @@ __device__ void horn_fit(Shared& sh, const PairView& pv, double mean_div, int& r
 __device__ void residual_pass(const Shared& sh, const PairView& pv, double mu, bool reweight) {
     const Pose& P = sh.pose;
     const double* geo = pv.geo; const int gs = pv.gstride;
-    for (int c = threadIdx.x; c < pv.N; c += T) {
+    for (int cr = threadIdx.x; cr < pv.nrows; cr += T) {
+        const int c = pv.rowmap[cr] & 0xffffu;       // only correspondences that still have a pair carry weight
         double px = geo[G_PX * gs + c] - P.sm[0], py = geo[G_PY * gs + c] - P.sm[1], pz = geo[G_PZ * gs + c] - P.sm[2];
         double qx = geo[G_QX * gs + c] - P.tm[0], qy = geo[G_QY * gs + c] - P.tm[1], qz = geo[G_QZ * gs + c] - P.tm[2];
         double dx = P.R[0] * px + P.R[1] * py + P.R[2] * pz - qx;
@@ -714,7 +726,7 @@ __device__ void x_degrees(Shared& sh, const PairView& pv, double mu) {
 
 // res <- h = max(0, OFFSET - res)   (rpmodule.py:265-266: a = w*(offset - r), clipped at 0)
 __device__ void residual_to_h(const PairView& pv) {
-    for (int c = threadIdx.x; c < pv.N; c += T) pv.res[c] = fmax(0.0, OFFSET - pv.res[c]);
+    for (int cr = threadIdx.x; cr < pv.nrows; cr += T) { const int c = pv.rowmap[cr] & 0xffffu; pv.res[c] = fmax(0.0, OFFSET - pv.res[c]); }
     __syncthreads();
 }
 
@@ -996,7 +1008,7 @@ __global__ void __launch_bounds__(T, RP_MIN_BLOCKS) rp_solve_kernel(const SolveA
             }
             for (int e = tid; e < N * NW; e += T) pv.mask[e] = 0u;
             if (tid < 8) sh.cnt[tid] = (tid == 4) ? b : 0;
-            if (tid == 0) sh.scal[0] = 0.0;
+            if (tid == 0) { sh.scal[0] = 0.0; sh.scal[2] = 0.0; sh.wmax_bits = 0ull; }
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) amax = fmax(amax, shfl_xor_d(amax, o));
             if (lane == 0) sh.red[red_buf][warp][0] = amax;
@@ -1063,6 +1075,7 @@ __global__ void __launch_bounds__(T, RP_MIN_BLOCKS) rp_solve_kernel(const SolveA
         if (!A.solve_only) {
             const int gs = pv.gstride; const double* geo = pv.geo;
             int m1 = 0, m2 = 0, nz = 0;
+            double wloc = 0.0;
             for (int e = tid; e < MC; e += T) {
                 unsigned rc = pv.edges[e];
                 int r = rc >> 16, c = rc & 0xffffu;
@@ -1092,14 +1105,31 @@ __global__ void __launch_bounds__(T, RP_MIN_BLOCKS) rp_solve_kernel(const SolveA
                         double seen = __dmul_rn(__dmul_rn(__dmul_rn(geo[G_WS * gs + r], geo[G_WS * gs + c]), geo[G_WT * gs + r]), geo[G_WT * gs + c]);   // :462-466
                         if (seen != 1.0) w *= UNOBS_DAMP;                                                                      // :467
                         ++m2; if (w != 0.0) ++nz;
-                        atomicOr(&pv.mask[(size_t)r * NW + (c >> 5)], 1u << (c & 31));
-                        atomicOr(&pv.mask[(size_t)c * NW + (r >> 5)], 1u << (r & 31));
+                        wloc = fmax(wloc, w);
                     }
                 }
                 pv.ew[e] = w;
             }
             m1 = __reduce_add_sync(0xffffffffu, m1); m2 = __reduce_add_sync(0xffffffffu, m2); nz = __reduce_add_sync(0xffffffffu, nz);
-            if (lane == 0) { atomicAdd(&sh.cnt[1], m1); atomicAdd(&sh.cnt[2], m2); atomicAdd(&sh.cnt[5], nz); }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) wloc = fmax(wloc, shfl_xor_d(wloc, o));
+            if (lane == 0) {
+                atomicAdd(&sh.cnt[1], m1); atomicAdd(&sh.cnt[2], m2); atomicAdd(&sh.cnt[5], nz);
+                atomicMax(&sh.wmax_bits, (unsigned long long)__double_as_longlong(wloc));
+            }
+            __syncthreads();
+            // second, light pass: pairs that matter numerically enter the symmetric bit mask (-> CSR)
+            const double thr = PRUNE_REL * __longlong_as_double((long long)sh.wmax_bits);
+            if (tid == 0) sh.scal[2] = thr;
+            for (int e = tid; e < MC; e += T) {
+                const double w = pv.ew[e];
+                if (w >= thr && w >= 0.0) {
+                    unsigned rc = pv.edges[e];
+                    int r = rc >> 16, c = rc & 0xffffu;
+                    atomicOr(&pv.mask[(size_t)r * NW + (c >> 5)], 1u << (c & 31));
+                    atomicOr(&pv.mask[(size_t)c * NW + (r >> 5)], 1u << (r & 31));
+                }
+            }
             __syncthreads();
         }
         const int M1 = sh.cnt[1], M2 = sh.cnt[2], NZ = sh.cnt[5];
@@ -1190,9 +1220,10 @@ __global__ void __launch_bounds__(T, RP_MIN_BLOCKS) rp_solve_kernel(const SolveA
                 if (re > rs) pv.rowmap[cidx[r]] = (unsigned)r | ((unsigned)(rs / E) << 16) | ((unsigned)((re - 1) / E) << 24);
                 else pv.geo[G_DEG * pv.gstride + r] = 0.0;
             }
+            const double csr_thr = sh.scal[2];
             for (int e = tid; e < MC; e += T) {
                 double w = pv.ew[e];
-                if (w < 0.0) continue;
+                if (w < 0.0 || w < csr_thr) continue;
                 unsigned rc = pv.edges[e];
                 int r = rc >> 16, c = rc & 0xffffu;
                 const int rs_r = pv.rowstart[r], rs_c = pv.rowstart[c];
@@ -1206,6 +1237,12 @@ __global__ void __launch_bounds__(T, RP_MIN_BLOCKS) rp_solve_kernel(const SolveA
             }
             __syncthreads();
             { DegStep dg; dg.deg = pv.geo + (size_t)G_DEG * pv.gstride; csr_walk(sh, pv, dg); }   // row degrees of W
+            __syncthreads();
+        }
+
+        if (A.solve_only && A.node_wp) {        // explicit per-node weights (no pair list): every node is active
+            for (int c = tid; c < N; c += T) pv.rowmap[c] = (unsigned)c;
+            pv.nrows = N;
             __syncthreads();
         }
 
