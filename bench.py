@@ -32,7 +32,7 @@ METRIC = "scan-pairs/sec (R,t solved) at N=512 corr"
 UNIT = "pairs/s"
 N_NOMINAL = 512
 TOPK = 5
-DRAM_BYTES_PER_PAIR_NCU = 345_800      # measured, see roofline.traffic_source
+DRAM_BYTES_PER_PAIR_NCU = 300_950      # measured, see roofline.traffic_source
 
 
 def parse():
@@ -280,8 +280,8 @@ def run_cuda_arm(args):
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": DRAM_BYTES_PER_PAIR_NCU * B, "traffic_source": "ncu --set full dram__bytes_read+write "
-                     "per pair at N_actual=515 (profiles/r1_solver_ncu_summary.txt, v5: 409 MB / 1184 pairs) x pairs per launch",
+                     "traffic": DRAM_BYTES_PER_PAIR_NCU * B, "traffic_source": "ncu --set full dram__bytes_read+write of this "
+                     "bench launch (profiles/r1_solver_bench_launch_ncu.txt: 1232.7 MB / 4096 pairs) x pairs per launch",
                      "peak_source": peak_src, "kernel": "rp_solve_kernel",
                      "kernel_ms": float(np.mean(kern_ms)),
                      "model": "SURVEY 8(d) dense-equivalent bytes: 4*N^2*(2+sum_a(It_a+1)) + 156*(n_s+n_t) per pair with the "
