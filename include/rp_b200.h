@@ -182,7 +182,7 @@ typedef struct rp_conv_src {
     int32_t sstride;
     int32_t s_off;
     float slope;          /* negative slope of the activation applied with act=1: 0.1 = LeakyReLU (SCNet), 0 = ReLU (ResNet) */
-    int32_t reserved;
+    int32_t dtype;        /* storage type of ptr: 0 = float32, 1 = bfloat16 (tensor-core kernels only) */
 } rp_conv_src;
 
 typedef struct rp_conv_desc {
@@ -201,6 +201,7 @@ typedef struct rp_conv_desc {
     const float* bias;    /* [Cout] or NULL (the 1x1 heads, mymodel.py:188,196,204,220,228) */
     int32_t tanh_out;     /* mymodel.py:374-375 */
     int32_t imgs_per_group; /* images per BN batch: 0 or 2 = one scan pair (SCNet); Resnet18_8s uses the whole call */
+    int32_t out_dtype;    /* storage type of out: 0 = float32, 1 = bfloat16 (tensor-core kernels and the small-Cin stem) */
 } rp_conv_desc;
 
 /* number of partial-statistics rows per group the layer writes (psum/psq are [G, nparts, Cout]) */
@@ -256,6 +257,18 @@ int64_t rp_conv_launch_count(void);
  * layer's weight tensor as bf16 blocks in the UMMA shared-memory image; see csrc/scnet_tc.cu. */
 int rp_conv_nparts_tc(const rp_conv_desc* d, int* nparts);
 int rp_conv_layer_tc(const rp_conv_desc* d, const void* w_packed, int bn, int tk, void* stream);
+
+/* Halo-tile variant (csrc/scnet_halo.cu): a CTA stages the input halo of a 16x8 block of output positions once per
+ * K chunk and every (sub-pixel class, tap) MMA reads it through a shifted shared-memory descriptor, so a 4x4 kernel no
+ * longer re-gathers its input 16 times.  bn in {32,64,128} with Cout % bn == 0, tk in {32,64} with every source
+ * C % tk == 0, at most 16 (class, tap) blocks, no bias/tanh.  flags bit 0: pad the halo row pitch to 16 pixels.
+ * rp_conv_halo_plan returns the partial-statistics rows per group, the number of (class, tap) weight blocks per
+ * K chunk and their order (tap_widx[i] = ky*k+kx, room for 16); w_packed is bf16
+ * [n-tile][K chunk][block][tk/8][bn/8][8 co][8 ci] (relativepose_b200/scnet_engine.py:pack_halo). */
+int rp_conv_halo_plan(const rp_conv_desc* d, int bn, int tk, int flags, int* nparts, int* ntap, int* tap_widx);
+int rp_conv_layer_halo(const rp_conv_desc* d, const void* w_packed, int bn, int tk, int flags, void* stream);
+/* test hook: the tile plan as 96 integers (layout in csrc/scnet_halo.cu) for the CPU emulation in tests/test_halo_plan.py */
+int rp_conv_halo_debug(const rp_conv_desc* d, int bn, int tk, int flags, int* out96);
 
 /* Unit-test hook for the tcgen05/TMEM building blocks: C[M,N] = A[M,K] * B[N,K]^T (device pointers, float32 in/out,
  * bf16-rounded operands, fp32 accumulation in TMEM).  M % 128 == 0, K % 64 == 0, bn in {64,128}, N % bn == 0. */

@@ -43,7 +43,7 @@ class RpConvSrc(ctypes.Structure):
     _fields_ = [("ptr", ctypes.c_void_p), ("pitch", ctypes.c_int32), ("ch_off", ctypes.c_int32),
                 ("C", ctypes.c_int32), ("act", ctypes.c_int32), ("scale", ctypes.c_void_p),
                 ("shift", ctypes.c_void_p), ("sstride", ctypes.c_int32), ("s_off", ctypes.c_int32),
-                ("slope", ctypes.c_float), ("reserved", ctypes.c_int32)]
+                ("slope", ctypes.c_float), ("dtype", ctypes.c_int32)]
 
 
 class RpConvDesc(ctypes.Structure):
@@ -53,13 +53,14 @@ class RpConvDesc(ctypes.Structure):
                 ("Cout", ctypes.c_int32), ("W", ctypes.c_void_p), ("out", ctypes.c_void_p),
                 ("out_pitch", ctypes.c_int32), ("out_ch_off", ctypes.c_int32), ("psum", ctypes.c_void_p),
                 ("psq", ctypes.c_void_p), ("bias", ctypes.c_void_p), ("tanh_out", ctypes.c_int32),
-                ("imgs_per_group", ctypes.c_int32)]
+                ("imgs_per_group", ctypes.c_int32), ("out_dtype", ctypes.c_int32)]
 
 
 EXPORTS = ("rp_abi_version", "rp_device_info", "rp_solve_workspace_bytes", "rp_solve_batch",
            "rp_solve_batch_ex", "rp_match_topk", "rp_launch_count", "rp_spectral_irls_solve", "rp_spectral_irls_workspace_bytes",
            "rp_conv_nparts", "rp_conv_layer", "rp_bn_finalize", "rp_scnet_resize_in", "rp_scnet_resize_out",
            "rp_conv_launch_count", "rp_tc_gemm_test", "rp_conv_nparts_tc", "rp_conv_layer_tc",
+           "rp_conv_halo_plan", "rp_conv_layer_halo", "rp_conv_halo_debug",
            "rp_bn_relu_maxpool", "rp_bn_add_relu", "rp_resize_nhwc", "rp_resize_to_nchw", "rp_interpolate")
 
 _lib = None
@@ -114,6 +115,13 @@ def load():
     lib.rp_conv_nparts_tc.argtypes = [ctypes.POINTER(RpConvDesc), ctypes.POINTER(ctypes.c_int)]
     lib.rp_conv_layer_tc.restype = i32
     lib.rp_conv_layer_tc.argtypes = [ctypes.POINTER(RpConvDesc), vp, i32, i32, vp]
+    lib.rp_conv_halo_plan.restype = i32
+    lib.rp_conv_halo_plan.argtypes = [ctypes.POINTER(RpConvDesc), i32, i32, i32, ctypes.POINTER(ctypes.c_int),
+                                      ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int)]
+    lib.rp_conv_halo_debug.restype = i32
+    lib.rp_conv_halo_debug.argtypes = [ctypes.POINTER(RpConvDesc), i32, i32, i32, ctypes.POINTER(ctypes.c_int)]
+    lib.rp_conv_layer_halo.restype = i32
+    lib.rp_conv_layer_halo.argtypes = [ctypes.POINTER(RpConvDesc), vp, i32, i32, i32, vp]
     lib.rp_bn_relu_maxpool.restype = i32
     lib.rp_bn_relu_maxpool.argtypes = [vp, i32, i32, i32, i32, i32, vp, vp, vp, i32, i32, vp]
     lib.rp_bn_add_relu.restype = i32

@@ -10,6 +10,7 @@
 //
 // This file: float32 CUDA-core implicit GEMM (exact-parity path, tolerance 1e-4 max-abs vs the reference
 // module) + resize / BN-finalise kernels.  The tcgen05 core for the large layers lives in scnet_tc.cu (round 2).
+#include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
@@ -279,9 +280,25 @@ __global__ void __launch_bounds__(128) conv3x3_small_cin(const ConvArgs A) {
                     for (int j = 0; j < 32; ++j) acc[j] = fmaf(x[c], w[c * 32 + j], acc[j]);
             }
         }
-        float* op = A.out + (((size_t)(g * 2 + im) * A.Hout + oy) * A.Wout + ox) * A.out_pitch + A.out_ch_off;
+        const size_t e = (((size_t)(g * 2 + im) * A.Hout + oy) * A.Wout + ox) * A.out_pitch + A.out_ch_off;
+        if (A.out_bf16) {          // bfloat16 storage: round first so the statistics describe the stored tensor
+            __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(A.out) + e;
 #pragma unroll
-        for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(op + j) = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
+            for (int j = 0; j < 32; j += 8) {
+                __nv_bfloat162 p[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    p[q] = __floats2bfloat162_rn(acc[j + 2 * q], acc[j + 2 * q + 1]);
+                    const float2 f = __bfloat1622float2(p[q]);
+                    acc[j + 2 * q] = f.x; acc[j + 2 * q + 1] = f.y;
+                }
+                *reinterpret_cast<uint4*>(op + j) = *reinterpret_cast<uint4*>(p);
+            }
+        } else {
+            float* op = A.out + e;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(op + j) = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
+        }
     }
     if (A.psum) {       // per-channel sums over the 128 pixels of this CTA: butterfly per warp, 4 warps combined in order
 #pragma unroll
@@ -403,7 +420,7 @@ __global__ void interpolate_kernel(const float* __restrict__ feat, int C, int H,
 inline bool small_cin_eligible(const rp_conv_desc* d) {
     return d->nsrc == 1 && !d->transposed && d->k == 3 && d->s == 1 && d->p == 1 && d->Cout == 32 && !d->bias &&
            !d->tanh_out && d->src[0].act == 0 && (d->src[0].C == 4 || d->src[0].C == 2) &&
-           (d->out_pitch % 4 == 0) && (d->out_ch_off % 4 == 0) && d->Hin == d->Hout && d->Win == d->Wout && (d->imgs_per_group == 0 || d->imgs_per_group == 2);
+           d->src[0].dtype == 0 && (d->out_pitch % (d->out_dtype == 1 ? 8 : 4) == 0) && (d->out_ch_off % (d->out_dtype == 1 ? 8 : 4) == 0) && d->Hin == d->Hout && d->Win == d->Wout && (d->imgs_per_group == 0 || d->imgs_per_group == 2);
 }
 
 }  // namespace
@@ -434,6 +451,8 @@ int rp_conv_layer(const rp_conv_desc* d, void* stream_) {
         ++g_conv_launches;
         return cudaGetLastError() == cudaSuccess ? RP_OK : RP_ERR_CUDA;
     }
+    if (d->out_dtype != 0) return RP_ERR_UNSUPPORTED;          // the float32 implicit GEMM reads and writes float32 only
+    for (int i = 0; i < d->nsrc; ++i) if (d->src[i].dtype != 0) return RP_ERR_UNSUPPORTED;
     dim3 grid(A.tiles_m, (A.Cout + BN_ - 1) / BN_, A.G * A.nclass);
     conv_igemm_f32<<<grid, CT, 0, stream>>>(A);
     ++g_conv_launches;

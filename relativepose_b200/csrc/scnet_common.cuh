@@ -24,6 +24,7 @@ struct ConvArgs {
     float* out; int out_pitch, out_ch_off;
     float* psum; float* psq;
     const float* bias; int tanh_out;
+    int out_bf16;       // raw output stored as bfloat16 (tensor-core kernels, small-Cin stem)
 };
 
 
@@ -39,6 +40,7 @@ inline bool build_args(const rp_conv_desc* d, ConvArgs* A, int bm) {
     A->G = d->G; A->Hin = d->Hin; A->Win = d->Win; A->Hout = d->Hout; A->Wout = d->Wout; A->Cout = d->Cout;
     A->W = d->W; A->out = d->out; A->out_pitch = d->out_pitch; A->out_ch_off = d->out_ch_off;
     A->psum = d->psum; A->psq = d->psq; A->bias = d->bias; A->tanh_out = d->tanh_out;
+    A->out_bf16 = d->out_dtype == 1 ? 1 : 0;
     const int k = d->k, s = d->s, p = d->p;
     if (!d->transposed) {
         // iy = oy*s - p + ky

@@ -16,85 +16,9 @@
 #include "../../include/rp_b200.h"
 #include "scnet_common.cuh"
 
+#include "tc_prims.cuh"
+
 namespace tc {
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-// UMMA shared-memory descriptor, K-major, SWIZZLE_NONE, version 1 (Blackwell).
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-    uint64_t d = 0;
-    d |= (uint64_t)((saddr >> 4) & 0x3fffu);              // start address  [0,14)
-    d |= (uint64_t)((lbo_bytes >> 4) & 0x3fffu) << 16;     // leading (K) byte offset  [16,30)
-    d |= (uint64_t)((sbo_bytes >> 4) & 0x3fffu) << 32;     // stride (M/N) byte offset [32,46)
-    d |= (uint64_t)1 << 46;                                // version = 1
-    return d;                                              // base_offset 0, lbo_mode 0, layout_type 0 (no swizzle)
-}
-
-// UMMA instruction descriptor: D=f32, A=B=bf16, both K-major, dense, M x N.
-__host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
-    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
-}
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    uint32_t done = 0;
-    const uint32_t a = smem_u32(bar);
-    while (!done) {
-        asm volatile("{\n\t.reg .pred p;\n\t"
-                     "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-                     "selp.u32 %0, 1, 0, p;\n\t}"
-                     : "=r"(done) : "r"(a), "r"(parity) : "memory");
-    }
-}
-__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-__device__ __forceinline__ void tmem_alloc(uint32_t* slot, uint32_t ncols) {      // whole warp
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(ncols) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {     // whole warp
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
-}
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile("{\n\t.reg .pred p;\n\t"
-                 "setp.ne.b32 p, %4, 0;\n\t"
-                 "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-                 ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-// 32 lanes x 32 columns of 32-bit: thread <-> TMEM lane (row of the accumulator), registers <-> columns
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
-    uint32_t* r = reinterpret_cast<uint32_t*>(v);
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-                 "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-                 "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-                   "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-                   "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-                 : "r"(taddr) : "memory");
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-
-// 8 consecutive K elements of one row -> one 16-byte unit of the canonical layout
-__device__ __forceinline__ void store_core_row(unsigned char* tile, int rows, int row, int kc, const float* v8) {
-    __nv_bfloat162 p0 = __floats2bfloat162_rn(v8[0], v8[1]);
-    __nv_bfloat162 p1 = __floats2bfloat162_rn(v8[2], v8[3]);
-    __nv_bfloat162 p2 = __floats2bfloat162_rn(v8[4], v8[5]);
-    __nv_bfloat162 p3 = __floats2bfloat162_rn(v8[6], v8[7]);
-    uint4 u;
-    u.x = *reinterpret_cast<uint32_t*>(&p0); u.y = *reinterpret_cast<uint32_t*>(&p1);
-    u.z = *reinterpret_cast<uint32_t*>(&p2); u.w = *reinterpret_cast<uint32_t*>(&p3);
-    const int off = ((kc * (rows >> 3) + (row >> 3)) * 8 + (row & 7)) * 16;
-    *reinterpret_cast<uint4*>(tile + off) = u;
-}
 
 constexpr int TM = 128;     // UMMA M
 constexpr int TK = 64;      // K per pipeline stage (4 MMAs)
@@ -186,14 +110,6 @@ __global__ void __launch_bounds__(128) gemm_bf16_test(const float* __restrict__ 
 constexpr int NS = 3;
 constexpr int CTA = 256;
 
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
-
 // A-tile geometry: K-core stride (LBO) padded by 16 bytes so that the 8 lanes that stage the 8 K-cores of one pixel
 // row hit 8 different 16-byte bank groups (conflict-free STS.128) while reading one contiguous 256-byte run of global.
 constexpr int A_LBO = (TM / 8) * 128 + 16;
@@ -272,23 +188,30 @@ __global__ void __launch_bounds__(CTA, 2) conv_igemm_tc(const scnet::ConvArgs A,
         bulk_g2s(smem + A_BYTES, weight_block(0), B_BYTES, &fullb_bar[0]);
     }
 
-    // raw A registers for the current and the next iteration (software pipelining of the gather)
-    float4 xc[NI][2], xn[NI][2];
+    // raw A registers for the current and the next iteration (software pipelining of the gather); 8 channels per
+    // item = 32 bytes of float32 or 16 bytes of bfloat16 storage
+    uint4 xc[NI][2], xn[NI][2];
     bool vc[NI], vn[NI];
-    auto issue_loads = [&](int i, float4 (&x)[NI][2], bool (&v)[NI]) {
+    auto issue_loads = [&](int i, uint4 (&x)[NI][2], bool (&v)[NI]) {
         const int t = i / nkt, kt = i - t * nkt;
         const scnet::Tap tp = C.taps[t];
         const int si = kt < nkt0 ? 0 : 1;
         const rp_conv_src& S = A.src[si];
         const int c0 = (kt - (si ? nkt0 : 0)) * TK + kc_l * 8;
+        const bool h16 = S.dtype == 1;
 #pragma unroll
         for (int j = 0; j < NI; ++j) {
             const int iy = l_a[j] * A.istr + tp.dy, ix = l_b[j] * A.istr + tp.dx;
             v[j] = l_val[j] && iy >= 0 && iy < A.Hin && ix >= 0 && ix < A.Win;
             if (v[j]) {
-                const float* p = S.ptr + (((size_t)l_img[j] * A.Hin + iy) * A.Win + ix) * S.pitch + S.ch_off + c0;
-                x[j][0] = *reinterpret_cast<const float4*>(p);
-                x[j][1] = *reinterpret_cast<const float4*>(p + 4);
+                const size_t e = (((size_t)l_img[j] * A.Hin + iy) * A.Win + ix) * S.pitch + S.ch_off + c0;
+                if (h16) {
+                    x[j][0] = *reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(S.ptr) + e);
+                } else {
+                    const uint4* p = reinterpret_cast<const uint4*>(S.ptr + e);
+                    x[j][0] = p[0];
+                    x[j][1] = p[1];
+                }
             }
         }
     };
@@ -313,13 +236,23 @@ __global__ void __launch_bounds__(CTA, 2) conv_igemm_tc(const scnet::ConvArgs A,
         const float hv[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
         const bool act = A.src[kt < nkt0 ? 0 : 1].act != 0;
         const float slope = A.src[kt < nkt0 ? 0 : 1].slope;
+        const bool h16 = A.src[kt < nkt0 ? 0 : 1].dtype == 1;
         mbar_wait(&empty_bar[stage], (uint32_t)((use & 1) ^ 1));     // MMAs that read this stage are done
 #pragma unroll
         for (int j = 0; j < NI; ++j) {
             const int prow = prow0 + j * ROWS_PER_PASS;
             uint4 u = make_uint4(0u, 0u, 0u, 0u);
             if (vc[j]) {
-                float v[8] = {xc[j][0].x, xc[j][0].y, xc[j][0].z, xc[j][0].w, xc[j][1].x, xc[j][1].y, xc[j][1].z, xc[j][1].w};
+                float v[8];
+                if (h16) {
+                    const __nv_bfloat162* hp = reinterpret_cast<const __nv_bfloat162*>(&xc[j][0]);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) { const float2 f = __bfloat1622float2(hp[q]); v[2 * q] = f.x; v[2 * q + 1] = f.y; }
+                } else {
+                    v[0] = __uint_as_float(xc[j][0].x); v[1] = __uint_as_float(xc[j][0].y); v[2] = __uint_as_float(xc[j][0].z);
+                    v[3] = __uint_as_float(xc[j][0].w); v[4] = __uint_as_float(xc[j][1].x); v[5] = __uint_as_float(xc[j][1].y);
+                    v[6] = __uint_as_float(xc[j][1].z); v[7] = __uint_as_float(xc[j][1].w);
+                }
                 if (act) {
 #pragma unroll
                     for (int q = 0; q < 8; ++q) { float z = fmaf(v[q], sv[q], hv[q]); v[q] = z > 0.f ? z : slope * z; }
@@ -358,12 +291,14 @@ __global__ void __launch_bounds__(CTA, 2) conv_igemm_tc(const scnet::ConvArgs A,
     // ---- epilogue (warps 0-3 own the TMEM lanes; all 8 warps help with the column sums)
     float* Tt = reinterpret_cast<float*>(smem);            // [128][33] transpose buffer
     float* op = nullptr;
+    __nv_bfloat16* oph = nullptr;
     if (warp < 4) {
         const int m_l = tile_m * TM + row;
         if (m_l < Mc) {
             const int im = m_l / HW; const int rem = m_l - im * HW; const int a_l = rem / C.Wb, b_l = rem - a_l * C.Wb;
             const int oy = a_l * A.ostr + C.py, ox = b_l * A.ostr + C.px;
-            op = A.out + (((size_t)(g * A.gsz + im) * A.Hout + oy) * A.Wout + ox) * A.out_pitch + A.out_ch_off;
+            const size_t e = (((size_t)(g * A.gsz + im) * A.Hout + oy) * A.Wout + ox) * A.out_pitch + A.out_ch_off;
+            if (A.out_bf16) oph = reinterpret_cast<__nv_bfloat16*>(A.out) + e; else op = A.out + e;
         }
     }
     for (int c0 = 0; c0 < BN; c0 += 32) {
@@ -375,6 +310,26 @@ __global__ void __launch_bounds__(CTA, 2) conv_igemm_tc(const scnet::ConvArgs A,
 #pragma unroll
                 for (int j = 0; j < 32; ++j) {
                     if (co0 + j < A.Cout) { float y = v[j] + (A.bias ? A.bias[co0 + j] : 0.f); v[j] = A.tanh_out ? tanhf(y) : y; }
+                }
+            }
+            if (A.out_bf16) {       // round to the storage type first: the statistics describe what the consumer reads
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = __bfloat162float(__float2bfloat16_rn(v[j]));
+                if (oph) {
+                    if (co0 + 31 < A.Cout && (((size_t)(oph + co0)) & 15) == 0) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 8) {
+                            __nv_bfloat162 p0 = __floats2bfloat162_rn(v[j], v[j + 1]), p1 = __floats2bfloat162_rn(v[j + 2], v[j + 3]);
+                            __nv_bfloat162 p2 = __floats2bfloat162_rn(v[j + 4], v[j + 5]), p3 = __floats2bfloat162_rn(v[j + 6], v[j + 7]);
+                            uint4 o;
+                            o.x = *reinterpret_cast<uint32_t*>(&p0); o.y = *reinterpret_cast<uint32_t*>(&p1);
+                            o.z = *reinterpret_cast<uint32_t*>(&p2); o.w = *reinterpret_cast<uint32_t*>(&p3);
+                            *reinterpret_cast<uint4*>(oph + co0 + j) = o;
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) if (co0 + j < A.Cout) oph[co0 + j] = __float2bfloat16_rn(v[j]);
+                    }
                 }
             }
             if (op) {
@@ -461,7 +416,8 @@ int rp_conv_layer_tc(const rp_conv_desc* d, const void* w_packed, int bn, int tk
     int nkt = 0;
     if (A.Cin_total > tc::MAX_CIN) return RP_ERR_UNSUPPORTED;
     for (int i = 0; i < d->nsrc; ++i) {
-        if (d->src[i].C % tk || (d->src[i].pitch % 4) || (d->src[i].ch_off % 4)) return RP_ERR_UNSUPPORTED;
+        const int al = d->src[i].dtype == 1 ? 8 : 4;
+        if (d->src[i].C % tk || (d->src[i].pitch % al) || (d->src[i].ch_off % al)) return RP_ERR_UNSUPPORTED;
         if (d->src[i].act && ((d->src[i].sstride % 4) || (d->src[i].s_off % 4))) return RP_ERR_UNSUPPORTED;
         nkt += d->src[i].C / tk;
     }

@@ -7,6 +7,7 @@ from .scnet_engine import ScnetEngine, _Act
 
 class ResnetEngine(ScnetEngine):
     _slope = 0.0          # ReLU
+    _act_default = 'fp32' # the pooling / residual / resize kernels of the trunk are float32
 
     def __init__(self, net, mode=None):
         ScnetEngine.__init__(self, net, mode)

@@ -18,6 +18,7 @@ class _Act(object):
     def __init__(self, buf, H, W, pitch, ch_off, C, scale=None, shift=None):
         self.buf, self.H, self.W, self.pitch, self.ch_off, self.C = buf, H, W, pitch, ch_off, C
         self.scale, self.shift = scale, shift
+        self.dtype = 1 if buf.element_size() == 2 else 0          # rp_conv_src.dtype: 0 float32, 1 bfloat16
 
     def view(self, ch_off, C):
         return _Act(self.buf, self.H, self.W, self.pitch, self.ch_off + ch_off, C, self.scale, self.shift)
@@ -44,7 +45,33 @@ def pack_tc(w_taps, src_channels, cout, bn, tk):
     return Wt.to(torch.bfloat16).contiguous()
 
 
+def pack_halo(w_taps, tap_widx, src_channels, cout, bn, tk):
+    import torch
+    return _pack_halo_f32(w_taps, tap_widx, src_channels, cout, bn, tk).to(torch.bfloat16).contiguous()
+
+
+def _pack_halo_f32(w_taps, tap_widx, src_channels, cout, bn, tk):
+    """Weights [taps, Cin_total, Cout] fp32 -> bf16 blocks [n-tile][K chunk][block][tk/8][bn/8][8 (co)][8 (ci)] for the
+    halo kernel (csrc/scnet_halo.cu): block i of a K chunk is tap ``tap_widx[i]`` (the (class, tap) order reported by
+    rp_conv_halo_plan), so the blocks one CTA consumes are contiguous and in consumption order."""
+    import torch
+    assert cout % bn == 0
+    ntn = cout // bn
+    k0s, base = [], 0
+    for c in src_channels:
+        assert c % tk == 0
+        k0s += [base + c0 for c0 in range(0, c, tk)]
+        base += c
+    W = w_taps[list(tap_widx)]                                                  # [nb, Cin, Cout]
+    Wt = torch.stack([W[:, k0:k0 + tk, :] for k0 in k0s], 0)                    # [kt, nb, tk, Cout]
+    Wt = Wt.reshape(len(k0s), len(tap_widx), tk // 8, 8, ntn, bn // 8, 8)       # [kt, nb, kc, kk, nt, nc, r]
+    return Wt.permute(4, 0, 1, 2, 5, 6, 3).contiguous()                         # [nt, kt, nb, kc, nc, r, kk]
+
+
 class ScnetEngine(object):
+    _act_default = 'bf16'    # storage of the BN'd activations in 'tc' mode (ResnetEngine: float32, its pooling /
+                             # residual kernels are float32)
+
     def __init__(self, net, mode=None):
         import os
         import torch
@@ -52,6 +79,11 @@ class ScnetEngine(object):
         self.mode = mode or os.environ.get("RP_SCNET_MODE", "tc")
         # replay the ~87 layer launches of a forward as one CUDA graph once a shape has been seen twice
         self.use_graph = os.environ.get("RP_SCNET_GRAPH", "1") == "1"
+        # halo-tile tcgen05 kernel for the 3x3 / 4x4 layers with a large enough spatial extent (csrc/scnet_halo.cu)
+        self.halo = os.environ.get("RP_SCNET_HALO", "1") == "1"
+        self.halo_flags = int(os.environ.get("RP_SCNET_HALO_FLAGS", "0"))
+        act = os.environ.get("RP_SCNET_ACT", self._act_default)
+        self.act_bf16 = self.mode == 'tc' and act == 'bf16'
         self._graphs = {}
         self._seen = {}
         self.torch = torch
@@ -93,10 +125,11 @@ class ScnetEngine(object):
             return
         n = 2 * P
         f = dict(dtype=torch.float32, device=device)
+        fa = dict(dtype=torch.bfloat16 if self.act_bf16 else torch.float32, device=device)
         B = {}
 
         def act(name, H, W, C):
-            B[name] = _Act(torch.empty((n, H, W, C), **f), H, W, C, 0, C,
+            B[name] = _Act(torch.empty((n, H, W, C), **fa), H, W, C, 0, C,
                            torch.empty((P, C), **f), torch.empty((P, C), **f))
 
         B['in20'] = _Act(torch.empty((n, 224, 224, 20), **f), 224, 224, 20, 0, 20)
@@ -129,6 +162,7 @@ class ScnetEngine(object):
         for i, a in enumerate(srcs):
             d.src[i].ptr = a.buf.data_ptr()
             d.src[i].pitch, d.src[i].ch_off, d.src[i].C = a.pitch, a.ch_off, a.C
+            d.src[i].dtype = a.dtype
             if a.scale is not None:
                 d.src[i].act = 1
                 d.src[i].slope = self._slope
@@ -141,8 +175,30 @@ class ScnetEngine(object):
         d.Hin, d.Win, d.Hout, d.Wout = srcs[0].H, srcs[0].W, out.H, out.W
         d.Cout = out.C
         d.W = self._packed[name].data_ptr()
+        d.out, d.out_pitch, d.out_ch_off = out.buf.data_ptr(), out.pitch, out.ch_off
+        d.out_dtype = out.dtype
+        d.bias = bias.data_ptr() if bias is not None else None
+        d.tanh_out = int(tanh)
         use_tc = self.mode == 'tc' and all(a.C % 32 == 0 for a in srcs)
-        if use_tc:
+        use_halo = False
+        nparts = ctypes.c_int(0)
+        if use_tc and self.halo and bn and k in (3, 4) and min(out.H, out.W) // (s if transposed else 1) >= 14:
+            # halo-tile kernel: stride-2 convolutions keep 4 parity planes of the halo, so their K chunk is 32
+            tk = 32 if (s == 2 and not transposed) else (64 if all(a.C % 64 == 0 for a in srcs) else 32)
+            cap = 64 if (transposed and s == 2) else 128                  # 4 accumulators x bn TMEM columns
+            bn_tile = next((b for b in (128, 64, 32) if b <= cap and out.C % b == 0), 0)
+            ntap = ctypes.c_int(0)
+            widx = (ctypes.c_int * 16)()
+            if bn_tile and self.lib.rp_conv_halo_plan(ctypes.byref(d), bn_tile, tk, self.halo_flags, ctypes.byref(nparts),
+                                                      ctypes.byref(ntap), widx) == _lib.RP_OK:
+                use_halo = True
+                key = (name, 'halo', bn_tile, tk)
+                if key not in self._packed_tc:
+                    w = self._packed[name]
+                    self._packed_tc[key] = pack_halo(w.reshape(k * k, w.shape[2], w.shape[3]), list(widx[:ntap.value]),
+                                                     [a.C for a in srcs], out.C, bn_tile, tk)
+                wtc = self._packed_tc[key]
+        if use_tc and not use_halo:
             tk = 64 if all(a.C % 64 == 0 for a in srcs) else 32
             bn_tile = 128 if out.C >= 128 else (64 if out.C >= 64 else 32)
             key = (name, bn_tile, tk)
@@ -150,13 +206,10 @@ class ScnetEngine(object):
                 w = self._packed[name]
                 self._packed_tc[key] = pack_tc(w.reshape(k * k, w.shape[2], w.shape[3]), [a.C for a in srcs], out.C, bn_tile, tk)
             wtc = self._packed_tc[key]
-        d.out, d.out_pitch, d.out_ch_off = out.buf.data_ptr(), out.pitch, out.ch_off
-        d.bias = bias.data_ptr() if bias is not None else None
-        d.tanh_out = int(tanh)
-        nparts = ctypes.c_int(0)
         if bn:
-            _lib.check((self.lib.rp_conv_nparts_tc if use_tc else self.lib.rp_conv_nparts)(ctypes.byref(d), ctypes.byref(nparts)),
-                       "rp_conv_nparts")
+            if not use_halo:
+                _lib.check((self.lib.rp_conv_nparts_tc if use_tc else self.lib.rp_conv_nparts)(ctypes.byref(d), ctypes.byref(nparts)),
+                           "rp_conv_nparts")
             need = self._P * nparts.value * out.C
             pt = self._bufs['partials']
             if pt is None or pt.numel() < 2 * need:
@@ -165,7 +218,10 @@ class ScnetEngine(object):
             d.psum, d.psq = pt.data_ptr(), pt.data_ptr() + 4 * need
         else:
             d.psum, d.psq = None, None
-        if use_tc:
+        if use_halo:
+            _lib.check(self.lib.rp_conv_layer_halo(ctypes.byref(d), wtc.data_ptr(), bn_tile, tk, self.halo_flags, stream),
+                       "rp_conv_layer_halo(%s)" % name)
+        elif use_tc:
             _lib.check(self.lib.rp_conv_layer_tc(ctypes.byref(d), wtc.data_ptr(), bn_tile, tk, stream), "rp_conv_layer_tc(%s)" % name)
         else:
             _lib.check(self.lib.rp_conv_layer(ctypes.byref(d), stream), "rp_conv_layer(%s)" % name)
@@ -265,7 +321,7 @@ class ScnetEngine(object):
         B = self._bufs
 
         def grab(a):
-            raw = a.buf[..., a.ch_off:a.ch_off + a.C]
+            raw = a.buf[..., a.ch_off:a.ch_off + a.C].float()
             out = {'raw': raw.permute(0, 3, 1, 2).contiguous()}
             if a.scale is not None:
                 sc = a.scale[:, a.ch_off:a.ch_off + a.C].repeat_interleave(2, 0)[:, None, None, :]

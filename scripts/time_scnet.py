@@ -7,6 +7,7 @@ from relativepose_b200.model.mymodel import SCNet
 a = types.SimpleNamespace(batchnorm=1, useTanh=1, skipLayer=1, outputType='rgbdnsf', snumclass=15)
 torch.manual_seed(0)
 net = SCNet(a).cuda()
+print("config: RP_SCNET_HALO=%s RP_SCNET_ACT=%s RP_SCNET_MODE=%s" % (os.environ.get("RP_SCNET_HALO", "1"), os.environ.get("RP_SCNET_ACT", "bf16"), os.environ.get("RP_SCNET_MODE", "tc")))
 for P in [int(v) for v in (sys.argv[1:] or ["1", "8"])]:
     x = torch.cat([torch.from_numpy(synth.make_panorama_pair(s, "suncg")) for s in range(P)], 0).cuda()
     for _ in range(5):          # includes the CUDA-graph capture on the third call

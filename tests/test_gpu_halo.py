@@ -1,0 +1,105 @@
+"""GPU parity of the halo-tile tcgen05 convolution (csrc/scnet_halo.cu) layer by layer against torch's conv2d /
+conv_transpose2d on the SAME bf16-rounded operands (producer BatchNorm + LeakyReLU applied in float32, rounded to
+bf16; weights rounded to bf16) -- so the only difference left is the fp32 accumulation order (tolerance 2e-3 of the
+output range; +2^-8 relative when the raw output is stored as bf16) -- and of the BN scale/shift the layer's
+partial statistics produce."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+CASES = [
+    # name, transposed, k, s, p, Hin, Win, [Cin...], Cout
+    ("conv3x3s1", 0, 3, 1, 1, 40, 56, [64], 64),
+    ("conv4x4s2_32to64", 0, 4, 2, 1, 112, 112, [32], 64),
+    ("conv4x4s2_768to256", 0, 4, 2, 1, 56, 56, [768], 256),
+    ("conv3x3s2p1", 0, 3, 2, 1, 40, 160, [64], 128),
+    ("deconv4x4s2_cat", 1, 4, 2, 1, 28, 28, [128, 128], 64),
+    ("deconv4x4s2_cat_c32", 1, 4, 2, 1, 56, 56, [64, 64], 32),
+    ("deconv3x3s1", 1, 3, 1, 1, 17, 23, [64], 128),
+    ("deconv3x3s2p0", 1, 3, 2, 0, 16, 15, [64], 32),
+]
+
+
+def _run(case, storage, flags=0):
+    import torch
+    import torch.nn.functional as F
+    from relativepose_b200.scnet_engine import ScnetEngine, _Act
+    name, tr, k, s, p, Hin, Win, cins, Cout = case
+    dev = torch.device("cuda:0")
+    G, gsz = 3, 2
+    n = G * gsz
+    Cin = sum(cins)
+    g = torch.Generator(device="cpu").manual_seed(7)
+    eng = ScnetEngine(None, mode='tc')
+    eng.halo, eng.halo_flags = True, flags
+    eng._P, eng._dev, eng._bufs = G, dev, {'partials': None}
+    dt = torch.bfloat16 if storage == 'bf16' else torch.float32
+    srcs, xs = [], []
+    for c in cins:
+        pitch = c + 8                                   # exercise pitch / channel offset
+        raw = torch.randn((n, Hin, Win, pitch), generator=g).to(dev).to(dt)
+        sc = (0.5 + torch.rand((G, pitch), generator=g)).to(dev)
+        sh = (0.3 * torch.randn((G, pitch), generator=g)).to(dev)
+        srcs.append(_Act(raw, Hin, Win, pitch, 8, c, sc, sh))
+        xa = raw.float() * sc.repeat_interleave(gsz, 0)[:, None, None, :] + sh.repeat_interleave(gsz, 0)[:, None, None, :]
+        xa = F.leaky_relu(xa, 0.1)[..., 8:8 + c].to(torch.bfloat16).float()
+        xs.append(xa)
+    x = torch.cat(xs, 3).permute(0, 3, 1, 2).contiguous()
+    if tr:
+        w = torch.randn((Cin, Cout, k, k), generator=g).to(dev) / (Cin * k * k / (s * s)) ** 0.5
+        Hout, Wout = (Hin - 1) * s - 2 * p + k, (Win - 1) * s - 2 * p + k
+        wq = w.to(torch.bfloat16).float()
+        ref = F.conv_transpose2d(x.double(), wq.double(), stride=s, padding=p)
+        eng._packed = {'L': w.permute(2, 3, 0, 1).contiguous()}
+    else:
+        w = torch.randn((Cout, Cin, k, k), generator=g).to(dev) / (Cin * k * k) ** 0.5
+        Hout, Wout = (Hin + 2 * p - k) // s + 1, (Win + 2 * p - k) // s + 1
+        wq = w.to(torch.bfloat16).float()
+        ref = F.conv2d(x.double(), wq.double(), stride=s, padding=p)
+        eng._packed = {'L': w.permute(2, 3, 1, 0).contiguous()}
+    opitch = Cout + 8
+    obuf = torch.full((n, Hout, Wout, opitch), 777.0, device=dev).to(dt)
+    out = _Act(obuf, Hout, Wout, opitch, 8, Cout, torch.zeros((G, opitch), device=dev), torch.zeros((G, opitch), device=dev))
+    gamma = (0.5 + torch.rand(Cout, generator=g)).to(dev)
+    beta = torch.randn(Cout, generator=g).to(dev)
+    launches = []
+    orig = eng.lib.rp_conv_layer_halo
+
+    def spy(*a):                                         # the layer must really run on the halo kernel
+        launches.append(1)
+        return orig(*a)
+    eng.lib.rp_conv_layer_halo = spy
+    try:
+        eng._conv('L', srcs, out, bool(tr), k, s, p, stream=torch.cuda.current_stream().cuda_stream, bn_params=(gamma, beta))
+    finally:
+        eng.lib.rp_conv_layer_halo = orig
+    torch.cuda.synchronize()
+    assert launches, "layer did not take the halo path"
+    got = obuf[..., 8:8 + Cout].float().permute(0, 3, 1, 2).double()
+    assert torch.all(obuf[..., :8].float() == 777.0), "wrote outside the channel window"
+    rng = ref.abs().max().item()
+    err = (got - ref).abs().max().item()
+    tol = 2e-3 * rng + (2.0 ** -8 * rng if storage == 'bf16' else 0.0)
+    # BN scale/shift from the partial statistics vs the statistics of the stored tensor
+    gg = got.reshape(G, gsz, Cout, -1).permute(0, 2, 1, 3).reshape(G, Cout, -1)
+    mean, var = gg.mean(2), gg.var(2, unbiased=False)
+    sc_ref = gamma.double() / torch.sqrt(var + 1e-5)
+    sh_ref = beta.double() - mean * sc_ref
+    e_sc = ((out.scale[:, 8:8 + Cout].double() - sc_ref).abs() / sc_ref.abs()).max().item()
+    e_sh = (out.shift[:, 8:8 + Cout].double() - sh_ref).abs().max().item()
+    return err, tol, rng, e_sc, e_sh
+
+
+@pytest.mark.parametrize("storage", ["fp32", "bf16"])
+@pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
+def test_halo_layer_matches_torch(case, storage):
+    err, tol, rng, e_sc, e_sh = _run(case, storage)
+    print("%s/%s: max err %.3e (tol %.3e, range %.2f), bn scale rel %.2e shift abs %.2e" % (case[0], storage, err, tol, rng, e_sc, e_sh))
+    assert err <= tol
+    assert e_sc <= 1e-3 and e_sh <= 5e-3
+
+
+def test_halo_layer_pitch16_variant():
+    err, tol, rng, e_sc, e_sh = _run(CASES[0], "fp32", flags=1)
+    assert err <= tol and e_sc <= 1e-3
