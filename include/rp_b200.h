@@ -215,6 +215,9 @@ int rp_bn_finalize(const float* psum, const float* psq, int G, int nparts, int C
 /* F.upsample(x,[224,224],'bilinear',align_corners=False) (mymodel.py:261) fused with the channel regrouping of
  * mymodel.py:264-286: in [n,16,H,W] NCHW -> out [n,224,224,20] NHWC = (rgb,mask | normal,mask | depth,mask) x (own, warped) */
 int rp_scnet_resize_in(const float* x, int n, int H, int W, float* out, void* stream);
+/* Same for the tensor-core stem: out [n,224,224,96] bfloat16 = 6 groups x [hi(4) | lo(4) | hi(4) | 0(4)], x = hi + lo
+ * (bf16 split), so that conv1* runs on tcgen05 with float32-class accuracy (csrc/scnet.cu). */
+int rp_scnet_resize_in_split(const float* x, int n, int H, int W, void* out, void* stream);
 /* F.upsample(xout,inShape,'bilinear',align_corners=False) (mymodel.py:379): in [n,224,224,C] NHWC -> out [n,C,H,W] NCHW */
 int rp_scnet_resize_out(const float* in, int n, int C, int H, int W, float* out, void* stream);
 
@@ -249,6 +252,27 @@ int rp_resize_to_nchw(const float* src, int n, int Hs, int Ws, int C, float* out
 
 /* rputil.interpolate (RPModule/rputil.py:43-58): feat [C,H,W], pt [K,2] normalised (x,y) -> out [C,K]; device float32 */
 int rp_interpolate(const float* feat, int C, int H, int W, const float* pt, int K, float* out, void* stream);
+
+/* ---- View warping between the two scans of a pair --------------------------------------
+ * util.warping (util.py:94-172) over a batch: view [B,8,160,640] float32 NCHW (rgb, normal, depth, valid), R [B,16]
+ * row-major 4x4 float64, dataset 0 = suncg, 1 = matterport, 2 = scannet -> out [B,8,160,640] float32 (the reference's
+ * float64 result cast the way its caller does, torch_op.v).  The observed window of the view (skybox face 1 / the
+ * 66x88 Kinect window) is lifted to 3-D (util.depth2pc / Pano2PointCloud), moved by R and splatted on the 4 faces
+ * (util.reproj_helper: numpy "last write wins" = the source pixel with the largest raster index wins).  An identity R
+ * yields zeros (util.py:95-96).  workspace: rp_warp_workspace_bytes(B) bytes (the int32 winner map). */
+int rp_warp_workspace_bytes(int B, size_t* bytes);
+int rp_warp_views(const float* view, const double* R, int B, int dataset, float* out, void* workspace, size_t workspace_bytes,
+                  void* stream);
+/* util.Pano2PointCloud (util.py:751-811), dense: depth [B,160,640] float32 -> pc [B,3,102400] float64 in the reference's
+ * point order (face, row, column); valid [B,102400] (may be NULL) = 1 where the reference keeps the point (scannet drops
+ * depth == 0, the caller compacts). */
+int rp_pano2pc(const float* depth, int B, int dataset, double* pc, unsigned char* valid, void* stream);
+/* The blend of RelativePoseEstimationViaCompletion (rpmodule.py:628-634): f [B,C,160,640] float32 network output (3:6
+ * normal, 6 depth), mask [B,160,640] float32, norm_gt [B,160,640,3] / depth_gt [B,160,640] float64 (is_f64) or float32
+ * -> normal_out / depth_out of the same type: observed region from the scan, the rest from the network, normals
+ * re-normalised (EPS 1e-12). */
+int rp_blend_completion(const float* f, int C, const float* mask, const void* norm_gt, const void* depth_gt, int is_f64, int B,
+                        void* normal_out, void* depth_out, void* stream);
 
 int64_t rp_launch_count(void);
 int64_t rp_conv_launch_count(void);

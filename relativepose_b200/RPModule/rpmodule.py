@@ -152,33 +152,20 @@ def fit_irls_sm(allSP, allTP, allSN, allTN, allWP, allWN, w_i1i2j1j2, mu, row, c
     return _fit_graph(allSP, allTP, allSN, allTN, allWP, allWN, w_i1i2j1j2, mu, row, col, 'irls+sm')
 
 
-def apply_mask(x, maskMethod):
-    """util.apply_mask (util.py:209-232) for the two masks the pipeline uses: 'second' observes skybox face 1 (columns
-    h..2h), 'kinect' a 66x88 window of it.  x: torch [n,c,h,w].  Returns (masked x, mask [n,1,h,w])."""
-    import torch
-    h, w = x.shape[2], x.shape[3]
-    m = torch.zeros((x.shape[0], 1, h, w), dtype=x.dtype, device=x.device)
-    if maskMethod == 'second':
-        m[:, :, :h, h:2 * h] = 1
-    elif maskMethod == 'kinect':
-        assert w == 640 and h == 160
-        dw, dh = int(89.67 // 2), int(67.25 // 2)
-        m[:, :, 80 - dh:80 + dh, 160 + 80 - dw:160 + 80 + dw] = 1
-    else:
-        raise ValueError("unknown maskMethod %r" % (maskMethod,))
-    return x * m, m
+from ..util import apply_mask          # noqa: E402,F401  (util.apply_mask, util.py:209-232; kept importable from here)
 
 
 def RelativePoseEstimationViaCompletion(net, data_s, data_t, args, warping_fn=None, keypoint_fn=None):
     """The main algorithm (rpmodule.py:569-662): alternate scan completion (``net`` = SCNet) and pairwise matching.
 
     args: snumclass, featureDim, outputType, maskMethod, alterStep, dataset, para (per-step sigma arrays),
-    representation, completion.  ``warping_fn(view_np [1,8,h,w], R4x4, dataset) -> np [1,8,h,w]`` is util.warping
-    (util.py:94-172; identity pose -> zeros, :95-96) and ``keypoint_fn`` the keypoint stage -- both are the
-    SURVEY.md section 8f "next" rows and have to be supplied (for alterStep == 1 warping is never needed)."""
+    representation, completion.  Warping (util.warping, util.py:94-172) and the blend of the completed scans with the
+    observed region (:628-634) run on the GPU (relativepose_b200/util.py -> csrc/rp_warp.cu): both warps of a step are one
+    batched call and the views never leave the device.  ``warping_fn(view_np [1,8,h,w], R4x4, dataset) -> np [1,8,h,w]``
+    overrides the warp (tests); ``keypoint_fn`` is the keypoint stage (SIFT + augmentation are SURVEY 8f row 2)."""
     import copy
     import torch
-    EPS = 1e-12
+    from .. import util as _util
     idx_f = 0
     for key, n in (('rgb', 3), ('n', 3), ('d', 1), ('s', args.snumclass)):
         if key in args.outputType:
@@ -189,14 +176,6 @@ def RelativePoseEstimationViaCompletion(net, data_s, data_t, args, warping_fn=No
     def v(a):
         return torch.as_tensor(np.asarray(a), dtype=torch.float32, device=dev)
 
-    def warp(view, R):
-        if np.linalg.norm(R - np.eye(4)) == 0:                       # util.py:95-96
-            return torch.zeros_like(view)
-        if warping_fn is None:
-            raise NotImplementedError("RelativePoseEstimationViaCompletion needs warping_fn for alterStep > 1 "
-                                      "(util.warping is a SURVEY 8f next row)")
-        return v(warping_fn(view.cpu().numpy(), R, args.dataset))
-
     with torch.no_grad():
         R_hat = np.eye(4)
         full = [torch.cat((v(d['rgb']), v(d['norm']), v(d['depth']).unsqueeze(2)), 2).permute(2, 0, 1).unsqueeze(0)
@@ -204,21 +183,26 @@ def RelativePoseEstimationViaCompletion(net, data_s, data_t, args, warping_fn=No
         views, masks = [], []
         for c in full:
             vw, m = apply_mask(c.clone(), args.maskMethod)           # :603-604
-            masks.append(m[0].cpu().numpy().transpose(1, 2, 0))
+            masks.append(m[0, 0])                                    # [h,w] on the device
             views.append(torch.cat((vw, (vw[:, 6:7] != 0).float()), 1))   # :609-612
         view_s, view_t = views
-        mask_s, mask_t = masks
+        norm_gt = torch.stack([torch.as_tensor(np.asarray(d['norm'])) for d in (data_s, data_t)]).to(dev)
+        depth_gt = torch.stack([torch.as_tensor(np.asarray(d['depth'])) for d in (data_s, data_t)]).to(dev)
+        mask2 = torch.stack(masks)
         for alter_ in range(args.alterStep):
-            view_t2s = warp(view_t, np.linalg.inv(R_hat))            # :616-617
-            view_s2t = warp(view_s, R_hat)
+            # warp each scan into the other's frame with the current estimate (:616-617); identity -> zeros (util.py:95-96)
+            if warping_fn is None:
+                w2 = _util.warping_device(torch.cat((view_t, view_s)), np.stack((np.linalg.inv(R_hat), R_hat)), args.dataset)
+                view_t2s, view_s2t = w2[0:1], w2[1:2]
+            else:
+                view_t2s = v(warping_fn(view_t.cpu().numpy(), np.linalg.inv(R_hat), args.dataset)) if np.linalg.norm(R_hat - np.eye(4)) else torch.zeros_like(view_t)
+                view_s2t = v(warping_fn(view_s.cpu().numpy(), R_hat, args.dataset)) if np.linalg.norm(R_hat - np.eye(4)) else torch.zeros_like(view_s)
             f = net(torch.cat((torch.cat((view_s, view_t2s), 1), torch.cat((view_t, view_s2t), 1))))   # :619-623
+            nrm2, dep2 = _util.blend_completion_device(f, mask2, norm_gt, depth_gt)                    # :628-634
             comp = []
-            for k, (d, m) in enumerate(((data_s, mask_s), (data_t, mask_t))):
-                fk = f[k].cpu().numpy()
-                nrm = (1 - m) * fk[3:6].transpose(1, 2, 0) + m * d['norm']                # :629-632
-                nrm = nrm / (np.linalg.norm(nrm, axis=2, keepdims=True) + EPS)
-                dep = (1 - m[:, :, 0]) * fk[6] + m[:, :, 0] * d['depth']                 # :633-634
-                c = {'normal': nrm, 'depth': dep, 'obs_mask': m.copy(),
+            for k, d in enumerate((data_s, data_t)):
+                m = masks[k].cpu().numpy()[:, :, None]
+                c = {'normal': nrm2[k].cpu().numpy(), 'depth': dep2[k].cpu().numpy(), 'obs_mask': m.copy(),
                      'rgb': (m * d['rgb'] * 255).astype('uint8'), 'feat': f[k, idx_f:idx_f_end]}   # :636-652
                 if 'scannet' in args.dataset:
                     c['rgb_full'] = (d['rgb_full'] * 255).astype('uint8')

@@ -58,9 +58,10 @@ class RpConvDesc(ctypes.Structure):
 
 EXPORTS = ("rp_abi_version", "rp_device_info", "rp_solve_workspace_bytes", "rp_solve_batch",
            "rp_solve_batch_ex", "rp_match_topk", "rp_launch_count", "rp_spectral_irls_solve", "rp_spectral_irls_workspace_bytes",
-           "rp_conv_nparts", "rp_conv_layer", "rp_bn_finalize", "rp_scnet_resize_in", "rp_scnet_resize_out",
+           "rp_conv_nparts", "rp_conv_layer", "rp_bn_finalize", "rp_scnet_resize_in", "rp_scnet_resize_in_split", "rp_scnet_resize_out",
            "rp_conv_launch_count", "rp_tc_gemm_test", "rp_conv_nparts_tc", "rp_conv_layer_tc",
            "rp_conv_halo_plan", "rp_conv_layer_halo", "rp_conv_halo_debug",
+           "rp_warp_workspace_bytes", "rp_warp_views", "rp_pano2pc", "rp_blend_completion",
            "rp_bn_relu_maxpool", "rp_bn_add_relu", "rp_resize_nhwc", "rp_resize_to_nchw", "rp_interpolate")
 
 _lib = None
@@ -108,6 +109,8 @@ def load():
     lib.rp_bn_finalize.argtypes = [vp, vp, i32, i32, i32, i32, vp, vp, vp, vp, i32, i32, vp]
     lib.rp_scnet_resize_in.restype = i32
     lib.rp_scnet_resize_in.argtypes = [vp, i32, i32, i32, vp, vp]
+    lib.rp_scnet_resize_in_split.restype = i32
+    lib.rp_scnet_resize_in_split.argtypes = [vp, i32, i32, i32, vp, vp]
     lib.rp_scnet_resize_out.restype = i32
     lib.rp_scnet_resize_out.argtypes = [vp, i32, i32, i32, i32, vp, vp]
     lib.rp_conv_launch_count.restype = i64
@@ -132,6 +135,14 @@ def load():
     lib.rp_resize_to_nchw.argtypes = [vp, i32, i32, i32, i32, vp, i32, i32, i32, vp]
     lib.rp_interpolate.restype = i32
     lib.rp_interpolate.argtypes = [vp, i32, i32, i32, vp, i32, vp, vp]
+    lib.rp_warp_workspace_bytes.restype = i32
+    lib.rp_warp_workspace_bytes.argtypes = [i32, ctypes.POINTER(ctypes.c_size_t)]
+    lib.rp_warp_views.restype = i32
+    lib.rp_warp_views.argtypes = [vp, vp, i32, i32, vp, vp, ctypes.c_size_t, vp]
+    lib.rp_pano2pc.restype = i32
+    lib.rp_pano2pc.argtypes = [vp, i32, i32, vp, vp, vp]
+    lib.rp_blend_completion.restype = i32
+    lib.rp_blend_completion.argtypes = [vp, i32, vp, vp, vp, i32, i32, vp, vp, vp]
     lib.rp_tc_gemm_test.restype = i32
     lib.rp_tc_gemm_test.argtypes = [vp, vp, vp, i32, i32, i32, i32, vp]
     if lib.rp_abi_version() != 1:

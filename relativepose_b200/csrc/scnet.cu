@@ -160,22 +160,30 @@ __global__ void __launch_bounds__(CT) conv_igemm_f32(const ConvArgs A) {
     }
 }
 
-// One warp per (group, channel): lanes stride over the partial rows (each lane sums its rows in order, then a
-// fixed butterfly) -- deterministic, and 32x less serial than one thread per channel for the 1568-row layers.
-__global__ void bn_finalize_kernel(const float* __restrict__ psum, const float* __restrict__ psq, int nparts, int Cout,
+// One block per (group, 32 channels): 32 x 32 threads, lanes = channels (coalesced 128-byte rows of the partials),
+// warps = row lanes striding over the partial rows; every thread sums its rows in order in float64, the 32 row lanes
+// are combined in a fixed order through shared memory -- deterministic, and the 3136-row partials of the 224x224
+// layers take 98 independent coalesced loads per thread instead of 98 strided ones per lane.
+__global__ void __launch_bounds__(1024) bn_finalize_kernel(const float* __restrict__ psum, const float* __restrict__ psq, int nparts, int Cout,
                                    int count, const float* __restrict__ gamma, const float* __restrict__ beta,
                                    float* __restrict__ scale, float* __restrict__ shift, int sstride, int s_off) {
+    __shared__ double rs[32][33], rq[32][33];
     const int g = blockIdx.y;
-    const int lane = threadIdx.x & 31;
-    const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (c >= Cout) return;
+    const int cl = threadIdx.x & 31, rl = threadIdx.x >> 5;
+    const int c = blockIdx.x * 32 + cl;
     double s = 0.0, q = 0.0;
-    const float* ps = psum + (size_t)g * nparts * Cout + c;
-    const float* pq = psq + (size_t)g * nparts * Cout + c;
-    for (int r = lane; r < nparts; r += 32) { s += (double)ps[(size_t)r * Cout]; q += (double)pq[(size_t)r * Cout]; }
+    if (c < Cout) {
+        const float* ps = psum + (size_t)g * nparts * Cout + c;
+        const float* pq = psq + (size_t)g * nparts * Cout + c;
+#pragma unroll 4
+        for (int r = rl; r < nparts; r += 32) { s += (double)ps[(size_t)r * Cout]; q += (double)pq[(size_t)r * Cout]; }
+    }
+    rs[rl][cl] = s; rq[rl][cl] = q;
+    __syncthreads();
+    if (rl == 0 && c < Cout) {
+        s = 0.0; q = 0.0;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); q += __shfl_xor_sync(0xffffffffu, q, o); }
-    if (lane == 0) {
+        for (int r = 0; r < 32; ++r) { s += rs[r][cl]; q += rq[r][cl]; }
         const double mean = s / count;
         double var = q / count - mean * mean;          // biased variance, as nn.BatchNorm2d normalises with
         if (var < 0.0) var = 0.0;
@@ -219,6 +227,45 @@ __global__ void scnet_resize_in_kernel(const float* __restrict__ x, int n, int H
     o[10] = v[8]; o[11] = v[9]; o[12] = v[10]; o[13] = v[15];
     o[14] = v[11]; o[15] = v[12]; o[16] = v[13]; o[17] = v[15];
     o[18] = v[14]; o[19] = v[15];
+}
+
+// Same resize + regrouping for the tensor-core stem (conv1* on the halo kernel, K chunk 16): out [n,224,224,96]
+// bfloat16 = 6 groups x 16 channels, each group = [hi(4) | lo(4) | hi(4) | 0(4)] of its (up to 4) float32 channels,
+// x = hi + lo with hi = bf16(x), lo = bf16(x - hi).  Against weights packed as [w_hi | w_hi | w_lo | 0] one K=16 MMA
+// per tap computes x_hi*w_hi + x_lo*w_hi + x_hi*w_lo: float32-class accuracy (error ~2^-16) in the K slots a
+// 4-channel layer would otherwise pad with zeros.
+__global__ void scnet_resize_in_split_kernel(const float* __restrict__ x, int n, int H, int W, __nv_bfloat16* __restrict__ out) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n * 224 * 224) return;
+    const int ox = idx % 224, oy = (idx / 224) % 224, im = idx / (224 * 224);
+    int y0, y1, x0, x1; float ly0, ly1, lx0, lx1;
+    bilin_coord(oy, (float)H / 224.f, H, y0, y1, ly0, ly1);
+    bilin_coord(ox, (float)W / 224.f, W, x0, x1, lx0, lx1);
+    float v[16];
+#pragma unroll
+    for (int c = 0; c < 16; ++c) {
+        const float* p = x + ((size_t)im * 16 + c) * H * W;
+        float p00 = p[(size_t)y0 * W + x0], p01 = p[(size_t)y0 * W + x1], p10 = p[(size_t)y1 * W + x0], p11 = p[(size_t)y1 * W + x1];
+        v[c] = ly0 * (lx0 * p00 + lx1 * p01) + ly1 * (lx0 * p10 + lx1 * p11);
+    }
+    // group -> source channels (mymodel.py:264-286): (rgb,mask) (normal,mask) (depth,mask) of the view, then of the warped view
+    const int src[6][4] = {{0, 1, 2, 7}, {3, 4, 5, 7}, {6, 7, -1, -1}, {8, 9, 10, 15}, {11, 12, 13, 15}, {14, 15, -1, -1}};
+    uint4* o = reinterpret_cast<uint4*>(out + (size_t)idx * 96);
+#pragma unroll
+    for (int gq = 0; gq < 6; ++gq) {
+        __nv_bfloat16 hi[4], lo[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const float f = src[gq][c] >= 0 ? v[src[gq][c]] : 0.f;
+            hi[c] = __float2bfloat16_rn(f);
+            lo[c] = __float2bfloat16_rn(f - __bfloat162float(hi[c]));
+        }
+        __nv_bfloat16 u[16];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) { u[c] = hi[c]; u[4 + c] = lo[c]; u[8 + c] = hi[c]; u[12 + c] = __float2bfloat16_rn(0.f); }
+        o[2 * gq] = *reinterpret_cast<uint4*>(&u[0]);
+        o[2 * gq + 1] = *reinterpret_cast<uint4*>(&u[8]);
+    }
 }
 
 __global__ void scnet_resize_out_kernel(const float* __restrict__ in, int n, int C, int H, int W, float* __restrict__ out) {
@@ -417,6 +464,105 @@ __global__ void interpolate_kernel(const float* __restrict__ feat, int C, int H,
     out[idx] = r;
 }
 
+// 1x1 output heads (deconv1rgb/n/d/s/f, mymodel.py:188-228: Conv2d(k=1) + bias [+ tanh], no BatchNorm): a K <= 128 by
+// Cout <= 32 matrix per pixel.  HBM-bound (the 3-channel heads) or FMA-bound (the 21/32-channel heads) -- far too
+// little work per 128-pixel tile to amortise a tensor-core CTA's setup, so: CUDA cores, PIX pixels per thread, the
+// zero-padded [K][CP] weights broadcast from shared memory, producer BatchNorm + LeakyReLU applied while loading
+// (float32 or bfloat16 storage).
+template <int CP, int PIX>
+__global__ void __launch_bounds__(128) conv1x1_head_kernel(const ConvArgs A) {
+    __shared__ __align__(16) float Ws[128 * CP];
+    __shared__ float s_sc[128], s_sh[128];
+    const int tid = threadIdx.x, g = blockIdx.y;
+    for (int i = tid; i < A.Cin_total * CP; i += 128) { const int k = i / CP, j = i - k * CP; Ws[i] = j < A.Cout ? A.W[(size_t)k * A.Cout + j] : 0.f; }
+    {
+        int cb = 0;
+        for (int si = 0; si < A.nsrc; ++si) {
+            const rp_conv_src& S = A.src[si];
+            for (int c = tid; c < S.C; c += 128) {
+                s_sc[cb + c] = S.act ? S.scale[(size_t)g * S.sstride + S.s_off + c] : 1.f;
+                s_sh[cb + c] = S.act ? S.shift[(size_t)g * S.sstride + S.s_off + c] : 0.f;
+            }
+            cb += S.C;
+        }
+    }
+    __syncthreads();
+    const int npx = A.gsz * A.Hout * A.Wout;
+    int px[PIX]; bool val[PIX];
+    float acc[PIX][CP];
+#pragma unroll
+    for (int u = 0; u < PIX; ++u) {
+        px[u] = blockIdx.x * (128 * PIX) + u * 128 + tid;
+        val[u] = px[u] < npx;
+#pragma unroll
+        for (int j = 0; j < CP; ++j) acc[u][j] = 0.f;
+    }
+    int cb = 0;
+    for (int si = 0; si < A.nsrc; ++si) {
+        const rp_conv_src& S = A.src[si];
+        const bool h16 = S.dtype == 1;
+        for (int c0 = 0; c0 < S.C; c0 += 8) {
+            float v[PIX][8];
+#pragma unroll
+            for (int u = 0; u < PIX; ++u) {
+#pragma unroll
+                for (int q = 0; q < 8; ++q) v[u][q] = 0.f;
+                if (val[u]) {
+                    const size_t e = ((size_t)g * npx + px[u]) * S.pitch + S.ch_off + c0;
+                    if (h16) {
+                        const uint4 x = *reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(S.ptr) + e);
+                        const __nv_bfloat162* hp = reinterpret_cast<const __nv_bfloat162*>(&x);
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) { const float2 f = __bfloat1622float2(hp[q]); v[u][2 * q] = f.x; v[u][2 * q + 1] = f.y; }
+                    } else {
+                        const float4 x0 = *reinterpret_cast<const float4*>(S.ptr + e), x1 = *reinterpret_cast<const float4*>(S.ptr + e + 4);
+                        v[u][0] = x0.x; v[u][1] = x0.y; v[u][2] = x0.z; v[u][3] = x0.w; v[u][4] = x1.x; v[u][5] = x1.y; v[u][6] = x1.z; v[u][7] = x1.w;
+                    }
+                    if (S.act) {
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) { const float z = fmaf(v[u][q], s_sc[cb + c0 + q], s_sh[cb + c0 + q]); v[u][q] = z > 0.f ? z : S.slope * z; }
+                    }
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const float* w = Ws + (cb + c0 + q) * CP;
+#pragma unroll
+                for (int j = 0; j < CP; j += 4) {
+                    const float4 w4 = *reinterpret_cast<const float4*>(w + j);
+#pragma unroll
+                    for (int u = 0; u < PIX; ++u) {
+                        acc[u][j] = fmaf(v[u][q], w4.x, acc[u][j]); acc[u][j + 1] = fmaf(v[u][q], w4.y, acc[u][j + 1]);
+                        acc[u][j + 2] = fmaf(v[u][q], w4.z, acc[u][j + 2]); acc[u][j + 3] = fmaf(v[u][q], w4.w, acc[u][j + 3]);
+                    }
+                }
+            }
+        }
+        cb += S.C;
+    }
+#pragma unroll
+    for (int u = 0; u < PIX; ++u) {
+        if (!val[u]) continue;
+        float* op = A.out + ((size_t)g * npx + px[u]) * A.out_pitch + A.out_ch_off;
+#pragma unroll
+        for (int j = 0; j < CP; ++j) {
+            if (j < A.Cout) { float y = acc[u][j] + (A.bias ? A.bias[j] : 0.f); op[j] = A.tanh_out ? tanhf(y) : y; }
+        }
+    }
+}
+
+inline bool head_eligible(const rp_conv_desc* d) {
+    if (d->transposed || d->k != 1 || d->s != 1 || d->p != 0 || d->psum || d->Cout > 32 || d->out_dtype != 0) return false;
+    if (d->Hin != d->Hout || d->Win != d->Wout) return false;
+    int K = 0;
+    for (int i = 0; i < d->nsrc; ++i) {
+        const int al = d->src[i].dtype == 1 ? 8 : 4;
+        if (d->src[i].C % 8 || d->src[i].pitch % al || d->src[i].ch_off % al) return false;
+        K += d->src[i].C;
+    }
+    return K <= 128;
+}
+
 inline bool small_cin_eligible(const rp_conv_desc* d) {
     return d->nsrc == 1 && !d->transposed && d->k == 3 && d->s == 1 && d->p == 1 && d->Cout == 32 && !d->bias &&
            !d->tanh_out && d->src[0].act == 0 && (d->src[0].C == 4 || d->src[0].C == 2) &&
@@ -451,6 +597,15 @@ int rp_conv_layer(const rp_conv_desc* d, void* stream_) {
         ++g_conv_launches;
         return cudaGetLastError() == cudaSuccess ? RP_OK : RP_ERR_CUDA;
     }
+    if (head_eligible(d)) {
+        const int npx = A.gsz * A.Hout * A.Wout;
+        if (A.Cout <= 4) { dim3 grid((npx + 511) / 512, A.G); conv1x1_head_kernel<4, 4><<<grid, 128, 0, stream>>>(A); }
+        else if (A.Cout <= 16) { dim3 grid((npx + 255) / 256, A.G); conv1x1_head_kernel<16, 2><<<grid, 128, 0, stream>>>(A); }
+        else if (A.Cout <= 24) { dim3 grid((npx + 255) / 256, A.G); conv1x1_head_kernel<24, 2><<<grid, 128, 0, stream>>>(A); }
+        else { dim3 grid((npx + 255) / 256, A.G); conv1x1_head_kernel<32, 2><<<grid, 128, 0, stream>>>(A); }
+        ++g_conv_launches;
+        return cudaGetLastError() == cudaSuccess ? RP_OK : RP_ERR_CUDA;
+    }
     if (d->out_dtype != 0) return RP_ERR_UNSUPPORTED;          // the float32 implicit GEMM reads and writes float32 only
     for (int i = 0; i < d->nsrc; ++i) if (d->src[i].dtype != 0) return RP_ERR_UNSUPPORTED;
     dim3 grid(A.tiles_m, (A.Cout + BN_ - 1) / BN_, A.G * A.nclass);
@@ -464,8 +619,8 @@ int rp_bn_finalize(const float* psum, const float* psq, int G, int nparts, int C
                    void* stream_) {
     if (!psum || !psq || !gamma || !beta || !scale || !shift || G < 1 || nparts < 1 || Cout < 1) return RP_ERR_INVALID_ARG;
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
-    dim3 grid((Cout + 7) / 8, G);                     // 8 warps per block, one warp per channel
-    bn_finalize_kernel<<<grid, 256, 0, stream>>>(psum, psq, nparts, Cout, count, gamma, beta, scale, shift, sstride, s_off);
+    dim3 grid((Cout + 31) / 32, G);                   // 32 channels x 32 row lanes per block
+    bn_finalize_kernel<<<grid, 1024, 0, stream>>>(psum, psq, nparts, Cout, count, gamma, beta, scale, shift, sstride, s_off);
     ++g_conv_launches;
     return cudaGetLastError() == cudaSuccess ? RP_OK : RP_ERR_CUDA;
 }
@@ -475,6 +630,15 @@ int rp_scnet_resize_in(const float* x, int n, int H, int W, float* out, void* st
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
     int total = n * 224 * 224;
     scnet_resize_in_kernel<<<(total + 255) / 256, 256, 0, stream>>>(x, n, H, W, out);
+    ++g_conv_launches;
+    return cudaGetLastError() == cudaSuccess ? RP_OK : RP_ERR_CUDA;
+}
+
+int rp_scnet_resize_in_split(const float* x, int n, int H, int W, void* out, void* stream_) {
+    if (!x || !out || n < 1) return RP_ERR_INVALID_ARG;
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    int total = n * 224 * 224;
+    scnet_resize_in_split_kernel<<<(total + 127) / 128, 128, 0, stream>>>(x, n, H, W, static_cast<__nv_bfloat16*>(out));
     ++g_conv_launches;
     return cudaGetLastError() == cudaSuccess ? RP_OK : RP_ERR_CUDA;
 }

@@ -424,6 +424,7 @@ int rp_conv_layer_halo(const rp_conv_desc* d, const void* w_packed, int bn, int 
 #define RP_HALO_CASE(BN_, TK_, NB_) if (bn == BN_ && tk == TK_) return halo::launch_halo<BN_, TK_, NB_>(H, w_packed, stream);
     RP_HALO_CASE(32, 64, 8) RP_HALO_CASE(64, 64, 6) RP_HALO_CASE(128, 64, 4)
     RP_HALO_CASE(32, 32, 8) RP_HALO_CASE(64, 32, 6) RP_HALO_CASE(128, 32, 4)
+    RP_HALO_CASE(32, 16, 8)
 #undef RP_HALO_CASE
     return RP_ERR_UNSUPPORTED;
 }

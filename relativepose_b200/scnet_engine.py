@@ -129,10 +129,14 @@ class ScnetEngine(object):
         B = {}
 
         def act(name, H, W, C):
-            B[name] = _Act(torch.empty((n, H, W, C), **fa), H, W, C, 0, C,
+            # the bottleneck tensors (<= 14x14) stay float32: they are tiny, and conv9's two-sample BatchNorm amplifies
+            # any storage rounding by up to 1/sqrt(eps) (tests/test_gpu_scnet.py)
+            B[name] = _Act(torch.empty((n, H, W, C), **(fa if H > 14 else f)), H, W, C, 0, C,
                            torch.empty((P, C), **f), torch.empty((P, C), **f))
 
         B['in20'] = _Act(torch.empty((n, 224, 224, 20), **f), 224, 224, 20, 0, 20)
+        if self.act_bf16:
+            B['in96'] = _Act(torch.empty((n, 224, 224, 96), dtype=torch.bfloat16, device=device), 224, 224, 96, 0, 96)
         for st in ('rgb', 'n', 'd'):
             for wh in ('', '_t2s'):
                 act('e1' + st + wh, 224, 224, 32)
@@ -154,8 +158,9 @@ class ScnetEngine(object):
     _slope = 0.1          # LeakyReLU(0.1) of the SCNet blocks; ResnetEngine overrides with 0 (ReLU)
     _gsz = 2              # images per BatchNorm batch (one scan pair)
 
-    def _conv(self, name, srcs, out, transposed, k, s, p, bn=True, bias=None, tanh=False, stream=None, bn_params=None):
+    def _conv(self, name, srcs, out, transposed, k, s, p, bn=True, bias=None, tanh=False, stream=None, bn_params=None, wkey=None):
         torch = self.torch
+        wkey = wkey or name                  # entry of self._packed holding this layer's [k,k,Cin,Cout] weights
         d = _lib.RpConvDesc()
         d.imgs_per_group = self._gsz
         d.nsrc = len(srcs)
@@ -174,17 +179,21 @@ class ScnetEngine(object):
         d.G = self._P
         d.Hin, d.Win, d.Hout, d.Wout = srcs[0].H, srcs[0].W, out.H, out.W
         d.Cout = out.C
-        d.W = self._packed[name].data_ptr()
+        d.W = self._packed[wkey].data_ptr()
         d.out, d.out_pitch, d.out_ch_off = out.buf.data_ptr(), out.pitch, out.ch_off
         d.out_dtype = out.dtype
         d.bias = bias.data_ptr() if bias is not None else None
         d.tanh_out = int(tanh)
-        use_tc = self.mode == 'tc' and all(a.C % 32 == 0 for a in srcs)
+        use_tc = self.mode == 'tc' and all(a.C % 16 == 0 for a in srcs)
+        if k == 1 and not bn and out.C <= 32 and sum(a.C for a in srcs) <= 128:
+            use_tc = False                   # 1x1 output heads: dedicated CUDA-core kernel inside rp_conv_layer
         use_halo = False
         nparts = ctypes.c_int(0)
         if use_tc and self.halo and bn and k in (3, 4) and min(out.H, out.W) // (s if transposed else 1) >= 14:
             # halo-tile kernel: stride-2 convolutions keep 4 parity planes of the halo, so their K chunk is 32
             tk = 32 if (s == 2 and not transposed) else (64 if all(a.C % 64 == 0 for a in srcs) else 32)
+            if any(a.C % 32 for a in srcs):
+                tk = 16                          # the bf16-split stem (conv1*, 16 channels per group)
             cap = 64 if (transposed and s == 2) else 128                  # 4 accumulators x bn TMEM columns
             bn_tile = next((b for b in (128, 64, 32) if b <= cap and out.C % b == 0), 0)
             ntap = ctypes.c_int(0)
@@ -192,15 +201,22 @@ class ScnetEngine(object):
             if bn_tile and self.lib.rp_conv_halo_plan(ctypes.byref(d), bn_tile, tk, self.halo_flags, ctypes.byref(nparts),
                                                       ctypes.byref(ntap), widx) == _lib.RP_OK:
                 use_halo = True
-                key = (name, 'halo', bn_tile, tk)
+                key = (wkey, 'halo', bn_tile, tk)
                 if key not in self._packed_tc:
-                    w = self._packed[name]
+                    w = self._packed[wkey]
                     self._packed_tc[key] = pack_halo(w.reshape(k * k, w.shape[2], w.shape[3]), list(widx[:ntap.value]),
                                                      [a.C for a in srcs], out.C, bn_tile, tk)
                 wtc = self._packed_tc[key]
+        if use_tc and not use_halo and any(a.C % 32 for a in srcs):
+            raise RuntimeError("layer %s: %r input channels need the halo kernel" % (name, [a.C for a in srcs]))
         if use_tc and not use_halo:
             tk = 64 if all(a.C % 64 == 0 for a in srcs) else 32
             bn_tile = 128 if out.C >= 128 else (64 if out.C >= 64 else 32)
+            # small-spatial layers (the 7x7 ... 1x1 bottleneck) have one M tile per pair: narrower N tiles put more
+            # CTAs on the 148 SMs (each streams its own slice of the weights; the A gather is tiny there)
+            m_tiles = -(-(self._gsz * out.H * out.W // (s * s if transposed else 1)) // 128) * (s * s if transposed else 1)
+            while bn_tile > 32 and m_tiles * -(-out.C // bn_tile) * self._P < 296:
+                bn_tile //= 2
             key = (name, bn_tile, tk)
             if key not in self._packed_tc:
                 w = self._packed[name]
@@ -275,13 +291,31 @@ class ScnetEngine(object):
             self._alloc(P, x.device, ctot)
             B = self._bufs
             stream = torch.cuda.current_stream().cuda_stream
-            _lib.check(self.lib.rp_scnet_resize_in(x.data_ptr(), n, H, W, B['in20'].buf.data_ptr(), stream), "resize_in")
+            split_stem = self.act_bf16 and self.halo     # conv1* on tcgen05 from the bf16 hi/lo split input
+            if split_stem:
+                _lib.check(self.lib.rp_scnet_resize_in_split(x.data_ptr(), n, H, W, B['in96'].buf.data_ptr(), stream), "resize_in_split")
+                for st in ('rgb', 'n', 'd'):
+                    if 'conv1' + st + '#split' not in self._packed:
+                        w = self._packed['conv1' + st]                          # [3,3,cin,32]
+                        hi = w.to(torch.bfloat16).float()
+                        lo = (w - hi).to(torch.bfloat16).float()
+                        ws = torch.zeros((3, 3, 16, 32), dtype=torch.float32, device=w.device)
+                        c = w.shape[2]
+                        ws[:, :, 0:c], ws[:, :, 4:4 + c], ws[:, :, 8:8 + c] = hi, hi, lo   # x [hi|lo|hi|0] . w [hi|hi|lo|0]
+                        self._packed['conv1' + st + '#split'] = ws.contiguous()
+            else:
+                _lib.check(self.lib.rp_scnet_resize_in(x.data_ptr(), n, H, W, B['in20'].buf.data_ptr(), stream), "resize_in")
             chan = {'rgb': (0, 4), 'n': (4, 4), 'd': (8, 2)}
             xin_slot = {'rgb': 0, 'rgb_t2s': 128, 'n': 256, 'n_t2s': 384, 'd': 512, 'd_t2s': 640}
             for wh, base in (('', 0), ('_t2s', 10)):
                 for st in ('rgb', 'n', 'd'):
                     off, c = chan[st]
-                    self._conv('conv1' + st, [B['in20'].view(base + off, c)], B['e1' + st + wh], False, 3, 1, 1, stream=stream)
+                    if split_stem:
+                        grp = {'rgb': 0, 'n': 1, 'd': 2}[st] + (3 if wh else 0)
+                        self._conv('conv1' + st, [B['in96'].view(16 * grp, 16)], B['e1' + st + wh], False, 3, 1, 1, stream=stream,
+                                   wkey='conv1' + st + '#split')
+                    else:
+                        self._conv('conv1' + st, [B['in20'].view(base + off, c)], B['e1' + st + wh], False, 3, 1, 1, stream=stream)
                     self._conv('conv2' + st, [B['e1' + st + wh]], B['e2' + st + wh], False, 4, 2, 1, stream=stream)
                     self._conv('conv3' + st, [B['e2' + st + wh]], B['xin'].view(xin_slot[st + wh], 128), False, 4, 2, 1, stream=stream)
             self._conv('conv4', [B['xin']], B['x4'], False, 4, 2, 1, stream=stream)

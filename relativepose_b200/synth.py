@@ -115,3 +115,40 @@ def make_panorama_pair(seed, dataset="suncg", H=160, W=640):
         out[v, 0:7] = view
         out[v, 7:8] = valid
     return out
+
+
+def make_warp_view(seed, dataset="suncg"):
+    """One observed view [1,8,160,640] float32 as RelativePoseEstimationViaCompletion assembles it (rpmodule.py:599-612):
+    rgb, unit normals, a smooth depth field with 5 % invalid zeros, masked to the observed face / Kinect window, plus the
+    validity channel.  The depth is smooth (not white noise) so that the warp produces coherent surfaces with many
+    many-to-one collisions -- the case the last-write-wins scatter of util.reproj_helper (util.py:603-608) is about."""
+    rs = np.random.RandomState(seed)
+    view = np.zeros((1, 8, 160, 640), np.float32)
+    view[0, 0:3] = rs.rand(3, 160, 640)
+    n = rs.randn(3, 160, 640)
+    view[0, 3:6] = n / np.linalg.norm(n, axis=0)
+    yy, xx = np.mgrid[0:160, 0:640]
+    d = 2.5 + 1.5 * np.sin(xx / 37.0 + seed) * np.cos(yy / 23.0) + 0.2 * rs.rand(160, 640)
+    d[rs.rand(160, 640) < 0.05] = 0
+    view[0, 6] = d
+    m = np.zeros((160, 640), np.float32)
+    if "scannet" in dataset:
+        m[80 - 33:80 + 33, 160 + 80 - 44:160 + 80 + 44] = 1
+    else:
+        m[:, 160:320] = 1
+    view[0, :7] *= m
+    view[0, 7] = (view[0, 6] != 0)
+    return view
+
+
+def make_pose(seed, max_angle=2.0, t_sigma=0.5):
+    """Seeded rigid transform [4,4] float64 (Rodrigues rotation about a random axis, angle U(0.2, max_angle))."""
+    rs = np.random.RandomState(100 + seed)
+    ax = rs.randn(3)
+    ax /= np.linalg.norm(ax)
+    ang = rs.uniform(0.2, max_angle)
+    K = np.array([[0, -ax[2], ax[1]], [ax[2], 0, -ax[0]], [-ax[1], ax[0], 0]])
+    R = np.eye(4)
+    R[:3, :3] = np.eye(3) + np.sin(ang) * K + (1 - np.cos(ang)) * K @ K
+    R[:3, 3] = rs.randn(3) * t_sigma
+    return R

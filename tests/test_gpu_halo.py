@@ -18,6 +18,7 @@ CASES = [
     ("deconv4x4s2_cat_c32", 1, 4, 2, 1, 56, 56, [64, 64], 32),
     ("deconv3x3s1", 1, 3, 1, 1, 17, 23, [64], 128),
     ("deconv3x3s2p0", 1, 3, 2, 0, 16, 15, [64], 32),
+    ("conv3x3s1_tk16_stem", 0, 3, 1, 1, 48, 40, [16], 32),
 ]
 
 
@@ -59,7 +60,7 @@ def _run(case, storage, flags=0):
         ref = F.conv2d(x.double(), wq.double(), stride=s, padding=p)
         eng._packed = {'L': w.permute(2, 3, 1, 0).contiguous()}
     opitch = Cout + 8
-    obuf = torch.full((n, Hout, Wout, opitch), 777.0, device=dev).to(dt)
+    obuf = torch.full((n, Hout, Wout, opitch), 768.0, device=dev).to(dt)
     out = _Act(obuf, Hout, Wout, opitch, 8, Cout, torch.zeros((G, opitch), device=dev), torch.zeros((G, opitch), device=dev))
     gamma = (0.5 + torch.rand(Cout, generator=g)).to(dev)
     beta = torch.randn(Cout, generator=g).to(dev)
@@ -77,7 +78,7 @@ def _run(case, storage, flags=0):
     torch.cuda.synchronize()
     assert launches, "layer did not take the halo path"
     got = obuf[..., 8:8 + Cout].float().permute(0, 3, 1, 2).double()
-    assert torch.all(obuf[..., :8].float() == 777.0), "wrote outside the channel window"
+    assert torch.all(obuf[..., :8].float() == 768.0), "wrote outside the channel window"
     rng = ref.abs().max().item()
     err = (got - ref).abs().max().item()
     tol = 2e-3 * rng + (2.0 ** -8 * rng if storage == 'bf16' else 0.0)

@@ -99,6 +99,7 @@ CASES = [
     ("deconv3x3s1", 1, 3, 1, 1, 17, 9, [64], 128, 128, 64),
     ("deconv3x3s2p0", 1, 3, 2, 0, 16, 9, [64], 32, 32, 64),
     ("conv3x3s1_pitch16", 0, 3, 1, 1, 20, 19, [64], 64, 64, 64),
+    ("conv3x3s1_tk16_stem", 0, 3, 1, 1, 20, 19, [16], 32, 32, 16),
 ]
 
 
