@@ -13,10 +13,11 @@
 //   * stride-2 convolutions split the halo into 4 parity planes (iy = 2(a+e)+q), so rows stay 16 bytes apart;
 //   * a stride-2 transposed convolution is its 4 sub-pixel classes over ONE halo: 16 (class, tap) MMAs per K step
 //     into 4 accumulators in TMEM (4 x BN columns).
-// Warp-specialised: warps 0-7 gather (producer BatchNorm + LeakyReLU + bf16 convert, 16-byte STS, double-buffered
-// halo), warp 8 streams the pre-packed weight blocks with cp.async.bulk (1-D TMA) through an NB-deep ring, warp 9
-// issues tcgen05.mma; mbarriers only (no __syncthreads in the main loop).  Epilogue: tcgen05.ld, raw output (fp32 or
-// bf16 NHWC) + deterministic per-tile partial batch statistics.
+// Persistent and warp-specialised (one CTA per SM looping over tiles): warps 4-11 gather (producer BatchNorm +
+// LeakyReLU + bf16 convert, 16-byte STS, double-buffered halo), warp 12 streams the pre-packed weight blocks with
+// cp.async.bulk (1-D TMA) through an NB-deep ring, warp 13 issues tcgen05.mma into one of two accumulator sets in TMEM,
+// warps 0-3 run the epilogue of the previous tile meanwhile (tcgen05.ld, bias/tanh, raw output fp32 or bf16 NHWC,
+// deterministic per-tile partial batch statistics).  mbarriers only; no __syncthreads in the steady state.
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -29,9 +30,10 @@ namespace halo {
 using namespace tc;
 
 constexpr int TH = 16, TW = 8, TM = 128;
-constexpr int LOADERS = 256, CTA = 320;
+constexpr int EPI = 128, LOADERS = 256, CTA = EPI + LOADERS + 64;    // warps 0-3 epilogue, 4-11 loaders, 12 TMA, 13 MMA
 constexpr int MAXT = 16;            // taps over all classes
 constexpr int MAXNPX = 640;         // halo pixels (4 planes x 17 x 9 = 612 for 4x4 s2)
+constexpr int EPI_SMEM = (4 * 32 * 33 + 16 * 4 * 64) * 4;            // per-warp transpose buffers + partial sums
 
 struct Plane { int qy, qx, oy, ox; };      // input row = (a0 + oy + hy) * istr + qy (same for columns)
 struct HTap { int cls, a_off, first; };    // a_off: byte offset of the tap's first row inside one K core of the halo
@@ -41,251 +43,313 @@ struct HaloArgs {
     int G, gsz, Hin, Win, Hout, Wout, Cout;
     int istr, ostr, nclass;
     int cls_py[4], cls_px[4], cls_Ha[4], cls_Wb[4];
-    int nty, ntx, tiles_m;
+    int nty, ntx, tiles_m, ntn, total_tiles;
     int nplane, PH, PW, NPX;               // uniform plane size, PW = row pitch in pixels
     int a_lbo;                             // bytes between the K cores of the halo (16 mod 128: conflict-free STS.128)
     Plane plane[4];
     int ntap;
     HTap tap[MAXT];
     int nkt, nkt0;                         // K chunks in total / in source 0
-    int tmem_cols;
+    int acc_cols, tmem_cols;               // TMEM columns of one accumulator set (nclass x BN) / allocated (2 sets)
     void* out; int out_pitch, out_ch_off, out_bf16;
     float* psum; float* psq;
+    const float* bias; int tanh_out;
 };
 
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
+struct TileCoord { int g, tile_m, tile_n, img, a0, b0; };
+__device__ __forceinline__ TileCoord decode_tile(const HaloArgs& A, int t) {
+    TileCoord c;
+    c.tile_n = t % A.ntn;
+    const int r = t / A.ntn;
+    c.tile_m = r % A.tiles_m;
+    c.g = r / A.tiles_m;
+    const int tiles_img = A.nty * A.ntx;
+    const int im = c.tile_m / tiles_img;
+    const int trem = c.tile_m - im * tiles_img;
+    const int tyi = trem / A.ntx;
+    c.a0 = tyi * TH; c.b0 = (trem - tyi * A.ntx) * TW;
+    c.img = c.g * A.gsz + im;
+    return c;
+}
+
+// Persistent: CTA b works on tiles b, b + gridDim.x, ...  (tile = scan pair, 16x8 block of output positions, n-tile).
+// Four roles run the same tile sequence and meet only at mbarriers:
+//   loaders  (256 thr)  halo of K chunk c -> smem buffer c&1            a_empty -> a_full
+//   TMA      (1 thr)    weight block (chunk, tap) -> ring slot          w_empty -> w_full
+//   MMA      (1 thr)    ntap x TK/16 tcgen05.mma per chunk into accumulator set tile&1; commits free slots / buffers
+//   epilogue (128 thr)  accumulator set tile&1 -> global + statistics   acc_full -> acc_empty
+// so the gather of tile i+1, the MMAs of tile i and the epilogue of tile i-1 overlap.
 template <int BN, int TK, int NB>
-__global__ void __launch_bounds__(CTA) conv_halo_tc(const HaloArgs A, const unsigned char* __restrict__ Wp) {
+__global__ void __launch_bounds__(CTA, 1) conv_halo_tc(const HaloArgs A, const unsigned char* __restrict__ Wp) {
     extern __shared__ __align__(128) unsigned char smem[];
     constexpr int KC = TK / 8;
     constexpr int B_BYTES = BN * TK * 2;
     constexpr int HSTEP = LOADERS / KC;            // halo pixels covered by one pass of the loader threads
     constexpr int U = 4;                           // loads in flight per loader thread
-    __shared__ __align__(8) uint64_t a_full[2], a_empty[2], w_full[NB], w_empty[NB], acc_full;
+    __shared__ __align__(8) uint64_t a_full[2], a_empty[2], w_full[NB], w_empty[NB], acc_full[2], acc_empty[2];
     __shared__ uint32_t tmem_slot;
     __shared__ int s_pix[MAXNPX];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int a_bytes = ((KC * A.a_lbo + 127) / 128) * 128;
-    unsigned char* sB = smem + 2 * a_bytes;
-    const int tile_m = blockIdx.x, tile_n = blockIdx.y, g = blockIdx.z;
-    const int tiles_img = A.nty * A.ntx;
-    const int im = tile_m / tiles_img;
-    const int trem = tile_m - im * tiles_img;
-    const int tyi = trem / A.ntx;
-    const int a0 = tyi * TH, b0 = (trem - tyi * A.ntx) * TW;
-    const int img = g * A.gsz + im;
+    unsigned char* sEpi = smem;                                  // [EPI_SMEM] epilogue scratch (never aliased)
+    unsigned char* sA = smem + EPI_SMEM;                         // 2 halo buffers
+    unsigned char* sB = sA + 2 * a_bytes;                        // NB weight slots
 
     if (tid == 0) {
         mbar_init(&a_full[0], LOADERS); mbar_init(&a_full[1], LOADERS);
         mbar_init(&a_empty[0], 1); mbar_init(&a_empty[1], 1);
 #pragma unroll
         for (int i = 0; i < NB; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
-        mbar_init(&acc_full, 1);
+        mbar_init(&acc_full[0], 1); mbar_init(&acc_full[1], 1);
+        mbar_init(&acc_empty[0], EPI); mbar_init(&acc_empty[1], EPI);
         fence_mbar_init();
     }
-    if (warp == 8) tmem_alloc(&tmem_slot, (uint32_t)A.tmem_cols);
-    {   // global pixel index of every halo pixel (-1 = zero padding); identical for every K chunk
-        const int ppl = A.PH * A.PW;
-        for (int h = tid; h < A.NPX; h += CTA) {
-            const int p = h / ppl; const int r = h - p * ppl; const int hy = r / A.PW; const int hx = r - hy * A.PW;
-            const int iy = (a0 + A.plane[p].oy + hy) * A.istr + A.plane[p].qy;
-            const int ix = (b0 + A.plane[p].ox + hx) * A.istr + A.plane[p].qx;
-            s_pix[h] = (iy >= 0 && iy < A.Hin && ix >= 0 && ix < A.Win) ? (img * A.Hin + iy) * A.Win + ix : -1;
-        }
-    }
+    if (warp == 12) tmem_alloc(&tmem_slot, (uint32_t)A.tmem_cols);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_d = tmem_slot;
 
-    if (warp < 8) {
+    if (warp >= 4 && warp < 12) {
         // ------------------------------------------------------------------ halo loaders
-        const int kc = tid % KC, h0 = tid / KC;
-        for (int c = 0; c < A.nkt; ++c) {
-            const int b = c & 1;
-            const int si = c < A.nkt0 ? 0 : 1;
-            const rp_conv_src& S = A.src[si];
-            const int ch = (c - (si ? A.nkt0 : 0)) * TK + kc * 8;
-            float sc[8], sh[8];
-            const bool act = S.act != 0;
-            const float slope = S.slope;
-            if (act) {
-                const float4* ps = reinterpret_cast<const float4*>(S.scale + (size_t)g * S.sstride + S.s_off + ch);
-                const float4* ph = reinterpret_cast<const float4*>(S.shift + (size_t)g * S.sstride + S.s_off + ch);
-                const float4 s0 = __ldg(ps), s1 = __ldg(ps + 1), q0 = __ldg(ph), q1 = __ldg(ph + 1);
-                sc[0] = s0.x; sc[1] = s0.y; sc[2] = s0.z; sc[3] = s0.w; sc[4] = s1.x; sc[5] = s1.y; sc[6] = s1.z; sc[7] = s1.w;
-                sh[0] = q0.x; sh[1] = q0.y; sh[2] = q0.z; sh[3] = q0.w; sh[4] = q1.x; sh[5] = q1.y; sh[6] = q1.z; sh[7] = q1.w;
-            } else {
-#pragma unroll
-                for (int q = 0; q < 8; ++q) { sc[q] = 1.f; sh[q] = 0.f; }
-            }
-            const bool in_bf16 = S.dtype == 1;
-            const size_t esz = in_bf16 ? 2 : 4;
-            const unsigned char* base = reinterpret_cast<const unsigned char*>(S.ptr) + (size_t)(S.ch_off + ch) * esz;
-            const size_t pstride = (size_t)S.pitch * esz;
-            mbar_wait(&a_empty[b], (uint32_t)(((c >> 1) & 1) ^ 1));      // the MMAs that read this buffer are done
-            unsigned char* dst = smem + b * a_bytes + kc * A.a_lbo;
-            for (int hb = h0; hb < A.NPX; hb += HSTEP * U) {
-                uint4 x[U][2];
-                int pix[U];
-#pragma unroll
-                for (int u = 0; u < U; ++u) {
-                    const int h = hb + u * HSTEP;
-                    pix[u] = h < A.NPX ? s_pix[h] : -2;
-                    if (pix[u] >= 0) {
-                        const uint4* p = reinterpret_cast<const uint4*>(base + (size_t)pix[u] * pstride);
-                        x[u][0] = __ldg(p);
-                        if (!in_bf16) x[u][1] = __ldg(p + 1);
-                    }
-                }
-#pragma unroll
-                for (int u = 0; u < U; ++u) {
-                    if (pix[u] == -2) continue;
-                    uint4 o = make_uint4(0u, 0u, 0u, 0u);
-                    if (pix[u] >= 0) {
-                        float v[8];
-                        if (in_bf16) {
-                            const __nv_bfloat162* hp = reinterpret_cast<const __nv_bfloat162*>(&x[u][0]);
-#pragma unroll
-                            for (int q = 0; q < 4; ++q) { float2 f = __bfloat1622float2(hp[q]); v[2 * q] = f.x; v[2 * q + 1] = f.y; }
-                        } else {
-                            v[0] = __uint_as_float(x[u][0].x); v[1] = __uint_as_float(x[u][0].y);
-                            v[2] = __uint_as_float(x[u][0].z); v[3] = __uint_as_float(x[u][0].w);
-                            v[4] = __uint_as_float(x[u][1].x); v[5] = __uint_as_float(x[u][1].y);
-                            v[6] = __uint_as_float(x[u][1].z); v[7] = __uint_as_float(x[u][1].w);
-                        }
-                        if (act) {
-#pragma unroll
-                            for (int q = 0; q < 8; ++q) { const float z = fmaf(v[q], sc[q], sh[q]); v[q] = z > 0.f ? z : slope * z; }
-                        }
-                        __nv_bfloat162 p0 = __floats2bfloat162_rn(v[0], v[1]), p1 = __floats2bfloat162_rn(v[2], v[3]);
-                        __nv_bfloat162 p2 = __floats2bfloat162_rn(v[4], v[5]), p3 = __floats2bfloat162_rn(v[6], v[7]);
-                        o.x = *reinterpret_cast<uint32_t*>(&p0); o.y = *reinterpret_cast<uint32_t*>(&p1);
-                        o.z = *reinterpret_cast<uint32_t*>(&p2); o.w = *reinterpret_cast<uint32_t*>(&p3);
-                    }
-                    *reinterpret_cast<uint4*>(dst + (size_t)(hb + u * HSTEP) * 16) = o;
+        const int lt = tid - EPI;
+        const int kc = lt % KC, h0 = lt / KC;
+        uint32_t cc = 0;                                         // chunk counter across tiles
+        for (int tile = blockIdx.x; tile < A.total_tiles; tile += gridDim.x) {
+            const TileCoord tc_ = decode_tile(A, tile);
+            named_bar_sync(2, LOADERS);                          // everyone is done with the previous tile's table
+            {   // global pixel index of every halo pixel (-1 = zero padding); identical for every K chunk
+                const int ppl = A.PH * A.PW;
+                for (int h = lt; h < A.NPX; h += LOADERS) {
+                    const int p = h / ppl; const int r = h - p * ppl; const int hy = r / A.PW; const int hx = r - hy * A.PW;
+                    const int iy = (tc_.a0 + A.plane[p].oy + hy) * A.istr + A.plane[p].qy;
+                    const int ix = (tc_.b0 + A.plane[p].ox + hx) * A.istr + A.plane[p].qx;
+                    s_pix[h] = (iy >= 0 && iy < A.Hin && ix >= 0 && ix < A.Win) ? (tc_.img * A.Hin + iy) * A.Win + ix : -1;
                 }
             }
-            fence_async_smem();                    // generic-proxy writes -> visible to the tensor core (async proxy)
-            mbar_arrive(&a_full[b]);
+            named_bar_sync(2, LOADERS);
+            const int g = tc_.g;
+            for (int c = 0; c < A.nkt; ++c, ++cc) {
+                const int b = cc & 1;
+                const int si = c < A.nkt0 ? 0 : 1;
+                const rp_conv_src& S = A.src[si];
+                const int ch = (c - (si ? A.nkt0 : 0)) * TK + kc * 8;
+                float sc[8], sh[8];
+                const bool act = S.act != 0;
+                const float slope = S.slope;
+                if (act) {
+                    const float4* ps = reinterpret_cast<const float4*>(S.scale + (size_t)g * S.sstride + S.s_off + ch);
+                    const float4* ph = reinterpret_cast<const float4*>(S.shift + (size_t)g * S.sstride + S.s_off + ch);
+                    const float4 s0 = __ldg(ps), s1 = __ldg(ps + 1), q0 = __ldg(ph), q1 = __ldg(ph + 1);
+                    sc[0] = s0.x; sc[1] = s0.y; sc[2] = s0.z; sc[3] = s0.w; sc[4] = s1.x; sc[5] = s1.y; sc[6] = s1.z; sc[7] = s1.w;
+                    sh[0] = q0.x; sh[1] = q0.y; sh[2] = q0.z; sh[3] = q0.w; sh[4] = q1.x; sh[5] = q1.y; sh[6] = q1.z; sh[7] = q1.w;
+                } else {
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) { sc[q] = 1.f; sh[q] = 0.f; }
+                }
+                const bool in_bf16 = S.dtype == 1;
+                const size_t esz = in_bf16 ? 2 : 4;
+                const unsigned char* base = reinterpret_cast<const unsigned char*>(S.ptr) + (size_t)(S.ch_off + ch) * esz;
+                const size_t pstride = (size_t)S.pitch * esz;
+                mbar_wait(&a_empty[b], (uint32_t)(((cc >> 1) & 1) ^ 1));  // the MMAs that read this buffer are done
+                unsigned char* dst = sA + b * a_bytes + kc * A.a_lbo;
+                for (int hb = h0; hb < A.NPX; hb += HSTEP * U) {
+                    uint4 x[U][2];
+                    int pix[U];
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        const int h = hb + u * HSTEP;
+                        pix[u] = h < A.NPX ? s_pix[h] : -2;
+                        if (pix[u] >= 0) {
+                            const uint4* p = reinterpret_cast<const uint4*>(base + (size_t)pix[u] * pstride);
+                            x[u][0] = __ldg(p);
+                            if (!in_bf16) x[u][1] = __ldg(p + 1);
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        if (pix[u] == -2) continue;
+                        uint4 o = make_uint4(0u, 0u, 0u, 0u);
+                        if (pix[u] >= 0) {
+                            float v[8];
+                            if (in_bf16) {
+                                const __nv_bfloat162* hp = reinterpret_cast<const __nv_bfloat162*>(&x[u][0]);
+#pragma unroll
+                                for (int q = 0; q < 4; ++q) { float2 f = __bfloat1622float2(hp[q]); v[2 * q] = f.x; v[2 * q + 1] = f.y; }
+                            } else {
+                                v[0] = __uint_as_float(x[u][0].x); v[1] = __uint_as_float(x[u][0].y);
+                                v[2] = __uint_as_float(x[u][0].z); v[3] = __uint_as_float(x[u][0].w);
+                                v[4] = __uint_as_float(x[u][1].x); v[5] = __uint_as_float(x[u][1].y);
+                                v[6] = __uint_as_float(x[u][1].z); v[7] = __uint_as_float(x[u][1].w);
+                            }
+                            if (act) {
+#pragma unroll
+                                for (int q = 0; q < 8; ++q) { const float z = fmaf(v[q], sc[q], sh[q]); v[q] = z > 0.f ? z : slope * z; }
+                            }
+                            __nv_bfloat162 p0 = __floats2bfloat162_rn(v[0], v[1]), p1 = __floats2bfloat162_rn(v[2], v[3]);
+                            __nv_bfloat162 p2 = __floats2bfloat162_rn(v[4], v[5]), p3 = __floats2bfloat162_rn(v[6], v[7]);
+                            o.x = *reinterpret_cast<uint32_t*>(&p0); o.y = *reinterpret_cast<uint32_t*>(&p1);
+                            o.z = *reinterpret_cast<uint32_t*>(&p2); o.w = *reinterpret_cast<uint32_t*>(&p3);
+                        }
+                        *reinterpret_cast<uint4*>(dst + (size_t)(hb + u * HSTEP) * 16) = o;
+                    }
+                }
+                fence_async_smem();                // generic-proxy writes -> visible to the tensor core (async proxy)
+                mbar_arrive(&a_full[b]);
+            }
         }
-    } else if (warp == 8) {
+    } else if (warp == 12) {
         // ------------------------------------------------------------------ weight stream (bulk TMA)
         if (lane == 0) {
-            const int total = A.nkt * A.ntap;
-            const unsigned char* wsrc = Wp + (size_t)tile_n * total * B_BYTES;
-            for (int wi = 0; wi < total; ++wi) {
-                const int slot = wi % NB;
-                mbar_wait(&w_empty[slot], (uint32_t)(((wi / NB) & 1) ^ 1));
-                mbar_expect_tx(&w_full[slot], B_BYTES);
-                bulk_g2s(sB + slot * B_BYTES, wsrc + (size_t)wi * B_BYTES, B_BYTES, &w_full[slot]);
+            const int per_tile = A.nkt * A.ntap;
+            uint32_t wi = 0;
+            for (int tile = blockIdx.x; tile < A.total_tiles; tile += gridDim.x) {
+                const int tile_n = tile % A.ntn;
+                const unsigned char* wsrc = Wp + (size_t)tile_n * per_tile * B_BYTES;
+                for (int i = 0; i < per_tile; ++i, ++wi) {
+                    const int slot = wi % NB;
+                    mbar_wait(&w_empty[slot], (uint32_t)(((wi / NB) & 1) ^ 1));
+                    mbar_expect_tx(&w_full[slot], B_BYTES);
+                    bulk_g2s(sB + slot * B_BYTES, wsrc + (size_t)i * B_BYTES, B_BYTES, &w_full[slot]);
+                }
             }
         }
         __syncwarp();
-    } else {
+    } else if (warp == 13) {
         // ------------------------------------------------------------------ MMA issue
         if (lane == 0) {
             const uint32_t idesc = make_idesc_bf16(TM, BN);
             const uint32_t sbo = (uint32_t)A.PW * 16u;
-            int wi = 0;
-            for (int c = 0; c < A.nkt; ++c) {
-                const int b = c & 1;
-                mbar_wait(&a_full[b], (uint32_t)((c >> 1) & 1));
+            uint32_t wi = 0, cc = 0, tl = 0;
+            for (int tile = blockIdx.x; tile < A.total_tiles; tile += gridDim.x, ++tl) {
+                const uint32_t ab = tl & 1;
+                mbar_wait(&acc_empty[ab], (uint32_t)(((tl >> 1) & 1) ^ 1));   // the epilogue has drained this accumulator set
                 tc_fence_after();
-                const uint32_t abase = smem_u32(smem + b * a_bytes);
-                for (int t = 0; t < A.ntap; ++t, ++wi) {
-                    const int slot = wi % NB;
-                    mbar_wait(&w_full[slot], (uint32_t)((wi / NB) & 1));
-                    const uint32_t bbase = smem_u32(sB + slot * B_BYTES);
-                    const uint32_t acol = tmem_d + (uint32_t)(A.tap[t].cls * BN);
+                const uint32_t acc0 = tmem_d + ab * (uint32_t)A.acc_cols;
+                for (int c = 0; c < A.nkt; ++c, ++cc) {
+                    const int b = cc & 1;
+                    mbar_wait(&a_full[b], (uint32_t)((cc >> 1) & 1));
+                    tc_fence_after();
+                    const uint32_t abase = smem_u32(sA + b * a_bytes);
+                    for (int t = 0; t < A.ntap; ++t, ++wi) {
+                        const int slot = wi % NB;
+                        mbar_wait(&w_full[slot], (uint32_t)((wi / NB) & 1));
+                        const uint32_t bbase = smem_u32(sB + slot * B_BYTES);
+                        const uint32_t acol = acc0 + (uint32_t)(A.tap[t].cls * BN);
 #pragma unroll
-                    for (int j = 0; j < TK / 16; ++j) {
-                        const uint64_t ad = make_smem_desc(abase + (uint32_t)A.tap[t].a_off + (uint32_t)(j * 2 * A.a_lbo), (uint32_t)A.a_lbo, sbo);
-                        const uint64_t bd = make_smem_desc(bbase + j * 2 * (BN / 8) * 128, (BN / 8) * 128, 128);
-                        umma_bf16(acol, ad, bd, idesc, (c > 0 || !A.tap[t].first || j > 0) ? 1u : 0u);
+                        for (int j = 0; j < TK / 16; ++j) {
+                            const uint64_t ad = make_smem_desc(abase + (uint32_t)A.tap[t].a_off + (uint32_t)(j * 2 * A.a_lbo), (uint32_t)A.a_lbo, sbo);
+                            const uint64_t bd = make_smem_desc(bbase + j * 2 * (BN / 8) * 128, (BN / 8) * 128, 128);
+                            umma_bf16(acol, ad, bd, idesc, (c > 0 || !A.tap[t].first || j > 0) ? 1u : 0u);
+                        }
+                        umma_commit(&w_empty[slot]);   // frees the weight slot once these MMAs have read it
                     }
-                    umma_commit(&w_empty[slot]);   // frees the weight slot once these MMAs have read it
+                    umma_commit(&a_empty[b]);          // frees the halo buffer
                 }
-                umma_commit(&a_empty[b]);          // frees the halo buffer
+                umma_commit(&acc_full[ab]);            // accumulator set complete
             }
-            umma_commit(&acc_full);
         }
         __syncwarp();
-    }
-
-    // ---------------------------------------------------------------------- epilogue (warps 0-7)
-    if (warp < 8) {
-        mbar_wait(&acc_full, 0u);
-        tc_fence_after();
-        named_bar_sync(1, LOADERS);                // every loader is past the main loop: stage memory is reusable
-        float* Tt = reinterpret_cast<float*>(smem) + warp * (32 * 33);         // per-warp [32 rows][33]
-        float* red = reinterpret_cast<float*>(smem) + 8 * 32 * 33;             // [unit][quarter][32] x {sum, sq}
-        const int q = warp & 3, hh = warp >> 2;
+    } else {
+        // ------------------------------------------------------------------ epilogue (warps 0-3 = TMEM lane quarters)
+        float* Tt = reinterpret_cast<float*>(sEpi) + warp * (32 * 33);         // per-warp [32 rows][33]
+        float* red = reinterpret_cast<float*>(sEpi) + 4 * 32 * 33;             // [unit][quarter][32] x {sum, sq}
+        const int q = warp;
         const int m = q * 32 + lane;
-        const int a = a0 + (m >> 3), bcol = b0 + (m & 7);
         const int nunit = A.nclass * (BN / 32);
-        for (int u = hh; u < nunit; u += 2) {
-            const int cls = u / (BN / 32), c0 = (u - cls * (BN / 32)) * 32;
-            float v[32];
-            tmem_ld32(tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)(cls * BN + c0), v);
-            const bool valid = a < A.cls_Ha[cls] && bcol < A.cls_Wb[cls];
-            const int co0 = tile_n * BN + c0;
-            if (valid) {
-                const int oy = a * A.ostr + A.cls_py[cls], ox = bcol * A.ostr + A.cls_px[cls];
-                const size_t opix = ((size_t)img * A.Hout + oy) * A.Wout + ox;
-                if (A.out_bf16) {
-                    __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(A.out) + opix * A.out_pitch + A.out_ch_off + co0;
+        uint32_t tl = 0;
+        for (int tile = blockIdx.x; tile < A.total_tiles; tile += gridDim.x, ++tl) {
+            const TileCoord tc_ = decode_tile(A, tile);
+            const uint32_t ab = tl & 1;
+            const int a = tc_.a0 + (m >> 3), bcol = tc_.b0 + (m & 7);
+            mbar_wait(&acc_full[ab], (uint32_t)((tl >> 1) & 1));
+            tc_fence_after();
+            for (int u = 0; u < nunit; ++u) {
+                const int cls = u / (BN / 32), c0 = (u - cls * (BN / 32)) * 32;
+                float v[32];
+                tmem_ld32(tmem_d + ((uint32_t)(q * 32) << 16) + ab * (uint32_t)A.acc_cols + (uint32_t)(cls * BN + c0), v);
+                const bool valid = a < A.cls_Ha[cls] && bcol < A.cls_Wb[cls];
+                const int co0 = tc_.tile_n * BN + c0;
+                if (A.bias || A.tanh_out) {
 #pragma unroll
-                    for (int j = 0; j < 32; j += 8) {
-                        __nv_bfloat162 p0 = __floats2bfloat162_rn(v[j], v[j + 1]), p1 = __floats2bfloat162_rn(v[j + 2], v[j + 3]);
-                        __nv_bfloat162 p2 = __floats2bfloat162_rn(v[j + 4], v[j + 5]), p3 = __floats2bfloat162_rn(v[j + 6], v[j + 7]);
-                        uint4 o;
-                        o.x = *reinterpret_cast<uint32_t*>(&p0); o.y = *reinterpret_cast<uint32_t*>(&p1);
-                        o.z = *reinterpret_cast<uint32_t*>(&p2); o.w = *reinterpret_cast<uint32_t*>(&p3);
-                        *reinterpret_cast<uint4*>(op + j) = o;
-                        // statistics of what the consumer will read (the rounded values)
-                        float2 f0 = __bfloat1622float2(p0), f1 = __bfloat1622float2(p1), f2 = __bfloat1622float2(p2), f3 = __bfloat1622float2(p3);
-                        v[j] = f0.x; v[j + 1] = f0.y; v[j + 2] = f1.x; v[j + 3] = f1.y;
-                        v[j + 4] = f2.x; v[j + 5] = f2.y; v[j + 6] = f3.x; v[j + 7] = f3.y;
+                    for (int j = 0; j < 32; ++j) {
+                        if (co0 + j < A.Cout) { const float y = v[j] + (A.bias ? __ldg(A.bias + co0 + j) : 0.f); v[j] = A.tanh_out ? tanhf(y) : y; }
                     }
-                } else {
-                    float* op = reinterpret_cast<float*>(A.out) + opix * A.out_pitch + A.out_ch_off + co0;
+                }
+                if (A.out_bf16) {          // statistics describe what the consumer will read: the rounded values
 #pragma unroll
-                    for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(op + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                    for (int j = 0; j < 32; ++j) v[j] = __bfloat162float(__float2bfloat16_rn(v[j]));
+                }
+                if (valid) {
+                    const int oy = a * A.ostr + A.cls_py[cls], ox = bcol * A.ostr + A.cls_px[cls];
+                    const size_t opix = ((size_t)tc_.img * A.Hout + oy) * A.Wout + ox;
+                    if (A.out_bf16) {
+                        __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(A.out) + opix * A.out_pitch + A.out_ch_off + co0;
+                        if (co0 + 31 < A.Cout) {
+#pragma unroll
+                            for (int j = 0; j < 32; j += 8) {
+                                __nv_bfloat162 p0 = __floats2bfloat162_rn(v[j], v[j + 1]), p1 = __floats2bfloat162_rn(v[j + 2], v[j + 3]);
+                                __nv_bfloat162 p2 = __floats2bfloat162_rn(v[j + 4], v[j + 5]), p3 = __floats2bfloat162_rn(v[j + 6], v[j + 7]);
+                                uint4 o;
+                                o.x = *reinterpret_cast<uint32_t*>(&p0); o.y = *reinterpret_cast<uint32_t*>(&p1);
+                                o.z = *reinterpret_cast<uint32_t*>(&p2); o.w = *reinterpret_cast<uint32_t*>(&p3);
+                                *reinterpret_cast<uint4*>(op + j) = o;
+                            }
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) if (co0 + j < A.Cout) op[j] = __float2bfloat16_rn(v[j]);
+                        }
+                    } else {
+                        float* op = reinterpret_cast<float*>(A.out) + opix * A.out_pitch + A.out_ch_off + co0;
+                        if (co0 + 31 < A.Cout && ((((size_t)op) & 15) == 0)) {
+#pragma unroll
+                            for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(op + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) if (co0 + j < A.Cout) op[j] = v[j];
+                        }
+                    }
+                }
+                if (A.psum) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) Tt[lane * 33 + j] = valid ? v[j] : 0.f;
+                    __syncwarp();
+                    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+                    for (int r = 0; r < 32; ++r) { const float x = Tt[r * 33 + lane]; s1 += x; s2 += x * x; }
+                    red[(u * 4 + q) * 64 + lane] = s1;
+                    red[(u * 4 + q) * 64 + 32 + lane] = s2;
+                    __syncwarp();
                 }
             }
+            tc_fence_before();
+            mbar_arrive(&acc_empty[ab]);               // this thread's tcgen05.ld of the set have completed (wait::ld)
             if (A.psum) {
-#pragma unroll
-                for (int j = 0; j < 32; ++j) Tt[lane * 33 + j] = valid ? v[j] : 0.f;
-                __syncwarp();
-                float s1 = 0.f, s2 = 0.f;
-#pragma unroll
-                for (int r = 0; r < 32; ++r) { const float x = Tt[r * 33 + lane]; s1 += x; s2 += x * x; }
-                red[(u * 4 + q) * 64 + lane] = s1;
-                red[(u * 4 + q) * 64 + 32 + lane] = s2;
-                __syncwarp();
-            }
-        }
-        if (A.psum) {
-            named_bar_sync(1, LOADERS);
-            for (int i = tid; i < nunit * 32; i += LOADERS) {
-                const int u = i >> 5, col = i & 31;
-                const int cls = u / (BN / 32), c0 = (u - cls * (BN / 32)) * 32;
-                const float* r = red + (u * 4) * 64;
-                const float s1 = ((r[col] + r[64 + col]) + r[128 + col]) + r[192 + col];
-                const float s2 = ((r[32 + col] + r[96 + col]) + r[160 + col]) + r[224 + col];
-                const size_t prow = (size_t)(g * A.nclass + cls) * A.tiles_m + tile_m;
-                A.psum[prow * A.Cout + tile_n * BN + c0 + col] = s1;
-                A.psq[prow * A.Cout + tile_n * BN + c0 + col] = s2;
+                named_bar_sync(3, EPI);
+                for (int i = tid; i < nunit * 32; i += EPI) {
+                    const int u = i >> 5, col = i & 31;
+                    const int cls = u / (BN / 32), c0 = (u - cls * (BN / 32)) * 32;
+                    const int co = tc_.tile_n * BN + c0 + col;
+                    if (co < A.Cout) {
+                        const float* r = red + (u * 4) * 64;
+                        const float s1 = ((r[col] + r[64 + col]) + r[128 + col]) + r[192 + col];
+                        const float s2 = ((r[32 + col] + r[96 + col]) + r[160 + col]) + r[224 + col];
+                        const size_t prow = (size_t)(tc_.g * A.nclass + cls) * A.tiles_m + tc_.tile_m;
+                        A.psum[prow * A.Cout + co] = s1;
+                        A.psq[prow * A.Cout + co] = s2;
+                    }
+                }
+                named_bar_sync(3, EPI);                // `red` is free for the next tile
             }
         }
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 8) tmem_dealloc(tmem_d, (uint32_t)A.tmem_cols);
+    if (warp == 12) tmem_dealloc(tmem_d, (uint32_t)A.tmem_cols);
 }
 
 // -------------------------------------------------------------------------------------------------------------------
@@ -295,8 +359,6 @@ static inline int floordiv(int a, int b) { int q = a / b; if ((a % b != 0) && ((
 static bool build_halo_args(const rp_conv_desc* d, HaloArgs* H, int bn, int tk, int* tap_widx, bool pitch16) {
     scnet::ConvArgs A;
     if (!scnet::build_args(d, &A, TM)) return false;
-    if (d->bias || d->tanh_out) return false;
-    if (d->Cout % bn) return false;
     H->nsrc = A.nsrc;
     for (int i = 0; i < A.nsrc; ++i) {
         H->src[i] = A.src[i];
@@ -316,6 +378,8 @@ static bool build_halo_args(const rp_conv_desc* d, HaloArgs* H, int bn, int tk, 
     }
     if (ntap > MAXT || Hb < 1 || Wb < 1) return false;
     H->nty = (Hb + TH - 1) / TH; H->ntx = (Wb + TW - 1) / TW; H->tiles_m = A.gsz * H->nty * H->ntx;
+    H->ntn = (A.Cout + bn - 1) / bn;
+    H->total_tiles = A.G * H->tiles_m * H->ntn;
     const int s = A.istr;
     H->nplane = s * s;
     if (H->nplane > 4) return false;
@@ -360,12 +424,15 @@ static bool build_halo_args(const rp_conv_desc* d, HaloArgs* H, int bn, int tk, 
     H->nkt = 0;
     for (int i = 0; i < A.nsrc; ++i) H->nkt += A.src[i].C / tk;
     H->nkt0 = A.src[0].C / tk;
+    H->acc_cols = A.nclass * bn;
     int cols = 32;
-    while (cols < A.nclass * bn) cols <<= 1;
+    while (cols < 2 * H->acc_cols) cols <<= 1;                 // two accumulator sets (epilogue of tile i-1 || MMAs of tile i)
     if (cols > 512) return false;
     H->tmem_cols = cols;
+    H->bias = d->bias; H->tanh_out = d->tanh_out;
+    if (d->out_dtype == 1 && (d->bias || d->tanh_out)) return false;
     H->out = d->out; H->out_pitch = d->out_pitch; H->out_ch_off = d->out_ch_off; H->out_bf16 = d->out_dtype == 1 ? 1 : 0;
-    if (H->out_bf16 ? ((d->out_pitch % 8) || (d->out_ch_off % 8)) : ((d->out_pitch % 4) || (d->out_ch_off % 4))) return false;
+    if (H->out_bf16 && ((d->out_pitch % 8) || (d->out_ch_off % 8))) return false;   // float32 output: any alignment (scalar stores)
     H->psum = d->psum; H->psq = d->psq;
     return true;
 }
@@ -374,13 +441,16 @@ template <int BN, int TK, int NB>
 static int launch_halo(const HaloArgs& H, const void* wp, cudaStream_t stream) {
     constexpr int KC = TK / 8;
     const size_t a_bytes = (size_t)((KC * H.a_lbo + 127) / 128) * 128;
-    size_t smem = 2 * a_bytes + (size_t)NB * BN * TK * 2;
-    const size_t epi = (size_t)(8 * 32 * 33 + 16 * 4 * 64) * 4;
-    if (smem < epi) smem = epi;
-    if (smem > 200 * 1024) return RP_ERR_UNSUPPORTED;
+    const size_t smem = (size_t)EPI_SMEM + 2 * a_bytes + (size_t)NB * BN * TK * 2;
+    if (smem > 220 * 1024) return RP_ERR_UNSUPPORTED;
     auto kern = conv_halo_tc<BN, TK, NB>;
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { cudaGetLastError(); return RP_ERR_CUDA; }
-    dim3 grid(H.tiles_m, H.Cout / BN, H.G);
+    static int n_sm = 0;
+    if (n_sm == 0) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n_sm < 1) { cudaGetLastError(); n_sm = 148; }
+    }
+    const int grid = H.total_tiles < n_sm ? H.total_tiles : n_sm;       // persistent: one CTA per SM
     kern<<<grid, CTA, smem, stream>>>(H, static_cast<const unsigned char*>(wp));
     ++scnet::g_conv_launches;
     return cudaGetLastError() == cudaSuccess ? RP_OK : RP_ERR_CUDA;
@@ -422,9 +492,9 @@ int rp_conv_layer_halo(const rp_conv_desc* d, const void* w_packed, int bn, int 
     if (!halo::build_halo_args(d, &H, bn, tk, nullptr, (flags & 1) != 0)) return RP_ERR_UNSUPPORTED;
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
 #define RP_HALO_CASE(BN_, TK_, NB_) if (bn == BN_ && tk == TK_) return halo::launch_halo<BN_, TK_, NB_>(H, w_packed, stream);
-    RP_HALO_CASE(32, 64, 8) RP_HALO_CASE(64, 64, 6) RP_HALO_CASE(128, 64, 4)
-    RP_HALO_CASE(32, 32, 8) RP_HALO_CASE(64, 32, 6) RP_HALO_CASE(128, 32, 4)
-    RP_HALO_CASE(32, 16, 8)
+    RP_HALO_CASE(32, 64, 16) RP_HALO_CASE(64, 64, 12) RP_HALO_CASE(128, 64, 6)
+    RP_HALO_CASE(32, 32, 16) RP_HALO_CASE(64, 32, 16) RP_HALO_CASE(128, 32, 8)
+    RP_HALO_CASE(32, 16, 16)
 #undef RP_HALO_CASE
     return RP_ERR_UNSUPPORTED;
 }

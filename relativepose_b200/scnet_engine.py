@@ -55,8 +55,11 @@ def _pack_halo_f32(w_taps, tap_widx, src_channels, cout, bn, tk):
     halo kernel (csrc/scnet_halo.cu): block i of a K chunk is tap ``tap_widx[i]`` (the (class, tap) order reported by
     rp_conv_halo_plan), so the blocks one CTA consumes are contiguous and in consumption order."""
     import torch
-    assert cout % bn == 0
-    ntn = cout // bn
+    ntn = -(-cout // bn)
+    if ntn * bn != cout:                                                        # zero-pad Cout to whole n-tiles
+        Wz = torch.zeros((w_taps.shape[0], w_taps.shape[1], ntn * bn), dtype=w_taps.dtype, device=w_taps.device)
+        Wz[:, :, :cout] = w_taps
+        w_taps = Wz
     k0s, base = [], 0
     for c in src_channels:
         assert c % tk == 0
@@ -82,6 +85,7 @@ class ScnetEngine(object):
         # halo-tile tcgen05 kernel for the 3x3 / 4x4 layers with a large enough spatial extent (csrc/scnet_halo.cu)
         self.halo = os.environ.get("RP_SCNET_HALO", "1") == "1"
         self.halo_flags = int(os.environ.get("RP_SCNET_HALO_FLAGS", "0"))
+        self.halo_min = int(os.environ.get("RP_SCNET_HALO_MIN", "1"))     # smallest base-grid extent that takes the halo kernel
         act = os.environ.get("RP_SCNET_ACT", self._act_default)
         self.act_bf16 = self.mode == 'tc' and act == 'bf16'
         self._graphs = {}
@@ -185,17 +189,18 @@ class ScnetEngine(object):
         d.bias = bias.data_ptr() if bias is not None else None
         d.tanh_out = int(tanh)
         use_tc = self.mode == 'tc' and all(a.C % 16 == 0 for a in srcs)
-        if k == 1 and not bn and out.C <= 32 and sum(a.C for a in srcs) <= 128:
-            use_tc = False                   # 1x1 output heads: dedicated CUDA-core kernel inside rp_conv_layer
+        if k == 1 and not bn and out.C <= 32 and sum(a.C for a in srcs) <= 128 and not self.halo:
+            use_tc = False                   # 1x1 output heads without the halo kernel: CUDA-core kernel inside rp_conv_layer
         use_halo = False
         nparts = ctypes.c_int(0)
-        if use_tc and self.halo and bn and k in (3, 4) and min(out.H, out.W) // (s if transposed else 1) >= 14:
+        if use_tc and self.halo and ((bn and k in (3, 4)) or (k == 1 and s == 1)) and \
+                min(out.H, out.W) // (s if transposed else 1) >= self.halo_min:
             # halo-tile kernel: stride-2 convolutions keep 4 parity planes of the halo, so their K chunk is 32
             tk = 32 if (s == 2 and not transposed) else (64 if all(a.C % 64 == 0 for a in srcs) else 32)
             if any(a.C % 32 for a in srcs):
                 tk = 16                          # the bf16-split stem (conv1*, 16 channels per group)
             cap = 64 if (transposed and s == 2) else 128                  # 4 accumulators x bn TMEM columns
-            bn_tile = next((b for b in (128, 64, 32) if b <= cap and out.C % b == 0), 0)
+            bn_tile = next((b for b in (128, 64, 32) if b <= cap and out.C % b == 0), 32)   # 32: Cout zero-padded (heads)
             ntap = ctypes.c_int(0)
             widx = (ctypes.c_int * 16)()
             if bn_tile and self.lib.rp_conv_halo_plan(ctypes.byref(d), bn_tile, tk, self.halo_flags, ctypes.byref(nparts),

@@ -19,6 +19,18 @@ CASES = [
     ("deconv3x3s1", 1, 3, 1, 1, 17, 23, [64], 128),
     ("deconv3x3s2p0", 1, 3, 2, 0, 16, 15, [64], 32),
     ("conv3x3s1_tk16_stem", 0, 3, 1, 1, 48, 40, [16], 32),
+    ("conv4x4s2_14to7", 0, 4, 2, 1, 14, 14, [512], 512),
+    ("conv3x3p0_to1x1", 0, 3, 1, 0, 3, 3, [512], 1024),
+    ("deconv3x3p0_from1x1", 1, 3, 1, 0, 1, 1, [1024], 512),
+    ("deconv3x3s2p0_3to7", 1, 3, 2, 0, 3, 3, [512, 512], 512),
+    ("conv3x3s1_many_tiles", 0, 3, 1, 1, 112, 112, [64], 64),
+]
+
+HEADS = [
+    # name, Hin, Win, [Cin...], Cout, tanh
+    ("head_rgb", 56, 40, [32, 32], 3, 0),
+    ("head_sem", 56, 40, [64], 21, 0),
+    ("head_feat_tanh", 56, 40, [64], 32, 1),
 ]
 
 
@@ -104,3 +116,58 @@ def test_halo_layer_matches_torch(case, storage):
 def test_halo_layer_pitch16_variant():
     err, tol, rng, e_sc, e_sh = _run(CASES[0], "fp32", flags=1)
     assert err <= tol and e_sc <= 1e-3
+
+
+@pytest.mark.parametrize("storage", ["fp32", "bf16"])
+@pytest.mark.parametrize("case", HEADS, ids=[c[0] for c in HEADS])
+def test_halo_1x1_head_with_bias(case, storage):
+    """The 1x1 output heads (Conv2d + bias [+ tanh], no BatchNorm, float32 output at an unaligned channel offset of a
+    wider tensor) on the halo kernel with Cout zero-padded to one n-tile."""
+    import torch
+    import torch.nn.functional as F
+    from relativepose_b200.scnet_engine import ScnetEngine, _Act
+    name, Hin, Win, cins, Cout, tanh = case
+    dev = torch.device("cuda:0")
+    G, gsz = 3, 2
+    n = G * gsz
+    g = torch.Generator(device="cpu").manual_seed(11)
+    eng = ScnetEngine(None, mode='tc')
+    eng.halo = True
+    eng._P, eng._dev, eng._bufs = G, dev, {'partials': None}
+    dt = torch.bfloat16 if storage == 'bf16' else torch.float32
+    srcs, xs = [], []
+    for c in cins:
+        raw = torch.randn((n, Hin, Win, c), generator=g).to(dev).to(dt)
+        sc = (0.5 + torch.rand((G, c), generator=g)).to(dev)
+        sh = (0.3 * torch.randn((G, c), generator=g)).to(dev)
+        srcs.append(_Act(raw, Hin, Win, c, 0, c, sc, sh))
+        xa = raw.float() * sc.repeat_interleave(gsz, 0)[:, None, None, :] + sh.repeat_interleave(gsz, 0)[:, None, None, :]
+        xs.append(F.leaky_relu(xa, 0.1).to(torch.bfloat16).float())
+    x = torch.cat(xs, 3).permute(0, 3, 1, 2).contiguous()
+    Cin = sum(cins)
+    w = torch.randn((Cout, Cin, 1, 1), generator=g).to(dev) / Cin ** 0.5
+    bias = torch.randn(Cout, generator=g).to(dev)
+    ref = F.conv2d(x.double(), w.to(torch.bfloat16).double(), bias.double())
+    if tanh:
+        ref = torch.tanh(ref)
+    eng._packed = {'L': w.permute(2, 3, 1, 0).contiguous()}
+    obuf = torch.full((n, Hin, Win, 54), 768.0, device=dev)
+    out = _Act(obuf, Hin, Win, 54, 3, Cout)                       # channel offset 3: unaligned float4
+    launches = []
+    orig = eng.lib.rp_conv_layer_halo
+
+    def spy(*a):
+        launches.append(1)
+        return orig(*a)
+    eng.lib.rp_conv_layer_halo = spy
+    try:
+        eng._conv('L', srcs, out, False, 1, 1, 0, bn=False, bias=bias, tanh=bool(tanh), stream=torch.cuda.current_stream().cuda_stream)
+    finally:
+        eng.lib.rp_conv_layer_halo = orig
+    torch.cuda.synchronize()
+    assert launches, "head did not take the halo path"
+    got = obuf[..., 3:3 + Cout].permute(0, 3, 1, 2).double()
+    assert torch.all(obuf[..., :3] == 768.0) and torch.all(obuf[..., 3 + Cout:] == 768.0), "wrote outside the channel window"
+    err = (got - ref).abs().max().item()
+    print("%s/%s: max err %.3e (range %.2f)" % (name, storage, err, ref.abs().max().item()))
+    assert err <= 2e-3 * max(1.0, ref.abs().max().item())

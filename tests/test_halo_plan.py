@@ -55,7 +55,7 @@ def _emulate(x, Wp, P, bn, tk, Cout, gsz, G, Hin, Win, Hout, Wout):
                 ix = (b0 + ox + hx) * P["istr"] + qx
                 if 0 <= iy < Hin and 0 <= ix < Win:
                     pix[h] = iy * Win + ix
-            for tile_n in range(Cout // bn):
+            for tile_n in range(-(-Cout // bn)):
                 acc = np.zeros((P["nclass"], 128, bn), np.float64)
                 seen = np.zeros(P["nclass"], bool)
                 for c in range(P["nkt"]):
@@ -84,7 +84,8 @@ def _emulate(x, Wp, P, bn, tk, Cout, gsz, G, Hin, Win, Hout, Wout):
                     py, px, Ha, Wb = P["cls"][cls]
                     ok = (a < Ha) & (b < Wb)
                     oy, ox = a[ok] * P["ostr"] + py, b[ok] * P["ostr"] + px
-                    out[img, oy, ox, tile_n * bn:(tile_n + 1) * bn] = acc[cls][ok]
+                    nco = min(bn, Cout - tile_n * bn)
+                    out[img, oy, ox, tile_n * bn:tile_n * bn + nco] = acc[cls][ok][:, :nco]
     return out
 
 
@@ -100,6 +101,12 @@ CASES = [
     ("deconv3x3s2p0", 1, 3, 2, 0, 16, 9, [64], 32, 32, 64),
     ("conv3x3s1_pitch16", 0, 3, 1, 1, 20, 19, [64], 64, 64, 64),
     ("conv3x3s1_tk16_stem", 0, 3, 1, 1, 20, 19, [16], 32, 32, 16),
+    ("head1x1_cout3", 0, 1, 1, 0, 20, 19, [32, 32], 3, 32, 32),
+    ("head1x1_cout21", 0, 1, 1, 0, 17, 9, [64], 21, 32, 64),
+    ("conv3x3p0_to1x1", 0, 3, 1, 0, 3, 3, [64], 128, 128, 64),
+    ("deconv3x3p0_from1x1", 1, 3, 1, 0, 1, 1, [64], 64, 64, 64),
+    ("conv4x4s2_14to7", 0, 4, 2, 1, 14, 14, [32], 32, 32, 32),
+    ("deconv3x3s2p0_3to7", 1, 3, 2, 0, 3, 3, [64, 64], 64, 64, 64),
 ]
 
 
@@ -141,7 +148,7 @@ def test_halo_plan_reproduces_convolution(case):
         wt = torch.from_numpy(w).permute(2, 3, 1, 0)
     assert tuple(ref.shape[2:]) == (Hout, Wout)
     Wp = pack_halo(wt.reshape(k * k, Cin, Cout).contiguous().float(), P["widx"], cins, Cout, bn, tk)
-    assert Wp.shape == (Cout // bn, P["nkt"], P["ntap"], tk // 8, bn // 8, 8, 8)
+    assert Wp.shape == (-(-Cout // bn), P["nkt"], P["ntap"], tk // 8, bn // 8, 8, 8)
     # the kernel reads bf16 weights; emulate with the unrounded values (this test is about addressing, not rounding)
     import relativepose_b200.scnet_engine as se
     Wf = se._pack_halo_f32(wt.reshape(k * k, Cin, Cout).contiguous().float(), P["widx"], cins, Cout, bn, tk)
