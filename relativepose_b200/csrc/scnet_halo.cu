@@ -44,6 +44,7 @@ struct HaloArgs {
     int istr, ostr, nclass;
     int cls_py[4], cls_px[4], cls_Ha[4], cls_Wb[4];
     int nty, ntx, tiles_m, ntn, total_tiles;
+    float inv_ntn, inv_tiles_m, inv_tiles_img, inv_ntx;   // reciprocals for fdiv()
     int nplane, PH, PW, NPX;               // uniform plane size, PW = row pitch in pixels
     int a_lbo;                             // bytes between the K cores of the halo (16 mod 128: conflict-free STS.128)
     Plane plane[4];
@@ -60,21 +61,42 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
+// n / d for 0 <= n < 2^24 through a float reciprocal and one correction step (the integer divide sequence costs ~20
+// instructions; a persistent CTA decodes a tile index per role and per tile)
+__device__ __forceinline__ int fdiv(int n, int d, float inv) {
+    int q = (int)((float)n * inv);
+    if (q * d > n) --q;
+    if ((q + 1) * d <= n) ++q;
+    return q;
+}
+
 struct TileCoord { int g, tile_m, tile_n, img, a0, b0; };
 __device__ __forceinline__ TileCoord decode_tile(const HaloArgs& A, int t) {
     TileCoord c;
-    c.tile_n = t % A.ntn;
-    const int r = t / A.ntn;
-    c.tile_m = r % A.tiles_m;
-    c.g = r / A.tiles_m;
+    const int r = fdiv(t, A.ntn, A.inv_ntn);
+    c.tile_n = t - r * A.ntn;
+    c.g = fdiv(r, A.tiles_m, A.inv_tiles_m);
+    c.tile_m = r - c.g * A.tiles_m;
     const int tiles_img = A.nty * A.ntx;
-    const int im = c.tile_m / tiles_img;
+    const int im = fdiv(c.tile_m, tiles_img, A.inv_tiles_img);
     const int trem = c.tile_m - im * tiles_img;
-    const int tyi = trem / A.ntx;
+    const int tyi = fdiv(trem, A.ntx, A.inv_ntx);
     c.a0 = tyi * TH; c.b0 = (trem - tyi * A.ntx) * TW;
     c.img = c.g * A.gsz + im;
     return c;
 }
+
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred = 0;
+    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+__device__ __forceinline__ float fast_tanh(float x) {
+    float y;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ uint64_t pack_desc(uint32_t lo, uint32_t hi) { return ((uint64_t)hi << 32) | (uint64_t)lo; }
 
 // Persistent: CTA b works on tiles b, b + gridDim.x, ...  (tile = scan pair, 16x8 block of output positions, n-tile).
 // Four roles run the same tile sequence and meet only at mbarriers:
@@ -93,6 +115,7 @@ __global__ void __launch_bounds__(CTA, 1) conv_halo_tc(const HaloArgs A, const u
     __shared__ __align__(8) uint64_t a_full[2], a_empty[2], w_full[NB], w_empty[NB], acc_full[2], acc_empty[2];
     __shared__ uint32_t tmem_slot;
     __shared__ int s_pix[MAXNPX];
+    __shared__ int s_lut[MAXNPX];                  // halo pixel -> (plane << 20 | row << 10 | column), tile independent
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int a_bytes = ((KC * A.a_lbo + 127) / 128) * 128;
     unsigned char* sEpi = smem;                                  // [EPI_SMEM] epilogue scratch (never aliased)
@@ -109,6 +132,13 @@ __global__ void __launch_bounds__(CTA, 1) conv_halo_tc(const HaloArgs A, const u
         fence_mbar_init();
     }
     if (warp == 12) tmem_alloc(&tmem_slot, (uint32_t)A.tmem_cols);
+    {
+        const int ppl = A.PH * A.PW;
+        for (int h = tid; h < A.NPX; h += CTA) {
+            const int p = h / ppl; const int r = h - p * ppl; const int hy = r / A.PW; const int hx = r - hy * A.PW;
+            s_lut[h] = (p << 20) | (hy << 10) | hx;
+        }
+    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -123,9 +153,9 @@ __global__ void __launch_bounds__(CTA, 1) conv_halo_tc(const HaloArgs A, const u
             const TileCoord tc_ = decode_tile(A, tile);
             named_bar_sync(2, LOADERS);                          // everyone is done with the previous tile's table
             {   // global pixel index of every halo pixel (-1 = zero padding); identical for every K chunk
-                const int ppl = A.PH * A.PW;
                 for (int h = lt; h < A.NPX; h += LOADERS) {
-                    const int p = h / ppl; const int r = h - p * ppl; const int hy = r / A.PW; const int hx = r - hy * A.PW;
+                    const int l = s_lut[h];
+                    const int p = l >> 20, hy = (l >> 10) & 1023, hx = l & 1023;
                     const int iy = (tc_.a0 + A.plane[p].oy + hy) * A.istr + A.plane[p].qy;
                     const int ix = (tc_.b0 + A.plane[p].ox + hx) * A.istr + A.plane[p].qx;
                     s_pix[h] = (iy >= 0 && iy < A.Hin && ix >= 0 && ix < A.Win) ? (tc_.img * A.Hin + iy) * A.Win + ix : -1;
@@ -157,45 +187,64 @@ __global__ void __launch_bounds__(CTA, 1) conv_halo_tc(const HaloArgs A, const u
                 const size_t pstride = (size_t)S.pitch * esz;
                 mbar_wait(&a_empty[b], (uint32_t)(((cc >> 1) & 1) ^ 1));  // the MMAs that read this buffer are done
                 unsigned char* dst = sA + b * a_bytes + kc * A.a_lbo;
-                for (int hb = h0; hb < A.NPX; hb += HSTEP * U) {
-                    uint4 x[U][2];
-                    int pix[U];
+                auto finish = [&](float (&v)[8], int h) {       // BatchNorm + LeakyReLU, bf16, one 16-byte core row
+                    if (act) {
 #pragma unroll
-                    for (int u = 0; u < U; ++u) {
-                        const int h = hb + u * HSTEP;
-                        pix[u] = h < A.NPX ? s_pix[h] : -2;
-                        if (pix[u] >= 0) {
-                            const uint4* p = reinterpret_cast<const uint4*>(base + (size_t)pix[u] * pstride);
-                            x[u][0] = __ldg(p);
-                            if (!in_bf16) x[u][1] = __ldg(p + 1);
+                        for (int q = 0; q < 8; ++q) { const float z = fmaf(v[q], sc[q], sh[q]); v[q] = z > 0.f ? z : slope * z; }
+                    }
+                    __nv_bfloat162 p0 = __floats2bfloat162_rn(v[0], v[1]), p1 = __floats2bfloat162_rn(v[2], v[3]);
+                    __nv_bfloat162 p2 = __floats2bfloat162_rn(v[4], v[5]), p3 = __floats2bfloat162_rn(v[6], v[7]);
+                    uint4 o;
+                    o.x = *reinterpret_cast<uint32_t*>(&p0); o.y = *reinterpret_cast<uint32_t*>(&p1);
+                    o.z = *reinterpret_cast<uint32_t*>(&p2); o.w = *reinterpret_cast<uint32_t*>(&p3);
+                    *reinterpret_cast<uint4*>(dst + (size_t)h * 16) = o;
+                };
+                if (in_bf16) {
+                    constexpr int UB = 2 * U;                       // 8 x 16-byte loads in flight per thread
+                    for (int hb = h0; hb < A.NPX; hb += HSTEP * UB) {
+                        uint4 x[UB];
+                        int pix[UB];
+#pragma unroll
+                        for (int u = 0; u < UB; ++u) {
+                            const int h = hb + u * HSTEP;
+                            pix[u] = h < A.NPX ? s_pix[h] : -2;
+                            if (pix[u] >= 0) x[u] = __ldg(reinterpret_cast<const uint4*>(base + (size_t)pix[u] * pstride));
+                        }
+#pragma unroll
+                        for (int u = 0; u < UB; ++u) {
+                            if (pix[u] == -2) continue;
+                            const int h = hb + u * HSTEP;
+                            if (pix[u] < 0) { *reinterpret_cast<uint4*>(dst + (size_t)h * 16) = make_uint4(0u, 0u, 0u, 0u); continue; }
+                            float v[8];
+                            const __nv_bfloat162* hp = reinterpret_cast<const __nv_bfloat162*>(&x[u]);
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) { const float2 f = __bfloat1622float2(hp[q]); v[2 * q] = f.x; v[2 * q + 1] = f.y; }
+                            finish(v, h);
                         }
                     }
+                } else {
+                    for (int hb = h0; hb < A.NPX; hb += HSTEP * U) {
+                        uint4 x[U][2];
+                        int pix[U];
 #pragma unroll
-                    for (int u = 0; u < U; ++u) {
-                        if (pix[u] == -2) continue;
-                        uint4 o = make_uint4(0u, 0u, 0u, 0u);
-                        if (pix[u] >= 0) {
-                            float v[8];
-                            if (in_bf16) {
-                                const __nv_bfloat162* hp = reinterpret_cast<const __nv_bfloat162*>(&x[u][0]);
-#pragma unroll
-                                for (int q = 0; q < 4; ++q) { float2 f = __bfloat1622float2(hp[q]); v[2 * q] = f.x; v[2 * q + 1] = f.y; }
-                            } else {
-                                v[0] = __uint_as_float(x[u][0].x); v[1] = __uint_as_float(x[u][0].y);
-                                v[2] = __uint_as_float(x[u][0].z); v[3] = __uint_as_float(x[u][0].w);
-                                v[4] = __uint_as_float(x[u][1].x); v[5] = __uint_as_float(x[u][1].y);
-                                v[6] = __uint_as_float(x[u][1].z); v[7] = __uint_as_float(x[u][1].w);
+                        for (int u = 0; u < U; ++u) {
+                            const int h = hb + u * HSTEP;
+                            pix[u] = h < A.NPX ? s_pix[h] : -2;
+                            if (pix[u] >= 0) {
+                                const uint4* p = reinterpret_cast<const uint4*>(base + (size_t)pix[u] * pstride);
+                                x[u][0] = __ldg(p);
+                                x[u][1] = __ldg(p + 1);
                             }
-                            if (act) {
-#pragma unroll
-                                for (int q = 0; q < 8; ++q) { const float z = fmaf(v[q], sc[q], sh[q]); v[q] = z > 0.f ? z : slope * z; }
-                            }
-                            __nv_bfloat162 p0 = __floats2bfloat162_rn(v[0], v[1]), p1 = __floats2bfloat162_rn(v[2], v[3]);
-                            __nv_bfloat162 p2 = __floats2bfloat162_rn(v[4], v[5]), p3 = __floats2bfloat162_rn(v[6], v[7]);
-                            o.x = *reinterpret_cast<uint32_t*>(&p0); o.y = *reinterpret_cast<uint32_t*>(&p1);
-                            o.z = *reinterpret_cast<uint32_t*>(&p2); o.w = *reinterpret_cast<uint32_t*>(&p3);
                         }
-                        *reinterpret_cast<uint4*>(dst + (size_t)(hb + u * HSTEP) * 16) = o;
+#pragma unroll
+                        for (int u = 0; u < U; ++u) {
+                            if (pix[u] == -2) continue;
+                            const int h = hb + u * HSTEP;
+                            if (pix[u] < 0) { *reinterpret_cast<uint4*>(dst + (size_t)h * 16) = make_uint4(0u, 0u, 0u, 0u); continue; }
+                            float v[8] = {__uint_as_float(x[u][0].x), __uint_as_float(x[u][0].y), __uint_as_float(x[u][0].z), __uint_as_float(x[u][0].w),
+                                          __uint_as_float(x[u][1].x), __uint_as_float(x[u][1].y), __uint_as_float(x[u][1].z), __uint_as_float(x[u][1].w)};
+                            finish(v, h);
+                        }
                     }
                 }
                 fence_async_smem();                // generic-proxy writes -> visible to the tensor core (async proxy)
@@ -204,56 +253,69 @@ __global__ void __launch_bounds__(CTA, 1) conv_halo_tc(const HaloArgs A, const u
         }
     } else if (warp == 12) {
         // ------------------------------------------------------------------ weight stream (bulk TMA)
-        if (lane == 0) {
-            const int per_tile = A.nkt * A.ntap;
-            uint32_t wi = 0;
-            for (int tile = blockIdx.x; tile < A.total_tiles; tile += gridDim.x) {
-                const int tile_n = tile % A.ntn;
-                const unsigned char* wsrc = Wp + (size_t)tile_n * per_tile * B_BYTES;
-                for (int i = 0; i < per_tile; ++i, ++wi) {
-                    const int slot = wi % NB;
-                    mbar_wait(&w_empty[slot], (uint32_t)(((wi / NB) & 1) ^ 1));
+        // (the whole warp runs the loop so that its control values stay warp-uniform; one elected lane issues)
+        const bool leader = elect_one();
+        const int per_tile = A.nkt * A.ntap;
+        uint32_t wi = 0;
+        for (int tile = blockIdx.x; tile < A.total_tiles; tile += gridDim.x) {
+            const int tile_n = tile - fdiv(tile, A.ntn, A.inv_ntn) * A.ntn;
+            const unsigned char* wsrc = Wp + (size_t)tile_n * per_tile * B_BYTES;
+            for (int i = 0; i < per_tile; ++i, ++wi) {
+                const int slot = wi % NB;
+                mbar_wait(&w_empty[slot], (uint32_t)(((wi / NB) & 1) ^ 1));
+                if (leader) {
                     mbar_expect_tx(&w_full[slot], B_BYTES);
                     bulk_g2s(sB + slot * B_BYTES, wsrc + (size_t)i * B_BYTES, B_BYTES, &w_full[slot]);
                 }
+                __syncwarp();
             }
         }
-        __syncwarp();
     } else if (warp == 13) {
         // ------------------------------------------------------------------ MMA issue
-        if (lane == 0) {
-            const uint32_t idesc = make_idesc_bf16(TM, BN);
-            const uint32_t sbo = (uint32_t)A.PW * 16u;
-            uint32_t wi = 0, cc = 0, tl = 0;
-            for (int tile = blockIdx.x; tile < A.total_tiles; tile += gridDim.x, ++tl) {
-                const uint32_t ab = tl & 1;
-                mbar_wait(&acc_empty[ab], (uint32_t)(((tl >> 1) & 1) ^ 1));   // the epilogue has drained this accumulator set
+        // Converged warp; descriptors are built from warp-uniform 32-bit words: low = start address >> 4 | LBO >> 4 << 16
+        // (a tap / K step only adds to the start-address field), high = SBO >> 4 | version 1 << 14.
+        const bool leader = elect_one();
+        const uint32_t idesc = make_idesc_bf16(TM, BN);
+        const uint32_t a_hi = (((uint32_t)A.PW * 16u) >> 4) | (1u << 14);
+        const uint32_t b_hi = (128u >> 4) | (1u << 14);
+        const uint32_t a_lo_k = (((uint32_t)A.a_lbo >> 4) & 0x3fffu) << 16;
+        const uint32_t b_lo_k = ((uint32_t)((BN / 8) * 128) >> 4) << 16;
+        const uint32_t a_step = (uint32_t)(2 * A.a_lbo) >> 4;              // one K=16 step = 2 K cores
+        constexpr uint32_t b_step = (uint32_t)(2 * (BN / 8) * 128) >> 4;
+        const uint32_t sA16 = smem_u32(sA) >> 4, sB16 = smem_u32(sB) >> 4;
+        uint32_t wi = 0, cc = 0, tl = 0;
+        for (int tile = blockIdx.x; tile < A.total_tiles; tile += gridDim.x, ++tl) {
+            const uint32_t ab = tl & 1;
+            mbar_wait(&acc_empty[ab], (uint32_t)(((tl >> 1) & 1) ^ 1));   // the epilogue has drained this accumulator set
+            tc_fence_after();
+            const uint32_t acc0 = tmem_d + ab * (uint32_t)A.acc_cols;
+            for (int c = 0; c < A.nkt; ++c, ++cc) {
+                const uint32_t b = cc & 1;
+                mbar_wait(&a_full[b], (uint32_t)((cc >> 1) & 1));
                 tc_fence_after();
-                const uint32_t acc0 = tmem_d + ab * (uint32_t)A.acc_cols;
-                for (int c = 0; c < A.nkt; ++c, ++cc) {
-                    const int b = cc & 1;
-                    mbar_wait(&a_full[b], (uint32_t)((cc >> 1) & 1));
-                    tc_fence_after();
-                    const uint32_t abase = smem_u32(sA + b * a_bytes);
-                    for (int t = 0; t < A.ntap; ++t, ++wi) {
-                        const int slot = wi % NB;
-                        mbar_wait(&w_full[slot], (uint32_t)((wi / NB) & 1));
-                        const uint32_t bbase = smem_u32(sB + slot * B_BYTES);
-                        const uint32_t acol = acc0 + (uint32_t)(A.tap[t].cls * BN);
+                const uint32_t a_lo_buf = a_lo_k | (sA16 + b * ((uint32_t)a_bytes >> 4));
+                for (int t = 0; t < A.ntap; ++t, ++wi) {
+                    const uint32_t slot = wi % NB;
+                    mbar_wait(&w_full[slot], (uint32_t)((wi / NB) & 1));
+                    const uint32_t a_lo = a_lo_buf + ((uint32_t)A.tap[t].a_off >> 4);
+                    const uint32_t b_lo = b_lo_k | (sB16 + slot * (uint32_t)(B_BYTES >> 4));
+                    const uint32_t acol = acc0 + (uint32_t)(A.tap[t].cls * BN);
+                    const uint32_t fresh = (c == 0 && A.tap[t].first) ? 1u : 0u;
+                    if (leader) {
 #pragma unroll
-                        for (int j = 0; j < TK / 16; ++j) {
-                            const uint64_t ad = make_smem_desc(abase + (uint32_t)A.tap[t].a_off + (uint32_t)(j * 2 * A.a_lbo), (uint32_t)A.a_lbo, sbo);
-                            const uint64_t bd = make_smem_desc(bbase + j * 2 * (BN / 8) * 128, (BN / 8) * 128, 128);
-                            umma_bf16(acol, ad, bd, idesc, (c > 0 || !A.tap[t].first || j > 0) ? 1u : 0u);
-                        }
+                        for (int j = 0; j < TK / 16; ++j)
+                            umma_bf16(acol, pack_desc(a_lo + j * a_step, a_hi), pack_desc(b_lo + j * b_step, b_hi), idesc,
+                                      (j > 0 || !fresh) ? 1u : 0u);
                         umma_commit(&w_empty[slot]);   // frees the weight slot once these MMAs have read it
                     }
-                    umma_commit(&a_empty[b]);          // frees the halo buffer
+                    __syncwarp();
                 }
-                umma_commit(&acc_full[ab]);            // accumulator set complete
+                if (leader) umma_commit(&a_empty[b]);  // frees the halo buffer
+                __syncwarp();
             }
+            if (leader) umma_commit(&acc_full[ab]);    // accumulator set complete
+            __syncwarp();
         }
-        __syncwarp();
     } else {
         // ------------------------------------------------------------------ epilogue (warps 0-3 = TMEM lane quarters)
         float* Tt = reinterpret_cast<float*>(sEpi) + warp * (32 * 33);         // per-warp [32 rows][33]
@@ -277,7 +339,7 @@ __global__ void __launch_bounds__(CTA, 1) conv_halo_tc(const HaloArgs A, const u
                 if (A.bias || A.tanh_out) {
 #pragma unroll
                     for (int j = 0; j < 32; ++j) {
-                        if (co0 + j < A.Cout) { const float y = v[j] + (A.bias ? __ldg(A.bias + co0 + j) : 0.f); v[j] = A.tanh_out ? tanhf(y) : y; }
+                        if (co0 + j < A.Cout) { const float y = v[j] + (A.bias ? __ldg(A.bias + co0 + j) : 0.f); v[j] = A.tanh_out ? fast_tanh(y) : y; }
                     }
                 }
                 if (A.out_bf16) {          // statistics describe what the consumer will read: the rounded values
@@ -380,6 +442,9 @@ static bool build_halo_args(const rp_conv_desc* d, HaloArgs* H, int bn, int tk, 
     H->nty = (Hb + TH - 1) / TH; H->ntx = (Wb + TW - 1) / TW; H->tiles_m = A.gsz * H->nty * H->ntx;
     H->ntn = (A.Cout + bn - 1) / bn;
     H->total_tiles = A.G * H->tiles_m * H->ntn;
+    if (H->total_tiles >= (1 << 24)) return false;
+    H->inv_ntn = 1.f / (float)H->ntn; H->inv_tiles_m = 1.f / (float)H->tiles_m;
+    H->inv_tiles_img = 1.f / (float)(H->nty * H->ntx); H->inv_ntx = 1.f / (float)H->ntx;
     const int s = A.istr;
     H->nplane = s * s;
     if (H->nplane > 4) return false;
@@ -494,7 +559,7 @@ int rp_conv_layer_halo(const rp_conv_desc* d, const void* w_packed, int bn, int 
 #define RP_HALO_CASE(BN_, TK_, NB_) if (bn == BN_ && tk == TK_) return halo::launch_halo<BN_, TK_, NB_>(H, w_packed, stream);
     RP_HALO_CASE(32, 64, 16) RP_HALO_CASE(64, 64, 12) RP_HALO_CASE(128, 64, 6)
     RP_HALO_CASE(32, 32, 16) RP_HALO_CASE(64, 32, 16) RP_HALO_CASE(128, 32, 8)
-    RP_HALO_CASE(32, 16, 16)
+    RP_HALO_CASE(32, 16, 16) RP_HALO_CASE(256, 32, 4)
 #undef RP_HALO_CASE
     return RP_ERR_UNSUPPORTED;
 }

@@ -200,7 +200,9 @@ class ScnetEngine(object):
             if any(a.C % 32 for a in srcs):
                 tk = 16                          # the bf16-split stem (conv1*, 16 channels per group)
             cap = 64 if (transposed and s == 2) else 128                  # 4 accumulators x bn TMEM columns
-            bn_tile = next((b for b in (128, 64, 32) if b <= cap and out.C % b == 0), 32)   # 32: Cout zero-padded (heads)
+            if s == 2 and not transposed:
+                cap = 256                                                 # one accumulator set of 256 columns (x2 sets = all of TMEM)
+            bn_tile = next((b for b in (256, 128, 64, 32) if b <= cap and out.C % b == 0), 32)   # 32: Cout zero-padded (heads)
             ntap = ctypes.c_int(0)
             widx = (ctypes.c_int * 16)()
             if bn_tile and self.lib.rp_conv_halo_plan(ctypes.byref(d), bn_tile, tk, self.halo_flags, ctypes.byref(nparts),

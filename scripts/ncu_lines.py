@@ -60,12 +60,14 @@ def main():
     ksub = sys.argv[3] if len(sys.argv) > 3 and not sys.argv[3].startswith("--") else "rp_solve_kernel"
     top = int(sys.argv[sys.argv.index("--top") + 1]) if "--top" in sys.argv else 40
     srcfile = None
-    txt = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], stdout=subprocess.PIPE, text=True).stdout
+    sel = ["--launch-skip", sys.argv[sys.argv.index("--skip") + 1], "--launch-count", "1"] if "--skip" in sys.argv else []
+    txt = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"] + sel, stdout=subprocess.PIPE, text=True).stdout
     rows = list(csv.reader(io.StringIO(txt)))
     hdr_i = next(i for i, r in enumerate(rows) if r and r[0] == "Address")
     hdr = rows[hdr_i]
     col = {h: i for i, h in enumerate(hdr)}
-    body = [r for r in rows[hdr_i + 1:] if len(r) == len(hdr)]
+    end = next((i for i in range(hdr_i + 1, len(rows)) if rows[i] and rows[i][0] == "Kernel Name"), len(rows))   # first kernel only
+    body = [r for r in rows[hdr_i + 1:end] if len(r) == len(hdr)]
     base = int(body[0][0], 16)
     lines = sass_lines(so, ksub)
     agg = defaultdict(lambda: defaultdict(float))
