@@ -469,7 +469,7 @@ __global__ void interpolate_kernel(const float* __restrict__ feat, int C, int H,
 // little work per 128-pixel tile to amortise a tensor-core CTA's setup, so: CUDA cores, PIX pixels per thread, the
 // zero-padded [K][CP] weights broadcast from shared memory, producer BatchNorm + LeakyReLU applied while loading
 // (float32 or bfloat16 storage).
-template <int CP, int PIX>
+template <int CP, int PIX, int CH>      // CP: padded Cout, PIX: pixels per thread, CH: channels loaded per step (8 or 32)
 __global__ void __launch_bounds__(128) conv1x1_head_kernel(const ConvArgs A) {
     __shared__ __align__(16) float Ws[128 * CP];
     __shared__ float s_sc[128], s_sh[128];
@@ -488,6 +488,7 @@ __global__ void __launch_bounds__(128) conv1x1_head_kernel(const ConvArgs A) {
     }
     __syncthreads();
     const int npx = A.gsz * A.Hout * A.Wout;
+    constexpr int NU = CH / 8;                                   // 8-channel units per step
     int px[PIX]; bool val[PIX];
     float acc[PIX][CP];
 #pragma unroll
@@ -501,39 +502,59 @@ __global__ void __launch_bounds__(128) conv1x1_head_kernel(const ConvArgs A) {
     for (int si = 0; si < A.nsrc; ++si) {
         const rp_conv_src& S = A.src[si];
         const bool h16 = S.dtype == 1;
-        for (int c0 = 0; c0 < S.C; c0 += 8) {
-            float v[PIX][8];
+        for (int c0 = 0; c0 < S.C; c0 += CH) {
+            uint4 raw[PIX][NU][2];                               // every load of the step is issued before any is used
 #pragma unroll
             for (int u = 0; u < PIX; ++u) {
+                if (!val[u]) continue;
+                const size_t e = ((size_t)g * npx + px[u]) * S.pitch + S.ch_off + c0;
 #pragma unroll
-                for (int q = 0; q < 8; ++q) v[u][q] = 0.f;
-                if (val[u]) {
-                    const size_t e = ((size_t)g * npx + px[u]) * S.pitch + S.ch_off + c0;
+                for (int w = 0; w < NU; ++w) {
                     if (h16) {
-                        const uint4 x = *reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(S.ptr) + e);
-                        const __nv_bfloat162* hp = reinterpret_cast<const __nv_bfloat162*>(&x);
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) { const float2 f = __bfloat1622float2(hp[q]); v[u][2 * q] = f.x; v[u][2 * q + 1] = f.y; }
+                        raw[u][w][0] = *reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(S.ptr) + e + 8 * w);
                     } else {
-                        const float4 x0 = *reinterpret_cast<const float4*>(S.ptr + e), x1 = *reinterpret_cast<const float4*>(S.ptr + e + 4);
-                        v[u][0] = x0.x; v[u][1] = x0.y; v[u][2] = x0.z; v[u][3] = x0.w; v[u][4] = x1.x; v[u][5] = x1.y; v[u][6] = x1.z; v[u][7] = x1.w;
-                    }
-                    if (S.act) {
-#pragma unroll
-                        for (int q = 0; q < 8; ++q) { const float z = fmaf(v[u][q], s_sc[cb + c0 + q], s_sh[cb + c0 + q]); v[u][q] = z > 0.f ? z : S.slope * z; }
+                        raw[u][w][0] = *reinterpret_cast<const uint4*>(S.ptr + e + 8 * w);
+                        raw[u][w][1] = *reinterpret_cast<const uint4*>(S.ptr + e + 8 * w + 4);
                     }
                 }
             }
 #pragma unroll
-            for (int q = 0; q < 8; ++q) {
-                const float* w = Ws + (cb + c0 + q) * CP;
+            for (int w = 0; w < NU; ++w) {
+                float v[PIX][8];
 #pragma unroll
-                for (int j = 0; j < CP; j += 4) {
-                    const float4 w4 = *reinterpret_cast<const float4*>(w + j);
+                for (int u = 0; u < PIX; ++u) {
 #pragma unroll
-                    for (int u = 0; u < PIX; ++u) {
-                        acc[u][j] = fmaf(v[u][q], w4.x, acc[u][j]); acc[u][j + 1] = fmaf(v[u][q], w4.y, acc[u][j + 1]);
-                        acc[u][j + 2] = fmaf(v[u][q], w4.z, acc[u][j + 2]); acc[u][j + 3] = fmaf(v[u][q], w4.w, acc[u][j + 3]);
+                    for (int q = 0; q < 8; ++q) v[u][q] = 0.f;
+                    if (!val[u]) continue;
+                    if (h16) {
+                        const __nv_bfloat162* hp = reinterpret_cast<const __nv_bfloat162*>(&raw[u][w][0]);
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) { const float2 f = __bfloat1622float2(hp[q]); v[u][2 * q] = f.x; v[u][2 * q + 1] = f.y; }
+                    } else {
+                        v[u][0] = __uint_as_float(raw[u][w][0].x); v[u][1] = __uint_as_float(raw[u][w][0].y);
+                        v[u][2] = __uint_as_float(raw[u][w][0].z); v[u][3] = __uint_as_float(raw[u][w][0].w);
+                        v[u][4] = __uint_as_float(raw[u][w][1].x); v[u][5] = __uint_as_float(raw[u][w][1].y);
+                        v[u][6] = __uint_as_float(raw[u][w][1].z); v[u][7] = __uint_as_float(raw[u][w][1].w);
+                    }
+                    if (S.act) {
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) {
+                            const float z = fmaf(v[u][q], s_sc[cb + c0 + 8 * w + q], s_sh[cb + c0 + 8 * w + q]);
+                            v[u][q] = z > 0.f ? z : S.slope * z;
+                        }
+                    }
+                }
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const float* wr = Ws + (cb + c0 + 8 * w + q) * CP;
+#pragma unroll
+                    for (int j = 0; j < CP; j += 4) {
+                        const float4 w4 = *reinterpret_cast<const float4*>(wr + j);
+#pragma unroll
+                        for (int u = 0; u < PIX; ++u) {
+                            acc[u][j] = fmaf(v[u][q], w4.x, acc[u][j]); acc[u][j + 1] = fmaf(v[u][q], w4.y, acc[u][j + 1]);
+                            acc[u][j + 2] = fmaf(v[u][q], w4.z, acc[u][j + 2]); acc[u][j + 3] = fmaf(v[u][q], w4.w, acc[u][j + 3]);
+                        }
                     }
                 }
             }
@@ -599,10 +620,13 @@ int rp_conv_layer(const rp_conv_desc* d, void* stream_) {
     }
     if (head_eligible(d)) {
         const int npx = A.gsz * A.Hout * A.Wout;
-        if (A.Cout <= 4) { dim3 grid((npx + 511) / 512, A.G); conv1x1_head_kernel<4, 4><<<grid, 128, 0, stream>>>(A); }
-        else if (A.Cout <= 16) { dim3 grid((npx + 255) / 256, A.G); conv1x1_head_kernel<16, 2><<<grid, 128, 0, stream>>>(A); }
-        else if (A.Cout <= 24) { dim3 grid((npx + 255) / 256, A.G); conv1x1_head_kernel<24, 2><<<grid, 128, 0, stream>>>(A); }
-        else { dim3 grid((npx + 255) / 256, A.G); conv1x1_head_kernel<32, 2><<<grid, 128, 0, stream>>>(A); }
+        bool c32 = true;
+        for (int i = 0; i < d->nsrc; ++i) c32 = c32 && (d->src[i].C % 32 == 0);
+        if (A.Cout <= 4 && c32) { dim3 grid((npx + 255) / 256, A.G); conv1x1_head_kernel<4, 2, 32><<<grid, 128, 0, stream>>>(A); }
+        else if (A.Cout <= 4) { dim3 grid((npx + 511) / 512, A.G); conv1x1_head_kernel<4, 4, 8><<<grid, 128, 0, stream>>>(A); }
+        else if (A.Cout <= 16) { dim3 grid((npx + 255) / 256, A.G); conv1x1_head_kernel<16, 2, 8><<<grid, 128, 0, stream>>>(A); }
+        else if (A.Cout <= 24) { dim3 grid((npx + 255) / 256, A.G); conv1x1_head_kernel<24, 2, 8><<<grid, 128, 0, stream>>>(A); }
+        else { dim3 grid((npx + 255) / 256, A.G); conv1x1_head_kernel<32, 2, 8><<<grid, 128, 0, stream>>>(A); }
         ++g_conv_launches;
         return cudaGetLastError() == cudaSuccess ? RP_OK : RP_ERR_CUDA;
     }

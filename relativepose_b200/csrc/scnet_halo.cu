@@ -52,6 +52,8 @@ struct HaloArgs {
     HTap tap[MAXT];
     int nkt, nkt0;                         // K chunks in total / in source 0
     int acc_cols, tmem_cols;               // TMEM columns of one accumulator set (nclass x BN) / allocated (2 sets)
+    int ng;                                // loader groups = halo buffers (2 or 4): group i fills buffer i with chunks i, i+ng, ...
+    float inv_nkt;
     void* out; int out_pitch, out_ch_off, out_bf16;
     float* psum; float* psq;
     const float* bias; int tanh_out;
@@ -110,21 +112,20 @@ __global__ void __launch_bounds__(CTA, 1) conv_halo_tc(const HaloArgs A, const u
     extern __shared__ __align__(128) unsigned char smem[];
     constexpr int KC = TK / 8;
     constexpr int B_BYTES = BN * TK * 2;
-    constexpr int HSTEP = LOADERS / KC;            // halo pixels covered by one pass of the loader threads
     constexpr int U = 4;                           // loads in flight per loader thread
-    __shared__ __align__(8) uint64_t a_full[2], a_empty[2], w_full[NB], w_empty[NB], acc_full[2], acc_empty[2];
+    __shared__ __align__(8) uint64_t a_full[4], a_empty[4], w_full[NB], w_empty[NB], acc_full[2], acc_empty[2];
     __shared__ uint32_t tmem_slot;
-    __shared__ int s_pix[MAXNPX];
+    __shared__ int s_pix[2 * MAXNPX];              // one pixel table per loader group (ng x NPX <= 2 x MAXNPX)
     __shared__ int s_lut[MAXNPX];                  // halo pixel -> (plane << 20 | row << 10 | column), tile independent
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int a_bytes = ((KC * A.a_lbo + 127) / 128) * 128;
     unsigned char* sEpi = smem;                                  // [EPI_SMEM] epilogue scratch (never aliased)
-    unsigned char* sA = smem + EPI_SMEM;                         // 2 halo buffers
-    unsigned char* sB = sA + 2 * a_bytes;                        // NB weight slots
+    unsigned char* sA = smem + EPI_SMEM;                         // ng halo buffers
+    unsigned char* sB = sA + A.ng * a_bytes;                     // NB weight slots
 
     if (tid == 0) {
-        mbar_init(&a_full[0], LOADERS); mbar_init(&a_full[1], LOADERS);
-        mbar_init(&a_empty[0], 1); mbar_init(&a_empty[1], 1);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { mbar_init(&a_full[i], (uint32_t)(LOADERS / A.ng)); mbar_init(&a_empty[i], 1); }
 #pragma unroll
         for (int i = 0; i < NB; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
         mbar_init(&acc_full[0], 1); mbar_init(&acc_full[1], 1);
@@ -146,25 +147,37 @@ __global__ void __launch_bounds__(CTA, 1) conv_halo_tc(const HaloArgs A, const u
 
     if (warp >= 4 && warp < 12) {
         // ------------------------------------------------------------------ halo loaders
-        const int lt = tid - EPI;
+        // The 256 loader threads form ng groups; group gi owns halo buffer gi and fills it with the chunks gi, gi + ng, ...
+        // of this CTA's (tile, K chunk) sequence, so ng gathers (global-load round trips) are in flight at once.
+        const int GT = LOADERS / A.ng;
+        const int gi = (tid - EPI) / GT, lt = (tid - EPI) - gi * GT;
         const int kc = lt % KC, h0 = lt / KC;
-        uint32_t cc = 0;                                         // chunk counter across tiles
-        for (int tile = blockIdx.x; tile < A.total_tiles; tile += gridDim.x) {
-            const TileCoord tc_ = decode_tile(A, tile);
-            named_bar_sync(2, LOADERS);                          // everyone is done with the previous tile's table
-            {   // global pixel index of every halo pixel (-1 = zero padding); identical for every K chunk
-                for (int h = lt; h < A.NPX; h += LOADERS) {
+        const int HSTEP = GT / KC;                               // halo pixels covered by one pass of a group
+        int* my_pix = s_pix + gi * A.NPX;
+        const int my_tiles = (A.total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+        const int total_chunks = my_tiles * A.nkt;
+        int cur_seq = -1;
+        TileCoord tc_ = decode_tile(A, blockIdx.x);
+        for (int cc = gi; cc < total_chunks; cc += A.ng) {
+            const int tseq = fdiv(cc, A.nkt, A.inv_nkt);
+            const int c = cc - tseq * A.nkt;
+            if (tseq != cur_seq) {
+                cur_seq = tseq;
+                tc_ = decode_tile(A, (int)blockIdx.x + tseq * (int)gridDim.x);
+                named_bar_sync(2 + gi, GT);                      // the group is done with its previous table
+                for (int h = lt; h < A.NPX; h += GT) {           // global pixel index of every halo pixel (-1 = zero padding)
                     const int l = s_lut[h];
                     const int p = l >> 20, hy = (l >> 10) & 1023, hx = l & 1023;
                     const int iy = (tc_.a0 + A.plane[p].oy + hy) * A.istr + A.plane[p].qy;
                     const int ix = (tc_.b0 + A.plane[p].ox + hx) * A.istr + A.plane[p].qx;
-                    s_pix[h] = (iy >= 0 && iy < A.Hin && ix >= 0 && ix < A.Win) ? (tc_.img * A.Hin + iy) * A.Win + ix : -1;
+                    my_pix[h] = (iy >= 0 && iy < A.Hin && ix >= 0 && ix < A.Win) ? (tc_.img * A.Hin + iy) * A.Win + ix : -1;
                 }
+                named_bar_sync(2 + gi, GT);
             }
-            named_bar_sync(2, LOADERS);
-            const int g = tc_.g;
-            for (int c = 0; c < A.nkt; ++c, ++cc) {
-                const int b = cc & 1;
+            {
+                const int g = tc_.g;
+                const int b = gi;
+                const uint32_t use = (uint32_t)(cc / A.ng);      // how often this buffer has been filled before
                 const int si = c < A.nkt0 ? 0 : 1;
                 const rp_conv_src& S = A.src[si];
                 const int ch = (c - (si ? A.nkt0 : 0)) * TK + kc * 8;
@@ -185,7 +198,7 @@ __global__ void __launch_bounds__(CTA, 1) conv_halo_tc(const HaloArgs A, const u
                 const size_t esz = in_bf16 ? 2 : 4;
                 const unsigned char* base = reinterpret_cast<const unsigned char*>(S.ptr) + (size_t)(S.ch_off + ch) * esz;
                 const size_t pstride = (size_t)S.pitch * esz;
-                mbar_wait(&a_empty[b], (uint32_t)(((cc >> 1) & 1) ^ 1));  // the MMAs that read this buffer are done
+                mbar_wait(&a_empty[b], (use & 1u) ^ 1u);         // the MMAs that read this buffer are done
                 unsigned char* dst = sA + b * a_bytes + kc * A.a_lbo;
                 auto finish = [&](float (&v)[8], int h) {       // BatchNorm + LeakyReLU, bf16, one 16-byte core row
                     if (act) {
@@ -207,7 +220,7 @@ __global__ void __launch_bounds__(CTA, 1) conv_halo_tc(const HaloArgs A, const u
 #pragma unroll
                         for (int u = 0; u < UB; ++u) {
                             const int h = hb + u * HSTEP;
-                            pix[u] = h < A.NPX ? s_pix[h] : -2;
+                            pix[u] = h < A.NPX ? my_pix[h] : -2;
                             if (pix[u] >= 0) x[u] = __ldg(reinterpret_cast<const uint4*>(base + (size_t)pix[u] * pstride));
                         }
 #pragma unroll
@@ -229,7 +242,7 @@ __global__ void __launch_bounds__(CTA, 1) conv_halo_tc(const HaloArgs A, const u
 #pragma unroll
                         for (int u = 0; u < U; ++u) {
                             const int h = hb + u * HSTEP;
-                            pix[u] = h < A.NPX ? s_pix[h] : -2;
+                            pix[u] = h < A.NPX ? my_pix[h] : -2;
                             if (pix[u] >= 0) {
                                 const uint4* p = reinterpret_cast<const uint4*>(base + (size_t)pix[u] * pstride);
                                 x[u][0] = __ldg(p);
@@ -290,8 +303,8 @@ __global__ void __launch_bounds__(CTA, 1) conv_halo_tc(const HaloArgs A, const u
             tc_fence_after();
             const uint32_t acc0 = tmem_d + ab * (uint32_t)A.acc_cols;
             for (int c = 0; c < A.nkt; ++c, ++cc) {
-                const uint32_t b = cc & 1;
-                mbar_wait(&a_full[b], (uint32_t)((cc >> 1) & 1));
+                const uint32_t b = cc % (uint32_t)A.ng;
+                mbar_wait(&a_full[b], (cc / (uint32_t)A.ng) & 1u);
                 tc_fence_after();
                 const uint32_t a_lo_buf = a_lo_k | (sA16 + b * ((uint32_t)a_bytes >> 4));
                 for (int t = 0; t < A.ntap; ++t, ++wi) {
@@ -391,7 +404,7 @@ __global__ void __launch_bounds__(CTA, 1) conv_halo_tc(const HaloArgs A, const u
             tc_fence_before();
             mbar_arrive(&acc_empty[ab]);               // this thread's tcgen05.ld of the set have completed (wait::ld)
             if (A.psum) {
-                named_bar_sync(3, EPI);
+                named_bar_sync(6, EPI);
                 for (int i = tid; i < nunit * 32; i += EPI) {
                     const int u = i >> 5, col = i & 31;
                     const int cls = u / (BN / 32), c0 = (u - cls * (BN / 32)) * 32;
@@ -405,7 +418,7 @@ __global__ void __launch_bounds__(CTA, 1) conv_halo_tc(const HaloArgs A, const u
                         A.psq[prow * A.Cout + co] = s2;
                     }
                 }
-                named_bar_sync(3, EPI);                // `red` is free for the next tile
+                named_bar_sync(6, EPI);                // `red` is free for the next tile
             }
         }
     }
@@ -489,6 +502,8 @@ static bool build_halo_args(const rp_conv_desc* d, HaloArgs* H, int bn, int tk, 
     H->nkt = 0;
     for (int i = 0; i < A.nsrc; ++i) H->nkt += A.src[i].C / tk;
     H->nkt0 = A.src[0].C / tk;
+    H->inv_nkt = 1.f / (float)H->nkt;
+    H->ng = 2;
     H->acc_cols = A.nclass * bn;
     int cols = 32;
     while (cols < 2 * H->acc_cols) cols <<= 1;                 // two accumulator sets (epilogue of tile i-1 || MMAs of tile i)
@@ -503,10 +518,14 @@ static bool build_halo_args(const rp_conv_desc* d, HaloArgs* H, int bn, int tk, 
 }
 
 template <int BN, int TK, int NB>
-static int launch_halo(const HaloArgs& H, const void* wp, cudaStream_t stream) {
+static int launch_halo(const HaloArgs& H0, const void* wp, cudaStream_t stream) {
     constexpr int KC = TK / 8;
+    HaloArgs H = H0;
     const size_t a_bytes = (size_t)((KC * H.a_lbo + 127) / 128) * 128;
-    const size_t smem = (size_t)EPI_SMEM + 2 * a_bytes + (size_t)NB * BN * TK * 2;
+    const size_t fixed = (size_t)EPI_SMEM + (size_t)NB * BN * TK * 2;
+    // four gathers in flight when the halo is small (stem, 3x3 / transposed layers, 1x1 heads), two otherwise
+    H.ng = (H.NPX * 4 <= 2 * MAXNPX && fixed + 4 * a_bytes <= 220 * 1024) ? 4 : 2;
+    const size_t smem = fixed + H.ng * a_bytes;
     if (smem > 220 * 1024) return RP_ERR_UNSUPPORTED;
     auto kern = conv_halo_tc<BN, TK, NB>;
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { cudaGetLastError(); return RP_ERR_CUDA; }

@@ -189,8 +189,9 @@ class ScnetEngine(object):
         d.bias = bias.data_ptr() if bias is not None else None
         d.tanh_out = int(tanh)
         use_tc = self.mode == 'tc' and all(a.C % 16 == 0 for a in srcs)
-        if k == 1 and not bn and out.C <= 32 and sum(a.C for a in srcs) <= 128 and not self.halo:
-            use_tc = False                   # 1x1 output heads without the halo kernel: CUDA-core kernel inside rp_conv_layer
+        if k == 1 and not bn and sum(a.C for a in srcs) <= 128 and (out.C <= 4 or (out.C <= 32 and not self.halo)):
+            use_tc = False                   # 3-channel heads are HBM-bound: CUDA-core kernel inside rp_conv_layer (also the
+                                             # fallback for the wider heads when the halo kernel is off)
         use_halo = False
         nparts = ctypes.c_int(0)
         if use_tc and self.halo and ((bn and k in (3, 4)) or (k == 1 and s == 1)) and \
