@@ -54,6 +54,7 @@ struct HaloArgs {
     int acc_cols, tmem_cols;               // TMEM columns of one accumulator set (nclass x BN) / allocated (2 sets)
     int ng;                                // loader groups = halo buffers (2 or 4): group i fills buffer i with chunks i, i+ng, ...
     float inv_nkt;
+    int w_resident;                        // all weight blocks of a tile fit in the ring: loaded once per CTA, never freed
     void* out; int out_pitch, out_ch_off, out_bf16;
     float* psum; float* psq;
     const float* bias; int tanh_out;
@@ -270,17 +271,28 @@ __global__ void __launch_bounds__(CTA, 1) conv_halo_tc(const HaloArgs A, const u
         const bool leader = elect_one();
         const int per_tile = A.nkt * A.ntap;
         uint32_t wi = 0;
-        for (int tile = blockIdx.x; tile < A.total_tiles; tile += gridDim.x) {
-            const int tile_n = tile - fdiv(tile, A.ntn, A.inv_ntn) * A.ntn;
-            const unsigned char* wsrc = Wp + (size_t)tile_n * per_tile * B_BYTES;
-            for (int i = 0; i < per_tile; ++i, ++wi) {
-                const int slot = wi % NB;
-                mbar_wait(&w_empty[slot], (uint32_t)(((wi / NB) & 1) ^ 1));
-                if (leader) {
-                    mbar_expect_tx(&w_full[slot], B_BYTES);
-                    bulk_g2s(sB + slot * B_BYTES, wsrc + (size_t)i * B_BYTES, B_BYTES, &w_full[slot]);
+        if (A.w_resident) {
+            // small layers (stem, heads, 32/64-channel 4x4 layers with one n-tile): the whole weight set sits in the ring
+            if (leader) {
+                for (int i = 0; i < per_tile; ++i) {
+                    mbar_expect_tx(&w_full[i], B_BYTES);
+                    bulk_g2s(sB + i * B_BYTES, Wp + (size_t)i * B_BYTES, B_BYTES, &w_full[i]);
                 }
-                __syncwarp();
+            }
+            __syncwarp();
+        } else {
+            for (int tile = blockIdx.x; tile < A.total_tiles; tile += gridDim.x) {
+                const int tile_n = tile - fdiv(tile, A.ntn, A.inv_ntn) * A.ntn;
+                const unsigned char* wsrc = Wp + (size_t)tile_n * per_tile * B_BYTES;
+                for (int i = 0; i < per_tile; ++i, ++wi) {
+                    const int slot = wi % NB;
+                    mbar_wait(&w_empty[slot], (uint32_t)(((wi / NB) & 1) ^ 1));
+                    if (leader) {
+                        mbar_expect_tx(&w_full[slot], B_BYTES);
+                        bulk_g2s(sB + slot * B_BYTES, wsrc + (size_t)i * B_BYTES, B_BYTES, &w_full[slot]);
+                    }
+                    __syncwarp();
+                }
             }
         }
     } else if (warp == 13) {
@@ -296,32 +308,65 @@ __global__ void __launch_bounds__(CTA, 1) conv_halo_tc(const HaloArgs A, const u
         const uint32_t a_step = (uint32_t)(2 * A.a_lbo) >> 4;              // one K=16 step = 2 K cores
         constexpr uint32_t b_step = (uint32_t)(2 * (BN / 8) * 128) >> 4;
         const uint32_t sA16 = smem_u32(sA) >> 4, sB16 = smem_u32(sB) >> 4;
+        // per-tap constants in registers (the tap loops below are fully unrolled; taps beyond ntap are skipped)
+        uint32_t tap_a[MAXT], tap_col[MAXT];
+        uint32_t first_mask = 0;
+#pragma unroll
+        for (int t = 0; t < MAXT; ++t) {
+            tap_a[t] = t < A.ntap ? ((uint32_t)A.tap[t].a_off >> 4) : 0u;
+            tap_col[t] = t < A.ntap ? (uint32_t)(A.tap[t].cls * BN) : 0u;
+            if (t < A.ntap && A.tap[t].first) first_mask |= 1u << t;
+        }
         uint32_t wi = 0, cc = 0, tl = 0;
+        bool w_ready = false;
         for (int tile = blockIdx.x; tile < A.total_tiles; tile += gridDim.x, ++tl) {
             const uint32_t ab = tl & 1;
             mbar_wait(&acc_empty[ab], (uint32_t)(((tl >> 1) & 1) ^ 1));   // the epilogue has drained this accumulator set
             tc_fence_after();
             const uint32_t acc0 = tmem_d + ab * (uint32_t)A.acc_cols;
+            if (A.w_resident && !w_ready) {                               // resident weights: wait for them once
+                for (int i = 0; i < A.nkt * A.ntap; ++i) mbar_wait(&w_full[i], 0u);
+                w_ready = true;
+            }
             for (int c = 0; c < A.nkt; ++c, ++cc) {
                 const uint32_t b = cc % (uint32_t)A.ng;
                 mbar_wait(&a_full[b], (cc / (uint32_t)A.ng) & 1u);
                 tc_fence_after();
                 const uint32_t a_lo_buf = a_lo_k | (sA16 + b * ((uint32_t)a_bytes >> 4));
-                for (int t = 0; t < A.ntap; ++t, ++wi) {
-                    const uint32_t slot = wi % NB;
-                    mbar_wait(&w_full[slot], (uint32_t)((wi / NB) & 1));
-                    const uint32_t a_lo = a_lo_buf + ((uint32_t)A.tap[t].a_off >> 4);
-                    const uint32_t b_lo = b_lo_k | (sB16 + slot * (uint32_t)(B_BYTES >> 4));
-                    const uint32_t acol = acc0 + (uint32_t)(A.tap[t].cls * BN);
-                    const uint32_t fresh = (c == 0 && A.tap[t].first) ? 1u : 0u;
-                    if (leader) {
+                const uint32_t fresh_mask = c == 0 ? first_mask : 0u;
+                if (A.w_resident) {
+                    const uint32_t b_lo0 = b_lo_k | (sB16 + (uint32_t)(c * A.ntap) * (uint32_t)(B_BYTES >> 4));
 #pragma unroll
-                        for (int j = 0; j < TK / 16; ++j)
-                            umma_bf16(acol, pack_desc(a_lo + j * a_step, a_hi), pack_desc(b_lo + j * b_step, b_hi), idesc,
-                                      (j > 0 || !fresh) ? 1u : 0u);
-                        umma_commit(&w_empty[slot]);   // frees the weight slot once these MMAs have read it
+                    for (int t = 0; t < MAXT; ++t) {
+                        if (t < A.ntap) {
+                            const uint32_t a_lo = a_lo_buf + tap_a[t];
+                            const uint32_t b_lo = b_lo0 + (uint32_t)t * (uint32_t)(B_BYTES >> 4);
+                            if (leader) {
+#pragma unroll
+                                for (int j = 0; j < TK / 16; ++j)
+                                    umma_bf16(acc0 + tap_col[t], pack_desc(a_lo + j * a_step, a_hi), pack_desc(b_lo + j * b_step, b_hi), idesc,
+                                              (j > 0 || !((fresh_mask >> t) & 1u)) ? 1u : 0u);
+                            }
+                        }
                     }
-                    __syncwarp();
+                } else {
+#pragma unroll
+                    for (int t = 0; t < MAXT; ++t) {
+                        if (t < A.ntap) {
+                            const uint32_t slot = wi % NB;
+                            mbar_wait(&w_full[slot], (uint32_t)((wi / NB) & 1));
+                            const uint32_t a_lo = a_lo_buf + tap_a[t];
+                            const uint32_t b_lo = b_lo_k | (sB16 + slot * (uint32_t)(B_BYTES >> 4));
+                            if (leader) {
+#pragma unroll
+                                for (int j = 0; j < TK / 16; ++j)
+                                    umma_bf16(acc0 + tap_col[t], pack_desc(a_lo + j * a_step, a_hi), pack_desc(b_lo + j * b_step, b_hi), idesc,
+                                              (j > 0 || !((fresh_mask >> t) & 1u)) ? 1u : 0u);
+                                umma_commit(&w_empty[slot]);   // frees the weight slot once these MMAs have read it
+                            }
+                            ++wi;
+                        }
+                    }
                 }
                 if (leader) umma_commit(&a_empty[b]);  // frees the halo buffer
                 __syncwarp();
@@ -504,6 +549,7 @@ static bool build_halo_args(const rp_conv_desc* d, HaloArgs* H, int bn, int tk, 
     H->nkt0 = A.src[0].C / tk;
     H->inv_nkt = 1.f / (float)H->nkt;
     H->ng = 2;
+    H->w_resident = 0;
     H->acc_cols = A.nclass * bn;
     int cols = 32;
     while (cols < 2 * H->acc_cols) cols <<= 1;                 // two accumulator sets (epilogue of tile i-1 || MMAs of tile i)
@@ -525,6 +571,7 @@ static int launch_halo(const HaloArgs& H0, const void* wp, cudaStream_t stream) 
     const size_t fixed = (size_t)EPI_SMEM + (size_t)NB * BN * TK * 2;
     // four gathers in flight when the halo is small (stem, 3x3 / transposed layers, 1x1 heads), two otherwise
     H.ng = (H.NPX * 4 <= 2 * MAXNPX && fixed + 4 * a_bytes <= 220 * 1024) ? 4 : 2;
+    H.w_resident = (H.ntn == 1 && H.nkt * H.ntap <= NB) ? 1 : 0;
     const size_t smem = fixed + H.ng * a_bytes;
     if (smem > 220 * 1024) return RP_ERR_UNSUPPORTED;
     auto kern = conv_halo_tc<BN, TK, NB>;
@@ -576,7 +623,7 @@ int rp_conv_layer_halo(const rp_conv_desc* d, const void* w_packed, int bn, int 
     if (!halo::build_halo_args(d, &H, bn, tk, nullptr, (flags & 1) != 0)) return RP_ERR_UNSUPPORTED;
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
 #define RP_HALO_CASE(BN_, TK_, NB_) if (bn == BN_ && tk == TK_) return halo::launch_halo<BN_, TK_, NB_>(H, w_packed, stream);
-    RP_HALO_CASE(32, 64, 16) RP_HALO_CASE(64, 64, 12) RP_HALO_CASE(128, 64, 6)
+    RP_HALO_CASE(32, 64, 32) RP_HALO_CASE(64, 64, 12) RP_HALO_CASE(128, 64, 6)
     RP_HALO_CASE(32, 32, 16) RP_HALO_CASE(64, 32, 16) RP_HALO_CASE(128, 32, 8)
     RP_HALO_CASE(32, 16, 16) RP_HALO_CASE(256, 32, 4)
 #undef RP_HALO_CASE
