@@ -220,6 +220,9 @@ int rp_scnet_resize_in(const float* x, int n, int H, int W, float* out, void* st
 int rp_scnet_resize_in_split(const float* x, int n, int H, int W, void* out, void* stream);
 /* F.upsample(xout,inShape,'bilinear',align_corners=False) (mymodel.py:379): in [n,224,224,C] NHWC -> out [n,C,H,W] NCHW */
 int rp_scnet_resize_out(const float* in, int n, int C, int H, int W, float* out, void* stream);
+/* same with `pitch` floats per pixel in memory and a device channel map (output channel c reads cmap[c]): the engine keeps
+ * every head at a 16-byte aligned channel offset of the 224x224 tensor */
+int rp_scnet_resize_out_map(const float* in, int n, int pitch, const int* cmap, int C, int H, int W, float* out, void* stream);
 
 /* Stage entry: the fitters only (rpmodule.py:484-508; fit_horn87 :60, fit_spectral :86, fit_irls :169, fit_irls_sm :212,
  * horn87_np :17).  Problem b owns nodes [node_off[b], node_off[b+1]) = candidate correspondences with source/target

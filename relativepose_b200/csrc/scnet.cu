@@ -268,7 +268,10 @@ __global__ void scnet_resize_in_split_kernel(const float* __restrict__ x, int n,
     }
 }
 
-__global__ void scnet_resize_out_kernel(const float* __restrict__ in, int n, int C, int H, int W, float* __restrict__ out) {
+// `pitch` floats per pixel in memory; output channel c reads channel cmap[c] (cmap == nullptr: identity) -- the engine
+// keeps each head at a 16-byte aligned channel offset so that the head kernels store float4s.
+__global__ void scnet_resize_out_kernel(const float* __restrict__ in, int n, int C, int H, int W, float* __restrict__ out,
+                                        int pitch, const int* __restrict__ cmap) {
     // in [n,224,224,C] NHWC -> out [n,C,H,W]: one thread per output pixel; the four corner pixels are contiguous
     // C-vectors, the per-channel stores are coalesced across the warp (consecutive ox)
     const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -278,12 +281,14 @@ __global__ void scnet_resize_out_kernel(const float* __restrict__ in, int n, int
     int y0, y1, x0, x1; float ly0, ly1, lx0, lx1;
     bilin_coord(oy, 224.f / (float)H, 224, y0, y1, ly0, ly1);
     bilin_coord(ox, 224.f / (float)W, 224, x0, x1, lx0, lx1);
-    const float* b = in + (size_t)im * 224 * 224 * C;
-    const float* p00 = b + ((size_t)y0 * 224 + x0) * C; const float* p01 = b + ((size_t)y0 * 224 + x1) * C;
-    const float* p10 = b + ((size_t)y1 * 224 + x0) * C; const float* p11 = b + ((size_t)y1 * 224 + x1) * C;
+    const float* b = in + (size_t)im * 224 * 224 * pitch;
+    const float* p00 = b + ((size_t)y0 * 224 + x0) * pitch; const float* p01 = b + ((size_t)y0 * 224 + x1) * pitch;
+    const float* p10 = b + ((size_t)y1 * 224 + x0) * pitch; const float* p11 = b + ((size_t)y1 * 224 + x1) * pitch;
     float* o = out + (size_t)im * C * H * W + (size_t)oy * W + ox;
-    for (int c = 0; c < C; ++c)
-        o[(size_t)c * H * W] = ly0 * (lx0 * p00[c] + lx1 * p01[c]) + ly1 * (lx0 * p10[c] + lx1 * p11[c]);
+    for (int c = 0; c < C; ++c) {
+        const int s = cmap ? cmap[c] : c;
+        o[(size_t)c * H * W] = ly0 * (lx0 * p00[s] + lx1 * p01[s]) + ly1 * (lx0 * p10[s] + lx1 * p11[s]);
+    }
 }
 
 // Direct 3x3/s1/p1 convolution for the tiny-Cin encoder stems (conv1rgb/conv1n: Cin=4, conv1d: Cin=2 -> 32 channels,
@@ -671,7 +676,16 @@ int rp_scnet_resize_out(const float* in, int n, int C, int H, int W, float* out,
     if (!in || !out || n < 1) return RP_ERR_INVALID_ARG;
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
     size_t total = (size_t)n * H * W;
-    scnet_resize_out_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(in, n, C, H, W, out);
+    scnet_resize_out_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(in, n, C, H, W, out, C, nullptr);
+    ++g_conv_launches;
+    return cudaGetLastError() == cudaSuccess ? RP_OK : RP_ERR_CUDA;
+}
+
+int rp_scnet_resize_out_map(const float* in, int n, int pitch, const int* cmap, int C, int H, int W, float* out, void* stream_) {
+    if (!in || !out || !cmap || n < 1 || pitch < 1) return RP_ERR_INVALID_ARG;
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    size_t total = (size_t)n * H * W;
+    scnet_resize_out_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(in, n, C, H, W, out, pitch, cmap);
     ++g_conv_launches;
     return cudaGetLastError() == cudaSuccess ? RP_OK : RP_ERR_CUDA;
 }

@@ -153,7 +153,14 @@ class ScnetEngine(object):
         for st in ('rgb', 'n', 'd', 's', 'f'):
             act('d3' + st, 112, 112, 64)
             act('d2' + st, 224, 224, 32 if st in ('rgb', 'n', 'd') else 64)
-        B['out224'] = _Act(torch.empty((n, 224, 224, cout_total), **f), 224, 224, cout_total, 0, cout_total)
+        # 224x224 output of the five heads, each at a 16-byte aligned channel offset (float4 stores in the head kernels)
+        snum = cout_total - 39
+        offs = {'rgb': 0, 'n': 4, 'd': 8, 's': 12, 'f': 12 + 4 * ((snum + 3) // 4)}
+        pitch = offs['f'] + 32
+        B['out224'] = _Act(torch.zeros((n, 224, 224, pitch), **f), 224, 224, pitch, 0, pitch)
+        cmap = list(range(0, 3)) + list(range(4, 7)) + [8] + list(range(12, 12 + snum)) + list(range(offs['f'], offs['f'] + 32))
+        B['head_off'] = offs
+        B['cmap'] = torch.tensor(cmap, dtype=torch.int32, device=device)
         B['ctot'] = cout_total
         B['partials'] = None
         self._bufs, self._P, self._dev = B, P, device
@@ -338,7 +345,7 @@ class ScnetEngine(object):
             self._conv('deconv6', [B['dx7'], B['x6']], B['dx6'], True, 4, 2, 1, stream=stream)
             self._conv('deconv5', [B['dx6'], B['x5']], B['dx5'], True, 4, 2, 1, stream=stream)
             self._conv('deconv4', [B['dx5'], B['x4']], B['dx4'], True, 4, 2, 1, stream=stream)
-            head_off = {'rgb': (0, 3), 'n': (3, 3), 'd': (6, 1), 's': (7, snum), 'f': (7 + snum, 32)}
+            head_off = {k: (B['head_off'][k], c) for k, c in (('rgb', 3), ('n', 3), ('d', 1), ('s', snum), ('f', 32))}
             for st in ('rgb', 'n', 'd'):
                 self._conv('deconv3' + st, [B['dx4'], B['xin'].view(xin_slot[st], 128)], B['d3' + st], True, 4, 2, 1, stream=stream)
                 self._conv('deconv2' + st, [B['d3' + st], B['e2' + st]], B['d2' + st], True, 4, 2, 1, stream=stream)
@@ -352,7 +359,8 @@ class ScnetEngine(object):
                 self._conv('deconv1' + st, [B['d2' + st]], B['out224'].view(o, c), False, 1, 1, 0, bn=False,
                            bias=getattr(net, 'deconv1' + st).bias, tanh=(st == 'f' and bool(net.useTanh)), stream=stream)
             out = torch.empty((n, ctot, H, W), dtype=torch.float32, device=x.device)
-            _lib.check(self.lib.rp_scnet_resize_out(B['out224'].buf.data_ptr(), n, ctot, H, W, out.data_ptr(), stream), "resize_out")
+            _lib.check(self.lib.rp_scnet_resize_out_map(B['out224'].buf.data_ptr(), n, B['out224'].pitch, B['cmap'].data_ptr(), ctot, H, W,
+                                                        out.data_ptr(), stream), "resize_out")
             if trace is not None:
                 self._dump(trace)
         return out
@@ -389,5 +397,5 @@ class ScnetEngine(object):
             g = grab(a)
             trace[k + ':raw'] = g['raw']
             trace[k + ':act'] = g['act']
-        trace['out224'] = B['out224'].buf.permute(0, 3, 1, 2).contiguous()
+        trace['out224'] = B['out224'].buf[..., B['cmap'].long()].permute(0, 3, 1, 2).contiguous()
         trace['in20'] = B['in20'].buf.permute(0, 3, 1, 2).contiguous()
