@@ -277,6 +277,17 @@ int rp_pano2pc(const float* depth, int B, int dataset, double* pc, unsigned char
 int rp_blend_completion(const float* f, int C, const float* mask, const void* norm_gt, const void* depth_gt, int is_f64, int B,
                         void* normal_out, void* depth_out, void* stream);
 
+/* ---- Keypoint augmentation (RPModule/rputil.py:179-214 + Sampling :355-371) ----------------
+ * For every query descriptor q[:, i] (q [C, nq] float32, the layout rputil.interpolate returns) the squared distance to
+ * every pixel of feat [C,H,W] is formed and K rounds of { argmax of exp(-d/2); suppress [y-window, min(H-1,y+window)) x
+ * [x-window, min(W-1,x+window)) with the map's minimum } pick pts [nq, K, 2] float64 (x, y).  rp_heat_sample is `Sampling`
+ * alone on a caller-provided distance map dist [n,H,W].  Device pointers. */
+int rp_match_sample_workspace_bytes(int nq, size_t* bytes);
+int rp_match_sample(const float* q, int C, int nq, const float* feat, int H, int W, int K, int window, double* pts,
+                    void* workspace, size_t workspace_bytes, void* stream);
+int rp_heat_sample(const float* dist, int n, int H, int W, int K, int window, double* pts,
+                   void* workspace, size_t workspace_bytes, void* stream);
+
 int64_t rp_launch_count(void);
 int64_t rp_conv_launch_count(void);
 

@@ -48,13 +48,19 @@ def getMatchingPrimitive(dataS, dataT, dataset, representation, doCompletion, ke
 
     ``keypoint_fn(dataS, dataT, dataset)`` must return the reference's 6-tuple
     ``(pts, ptsNorm, ptsW, ptt, pttNorm, pttW)`` (rputil.getKeypoint / getKeypoint_kinect: pixel coordinates [n,2],
-    coordinates normalised by (W,H), weights 1.0 / 0.99).  The reference's own detector is OpenCV-contrib SIFT plus
-    an unseeded random augmentation (rputil.py:141-353) and sits outside this repo's parity perimeter
-    (SURVEY.md section 8f row 2), so it has to be supplied."""
-    if keypoint_fn is None:
-        raise NotImplementedError("getMatchingPrimitive needs keypoint_fn (the SIFT keypoint stage of rputil.getKeypoint is "
-                                  "outside the B200 hot path; see DESIGN.md section 8)")
-    pts, ptsNorm, ptsW, ptt, pttNorm, pttW = keypoint_fn(dataS, dataT, dataset)
+    coordinates normalised by (W,H), weights 1.0 / 0.99).  Default (None): rputil.getKeypoint / getKeypoint_kinect as in
+    the reference -- OpenCV SIFT on the CPU, the descriptor-distance augmentation on the GPU (csrc/rp_keypoint.cu), random
+    draws from the global numpy state."""
+    if keypoint_fn is None:                                                     # rpmodule.py:517-520
+        if 'suncg' in dataset or 'matterport' in dataset:
+            pts, ptsNorm, ptsW, ptt, pttNorm, pttW = getKeypoint(dataS['rgb'], dataT['rgb'], dataS['feat'], dataT['feat'])
+        elif 'scannet' in dataset:
+            pts, ptsNorm, ptsW, ptt, pttNorm, pttW = getKeypoint_kinect(dataS['rgb'], dataT['rgb'], dataS['feat'], dataT['feat'],
+                                                                        dataS['rgb_full'], dataT['rgb_full'])
+        else:
+            raise ValueError("unknown dataset %r" % (dataset,))
+    else:
+        pts, ptsNorm, ptsW, ptt, pttNorm, pttW = keypoint_fn(dataS, dataT, dataset)
     if pts is None or ptt is None or pts.shape[1] < 2 or ptt.shape[1] < 2:
         return None, None, None, None, None, None, None, None
     pts3d, ptsns = getPixel(dataS['depth'], dataS['normal'], pts, dataset=dataset, representation=representation)

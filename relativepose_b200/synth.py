@@ -152,3 +152,25 @@ def make_pose(seed, max_angle=2.0, t_sigma=0.5):
     R[:3, :3] = np.eye(3) + np.sin(ang) * K + (1 - np.cos(ang)) * K @ K
     R[:3, 3] = rs.randn(3) * t_sigma
     return R
+
+
+def make_feature_map(seed, C=32, H=160, W=640):
+    """Smooth, tanh-bounded synthetic descriptor map [C,H,W] float32 (the f-head of SCNet is tanh bounded and spatially
+    smooth): bilinearly zoomed low-resolution noise plus a little per-pixel noise.  numpy/scipy only, deterministic."""
+    from scipy import ndimage
+    rs = np.random.RandomState(seed)
+    lo = rs.randn(C, H // 8, W // 8)
+    f = ndimage.zoom(lo, (1, 8, 8), order=1)
+    return np.tanh(f + 0.05 * rs.randn(C, H, W)).astype(np.float32)
+
+
+def make_texture_image(seed, H=160, W=640):
+    """uint8 [H,W,3] image of random soft blobs (something a SIFT detector finds keypoints on)."""
+    rs = np.random.RandomState(seed)
+    yy, xx = np.mgrid[0:H, 0:W]
+    img = np.zeros((H, W, 3))
+    for _ in range(int(150 * H * W / (160 * 640))):
+        x, y, r = rs.randint(0, W), rs.randint(0, H), rs.randint(3, 14)
+        m = 1.0 / (1.0 + np.exp((np.sqrt((xx - x) ** 2 + (yy - y) ** 2) - r) / 1.2))
+        img = img * (1 - m[:, :, None]) + m[:, :, None] * rs.rand(3)
+    return (img * 255).astype(np.uint8)

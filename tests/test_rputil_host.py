@@ -13,8 +13,12 @@ def test_getpixel_matches_reference():
         assert np.abs(pc - G["pc_" + ds]).max() <= 1e-12 and np.abs(nn - G["nn_" + ds]).max() <= 1e-12
 
 
-def test_matching_primitive_needs_keypoints():
+def test_matching_primitive_default_keypoint_stage_is_the_reference_one():
+    """Without keypoint_fn the reference's own stage runs (rputil.getKeypoint: it reads dataS['rgb'] first); an unknown
+    dataset is rejected before any work."""
     import pytest
     from RPModule.rpmodule import getMatchingPrimitive
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(KeyError):
         getMatchingPrimitive({}, {}, "suncg", "skybox", True)
+    with pytest.raises(ValueError):
+        getMatchingPrimitive({}, {}, "nyu", "skybox", True)
