@@ -288,6 +288,14 @@ int rp_match_sample(const float* q, int C, int nq, const float* feat, int H, int
 int rp_heat_sample(const float* dist, int n, int H, int W, int K, int window, double* pts,
                    void* workspace, size_t workspace_bytes, void* stream);
 
+/* Net -> solver hand-off on the device (rpmodule.getMatchingPrimitive, rpmodule.py:511-538, fixed keypoint counts): for
+ * image i and keypoint k at pixel pts[i,k] = (x,y) (float64): rputil.getPixel (rputil.py:61-119) on depth [n_img,160,640] /
+ * normal [n_img,160,640,3] (float64) -> pc_out / nn_out [n_img,K,3]; rputil.interpolate (rputil.py:43-58) of the C-channel
+ * float32 map feat + i*feat_img_stride ([C,160,640]) -> desc_out [n_img,K,C] (the row layout rp_solve_batch reads). */
+int rp_gather_primitives(const float* feat, int C, long long feat_img_stride, const double* depth, const double* normal,
+                         const double* pts, int n_img, int K, int dataset, double* pc_out, double* nn_out, float* desc_out,
+                         void* stream);
+
 int64_t rp_launch_count(void);
 int64_t rp_conv_launch_count(void);
 

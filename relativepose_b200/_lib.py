@@ -61,7 +61,7 @@ EXPORTS = ("rp_abi_version", "rp_device_info", "rp_solve_workspace_bytes", "rp_s
            "rp_conv_nparts", "rp_conv_layer", "rp_bn_finalize", "rp_scnet_resize_in", "rp_scnet_resize_in_split", "rp_scnet_resize_out", "rp_scnet_resize_out_map",
            "rp_conv_launch_count", "rp_tc_gemm_test", "rp_conv_nparts_tc", "rp_conv_layer_tc",
            "rp_conv_halo_plan", "rp_conv_layer_halo", "rp_conv_halo_debug",
-           "rp_match_sample_workspace_bytes", "rp_match_sample", "rp_heat_sample", "rp_warp_workspace_bytes", "rp_warp_views", "rp_pano2pc", "rp_blend_completion",
+           "rp_gather_primitives", "rp_match_sample_workspace_bytes", "rp_match_sample", "rp_heat_sample", "rp_warp_workspace_bytes", "rp_warp_views", "rp_pano2pc", "rp_blend_completion",
            "rp_bn_relu_maxpool", "rp_bn_add_relu", "rp_resize_nhwc", "rp_resize_to_nchw", "rp_interpolate")
 
 _lib = None
@@ -151,6 +151,8 @@ def load():
     lib.rp_match_sample.argtypes = [vp, i32, i32, vp, i32, i32, i32, i32, vp, vp, ctypes.c_size_t, vp]
     lib.rp_heat_sample.restype = i32
     lib.rp_heat_sample.argtypes = [vp, i32, i32, i32, i32, i32, vp, vp, ctypes.c_size_t, vp]
+    lib.rp_gather_primitives.restype = i32
+    lib.rp_gather_primitives.argtypes = [vp, i32, ctypes.c_longlong, vp, vp, vp, i32, i32, i32, vp, vp, vp, vp]
     lib.rp_tc_gemm_test.restype = i32
     lib.rp_tc_gemm_test.argtypes = [vp, vp, vp, i32, i32, i32, i32, vp]
     if lib.rp_abi_version() != 1:

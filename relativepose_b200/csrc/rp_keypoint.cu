@@ -179,3 +179,84 @@ int rp_heat_sample(const float* dist, int n, int H, int W, int K, int window, do
 }
 
 }  // extern "C"
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Net -> solver hand-off on the device (rpmodule.getMatchingPrimitive, rpmodule.py:511-538, for fixed keypoint counts):
+// per (image, keypoint) rputil.getPixel (rputil.py:61-119: bilinear depth / normal at the sub-pixel location, pinhole
+// back-projection on the 160x640 four-face skybox, face rotation; float64) and rputil.interpolate of the descriptor map
+// (rputil.py:43-58; float32, the reference's operation order), written as the rows [K,3] / [K,3] / [K,C] the solver reads.
+namespace prim {
+
+__global__ void gather_primitives_kernel(const float* __restrict__ feat, int C, long long feat_img_stride,
+                                         const double* __restrict__ depth, const double* __restrict__ normal,
+                                         const double* __restrict__ pts, int n_img, int K, int dataset,
+                                         double* __restrict__ pc_out, double* __restrict__ nn_out, float* __restrict__ desc_out) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n_img * K) return;
+    const int im = idx / K;
+    constexpr int H = 160, W = 640;
+    const double px = pts[2 * (size_t)idx], py = pts[2 * (size_t)idx + 1];
+    // ---- getPixel
+    {
+        const int tx = (int)floor(px), ty = (int)floor(py);
+        const double fx = px - (double)tx, fy = py - (double)ty;
+        const double w00 = (1.0 - fy) * (1.0 - fx), w01 = fx * (1.0 - fy), w10 = fy * (1.0 - fx), w11 = fx * fy;
+        const double* d = depth + (size_t)im * H * W;
+        const size_t p00 = (size_t)ty * W + tx, p01 = p00 + 1, p10 = p00 + W, p11 = p10 + 1;
+        const double val = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(d[p00], w00), __dmul_rn(d[p01], w01)), __dmul_rn(d[p10], w10)), __dmul_rn(d[p11], w11));
+        const double* nm = normal + (size_t)im * H * W * 3;
+        double n[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+            n[c] = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(nm[p00 * 3 + c], w00), __dmul_rn(nm[p01 * 3 + c], w01)), __dmul_rn(nm[p10 * 3 + c], w10)), __dmul_rn(nm[p11 * 3 + c], w11));
+        const double nrm = sqrt(__dadd_rn(__dadd_rn(__dmul_rn(n[0], n[0]), __dmul_rn(n[1], n[1])), __dmul_rn(n[2], n[2])));
+#pragma unroll
+        for (int c = 0; c < 3; ++c) nn_out[(size_t)idx * 3 + c] = n[c] / nrm;
+        const int face = (int)floor(px / 160.0);
+        const int r = dataset == 0 ? face : ((face + 3) & 3);
+        const double y = __dmul_rn(__dmul_rn(__dsub_rn(0.5, py / 160.0), 2.0), val);
+        const double x = __dmul_rn(__dmul_rn(__dsub_rn(__dsub_rn(px, (double)(face * 160)) / 160.0, 0.5), 2.0), val);
+        const double z = -val;
+        double ox, oz;
+        if (r == 0) { ox = x; oz = z; } else if (r == 1) { ox = -z; oz = x; } else if (r == 2) { ox = -x; oz = -z; } else { ox = z; oz = -x; }
+        pc_out[(size_t)idx * 3] = ox; pc_out[(size_t)idx * 3 + 1] = y; pc_out[(size_t)idx * 3 + 2] = oz;
+    }
+    // ---- interpolate (normalised coordinates pass through float32, as torch_op.v(ptsNorm) does)
+    {
+        const float xn = (float)(px / 640.0), yn = (float)(py / 160.0);
+        const float x = xn * (float)(W - 1), y = yn * (float)(H - 1);
+        const float x0 = floorf(x), y0 = floorf(y);
+        int ix = (int)x0, iy = (int)y0;
+        ix = ix < 0 ? 0 : (ix > W - 2 ? W - 2 : ix);
+        iy = iy < 0 ? 0 : (iy > H - 2 ? H - 2 : iy);
+        const float wx0 = __fsub_rn(__fadd_rn(x0, 1.f), x), wy0 = __fsub_rn(__fadd_rn(y0, 1.f), y);
+        const float wx1 = __fsub_rn(x, x0), wy1 = __fsub_rn(y, y0);
+        const float* fb = feat + (size_t)im * feat_img_stride;
+        for (int c = 0; c < C; ++c) {
+            const float* f = fb + (size_t)c * H * W;
+            const float v00 = f[(size_t)iy * W + ix], v10 = f[(size_t)(iy + 1) * W + ix];
+            const float v01 = f[(size_t)iy * W + ix + 1], v11 = f[(size_t)(iy + 1) * W + ix + 1];
+            float rr = __fmul_rn(__fmul_rn(v00, wx0), wy0);
+            rr = __fadd_rn(rr, __fmul_rn(__fmul_rn(v10, wx0), wy1));
+            rr = __fadd_rn(rr, __fmul_rn(__fmul_rn(v01, wx1), wy0));
+            rr = __fadd_rn(rr, __fmul_rn(__fmul_rn(v11, wx1), wy1));
+            desc_out[(size_t)idx * C + c] = rr;
+        }
+    }
+}
+
+}  // namespace prim
+
+extern "C" int rp_gather_primitives(const float* feat, int C, long long feat_img_stride, const double* depth, const double* normal,
+                                    const double* pts, int n_img, int K, int dataset, double* pc_out, double* nn_out,
+                                    float* desc_out, void* stream_) {
+    if (n_img == 0 || K == 0) return RP_OK;
+    if (!feat || !depth || !normal || !pts || !pc_out || !nn_out || !desc_out || C < 1 || n_img < 0 || K < 0 || dataset < 0 || dataset > 2)
+        return RP_ERR_INVALID_ARG;
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    const int n = n_img * K;
+    prim::gather_primitives_kernel<<<(n + 127) / 128, 128, 0, stream>>>(feat, C, feat_img_stride, depth, normal, pts, n_img, K, dataset,
+                                                                        pc_out, nn_out, desc_out);
+    ++scnet::g_conv_launches;
+    return cudaGetLastError() == cudaSuccess ? RP_OK : RP_ERR_CUDA;
+}

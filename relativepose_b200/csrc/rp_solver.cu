@@ -368,7 +368,9 @@ struct Shared {
 };
 
 // Per-correspondence geometry, SoA in the slot's global workspace (stride = Nmax doubles).
-enum { G_PX = 0, G_PY, G_PZ, G_QX, G_QY, G_QZ, G_NX, G_NY, G_NZ, G_MX, G_MY, G_MZ, G_WS, G_WT, G_F, G_DEG, G_COUNT };
+enum { G_PX = 0, G_PY, G_PZ, G_QX, G_QY, G_QZ, G_NX, G_NY, G_NZ, G_MX, G_MY, G_MZ, G_WS, G_WT, G_F, G_DEG,
+       G_T0, G_T1,        // scratch N-vectors of the accelerated eigen iteration (search direction p and A p)
+       G_COUNT };
 
 struct PairView {
     int ns, nt, K, N, NW;
@@ -666,12 +668,152 @@ struct DegStep {              // row sums of W
     __device__ __forceinline__ void fin(int p, double s1, double) const { deg[p] = s1; }
 };
 
+template <bool USE_SV>
+struct MatVecStep {           // out = S (diag(h) W + W diag(h)) S in
+    const double* __restrict__ in; double* __restrict__ out;
+    const double* __restrict__ h; const double* __restrict__ sv;
+    __device__ __forceinline__ void term(int c, double w, double& s1, double& s2) const {
+        double gc = in[c];
+        if (USE_SV) gc *= sv[c];
+        s1 += w * gc; s2 += w * (h[c] * gc);
+    }
+    __device__ __forceinline__ void fin(int p, double s1, double s2) {
+        double y = h[p] * s1 + s2;
+        if (USE_SV) y *= sv[p];
+        out[p] = y;
+    }
+};
+
+constexpr int PI_SWITCH = 48;       // ROBUST variant: plain power steps before the accelerated iteration takes over
+constexpr int PI_FAST_CAP = 64;     // fast variant: power steps after which a pair is handed to the ROBUST variant
+constexpr int RP_STATUS_RETRY = -100;   // internal: pair waits for the ROBUST pass (never visible to the caller)
+
+// Continuation of the power iteration for graphs whose two leading eigenvalues nearly coincide (two weakly coupled
+// groups of mutually consistent correspondences: lambda_2/lambda_1 -> 1, where the power method needs ~1/(1 - ratio)
+// steps and ARPACK's restarted Arnoldi, which the reference calls (rpmodule.py:134,273), does not care).  Locally
+// optimal CG: every step takes the best Rayleigh-Ritz vector in span{x, r, p} -- the iterate, its (orthonormalised)
+// residual and the previous update -- so the error contracts like 1 - 2 sqrt(gap) instead of 1 - gap; one CSR pass
+// (A r) per step, A x and A p follow by linearity.  The 3x3 projected problem is expressed in the orthonormal basis
+// {x, r, p_perp} through inner products only (one 8-value reduction) and solved redundantly by every thread with the
+// Jacobi routine of the Horn fit.  On entry pv.ua holds the unit iterate of the power phase; on return the unit
+// eigenvector.  A "converged" residual that was reached through the A x recurrence is re-checked with a true product.
+// (Only instantiated in the ROBUST variant of the kernel, see rp_solve_kernel: inlined into the fused kernel it costs the
+//  common path ~9 % through register spills, as a call it forces the per-pair view into local memory.)
+template <bool USE_SV>
+__device__ __forceinline__ int lopcg_continue(Shared& sh, const PairView& pv, double tol, int max_it, int& red_buf, int* converged) {
+    const int tid = threadIdx.x;
+    const int N = pv.N;
+    double* __restrict__ x = pv.ua; double* __restrict__ r = pv.ub;
+    double* __restrict__ Ar = pv.aP; double* __restrict__ Ax = pv.aN;
+    double* __restrict__ p = pv.geo + (size_t)G_T0 * pv.gstride;
+    double* __restrict__ Ap = pv.geo + (size_t)G_T1 * pv.gstride;
+    for (int c = tid; c < N; c += T) { r[c] = 0.0; Ar[c] = 0.0; Ax[c] = 0.0; p[c] = 0.0; Ap[c] = 0.0; }
+    __syncthreads();
+    MatVecStep<USE_SV> mv; mv.h = pv.res; mv.sv = pv.sv;
+    double lam = 0.0;
+    auto true_product = [&]() {                          // Ax = A x, lam = x . Ax
+        mv.in = x; mv.out = Ax;
+        csr_walk(sh, pv, mv);
+        __syncthreads();
+        double v[1] = {0.0};
+        for (int c = tid; c < N; c += T) v[0] += x[c] * Ax[c];
+        block_sum<1>(sh, v, red_buf);
+        lam = v[0];
+    };
+    true_product();
+    bool have_p = false, fresh = true;
+    int it = 1;
+    *converged = 0;
+    while (it < max_it) {
+        double v2[2] = {0.0, 0.0};
+        for (int c = tid; c < N; c += T) { const double rc = Ax[c] - lam * x[c]; r[c] = rc; v2[0] += rc * rc; v2[1] += x[c] * rc; }
+        block_sum<2>(sh, v2, red_buf);
+        const double rn2 = v2[0] - v2[1] * v2[1];
+        if (v2[0] <= tol * tol * lam * lam || !(rn2 > 0.0)) {
+            if (fresh) { *converged = 1; break; }
+            true_product(); ++it;                        // re-check against a true product, restart the direction
+            fresh = true; have_p = false;
+            continue;
+        }
+        const double rinv = rsqrt(rn2);
+        for (int c = tid; c < N; c += T) r[c] = (r[c] - v2[1] * x[c]) * rinv;
+        __syncthreads();                                 // r complete before it is gathered
+        mv.in = r; mv.out = Ar;
+        csr_walk(sh, pv, mv);
+        __syncthreads();
+        ++it;
+        double d[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};     // xAr rAr | xAp rAp pAp xp rp pp
+        for (int c = tid; c < N; c += T) {
+            const double xc = x[c], rc = r[c], arc = Ar[c];
+            d[0] += xc * arc; d[1] += rc * arc;
+            if (have_p) {
+                const double pc = p[c], apc = Ap[c];
+                d[2] += xc * apc; d[3] += rc * apc; d[4] += pc * apc; d[5] += xc * pc; d[6] += rc * pc; d[7] += pc * pc;
+            }
+        }
+        block_sum<8>(sh, d, red_buf);
+        double B[4][4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) B[i][j] = 0.0;
+        B[0][0] = lam; B[0][1] = B[1][0] = d[0]; B[1][1] = d[1];
+        bool use_p = false;
+        double ninv = 0.0;
+        if (have_p) {
+            const double n2 = d[7] - d[5] * d[5] - d[6] * d[6];
+            if (d[7] > 0.0 && n2 > 1e-20 * d[7]) {
+                use_p = true;
+                ninv = rsqrt(n2);
+                B[0][2] = B[2][0] = (d[2] - d[5] * lam - d[6] * d[0]) * ninv;
+                B[1][2] = B[2][1] = (d[3] - d[5] * d[0] - d[6] * d[1]) * ninv;
+                B[2][2] = (d[4] - 2.0 * d[5] * d[2] - 2.0 * d[6] * d[3] + d[5] * d[5] * lam + 2.0 * d[5] * d[6] * d[0] + d[6] * d[6] * d[1]) * ninv * ninv;
+            }
+        }
+        double low = fmin(fmin(B[0][0] - fabs(B[0][1]) - fabs(B[0][2]), B[1][1] - fabs(B[0][1]) - fabs(B[1][2])),
+                          B[2][2] - fabs(B[0][2]) - fabs(B[1][2])) - 1.0 - fabs(lam);
+        if (!use_p) B[2][2] = low - 1.0;                 // decoupled filler rows below the spectrum
+        B[3][3] = low - 2.0;
+        double a[4];
+        jacobi4_max(B, a);
+        if (a[0] < 0.0) { a[0] = -a[0]; a[1] = -a[1]; a[2] = -a[2]; }
+        double theta = 0.0;
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int j = 0; j < 3; ++j) theta += a[i] * B[i][j] * a[j];
+        const double c2 = use_p ? a[2] * ninv : 0.0;
+        const double c1 = use_p ? a[1] - c2 * d[6] : a[1];
+        const double c0 = use_p ? a[0] - c2 * d[5] : a[0];
+        for (int c = tid; c < N; c += T) {
+            const double xc = x[c], rc = r[c], arc = Ar[c], axc = Ax[c];
+            const double pc = use_p ? p[c] : 0.0, apc = use_p ? Ap[c] : 0.0;
+            x[c] = c0 * xc + c1 * rc + c2 * pc;
+            Ax[c] = c0 * axc + c1 * arc + c2 * apc;
+            p[c] = c1 * rc + c2 * pc;
+            Ap[c] = c1 * arc + c2 * apc;
+        }
+        lam = theta;
+        have_p = true; fresh = false;
+        __syncthreads();
+    }
+    {   // unit norm (the basis is orthonormal up to rounding)
+        double v[1] = {0.0};
+        for (int c = tid; c < N; c += T) v[0] += x[c] * x[c];
+        block_sum<1>(sh, v, red_buf);
+        const double inv = v[0] > 0.0 ? rsqrt(v[0]) : 0.0;
+        for (int c = tid; c < N; c += T) x[c] *= inv;
+    }
+    __syncthreads();
+    return it;
+}
+
 // Leading eigenvector of A = S (diag(h) W + W diag(h)) S (S = diag(sv) or identity; h lives in pv.res) by power
 // iteration -- the compact-matrix equivalent of csc_matrix + eigs(k=1) (rpmodule.py:270-276, :131-136).
 // The iterate is kept un-normalised (y_k = A u_k, u_{k+1} = y_k/||y_k||) and the step's single reduction
 // carries both ||y_k||^2 and the residual ||y_k - lambda_{k-1} u_k||^2, i.e. lambda^2 ||u_{k+1}-u_k||^2 with a
 // one-step-stale lambda.  On return pv.ua holds the unit eigenvector (non-negative).
-template <bool USE_SV>
+template <bool USE_SV, bool ROBUST>
 __device__ int power_iteration(Shared& sh, const PairView& pv, double tol, int max_it, bool warm,
                                int& red_buf, int* converged) {
     const int tid = threadIdx.x;
@@ -691,14 +833,17 @@ __device__ int power_iteration(Shared& sh, const PairView& pv, double tol, int m
     int it = 0;
     *converged = 0;
     double res_prev = CUDART_INF;
-    for (it = 0; it < max_it; ++it) {
+    const int cap = ROBUST ? PI_SWITCH : PI_FAST_CAP;
+    const int max_pi = max_it < cap ? max_it : cap;
+    bool dead = false;
+    for (it = 0; it < max_pi; ++it) {
         st.acc0 = 0.0; st.acc1 = 0.0;
         csr_walk(sh, pv, st);
         double v[2] = {st.acc0, st.acc1};
         block_sum<2>(sh, v, red_buf);                    // barrier: nxt complete, cur no longer read
         double nrm2 = v[0];
         { const double* t = st.cur; st.cur = st.nxt; st.nxt = const_cast<double*>(t); }
-        if (!(nrm2 > 0.0)) { st.inv = 0.0; ++it; break; }
+        if (!(nrm2 > 0.0)) { st.inv = 0.0; ++it; dead = true; break; }
         double lam = sqrt(nrm2);
         st.inv = 1.0 / lam;
         if (it > 0) {
@@ -712,6 +857,12 @@ __device__ int power_iteration(Shared& sh, const PairView& pv, double tol, int m
     { const double* cur = st.cur; const double inv = st.inv;
       for (int p = tid; p < N; p += T) pv.ua[p] = cur[p] * inv; }   // leave the unit vector in pv.ua
     __syncthreads();
+    if (ROBUST) {
+        if (!*converged && !dead && it >= PI_SWITCH && max_it > PI_SWITCH)
+            it += lopcg_continue<USE_SV>(sh, pv, tol, max_it - it, red_buf, converged);
+    } else if (dead) {
+        *converged = 1;                                  // zero matrix: nothing a second pass could improve
+    }
     return it;
 }
 
@@ -840,11 +991,16 @@ __device__ __forceinline__ void write_identity(double* T_out) {
     if (T_out && threadIdx.x < 16) T_out[threadIdx.x] = ((threadIdx.x % 5) == 0) ? 1.0 : 0.0;
 }
 
+// ROBUST = false: the fused kernel with a plain power iteration capped at PI_FAST_CAP steps; a pair whose iteration has
+// not converged by then is marked RP_STATUS_RETRY and left.  ROBUST = true: launched right behind it on the same
+// stream, redoes exactly those pairs with the accelerated eigen iteration (lopcg_continue) -- a few microseconds when
+// there is none, and the common path keeps its register allocation.
+template <bool ROBUST>
 __global__ void __launch_bounds__(T, RP_MIN_BLOCKS) rp_solve_kernel(const SolveArgs A) {
     extern __shared__ __align__(16) unsigned char dyn_smem[];
     __shared__ Shared sh;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    int* work_counter = reinterpret_cast<int*>(A.ws);
+    int* work_counter = reinterpret_cast<int*>(A.ws) + (ROBUST ? 1 : 0);
     char* slot = A.ws + 256 + (size_t)blockIdx.x * A.slot_bytes;
 
     for (;;) {
@@ -853,6 +1009,7 @@ __global__ void __launch_bounds__(T, RP_MIN_BLOCKS) rp_solve_kernel(const SolveA
         __syncthreads();
         const int b = sh.cnt[4];
         if (b >= A.B) break;
+        if (ROBUST && A.status[b] != RP_STATUS_RETRY) continue;
 
         const rp_params par = A.params[A.param_idx ? A.param_idx[b] : 0];
         const int s0 = A.off_s[b], t0 = A.off_t[b];
@@ -1249,6 +1406,7 @@ __global__ void __launch_bounds__(T, RP_MIN_BLOCKS) rp_solve_kernel(const SolveA
         // ------------------------------------------------------------------ F. fitters
         const double mu = par.mu;
         int tot_it = 0, max_it_seen = 0, not_conv = 0;
+        bool retry = false;                              // fast variant: the eigen iteration needs the ROBUST pass
         for (int c = tid; c < N; c += T) {
             double dP = pv.geo[G_DEG * pv.gstride + c], dN = dP;
             if (A.solve_only && A.node_wp) { dP = A.node_wp[s0 + c]; dN = A.node_wn[s0 + c]; }   // stacked-row weights of fit_horn87 / fit_irls
@@ -1264,8 +1422,9 @@ __global__ void __launch_bounds__(T, RP_MIN_BLOCKS) rp_solve_kernel(const SolveA
             for (int alt = 0; alt < NUM_ALTER; ++alt) {
                 residual_to_h(pv);
                 int conv = 0;
-                int it = power_iteration<false>(sh, pv, par.power_tol, par.max_power_iters, alt > 0, red_buf, &conv);
+                int it = power_iteration<false, ROBUST>(sh, pv, par.power_tol, par.max_power_iters, alt > 0, red_buf, &conv);
                 tot_it += it; max_it_seen = it > max_it_seen ? it : max_it_seen; not_conv |= !conv;
+                if (!ROBUST && !conv && par.max_power_iters > PI_FAST_CAP) { retry = true; break; }
                 if (A.has_dbg && A.dbg.u) for (int c = tid; c < N; c += T) A.dbg.u[((size_t)b * NUM_ALTER + alt) * A.dbg.u_stride + c] = pv.ua[c];
                 x_degrees(sh, pv, mu);
                 irls_rounds(sh, pv, mu, red_buf);
@@ -1278,8 +1437,9 @@ __global__ void __launch_bounds__(T, RP_MIN_BLOCKS) rp_solve_kernel(const SolveA
                 residual_pass(sh, pv, mu, false);
                 residual_to_h(pv);
                 int conv = 0;
-                int it = power_iteration<true>(sh, pv, par.power_tol, par.max_power_iters, false, red_buf, &conv);
+                int it = power_iteration<true, ROBUST>(sh, pv, par.power_tol, par.max_power_iters, false, red_buf, &conv);
                 tot_it += it; max_it_seen = it > max_it_seen ? it : max_it_seen; not_conv |= !conv;
+                if (!ROBUST && !conv && par.max_power_iters > PI_FAST_CAP) { retry = true; break; }
                 if (A.has_dbg && A.dbg.u) for (int c = tid; c < N; c += T) A.dbg.u[((size_t)b * NUM_ALTER + alt) * A.dbg.u_stride + c] = pv.ua[c];
                 x_degrees(sh, pv, mu);
                 for (int c = tid; c < N; c += T) pv.sv[c] = pv.ua[c];     // next affinity uses allWP = mu*x (:126,148)
@@ -1289,6 +1449,10 @@ __global__ void __launch_bounds__(T, RP_MIN_BLOCKS) rp_solve_kernel(const SolveA
         } else {
             write_identity(Tout);
             if (tid == 0) A.status[b] = RP_STATUS_UNSUPPORTED;
+            continue;
+        }
+        if (retry) {                                     // uniform: decided from block-wide reductions
+            if (tid == 0) A.status[b] = RP_STATUS_RETRY;
             continue;
         }
         if (tid < 16) {
@@ -1358,8 +1522,8 @@ int default_slots(size_t smem_bytes) {
     if (cudaGetDevice(&dev) != cudaSuccess) return -1;
     if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return -1;
     int per = 0;
-    cudaFuncSetAttribute(rp_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, rp_solve_kernel, T, smem_bytes) != cudaSuccess) return -1;
+    cudaFuncSetAttribute(rp_solve_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, rp_solve_kernel<false>, T, smem_bytes) != cudaSuccess) return -1;
     if (per < 1) per = 1;
     return sms * per;
 }
@@ -1421,7 +1585,8 @@ int rp_solve_batch_ex(int B, const int32_t* off_s, const int32_t* off_t,
     if (!make_layout(max_ns, max_topk, edge_cap, &L)) return RP_ERR_UNSUPPORTED;
     SmemPlan S;
     if (!make_smem_plan(L, max_nt, feat_dim, &S)) return RP_ERR_UNSUPPORTED;
-    if (cudaFuncSetAttribute(rp_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S.bytes) != cudaSuccess) {
+    if (cudaFuncSetAttribute(rp_solve_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S.bytes) != cudaSuccess ||
+        cudaFuncSetAttribute(rp_solve_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S.bytes) != cudaSuccess) {
         cudaGetLastError();
         return RP_ERR_CUDA;
     }
@@ -1448,8 +1613,12 @@ int rp_solve_batch_ex(int B, const int32_t* off_s, const int32_t* off_t,
     a.mask_in_smem = S.mask_in_smem; a.tfeat_stride = S.tfeat_stride; a.sm_mask_off = S.mask_off;
     if (cudaMemsetAsync(workspace, 0, 256, stream) != cudaSuccess) { cudaGetLastError(); return RP_ERR_CUDA; }
     int grid = B < n_slots ? B : n_slots;
-    rp_solve_kernel<<<grid, T, S.bytes, stream>>>(a);
+    rp_solve_kernel<false><<<grid, T, S.bytes, stream>>>(a);
     ++g_launches;
+    if (a.stop_after == RP_STAGE_SOLVE) {                // pairs whose eigen iteration needs the accelerated method
+        rp_solve_kernel<true><<<grid, T, S.bytes, stream>>>(a);
+        ++g_launches;
+    }
     if (cudaGetLastError() != cudaSuccess) return RP_ERR_CUDA;
     return RP_OK;
 }
@@ -1504,7 +1673,8 @@ int rp_spectral_irls_solve(int B, const int32_t* node_off,
     if (!make_layout(max_nodes, 1, edge_cap, &L)) return RP_ERR_UNSUPPORTED;
     SmemPlan S;
     if (!make_smem_plan(L, 1, 8, &S)) return RP_ERR_UNSUPPORTED;
-    if (cudaFuncSetAttribute(rp_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S.bytes) != cudaSuccess) {
+    if (cudaFuncSetAttribute(rp_solve_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S.bytes) != cudaSuccess ||
+        cudaFuncSetAttribute(rp_solve_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S.bytes) != cudaSuccess) {
         cudaGetLastError();
         return RP_ERR_CUDA;
     }
@@ -1528,8 +1698,12 @@ int rp_spectral_irls_solve(int B, const int32_t* node_off,
     a.mask_in_smem = S.mask_in_smem; a.tfeat_stride = S.tfeat_stride; a.sm_mask_off = S.mask_off;
     if (cudaMemsetAsync(workspace, 0, 256, stream) != cudaSuccess) { cudaGetLastError(); return RP_ERR_CUDA; }
     int grid = B < n_slots ? B : n_slots;
-    rp_solve_kernel<<<grid, T, S.bytes, stream>>>(a);
+    rp_solve_kernel<false><<<grid, T, S.bytes, stream>>>(a);
     ++g_launches;
+    if (a.stop_after == RP_STAGE_SOLVE) {                // pairs whose eigen iteration needs the accelerated method
+        rp_solve_kernel<true><<<grid, T, S.bytes, stream>>>(a);
+        ++g_launches;
+    }
     if (cudaGetLastError() != cudaSuccess) return RP_ERR_CUDA;
     return RP_OK;
 }

@@ -1,0 +1,100 @@
+"""Device-resident batched pipeline for BASELINE configs[2] / [3]: network forward -> matching primitives -> RPModule solve
+for B scan pairs at once, and the batched form of RelativePoseEstimationViaCompletion (rpmodule.py:569-662).
+
+The reference processes one pair at a time and crosses the host boundary four times per alternation step (SURVEY.md
+section 3.1).  Here the hand-off (rpmodule.getMatchingPrimitive, :511-538) is one kernel (csrc/rp_keypoint.cu:
+rp_gather_primitives) writing the rows rp_solve_batch reads; only the [B,4,4] poses come back to the host.  Keypoint pixel
+locations are an input ([2B,K,2]; SIFT is OpenCV on the CPU and stays outside).
+
+Image order everywhere: [source_0, target_0, source_1, target_1, ...] (pair b = images 2b, 2b+1), the order
+SCNet.forward takes (evaluation.py:240).
+"""
+import ctypes
+
+import numpy as np
+
+from . import _lib, solver as _solver, util as _util
+
+
+def gather_primitives(feat, depth, normal, pts, weights, dataset):
+    """feat: CUDA float32 [2B,C,160,640] (may be a channel slice of the network output); depth [2B,160,640], normal
+    [2B,160,640,3] (CUDA, converted to float64); pts [2B,K,2] pixel (x,y) float64; weights [2B,K] (1.0 observed / 0.99).
+    -> DeviceBatch for PoseSolver.solve_device."""
+    import torch
+    lib = _lib.load()
+    n_img, C = feat.shape[0], feat.shape[1]
+    assert feat.is_cuda and feat.dtype == torch.float32 and feat.shape[2] == 160 and feat.shape[3] == 640
+    assert feat.stride(3) == 1 and feat.stride(2) == 640 and feat.stride(1) == 160 * 640, "feature maps must be contiguous planes"
+    dev = feat.device
+    depth = depth.to(dev).to(torch.float64).contiguous()
+    normal = normal.to(dev).to(torch.float64).contiguous()
+    pts = torch.as_tensor(pts, dtype=torch.float64).to(dev).contiguous()
+    weights = torch.as_tensor(weights, dtype=torch.float64).to(dev).contiguous()
+    K = pts.shape[1]
+    B = n_img // 2
+    pc = torch.empty((n_img, K, 3), dtype=torch.float64, device=dev)
+    nn = torch.empty((n_img, K, 3), dtype=torch.float64, device=dev)
+    desc = torch.empty((n_img, K, C), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.rp_gather_primitives(feat.data_ptr(), C, feat.stride(0), depth.data_ptr(), normal.data_ptr(), pts.data_ptr(),
+                                            n_img, K, _util.dataset_id(dataset), pc.data_ptr(), nn.data_ptr(), desc.data_ptr(),
+                                            torch.cuda.current_stream().cuda_stream), "rp_gather_primitives")
+
+    def side(a, k):
+        return a.view(B, 2, K, -1)[:, k].reshape(B * K, -1)
+    return _solver.DeviceBatch.from_device_arrays(side(pc, 0), side(nn, 0), side(desc, 0), weights.view(B, 2, K)[:, 0].reshape(-1),
+                                                  side(pc, 1), side(nn, 1), side(desc, 1), weights.view(B, 2, K)[:, 1].reshape(-1), B)
+
+
+def solve_from_maps(feat, depth, normal, pts, weights, para, dataset, solver=None):
+    """Poses [B,4,4] float64 (numpy) for B pairs from descriptor / depth / normal maps and keypoints; one gather kernel +
+    one fused solver launch."""
+    solver = solver or _solver.default_solver(feat.device)
+    d = gather_primitives(feat, depth, normal, pts, weights, dataset)
+    T, status, _ = solver.solve_device(d, [_solver.params_from_opts(para)])
+    return T.cpu().numpy()
+
+
+def RelativePoseEstimationViaCompletion_batch(net, rgb, norm, depth, pts, weights, args):
+    """Batched rpmodule.RelativePoseEstimationViaCompletion (rpmodule.py:569-662) for B pairs with given keypoints.
+
+    rgb [2B,160,640,3], norm [2B,160,640,3], depth [2B,160,640] (numpy or tensors; the complete scans), pts [2B,K,2],
+    weights [2B,K]; args as in the reference (snumclass, featureDim, outputType, maskMethod, alterStep, dataset, para with
+    per-step sigma arrays).  Per alternation: one batched warp of all 2B views, one SCNet forward over all pairs, one blend,
+    one gather, one solve.  Returns [B,4,4] float64."""
+    import copy
+    import torch
+    dev = next(net.parameters()).device
+    f32 = lambda a: torch.as_tensor(np.asarray(a) if not torch.is_tensor(a) else a, dtype=torch.float32).to(dev)
+    idx_f = 0
+    for key, n in (('rgb', 3), ('n', 3), ('d', 1), ('s', args.snumclass)):
+        if key in args.outputType:
+            idx_f += n
+    n_img = len(rgb)
+    B = n_img // 2
+    with torch.no_grad():
+        full = torch.cat((f32(rgb), f32(norm), f32(depth).unsqueeze(3)), 3).permute(0, 3, 1, 2).contiguous()      # [2B,7,h,w]
+        vw, m = _util.apply_mask(full, args.maskMethod)
+        views = torch.cat((vw, (vw[:, 6:7] != 0).float()), 1)                                                    # [2B,8,h,w]
+        mask = m[:, 0].contiguous()
+        norm_gt = torch.as_tensor(np.asarray(norm) if not torch.is_tensor(norm) else norm).to(dev)
+        depth_gt = torch.as_tensor(np.asarray(depth) if not torch.is_tensor(depth) else depth).to(dev)
+        swap = torch.arange(n_img, device=dev) ^ 1                    # the other scan of the pair
+        R_hat = np.tile(np.eye(4), (B, 1, 1))
+        solver = _solver.default_solver(dev)
+        for alter_ in range(args.alterStep):
+            # view i receives the other scan warped into its frame: sources get the target moved by inv(R), targets the
+            # source moved by R (rpmodule.py:616-617); identity -> zeros inside the kernel
+            Rs = np.empty((n_img, 4, 4))
+            Rs[0::2] = np.linalg.inv(R_hat)
+            Rs[1::2] = R_hat
+            warped = _util.warping_device(views[swap], Rs, args.dataset)
+            f = net(torch.cat((views, warped), 1))                                                               # :619-623
+            nrm2, dep2 = _util.blend_completion_device(f, mask, norm_gt, depth_gt)                                # :628-634
+            para_this = copy.copy(args.para)
+            for name in ('sigmaAngle1', 'sigmaAngle2', 'sigmaDist', 'sigmaFeat'):
+                setattr(para_this, name, getattr(args.para, name)[alter_])
+            d = gather_primitives(f[:, idx_f:idx_f + args.featureDim], dep2, nrm2, pts, weights, args.dataset)
+            T, status, _ = solver.solve_device(d, [_solver.params_from_opts(para_this)])
+            R_hat = T.cpu().numpy()
+    return R_hat

@@ -142,8 +142,37 @@ class PackedBatch(object):
         return d
 
 
+class _UniformHost(object):
+    """The host-side facts DeviceBatch needs (numpy's tie-order tables) for a batch with one keypoint count per side."""
+
+    def __init__(self, B, n_t):
+        self.B, self.nt_list, self._zero_rows = B, np.full([B], n_t, dtype=np.int64), {}
+
+    zero_rows = PackedBatch.zero_rows
+
+
 class DeviceBatch(object):
     """Same arrays, resident in HBM."""
+
+    @staticmethod
+    def from_device_arrays(pc_s, nrm_s, feat_s, w_s, pc_t, nrm_t, feat_t, w_t, B, sum_order=1):
+        """Wrap arrays that already live on the device (the net -> solver hand-off, pipeline.py): [B*n,3] float64 positions
+        and normals, [B*n,D] float32 descriptors, [B*n] float64 weights per side, the same keypoint count for every pair.
+        sum_order 1 = the sequential float32 summation the reference's own pipeline gets (transposed 'feat' views,
+        rpmodule.py:531-532)."""
+        import torch
+        d = DeviceBatch()
+        dev = pc_s.device
+        n_s, n_t = pc_s.shape[0] // B, pc_t.shape[0] // B
+        d.B, d.max_ns, d.max_nt, d.feat_dim = B, n_s, n_t, feat_s.shape[1]
+        d.pc_s, d.nrm_s, d.feat_s, d.w_s = pc_s.contiguous(), nrm_s.contiguous(), feat_s.contiguous(), w_s.contiguous()
+        d.pc_t, d.nrm_t, d.feat_t, d.w_t = pc_t.contiguous(), nrm_t.contiguous(), feat_t.contiguous(), w_t.contiguous()
+        d.off_s_t = (torch.arange(B + 1, dtype=torch.int32, device=dev) * n_s).contiguous()
+        d.off_t_t = (torch.arange(B + 1, dtype=torch.int32, device=dev) * n_t).contiguous()
+        d.sum_order_t = torch.full((B,), int(sum_order), dtype=torch.int32, device=dev)
+        d.host = _UniformHost(B, n_t)
+        d._zero_dev = {}
+        return d
 
     def zero_rows(self, topk, stride, device):
         key = (int(topk), int(stride))
