@@ -381,14 +381,16 @@ class PoseSolver(object):
             ws = torch.empty(nbytes.value, dtype=torch.uint8, device=dev)
             T = torch.empty((B, 4, 4), dtype=torch.float64, device=dev)
             status = torch.empty((B,), dtype=torch.int32, device=dev)
+            stats = torch.zeros((B, _lib.STATS_STRIDE), dtype=torch.int32, device=dev)
             ptr = lambda t: t.data_ptr() if t is not None else None                              # noqa: E731
             rc = self.lib.rp_spectral_irls_solve(B, t_off.data_ptr(), t_sp.data_ptr(), t_sn.data_ptr(), t_tp.data_ptr(),
                                                  t_tn.data_ptr(), ptr(t_wp), ptr(t_wn), ptr(t_eo), ptr(t_rc), ptr(t_ew),
                                                  par.data_ptr(), None, max_nodes, self.n_slots, max_edges,
-                                                 ws.data_ptr(), ws.numel(), T.data_ptr(), status.data_ptr(), None,
+                                                 ws.data_ptr(), ws.numel(), T.data_ptr(), status.data_ptr(), stats.data_ptr(),
                                                  torch.cuda.current_stream().cuda_stream)
             _lib.check(rc, "rp_spectral_irls_solve")
             st = status.cpu().numpy()
+            self.last_fit_stats = stats.cpu().numpy()      # [B,8] (include/rp_b200.h: stats), e.g. eigen iterations
         if (st != 0).any():
             raise RuntimeError("rp_spectral_irls_solve: status %s" % st[st != 0][:4])
         return T.cpu().numpy()
