@@ -272,8 +272,11 @@ __global__ void scnet_resize_in_split_kernel(const float* __restrict__ x, int n,
 // keeps each head at a 16-byte aligned channel offset so that the head kernels store float4s.
 __global__ void scnet_resize_out_kernel(const float* __restrict__ in, int n, int C, int H, int W, float* __restrict__ out,
                                         int pitch, const int* __restrict__ cmap) {
-    // in [n,224,224,C] NHWC -> out [n,C,H,W]: one thread per output pixel; the four corner pixels are contiguous
-    // C-vectors, the per-channel stores are coalesced across the warp (consecutive ox)
+    // in [n,224,224,pitch] NHWC -> out [n,C,H,W]: one thread per output pixel; the four corner pixels are contiguous
+    // channel vectors, the per-channel stores are coalesced across the warp (consecutive ox); 4 channels in flight
+    __shared__ int s_map[256];
+    for (int i = threadIdx.x; i < C && i < 256; i += blockDim.x) s_map[i] = cmap ? cmap[i] : i;
+    __syncthreads();
     const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const size_t total = (size_t)n * H * W;
     if (idx >= total) return;
@@ -285,8 +288,19 @@ __global__ void scnet_resize_out_kernel(const float* __restrict__ in, int n, int
     const float* p00 = b + ((size_t)y0 * 224 + x0) * pitch; const float* p01 = b + ((size_t)y0 * 224 + x1) * pitch;
     const float* p10 = b + ((size_t)y1 * 224 + x0) * pitch; const float* p11 = b + ((size_t)y1 * 224 + x1) * pitch;
     float* o = out + (size_t)im * C * H * W + (size_t)oy * W + ox;
-    for (int c = 0; c < C; ++c) {
-        const int s = cmap ? cmap[c] : c;
+    int c = 0;
+    for (; c + 4 <= C; c += 4) {
+        float v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int s = s_map[c + u];
+            v[u] = ly0 * (lx0 * __ldg(p00 + s) + lx1 * __ldg(p01 + s)) + ly1 * (lx0 * __ldg(p10 + s) + lx1 * __ldg(p11 + s));
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) o[(size_t)(c + u) * H * W] = v[u];
+    }
+    for (; c < C; ++c) {
+        const int s = s_map[c];
         o[(size_t)c * H * W] = ly0 * (lx0 * p00[s] + lx1 * p01[s]) + ly1 * (lx0 * p10[s] + lx1 * p11[s]);
     }
 }

@@ -32,6 +32,7 @@ using namespace tc;
 constexpr int TH = 16, TW = 8, TM = 128;
 constexpr int EPI = 128, LOADERS = 256, CTA = EPI + LOADERS + 64;    // warps 0-3 epilogue, 4-11 loaders, 12 TMA, 13 MMA
 constexpr int MAXT = 16;            // taps over all classes
+constexpr int MAXACC = 8;           // accumulator sets in TMEM (512 columns / (classes x BN), at most 8)
 constexpr int MAXNPX = 640;         // halo pixels (4 planes x 17 x 9 = 612 for 4x4 s2)
 constexpr int EPI_SMEM = (4 * 32 * 33 + 16 * 4 * 64) * 4;            // per-warp transpose buffers + partial sums
 
@@ -51,7 +52,7 @@ struct HaloArgs {
     int ntap;
     HTap tap[MAXT];
     int nkt, nkt0;                         // K chunks in total / in source 0
-    int acc_cols, tmem_cols;               // TMEM columns of one accumulator set (nclass x BN) / allocated (2 sets)
+    int acc_cols, tmem_cols, nacc;         // TMEM columns of one accumulator set (nclass x BN) / allocated / number of sets
     int ng;                                // loader groups = halo buffers (2 or 4): group i fills buffer i with chunks i, i+ng, ...
     float inv_nkt;
     int w_resident;                        // all weight blocks of a tile fit in the ring: loaded once per CTA, never freed
@@ -114,10 +115,11 @@ __global__ void __launch_bounds__(CTA, 1) conv_halo_tc(const HaloArgs A, const u
     constexpr int KC = TK / 8;
     constexpr int B_BYTES = BN * TK * 2;
     constexpr int U = 4;                           // loads in flight per loader thread
-    __shared__ __align__(8) uint64_t a_full[4], a_empty[4], w_full[NB], w_empty[NB], acc_full[2], acc_empty[2];
+    __shared__ __align__(8) uint64_t a_full[4], a_empty[4], w_full[NB], w_empty[NB], acc_full[MAXACC], acc_empty[MAXACC];
     __shared__ uint32_t tmem_slot;
     __shared__ int s_pix[2 * MAXNPX];              // one pixel table per loader group (ng x NPX <= 2 x MAXNPX)
     __shared__ int s_lut[MAXNPX];                  // halo pixel -> (plane << 20 | row << 10 | column), tile independent
+    __shared__ __align__(16) float s_bias[256];                  // bias of the 1x1 heads (Cout <= 256), zero padded to whole n-tiles
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int a_bytes = ((KC * A.a_lbo + 127) / 128) * 128;
     unsigned char* sEpi = smem;                                  // [EPI_SMEM] epilogue scratch (never aliased)
@@ -129,8 +131,8 @@ __global__ void __launch_bounds__(CTA, 1) conv_halo_tc(const HaloArgs A, const u
         for (int i = 0; i < 4; ++i) { mbar_init(&a_full[i], (uint32_t)(LOADERS / A.ng)); mbar_init(&a_empty[i], 1); }
 #pragma unroll
         for (int i = 0; i < NB; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
-        mbar_init(&acc_full[0], 1); mbar_init(&acc_full[1], 1);
-        mbar_init(&acc_empty[0], EPI); mbar_init(&acc_empty[1], EPI);
+#pragma unroll
+        for (int i = 0; i < MAXACC; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], EPI); }
         fence_mbar_init();
     }
     if (warp == 12) tmem_alloc(&tmem_slot, (uint32_t)A.tmem_cols);
@@ -141,6 +143,7 @@ __global__ void __launch_bounds__(CTA, 1) conv_halo_tc(const HaloArgs A, const u
             s_lut[h] = (p << 20) | (hy << 10) | hx;
         }
     }
+    for (int i = tid; i < 256; i += CTA) s_bias[i] = (A.bias && i < A.Cout) ? A.bias[i] : 0.f;
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -199,7 +202,7 @@ __global__ void __launch_bounds__(CTA, 1) conv_halo_tc(const HaloArgs A, const u
                 const size_t esz = in_bf16 ? 2 : 4;
                 const unsigned char* base = reinterpret_cast<const unsigned char*>(S.ptr) + (size_t)(S.ch_off + ch) * esz;
                 const size_t pstride = (size_t)S.pitch * esz;
-                mbar_wait(&a_empty[b], (use & 1u) ^ 1u);         // the MMAs that read this buffer are done
+                mbar_wait_backoff(&a_empty[b], (use & 1u) ^ 1u); // the MMAs that read this buffer are done
                 unsigned char* dst = sA + b * a_bytes + kc * A.a_lbo;
                 auto finish = [&](float (&v)[8], int h) {       // BatchNorm + LeakyReLU, bf16, one 16-byte core row
                     if (act) {
@@ -286,7 +289,7 @@ __global__ void __launch_bounds__(CTA, 1) conv_halo_tc(const HaloArgs A, const u
                 const unsigned char* wsrc = Wp + (size_t)tile_n * per_tile * B_BYTES;
                 for (int i = 0; i < per_tile; ++i, ++wi) {
                     const int slot = wi % NB;
-                    mbar_wait(&w_empty[slot], (uint32_t)(((wi / NB) & 1) ^ 1));
+                    mbar_wait_backoff(&w_empty[slot], (uint32_t)(((wi / NB) & 1) ^ 1));
                     if (leader) {
                         mbar_expect_tx(&w_full[slot], B_BYTES);
                         bulk_g2s(sB + slot * B_BYTES, wsrc + (size_t)i * B_BYTES, B_BYTES, &w_full[slot]);
@@ -320,8 +323,8 @@ __global__ void __launch_bounds__(CTA, 1) conv_halo_tc(const HaloArgs A, const u
         uint32_t wi = 0, cc = 0, tl = 0;
         bool w_ready = false;
         for (int tile = blockIdx.x; tile < A.total_tiles; tile += gridDim.x, ++tl) {
-            const uint32_t ab = tl & 1;
-            mbar_wait(&acc_empty[ab], (uint32_t)(((tl >> 1) & 1) ^ 1));   // the epilogue has drained this accumulator set
+            const uint32_t ab = tl % (uint32_t)A.nacc;
+            mbar_wait(&acc_empty[ab], ((tl / (uint32_t)A.nacc) & 1u) ^ 1u);   // the epilogue has drained this accumulator set
             tc_fence_after();
             const uint32_t acc0 = tmem_d + ab * (uint32_t)A.acc_cols;
             if (A.w_resident && !w_ready) {                               // resident weights: wait for them once
@@ -384,9 +387,9 @@ __global__ void __launch_bounds__(CTA, 1) conv_halo_tc(const HaloArgs A, const u
         uint32_t tl = 0;
         for (int tile = blockIdx.x; tile < A.total_tiles; tile += gridDim.x, ++tl) {
             const TileCoord tc_ = decode_tile(A, tile);
-            const uint32_t ab = tl & 1;
+            const uint32_t ab = tl % (uint32_t)A.nacc;
             const int a = tc_.a0 + (m >> 3), bcol = tc_.b0 + (m & 7);
-            mbar_wait(&acc_full[ab], (uint32_t)((tl >> 1) & 1));
+            mbar_wait(&acc_full[ab], (tl / (uint32_t)A.nacc) & 1u);
             tc_fence_after();
             for (int u = 0; u < nunit; ++u) {
                 const int cls = u / (BN / 32), c0 = (u - cls * (BN / 32)) * 32;
@@ -394,10 +397,16 @@ __global__ void __launch_bounds__(CTA, 1) conv_halo_tc(const HaloArgs A, const u
                 tmem_ld32(tmem_d + ((uint32_t)(q * 32) << 16) + ab * (uint32_t)A.acc_cols + (uint32_t)(cls * BN + c0), v);
                 const bool valid = a < A.cls_Ha[cls] && bcol < A.cls_Wb[cls];
                 const int co0 = tc_.tile_n * BN + c0;
-                if (A.bias || A.tanh_out) {
+                if (A.bias || A.tanh_out) {                 // (bias/tanh layers have Cout <= 256, checked on the host)
+                    const float4* bp = reinterpret_cast<const float4*>(s_bias + co0);
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        if (co0 + j < A.Cout) { const float y = v[j] + (A.bias ? __ldg(A.bias + co0 + j) : 0.f); v[j] = A.tanh_out ? fast_tanh(y) : y; }
+                    for (int j = 0; j < 32; j += 4) {
+                        const float4 b4 = bp[j >> 2];
+                        v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
+                    }
+                    if (A.tanh_out) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = fast_tanh(v[j]);
                     }
                 }
                 if (A.out_bf16) {          // statistics describe what the consumer will read: the rounded values
@@ -551,12 +560,15 @@ static bool build_halo_args(const rp_conv_desc* d, HaloArgs* H, int bn, int tk, 
     H->ng = 2;
     H->w_resident = 0;
     H->acc_cols = A.nclass * bn;
+    if (2 * H->acc_cols > 512) return false;
+    H->nacc = 512 / H->acc_cols;                              // 2..8 accumulator sets: the MMA warp runs that many tiles ahead of
+    if (H->nacc > MAXACC) H->nacc = MAXACC;                    // the epilogue, so neither waits for the other's hand-off latency
     int cols = 32;
-    while (cols < 2 * H->acc_cols) cols <<= 1;                 // two accumulator sets (epilogue of tile i-1 || MMAs of tile i)
-    if (cols > 512) return false;
+    while (cols < H->nacc * H->acc_cols) cols <<= 1;
     H->tmem_cols = cols;
     H->bias = d->bias; H->tanh_out = d->tanh_out;
     if (d->out_dtype == 1 && (d->bias || d->tanh_out)) return false;
+    if ((d->bias || d->tanh_out) && H->ntn * bn > 256) return false;
     H->out = d->out; H->out_pitch = d->out_pitch; H->out_ch_off = d->out_ch_off; H->out_bf16 = d->out_dtype == 1 ? 1 : 0;
     if (H->out_bf16 && ((d->out_pitch % 8) || (d->out_ch_off % 8))) return false;   // float32 output: any alignment (scalar stores)
     H->psum = d->psum; H->psq = d->psq;
