@@ -32,7 +32,7 @@ METRIC = "scan-pairs/sec (R,t solved) at N=512 corr"
 UNIT = "pairs/s"
 N_NOMINAL = 512
 TOPK = 5
-DRAM_BYTES_PER_PAIR_NCU = 300_950      # measured, see roofline.traffic_source
+DRAM_BYTES_PER_PAIR_NCU = 299_028      # measured, see roofline.traffic_source
 
 
 def parse():
@@ -65,21 +65,23 @@ def _cpu_worker(job):
     return time.perf_counter() - t0, T
 
 
-def cpu_baseline(n_kp, sample, first_seed=10_000_000):
+def cpu_baseline(n_kp, sample, first_seed=10_000_000, target_s=15.0):
     """Oracle port (numpy/scipy restatement of rpmodule.py:317-508) on all host cores, one process per core
-    (the reference's own way to use more than one core: --entrySplit process sharding, evaluation.py:59)."""
+    (the reference's own way to use more than one core: --entrySplit process sharding, evaluation.py:59).
+    sample <= 0: sized from the warm-up pass for about `target_s` seconds of wall time (bounded sample of the workload)."""
     import multiprocessing as mp
     from relativepose_b200 import synth
     cores = os.cpu_count() or 1
-    if sample <= 0:
-        sample = max(4 * cores, 16)
     sig = tuple(float(x) for x in synth.shipped_params("suncg")[0])
-    jobs = [(first_seed + i, n_kp, sig) for i in range(sample)]
     ctx = mp.get_context("fork")
     with ctx.Pool(cores) as pool:
-        pool.map(_cpu_worker, jobs[:cores])            # warm the workers (imports, BLAS init)
+        warm = pool.map(_cpu_worker, [(first_seed - 1 - i, n_kp, sig) for i in range(cores)])   # imports, BLAS init
+        if sample <= 0:
+            lat0 = float(np.median([r[0] for r in warm]))
+            sample = int(min(max(4 * cores, cores * target_s / max(lat0, 1e-4)), 20000))
+        jobs = [(first_seed + i, n_kp, sig) for i in range(sample)]
         t0 = time.perf_counter()
-        res = pool.map(_cpu_worker, jobs, chunksize=1)
+        res = pool.map(_cpu_worker, jobs, chunksize=max(1, sample // (cores * 16)))
         wall = time.perf_counter() - t0
     lat = np.array([r[0] for r in res])
     return {"value": sample / wall, "unit": UNIT, "cores": cores, "kind": "port",
@@ -96,7 +98,7 @@ def run_reference_arm(args):
     walls, counts = [], []
     cb = None
     for i in range(args.warmup + args.steps):
-        cb, wall, cnt = cpu_baseline(n_kp, args.cpu_sample, first_seed=20_000_000 + 1000 * i)
+        cb, wall, cnt = cpu_baseline(n_kp, args.cpu_sample, first_seed=20_000_000 + 100_000 * i, target_s=8.0)
         if i >= args.warmup:
             walls.append(wall)
             counts.append(cnt)
@@ -105,7 +107,7 @@ def run_reference_arm(args):
     out = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sum(walls) / len(walls),
            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-           "config": workload_config(args, n_kp, counts[0]), "cpu_baseline": cb,
+           "config": workload_config(args, n_kp, args.pairs), "cpu_baseline": cb,       # the CUDA arm's config; each step = cb["sample"]
            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(out))
 
@@ -129,7 +131,7 @@ class ClockSampler(object):
 
     def start(self):
         try:
-            self.p = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100",
+            self.p = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "20",
                                        "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except Exception:
             self.p = None
@@ -281,7 +283,7 @@ def run_cuda_arm(args):
         "clocks": clocks,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": DRAM_BYTES_PER_PAIR_NCU * B, "traffic_source": "ncu --set full dram__bytes_read+write of this "
-                     "bench launch (profiles/r1_solver_bench_launch_ncu.txt: 1232.7 MB / 4096 pairs) x pairs per launch",
+                     "bench launch (profiles/r1_solver_bench_launch_ncu.txt: 395.9 MB read + 828.9 MB written / 4096 pairs) x pairs per launch",
                      "peak_source": peak_src, "kernel": "rp_solve_kernel",
                      "kernel_ms": float(np.mean(kern_ms)),
                      "model": "SURVEY 8(d) dense-equivalent bytes: 4*N^2*(2+sum_a(It_a+1)) + 156*(n_s+n_t) per pair with the "
