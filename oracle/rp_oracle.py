@@ -124,11 +124,17 @@ def _irls_rounds(rows, allW, mu, trace=None):
     return R, t, SPc, TPc, allW
 
 
+# 'LM' (largest magnitude) is what the reference's bare ``eigs(A, k=1)`` asks ARPACK for.  On a bipartite affinity
+# (lambda_max = |lambda_min| exactly) ARPACK may return either end of the spectrum, platform dependent; tests of that
+# ill-posed situation switch to 'LR' (largest real part = the Perron vector, which the CUDA path always returns).
+EIG_WHICH = 'LM'
+
+
 def _leading_eigvec(a_pair, row, col, dim):
     """Sparse symmetric affinity, leading eigenvector, unit norm.  rpmodule.py:131-136,270-276."""
     A = sp.csc_matrix((a_pair, (row, col)), shape=(dim, dim))
     A = A + A.T
-    _, u = eigs(A, k=1)
+    _, u = eigs(A, k=1, which=EIG_WHICH)
     u = u.real
     u /= np.linalg.norm(u)
     return u

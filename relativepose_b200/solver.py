@@ -233,13 +233,17 @@ class PoseSolver(object):
         return self._ws, key
 
     # ------------------------------------------------------------------ main entry
-    def solve_device(self, dbatch, plist, param_idx=None, stop_after=_lib.STAGE_SOLVE, debug=None, edge_cap=None):
-        """Launch on a DeviceBatch.  Returns device tensors (T [B,4,4] f64, status [B] i32, stats [B,8] i32)."""
+    def solve_device(self, dbatch, plist, param_idx=None, stop_after=_lib.STAGE_SOLVE, debug=None, edge_cap=None, out=None):
+        """Launch on a DeviceBatch.  Returns device tensors (T [B,4,4] f64, status [B] i32, stats [B,8] i32); `out` supplies
+        them preallocated (the small-batch path keeps all three in one buffer for a single device-to-host copy)."""
         torch = self.torch
         B = dbatch.B
-        T = torch.empty((B, 4, 4), dtype=torch.float64, device=self.device)
-        status = torch.empty((B,), dtype=torch.int32, device=self.device)
-        stats = torch.empty((B, _lib.STATS_STRIDE), dtype=torch.int32, device=self.device)
+        if out is not None:
+            T, status, stats = out
+        else:
+            T = torch.empty((B, 4, 4), dtype=torch.float64, device=self.device)
+            status = torch.empty((B,), dtype=torch.int32, device=self.device)
+            stats = torch.empty((B, _lib.STATS_STRIDE), dtype=torch.int32, device=self.device)
         if B == 0:
             return T, status, stats
         topk = max(min(int(p.topk), _lib.MAX_TOPK + 1) for p in plist)
@@ -395,8 +399,87 @@ class PoseSolver(object):
             raise RuntimeError("rp_spectral_irls_solve: status %s" % st[st != 0][:4])
         return T.cpu().numpy()
 
+    SMALL_BATCH = 16
+
     def solve_records(self, records, para, return_stats=False):
+        if 0 < len(records) <= self.SMALL_BATCH:
+            return self._solve_small(records, para, return_stats)
         return self.solve_packed(PackedBatch(records), para, return_stats=return_stats)
+
+    def _solve_small(self, records, para, return_stats):
+        """Latency path for a few pairs (RelativePoseEstimation_helper is B = 1): every input goes through ONE pinned
+        staging buffer and ONE host-to-device copy, poses + status + stats come back in ONE device-to-host copy (the general
+        path pins eight arrays and issues a dozen copies, ~0.3 ms of host time per call)."""
+        torch = self.torch
+        B = len(records)
+        plist = [params_from_opts(para)]
+        ns = [int(np.asarray(r["pc_src"]).shape[0]) for r in records]
+        nt = [int(np.asarray(r["pc_tgt"]).shape[0]) for r in records]
+        D = int(np.asarray(records[0]["feat_src"]).shape[1]) if np.asarray(records[0]["feat_src"]).ndim == 2 else FEAT_DIM_DEFAULT
+        Ns, Nt = sum(ns), sum(nt)
+        max_ns, max_nt = max(ns), max(nt)
+        topk_raw = int(plist[0].topk)
+        stride = max(1, min(min(topk_raw, _lib.MAX_TOPK + 1), max(max_nt - 1, 1)))       # as solve_device clips it
+        off_s = np.zeros(B + 1, np.int32); off_s[1:] = np.cumsum(ns)
+        off_t = np.zeros(B + 1, np.int32); off_t[1:] = np.cumsum(nt)
+        order = np.array([0 if (np.asarray(r["feat_src"]).flags["C_CONTIGUOUS"] and np.asarray(r["feat_tgt"]).flags["C_CONTIGUOUS"])
+                          else 1 for r in records], dtype=np.int32)
+        ztab = np.full([B, stride], -1, dtype=np.int32)
+        for b in range(B):
+            K = min(topk_raw, nt[b] - 1)
+            if 1 <= K <= stride:
+                ztab[b, :K] = zero_row_topk(nt[b], K)
+
+        def cat(key, dtype, cols):
+            return np.concatenate([np.asarray(r[key], dtype=dtype).reshape(-1, cols) if cols else np.asarray(r[key], dtype=dtype).reshape(-1)
+                                   for r in records], 0)
+        parts = [("off_s_t", off_s), ("off_t_t", off_t), ("sum_order_t", order), ("ztab", ztab),
+                 ("pc_s", cat("pc_src", np.float64, 3)), ("nrm_s", cat("normal_src", np.float64, 3)), ("w_s", cat("weight_src", np.float64, 0)),
+                 ("pc_t", cat("pc_tgt", np.float64, 3)), ("nrm_t", cat("normal_tgt", np.float64, 3)), ("w_t", cat("weight_tgt", np.float64, 0)),
+                 ("feat_s", cat("feat_src", np.float32, D)), ("feat_t", cat("feat_tgt", np.float32, D))]
+        offs, total = [], 0
+        for _, a in parts:
+            offs.append(total)
+            total += (a.nbytes + 255) // 256 * 256
+        out_bytes = B * (16 * 8 + 4 + _lib.STATS_STRIDE * 4)
+        if getattr(self, "_stage_host", None) is None or self._stage_host.numel() < total:
+            cap = max(total, 1 << 16)
+            self._stage_host = torch.empty((cap,), dtype=torch.uint8).pin_memory()
+            self._stage_dev = torch.empty((cap,), dtype=torch.uint8, device=self.device)
+        if getattr(self, "_out_host", None) is None or self._out_host.numel() < out_bytes:
+            cap = max(out_bytes, 1 << 12)
+            self._out_host = torch.empty((cap,), dtype=torch.uint8).pin_memory()
+            self._out_dev = torch.empty((cap,), dtype=torch.uint8, device=self.device)
+        hb = self._stage_host.numpy()
+        for (_, a), o in zip(parts, offs):
+            hb[o:o + a.nbytes] = np.ascontiguousarray(a).view(np.uint8).reshape(-1)
+        with torch.cuda.device(self.device):
+            self._stage_dev[:total].copy_(self._stage_host[:total], non_blocking=True)
+            d = DeviceBatch()
+            d.B, d.max_ns, d.max_nt, d.feat_dim = B, max_ns, max_nt, D
+            tdt = {np.dtype(np.int32): torch.int32, np.dtype(np.float64): torch.float64, np.dtype(np.float32): torch.float32}
+            views = {}
+            for (name, a), o in zip(parts, offs):
+                views[name] = self._stage_dev[o:o + a.nbytes].view(tdt[a.dtype]).view(a.shape if a.ndim > 1 else (-1,))
+            for name in PackedBatch.FIELDS + ("off_s_t", "off_t_t", "sum_order_t"):
+                setattr(d, name, views[name])
+            d.host = None
+            d._zero_dev = {(topk_raw, stride): views["ztab"]}
+            od = self._out_dev
+            T = od[:B * 128].view(torch.float64).view(B, 4, 4)
+            status = od[B * 128:B * 132].view(torch.int32)
+            stats = od[B * 132:out_bytes].view(torch.int32).view(B, _lib.STATS_STRIDE)
+            self.solve_device(d, plist, out=(T, status, stats))
+            self._out_host[:out_bytes].copy_(od[:out_bytes], non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+        ob = self._out_host.numpy()
+        Th = ob[:B * 128].view(np.float64).reshape(B, 4, 4).copy()
+        sth = ob[B * 128:B * 132].view(np.int32).copy()
+        if (sth == _lib.STATUS_EDGE_OVERFLOW).any() or (sth == _lib.STATUS_UNSUPPORTED).any():
+            return self.solve_packed(PackedBatch(records), para, return_stats=return_stats)      # general path handles both
+        if return_stats:
+            return Th, sth, ob[B * 132:out_bytes].view(np.int32).reshape(B, _lib.STATS_STRIDE).copy()
+        return Th
 
 
 _default_solver = {}
