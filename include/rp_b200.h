@@ -212,6 +212,14 @@ int rp_conv_layer(const rp_conv_desc* d, void* stream);
 int rp_bn_finalize(const float* psum, const float* psq, int G, int nparts, int Cout, int count,
                    const float* gamma, const float* beta, float* scale, float* shift, int sstride, int s_off,
                    void* stream);
+/* same for very long partial lists (Resnet18_8s: the BatchNorm batch is the whole call): nsplit row slices summed in
+ * float64 into scratch [G, nsplit, Cout, 2] doubles, then combined in order */
+int rp_bn_finalize_split(const float* psum, const float* psq, int G, int nparts, int Cout, int count,
+                         const float* gamma, const float* beta, float* scale, float* shift, int sstride, int s_off,
+                         int nsplit, double* scratch, void* stream);
+/* im2col of NHWC float32 [n,H,W,C] into bfloat16 rows [n,Hout,Wout,Kpad] (K = (ky*k+kx)*C + c, zero padded): the 7x7/s2
+ * stem of Resnet18_8s (mymodel.py:51-54,85) becomes a 1x1 convolution with K = 352 on the tensor cores */
+int rp_im2col_bf16(const float* x, int n, int H, int W, int C, int k, int s, int p, int Hout, int Wout, int Kpad, void* out, void* stream);
 /* F.upsample(x,[224,224],'bilinear',align_corners=False) (mymodel.py:261) fused with the channel regrouping of
  * mymodel.py:264-286: in [n,16,H,W] NCHW -> out [n,224,224,20] NHWC = (rgb,mask | normal,mask | depth,mask) x (own, warped) */
 int rp_scnet_resize_in(const float* x, int n, int H, int W, float* out, void* stream);

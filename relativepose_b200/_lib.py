@@ -58,7 +58,7 @@ class RpConvDesc(ctypes.Structure):
 
 EXPORTS = ("rp_abi_version", "rp_device_info", "rp_solve_workspace_bytes", "rp_solve_batch",
            "rp_solve_batch_ex", "rp_match_topk", "rp_launch_count", "rp_spectral_irls_solve", "rp_spectral_irls_workspace_bytes",
-           "rp_conv_nparts", "rp_conv_layer", "rp_bn_finalize", "rp_scnet_resize_in", "rp_scnet_resize_in_split", "rp_scnet_resize_out", "rp_scnet_resize_out_map",
+           "rp_conv_nparts", "rp_conv_layer", "rp_bn_finalize", "rp_bn_finalize_split", "rp_im2col_bf16", "rp_scnet_resize_in", "rp_scnet_resize_in_split", "rp_scnet_resize_out", "rp_scnet_resize_out_map",
            "rp_conv_launch_count", "rp_tc_gemm_test", "rp_conv_nparts_tc", "rp_conv_layer_tc",
            "rp_conv_halo_plan", "rp_conv_layer_halo", "rp_conv_halo_debug",
            "rp_gather_primitives", "rp_match_sample_workspace_bytes", "rp_match_sample", "rp_heat_sample", "rp_warp_workspace_bytes", "rp_warp_views", "rp_pano2pc", "rp_blend_completion",
@@ -107,6 +107,10 @@ def load():
     lib.rp_conv_layer.argtypes = [ctypes.POINTER(RpConvDesc), vp]
     lib.rp_bn_finalize.restype = i32
     lib.rp_bn_finalize.argtypes = [vp, vp, i32, i32, i32, i32, vp, vp, vp, vp, i32, i32, vp]
+    lib.rp_bn_finalize_split.restype = i32
+    lib.rp_bn_finalize_split.argtypes = [vp, vp, i32, i32, i32, i32, vp, vp, vp, vp, i32, i32, i32, vp, vp]
+    lib.rp_im2col_bf16.restype = i32
+    lib.rp_im2col_bf16.argtypes = [vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp, vp]
     lib.rp_scnet_resize_in.restype = i32
     lib.rp_scnet_resize_in.argtypes = [vp, i32, i32, i32, vp, vp]
     lib.rp_scnet_resize_in_split.restype = i32

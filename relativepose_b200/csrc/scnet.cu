@@ -193,6 +193,82 @@ __global__ void __launch_bounds__(1024) bn_finalize_kernel(const float* __restri
     }
 }
 
+// Two-stage variant for very long partial lists (Resnet18_8s: one BatchNorm batch = the whole call, 12 800+ tile rows):
+// stage 1 sums row slices in float64 (grid.z slices), stage 2 combines the slices in order and finalises.
+__global__ void __launch_bounds__(1024) bn_partial_kernel(const float* __restrict__ psum, const float* __restrict__ psq, int nparts, int Cout,
+                                                          int nsplit, double* __restrict__ scratch) {
+    __shared__ double rs[32][33], rq[32][33];
+    const int g = blockIdx.y, z = blockIdx.z;
+    const int cl = threadIdx.x & 31, rl = threadIdx.x >> 5;
+    const int c = blockIdx.x * 32 + cl;
+    const int per = (nparts + nsplit - 1) / nsplit, r0 = z * per, r1 = min(nparts, r0 + per);
+    double s = 0.0, q = 0.0;
+    if (c < Cout) {
+        const float* ps = psum + (size_t)g * nparts * Cout + c;
+        const float* pq = psq + (size_t)g * nparts * Cout + c;
+#pragma unroll 4
+        for (int r = r0 + rl; r < r1; r += 32) { s += (double)ps[(size_t)r * Cout]; q += (double)pq[(size_t)r * Cout]; }
+    }
+    rs[rl][cl] = s; rq[rl][cl] = q;
+    __syncthreads();
+    if (rl == 0 && c < Cout) {
+        s = 0.0; q = 0.0;
+#pragma unroll
+        for (int r = 0; r < 32; ++r) { s += rs[r][cl]; q += rq[r][cl]; }
+        scratch[(((size_t)g * nsplit + z) * Cout + c) * 2] = s;
+        scratch[(((size_t)g * nsplit + z) * Cout + c) * 2 + 1] = q;
+    }
+}
+
+__global__ void bn_combine_kernel(const double* __restrict__ scratch, int nsplit, int Cout, int count, const float* __restrict__ gamma,
+                                  const float* __restrict__ beta, float* __restrict__ scale, float* __restrict__ shift, int sstride, int s_off) {
+    const int g = blockIdx.y, c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= Cout) return;
+    double s = 0.0, q = 0.0;
+    for (int z = 0; z < nsplit; ++z) { s += scratch[(((size_t)g * nsplit + z) * Cout + c) * 2]; q += scratch[(((size_t)g * nsplit + z) * Cout + c) * 2 + 1]; }
+    const double mean = s / count;
+    double var = q / count - mean * mean;
+    if (var < 0.0) var = 0.0;
+    const double sc = (double)gamma[c] / sqrt(var + BN_EPS);
+    scale[(size_t)g * sstride + s_off + c] = (float)sc;
+    shift[(size_t)g * sstride + s_off + c] = (float)((double)beta[c] - mean * sc);
+}
+
+// im2col of an NHWC float32 image batch into bf16 rows [n, Hout, Wout, Kpad], K index = (ky*k + kx)*C + c, zero padded to
+// Kpad (multiple of 32) and outside the image: turns the 7x7/s2 stem of Resnet18_8s (Cin = 7, 49 taps -- too many taps
+// and too few channels for the halo kernel's per-tap K chunks) into a 1x1 convolution with K = 352 on tcgen05.
+__global__ void __launch_bounds__(256) im2col_bf16_kernel(const float* __restrict__ x, int n, int H, int W, int C, int k, int s, int p,
+                                                          int Hout, int Wout, int Kpad, __nv_bfloat16* __restrict__ out) {
+    __shared__ int s_tab[1024];                    // K index -> (ky << 20 | kx << 10 | c), -1 = padding (Kpad <= 1024)
+    for (int kk = threadIdx.x; kk < Kpad; kk += blockDim.x) {
+        int e = -1;
+        if (kk < k * k * C) { const int tap = kk / C, c = kk - tap * C; const int ky = tap / k, kx = tap - ky * k; e = (ky << 20) | (kx << 10) | c; }
+        s_tab[kk] = e;
+    }
+    __syncthreads();
+    const int units = Kpad / 8;
+    // one block = 256 consecutive (pixel, 8-K unit) items: the unit index runs fastest, so a warp writes 512 contiguous bytes
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t total = (size_t)n * Hout * Wout * units;
+    if (idx >= total) return;
+    const int u = (int)(idx % units);
+    const size_t pix = idx / units;
+    const int ox = (int)(pix % Wout); const int oy = (int)((pix / Wout) % Hout); const int im = (int)(pix / ((size_t)Wout * Hout));
+    const int iy0 = oy * s - p, ix0 = ox * s - p;
+    const float* xb = x + (size_t)im * H * W * C;
+    float f[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int e = s_tab[u * 8 + j];
+        const int iy = iy0 + (e >> 20), ix = ix0 + ((e >> 10) & 1023);
+        f[j] = (e >= 0 && iy >= 0 && iy < H && ix >= 0 && ix < W) ? __ldg(xb + ((size_t)iy * W + ix) * C + (e & 1023)) : 0.f;
+    }
+    __nv_bfloat162 v[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) v[j] = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
+    *reinterpret_cast<uint4*>(out + idx * 8) = *reinterpret_cast<uint4*>(v);
+}
+
 // ATen upsample_bilinear2d, align_corners=False: src = (dst+0.5)*scale-0.5 clamped at 0, scale = in/out in float.
 __device__ __forceinline__ void bilin_coord(int d, float scale, int in_size, int& i0, int& i1, float& l0, float& l1) {
     float r = scale * ((float)d + 0.5f) - 0.5f;
@@ -413,15 +489,24 @@ __global__ void bn_relu_maxpool_kernel(const float* __restrict__ in, int n, int 
 __global__ void bn_add_relu_kernel(const float* __restrict__ a, const float* __restrict__ sa, const float* __restrict__ ha,
                                    const float* __restrict__ b, const float* __restrict__ sb, const float* __restrict__ hb,
                                    float* __restrict__ out, int n, int HW, int C, int gsz) {
-    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const size_t total = (size_t)n * HW * C;
-    if (idx >= total) return;
+    // 4 channels per thread (C % 4 == 0): float4 loads / stores, HBM-bound
+    const size_t i4 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t total4 = (size_t)n * HW * C / 4;
+    if (i4 >= total4) return;
+    const size_t idx = i4 * 4;
     const int c = (int)(idx % C);
     const int g = (int)(idx / ((size_t)C * HW)) / gsz;
-    float x = fmaf(a[idx], sa[(size_t)g * C + c], ha[(size_t)g * C + c]);
-    float y = sb ? fmaf(b[idx], sb[(size_t)g * C + c], hb[(size_t)g * C + c]) : b[idx];
-    float z = x + y;
-    out[idx] = z > 0.f ? z : 0.f;
+    const float4 av = *reinterpret_cast<const float4*>(a + idx), bv = *reinterpret_cast<const float4*>(b + idx);
+    const float4 s1 = *reinterpret_cast<const float4*>(sa + (size_t)g * C + c), h1 = *reinterpret_cast<const float4*>(ha + (size_t)g * C + c);
+    float4 y = bv;
+    if (sb) {
+        const float4 s2 = *reinterpret_cast<const float4*>(sb + (size_t)g * C + c), h2 = *reinterpret_cast<const float4*>(hb + (size_t)g * C + c);
+        y.x = fmaf(bv.x, s2.x, h2.x); y.y = fmaf(bv.y, s2.y, h2.y); y.z = fmaf(bv.z, s2.z, h2.z); y.w = fmaf(bv.w, s2.w, h2.w);
+    }
+    float4 o;
+    o.x = fmaxf(fmaf(av.x, s1.x, h1.x) + y.x, 0.f); o.y = fmaxf(fmaf(av.y, s1.y, h1.y) + y.y, 0.f);
+    o.z = fmaxf(fmaf(av.z, s1.z, h1.z) + y.z, 0.f); o.w = fmaxf(fmaf(av.w, s1.w, h1.w) + y.w, 0.f);
+    *reinterpret_cast<float4*>(out + idx) = o;
 }
 
 __global__ void resize_nhwc_kernel(const float* __restrict__ src, int n, int Hs, int Ws, int C, float* __restrict__ dst,
@@ -668,6 +753,28 @@ int rp_bn_finalize(const float* psum, const float* psq, int G, int nparts, int C
     return cudaGetLastError() == cudaSuccess ? RP_OK : RP_ERR_CUDA;
 }
 
+int rp_bn_finalize_split(const float* psum, const float* psq, int G, int nparts, int Cout, int count,
+                         const float* gamma, const float* beta, float* scale, float* shift, int sstride, int s_off,
+                         int nsplit, double* scratch, void* stream_) {
+    if (!psum || !psq || !gamma || !beta || !scale || !shift || !scratch || G < 1 || nparts < 1 || Cout < 1 || nsplit < 1) return RP_ERR_INVALID_ARG;
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    dim3 g1((Cout + 31) / 32, G, nsplit);
+    bn_partial_kernel<<<g1, 1024, 0, stream>>>(psum, psq, nparts, Cout, nsplit, scratch);
+    dim3 g2((Cout + 127) / 128, G);
+    bn_combine_kernel<<<g2, 128, 0, stream>>>(scratch, nsplit, Cout, count, gamma, beta, scale, shift, sstride, s_off);
+    g_conv_launches += 2;
+    return cudaGetLastError() == cudaSuccess ? RP_OK : RP_ERR_CUDA;
+}
+
+int rp_im2col_bf16(const float* x, int n, int H, int W, int C, int k, int s, int p, int Hout, int Wout, int Kpad, void* out, void* stream_) {
+    if (!x || !out || n < 1 || C < 1 || C > 1023 || k < 1 || k > 31 || s < 1 || Kpad < k * k * C || (Kpad % 8) || Kpad > 1024) return RP_ERR_INVALID_ARG;
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    const size_t total = (size_t)n * Hout * Wout * (Kpad / 8);
+    im2col_bf16_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(x, n, H, W, C, k, s, p, Hout, Wout, Kpad, static_cast<__nv_bfloat16*>(out));
+    ++g_conv_launches;
+    return cudaGetLastError() == cudaSuccess ? RP_OK : RP_ERR_CUDA;
+}
+
 int rp_scnet_resize_in(const float* x, int n, int H, int W, float* out, void* stream_) {
     if (!x || !out || n < 1) return RP_ERR_INVALID_ARG;
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
@@ -718,7 +825,8 @@ int rp_bn_add_relu(const float* a, const float* sa, const float* ha, const float
                    float* out, int n, int HW, int C, int imgs_per_group, void* stream_) {
     if (!a || !sa || !ha || !b || !out || n < 1 || imgs_per_group < 1) return RP_ERR_INVALID_ARG;
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
-    size_t total = (size_t)n * HW * C;
+    if (C % 4) return RP_ERR_UNSUPPORTED;
+    size_t total = (size_t)n * HW * C / 4;
     bn_add_relu_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(a, sa, ha, b, sb, hb, out, n, HW, C, imgs_per_group);
     ++g_conv_launches;
     return cudaGetLastError() == cudaSuccess ? RP_OK : RP_ERR_CUDA;

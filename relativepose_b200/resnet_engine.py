@@ -52,7 +52,21 @@ class ResnetEngine(ScnetEngine):
             xin = _Act(x.permute(0, 2, 3, 1).contiguous(), H, W, cin, 0, cin)      # NCHW -> NHWC view of the input (plumbing)
             H1, W1 = co(H, 7, 2, 3), co(W, 7, 2, 3)
             c1 = act(H1, W1, 64)
-            self._conv('resnet18_32s.conv1', [xin], c1, False, 7, 2, 3, stream=stream, bn_params=(tr.bn1.weight, tr.bn1.bias))
+            if self.mode == 'tc' and self.halo:
+                # 7x7/s2 stem (Cin = num_input): im2col into bf16 rows of K = 49*Cin padded to a multiple of 32, then a 1x1
+                # convolution on the halo kernel (the CUDA-core implicit GEMM took 58 % of the forward)
+                Kp = -(-(49 * cin) // 32) * 32
+                col = torch.empty((n, H1, W1, Kp), dtype=torch.bfloat16, device=x.device)
+                _lib.check(self.lib.rp_im2col_bf16(xin.buf.data_ptr(), n, H, W, cin, 7, 2, 3, H1, W1, Kp, col.data_ptr(), stream), "rp_im2col_bf16")
+                if 'resnet18_32s.conv1#col' not in self._packed:
+                    w = self._packed['resnet18_32s.conv1']                                   # [7,7,cin,64]
+                    wc = torch.zeros((1, 1, Kp, w.shape[3]), dtype=torch.float32, device=w.device)
+                    wc[0, 0, :49 * cin] = w.reshape(49 * cin, w.shape[3])
+                    self._packed['resnet18_32s.conv1#col'] = wc.contiguous()
+                self._conv('resnet18_32s.conv1', [_Act(col, H1, W1, Kp, 0, Kp)], c1, False, 1, 1, 0, stream=stream,
+                           bn_params=(tr.bn1.weight, tr.bn1.bias), wkey='resnet18_32s.conv1#col')
+            else:
+                self._conv('resnet18_32s.conv1', [xin], c1, False, 7, 2, 3, stream=stream, bn_params=(tr.bn1.weight, tr.bn1.bias))
             H2, W2 = co(H1, 3, 2, 1), co(W1, 3, 2, 1)
             cur = act(H2, W2, 64, bn=False)
             _lib.check(self.lib.rp_bn_relu_maxpool(c1.buf.data_ptr(), n, H1, W1, 64, n, c1.scale.data_ptr(), c1.shift.data_ptr(),

@@ -260,10 +260,21 @@ class ScnetEngine(object):
             if bn_params is None:
                 bnm = getattr(self.net, name)[1]
                 bn_params = (bnm.weight, bnm.bias)
-            _lib.check(self.lib.rp_bn_finalize(d.psum, d.psq, self._P, nparts.value, out.C, self._gsz * out.H * out.W,
-                                               bn_params[0].data_ptr(), bn_params[1].data_ptr(),
-                                               out.scale.data_ptr(), out.shift.data_ptr(), out.pitch, out.ch_off, stream),
-                       "rp_bn_finalize(%s)" % name)
+            if nparts.value >= 4096:              # one long list (Resnet18_8s): slice it over more blocks
+                nsplit = 32
+                sc = self._bufs.get('bn_scratch')
+                if sc is None or sc.numel() < self._P * nsplit * out.C * 2:
+                    sc = torch.empty((self._P * nsplit * out.C * 2,), dtype=torch.float64, device=self._dev)
+                    self._bufs['bn_scratch'] = sc
+                _lib.check(self.lib.rp_bn_finalize_split(d.psum, d.psq, self._P, nparts.value, out.C, self._gsz * out.H * out.W,
+                                                         bn_params[0].data_ptr(), bn_params[1].data_ptr(), out.scale.data_ptr(),
+                                                         out.shift.data_ptr(), out.pitch, out.ch_off, nsplit, sc.data_ptr(), stream),
+                           "rp_bn_finalize_split(%s)" % name)
+            else:
+                _lib.check(self.lib.rp_bn_finalize(d.psum, d.psq, self._P, nparts.value, out.C, self._gsz * out.H * out.W,
+                                                   bn_params[0].data_ptr(), bn_params[1].data_ptr(),
+                                                   out.scale.data_ptr(), out.shift.data_ptr(), out.pitch, out.ch_off, stream),
+                           "rp_bn_finalize(%s)" % name)
 
     # ---------------------------------------------------------------- forward
     def forward(self, x, trace=None):
