@@ -188,3 +188,19 @@ def test_large_n_sweep_end(solver):
     assert status[0] == 0 and stats[0, 0] == 2050
     assert stats[0, 2] == tr['pairs'].shape[0], "surviving pair count differs"
     assert np.linalg.norm(T[0] - To) <= T_TOL
+
+
+def test_small_batch_path_is_bitwise_the_general_path(solver):
+    """PoseSolver.solve_records sends <= 16 pairs through one staging buffer / one H2D / one D2H (_solve_small); the poses,
+    status and stats must be bit-identical to the general pinned-array path, for ragged pairs and both descriptor layouts."""
+    from relativepose_b200 import synth
+    from relativepose_b200.RPModule.rputil import opts
+    from relativepose_b200.solver import PackedBatch
+    recs = [synth.make_pair(300 + i, n, m) for i, (n, m) in enumerate(((26, 31), (40, 40), (52, 37), (3, 9), (2, 5)))]
+    recs[1] = dict(recs[1]); recs[1]['feat_src'] = np.asfortranarray(recs[1]['feat_src'])      # a transposed-view layout
+    para = opts(*synth.shipped_params('suncg')[0])
+    Ts, ss, sts = solver.solve_records(recs, para, return_stats=True)
+    Tg, sg, stg = solver.solve_packed(PackedBatch(recs), para, return_stats=True)
+    assert np.array_equal(Ts, Tg) and np.array_equal(ss, sg) and np.array_equal(sts, stg)
+    T1 = solver.solve_records(recs[:1], para)
+    assert np.array_equal(T1[0], Tg[0])
