@@ -1,8 +1,8 @@
 #!/bin/bash
 mkdir -p gpurun_out
 {
-echo "=== resnet tests"; timeout 900 python -m pytest tests/test_gpu_resnet.py tests/test_gpu_scnet.py -q -s 2>&1 | grep "final\|passed\|failed\|rror" | tail -12
-echo "=== configs[2]/[3]"; timeout 600 python scripts/bench_pipeline.py 2>&1 | tail -5
-echo "=== resnet launches"; timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv --log-file gpurun_out/resnet_launches2.csv python scripts/prof_resnet.py 64 2>&1 | tail -1
-} > gpurun_out/round_ad.log 2>&1
-tail -20 gpurun_out/round_ad.log
+echo "=== all gpu"; timeout 1500 python -m pytest tests -m gpu -q 2>&1 | tail -3
+echo "=== smoke"; timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
+echo "=== bench"; timeout 900 python bench.py 2>&1 | tail -1 > gpurun_out/bench_line_N1.json; python -c "import json; d=json.load(open('gpurun_out/bench_line_N1.json')); print(d['value'], d['per_pair_p50_ms'], d['e2e']['value'], d['cpu_baseline'])"
+} > gpurun_out/round_af.log 2>&1
+tail -12 gpurun_out/round_af.log
