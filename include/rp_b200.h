@@ -153,6 +153,20 @@ int rp_solve_batch_ex(int B, const int32_t* off_s, const int32_t* off_t,
                       double* T_out, int32_t* status, int32_t* stats,
                       int stop_after, const rp_debug* dbg, void* stream);
 
+/* Stage entry: rpmodule.py:342-472 (descriptor weights, top-k, pair enumeration, distance / angle filters, pair weight):
+ * the geometrically consistent pairs of every scan pair.  topk_idx [sum n_s, max_topk] (-1 padded), edge_rc
+ * [B, edge_cap, 2] = the two correspondence indices (source index * K + rank) of each surviving pair, edge_w [B, edge_cap];
+ * the number of pairs is stats[b*8 + 2].  `edge_cap` is the capacity of the two output arrays; the workspace is the one of
+ * rp_solve_batch with its edge_cap = 0 (worst case). */
+int rp_affinity_build(int B, const int32_t* off_s, const int32_t* off_t,
+                      const double* pc_s, const double* nrm_s, const float* feat_s, const double* w_s,
+                      const double* pc_t, const double* nrm_t, const float* feat_t, const double* w_t,
+                      int feat_dim, const rp_params* params, const int32_t* param_idx,
+                      const int32_t* zero_row_topk, const int32_t* feat_sum_order,
+                      int max_ns, int max_nt, int max_topk,
+                      int n_slots, int64_t edge_cap, void* workspace, size_t workspace_bytes,
+                      int32_t* topk_idx, int32_t* edge_rc, double* edge_w, int32_t* status, int32_t* stats, void* stream);
+
 /* Stage entry: rpmodule.py:342-375 only (dij -> wij -> row-normalise -> top-k). */
 int rp_match_topk(int B, const int32_t* off_s, const int32_t* off_t,
                   const float* feat_s, const double* w_s, const float* feat_t, const double* w_t,
@@ -303,6 +317,23 @@ int rp_heat_sample(const float* dist, int n, int H, int W, int K, int window, do
 int rp_gather_primitives(const float* feat, int C, long long feat_img_stride, const double* depth, const double* normal,
                          const double* pts, int n_img, int K, int dataset, double* pc_out, double* nn_out, float* desc_out,
                          void* stream);
+
+/* ---- A network forward as one native call (scnet_forward / resnet18_8s_forward) -----------------
+ * The host freezes the layer calls of one forward into an op list once per (input shape, weights): op i = one of the layer
+ * entry points above (`kind`) with its rp_conv_desc and/or up to 16 scalar arguments in call order (pointers and integers as
+ * 64-bit words).  rp_scnet_forward (model/mymodel.py:259-380) / rp_resnet18_8s_forward (:82-122) issue every launch on
+ * `stream`; the buffers the ops point to must stay allocated (relativepose_b200/scnet_engine.py keeps them per shape). */
+enum { RP_OP_CONV = 1, RP_OP_CONV_TC, RP_OP_CONV_HALO, RP_OP_BN_FINALIZE, RP_OP_BN_FINALIZE_SPLIT, RP_OP_RESIZE_IN,
+       RP_OP_RESIZE_IN_SPLIT, RP_OP_RESIZE_OUT_MAP, RP_OP_IM2COL, RP_OP_BN_RELU_MAXPOOL, RP_OP_BN_ADD_RELU, RP_OP_RESIZE_NHWC,
+       RP_OP_RESIZE_TO_NCHW };
+typedef struct rp_net_op {
+    int32_t kind;         /* RP_OP_* */
+    int32_t reserved;
+    rp_conv_desc conv;    /* RP_OP_CONV / _TC / _HALO */
+    uint64_t arg[16];     /* the remaining arguments of the call, in order (without the trailing stream) */
+} rp_net_op;
+int rp_scnet_forward(const rp_net_op* ops, int n_ops, void* stream);
+int rp_resnet18_8s_forward(const rp_net_op* ops, int n_ops, void* stream);
 
 int64_t rp_launch_count(void);
 int64_t rp_conv_launch_count(void);

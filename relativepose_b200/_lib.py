@@ -56,12 +56,21 @@ class RpConvDesc(ctypes.Structure):
                 ("imgs_per_group", ctypes.c_int32), ("out_dtype", ctypes.c_int32)]
 
 
+class RpNetOp(ctypes.Structure):
+    _fields_ = [("kind", ctypes.c_int32), ("reserved", ctypes.c_int32), ("conv", RpConvDesc), ("arg", ctypes.c_uint64 * 16)]
+
+
+# op kinds of rp_scnet_forward / rp_resnet18_8s_forward (include/rp_b200.h: RP_OP_*), keyed by the layer entry point
+NET_OPS = {"rp_conv_layer": 1, "rp_conv_layer_tc": 2, "rp_conv_layer_halo": 3, "rp_bn_finalize": 4, "rp_bn_finalize_split": 5,
+           "rp_scnet_resize_in": 6, "rp_scnet_resize_in_split": 7, "rp_scnet_resize_out_map": 8, "rp_im2col_bf16": 9,
+           "rp_bn_relu_maxpool": 10, "rp_bn_add_relu": 11, "rp_resize_nhwc": 12, "rp_resize_to_nchw": 13}
+
 EXPORTS = ("rp_abi_version", "rp_device_info", "rp_solve_workspace_bytes", "rp_solve_batch",
            "rp_solve_batch_ex", "rp_match_topk", "rp_launch_count", "rp_spectral_irls_solve", "rp_spectral_irls_workspace_bytes",
            "rp_conv_nparts", "rp_conv_layer", "rp_bn_finalize", "rp_bn_finalize_split", "rp_im2col_bf16", "rp_scnet_resize_in", "rp_scnet_resize_in_split", "rp_scnet_resize_out", "rp_scnet_resize_out_map",
            "rp_conv_launch_count", "rp_tc_gemm_test", "rp_conv_nparts_tc", "rp_conv_layer_tc",
            "rp_conv_halo_plan", "rp_conv_layer_halo", "rp_conv_halo_debug",
-           "rp_gather_primitives", "rp_match_sample_workspace_bytes", "rp_match_sample", "rp_heat_sample", "rp_warp_workspace_bytes", "rp_warp_views", "rp_pano2pc", "rp_blend_completion",
+           "rp_affinity_build", "rp_scnet_forward", "rp_resnet18_8s_forward", "rp_gather_primitives", "rp_match_sample_workspace_bytes", "rp_match_sample", "rp_heat_sample", "rp_warp_workspace_bytes", "rp_warp_views", "rp_pano2pc", "rp_blend_completion",
            "rp_bn_relu_maxpool", "rp_bn_add_relu", "rp_resize_nhwc", "rp_resize_to_nchw", "rp_interpolate")
 
 _lib = None
@@ -157,6 +166,13 @@ def load():
     lib.rp_heat_sample.argtypes = [vp, i32, i32, i32, i32, i32, vp, vp, ctypes.c_size_t, vp]
     lib.rp_gather_primitives.restype = i32
     lib.rp_gather_primitives.argtypes = [vp, i32, ctypes.c_longlong, vp, vp, vp, i32, i32, i32, vp, vp, vp, vp]
+    lib.rp_affinity_build.restype = i32
+    lib.rp_affinity_build.argtypes = [i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, vp, vp, vp, vp, i32, i32, i32, i32, i64, vp,
+                                      ctypes.c_size_t, vp, vp, vp, vp, vp, vp]
+    lib.rp_scnet_forward.restype = i32
+    lib.rp_scnet_forward.argtypes = [ctypes.POINTER(RpNetOp), i32, vp]
+    lib.rp_resnet18_8s_forward.restype = i32
+    lib.rp_resnet18_8s_forward.argtypes = [ctypes.POINTER(RpNetOp), i32, vp]
     lib.rp_tc_gemm_test.restype = i32
     lib.rp_tc_gemm_test.argtypes = [vp, vp, vp, i32, i32, i32, i32, vp]
     if lib.rp_abi_version() != 1:

@@ -1575,7 +1575,7 @@ int rp_solve_batch_ex(int B, const int32_t* off_s, const int32_t* off_t,
                       int stop_after, const rp_debug* dbg, void* stream_) {
     if (B < 0 || !off_s || !off_t || !feat_s || !feat_t || !w_s || !w_t || !params || !workspace || !status)
         return RP_ERR_INVALID_ARG;
-    if (stop_after != RP_STAGE_TOPK && !T_out) return RP_ERR_INVALID_ARG;
+    if (stop_after == RP_STAGE_SOLVE && !T_out) return RP_ERR_INVALID_ARG;
     if (stop_after != RP_STAGE_TOPK && (!pc_s || !pc_t || !nrm_s || !nrm_t)) return RP_ERR_INVALID_ARG;
     if (stop_after < RP_STAGE_TOPK || stop_after > RP_STAGE_SOLVE) return RP_ERR_INVALID_ARG;
     if (max_topk > RP_MAX_TOPK || max_topk < 1 || feat_dim < 1 || feat_dim > RP_MAX_FEAT_DIM) return RP_ERR_UNSUPPORTED;
@@ -1649,6 +1649,23 @@ int rp_match_topk(int B, const int32_t* off_s, const int32_t* off_t,
     return rp_solve_batch_ex(B, off_s, off_t, nullptr, nullptr, feat_s, w_s, nullptr, nullptr, feat_t, w_t, feat_dim,
                              params, param_idx, zero_row_topk, feat_sum_order, max_ns, max_nt, max_topk, n_slots, 0, workspace,
                              workspace_bytes, nullptr, status, nullptr, RP_STAGE_TOPK, &d, stream);
+}
+
+// Stage entry rpmodule.py:342-472: the surviving (geometrically consistent) pairs and their weights.
+int rp_affinity_build(int B, const int32_t* off_s, const int32_t* off_t,
+                      const double* pc_s, const double* nrm_s, const float* feat_s, const double* w_s,
+                      const double* pc_t, const double* nrm_t, const float* feat_t, const double* w_t,
+                      int feat_dim, const rp_params* params, const int32_t* param_idx,
+                      const int32_t* zero_row_topk, const int32_t* feat_sum_order,
+                      int max_ns, int max_nt, int max_topk,
+                      int n_slots, int64_t edge_cap, void* workspace, size_t workspace_bytes,
+                      int32_t* topk_idx, int32_t* edge_rc, double* edge_w, int32_t* status, int32_t* stats, void* stream) {
+    if (!edge_rc || !edge_w || !status || edge_cap < 1) return RP_ERR_INVALID_ARG;
+    rp_debug d = {};
+    d.topk_idx = topk_idx; d.edge_rc = edge_rc; d.edge_w = edge_w; d.edge_cap = edge_cap;
+    return rp_solve_batch_ex(B, off_s, off_t, pc_s, nrm_s, feat_s, w_s, pc_t, nrm_t, feat_t, w_t, feat_dim,
+                             params, param_idx, zero_row_topk, feat_sum_order, max_ns, max_nt, max_topk, n_slots, 0, workspace,
+                             workspace_bytes, nullptr, status, stats, RP_STAGE_AFFINITY, &d, stream);
 }
 
 // Stage entry rpmodule.py:484-508 (fitters only): B problems, each a set of correspondences ("nodes": source/target

@@ -88,6 +88,11 @@ class ScnetEngine(object):
         self.halo_min = int(os.environ.get("RP_SCNET_HALO_MIN", "1"))     # smallest base-grid extent that takes the halo kernel
         act = os.environ.get("RP_SCNET_ACT", self._act_default)
         self.act_bf16 = self.mode == 'tc' and act == 'bf16'
+        # the forward as ONE native call: after a warm-up run the layer calls of a forward are frozen into an op list
+        # (rp_net_op) that rp_scnet_forward / rp_resnet18_8s_forward replays (and that the CUDA graph captures)
+        self.use_plan = os.environ.get("RP_SCNET_PLAN", "1") == "1"
+        self._rec = None
+        self._plans = {}
         self._graphs = {}
         self._seen = {}
         self.torch = torch
@@ -99,6 +104,27 @@ class ScnetEngine(object):
         self._bufs = {}
         self._P = 0
         self._dev = None
+
+    _forward_entry = "rp_scnet_forward"
+
+    def _run(self, name, *args):
+        """One layer call of the C ABI (last argument: the stream); recorded into the op list while a plan is being built."""
+        cargs = [ctypes.byref(a) if isinstance(a, _lib.RpConvDesc) else a for a in args]
+        _lib.check(getattr(self.lib, name)(*cargs), name)
+        if self._rec is not None:
+            op = _lib.RpNetOp()
+            op.kind = _lib.NET_OPS[name]
+            rest = list(args[:-1])
+            if rest and isinstance(rest[0], _lib.RpConvDesc):
+                op.conv = _lib.RpConvDesc.from_buffer_copy(rest[0])
+                rest = rest[1:]
+            for i, a in enumerate(rest):
+                op.arg[i] = (0 if a is None else int(a)) & 0xFFFFFFFFFFFFFFFF
+            self._rec.append(op)
+
+    def _run_plan(self, plan):
+        ops, n = plan
+        _lib.check(getattr(self.lib, self._forward_entry)(ops, n, self.torch.cuda.current_stream().cuda_stream), self._forward_entry)
 
     # ---------------------------------------------------------------- weights
     def _pack(self):
@@ -128,6 +154,7 @@ class ScnetEngine(object):
         if self._P == P and self._dev == device and self._bufs.get('ctot') == cout_total:
             return
         n = 2 * P
+        self._plans, self._graphs, self._seen = {}, {}, {}          # they hold pointers into the buffers replaced below
         f = dict(dtype=torch.float32, device=device)
         fa = dict(dtype=torch.bfloat16 if self.act_bf16 else torch.float32, device=device)
         B = {}
@@ -250,12 +277,11 @@ class ScnetEngine(object):
         else:
             d.psum, d.psq = None, None
         if use_halo:
-            _lib.check(self.lib.rp_conv_layer_halo(ctypes.byref(d), wtc.data_ptr(), bn_tile, tk, self.halo_flags, stream),
-                       "rp_conv_layer_halo(%s)" % name)
+            self._run("rp_conv_layer_halo", d, wtc.data_ptr(), bn_tile, tk, self.halo_flags, stream)
         elif use_tc:
-            _lib.check(self.lib.rp_conv_layer_tc(ctypes.byref(d), wtc.data_ptr(), bn_tile, tk, stream), "rp_conv_layer_tc(%s)" % name)
+            self._run("rp_conv_layer_tc", d, wtc.data_ptr(), bn_tile, tk, stream)
         else:
-            _lib.check(self.lib.rp_conv_layer(ctypes.byref(d), stream), "rp_conv_layer(%s)" % name)
+            self._run("rp_conv_layer", d, stream)
         if bn:
             if bn_params is None:
                 bnm = getattr(self.net, name)[1]
@@ -266,37 +292,52 @@ class ScnetEngine(object):
                 if sc is None or sc.numel() < self._P * nsplit * out.C * 2:
                     sc = torch.empty((self._P * nsplit * out.C * 2,), dtype=torch.float64, device=self._dev)
                     self._bufs['bn_scratch'] = sc
-                _lib.check(self.lib.rp_bn_finalize_split(d.psum, d.psq, self._P, nparts.value, out.C, self._gsz * out.H * out.W,
+                self._run("rp_bn_finalize_split", d.psum, d.psq, self._P, nparts.value, out.C, self._gsz * out.H * out.W,
                                                          bn_params[0].data_ptr(), bn_params[1].data_ptr(), out.scale.data_ptr(),
-                                                         out.shift.data_ptr(), out.pitch, out.ch_off, nsplit, sc.data_ptr(), stream),
-                           "rp_bn_finalize_split(%s)" % name)
+                                                         out.shift.data_ptr(), out.pitch, out.ch_off, nsplit, sc.data_ptr(), stream)
             else:
-                _lib.check(self.lib.rp_bn_finalize(d.psum, d.psq, self._P, nparts.value, out.C, self._gsz * out.H * out.W,
+                self._run("rp_bn_finalize", d.psum, d.psq, self._P, nparts.value, out.C, self._gsz * out.H * out.W,
                                                    bn_params[0].data_ptr(), bn_params[1].data_ptr(),
-                                                   out.scale.data_ptr(), out.shift.data_ptr(), out.pitch, out.ch_off, stream),
-                           "rp_bn_finalize(%s)" % name)
+                                                   out.scale.data_ptr(), out.shift.data_ptr(), out.pitch, out.ch_off, stream)
 
     # ---------------------------------------------------------------- forward
     def forward(self, x, trace=None):
         torch = self.torch
-        if self.use_graph and trace is None and x.is_cuda and x.dim() == 4:
+        if (self.use_plan or self.use_graph) and trace is None and x.is_cuda and x.dim() == 4:
             key = (tuple(x.shape), str(x.device), self.mode, tuple((p.data_ptr(), p._version) for p in self.net.parameters()))
             ent = self._graphs.get(key)
-            if ent is not None:
+            if ent is not None:                       # CUDA-graph replay of the native forward
                 gph, xs, ys = ent
                 xs.copy_(x)
                 gph.replay()
                 return ys.clone()
-            self._seen[key] = self._seen.get(key, 0) + 1
-            if self._seen[key] == 3:              # two eager runs have warmed every buffer: capture the third
-                xs = x.contiguous().float().clone()
+            ent = self._plans.get(key)
+            if ent is not None:
+                xs, ys, plan = ent
+                if self.use_graph:                    # third call: capture the one native call into a graph
+                    with torch.cuda.device(x.device):
+                        torch.cuda.synchronize()
+                        gph = torch.cuda.CUDAGraph()
+                        with torch.cuda.graph(gph):
+                            self._run_plan(plan)
+                    self._graphs = {key: (gph, xs, ys)}
+                    xs.copy_(x)
+                    gph.replay()
+                    return ys.clone()
                 with torch.cuda.device(x.device):
-                    torch.cuda.synchronize()
-                    gph = torch.cuda.CUDAGraph()
-                    with torch.cuda.graph(gph):
-                        ys = self._forward_eager(xs, None)
-                self._graphs = {key: (gph, xs, ys)}       # one cached graph (buffers are shared between shapes)
-                gph.replay()
+                    xs.copy_(x)
+                    self._run_plan(plan)
+                return ys.clone()
+            self._seen[key] = self._seen.get(key, 0) + 1
+            if self._seen[key] == 2:                  # the first run sized every buffer: freeze the second one into a plan
+                xs = x.contiguous().float().clone()
+                self._rec = []
+                try:
+                    ys = self._forward_eager(xs, None)
+                    rec = self._rec
+                finally:
+                    self._rec = None
+                self._plans = {key: (xs, ys, ((_lib.RpNetOp * len(rec))(*rec), len(rec)))}     # one plan: buffers are shared between shapes
                 return ys.clone()
         return self._forward_eager(x, trace)
 
@@ -319,7 +360,7 @@ class ScnetEngine(object):
             stream = torch.cuda.current_stream().cuda_stream
             split_stem = self.act_bf16 and self.halo     # conv1* on tcgen05 from the bf16 hi/lo split input
             if split_stem:
-                _lib.check(self.lib.rp_scnet_resize_in_split(x.data_ptr(), n, H, W, B['in96'].buf.data_ptr(), stream), "resize_in_split")
+                self._run("rp_scnet_resize_in_split", x.data_ptr(), n, H, W, B['in96'].buf.data_ptr(), stream)
                 for st in ('rgb', 'n', 'd'):
                     if 'conv1' + st + '#split' not in self._packed:
                         w = self._packed['conv1' + st]                          # [3,3,cin,32]
@@ -330,7 +371,7 @@ class ScnetEngine(object):
                         ws[:, :, 0:c], ws[:, :, 4:4 + c], ws[:, :, 8:8 + c] = hi, hi, lo   # x [hi|lo|hi|0] . w [hi|hi|lo|0]
                         self._packed['conv1' + st + '#split'] = ws.contiguous()
             else:
-                _lib.check(self.lib.rp_scnet_resize_in(x.data_ptr(), n, H, W, B['in20'].buf.data_ptr(), stream), "resize_in")
+                self._run("rp_scnet_resize_in", x.data_ptr(), n, H, W, B['in20'].buf.data_ptr(), stream)
             chan = {'rgb': (0, 4), 'n': (4, 4), 'd': (8, 2)}
             xin_slot = {'rgb': 0, 'rgb_t2s': 128, 'n': 256, 'n_t2s': 384, 'd': 512, 'd_t2s': 640}
             for wh, base in (('', 0), ('_t2s', 10)):
@@ -370,8 +411,8 @@ class ScnetEngine(object):
                 self._conv('deconv1' + st, [B['d2' + st]], B['out224'].view(o, c), False, 1, 1, 0, bn=False,
                            bias=getattr(net, 'deconv1' + st).bias, tanh=(st == 'f' and bool(net.useTanh)), stream=stream)
             out = torch.empty((n, ctot, H, W), dtype=torch.float32, device=x.device)
-            _lib.check(self.lib.rp_scnet_resize_out_map(B['out224'].buf.data_ptr(), n, B['out224'].pitch, B['cmap'].data_ptr(), ctot, H, W,
-                                                        out.data_ptr(), stream), "resize_out")
+            self._run("rp_scnet_resize_out_map", B['out224'].buf.data_ptr(), n, B['out224'].pitch, B['cmap'].data_ptr(), ctot, H, W,
+                                                        out.data_ptr(), stream)
             if trace is not None:
                 self._dump(trace)
         return out

@@ -1,8 +1,6 @@
 #!/bin/bash
 mkdir -p gpurun_out
 {
-echo "=== all gpu"; timeout 1500 python -m pytest tests -m gpu -q 2>&1 | tail -3
-echo "=== smoke"; timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
-echo "=== bench"; timeout 900 python bench.py 2>&1 | tail -1 > gpurun_out/bench_line_N1.json; python -c "import json; d=json.load(open('gpurun_out/bench_line_N1.json')); print(d['value'], d['per_pair_p50_ms'], d['e2e']['value'], d['cpu_baseline'])"
-} > gpurun_out/round_af.log 2>&1
-tail -12 gpurun_out/round_af.log
+echo "=== plan tests"; timeout 900 python -m pytest tests/test_gpu_plan.py tests/test_gpu_solver.py -q 2>&1 | tail -5
+} > gpurun_out/round_ah.log 2>&1
+tail -30 gpurun_out/round_ah.log
