@@ -237,36 +237,53 @@ __global__ void bn_combine_kernel(const double* __restrict__ scratch, int nsplit
 // im2col of an NHWC float32 image batch into bf16 rows [n, Hout, Wout, Kpad], K index = (ky*k + kx)*C + c, zero padded to
 // Kpad (multiple of 32) and outside the image: turns the 7x7/s2 stem of Resnet18_8s (Cin = 7, 49 taps -- too many taps
 // and too few channels for the halo kernel's per-tap K chunks) into a 1x1 convolution with K = 352 on tcgen05.
+constexpr int IC_PX = 32;                          // output pixels (one row segment) per block
+constexpr int IC_ROW = 512;                        // floats per staged input row: (IC_PX*s + k - s) * C <= IC_ROW
 __global__ void __launch_bounds__(256) im2col_bf16_kernel(const float* __restrict__ x, int n, int H, int W, int C, int k, int s, int p,
                                                           int Hout, int Wout, int Kpad, __nv_bfloat16* __restrict__ out) {
-    __shared__ int s_tab[1024];                    // K index -> (ky << 20 | kx << 10 | c), -1 = padding (Kpad <= 1024)
-    for (int kk = threadIdx.x; kk < Kpad; kk += blockDim.x) {
+    // One block = 32 consecutive output pixels of one output row: the k input rows they read are staged in shared memory
+    // once (coalesced), every (pixel, 8-K unit) item is then assembled from shared memory and written as one 16-byte store
+    // (a warp writes 512 contiguous bytes).  Without the staging the kernel re-reads its input ~12x through L2.
+    __shared__ int s_tab[1024];                    // K index -> offset ky*IC_ROW + kx*C + c into the staged rows, -1 = padding
+    __shared__ float patch[7 * IC_ROW];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int kk = tid; kk < Kpad; kk += 256) {
         int e = -1;
-        if (kk < k * k * C) { const int tap = kk / C, c = kk - tap * C; const int ky = tap / k, kx = tap - ky * k; e = (ky << 20) | (kx << 10) | c; }
+        if (kk < k * k * C) { const int tap = kk / C, c = kk - tap * C; const int ky = tap / k, kx = tap - ky * k; e = ky * IC_ROW + kx * C + c; }
         s_tab[kk] = e;
+    }
+    const int segs = (Wout + IC_PX - 1) / IC_PX;
+    const int seg = blockIdx.x % segs;
+    const int oy = (blockIdx.x / segs) % Hout;
+    const int im = blockIdx.x / (segs * Hout);
+    const int ox0 = seg * IC_PX;
+    const int pwc = (IC_PX * s + k - s) * C;       // floats of one staged row: contiguous in NHWC memory
+    const int iy0 = oy * s - p, g0 = (ox0 * s - p) * C;
+    const float* xb = x + (size_t)im * H * W * C;
+    for (int r = 0; r < k; ++r) {
+        const int iy = iy0 + r;
+        const float* row = xb + (size_t)iy * W * C;
+        for (int q = tid; q < pwc; q += 256) {
+            const int gidx = g0 + q;
+            patch[r * IC_ROW + q] = (iy >= 0 && iy < H && gidx >= 0 && gidx < W * C) ? __ldg(row + gidx) : 0.f;
+        }
     }
     __syncthreads();
     const int units = Kpad / 8;
-    // one block = 256 consecutive (pixel, 8-K unit) items: the unit index runs fastest, so a warp writes 512 contiguous bytes
-    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const size_t total = (size_t)n * Hout * Wout * units;
-    if (idx >= total) return;
-    const int u = (int)(idx % units);
-    const size_t pix = idx / units;
-    const int ox = (int)(pix % Wout); const int oy = (int)((pix / Wout) % Hout); const int im = (int)(pix / ((size_t)Wout * Hout));
-    const int iy0 = oy * s - p, ix0 = ox * s - p;
-    const float* xb = x + (size_t)im * H * W * C;
-    float f[8];
+    for (int px = warp; px < IC_PX; px += 8) {     // a warp owns a pixel, its lanes the 8-K units: 512 contiguous bytes per store
+        if (ox0 + px >= Wout) break;
+        const float* pp = patch + px * s * C;
+        __nv_bfloat16* orow = out + (((size_t)im * Hout + oy) * Wout + ox0 + px) * Kpad;
+        for (int u = lane; u < units; u += 32) {
+            float f[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        const int e = s_tab[u * 8 + j];
-        const int iy = iy0 + (e >> 20), ix = ix0 + ((e >> 10) & 1023);
-        f[j] = (e >= 0 && iy >= 0 && iy < H && ix >= 0 && ix < W) ? __ldg(xb + ((size_t)iy * W + ix) * C + (e & 1023)) : 0.f;
+            for (int j = 0; j < 8; ++j) { const int e = s_tab[u * 8 + j]; f[j] = e >= 0 ? pp[e] : 0.f; }
+            __nv_bfloat162 v[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) v[j] = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
+            *reinterpret_cast<uint4*>(orow + u * 8) = *reinterpret_cast<uint4*>(v);
+        }
     }
-    __nv_bfloat162 v[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) v[j] = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
-    *reinterpret_cast<uint4*>(out + idx * 8) = *reinterpret_cast<uint4*>(v);
 }
 
 // ATen upsample_bilinear2d, align_corners=False: src = (dst+0.5)*scale-0.5 clamped at 0, scale = in/out in float.
@@ -769,8 +786,9 @@ int rp_bn_finalize_split(const float* psum, const float* psq, int G, int nparts,
 int rp_im2col_bf16(const float* x, int n, int H, int W, int C, int k, int s, int p, int Hout, int Wout, int Kpad, void* out, void* stream_) {
     if (!x || !out || n < 1 || C < 1 || C > 1023 || k < 1 || k > 31 || s < 1 || Kpad < k * k * C || (Kpad % 8) || Kpad > 1024) return RP_ERR_INVALID_ARG;
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
-    const size_t total = (size_t)n * Hout * Wout * (Kpad / 8);
-    im2col_bf16_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(x, n, H, W, C, k, s, p, Hout, Wout, Kpad, static_cast<__nv_bfloat16*>(out));
+    if (k > 7 || (IC_PX * s + k - s) * C > IC_ROW) return RP_ERR_UNSUPPORTED;
+    const size_t blocks = (size_t)n * Hout * ((Wout + IC_PX - 1) / IC_PX);
+    im2col_bf16_kernel<<<(unsigned)blocks, 256, 0, stream>>>(x, n, H, W, C, k, s, p, Hout, Wout, Kpad, static_cast<__nv_bfloat16*>(out));
     ++g_conv_launches;
     return cudaGetLastError() == cudaSuccess ? RP_OK : RP_ERR_CUDA;
 }

@@ -61,3 +61,22 @@ def test_resnet_module_surface():
     assert 'resnet18_32s.layer2.0.downsample.0.weight' in keys and 'score_8s.bias' in keys and 'resnet18_32s.bn1.running_mean' in keys
     with pytest.raises(RuntimeError):
         net(torch.zeros(2, 7, 32, 128))
+
+
+def test_im2col_bf16_matches_unfold():
+    """rp_im2col_bf16 (the Resnet18_8s stem's patch matrix) against torch's unfold, K order (ky, kx, c), zero padded."""
+    import torch
+    import torch.nn.functional as F
+    from relativepose_b200 import _lib
+    lib = _lib.load()
+    n, H, W, C, k, s, p = 3, 37, 70, 7, 7, 2, 3
+    Ho, Wo = (H + 2 * p - k) // s + 1, (W + 2 * p - k) // s + 1
+    Kp = -(-(k * k * C) // 32) * 32
+    x = torch.randn((n, C, H, W), device='cuda')
+    xin = x.permute(0, 2, 3, 1).contiguous()
+    out = torch.full((n, Ho, Wo, Kp), 7.0, dtype=torch.bfloat16, device='cuda')
+    _lib.check(lib.rp_im2col_bf16(xin.data_ptr(), n, H, W, C, k, s, p, Ho, Wo, Kp, out.data_ptr(), torch.cuda.current_stream().cuda_stream), "im2col")
+    cols = F.unfold(x, k, padding=p, stride=s)                                   # [n, C*k*k, Ho*Wo], K order (c, ky, kx)
+    ref = cols.view(n, C, k * k, Ho, Wo).permute(0, 3, 4, 2, 1).reshape(n, Ho, Wo, k * k * C)
+    assert torch.equal(out[..., :k * k * C].float(), ref.to(torch.bfloat16).float())
+    assert torch.all(out[..., k * k * C:] == 0)
