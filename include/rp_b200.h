@@ -272,7 +272,8 @@ int rp_bn_add_relu(const float* a, const float* sa, const float* ha, const float
                    float* out, int n, int HW, int C, int imgs_per_group, void* stream);
 /* F.upsample(src, size, 'bilinear', align_corners=False) on NHWC: dst = (accumulate ? dst : 0) + up(src) */
 int rp_resize_nhwc(const float* src, int n, int Hs, int Ws, int C, float* dst, int Hd, int Wd, int accumulate, void* stream);
-/* final F.upsample to the input size + optional tanh, NHWC [n,Hs,Ws,C] -> NCHW [n,C,H,W] (mymodel.py:111,120-121) */
+/* final F.upsample to the input size + optional tanh (tanh_out 1 = tanhf, 2 = tanh.approx.f32 for the bf16 tensor-core mode),
+ * NHWC [n,Hs,Ws,C] -> NCHW [n,C,H,W] (mymodel.py:111,120-121) */
 int rp_resize_to_nchw(const float* src, int n, int Hs, int Ws, int C, float* out, int H, int W, int tanh_out, void* stream);
 
 /* rputil.interpolate (RPModule/rputil.py:43-58): feat [C,H,W], pt [K,2] normalised (x,y) -> out [C,K]; device float32 */

@@ -481,26 +481,32 @@ __global__ void __launch_bounds__(128) conv3x3_small_cin(const ConvArgs A) {
 __global__ void bn_relu_maxpool_kernel(const float* __restrict__ in, int n, int H, int W, int C, int gsz,
                                        const float* __restrict__ scale, const float* __restrict__ shift,
                                        float* __restrict__ out, int Ho, int Wo) {
-    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const size_t total = (size_t)n * Ho * Wo * C;
-    if (idx >= total) return;
-    const int c = (int)(idx % C); const int ox = (int)((idx / C) % Wo); const int oy = (int)((idx / ((size_t)C * Wo)) % Ho);
-    const int im = (int)(idx / ((size_t)C * Wo * Ho));
+    // 4 channels per thread (C % 4 == 0): float4 loads / stores
+    const size_t i4 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int C4 = C / 4;
+    const size_t total = (size_t)n * Ho * Wo * C4;
+    if (i4 >= total) return;
+    const int c = (int)(i4 % C4) * 4; const int ox = (int)((i4 / C4) % Wo); const int oy = (int)((i4 / ((size_t)C4 * Wo)) % Ho);
+    const int im = (int)(i4 / ((size_t)C4 * Wo * Ho));
     const int g = im / gsz;
-    const float sc = scale ? scale[(size_t)g * C + c] : 1.f, sh = shift ? shift[(size_t)g * C + c] : 0.f;
-    float m = -INFINITY;
+    float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (scale) sc = *reinterpret_cast<const float4*>(scale + (size_t)g * C + c);
+    if (shift) sh = *reinterpret_cast<const float4*>(shift + (size_t)g * C + c);
+    float4 m = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+#pragma unroll
     for (int ky = 0; ky < 3; ++ky) {
         const int iy = oy * 2 - 1 + ky;
         if (iy < 0 || iy >= H) continue;
+#pragma unroll
         for (int kx = 0; kx < 3; ++kx) {
             const int ix = ox * 2 - 1 + kx;
             if (ix < 0 || ix >= W) continue;
-            float v = fmaf(in[(((size_t)im * H + iy) * W + ix) * C + c], sc, sh);
-            v = v > 0.f ? v : 0.f;
-            m = fmaxf(m, v);
+            const float4 v = *reinterpret_cast<const float4*>(in + (((size_t)im * H + iy) * W + ix) * C + c);
+            m.x = fmaxf(m.x, fmaxf(fmaf(v.x, sc.x, sh.x), 0.f)); m.y = fmaxf(m.y, fmaxf(fmaf(v.y, sc.y, sh.y), 0.f));
+            m.z = fmaxf(m.z, fmaxf(fmaf(v.z, sc.z, sh.z), 0.f)); m.w = fmaxf(m.w, fmaxf(fmaf(v.w, sc.w, sh.w), 0.f));
         }
     }
-    out[idx] = m;
+    *reinterpret_cast<float4*>(out + i4 * 4) = m;
 }
 
 __global__ void bn_add_relu_kernel(const float* __restrict__ a, const float* __restrict__ sa, const float* __restrict__ ha,
@@ -557,7 +563,10 @@ __global__ void resize_to_nchw_kernel(const float* __restrict__ src, int n, int 
     float* o = out + (size_t)im * C * H * W + (size_t)oy * W + ox;
     for (int c = 0; c < C; ++c) {
         float v = ly0 * (lx0 * p00[c] + lx1 * p01[c]) + ly1 * (lx0 * p10[c] + lx1 * p11[c]);
-        o[(size_t)c * H * W] = tanh_out ? tanhf(v) : v;
+        float y = v;
+        if (tanh_out == 1) y = tanhf(v);
+        else if (tanh_out == 2) asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(v));      // tensor-core mode: error ~5e-4, far below bf16
+        o[(size_t)c * H * W] = y;
     }
 }
 
@@ -833,7 +842,8 @@ int rp_bn_relu_maxpool(const float* in, int n, int H, int W, int C, int imgs_per
                        const float* scale, const float* shift, float* out, int Ho, int Wo, void* stream_) {
     if (!in || !out || n < 1 || imgs_per_group < 1) return RP_ERR_INVALID_ARG;
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
-    size_t total = (size_t)n * Ho * Wo * C;
+    if (C % 4) return RP_ERR_UNSUPPORTED;
+    size_t total = (size_t)n * Ho * Wo * C / 4;
     bn_relu_maxpool_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(in, n, H, W, C, imgs_per_group, scale, shift, out, Ho, Wo);
     ++g_conv_launches;
     return cudaGetLastError() == cudaSuccess ? RP_OK : RP_ERR_CUDA;

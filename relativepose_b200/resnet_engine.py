@@ -157,5 +157,5 @@ class ResnetEngine(ScnetEngine):
             self._run("rp_resize_nhwc", s16.buf.data_ptr(), n, s16.H, s16.W, 32, s8.buf.data_ptr(), s8.H, s8.W, 1, stream)
             out = torch.empty((n, 32, H, W), **f)
             self._run("rp_resize_to_nchw", s8.buf.data_ptr(), n, s8.H, s8.W, 32, out.data_ptr(), H, W,
-                                                  int(bool(net.args.useTanh)), stream)
+                                                  (2 if self.mode == 'tc' else 1) if bool(net.args.useTanh) else 0, stream)
         return out
