@@ -122,7 +122,7 @@ def workload_config(args, n_kp, pairs):
 
 
 class ClockSampler(object):
-    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
+    Q = "timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
     def __init__(self, index=0):
@@ -136,7 +136,10 @@ class ClockSampler(object):
         except Exception:
             self.p = None
 
-    def stop(self):
+    def stop(self, window=None):
+        """window = (t0, t1) wall-clock bounds (time.time()) of the timed region: only samples inside it are used (the
+        sampler is started well before, nvidia-smi needs ~0.2 s to emit its first line); falls back to all samples."""
+        import datetime
         if self.p is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -146,20 +149,25 @@ class ClockSampler(object):
         except Exception:
             self.p.kill()
             out = ""
-        sm, mx, reasons = [], [], set()
+        rows = []
         for line in out.strip().splitlines():
             f = [x.strip() for x in line.split(",")]
             if len(f) < 9:
                 continue
             try:
-                sm.append(float(f[1])); mx.append(float(f[2]))
+                ts = datetime.datetime.strptime(f[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                rows.append((ts, float(f[1]), float(f[2]), f[5:9]))
             except ValueError:
                 continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+        inside = [r for r in rows if window and window[0] - 0.02 <= r[0] <= window[1] + 0.02]
+        use = inside if inside else rows
+        sm, mx, reasons = [r[1] for r in use], [r[2] for r in use], set()
+        for r in use:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": float(max(mx)) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "samples_in_timed_region": len(inside)}
 
 
 def algorithmic_bytes(n_s, n_t, N, power_its):
@@ -214,15 +222,18 @@ def run_cuda_arm(args):
         return x
 
     # ---------------- device-resident throughput ("value")
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()                      # before the warm-up: nvidia-smi needs a moment to emit its first sample
     for _ in range(args.warmup):
         solver.solve_device(dbatch, plist)
     barrier()
-    sampler = ClockSampler(local_rank)
     if rank == 0:
-        sampler.start()
+        time.sleep(0.3)
     launches0 = lib.rp_launch_count()
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     barrier()
+    w0 = time.time()
     t0 = time.perf_counter()
     for i in range(args.steps):
         evs[i][0].record()
@@ -230,8 +241,9 @@ def run_cuda_arm(args):
         evs[i][1].record()
     barrier()
     wall = time.perf_counter() - t0
+    w1 = time.time()
     launches = lib.rp_launch_count() - launches0
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop((w0, w1)) if rank == 0 else None
     kern_ms = [a.elapsed_time(b) for a, b in evs]
     wall = max_over_ranks(wall)
     value = world * B * args.steps / wall

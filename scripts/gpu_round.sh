@@ -1,8 +1,9 @@
 #!/bin/bash
 mkdir -p gpurun_out
 {
-echo "=== resnet tests"; timeout 900 python -m pytest tests/test_gpu_resnet.py tests/test_gpu_plan.py -q 2>&1 | tail -4
-echo "=== configs"; PAIRS=32 timeout 600 python scripts/bench_pipeline.py 2>&1 | head -1
-echo "=== resnet launches"; RP_SCNET_PLAN=0 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv --log-file gpurun_out/resnet_launches3.csv python scripts/prof_resnet.py 64 2>&1 | tail -1
-} > gpurun_out/round_ai.log 2>&1
-tail -30 gpurun_out/round_ai.log
+echo "=== all gpu"; timeout 1500 python -m pytest tests -m gpu -q 2>&1 | tail -3
+echo "=== smoke"; timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
+echo "=== bench"; timeout 900 python bench.py 2>&1 | tail -1 > gpurun_out/bench_line_N1.json; python -c "import json; d=json.load(open('gpurun_out/bench_line_N1.json')); print(d['value'], d['per_pair_p50_ms'], d['e2e']['value'], d['cpu_baseline'], d['clocks'])"
+echo "=== time scnet"; timeout 300 python scripts/time_scnet.py 1 8 32 2>&1 | tail -3
+} > gpurun_out/round_final3.log 2>&1
+tail -12 gpurun_out/round_final3.log
