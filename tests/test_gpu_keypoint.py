@@ -60,3 +60,16 @@ def test_get_keypoint_no_detections():
     f = torch.zeros((32, 160, 640), device='cuda')
     out = rputil.getKeypoint(np.zeros((160, 640, 3), np.uint8), np.zeros((160, 640, 3), np.uint8), f, f, sift_fn=lambda g: np.zeros((0, 2)))
     assert out == (None,) * 6
+
+
+def test_match_sample_is_independent_of_the_query_batch():
+    """100 queries in one call == the same queries in chunks (queries never interact; slices are combined in index order)."""
+    import torch
+    from RPModule import rputil
+    from relativepose_b200 import synth
+    feat = torch.from_numpy(synth.make_feature_map(5)).cuda()
+    q = torch.tanh(torch.randn((32, 100), generator=torch.Generator().manual_seed(1))).cuda()
+    full = rputil.match_sample(q, feat, 2)
+    parts = np.concatenate([rputil.match_sample(q[:, i:i + 17].contiguous(), feat, 2) for i in range(0, 100, 17)])
+    assert full.shape == (100, 2, 2) and np.array_equal(full, parts)
+    assert (full[:, 0] != full[:, 1]).any(axis=1).all()                      # the second pick lies outside the first one's window

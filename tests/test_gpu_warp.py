@@ -120,3 +120,17 @@ def test_via_completion_two_steps_gpu_warp_equals_oracle_warp():
     T_orc = RelativePoseEstimationViaCompletion(net, s, t, args, keypoint_fn=keypoints, warping_fn=oracle_warp)
     print("two-step completion: |T_gpu - T_oracle_warp| = %.3e, oracle warps used: %d" % (np.linalg.norm(T_gpu - T_orc), len(calls)))
     assert np.isfinite(T_gpu).all() and np.linalg.norm(T_gpu - T_orc) <= 1e-6
+
+
+def test_warp_batch_invariance_full_size():
+    """64 views in one call (configs[3]: 32 ScanNet pairs) == the same views one by one, bit for bit (the winner map is per
+    view; nothing crosses views)."""
+    import torch
+    from relativepose_b200 import synth, util
+    views = torch.from_numpy(np.concatenate([synth.make_warp_view(s % 5, 'scannet') for s in range(64)])).cuda()
+    Rs = np.stack([synth.make_pose(s) if s % 7 else np.eye(4) for s in range(64)])
+    big = util.warping_device(views, Rs, 'scannet')
+    for b in (0, 1, 7, 33, 63):
+        one = util.warping_device(views[b:b + 1], Rs[b:b + 1], 'scannet')
+        assert torch.equal(big[b:b + 1], one)
+    assert not big[0].any() and not big[7].any() and big[1].any()          # identity poses -> zeros (util.py:95-96)
