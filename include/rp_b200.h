@@ -289,6 +289,11 @@ int rp_interpolate(const float* feat, int C, int H, int W, const float* pt, int 
 int rp_warp_workspace_bytes(int B, size_t* bytes);
 int rp_warp_views(const float* view, const double* R, int B, int dataset, float* out, void* workspace, size_t workspace_bytes,
                   void* stream);
+/* same with explicit image strides (floats) and an optional source index: output b = view[src_index[b]] warped by R[b], written
+ * at out + b*out_img_stride -- the batched alternation warps every scan's partner straight into channels 8..15 of the network
+ * input (rpmodule.py:616-621) without materialising views[swap] or the torch.cat */
+int rp_warp_views_ex(const float* view, long long view_img_stride, const int32_t* src_index, const double* R, int B, int dataset,
+                     float* out, long long out_img_stride, void* workspace, size_t workspace_bytes, void* stream);
 /* util.Pano2PointCloud (util.py:751-811), dense: depth [B,160,640] float32 -> pc [B,3,102400] float64 in the reference's
  * point order (face, row, column); valid [B,102400] (may be NULL) = 1 where the reference keeps the point (scannet drops
  * depth == 0, the caller compacts). */

@@ -70,7 +70,7 @@ EXPORTS = ("rp_abi_version", "rp_device_info", "rp_solve_workspace_bytes", "rp_s
            "rp_conv_nparts", "rp_conv_layer", "rp_bn_finalize", "rp_bn_finalize_split", "rp_im2col_bf16", "rp_scnet_resize_in", "rp_scnet_resize_in_split", "rp_scnet_resize_out", "rp_scnet_resize_out_map",
            "rp_conv_launch_count", "rp_tc_gemm_test", "rp_conv_nparts_tc", "rp_conv_layer_tc",
            "rp_conv_halo_plan", "rp_conv_layer_halo", "rp_conv_halo_debug",
-           "rp_affinity_build", "rp_scnet_forward", "rp_resnet18_8s_forward", "rp_gather_primitives", "rp_match_sample_workspace_bytes", "rp_match_sample", "rp_heat_sample", "rp_warp_workspace_bytes", "rp_warp_views", "rp_pano2pc", "rp_blend_completion",
+           "rp_affinity_build", "rp_scnet_forward", "rp_resnet18_8s_forward", "rp_gather_primitives", "rp_match_sample_workspace_bytes", "rp_match_sample", "rp_heat_sample", "rp_warp_workspace_bytes", "rp_warp_views", "rp_warp_views_ex", "rp_pano2pc", "rp_blend_completion",
            "rp_bn_relu_maxpool", "rp_bn_add_relu", "rp_resize_nhwc", "rp_resize_to_nchw", "rp_interpolate")
 
 _lib = None
@@ -154,6 +154,8 @@ def load():
     lib.rp_warp_workspace_bytes.argtypes = [i32, ctypes.POINTER(ctypes.c_size_t)]
     lib.rp_warp_views.restype = i32
     lib.rp_warp_views.argtypes = [vp, vp, i32, i32, vp, vp, ctypes.c_size_t, vp]
+    lib.rp_warp_views_ex.restype = i32
+    lib.rp_warp_views_ex.argtypes = [vp, ctypes.c_longlong, vp, vp, i32, i32, vp, ctypes.c_longlong, vp, ctypes.c_size_t, vp]
     lib.rp_pano2pc.restype = i32
     lib.rp_pano2pc.argtypes = [vp, i32, i32, vp, vp, vp]
     lib.rp_blend_completion.restype = i32

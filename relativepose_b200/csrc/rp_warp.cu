@@ -94,8 +94,8 @@ __device__ __forceinline__ bool project(int ds, const double P[3], int& ox, int&
     return false;
 }
 
-__global__ void warp_scatter_kernel(const float* __restrict__ view, const double* __restrict__ Rall, int B, int ds,
-                                    int* __restrict__ zbuf) {
+__global__ void warp_scatter_kernel(const float* __restrict__ view, long long view_stride, const int* __restrict__ src_index,
+                                    const double* __restrict__ Rall, int B, int ds, int* __restrict__ zbuf) {
     const Window wd = window_of(ds);
     const int npx = wd.w * wd.h;
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -105,14 +105,15 @@ __global__ void warp_scatter_kernel(const float* __restrict__ view, const double
     if (is_identity(R)) return;
     const int ly = j / wd.w, lx = j - ly * wd.w;
     double P[3];
-    if (!target_point(ds, view + (size_t)b * 8 * HW, R, lx, ly, wd, P)) return;
+    if (!target_point(ds, view + (size_t)(src_index ? src_index[b] : b) * view_stride, R, lx, ly, wd, P)) return;
     int ox, oy, slot; double depth;
     if (!project(ds, P, ox, oy, slot, depth)) return;
     atomicMax(&zbuf[(size_t)b * HW + oy * W + ox], j);
 }
 
-__global__ void warp_gather_kernel(const float* __restrict__ view, const double* __restrict__ Rall, int B, int ds,
-                                   const int* __restrict__ zbuf, float* __restrict__ out) {
+__global__ void warp_gather_kernel(const float* __restrict__ view, long long view_stride, const int* __restrict__ src_index,
+                                   const double* __restrict__ Rall, int B, int ds, const int* __restrict__ zbuf,
+                                   float* __restrict__ out, long long out_stride) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= B * HW) return;
     const int b = idx / HW, t = idx - b * HW;
@@ -121,7 +122,7 @@ __global__ void warp_gather_kernel(const float* __restrict__ view, const double*
     const int j = is_identity(R) ? -1 : zbuf[idx];
     if (j >= 0) {
         const Window wd = window_of(ds);
-        const float* vb = view + (size_t)b * 8 * HW;
+        const float* vb = view + (size_t)(src_index ? src_index[b] : b) * view_stride;
         const int ly = j / wd.w, lx = j - ly * wd.w;
         const int sp = (wd.y0 + ly) * W + wd.x0 + lx;
         double P[3];
@@ -135,7 +136,7 @@ __global__ void warp_gather_kernel(const float* __restrict__ view, const double*
         o[6] = (float)depth;
         o[7] = depth != 0.0 ? 1.f : 0.f;
     }
-    float* ob = out + (size_t)b * 8 * HW + t;
+    float* ob = out + (size_t)b * out_stride + t;
 #pragma unroll
     for (int c = 0; c < 8; ++c) ob[(size_t)c * HW] = o[c];
 }
@@ -200,20 +201,26 @@ int rp_warp_workspace_bytes(int B, size_t* bytes) {
     return RP_OK;
 }
 
-int rp_warp_views(const float* view, const double* R, int B, int dataset, float* out, void* workspace, size_t workspace_bytes,
-                  void* stream_) {
+int rp_warp_views_ex(const float* view, long long view_img_stride, const int32_t* src_index, const double* R, int B, int dataset,
+                     float* out, long long out_img_stride, void* workspace, size_t workspace_bytes, void* stream_) {
     if (B == 0) return RP_OK;
     if (!view || !R || !out || !workspace || B < 0 || dataset < 0 || dataset > 2) return RP_ERR_INVALID_ARG;
+    if (view_img_stride < 8LL * warp::HW || out_img_stride < 8LL * warp::HW) return RP_ERR_INVALID_ARG;
     if (workspace_bytes < (size_t)B * warp::HW * sizeof(int)) return RP_ERR_WORKSPACE_TOO_SMALL;
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
     int* zbuf = static_cast<int*>(workspace);
     if (cudaMemsetAsync(zbuf, 0xFF, (size_t)B * warp::HW * sizeof(int), stream) != cudaSuccess) return RP_ERR_CUDA;
     const warp::Window wd = warp::window_of(dataset);
     const int ns = B * wd.w * wd.h, nt = B * warp::HW;
-    warp::warp_scatter_kernel<<<(ns + 255) / 256, 256, 0, stream>>>(view, R, B, dataset, zbuf);
-    warp::warp_gather_kernel<<<(nt + 255) / 256, 256, 0, stream>>>(view, R, B, dataset, zbuf, out);
+    warp::warp_scatter_kernel<<<(ns + 255) / 256, 256, 0, stream>>>(view, view_img_stride, src_index, R, B, dataset, zbuf);
+    warp::warp_gather_kernel<<<(nt + 255) / 256, 256, 0, stream>>>(view, view_img_stride, src_index, R, B, dataset, zbuf, out, out_img_stride);
     scnet::g_conv_launches += 2;
     return cudaGetLastError() == cudaSuccess ? RP_OK : RP_ERR_CUDA;
+}
+
+int rp_warp_views(const float* view, const double* R, int B, int dataset, float* out, void* workspace, size_t workspace_bytes,
+                  void* stream_) {
+    return rp_warp_views_ex(view, 8LL * warp::HW, nullptr, R, B, dataset, out, 8LL * warp::HW, workspace, workspace_bytes, stream_);
 }
 
 int rp_pano2pc(const float* depth, int B, int dataset, double* pc, unsigned char* valid, void* stream_) {

@@ -79,7 +79,9 @@ def RelativePoseEstimationViaCompletion_batch(net, rgb, norm, depth, pts, weight
         mask = m[:, 0].contiguous()
         norm_gt = torch.as_tensor(np.asarray(norm) if not torch.is_tensor(norm) else norm).to(dev)
         depth_gt = torch.as_tensor(np.asarray(depth) if not torch.is_tensor(depth) else depth).to(dev)
-        swap = torch.arange(n_img, device=dev) ^ 1                    # the other scan of the pair
+        swap = (torch.arange(n_img, device=dev) ^ 1).to(torch.int32)   # the other scan of the pair
+        inp = torch.empty((n_img, 16, 160, 640), dtype=torch.float32, device=dev)
+        inp[:, :8] = views                                            # network input: own view | partner warped into this frame
         R_hat = np.tile(np.eye(4), (B, 1, 1))
         solver = _solver.default_solver(dev)
         for alter_ in range(args.alterStep):
@@ -88,8 +90,8 @@ def RelativePoseEstimationViaCompletion_batch(net, rgb, norm, depth, pts, weight
             Rs = np.empty((n_img, 4, 4))
             Rs[0::2] = np.linalg.inv(R_hat)
             Rs[1::2] = R_hat
-            warped = _util.warping_device(views[swap], Rs, args.dataset)
-            f = net(torch.cat((views, warped), 1))                                                               # :619-623
+            _util.warping_device(inp, Rs, args.dataset, out=inp[:, 8:], src_index=swap)       # reads channels 0..7, writes 8..15
+            f = net(inp)                                                                                         # :619-623
             nrm2, dep2 = _util.blend_completion_device(f, mask, norm_gt, depth_gt)                                # :628-634
             para_this = copy.copy(args.para)
             for name in ('sigmaAngle1', 'sigmaAngle2', 'sigmaDist', 'sigmaFeat'):

@@ -35,18 +35,23 @@ def _torch():
 _ws = {}
 
 
-def warping_device(views, R, dataList, out=None):
-    """views: CUDA float32 [B,8,160,640]; R: [B,4,4] (numpy / tensor, float64) -> CUDA float32 [B,8,160,640]."""
+def warping_device(views, R, dataList, out=None, src_index=None):
+    """views: CUDA float32 [B,8,160,640] (or a [B,>=8,160,640] tensor whose first 8 channels are the view); R: [B,4,4]
+    (numpy / tensor, float64) -> CUDA float32 [B,8,160,640].  ``src_index`` (int32 CUDA [B]): output b is views[src_index[b]]
+    warped by R[b].  ``out``: a [B,8,160,640] tensor or a channel slice of a wider [B,C,160,640] one (image stride C*H*W)."""
     torch = _torch()
     lib = _lib.load()
-    if views.dim() != 4 or views.shape[1] != 8 or views.shape[2] != 160 or views.shape[3] != 640:
+    if views.dim() != 4 or views.shape[1] < 8 or views.shape[2] != 160 or views.shape[3] != 640:
         raise ValueError("expected views [B,8,160,640]")
-    views = views.contiguous().float()
+    if views.dtype != torch.float32 or views.stride(3) != 1 or views.stride(2) != 640 or views.stride(1) != 160 * 640:
+        views = views[:, :8].contiguous().float()
     B = views.shape[0]
     dev = views.device
     Rt = torch.as_tensor(np.ascontiguousarray(np.asarray(R.cpu() if hasattr(R, 'cpu') else R, dtype=np.float64).reshape(B, 16))).to(dev)
     if out is None:
-        out = torch.empty_like(views)
+        out = torch.empty((B, 8, 160, 640), dtype=torch.float32, device=dev)
+    assert out.dtype == torch.float32 and out.shape[0] == B and out.shape[1] == 8 and out.stride(3) == 1 and out.stride(2) == 640 \
+        and out.stride(1) == 160 * 640, "out must be [B,8,160,640] planes (possibly a channel slice of a wider tensor)"
     need = ctypes.c_size_t(0)
     _lib.check(lib.rp_warp_workspace_bytes(B, ctypes.byref(need)), "rp_warp_workspace_bytes")
     key = (str(dev), 'warp')
@@ -55,8 +60,9 @@ def warping_device(views, R, dataList, out=None):
         ws = torch.empty((max(need.value, 1),), dtype=torch.uint8, device=dev)
         _ws[key] = ws
     with torch.cuda.device(dev):
-        _lib.check(lib.rp_warp_views(views.data_ptr(), Rt.data_ptr(), B, dataset_id(dataList), out.data_ptr(), ws.data_ptr(),
-                                     ws.numel(), torch.cuda.current_stream().cuda_stream), "rp_warp_views")
+        _lib.check(lib.rp_warp_views_ex(views.data_ptr(), views.stride(0), src_index.data_ptr() if src_index is not None else None,
+                                        Rt.data_ptr(), B, dataset_id(dataList), out.data_ptr(), out.stride(0), ws.data_ptr(),
+                                        ws.numel(), torch.cuda.current_stream().cuda_stream), "rp_warp_views_ex")
     return out
 
 
