@@ -14,10 +14,11 @@
 //   * a stride-2 transposed convolution is its 4 sub-pixel classes over ONE halo: 16 (class, tap) MMAs per K step
 //     into 4 accumulators in TMEM (4 x BN columns).
 // Persistent and warp-specialised (one CTA per SM looping over tiles): warps 4-11 gather (producer BatchNorm +
-// LeakyReLU + bf16 convert, 16-byte STS, double-buffered halo), warp 12 streams the pre-packed weight blocks with
-// cp.async.bulk (1-D TMA) through an NB-deep ring, warp 13 issues tcgen05.mma into one of two accumulator sets in TMEM,
-// warps 0-3 run the epilogue of the previous tile meanwhile (tcgen05.ld, bias/tanh, raw output fp32 or bf16 NHWC,
-// deterministic per-tile partial batch statistics).  mbarriers only; no __syncthreads in the steady state.
+// LeakyReLU + bf16 convert, 16-byte STS; 2 or 4 loader groups, each filling its own halo buffer), warp 12 streams the
+// pre-packed weight blocks with cp.async.bulk (1-D TMA) through an NB-deep ring (or loads them once when they all fit),
+// warp 13 issues tcgen05.mma into one of 2-8 accumulator sets in TMEM, warps 0-3 run the epilogue of earlier tiles
+// meanwhile (tcgen05.ld, bias/tanh, raw output fp32 or bf16 NHWC, deterministic per-tile partial batch statistics).
+// mbarriers only; no __syncthreads in the steady state.
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -104,11 +105,11 @@ __device__ __forceinline__ uint64_t pack_desc(uint32_t lo, uint32_t hi) { return
 
 // Persistent: CTA b works on tiles b, b + gridDim.x, ...  (tile = scan pair, 16x8 block of output positions, n-tile).
 // Four roles run the same tile sequence and meet only at mbarriers:
-//   loaders  (256 thr)  halo of K chunk c -> smem buffer c&1            a_empty -> a_full
-//   TMA      (1 thr)    weight block (chunk, tap) -> ring slot          w_empty -> w_full
-//   MMA      (1 thr)    ntap x TK/16 tcgen05.mma per chunk into accumulator set tile&1; commits free slots / buffers
-//   epilogue (128 thr)  accumulator set tile&1 -> global + statistics   acc_full -> acc_empty
-// so the gather of tile i+1, the MMAs of tile i and the epilogue of tile i-1 overlap.
+//   loaders  (256 thr)  halo of K chunk c -> smem buffer c % ng (group c % ng)     a_empty -> a_full
+//   TMA      (1 thr)    weight block (chunk, tap) -> ring slot (or all blocks once)  w_empty -> w_full
+//   MMA      (1 thr)    ntap x TK/16 tcgen05.mma per chunk into accumulator set tile % nacc; commits free slots / buffers
+//   epilogue (128 thr)  accumulator set tile % nacc -> global + statistics          acc_full -> acc_empty
+// so the gathers of the next tiles, the MMAs of tile i and the epilogue of earlier tiles overlap.
 template <int BN, int TK, int NB>
 __global__ void __launch_bounds__(CTA, 1) conv_halo_tc(const HaloArgs A, const unsigned char* __restrict__ Wp) {
     extern __shared__ __align__(128) unsigned char smem[];
