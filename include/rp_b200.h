@@ -115,6 +115,11 @@ int rp_device_info(int* sm_count, int* cc_major, int* cc_minor, size_t* total_me
 int rp_solve_workspace_bytes(int n_slots, int max_ns, int max_nt, int max_topk, int feat_dim,
                              int64_t edge_cap, size_t* bytes);
 
+/* The default slot count (resident CTAs on the current device) for pairs of this size: callers with fewer than that
+ * many pairs size the workspace for min(B, default) slots.  Pairs with n_s*topK <= 16383 are supported; above ~2800
+ * correspondences (or n_t > ~1400) the per-pair vectors move from shared memory into the slot's workspace. */
+int rp_solve_default_slots(int max_ns, int max_nt, int max_topk, int feat_dim, int* n_slots);
+
 /* Replaces RelativePoseEstimation_helper (RPModule/rpmodule.py:317-508) for a ragged batch of B
  * scan pairs -- descriptor distance + soft match + top-k, pairwise consistency affinity,
  * spectral/IRLS solve -- one fused launch.

@@ -10,17 +10,31 @@ section 8(c) describes:
   * ``matplotlib`` / ``open3d`` (unused by the solver; rpmodule.py:10,
     rputil.py:4) are replaced by empty stub modules when absent.
 
-This only works where /root/reference exists (the build container).  It is used
+This works where /root/reference exists (the build container) or where baseline/_ref was installed from it
+(oracle/install_reference.py; travels to the GPU box, git-ignored).  It is used
 by tests/golden/make_golden.py to produce the committed golden vectors and by
 the ``not gpu`` tests to re-pin the numpy restatement when the tree is present.
-Nothing in the product path may import this module.
+and by bench.py's CPU arm (cpu_baseline.kind == "reference").  Nothing in the product path may import this module.
 """
 import importlib.util
 import os
 import sys
 import types
 
-REFERENCE_ROOT = os.environ.get("RP_REFERENCE_ROOT", "/root/reference")
+_REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _find_root():
+    """$RP_REFERENCE_ROOT, else the build container's read-only tree, else the offline install that travels to the GPU
+    box (baseline/_ref, made by oracle/install_reference.py; unmodified files)."""
+    cands = [os.environ.get("RP_REFERENCE_ROOT"), "/root/reference", os.path.join(_REPO, "baseline", "_ref")]
+    for c in cands:
+        if c and os.path.isfile(os.path.join(c, "RPModule", "rpmodule.py")):
+            return c
+    return cands[1]
+
+
+REFERENCE_ROOT = _find_root()
 
 
 def reference_available():

@@ -188,7 +188,7 @@ def RelativePoseEstimationViaCompletion(net, data_s, data_t, args, warping_fn=No
                 for d in (data_s, data_t)]                           # :599-600
         views, masks = [], []
         for c in full:
-            vw, m = apply_mask(c.clone(), args.maskMethod)           # :603-604
+            vw, m, _geow = apply_mask(c.clone(), args.maskMethod)           # :603-604
             masks.append(m[0, 0])                                    # [h,w] on the device
             views.append(torch.cat((vw, (vw[:, 6:7] != 0).float()), 1))   # :609-612
         view_s, view_t = views

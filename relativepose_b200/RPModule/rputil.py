@@ -89,14 +89,16 @@ def getPixel(depth, normal, pts, dataset='suncg', representation='skybox'):
 
 # ---------------------------------------------------------------------------------------------------------------------
 # Keypoint detection + augmentation (rputil.py:141-353, Sampling :355-371).
-def _sampling_device(fn, n, *args):
+def _sampling_device(fn, n, dev, *args):
+    """Launch rp_match_sample / rp_heat_sample on ``dev`` (the device of the caller's tensors, not the current one)."""
     import torch
     from .. import _lib
-    out = torch.empty((n, args[-2], 2), dtype=torch.float64, device='cuda')
-    need = ctypes.c_size_t(0)
-    _lib.check(_lib.load().rp_match_sample_workspace_bytes(n, ctypes.byref(need)), "rp_match_sample_workspace_bytes")
-    ws = torch.empty((need.value,), dtype=torch.uint8, device='cuda')
-    _lib.check(fn(*args, out.data_ptr(), ws.data_ptr(), ws.numel(), torch.cuda.current_stream().cuda_stream), "rp_*_sample")
+    with torch.cuda.device(dev):
+        out = torch.empty((n, args[-2], 2), dtype=torch.float64, device=dev)
+        need = ctypes.c_size_t(0)
+        _lib.check(_lib.load().rp_match_sample_workspace_bytes(n, ctypes.byref(need)), "rp_match_sample_workspace_bytes")
+        ws = torch.empty((need.value,), dtype=torch.uint8, device=dev)
+        _lib.check(fn(*args, out.data_ptr(), ws.data_ptr(), ws.numel(), torch.cuda.current_stream().cuda_stream), "rp_*_sample")
     return out.cpu().numpy()
 
 
@@ -106,9 +108,12 @@ def Sampling(heatmap, K):
     import torch
     from .. import _lib
     lib = _lib.load()
-    d = torch.as_tensor(np.asarray(heatmap.cpu()) if hasattr(heatmap, 'cpu') else heatmap, dtype=torch.float32).cuda().contiguous()
+    if torch.is_tensor(heatmap) and heatmap.is_cuda:
+        d = heatmap.float().contiguous()                     # stays on the caller's device
+    else:
+        d = torch.as_tensor(np.asarray(heatmap), dtype=torch.float32).cuda().contiguous()
     n, h, w = d.shape
-    return _sampling_device(lib.rp_heat_sample, n, d.data_ptr(), n, h, w, K, 15)
+    return _sampling_device(lib.rp_heat_sample, n, d.device, d.data_ptr(), n, h, w, K, 15)
 
 
 def match_sample(q, feat, K=2):
@@ -120,7 +125,8 @@ def match_sample(q, feat, K=2):
     q = q.contiguous().float()
     feat = feat.contiguous().float()
     C, n = q.shape
-    return _sampling_device(lib.rp_match_sample, n, q.data_ptr(), C, n, feat.data_ptr(), feat.shape[1], feat.shape[2], K, 15)
+    q = q.to(feat.device)
+    return _sampling_device(lib.rp_match_sample, n, feat.device, q.data_ptr(), C, n, feat.data_ptr(), feat.shape[1], feat.shape[2], K, 15)
 
 
 def _default_sift(gray):

@@ -86,6 +86,8 @@ struct SolveArgs {
     int mask_in_smem;
     int tfeat_stride;       // odd stride (floats) of the staged target descriptors
     size_t sm_mask_off;     // byte offset of the bit mask in dynamic shared memory (when mask_in_smem)
+    int dyn_in_global;      // scan pairs too large for shared memory: the per-pair vectors live in the slot (o_dyn)
+    size_t o_dyn;
 };
 
 // ----------------------------------------------------------------------------------------------
@@ -1002,6 +1004,8 @@ __global__ void __launch_bounds__(T, RP_MIN_BLOCKS) rp_solve_kernel(const SolveA
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     int* work_counter = reinterpret_cast<int*>(A.ws) + (ROBUST ? 1 : 0);
     char* slot = A.ws + 256 + (size_t)blockIdx.x * A.slot_bytes;
+    // per-pair vectors / staging: dynamic shared memory, or (N too large for it) the same layout in the slot's workspace
+    unsigned char* const dyn = A.dyn_in_global ? reinterpret_cast<unsigned char*>(slot + A.o_dyn) : dyn_smem;
 
     for (;;) {
         __syncthreads();
@@ -1040,16 +1044,16 @@ __global__ void __launch_bounds__(T, RP_MIN_BLOCKS) rp_solve_kernel(const SolveA
         pv.cols = reinterpret_cast<uint16_t*>(slot + A.o_cols);
         pv.vals = reinterpret_cast<double*>(slot + A.o_vals);
         {
-            double* v = reinterpret_cast<double*>(dyn_smem);
+            double* v = reinterpret_cast<double*>(dyn);
             pv.aP = v; pv.aN = v + A.Nmax; pv.res = v + 2 * A.Nmax; pv.ua = v + 3 * A.Nmax;
             pv.ub = v + 4 * A.Nmax; pv.sv = v + 5 * A.Nmax;
             pv.S = v + 6 * A.Nmax;                                   // 2*Nmax doubles
             pv.rowstart = reinterpret_cast<int*>(v + 8 * A.Nmax);    // Nmax+1 ints
             pv.rowmap = reinterpret_cast<unsigned*>(pv.rowstart + (A.Nmax + 1));   // Nmax words
             pv.E = 1; pv.nnz = 0; pv.nrows = 0;
-            pv.sp4 = reinterpret_cast<float4*>(dyn_smem);
+            pv.sp4 = reinterpret_cast<float4*>(dyn);
             pv.tq4 = pv.sp4 + ns;
-            pv.mask = A.mask_in_smem ? reinterpret_cast<unsigned*>(dyn_smem + A.sm_mask_off)
+            pv.mask = A.mask_in_smem ? reinterpret_cast<unsigned*>(dyn + A.sm_mask_off)
                                      : reinterpret_cast<unsigned*>(slot + A.o_mask);
         }
         const int N = pv.N, NW = pv.NW;
@@ -1057,7 +1061,7 @@ __global__ void __launch_bounds__(T, RP_MIN_BLOCKS) rp_solve_kernel(const SolveA
 
         // ------------------------------------------------------------------ A. descriptor front end
         if (!A.solve_only) {
-            float* tfeat = reinterpret_cast<float*>(dyn_smem);       // aliases the vectors (not yet live)
+            float* tfeat = reinterpret_cast<float*>(dyn);            // aliases the vectors (not yet live)
             const int ts = A.tfeat_stride;
             const bool vec4 = ((D & 7) == 0) && ((ts & 3) == 0);
             const bool seq_sum = A.feat_sum_order && A.feat_sum_order[b] != 0;
@@ -1471,14 +1475,14 @@ __global__ void __launch_bounds__(T, RP_MIN_BLOCKS) rp_solve_kernel(const SolveA
 
 // ----------------------------------------------------------------------------------------------
 struct Layout {
-    size_t o_geo, o_cj, o_mask, o_edges, o_ew, o_rowstart, o_cols, o_vals, slot_bytes;
+    size_t o_geo, o_cj, o_mask, o_edges, o_ew, o_rowstart, o_cols, o_vals, o_dyn, slot_bytes;
     int Nmax, NWmax;
     long long edge_cap;
 };
 
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
-bool make_layout(int max_ns, int max_topk, long long edge_cap, Layout* L) {
+bool make_layout(int max_ns, int max_topk, long long edge_cap, size_t dyn_bytes, Layout* L) {
     long long Nmax = (long long)max_ns * max_topk;
     if (Nmax < 1 || Nmax > 16383) return false;     // 14-bit column field in the CSR word
     long long P = Nmax * (Nmax - 1) / 2;
@@ -1494,13 +1498,16 @@ bool make_layout(int max_ns, int max_topk, long long edge_cap, Layout* L) {
     L->o_rowstart = o; o = align_up(o + sizeof(uint16_t) * Nmax * L->NWmax, 256);
     L->o_cols = o; o = align_up(o + sizeof(uint16_t) * (2 * edge_cap + 2 * T), 256);     // lane-interleaved: up to T-1 pad
     L->o_vals = o; o = align_up(o + sizeof(double) * (2 * edge_cap + 2 * T), 256);
+    L->o_dyn = o; o = align_up(o + dyn_bytes, 256);          // only for pairs whose vectors do not fit shared memory
     L->slot_bytes = o;
     return true;
 }
 
-struct SmemPlan { size_t bytes; int mask_in_smem; int tfeat_stride; size_t mask_off; };
+struct SmemPlan { size_t bytes; int mask_in_smem; int tfeat_stride; size_t mask_off; int dyn_in_global; size_t dyn_bytes; };
 
-bool make_smem_plan(const Layout& L, int max_nt, int feat_dim, SmemPlan* S) {
+bool make_smem_plan(long long Nmax_, int max_nt, int feat_dim, SmemPlan* S) {
+    if (Nmax_ < 1 || Nmax_ > 16383) return false;
+    struct { int Nmax, NWmax; } L = {(int)Nmax_, (int)((Nmax_ + 31) / 32)};
     // ~227 KB per SM shared by RP_MIN_BLOCKS CTAs; the static part (struct Shared) is ~3-8 KB
     const size_t budget = (size_t)(220 * 1024) / RP_MIN_BLOCKS - 9 * 1024;
     const size_t hard = 200 * 1024;
@@ -1512,8 +1519,12 @@ bool make_smem_plan(const Layout& L, int max_nt, int feat_dim, SmemPlan* S) {
     base = align_up(base, 16);
     int in_smem = (base + mask <= budget) ? 1 : 0;
     size_t need = base + (in_smem ? mask : 0);
-    if (need > hard) return false;
-    S->bytes = need; S->mask_in_smem = in_smem; S->tfeat_stride = ts; S->mask_off = base;
+    S->tfeat_stride = ts; S->mask_off = base;
+    if (need > hard) {          // big pair (n_s * topK > ~2800 or n_t > ~1400): same layout in the slot's global workspace
+        S->bytes = 0; S->mask_in_smem = 0; S->dyn_in_global = 1; S->dyn_bytes = base;
+        return true;
+    }
+    S->bytes = need; S->mask_in_smem = in_smem; S->dyn_in_global = 0; S->dyn_bytes = 0;
     return true;
 }
 
@@ -1552,15 +1563,26 @@ int rp_solve_workspace_bytes(int n_slots, int max_ns, int max_nt, int max_topk, 
                              int64_t edge_cap, size_t* bytes) {
     if (!bytes || max_ns < 1 || max_nt < 1 || max_topk < 1) return RP_ERR_INVALID_ARG;
     if (max_topk > RP_MAX_TOPK || feat_dim < 1 || feat_dim > RP_MAX_FEAT_DIM) return RP_ERR_UNSUPPORTED;
-    Layout L;
-    if (!make_layout(max_ns, max_topk, edge_cap, &L)) return RP_ERR_UNSUPPORTED;
     SmemPlan S;
-    if (!make_smem_plan(L, max_nt, feat_dim, &S)) return RP_ERR_UNSUPPORTED;
+    if (!make_smem_plan((long long)max_ns * max_topk, max_nt, feat_dim, &S)) return RP_ERR_UNSUPPORTED;
+    Layout L;
+    if (!make_layout(max_ns, max_topk, edge_cap, S.dyn_bytes, &L)) return RP_ERR_UNSUPPORTED;
     if (n_slots <= 0) {
         n_slots = default_slots(S.bytes);
         if (n_slots < 0) { cudaGetLastError(); return RP_ERR_NO_DEVICE; }
     }
     *bytes = 256 + (size_t)n_slots * L.slot_bytes;
+    return RP_OK;
+}
+
+int rp_solve_default_slots(int max_ns, int max_nt, int max_topk, int feat_dim, int* n_slots) {
+    if (!n_slots || max_ns < 1 || max_nt < 1 || max_topk < 1) return RP_ERR_INVALID_ARG;
+    if (max_topk > RP_MAX_TOPK || feat_dim < 1 || feat_dim > RP_MAX_FEAT_DIM) return RP_ERR_UNSUPPORTED;
+    SmemPlan S;
+    if (!make_smem_plan((long long)max_ns * max_topk, max_nt, feat_dim, &S)) return RP_ERR_UNSUPPORTED;
+    int n = default_slots(S.bytes);
+    if (n < 0) { cudaGetLastError(); return RP_ERR_NO_DEVICE; }
+    *n_slots = n;
     return RP_OK;
 }
 
@@ -1581,10 +1603,10 @@ int rp_solve_batch_ex(int B, const int32_t* off_s, const int32_t* off_t,
     if (max_topk > RP_MAX_TOPK || max_topk < 1 || feat_dim < 1 || feat_dim > RP_MAX_FEAT_DIM) return RP_ERR_UNSUPPORTED;
     if (B == 0) return RP_OK;
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
-    Layout L;
-    if (!make_layout(max_ns, max_topk, edge_cap, &L)) return RP_ERR_UNSUPPORTED;
     SmemPlan S;
-    if (!make_smem_plan(L, max_nt, feat_dim, &S)) return RP_ERR_UNSUPPORTED;
+    if (!make_smem_plan((long long)max_ns * max_topk, max_nt, feat_dim, &S)) return RP_ERR_UNSUPPORTED;
+    Layout L;
+    if (!make_layout(max_ns, max_topk, edge_cap, S.dyn_bytes, &L)) return RP_ERR_UNSUPPORTED;
     if (cudaFuncSetAttribute(rp_solve_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S.bytes) != cudaSuccess ||
         cudaFuncSetAttribute(rp_solve_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S.bytes) != cudaSuccess) {
         cudaGetLastError();
@@ -1611,6 +1633,7 @@ int rp_solve_batch_ex(int B, const int32_t* off_s, const int32_t* off_t,
     a.has_dbg = dbg ? 1 : 0;
     if (dbg) a.dbg = *dbg; else { rp_debug z = {}; a.dbg = z; }
     a.mask_in_smem = S.mask_in_smem; a.tfeat_stride = S.tfeat_stride; a.sm_mask_off = S.mask_off;
+    a.dyn_in_global = S.dyn_in_global; a.o_dyn = L.o_dyn;
     if (cudaMemsetAsync(workspace, 0, 256, stream) != cudaSuccess) { cudaGetLastError(); return RP_ERR_CUDA; }
     int grid = B < n_slots ? B : n_slots;
     rp_solve_kernel<false><<<grid, T, S.bytes, stream>>>(a);
@@ -1686,10 +1709,10 @@ int rp_spectral_irls_solve(int B, const int32_t* node_off,
     if (edge_off && (!edge_rc || !edge_w)) return RP_ERR_INVALID_ARG;
     if (B == 0) return RP_OK;
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
-    Layout L;
-    if (!make_layout(max_nodes, 1, edge_cap, &L)) return RP_ERR_UNSUPPORTED;
     SmemPlan S;
-    if (!make_smem_plan(L, 1, 8, &S)) return RP_ERR_UNSUPPORTED;
+    if (!make_smem_plan(max_nodes, 1, 8, &S)) return RP_ERR_UNSUPPORTED;
+    Layout L;
+    if (!make_layout(max_nodes, 1, edge_cap, S.dyn_bytes, &L)) return RP_ERR_UNSUPPORTED;
     if (cudaFuncSetAttribute(rp_solve_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S.bytes) != cudaSuccess ||
         cudaFuncSetAttribute(rp_solve_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S.bytes) != cudaSuccess) {
         cudaGetLastError();
@@ -1713,6 +1736,7 @@ int rp_spectral_irls_solve(int B, const int32_t* node_off,
     a.T_out = T_out; a.status = status; a.stats = stats;
     a.stop_after = RP_STAGE_SOLVE; a.has_dbg = 0;
     a.mask_in_smem = S.mask_in_smem; a.tfeat_stride = S.tfeat_stride; a.sm_mask_off = S.mask_off;
+    a.dyn_in_global = S.dyn_in_global; a.o_dyn = L.o_dyn;
     if (cudaMemsetAsync(workspace, 0, 256, stream) != cudaSuccess) { cudaGetLastError(); return RP_ERR_CUDA; }
     int grid = B < n_slots ? B : n_slots;
     rp_solve_kernel<false><<<grid, T, S.bytes, stream>>>(a);

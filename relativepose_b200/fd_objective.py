@@ -43,7 +43,7 @@ class Objective(object):
             raise Exception("unknown method!")
         if not self.primitives:
             return np.zeros((0, 4, 4))
-        T, status, _ = self.solver.solve_device(self.dbatch, [_solver.params_from_opts(para)])
+        T, status, _ = self.solver.solve_device_checked(self.dbatch, [_solver.params_from_opts(para)])
         self.evaluations += 1
         return T.cpu().numpy()
 

@@ -51,7 +51,7 @@ def solve_from_maps(feat, depth, normal, pts, weights, para, dataset, solver=Non
     one fused solver launch."""
     solver = solver or _solver.default_solver(feat.device)
     d = gather_primitives(feat, depth, normal, pts, weights, dataset)
-    T, status, _ = solver.solve_device(d, [_solver.params_from_opts(para)])
+    T, status, _ = solver.solve_device_checked(d, [_solver.params_from_opts(para)])
     return T.cpu().numpy()
 
 
@@ -74,7 +74,7 @@ def RelativePoseEstimationViaCompletion_batch(net, rgb, norm, depth, pts, weight
     B = n_img // 2
     with torch.no_grad():
         full = torch.cat((f32(rgb), f32(norm), f32(depth).unsqueeze(3)), 3).permute(0, 3, 1, 2).contiguous()      # [2B,7,h,w]
-        vw, m = _util.apply_mask(full, args.maskMethod)
+        vw, m, _geow = _util.apply_mask(full, args.maskMethod)
         views = torch.cat((vw, (vw[:, 6:7] != 0).float()), 1)                                                    # [2B,8,h,w]
         mask = m[:, 0].contiguous()
         norm_gt = torch.as_tensor(np.asarray(norm) if not torch.is_tensor(norm) else norm).to(dev)
@@ -97,6 +97,6 @@ def RelativePoseEstimationViaCompletion_batch(net, rgb, norm, depth, pts, weight
             for name in ('sigmaAngle1', 'sigmaAngle2', 'sigmaDist', 'sigmaFeat'):
                 setattr(para_this, name, getattr(args.para, name)[alter_])
             d = gather_primitives(f[:, idx_f:idx_f + args.featureDim], dep2, nrm2, pts, weights, args.dataset)
-            T, status, _ = solver.solve_device(d, [_solver.params_from_opts(para_this)])
+            T, status, _ = solver.solve_device_checked(d, [_solver.params_from_opts(para_this)])
             R_hat = T.cpu().numpy()
     return R_hat

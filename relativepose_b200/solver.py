@@ -189,7 +189,15 @@ class SolveResult(object):
 class PoseSolver(object):
     """Owns the device workspace and parameter block for one GPU/stream."""
 
-    def __init__(self, device=None, n_slots=0, edge_frac=1.0):
+    # Candidate-list capacity per slot when edge_frac is None: the float32 pre-test keeps a few per cent of the N(N-1)/2
+    # correspondence pairs (8 % on the synthetic SUNCG-shape pairs, 3-4 % on rendered rooms), so a quarter of the worst
+    # case (never less than 64 Ki entries) is ample; a pair that overflows it reports STATUS_EDGE_OVERFLOW and the batch is
+    # redone at full capacity (solve_packed / _solve_small / pipeline callers via check_status).
+    AUTO_EDGE_FRAC = 0.25
+    AUTO_EDGE_FLOOR = 1 << 16
+    WS_BUDGET_FRAC = 0.4         # of the device memory: more slots than fit this are not resident
+
+    def __init__(self, device=None, n_slots=0, edge_frac=None):
         import torch
         self.torch = torch
         self.lib = _lib.load()
@@ -202,6 +210,7 @@ class PoseSolver(object):
         self._ws_key = None
         self._par_dev = None
         self._par_key = None
+        self._slots_cache = {}
 
     # ------------------------------------------------------------------ helpers
     def _params_device(self, plist):
@@ -214,23 +223,64 @@ class PoseSolver(object):
         return self._par_dev
 
     def _edge_cap(self, max_ns, topk):
+        """0 = worst case (every correspondence pair)."""
         N = max_ns * topk
         P = N * (N - 1) // 2
+        if self.edge_frac is None:
+            cap = max(self.AUTO_EDGE_FLOOR, int(P * self.AUTO_EDGE_FRAC))
+            return cap if cap < P else 0
         return max(3, int(P * self.edge_frac)) if self.edge_frac < 1.0 else 0
 
-    def _workspace(self, max_ns, max_nt, topk, feat_dim, edge_cap):
-        key = (max_ns, max_nt, topk, feat_dim, edge_cap, self.n_slots)
-        if self._ws_key is not None and self._ws is not None:
-            k = self._ws_key
-            if k[0] >= max_ns and k[1] >= max_nt and k[2] == topk and k[3] == feat_dim and k[4] == edge_cap:
-                return self._ws, k
+    def _ws_bytes(self, n_slots, max_ns, max_nt, topk, feat_dim, edge_cap):
         nbytes = ctypes.c_size_t(0)
+        _lib.check(self.lib.rp_solve_workspace_bytes(n_slots, max_ns, max_nt, topk, feat_dim, edge_cap, ctypes.byref(nbytes)),
+                   "rp_solve_workspace_bytes")
+        return nbytes.value
+
+    def _slots_for(self, B, max_ns, max_nt, topk, feat_dim, edge_cap):
+        """Slots (resident CTAs) to size the workspace for: the caller's n_slots, else min(B, device default), never more
+        than fit WS_BUDGET_FRAC of the device memory (a slot holds O(edge_cap) bytes)."""
+        if self.n_slots > 0:
+            return self.n_slots
+        key = (max_ns, max_nt, topk, feat_dim)
+        if key not in self._slots_cache:
+            n = ctypes.c_int(0)
+            _lib.check(self.lib.rp_solve_default_slots(max_ns, max_nt, topk, feat_dim, ctypes.byref(n)), "rp_solve_default_slots")
+            self._slots_cache[key] = n.value
+        slots = max(1, min(B, self._slots_cache[key]))
+        one = self._ws_bytes(1, max_ns, max_nt, topk, feat_dim, edge_cap)
+        per = self._ws_bytes(2, max_ns, max_nt, topk, feat_dim, edge_cap) - one
+        budget = int(self.torch.cuda.get_device_properties(self.device).total_memory * self.WS_BUDGET_FRAC)
+        return max(1, min(slots, (budget - one) // max(per, 1) + 1))
+
+    def _workspace(self, B, max_ns, max_nt, topk, feat_dim, edge_cap):
+        """Returns (workspace tensor, key); key[0], key[1], key[5] = the max_ns, max_nt, n_slots it was sized for."""
         with self.torch.cuda.device(self.device):
-            _lib.check(self.lib.rp_solve_workspace_bytes(self.n_slots, max_ns, max_nt, topk, feat_dim, edge_cap,
-                                                         ctypes.byref(nbytes)), "rp_solve_workspace_bytes")
-        self._ws = self.torch.empty(nbytes.value, dtype=self.torch.uint8, device=self.device)
-        self._ws_key = key
-        return self._ws, key
+            if self._ws_key is not None and self._ws is not None:
+                k = self._ws_key
+                if k[0] >= max_ns and k[1] >= max_nt and k[2] == topk and k[3] == feat_dim and k[4] == edge_cap and \
+                        (k[5] >= B or k[5] >= self._slots_for(B, k[0], k[1], topk, feat_dim, edge_cap)):
+                    return self._ws, k
+            slots = self._slots_for(B, max_ns, max_nt, topk, feat_dim, edge_cap)
+            nbytes = self._ws_bytes(slots, max_ns, max_nt, topk, feat_dim, edge_cap)
+            self._ws = None                                        # release the old block before taking the new one
+            self._ws = self.torch.empty(nbytes, dtype=self.torch.uint8, device=self.device)
+        self._ws_key = (max_ns, max_nt, topk, feat_dim, edge_cap, slots)
+        return self._ws, self._ws_key
+
+    def check_status(self, status_host, redo):
+        """Shared post-solve policy: a pair whose candidate list overflowed the bounded default capacity is redone at full
+        capacity (``redo()`` must re-run the same batch with edge_cap=0 and return the new host status); a pair outside the
+        supported range raises.  Returns True when ``redo`` ran."""
+        ran = False
+        if (status_host == _lib.STATUS_EDGE_OVERFLOW).any():
+            status_host = redo()
+            ran = True
+        if (status_host == _lib.STATUS_UNSUPPORTED).any():
+            raise RuntimeError("scan pair outside the CUDA solver's supported range (topK > %d or n_s*topK > 16383)" % _lib.MAX_TOPK)
+        if (status_host == _lib.STATUS_EDGE_OVERFLOW).any():
+            raise RuntimeError("candidate list overflow at full capacity (internal error)")
+        return ran
 
     # ------------------------------------------------------------------ main entry
     def solve_device(self, dbatch, plist, param_idx=None, stop_after=_lib.STAGE_SOLVE, debug=None, edge_cap=None, out=None):
@@ -252,7 +302,7 @@ class PoseSolver(object):
             raise RuntimeError("topK=%d > %d is not supported by the CUDA solver" % (topk, _lib.MAX_TOPK))
         if edge_cap is None:
             edge_cap = self._edge_cap(dbatch.max_ns, topk)
-        ws, key = self._workspace(dbatch.max_ns, dbatch.max_nt, topk, dbatch.feat_dim, edge_cap)
+        ws, key = self._workspace(B, dbatch.max_ns, dbatch.max_nt, topk, dbatch.feat_dim, edge_cap)
         par = self._params_device(plist)
         pidx = param_idx.data_ptr() if param_idx is not None else None
         zrows = dbatch.zero_rows(max(int(p.topk) for p in plist), topk, self.device)
@@ -266,10 +316,23 @@ class PoseSolver(object):
                 dbatch.pc_s.data_ptr(), dbatch.nrm_s.data_ptr(), dbatch.feat_s.data_ptr(), dbatch.w_s.data_ptr(),
                 dbatch.pc_t.data_ptr(), dbatch.nrm_t.data_ptr(), dbatch.feat_t.data_ptr(), dbatch.w_t.data_ptr(),
                 dbatch.feat_dim, par.data_ptr(), pidx, zrows.data_ptr(), dbatch.sum_order_t.data_ptr(), key[0], key[1], topk,
-                self.n_slots, edge_cap, ws.data_ptr(), ws.numel(),
+                key[5], edge_cap, ws.data_ptr(), ws.numel(),
                 T.data_ptr(), status.data_ptr(), stats.data_ptr(), stop_after, dbg, stream)
         _lib.check(rc, "rp_solve_batch_ex")
         return T, status, stats
+
+    def solve_device_checked(self, dbatch, plist, **kw):
+        """solve_device + the status policy (check_status): overflowed pairs are redone at full candidate capacity,
+        unsupported pairs raise.  Synchronises (reads the [B] status back).  Returns (T, status, stats) device tensors."""
+        res = list(self.solve_device(dbatch, plist, **kw))
+
+        def redo():
+            kw2 = dict(kw)
+            kw2['edge_cap'] = 0
+            res[:] = self.solve_device(dbatch, plist, **kw2)
+            return res[1].cpu().numpy()
+        self.check_status(res[1].cpu().numpy(), redo)
+        return tuple(res)
 
     def solve_packed(self, packed, para, return_stats=False, chunks=None):
         """Host buffers in -> host poses out ([B,4,4] float64).  The batch is cut into `chunks` pair ranges; the
@@ -285,13 +348,16 @@ class PoseSolver(object):
             T, status, stats = self.solve_device(d, plist)
         else:
             d, T, status, stats = self._solve_pipelined(packed, plist, chunks)
-        Th = T.cpu().numpy()
+        res = [T, status, stats]
+
+        def redo():                                     # bounded candidate capacity overflowed: full capacity
+            res[0], res[1], res[2] = self.solve_device(d, plist, edge_cap=0)
+            return res[1].cpu().numpy()
         sth = status.cpu().numpy()
-        if (sth == _lib.STATUS_EDGE_OVERFLOW).any():        # only with edge_frac < 1: redo with full capacity
-            T, status, stats = self.solve_device(d, plist, edge_cap=0)
-            Th, sth = T.cpu().numpy(), status.cpu().numpy()
-        if (sth == _lib.STATUS_UNSUPPORTED).any():
-            raise RuntimeError("pair outside the CUDA solver's supported range (topK>%d?)" % _lib.MAX_TOPK)
+        if self.check_status(sth, redo):
+            sth = res[1].cpu().numpy()
+        T, status, stats = res
+        Th = T.cpu().numpy()
         if return_stats:
             return Th, sth, stats.cpu().numpy()
         return Th
@@ -319,7 +385,7 @@ class PoseSolver(object):
             stats = torch.empty((B, _lib.STATS_STRIDE), dtype=torch.int32, device=dev)
             topk = max(1, min(max(int(p.topk) for p in plist), max(packed.max_nt - 1, 1)))
             edge_cap = self._edge_cap(packed.max_ns, topk)
-            ws, key = self._workspace(packed.max_ns, packed.max_nt, topk, packed.feat_dim, edge_cap)
+            ws, key = self._workspace(B, packed.max_ns, packed.max_nt, topk, packed.feat_dim, edge_cap)
             par = self._params_device(plist)
             zrows = d.zero_rows(max(int(p.topk) for p in plist), topk, dev)
             cs.wait_stream(main)                          # allocations above are visible to the copy stream
@@ -344,7 +410,7 @@ class PoseSolver(object):
                     d.pc_s.data_ptr(), d.nrm_s.data_ptr(), d.feat_s.data_ptr(), d.w_s.data_ptr(),
                     d.pc_t.data_ptr(), d.nrm_t.data_ptr(), d.feat_t.data_ptr(), d.w_t.data_ptr(),
                     d.feat_dim, par.data_ptr(), None, zrows.data_ptr() + 4 * topk * b0, d.sum_order_t.data_ptr() + 4 * b0, key[0], key[1], topk,
-                    self.n_slots, edge_cap, ws.data_ptr(), ws.numel(),
+                    key[5], edge_cap, ws.data_ptr(), ws.numel(),
                     T.data_ptr() + 128 * b0, status.data_ptr() + 4 * b0, stats.data_ptr() + 4 * _lib.STATS_STRIDE * b0,
                     _lib.STAGE_SOLVE, None, main.cuda_stream)
                 _lib.check(rc, "rp_solve_batch_ex")
@@ -380,7 +446,12 @@ class PoseSolver(object):
             t_wp, t_wn = d64(node_w[0]), d64(node_w[1])
         nbytes = ctypes.c_size_t(0)
         with torch.cuda.device(dev):
-            _lib.check(self.lib.rp_spectral_irls_workspace_bytes(self.n_slots, max_nodes, max_edges, ctypes.byref(nbytes)),
+            n_slots = self.n_slots
+            if n_slots <= 0:
+                nd = ctypes.c_int(0)
+                _lib.check(self.lib.rp_solve_default_slots(max_nodes, 1, 1, 8, ctypes.byref(nd)), "rp_solve_default_slots")
+                n_slots = max(1, min(B, nd.value))
+            _lib.check(self.lib.rp_spectral_irls_workspace_bytes(n_slots, max_nodes, max_edges, ctypes.byref(nbytes)),
                        "rp_spectral_irls_workspace_bytes")
             ws = torch.empty(nbytes.value, dtype=torch.uint8, device=dev)
             T = torch.empty((B, 4, 4), dtype=torch.float64, device=dev)
@@ -389,7 +460,7 @@ class PoseSolver(object):
             ptr = lambda t: t.data_ptr() if t is not None else None                              # noqa: E731
             rc = self.lib.rp_spectral_irls_solve(B, t_off.data_ptr(), t_sp.data_ptr(), t_sn.data_ptr(), t_tp.data_ptr(),
                                                  t_tn.data_ptr(), ptr(t_wp), ptr(t_wn), ptr(t_eo), ptr(t_rc), ptr(t_ew),
-                                                 par.data_ptr(), None, max_nodes, self.n_slots, max_edges,
+                                                 par.data_ptr(), None, max_nodes, n_slots, max_edges,
                                                  ws.data_ptr(), ws.numel(), T.data_ptr(), status.data_ptr(), stats.data_ptr(),
                                                  torch.cuda.current_stream().cuda_stream)
             _lib.check(rc, "rp_spectral_irls_solve")

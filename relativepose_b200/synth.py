@@ -174,3 +174,76 @@ def make_texture_image(seed, H=160, W=640):
         m = 1.0 / (1.0 + np.exp((np.sqrt((xx - x) ** 2 + (yy - y) ** 2) - r) / 1.2))
         img = img * (1 - m[:, :, None]) + m[:, :, None] * rs.rand(3)
     return (img * 255).astype(np.uint8)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# A geometrically consistent scan pair: the inside of a textured box room rendered into the reference's 160x640 four-face
+# skybox (util.Pano2PointCloud 'suncg' convention, util.py:755-773: face i looks along -z of Rs[i], x = (col/h-0.5)*2,
+# y = (0.5-row/h)*2, depth = distance along the face axis).  Used by the RelativePoseEstimationViaCompletion golden
+# (tests/golden/make_via_completion_golden.py) and the alternation benchmark: the two scans see the same walls, so the
+# warp, the blend and the matcher get consistent geometry (random panoramas do not overlap in 3-D).
+_SKYBOX_RS = np.array([[[1, 0, 0], [0, 1, 0], [0, 0, 1]],
+                       [[0, 0, -1], [0, 1, 0], [1, 0, 0]],
+                       [[-1, 0, 0], [0, 1, 0], [0, 0, -1]],
+                       [[0, 0, 1], [0, 1, 0], [-1, 0, 0]]], dtype=np.float64)
+
+
+def _room_texture(rs, res=48):
+    """Per-wall low-resolution colour tiles (piecewise constant: corners for a SIFT detector) plus smooth shading."""
+    return rs.rand(6, res, res, 3), rs.uniform(0.5, 3.0, size=(6, 3, 2)), rs.uniform(0, 6.28, size=(6, 3, 2))
+
+
+def render_room_scan(T_w2c, half, tex, H=160):
+    """Render one scan.  T_w2c [4,4] world -> camera, half = box half-extents (x, y, z).  Returns the reference's scan dict
+    {'rgb' [H,4H,3] in [0,1], 'norm' [H,4H,3] unit normals in the camera frame, 'depth' [H,4H]} (float64)."""
+    tiles, freq, phase = tex
+    res = tiles.shape[1]
+    R_c2w = T_w2c[:3, :3].T
+    o = -R_c2w @ T_w2c[:3, 3]                                   # camera centre in the world
+    ys, xs = np.meshgrid(np.arange(H), np.arange(H), indexing='ij')
+    ys, xs = (0.5 - ys / H) * 2, (xs / H - 0.5) * 2
+    rgb = np.zeros((H, 4 * H, 3)); nrm = np.zeros((H, 4 * H, 3)); dep = np.zeros((H, 4 * H))
+    for i in range(4):
+        d_face = np.stack((xs.ravel(), ys.ravel(), -np.ones(H * H)), 0)          # z-depth 1 along the face axis
+        d_w = R_c2w @ (_SKYBOX_RS[i] @ d_face)                                    # [3, H*H]
+        with np.errstate(divide='ignore', invalid='ignore'):
+            t_hi = (np.asarray(half)[:, None] - o[:, None]) / d_w
+            t_lo = (-np.asarray(half)[:, None] - o[:, None]) / d_w
+        t_ax = np.where(d_w > 0, t_hi, np.where(d_w < 0, t_lo, np.inf))           # exit distance per axis
+        ax = np.argmin(t_ax, 0)
+        t = t_ax[ax, np.arange(H * H)]
+        p = o[:, None] + d_w * t                                                  # world hit point
+        sign = np.sign(d_w[ax, np.arange(H * H)])
+        wall = 2 * ax + (sign > 0)
+        n_w = np.zeros((3, H * H)); n_w[ax, np.arange(H * H)] = -sign             # inward normal
+        ua, va = (ax + 1) % 3, (ax + 2) % 3
+        u = p[ua, np.arange(H * H)]; v = p[va, np.arange(H * H)]
+        hu = np.asarray(half)[ua]; hv = np.asarray(half)[va]
+        iu = np.clip(((u / hu * 0.5 + 0.5) * res).astype(int), 0, res - 1)
+        iv = np.clip(((v / hv * 0.5 + 0.5) * res).astype(int), 0, res - 1)
+        col = tiles[wall, iu, iv]                                                 # [H*H,3]
+        shade = 0.5 + 0.5 * np.sin(freq[wall, :, 0] * u[:, None] + phase[wall, :, 0]) * np.sin(freq[wall, :, 1] * v[:, None] + phase[wall, :, 1])
+        col = 0.7 * col + 0.3 * shade
+        rgb[:, i * H:(i + 1) * H] = col.reshape(H, H, 3)
+        nrm[:, i * H:(i + 1) * H] = (T_w2c[:3, :3] @ n_w).T.reshape(H, H, 3)
+        dep[:, i * H:(i + 1) * H] = t.reshape(H, H)
+    return {'rgb': rgb, 'norm': nrm, 'depth': dep}
+
+
+def make_room_scan_pair(seed, max_yaw=0.6, max_shift=0.4, tex_res=48):
+    """Two scans of one room.  Returns (data_s, data_t, R_gt) with R_gt [4,4] mapping source-camera to target-camera
+    coordinates (the convention of rpmodule.py:616-617: ``warping(view_s, R_hat)``)."""
+    rs = np.random.RandomState(seed)
+    half = np.array([rs.uniform(2.0, 3.5), rs.uniform(1.2, 1.6), rs.uniform(2.0, 3.5)])
+    tex = _room_texture(rs, tex_res)
+
+    def cam():
+        yaw, tilt = rs.uniform(-max_yaw, max_yaw), rs.uniform(-0.05, 0.05)
+        cy, sy, ct, st = np.cos(yaw), np.sin(yaw), np.cos(tilt), np.sin(tilt)
+        R = np.array([[cy, 0, sy], [0, 1, 0], [-sy, 0, cy]]) @ np.array([[1, 0, 0], [0, ct, -st], [0, st, ct]])
+        T = np.eye(4)
+        T[:3, :3] = R
+        T[:3, 3] = -R @ (rs.uniform(-max_shift, max_shift, 3) * np.array([1, 0.3, 1]))
+        return T
+    Ts, Tt = cam(), cam()
+    return render_room_scan(Ts, half, tex), render_room_scan(Tt, half, tex), Tt @ np.linalg.inv(Ts)

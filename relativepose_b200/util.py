@@ -3,7 +3,7 @@ every alternation of RelativePoseEstimationViaCompletion (SURVEY.md section 8f r
 
   warping(view, R, dataList)            util.py:94-172   (+ reproj_helper :537-749, depth2pc :468-523)
   Pano2PointCloud(depth, dataList)      util.py:751-811
-  apply_mask(x, maskMethod)             util.py:209-232
+  apply_mask(x, maskMethod, *arg)       util.py:209-232
   blend_completion(...)                 RPModule/rpmodule.py:628-634 (not a function of its own in the reference)
 
 The ``*_device`` forms take / return CUDA tensors and whole batches (one launch pair per call, no host round trip);
@@ -100,21 +100,28 @@ def Pano2PointCloud(depth, dataList):
     return pc.cpu().numpy()
 
 
-def apply_mask(x, maskMethod):
-    """util.apply_mask (util.py:209-232) for the two masks the pipeline uses: 'second' observes skybox face 1 (columns
-    h..2h), 'kinect' a 66x88 window of it.  x: torch [n,c,h,w].  Returns (masked x, mask [n,1,h,w])."""
+def apply_mask(x, maskMethod, *arg):
+    """util.apply_mask (util.py:209-232).  x: torch [n,c,h,w].  Returns the reference's 3-tuple (masked x, mask [n,1,h,w],
+    geow [n,1,h,w]): 'second' observes skybox face 1 (columns h..2h) and geow = exp(-d/(2*0.7^2)) of the normalised column
+    distance d to the nearest face border, zero on the observed face (:215-222); 'kinect' observes a 66x88 window of that
+    face and geow = 1 - mask (:223-229).  Any other maskMethod leaves mask and geow all zero, as the reference does."""
     import torch
     h, w = x.shape[2], x.shape[3]
     m = torch.zeros((x.shape[0], 1, h, w), dtype=x.dtype, device=x.device)
+    geow = torch.zeros((x.shape[0], 1, h, w), dtype=x.dtype, device=x.device)
     if maskMethod == 'second':
         m[:, :, :h, h:2 * h] = 1
+        xs = np.arange(w)
+        dist = np.stack((np.abs(xs - h), np.abs(xs - 2 * h), np.abs(xs - w - h), np.abs(xs - w - 2 * h)), 0).min(0) / h
+        dist = np.exp(-dist / (2 * 0.7 ** 2))
+        dist[h:2 * h] = 0
+        geow[:] = torch.as_tensor(dist, dtype=x.dtype, device=x.device)[None, None, None, :]
     elif maskMethod == 'kinect':
         assert w == 640 and h == 160
         dw, dh = int(89.67 // 2), int(67.25 // 2)
         m[:, :, 80 - dh:80 + dh, 160 + 80 - dw:160 + 80 + dw] = 1
-    else:
-        raise ValueError("unknown maskMethod %r" % (maskMethod,))
-    return x * m, m
+        geow = 1 - m
+    return x * m, m, geow
 
 
 def blend_completion_device(f, mask, norm_gt, depth_gt):
