@@ -367,7 +367,7 @@ def run_c4(torch, dev, rank, world, total_pairs, barrier, max_over_ranks):
     from relativepose_b200 import pipeline, sharding, synth
     from relativepose_b200.model.mymodel import SCNet
     from relativepose_b200.RPModule.rputil import opts
-    lo, hi = sharding.shard_bounds(total_pairs, world, rank)
+    lo, hi = sharding.shard_bounds(total_pairs, rank, world)
     mine = hi - lo
     torch.manual_seed(0)
     snet = SCNet(types.SimpleNamespace(batchnorm=1, useTanh=0, skipLayer=1, outputType='rgbdnsf', snumclass=21)).to(dev)

@@ -106,6 +106,10 @@ typedef struct rp_debug {
 
 int rp_abi_version(void);
 
+/* 16-bit operand / activation-storage format of the tensor-core convolution kernels: 1 = IEEE half (default build),
+ * 0 = bfloat16.  Buffers with rp_conv_src.dtype == 1 / out_dtype == 1 hold this format. */
+int rp_h16_format(void);
+
 /* Number of SMs / device name of the current CUDA device (host utility). */
 int rp_device_info(int* sm_count, int* cc_major, int* cc_minor, size_t* total_mem);
 

@@ -24,33 +24,49 @@ def _nvcc():
     raise RuntimeError("nvcc not found")
 
 
-def _stale(out, srcs):
+def _stale(out, deps):
     if not os.path.exists(out):
         return True
     t = os.path.getmtime(out)
-    deps = list(srcs) + [os.path.join(INCLUDE, f) for f in os.listdir(INCLUDE)]
-    deps += [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
     return any(os.path.getmtime(d) > t for d in deps)
 
 
 def build_all(force=False, verbose=False):
+    """Each .cu is compiled to an object (only when stale, in parallel), then linked into the one shared library."""
+    from concurrent.futures import ThreadPoolExecutor
     built = []
+    objdir = os.path.join(HERE, "build")
+    os.makedirs(objdir, exist_ok=True)
+    headers = [os.path.join(INCLUDE, f) for f in os.listdir(INCLUDE)]
+    headers += [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
     for out, srcs in LIBS.items():
         outp = os.path.join(HERE, out)
-        srcp = [os.path.join(CSRC, s) for s in srcs]
-        if not force and not _stale(outp, srcp):
-            continue
-        cmd = [_nvcc()] + NVCC_FLAGS + ["-I", INCLUDE, "-o", outp] + srcp
-        if verbose:
-            cmd.insert(1, "-Xptxas")
-            cmd.insert(2, "-v")
-            print(" ".join(cmd))
-        r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
-        if r.returncode != 0:
-            raise RuntimeError("nvcc failed for %s:\n%s" % (out, r.stdout))
-        if verbose:
-            print(r.stdout)
-        built.append(out)
+        jobs, objs = [], []
+        for sname in srcs:
+            src = os.path.join(CSRC, sname)
+            obj = os.path.join(objdir, sname[:-3] + ".o")
+            objs.append(obj)
+            if force or _stale(obj, [src] + headers):
+                cmd = [_nvcc()] + [f for f in NVCC_FLAGS if f != "-shared"] + ["-I", INCLUDE, "-c", "-o", obj, src]
+                if verbose:
+                    cmd[1:1] = ["-Xptxas", "-v"]
+                jobs.append((sname, cmd))
+
+        def run(job):
+            r = subprocess.run(job[1], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+            return job[0], r.returncode, r.stdout
+        with ThreadPoolExecutor(max_workers=max(1, min(len(jobs), os.cpu_count() or 1))) as ex:
+            for name, rc, log in ex.map(run, jobs):
+                if rc != 0:
+                    raise RuntimeError("nvcc failed for %s:\n%s" % (name, log))
+                if verbose:
+                    print("== %s\n%s" % (name, log))
+        if jobs or force or _stale(outp, objs):
+            r = subprocess.run([_nvcc(), "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", outp] + objs,
+                               stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+            if r.returncode != 0:
+                raise RuntimeError("link failed for %s:\n%s" % (out, r.stdout))
+            built.append(out)
     return built
 
 

@@ -159,6 +159,52 @@ __device__ float numpy_sqdist_f32_seq(const float* __restrict__ s, const float* 
     return res;
 }
 
+// ---- 32-channel descriptors, one source row per thread (phase A of the fused kernel) ---------------------------------
+// Packed float32 pairs (FADD2 / FMUL2 on sm_100a): subtraction and squaring are element-wise IEEE operations, so the pair
+// forms give the same bits as the scalar ones with half the instructions.  The *additions* stay scalar: ptxas contracts a
+// mul.rn.f32x2 feeding an add.rn.f32x2 into FFMA2 (it honours .rn only for the scalar forms), which would change dij.
+__device__ __forceinline__ unsigned long long f32x2_sub(unsigned long long a, unsigned long long b) {
+    unsigned long long d;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ unsigned long long f32x2_sq(unsigned long long a) {
+    unsigned long long d;
+    asm("mul.rn.f32x2 %0, %1, %1;" : "=l"(d) : "l"(a));
+    return d;
+}
+__device__ __forceinline__ void f32x2_unpack(unsigned long long v, float& lo, float& hi) {
+    lo = __uint_as_float((unsigned)(v & 0xffffffffull)); hi = __uint_as_float((unsigned)(v >> 32));
+}
+// sq[c] = (s[c] - t[c])^2 for the 32 channels; s in registers as 16 packed pairs, t from shared memory (16-byte aligned row)
+__device__ __forceinline__ void sqdiff32(const unsigned long long (&s)[16], const float* __restrict__ t, float (&sq)[32]) {
+    const ulonglong2* t2 = reinterpret_cast<const ulonglong2*>(t);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        const ulonglong2 tv = t2[q];
+        f32x2_unpack(f32x2_sq(f32x2_sub(s[2 * q], tv.x)), sq[4 * q], sq[4 * q + 1]);
+        f32x2_unpack(f32x2_sq(f32x2_sub(s[2 * q + 1], tv.y)), sq[4 * q + 2], sq[4 * q + 3]);
+    }
+}
+// NumPy's pairwise float32 add.reduce of 32 values (8 accumulators, see numpy_sqdist_f32) / the plain sequential sum
+__device__ __forceinline__ float sum32_numpy(const float (&sq)[32]) {
+    float r[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) r[j] = sq[j];
+#pragma unroll
+    for (int i = 8; i < 32; i += 8)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) r[j] = __fadd_rn(r[j], sq[i + j]);
+    return __fadd_rn(__fadd_rn(__fadd_rn(r[0], r[1]), __fadd_rn(r[2], r[3])),
+                     __fadd_rn(__fadd_rn(r[4], r[5]), __fadd_rn(r[6], r[7])));
+}
+__device__ __forceinline__ float sum32_seq(const float (&sq)[32]) {
+    float res = sq[0];
+#pragma unroll
+    for (int i = 1; i < 32; ++i) res = __fadd_rn(res, sq[i]);
+    return res;
+}
+
 // (a0*b0 + a1*b1) + a2*b2 with separately rounded products: NumPy's (a*b).sum(1) on [P,3].
 __device__ __forceinline__ double dot3_np(double a0, double a1, double a2, double b0, double b1, double b2) {
     return __dadd_rn(__dadd_rn(__dmul_rn(a0, b0), __dmul_rn(a1, b1)), __dmul_rn(a2, b2));
@@ -884,10 +930,10 @@ __device__ void residual_to_h(const PairView& pv) {
 }
 
 // Phase C: conservative float32 pre-test of the distance-consistency condition (rpmodule.py:399-404).
-// The source distance depends only on the source keypoint pair (i1,i2) and is shared by the KK*KK
-// correspondence pairs built on it: lanes hold i2 (and the KK target points of its correspondences in
-// registers), i1 is broadcast, and each (k1,k2) costs one 3-d distance.  Each lane records its keeps in a
-// KK*KK-bit mask; one warp scan per (i1, 32 x i2) cell then appends them to the per-warp stage buffer,
+// The source distance depends only on the source keypoint pair (i1,i2) and is shared by the KK*KK correspondence pairs
+// built on it.  The n_s(n_s-1)/2 source pairs are enumerated in row-major triangular order, one per lane (every lane of
+// every warp step is busy, whatever n_s is): the lane loads both keypoints and their 2*KK target points and runs the KK*KK
+// tests, recording its keeps in a KK*KK-bit mask; one warp scan per step then appends them to the per-warp stage buffer,
 // which is flushed 32 entries at a time into the candidate list.
 template <int KK>
 __device__ void pretest_pairs(Shared& sh, const PairView& pv, float tau, float sep2, long long edge_cap) {
@@ -896,23 +942,24 @@ __device__ void pretest_pairs(Shared& sh, const PairView& pv, float tau, float s
     const float4* sp4 = pv.sp4; const float4* tq4 = pv.tq4;
     unsigned* stg = sh.stage[warp];
     int nst = 0;                                                     // staged entries (warp-uniform)
-    const int nchunk = (ns + 31) >> 5;
-    // (i2-chunk, i1) cells, i1 <= last i2 of the chunk; cells are dealt round-robin to the warps
-    for (int ch = 0; ch < nchunk; ++ch) {
-        const int i2 = (ch << 5) + lane;
-        const bool v2 = i2 < ns;
-        const int i2c = v2 ? i2 : ns - 1;
-        const float4 p2 = sp4[i2c];
-        float4 q2[KK];
+    const int P = ns * (ns - 1) / 2;
+    for (int p0 = warp * 32; p0 < P; p0 += T) {
+        {
+            const int p = p0 + lane;
+            const bool vs0 = p < P;
+            const int pc = vs0 ? p : P - 1;
+            int i2 = (int)((1.0f + sqrtf(1.0f + 8.0f * (float)pc)) * 0.5f);      // largest i2 with i2 (i2 - 1) / 2 <= pc
+            while (i2 * (i2 - 1) / 2 > pc) --i2;
+            while ((i2 + 1) * i2 / 2 <= pc) ++i2;
+            const int i1 = pc - i2 * (i2 - 1) / 2;                                // 0 <= i1 < i2
+            const float4 p1 = sp4[i1], p2 = sp4[i2];
+            float4 q2[KK];
 #pragma unroll
-        for (int k = 0; k < KK; ++k) q2[k] = tq4[i2c * KK + k];
-        const int i1_end = min(ns - 1, (ch << 5) + 31);              // i1 < i2 <= chunk end
-        for (int i1 = warp; i1 < i1_end; i1 += NWARP) {
-            const float4 p1 = sp4[i1];
+            for (int k = 0; k < KK; ++k) q2[k] = tq4[i2 * KK + k];
             float ax = p1.x - p2.x, ay = p1.y - p2.y, az = p1.z - p2.z;
             float S = ax * ax + ay * ay + az * az;
             float ds = S * rsqrt_approx(S + 1e-30f);
-            const bool vs = v2 && (i2 > i1) && (S > sep2);          // min(ds,dt) > sep  =>  ds > sep
+            const bool vs = vs0 && (S > sep2);                      // min(ds,dt) > sep  =>  ds > sep
             unsigned long long keepm = 0ull;
 #pragma unroll
             for (int k1 = 0; k1 < KK; ++k1) {
@@ -1071,6 +1118,84 @@ __global__ void __launch_bounds__(T, RP_MIN_BLOCKS) rp_solve_kernel(const SolveA
                 tfeat[j * ts + c] = __fdiv_rn(ft[e], FEAT_SCALING);    // rpmodule.py:343
             }
             __syncthreads();
+            if (D == 32 && vec4 && (reinterpret_cast<uintptr_t>(A.feat_s) & 15) == 0) {
+                // One source keypoint per THREAD: its 32 channels live in registers, the target rows are read from shared
+                // memory as warp-wide broadcasts, and distance, soft-match norm and the top-k list are all thread-local --
+                // no shuffles, no per-(i,j) division (candidates are ranked by dij * (1/den), a monotone image of the
+                // reference's exp(-dij/den); the exact quotient is only formed for entries that reach the norm or the list).
+                const double rden_obs = 1.0 / par.feat_den_obs, rden_any = 1.0 / par.feat_den;
+                for (int i0 = 0; i0 < ns; i0 += T) {
+                    const int i = i0 + tid;
+                    const bool act = i < ns;
+                    const int ic = act ? i : ns - 1;
+                    unsigned long long sreg[16];
+                    {
+                        const float4* fs4 = reinterpret_cast<const float4*>(A.feat_s + (size_t)(s0 + ic) * 32);
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) {
+                            const float4 v = fs4[q];
+                            const float a0 = __fdiv_rn(v.x, FEAT_SCALING), a1 = __fdiv_rn(v.y, FEAT_SCALING);      // :342
+                            const float a2 = __fdiv_rn(v.z, FEAT_SCALING), a3 = __fdiv_rn(v.w, FEAT_SCALING);
+                            sreg[2 * q] = (unsigned long long)__float_as_uint(a0) | ((unsigned long long)__float_as_uint(a1) << 32);
+                            sreg[2 * q + 1] = (unsigned long long)__float_as_uint(a2) | ((unsigned long long)__float_as_uint(a3) << 32);
+                        }
+                    }
+                    const double wsi = A.w_s[s0 + ic];
+                    double lk[KMAX]; int li[KMAX];
+#pragma unroll
+                    for (int k = 0; k < KMAX; ++k) { lk[k] = CUDART_INF; li[k] = 0x7fffffff; }
+                    double ss = 0.0;
+                    for (int j = 0; j < nt; ++j) {
+                        float sq[32];
+                        sqdiff32(sreg, tfeat + j * ts, sq);
+                        const float dij = seq_sum ? sum32_seq(sq) : sum32_numpy(sq);                       // :355
+                        if (A.has_dbg && A.dbg.dij && act) A.dbg.dij[A.dbg.dij_off[b] + (int64_t)i * nt + j] = dij;
+                        const bool obs = __dmul_rn(wsi, __ldg(A.w_t + t0 + j)) == 1.0;                     // :354
+                        const double qk = (double)dij * (obs ? rden_obs : rden_any);                       // ranks like -key
+                        if (qk < 372.6000001) {                // below -372.6 exp(key)^2 < 2^-1075 rounds to +0: a no-op in the norm
+                            const double key = (double)(-dij) / (obs ? par.feat_den_obs : par.feat_den);   // :356-358
+                            if (key > -372.6) { const double e = exp(key); ss += e * e; }
+                        }
+                        if (qk < lk[KMAX - 1]) {               // strict: of equal keys the lower index stays ahead
+                            double ck = qk; int ci = j;
+#pragma unroll
+                            for (int k = 0; k < KMAX; ++k) {
+                                if (ck < lk[k]) { const double tk = lk[k]; const int ti = li[k]; lk[k] = ck; li[k] = ci; ck = tk; ci = ti; }
+                            }
+                        }
+                    }
+                    if (act) {
+                        const double nm = sqrt(ss);                                                        // :359
+#pragma unroll
+                        for (int k = 0; k < KMAX; ++k) {
+                            if (k < K) {
+                                int idx = li[k];
+                                double f = 0.0;
+                                if (idx == 0x7fffffff) idx = k < nt ? k : 0;      // NaN descriptors: arbitrary but valid
+                                else if (nm != 0.0) {
+                                    float sq[32];
+                                    sqdiff32(sreg, tfeat + idx * ts, sq);
+                                    const float dk = seq_sum ? sum32_seq(sq) : sum32_numpy(sq);
+                                    const bool obs = __dmul_rn(wsi, __ldg(A.w_t + t0 + idx)) == 1.0;
+                                    f = exp((double)(-dk) / (obs ? par.feat_den_obs : par.feat_den)) / nm;  // :360-363
+                                }
+                                if (nm == 0.0 && A.zero_row_topk) {                // all-zero row: numpy's tie order (host supplied)
+                                    const int z = A.zero_row_topk[(size_t)b * A.max_topk + k];
+                                    if (z >= 0 && z < nt) idx = z;
+                                }
+                                const int c = i * K + k;
+                                pv.cj[c] = idx;
+                                pv.geo[G_F * pv.gstride + c] = f;
+                                if (A.has_dbg && A.dbg.topk_idx) A.dbg.topk_idx[(size_t)(s0 + i) * A.max_topk + k] = idx;
+                                if (A.has_dbg && A.dbg.topk_f) A.dbg.topk_f[(size_t)(s0 + i) * A.max_topk + k] = f;
+                            } else if (k < A.max_topk) {
+                                if (A.has_dbg && A.dbg.topk_idx) A.dbg.topk_idx[(size_t)(s0 + i) * A.max_topk + k] = -1;
+                                if (A.has_dbg && A.dbg.topk_f) A.dbg.topk_f[(size_t)(s0 + i) * A.max_topk + k] = 0.0;
+                            }
+                        }
+                    }
+                }
+            } else
             for (int i = warp; i < ns; i += NWARP) {
                 const float* fs = A.feat_s + (size_t)(s0 + i) * D;
                 for (int c = lane; c < D; c += 32) sh.sfeat[warp][c] = __fdiv_rn(fs[c], FEAT_SCALING);   // :342
@@ -1233,11 +1358,66 @@ __global__ void __launch_bounds__(T, RP_MIN_BLOCKS) rp_solve_kernel(const SolveA
         }
 
         // ------------------------------------------------------------------ D. exact tests + pair weight (:399-467)
+        // Stage 1, every candidate: the exact float64 distance test in NumPy's operation order (counts M1), then a cheap
+        // rejection of the three angle conditions -- |acos x - acos y| < th  <=>  x y + sqrt((1-x^2)(1-y^2)) > cos th on
+        // [0, pi], one square root instead of two acos -- with a 1e-9 margin that can only let a pair THROUGH.  Candidates
+        // that are not certainly rejected (a fifth of them) are compacted into a survivor list.  Stage 2, survivors only,
+        // all lanes busy: the reference's own arithmetic (six acos, the filters exactly as :430-436, the pair weight).
         if (!A.solve_only) {
             const int gs = pv.gstride; const double* geo = pv.geo;
+            unsigned* surv = reinterpret_cast<unsigned*>(pv.cols);      // the CSR arrays are not built yet
             int m1 = 0, m2 = 0, nz = 0;
             double wloc = 0.0;
-            for (int e = tid; e < MC; e += T) {
+            const double th = sqrt(par.angle_thre_sq);
+            const bool cheap = th > 0.0 && th < 3.14159;                // otherwise everything goes to stage 2
+            const double cth = cheap ? cos(th) - 1e-9 : -4.0;
+            for (int e0 = 0; e0 < MC; e0 += T) {
+                const int e = e0 + tid;
+                bool maybe = false;
+                if (e < MC) {
+                    unsigned rc = pv.edges[e];
+                    int r = rc >> 16, c = rc & 0xffffu;
+                    double ax = geo[G_PX * gs + r] - geo[G_PX * gs + c], ay = geo[G_PY * gs + r] - geo[G_PY * gs + c], az = geo[G_PZ * gs + r] - geo[G_PZ * gs + c];
+                    double bx = geo[G_QX * gs + r] - geo[G_QX * gs + c], by = geo[G_QY * gs + r] - geo[G_QY * gs + c], bz = geo[G_QZ * gs + r] - geo[G_QZ * gs + c];
+                    double dis_s = sqrt(dot3_np(ax, ay, az, ax, ay, az));                // :399
+                    double dis_t = sqrt(dot3_np(bx, by, bz, bx, by, bz));                // :400
+                    double df = dis_s - dis_t;
+                    double dd = __dmul_rn(df, df);                                       // :401
+                    if ((dd < par.dist_thre_sq) && (fmin(dis_s, dis_t) > par.sep_thre)) {   // :404
+                        ++m1;
+                        maybe = true;
+                        double n1x = geo[G_NX * gs + r], n1y = geo[G_NY * gs + r], n1z = geo[G_NZ * gs + r];
+                        double n2x = geo[G_NX * gs + c], n2y = geo[G_NY * gs + c], n2z = geo[G_NZ * gs + c];
+                        double m1x = geo[G_MX * gs + r], m1y = geo[G_MY * gs + r], m1z = geo[G_MZ * gs + r];
+                        double m2x = geo[G_MX * gs + c], m2y = geo[G_MY * gs + c], m2z = geo[G_MZ * gs + c];
+                        double x = clip1(dot3_np(n1x, n1y, n1z, n2x, n2y, n2z)), y = clip1(dot3_np(m1x, m1y, m1z, m2x, m2y, m2z));
+                        if (x * y + sqrt((1.0 - x * x) * (1.0 - y * y)) < cth) maybe = false;
+                        else {
+                            const double is = 1.0 / dis_s, it = 1.0 / dis_t;
+                            double e1x = ax * is, e1y = ay * is, e1z = az * is;
+                            double e2x = bx * it, e2y = by * it, e2z = bz * it;
+                            x = clip1(dot3_np(n1x, n1y, n1z, e1x, e1y, e1z)); y = clip1(dot3_np(m1x, m1y, m1z, e2x, e2y, e2z));
+                            if (x * y + sqrt((1.0 - x * x) * (1.0 - y * y)) < cth) maybe = false;
+                            else {
+                                x = clip1(dot3_np(n2x, n2y, n2z, e1x, e1y, e1z)); y = clip1(dot3_np(m2x, m2y, m2z, e2x, e2y, e2z));
+                                if (x * y + sqrt((1.0 - x * x) * (1.0 - y * y)) < cth) maybe = false;
+                            }
+                        }
+                    }
+                    if (!maybe) pv.ew[e] = -1.0;
+                }
+                const unsigned bal = __ballot_sync(0xffffffffu, maybe);
+                if (bal) {
+                    int base = 0;
+                    if (lane == 0) base = atomicAdd(&sh.cnt[7], __popc(bal));
+                    base = __shfl_sync(0xffffffffu, base, 0);
+                    if (maybe) surv[base + __popc(bal & ((1u << lane) - 1u))] = (unsigned)e;
+                }
+            }
+            __syncthreads();
+            const int NSV = sh.cnt[7];
+            for (int sidx = tid; sidx < NSV; sidx += T) {
+                const int e = (int)surv[sidx];
                 unsigned rc = pv.edges[e];
                 int r = rc >> 16, c = rc & 0xffffu;
                 double ax = geo[G_PX * gs + r] - geo[G_PX * gs + c], ay = geo[G_PY * gs + r] - geo[G_PY * gs + c], az = geo[G_PZ * gs + r] - geo[G_PZ * gs + c];
@@ -1247,8 +1427,7 @@ __global__ void __launch_bounds__(T, RP_MIN_BLOCKS) rp_solve_kernel(const SolveA
                 double df = dis_s - dis_t;
                 double dd = __dmul_rn(df, df);                                       // :401
                 double w = -1.0;
-                if ((dd < par.dist_thre_sq) && (fmin(dis_s, dis_t) > par.sep_thre)) {   // :404
-                    ++m1;
+                {
                     const double is = 1.0 / dis_s, it = 1.0 / dis_t;                    // :424-427 (a * (1/|a|), <= 1 ulp from a/|a|)
                     double e1x = ax * is, e1y = ay * is, e1z = az * is;
                     double e2x = bx * it, e2y = by * it, e2z = bz * it;

@@ -10,7 +10,7 @@
 //
 // This file: float32 CUDA-core implicit GEMM (exact-parity path, tolerance 1e-4 max-abs vs the reference
 // module) + resize / BN-finalise kernels.  The tcgen05 core for the large layers lives in scnet_tc.cu (round 2).
-#include <cuda_bf16.h>
+#include "rp_h16.cuh"
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
@@ -240,7 +240,7 @@ __global__ void bn_combine_kernel(const double* __restrict__ scratch, int nsplit
 constexpr int IC_PX = 32;                          // output pixels (one row segment) per block
 constexpr int IC_ROW = 512;                        // floats per staged input row: (IC_PX*s + k - s) * C <= IC_ROW
 __global__ void __launch_bounds__(256) im2col_bf16_kernel(const float* __restrict__ x, int n, int H, int W, int C, int k, int s, int p,
-                                                          int Hout, int Wout, int Kpad, __nv_bfloat16* __restrict__ out) {
+                                                          int Hout, int Wout, int Kpad, rp_h16* __restrict__ out) {
     // One block = 32 consecutive output pixels of one output row: the k input rows they read are staged in shared memory
     // once (coalesced), every (pixel, 8-K unit) item is then assembled from shared memory and written as one 16-byte store
     // (a warp writes 512 contiguous bytes).  Without the staging the kernel re-reads its input ~12x through L2.
@@ -273,14 +273,14 @@ __global__ void __launch_bounds__(256) im2col_bf16_kernel(const float* __restric
     for (int px = warp; px < IC_PX; px += 8) {     // a warp owns a pixel, its lanes the 8-K units: 512 contiguous bytes per store
         if (ox0 + px >= Wout) break;
         const float* pp = patch + px * s * C;
-        __nv_bfloat16* orow = out + (((size_t)im * Hout + oy) * Wout + ox0 + px) * Kpad;
+        rp_h16* orow = out + (((size_t)im * Hout + oy) * Wout + ox0 + px) * Kpad;
         for (int u = lane; u < units; u += 32) {
             float f[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) { const int e = s_tab[u * 8 + j]; f[j] = e >= 0 ? pp[e] : 0.f; }
-            __nv_bfloat162 v[4];
+            rp_h162 v[4];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) v[j] = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
+            for (int j = 0; j < 4; ++j) v[j] = rp_f2_to_h2(f[2 * j], f[2 * j + 1]);
             *reinterpret_cast<uint4*>(orow + u * 8) = *reinterpret_cast<uint4*>(v);
         }
     }
@@ -327,7 +327,7 @@ __global__ void scnet_resize_in_kernel(const float* __restrict__ x, int n, int H
 // x = hi + lo with hi = bf16(x), lo = bf16(x - hi).  Against weights packed as [w_hi | w_hi | w_lo | 0] one K=16 MMA
 // per tap computes x_hi*w_hi + x_lo*w_hi + x_hi*w_lo: float32-class accuracy (error ~2^-16) in the K slots a
 // 4-channel layer would otherwise pad with zeros.
-__global__ void scnet_resize_in_split_kernel(const float* __restrict__ x, int n, int H, int W, __nv_bfloat16* __restrict__ out) {
+__global__ void scnet_resize_in_split_kernel(const float* __restrict__ x, int n, int H, int W, rp_h16* __restrict__ out) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= n * 224 * 224) return;
     const int ox = idx % 224, oy = (idx / 224) % 224, im = idx / (224 * 224);
@@ -346,16 +346,16 @@ __global__ void scnet_resize_in_split_kernel(const float* __restrict__ x, int n,
     uint4* o = reinterpret_cast<uint4*>(out + (size_t)idx * 96);
 #pragma unroll
     for (int gq = 0; gq < 6; ++gq) {
-        __nv_bfloat16 hi[4], lo[4];
+        rp_h16 hi[4], lo[4];
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
             const float f = src[gq][c] >= 0 ? v[src[gq][c]] : 0.f;
-            hi[c] = __float2bfloat16_rn(f);
-            lo[c] = __float2bfloat16_rn(f - __bfloat162float(hi[c]));
+            hi[c] = rp_f_to_h(f);
+            lo[c] = rp_f_to_h(f - rp_h_to_f(hi[c]));
         }
-        __nv_bfloat16 u[16];
+        rp_h16 u[16];
 #pragma unroll
-        for (int c = 0; c < 4; ++c) { u[c] = hi[c]; u[4 + c] = lo[c]; u[8 + c] = hi[c]; u[12 + c] = __float2bfloat16_rn(0.f); }
+        for (int c = 0; c < 4; ++c) { u[c] = hi[c]; u[4 + c] = lo[c]; u[8 + c] = hi[c]; u[12 + c] = rp_f_to_h(0.f); }
         o[2 * gq] = *reinterpret_cast<uint4*>(&u[0]);
         o[2 * gq + 1] = *reinterpret_cast<uint4*>(&u[8]);
     }
@@ -441,14 +441,14 @@ __global__ void __launch_bounds__(128) conv3x3_small_cin(const ConvArgs A) {
         }
         const size_t e = (((size_t)(g * 2 + im) * A.Hout + oy) * A.Wout + ox) * A.out_pitch + A.out_ch_off;
         if (A.out_bf16) {          // bfloat16 storage: round first so the statistics describe the stored tensor
-            __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(A.out) + e;
+            rp_h16* op = reinterpret_cast<rp_h16*>(A.out) + e;
 #pragma unroll
             for (int j = 0; j < 32; j += 8) {
-                __nv_bfloat162 p[4];
+                rp_h162 p[4];
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
-                    p[q] = __floats2bfloat162_rn(acc[j + 2 * q], acc[j + 2 * q + 1]);
-                    const float2 f = __bfloat1622float2(p[q]);
+                    p[q] = rp_f2_to_h2(acc[j + 2 * q], acc[j + 2 * q + 1]);
+                    const float2 f = rp_h2_to_f2(p[q]);
                     acc[j + 2 * q] = f.x; acc[j + 2 * q + 1] = f.y;
                 }
                 *reinterpret_cast<uint4*>(op + j) = *reinterpret_cast<uint4*>(p);
@@ -697,7 +697,7 @@ __global__ void __launch_bounds__(128) conv1x1_head_kernel(const ConvArgs A) {
 #pragma unroll
                 for (int w = 0; w < NU; ++w) {
                     if (h16) {
-                        raw[u][w][0] = *reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(S.ptr) + e + 8 * w);
+                        raw[u][w][0] = *reinterpret_cast<const uint4*>(reinterpret_cast<const rp_h16*>(S.ptr) + e + 8 * w);
                     } else {
                         raw[u][w][0] = *reinterpret_cast<const uint4*>(S.ptr + e + 8 * w);
                         raw[u][w][1] = *reinterpret_cast<const uint4*>(S.ptr + e + 8 * w + 4);
@@ -713,9 +713,9 @@ __global__ void __launch_bounds__(128) conv1x1_head_kernel(const ConvArgs A) {
                     for (int q = 0; q < 8; ++q) v[u][q] = 0.f;
                     if (!val[u]) continue;
                     if (h16) {
-                        const __nv_bfloat162* hp = reinterpret_cast<const __nv_bfloat162*>(&raw[u][w][0]);
+                        const rp_h162* hp = reinterpret_cast<const rp_h162*>(&raw[u][w][0]);
 #pragma unroll
-                        for (int q = 0; q < 4; ++q) { const float2 f = __bfloat1622float2(hp[q]); v[u][2 * q] = f.x; v[u][2 * q + 1] = f.y; }
+                        for (int q = 0; q < 4; ++q) { const float2 f = rp_h2_to_f2(hp[q]); v[u][2 * q] = f.x; v[u][2 * q + 1] = f.y; }
                     } else {
                         v[u][0] = __uint_as_float(raw[u][w][0].x); v[u][1] = __uint_as_float(raw[u][w][0].y);
                         v[u][2] = __uint_as_float(raw[u][w][0].z); v[u][3] = __uint_as_float(raw[u][w][0].w);
@@ -853,7 +853,7 @@ int rp_im2col_bf16(const float* x, int n, int H, int W, int C, int k, int s, int
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
     if (k > 7 || (IC_PX * s + k - s) * C > IC_ROW) return RP_ERR_UNSUPPORTED;
     const size_t blocks = (size_t)n * Hout * ((Wout + IC_PX - 1) / IC_PX);
-    im2col_bf16_kernel<<<(unsigned)blocks, 256, 0, stream>>>(x, n, H, W, C, k, s, p, Hout, Wout, Kpad, static_cast<__nv_bfloat16*>(out));
+    im2col_bf16_kernel<<<(unsigned)blocks, 256, 0, stream>>>(x, n, H, W, C, k, s, p, Hout, Wout, Kpad, static_cast<rp_h16*>(out));
     ++g_conv_launches;
     return cudaGetLastError() == cudaSuccess ? RP_OK : RP_ERR_CUDA;
 }
@@ -871,7 +871,7 @@ int rp_scnet_resize_in_split(const float* x, int n, int H, int W, void* out, voi
     if (!x || !out || n < 1) return RP_ERR_INVALID_ARG;
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
     int total = n * 224 * 224;
-    scnet_resize_in_split_kernel<<<(total + 127) / 128, 128, 0, stream>>>(x, n, H, W, static_cast<__nv_bfloat16*>(out));
+    scnet_resize_in_split_kernel<<<(total + 127) / 128, 128, 0, stream>>>(x, n, H, W, static_cast<rp_h16*>(out));
     ++g_conv_launches;
     return cudaGetLastError() == cudaSuccess ? RP_OK : RP_ERR_CUDA;
 }

@@ -19,7 +19,7 @@
 // warp 13 issues tcgen05.mma into one of 2-8 accumulator sets in TMEM, warps 0-3 run the epilogue of earlier tiles
 // meanwhile (tcgen05.ld, bias/tanh, raw output fp32 or bf16 NHWC, deterministic per-tile partial batch statistics).
 // mbarriers only; no __syncthreads in the steady state.
-#include <cuda_bf16.h>
+#include "rp_h16.cuh"
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -210,8 +210,8 @@ __global__ void __launch_bounds__(CTA, 1) conv_halo_tc(const HaloArgs A, const u
 #pragma unroll
                         for (int q = 0; q < 8; ++q) { const float z = fmaf(v[q], sc[q], sh[q]); v[q] = z > 0.f ? z : slope * z; }
                     }
-                    __nv_bfloat162 p0 = __floats2bfloat162_rn(v[0], v[1]), p1 = __floats2bfloat162_rn(v[2], v[3]);
-                    __nv_bfloat162 p2 = __floats2bfloat162_rn(v[4], v[5]), p3 = __floats2bfloat162_rn(v[6], v[7]);
+                    rp_h162 p0 = rp_f2_to_h2(v[0], v[1]), p1 = rp_f2_to_h2(v[2], v[3]);
+                    rp_h162 p2 = rp_f2_to_h2(v[4], v[5]), p3 = rp_f2_to_h2(v[6], v[7]);
                     uint4 o;
                     o.x = *reinterpret_cast<uint32_t*>(&p0); o.y = *reinterpret_cast<uint32_t*>(&p1);
                     o.z = *reinterpret_cast<uint32_t*>(&p2); o.w = *reinterpret_cast<uint32_t*>(&p3);
@@ -234,9 +234,9 @@ __global__ void __launch_bounds__(CTA, 1) conv_halo_tc(const HaloArgs A, const u
                             const int h = hb + u * HSTEP;
                             if (pix[u] < 0) { *reinterpret_cast<uint4*>(dst + (size_t)h * 16) = make_uint4(0u, 0u, 0u, 0u); continue; }
                             float v[8];
-                            const __nv_bfloat162* hp = reinterpret_cast<const __nv_bfloat162*>(&x[u]);
+                            const rp_h162* hp = reinterpret_cast<const rp_h162*>(&x[u]);
 #pragma unroll
-                            for (int q = 0; q < 4; ++q) { const float2 f = __bfloat1622float2(hp[q]); v[2 * q] = f.x; v[2 * q + 1] = f.y; }
+                            for (int q = 0; q < 4; ++q) { const float2 f = rp_h2_to_f2(hp[q]); v[2 * q] = f.x; v[2 * q + 1] = f.y; }
                             finish(v, h);
                         }
                     }
@@ -412,18 +412,18 @@ __global__ void __launch_bounds__(CTA, 1) conv_halo_tc(const HaloArgs A, const u
                 }
                 if (A.out_bf16) {          // statistics describe what the consumer will read: the rounded values
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) v[j] = __bfloat162float(__float2bfloat16_rn(v[j]));
+                    for (int j = 0; j < 32; ++j) v[j] = rp_h_to_f(rp_f_to_h(v[j]));
                 }
                 if (valid) {
                     const int oy = a * A.ostr + A.cls_py[cls], ox = bcol * A.ostr + A.cls_px[cls];
                     const size_t opix = ((size_t)tc_.img * A.Hout + oy) * A.Wout + ox;
                     if (A.out_bf16) {
-                        __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(A.out) + opix * A.out_pitch + A.out_ch_off + co0;
+                        rp_h16* op = reinterpret_cast<rp_h16*>(A.out) + opix * A.out_pitch + A.out_ch_off + co0;
                         if (co0 + 31 < A.Cout) {
 #pragma unroll
                             for (int j = 0; j < 32; j += 8) {
-                                __nv_bfloat162 p0 = __floats2bfloat162_rn(v[j], v[j + 1]), p1 = __floats2bfloat162_rn(v[j + 2], v[j + 3]);
-                                __nv_bfloat162 p2 = __floats2bfloat162_rn(v[j + 4], v[j + 5]), p3 = __floats2bfloat162_rn(v[j + 6], v[j + 7]);
+                                rp_h162 p0 = rp_f2_to_h2(v[j], v[j + 1]), p1 = rp_f2_to_h2(v[j + 2], v[j + 3]);
+                                rp_h162 p2 = rp_f2_to_h2(v[j + 4], v[j + 5]), p3 = rp_f2_to_h2(v[j + 6], v[j + 7]);
                                 uint4 o;
                                 o.x = *reinterpret_cast<uint32_t*>(&p0); o.y = *reinterpret_cast<uint32_t*>(&p1);
                                 o.z = *reinterpret_cast<uint32_t*>(&p2); o.w = *reinterpret_cast<uint32_t*>(&p3);
@@ -431,7 +431,7 @@ __global__ void __launch_bounds__(CTA, 1) conv_halo_tc(const HaloArgs A, const u
                             }
                         } else {
 #pragma unroll
-                            for (int j = 0; j < 32; ++j) if (co0 + j < A.Cout) op[j] = __float2bfloat16_rn(v[j]);
+                            for (int j = 0; j < 32; ++j) if (co0 + j < A.Cout) op[j] = rp_f_to_h(v[j]);
                         }
                     } else {
                         float* op = reinterpret_cast<float*>(A.out) + opix * A.out_pitch + A.out_ch_off + co0;

@@ -9,7 +9,7 @@
 // tcgen05.commit signals an mbarrier, the epilogue reads the accumulator with tcgen05.ld (32 lanes x 32 columns
 // per warp and instruction).  Descriptor bit layouts follow cute/arch/mma_sm100_desc.hpp (UMMA::SmemDescriptor,
 // UMMA::InstrDescriptor).
-#include <cuda_bf16.h>
+#include "rp_h16.cuh"
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -206,7 +206,7 @@ __global__ void __launch_bounds__(CTA, 2) conv_igemm_tc(const scnet::ConvArgs A,
             if (v[j]) {
                 const size_t e = (((size_t)l_img[j] * A.Hin + iy) * A.Win + ix) * S.pitch + S.ch_off + c0;
                 if (h16) {
-                    x[j][0] = *reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(S.ptr) + e);
+                    x[j][0] = *reinterpret_cast<const uint4*>(reinterpret_cast<const rp_h16*>(S.ptr) + e);
                 } else {
                     const uint4* p = reinterpret_cast<const uint4*>(S.ptr + e);
                     x[j][0] = p[0];
@@ -245,9 +245,9 @@ __global__ void __launch_bounds__(CTA, 2) conv_igemm_tc(const scnet::ConvArgs A,
             if (vc[j]) {
                 float v[8];
                 if (h16) {
-                    const __nv_bfloat162* hp = reinterpret_cast<const __nv_bfloat162*>(&xc[j][0]);
+                    const rp_h162* hp = reinterpret_cast<const rp_h162*>(&xc[j][0]);
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) { const float2 f = __bfloat1622float2(hp[q]); v[2 * q] = f.x; v[2 * q + 1] = f.y; }
+                    for (int q = 0; q < 4; ++q) { const float2 f = rp_h2_to_f2(hp[q]); v[2 * q] = f.x; v[2 * q + 1] = f.y; }
                 } else {
                     v[0] = __uint_as_float(xc[j][0].x); v[1] = __uint_as_float(xc[j][0].y); v[2] = __uint_as_float(xc[j][0].z);
                     v[3] = __uint_as_float(xc[j][0].w); v[4] = __uint_as_float(xc[j][1].x); v[5] = __uint_as_float(xc[j][1].y);
@@ -257,8 +257,8 @@ __global__ void __launch_bounds__(CTA, 2) conv_igemm_tc(const scnet::ConvArgs A,
 #pragma unroll
                     for (int q = 0; q < 8; ++q) { float z = fmaf(v[q], sv[q], hv[q]); v[q] = z > 0.f ? z : slope * z; }
                 }
-                __nv_bfloat162 p0 = __floats2bfloat162_rn(v[0], v[1]), p1 = __floats2bfloat162_rn(v[2], v[3]);
-                __nv_bfloat162 p2 = __floats2bfloat162_rn(v[4], v[5]), p3 = __floats2bfloat162_rn(v[6], v[7]);
+                rp_h162 p0 = rp_f2_to_h2(v[0], v[1]), p1 = rp_f2_to_h2(v[2], v[3]);
+                rp_h162 p2 = rp_f2_to_h2(v[4], v[5]), p3 = rp_f2_to_h2(v[6], v[7]);
                 u.x = *reinterpret_cast<uint32_t*>(&p0); u.y = *reinterpret_cast<uint32_t*>(&p1);
                 u.z = *reinterpret_cast<uint32_t*>(&p2); u.w = *reinterpret_cast<uint32_t*>(&p3);
             }
@@ -291,14 +291,14 @@ __global__ void __launch_bounds__(CTA, 2) conv_igemm_tc(const scnet::ConvArgs A,
     // ---- epilogue (warps 0-3 own the TMEM lanes; all 8 warps help with the column sums)
     float* Tt = reinterpret_cast<float*>(smem);            // [128][33] transpose buffer
     float* op = nullptr;
-    __nv_bfloat16* oph = nullptr;
+    rp_h16* oph = nullptr;
     if (warp < 4) {
         const int m_l = tile_m * TM + row;
         if (m_l < Mc) {
             const int im = m_l / HW; const int rem = m_l - im * HW; const int a_l = rem / C.Wb, b_l = rem - a_l * C.Wb;
             const int oy = a_l * A.ostr + C.py, ox = b_l * A.ostr + C.px;
             const size_t e = (((size_t)(g * A.gsz + im) * A.Hout + oy) * A.Wout + ox) * A.out_pitch + A.out_ch_off;
-            if (A.out_bf16) oph = reinterpret_cast<__nv_bfloat16*>(A.out) + e; else op = A.out + e;
+            if (A.out_bf16) oph = reinterpret_cast<rp_h16*>(A.out) + e; else op = A.out + e;
         }
     }
     for (int c0 = 0; c0 < BN; c0 += 32) {
@@ -314,13 +314,13 @@ __global__ void __launch_bounds__(CTA, 2) conv_igemm_tc(const scnet::ConvArgs A,
             }
             if (A.out_bf16) {       // round to the storage type first: the statistics describe what the consumer reads
 #pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] = __bfloat162float(__float2bfloat16_rn(v[j]));
+                for (int j = 0; j < 32; ++j) v[j] = rp_h_to_f(rp_f_to_h(v[j]));
                 if (oph) {
                     if (co0 + 31 < A.Cout && (((size_t)(oph + co0)) & 15) == 0) {
 #pragma unroll
                         for (int j = 0; j < 32; j += 8) {
-                            __nv_bfloat162 p0 = __floats2bfloat162_rn(v[j], v[j + 1]), p1 = __floats2bfloat162_rn(v[j + 2], v[j + 3]);
-                            __nv_bfloat162 p2 = __floats2bfloat162_rn(v[j + 4], v[j + 5]), p3 = __floats2bfloat162_rn(v[j + 6], v[j + 7]);
+                            rp_h162 p0 = rp_f2_to_h2(v[j], v[j + 1]), p1 = rp_f2_to_h2(v[j + 2], v[j + 3]);
+                            rp_h162 p2 = rp_f2_to_h2(v[j + 4], v[j + 5]), p3 = rp_f2_to_h2(v[j + 6], v[j + 7]);
                             uint4 o;
                             o.x = *reinterpret_cast<uint32_t*>(&p0); o.y = *reinterpret_cast<uint32_t*>(&p1);
                             o.z = *reinterpret_cast<uint32_t*>(&p2); o.w = *reinterpret_cast<uint32_t*>(&p3);
@@ -328,7 +328,7 @@ __global__ void __launch_bounds__(CTA, 2) conv_igemm_tc(const scnet::ConvArgs A,
                         }
                     } else {
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) if (co0 + j < A.Cout) oph[co0 + j] = __float2bfloat16_rn(v[j]);
+                        for (int j = 0; j < 32; ++j) if (co0 + j < A.Cout) oph[co0 + j] = rp_f_to_h(v[j]);
                     }
                 }
             }
@@ -387,6 +387,10 @@ int launch_conv_tc(const scnet::ConvArgs& A, const void* wp, int nkt, cudaStream
 }  // namespace tc
 
 extern "C" {
+
+// 16-bit operand / activation format the library was built with: 1 = IEEE half, 0 = bfloat16 (rp_h16.cuh).
+int rp_h16_format(void) { return RP_H16_FP16 ? 1 : 0; }
+
 
 // Unit-test hook for the tcgen05 building blocks: C = A * B^T with bf16-rounded operands (device pointers).
 int rp_tc_gemm_test(const float* A, const float* B, float* C, int M, int N, int K, int bn, void* stream_) {

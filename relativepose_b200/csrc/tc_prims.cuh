@@ -2,7 +2,7 @@
 // convolution kernels (scnet_tc.cu, scnet_halo.cu).  Descriptor bit layouts follow cute/arch/mma_sm100_desc.hpp
 // (UMMA::SmemDescriptor, UMMA::InstrDescriptor).
 #pragma once
-#include <cuda_bf16.h>
+#include "rp_h16.cuh"
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -20,9 +20,11 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_
     return d;                                              // base_offset 0, lbo_mode 0, layout_type 0 (no swizzle)
 }
 
-// UMMA instruction descriptor: D=f32, A=B=bf16, both K-major, dense, M x N.
+// UMMA instruction descriptor: D=f32, A=B=the 16-bit operand format of rp_h16.cuh (a_format / b_format: 0 = f16, 1 = bf16),
+// both K-major, dense, M x N.
 __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
-    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+    return (1u << 4) | ((uint32_t)RP_H16_UMMA_FORMAT << 7) | ((uint32_t)RP_H16_UMMA_FORMAT << 10) |
+           ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
@@ -89,10 +91,10 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
 
 // 8 consecutive K elements of one row -> one 16-byte unit of the canonical layout
 __device__ __forceinline__ void store_core_row(unsigned char* tile, int rows, int row, int kc, const float* v8) {
-    __nv_bfloat162 p0 = __floats2bfloat162_rn(v8[0], v8[1]);
-    __nv_bfloat162 p1 = __floats2bfloat162_rn(v8[2], v8[3]);
-    __nv_bfloat162 p2 = __floats2bfloat162_rn(v8[4], v8[5]);
-    __nv_bfloat162 p3 = __floats2bfloat162_rn(v8[6], v8[7]);
+    rp_h162 p0 = rp_f2_to_h2(v8[0], v8[1]);
+    rp_h162 p1 = rp_f2_to_h2(v8[2], v8[3]);
+    rp_h162 p2 = rp_f2_to_h2(v8[4], v8[5]);
+    rp_h162 p3 = rp_f2_to_h2(v8[6], v8[7]);
     uint4 u;
     u.x = *reinterpret_cast<uint32_t*>(&p0); u.y = *reinterpret_cast<uint32_t*>(&p1);
     u.z = *reinterpret_cast<uint32_t*>(&p2); u.w = *reinterpret_cast<uint32_t*>(&p3);

@@ -2,7 +2,7 @@
 import ctypes
 
 from . import _lib
-from .scnet_engine import ScnetEngine, _Act
+from .scnet_engine import ScnetEngine, _Act, h16
 
 
 class ResnetEngine(ScnetEngine):
@@ -101,7 +101,7 @@ class ResnetEngine(ScnetEngine):
                 # 7x7/s2 stem (Cin = num_input): im2col into bf16 rows of K = 49*Cin padded to a multiple of 32, then a 1x1
                 # convolution on the halo kernel (the CUDA-core implicit GEMM took 58 % of the forward)
                 Kp = -(-(49 * cin) // 32) * 32
-                col = self._take((n, H1, W1, Kp), torch.bfloat16)
+                col = self._take((n, H1, W1, Kp), h16())
                 self._run("rp_im2col_bf16", xin.buf.data_ptr(), n, H, W, cin, 7, 2, 3, H1, W1, Kp, col.data_ptr(), stream)
                 if 'resnet18_32s.conv1#col' not in self._packed:
                     w = self._packed['resnet18_32s.conv1']                                   # [7,7,cin,64]

@@ -12,6 +12,12 @@ from . import _lib
 NGF = 64
 
 
+def h16():
+    """torch dtype of the kernels' 16-bit operand / activation format (csrc/rp_h16.cuh: IEEE half by default)."""
+    import torch
+    return torch.float16 if _lib.h16_is_fp16() else torch.bfloat16
+
+
 class _Act(object):
     """A raw NHWC activation view: buffer [2P,H,W,pitch], channel window, BN scale/shift [P,pitch]."""
 
@@ -42,12 +48,12 @@ def pack_tc(w_taps, src_channels, cout, bn, tk):
     Wt = torch.stack([W[:, k0:k0 + tk, :] for k0 in k0s], 1)                   # [t, kt, tk, cpad]
     Wt = Wt.reshape(taps, len(k0s), tk // 8, 8, ntn, bn // 8, 8)               # [t, kt, kc, kk, nt, nc, r]
     Wt = Wt.permute(0, 1, 4, 2, 5, 6, 3).contiguous()                          # [t, kt, nt, kc, nc, r, kk]
-    return Wt.to(torch.bfloat16).contiguous()
+    return Wt.to(h16()).contiguous()
 
 
 def pack_halo(w_taps, tap_widx, src_channels, cout, bn, tk):
     import torch
-    return _pack_halo_f32(w_taps, tap_widx, src_channels, cout, bn, tk).to(torch.bfloat16).contiguous()
+    return _pack_halo_f32(w_taps, tap_widx, src_channels, cout, bn, tk).to(h16()).contiguous()
 
 
 def _pack_halo_f32(w_taps, tap_widx, src_channels, cout, bn, tk):
@@ -156,7 +162,7 @@ class ScnetEngine(object):
         n = 2 * P
         self._plans, self._graphs, self._seen = {}, {}, {}          # they hold pointers into the buffers replaced below
         f = dict(dtype=torch.float32, device=device)
-        fa = dict(dtype=torch.bfloat16 if self.act_bf16 else torch.float32, device=device)
+        fa = dict(dtype=h16() if self.act_bf16 else torch.float32, device=device)
         B = {}
 
         def act(name, H, W, C):
@@ -167,7 +173,7 @@ class ScnetEngine(object):
 
         B['in20'] = _Act(torch.empty((n, 224, 224, 20), **f), 224, 224, 20, 0, 20)
         if self.act_bf16:
-            B['in96'] = _Act(torch.empty((n, 224, 224, 96), dtype=torch.bfloat16, device=device), 224, 224, 96, 0, 96)
+            B['in96'] = _Act(torch.empty((n, 224, 224, 96), dtype=h16(), device=device), 224, 224, 96, 0, 96)
         for st in ('rgb', 'n', 'd'):
             for wh in ('', '_t2s'):
                 act('e1' + st + wh, 224, 224, 32)
@@ -364,8 +370,8 @@ class ScnetEngine(object):
                 for st in ('rgb', 'n', 'd'):
                     if 'conv1' + st + '#split' not in self._packed:
                         w = self._packed['conv1' + st]                          # [3,3,cin,32]
-                        hi = w.to(torch.bfloat16).float()
-                        lo = (w - hi).to(torch.bfloat16).float()
+                        hi = w.to(h16()).float()
+                        lo = (w - hi).to(h16()).float()
                         ws = torch.zeros((3, 3, 16, 32), dtype=torch.float32, device=w.device)
                         c = w.shape[2]
                         ws[:, :, 0:c], ws[:, :, 4:4 + c], ws[:, :, 8:8 + c] = hi, hi, lo   # x [hi|lo|hi|0] . w [hi|hi|lo|0]

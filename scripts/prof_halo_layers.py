@@ -2,7 +2,7 @@
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
-from relativepose_b200.scnet_engine import ScnetEngine, _Act
+from relativepose_b200.scnet_engine import ScnetEngine, _Act, h16
 G = int(sys.argv[1]) if len(sys.argv) > 1 else 8
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 1
 dev = torch.device("cuda:0")
@@ -24,13 +24,13 @@ todo = []
 for name, tr, k, s, p, Hin, cins, Cout, bn in LAYERS:
     srcs = []
     for c in cins:
-        raw = torch.randn((n, Hin, Hin, c), device=dev).to(torch.bfloat16)
+        raw = torch.randn((n, Hin, Hin, c), device=dev).to(h16())
         srcs.append(_Act(raw, Hin, Hin, c, 0, c, torch.ones((G, c), device=dev), torch.zeros((G, c), device=dev)))
     Cin = sum(cins)
     Hout = (Hin - 1) * s - 2 * p + k if tr else (Hin + 2 * p - k) // s + 1
     eng._packed[name] = torch.randn((k, k, Cin, Cout), device=dev) / (Cin * k * k) ** 0.5
     if bn:
-        out = _Act(torch.empty((n, Hout, Hout, Cout), device=dev, dtype=torch.bfloat16), Hout, Hout, Cout, 0, Cout,
+        out = _Act(torch.empty((n, Hout, Hout, Cout), device=dev, dtype=h16()), Hout, Hout, Cout, 0, Cout,
                    torch.zeros((G, Cout), device=dev), torch.zeros((G, Cout), device=dev))
         kw = dict(bn_params=(torch.ones(Cout, device=dev), torch.zeros(Cout, device=dev)))
     else:

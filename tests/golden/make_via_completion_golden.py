@@ -13,7 +13,7 @@ Scenes: relativepose_b200.synth.make_room_scan_pair (two skybox scans of one tex
 rows 0-2 of the shipped final_param_suncg_rlevel_3.txt (evaluation.py:95-101).  Stored per scene and step: R_hat, the
 primitives handed to RelativePoseEstimation_helper (keypoint pixels, 3-D points, normals, descriptors, weights), the
 oracle's trace of that solve (top-k sets, surviving-pair counts), a strided sample + per-channel moments of the network
-output.  Usage: python tests/golden/make_via_completion_golden.py
+output, and the same sample from the reference module run in float64 (the yardstick for float32 summation-order noise).  Usage: python tests/golden/make_via_completion_golden.py
 """
 import importlib.util
 import os
@@ -92,6 +92,9 @@ def main():
         rec.setdefault('net', []).append((x.detach().numpy().copy(), y.detach().numpy().copy()))
         return y
     net.forward = fwd_spy
+    net64 = refmodel.SCNet(a)                       # the same module in float64: the "exact" output both float32 runs aim at
+    net64.load_state_dict(sd)
+    net64 = net64.double()
 
     P = synth.shipped_params('suncg')
     blob, names = {}, []
@@ -111,6 +114,7 @@ def main():
         blob[name + '/sigma'] = np.stack((P[:ALTER, 0], P[:ALTER, 1], P[:ALTER, 2], sf), 1)
         blob[name + '/R_gt'] = R_gt
         blob[name + '/R_final'] = R_hat
+        first_run = {k: list(v) for k, v in rec.items()}
         for k in range(n_steps):
             dS, dT, para_k, T = rec['prim'][k]
             pre = "%s/step%d/" % (name, k)
@@ -139,10 +143,41 @@ def main():
             blob[pre + 'topk'] = np.asarray(tr['topk'])
             blob[pre + 'counts'] = np.array([tr.get('n_dist', -1), tr.get('n_angle', -1), tr.get('status', -1)])
             x, y = rec['net'][k]
-            blob[pre + 'net_sub'] = y[:, :, ::8, ::8].astype(np.float32)
+            blob[pre + 'net_sub'] = y[:, :, ::8, ::16].astype(np.float32)
             blob[pre + 'net_mean'] = y.mean(axis=(2, 3))
             blob[pre + 'net_std'] = y.std(axis=(2, 3))
             blob[pre + 'net_in_sum'] = x.astype(np.float64).sum(axis=(2, 3))
+            with torch.no_grad():
+                y64 = net64(torch.from_numpy(x).double()).numpy()
+            blob[pre + 'net_sub32m64_x1e4'] = ((y.astype(np.float64) - y64)[:, :, ::8, ::16] * 1e4).astype(np.float16)   # float32 run minus float64 run
+            print("    reference float32 vs float64 module: max-abs per head", [float(np.abs(y[:, a_:b_] - y64[:, a_:b_]).max()) for a_, b_ in ((0, 3), (3, 6), (6, 7), (7, 22), (22, 54))])
+        # The alternation is chaotic with these (random) weights: warping scatters to rounded pixels and the bottleneck
+        # BatchNorm sees two samples, so a pose that differs in the 5th digit gives a visibly different completion.  Measure
+        # it on the reference itself: rerun with the pose of step 0 moved by 1e-5 rad / 1e-5 m and record how far the
+        # reference's own later poses move.  (This is the yardstick for the free-running comparison in the GPU test.)
+        rec.clear()
+        calls = {'n': 0}
+
+        def perturbed_rpe(*a_, **k_):
+            T = orig_rpe(*a_, **k_)
+            if calls['n'] == 0:
+                c, s_ = np.cos(1e-5), np.sin(1e-5)
+                dR = np.eye(4)
+                dR[:3, :3] = np.array([[c, -s_, 0], [s_, c, 0], [0, 0, 1]])
+                dR[:3, 3] = 1e-5
+                T = dR @ T
+            calls['n'] += 1
+            return T
+        orig_rpe = ref.RelativePoseEstimation
+        ref.RelativePoseEstimation = perturbed_rpe
+        try:
+            np.random.seed(1000 + seed)
+            ref.RelativePoseEstimationViaCompletion(net, data_s, data_t, args)
+        finally:
+            ref.RelativePoseEstimation = orig_rpe
+        sens = [float(np.linalg.norm(rec['prim'][k][3] - first_run['prim'][k][3])) for k in range(min(n_steps, len(rec.get('prim', []))))]
+        print("  reference self-sensitivity (pose after step 0 moved by 1e-5): per-step |dT|_F =", sens)
+        blob[name + '/ref_sensitivity_dT'] = np.array(sens)
     blob['names'] = np.array(names)
     path = os.path.join(HERE, 'via_completion_golden.npz')
     np.savez_compressed(path, **blob)

@@ -6,6 +6,8 @@ partial statistics produce."""
 import numpy as np
 import pytest
 
+from relativepose_b200.scnet_engine import h16
+
 pytestmark = pytest.mark.gpu
 
 CASES = [
@@ -47,7 +49,7 @@ def _run(case, storage, flags=0):
     eng = ScnetEngine(None, mode='tc')
     eng.halo, eng.halo_flags = True, flags
     eng._P, eng._dev, eng._bufs = G, dev, {'partials': None}
-    dt = torch.bfloat16 if storage == 'bf16' else torch.float32
+    dt = h16() if storage == 'bf16' else torch.float32
     srcs, xs = [], []
     for c in cins:
         pitch = c + 8                                   # exercise pitch / channel offset
@@ -56,19 +58,19 @@ def _run(case, storage, flags=0):
         sh = (0.3 * torch.randn((G, pitch), generator=g)).to(dev)
         srcs.append(_Act(raw, Hin, Win, pitch, 8, c, sc, sh))
         xa = raw.float() * sc.repeat_interleave(gsz, 0)[:, None, None, :] + sh.repeat_interleave(gsz, 0)[:, None, None, :]
-        xa = F.leaky_relu(xa, 0.1)[..., 8:8 + c].to(torch.bfloat16).float()
+        xa = F.leaky_relu(xa, 0.1)[..., 8:8 + c].to(h16()).float()
         xs.append(xa)
     x = torch.cat(xs, 3).permute(0, 3, 1, 2).contiguous()
     if tr:
         w = torch.randn((Cin, Cout, k, k), generator=g).to(dev) / (Cin * k * k / (s * s)) ** 0.5
         Hout, Wout = (Hin - 1) * s - 2 * p + k, (Win - 1) * s - 2 * p + k
-        wq = w.to(torch.bfloat16).float()
+        wq = w.to(h16()).float()
         ref = F.conv_transpose2d(x.double(), wq.double(), stride=s, padding=p)
         eng._packed = {'L': w.permute(2, 3, 0, 1).contiguous()}
     else:
         w = torch.randn((Cout, Cin, k, k), generator=g).to(dev) / (Cin * k * k) ** 0.5
         Hout, Wout = (Hin + 2 * p - k) // s + 1, (Win + 2 * p - k) // s + 1
-        wq = w.to(torch.bfloat16).float()
+        wq = w.to(h16()).float()
         ref = F.conv2d(x.double(), wq.double(), stride=s, padding=p)
         eng._packed = {'L': w.permute(2, 3, 1, 0).contiguous()}
     opitch = Cout + 8
@@ -135,7 +137,7 @@ def test_halo_1x1_head_with_bias(case, storage):
     eng = ScnetEngine(None, mode='tc')
     eng.halo = True
     eng._P, eng._dev, eng._bufs = G, dev, {'partials': None}
-    dt = torch.bfloat16 if storage == 'bf16' else torch.float32
+    dt = h16() if storage == 'bf16' else torch.float32
     srcs, xs = [], []
     for c in cins:
         raw = torch.randn((n, Hin, Win, c), generator=g).to(dev).to(dt)
@@ -144,12 +146,12 @@ def test_halo_1x1_head_with_bias(case, storage):
         srcs.append(_Act(raw, Hin, Win, c, 0, c, sc, sh))
         xa = raw.float() * sc.repeat_interleave(gsz, 0)[:, None, None, :] + sh.repeat_interleave(gsz, 0)[:, None, None, :]
         xa = F.leaky_relu(xa, 0.1)
-        xs.append(xa.to(torch.bfloat16).float() if Cout > 4 else xa)      # 3-channel heads run in float32 on CUDA cores
+        xs.append(xa.to(h16()).float() if Cout > 4 else xa)      # 3-channel heads run in float32 on CUDA cores
     x = torch.cat(xs, 3).permute(0, 3, 1, 2).contiguous()
     Cin = sum(cins)
     w = torch.randn((Cout, Cin, 1, 1), generator=g).to(dev) / Cin ** 0.5
     bias = torch.randn(Cout, generator=g).to(dev)
-    ref = F.conv2d(x.double(), (w.to(torch.bfloat16) if Cout > 4 else w).double(), bias.double())
+    ref = F.conv2d(x.double(), (w.to(h16()) if Cout > 4 else w).double(), bias.double())
     if tanh:
         ref = torch.tanh(ref)
     eng._packed = {'L': w.permute(2, 3, 1, 0).contiguous()}

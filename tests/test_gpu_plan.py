@@ -81,7 +81,7 @@ def test_affinity_build_stage_entry():
     lib = _lib.load()
     plist = [params_from_opts(para)]
     K = 5
-    ws, key = sol._workspace(d.max_ns, d.max_nt, K, d.feat_dim, 0)
+    ws, key = sol._workspace(1, d.max_ns, d.max_nt, K, d.feat_dim, 0)
     par = sol._params_device(plist)
     cap = 4096
     dev = sol.device
@@ -93,7 +93,7 @@ def test_affinity_build_stage_entry():
     zr = d.zero_rows(K, K, dev)
     rc = lib.rp_affinity_build(1, d.off_s_t.data_ptr(), d.off_t_t.data_ptr(), d.pc_s.data_ptr(), d.nrm_s.data_ptr(), d.feat_s.data_ptr(),
                                d.w_s.data_ptr(), d.pc_t.data_ptr(), d.nrm_t.data_ptr(), d.feat_t.data_ptr(), d.w_t.data_ptr(), d.feat_dim,
-                               par.data_ptr(), None, zr.data_ptr(), d.sum_order_t.data_ptr(), key[0], key[1], K, sol.n_slots, cap,
+                               par.data_ptr(), None, zr.data_ptr(), d.sum_order_t.data_ptr(), key[0], key[1], K, key[5], cap,
                                ws.data_ptr(), ws.numel(), topk.data_ptr(), erc.data_ptr(), ew.data_ptr(), status.data_ptr(),
                                stats.data_ptr(), torch.cuda.current_stream().cuda_stream)
     assert rc == 0

@@ -9,6 +9,8 @@ import types
 import numpy as np
 import pytest
 
+from relativepose_b200.scnet_engine import h16
+
 pytestmark = pytest.mark.gpu
 
 
@@ -74,9 +76,9 @@ def test_im2col_bf16_matches_unfold():
     Kp = -(-(k * k * C) // 32) * 32
     x = torch.randn((n, C, H, W), device='cuda')
     xin = x.permute(0, 2, 3, 1).contiguous()
-    out = torch.full((n, Ho, Wo, Kp), 7.0, dtype=torch.bfloat16, device='cuda')
+    out = torch.full((n, Ho, Wo, Kp), 7.0, dtype=h16(), device='cuda')
     _lib.check(lib.rp_im2col_bf16(xin.data_ptr(), n, H, W, C, k, s, p, Ho, Wo, Kp, out.data_ptr(), torch.cuda.current_stream().cuda_stream), "im2col")
     cols = F.unfold(x, k, padding=p, stride=s)                                   # [n, C*k*k, Ho*Wo], K order (c, ky, kx)
     ref = cols.view(n, C, k * k, Ho, Wo).permute(0, 3, 4, 2, 1).reshape(n, Ho, Wo, k * k * C)
-    assert torch.equal(out[..., :k * k * C].float(), ref.to(torch.bfloat16).float())
+    assert torch.equal(out[..., :k * k * C].float(), ref.to(h16()).float())
     assert torch.all(out[..., k * k * C:] == 0)

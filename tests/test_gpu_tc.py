@@ -2,6 +2,8 @@
 The accumulation is fp32 in both, so only summation order differs: tolerance 1e-4 relative to ||row||."""
 import pytest
 
+from relativepose_b200.scnet_engine import h16
+
 pytestmark = pytest.mark.gpu
 
 
@@ -17,7 +19,7 @@ def test_tc_gemm_matches_torch(M, N, K, bn):
     rc = lib.rp_tc_gemm_test(A.data_ptr(), B.data_ptr(), C.data_ptr(), M, N, K, bn, torch.cuda.current_stream().cuda_stream)
     assert rc == 0
     torch.cuda.synchronize()
-    ref = A.bfloat16().float() @ B.bfloat16().float().t()
+    ref = A.to(h16()).float() @ B.to(h16()).float().t()
     err = (C - ref).abs().max().item()
     scale = ref.abs().max().item()
     print("M=%d N=%d K=%d bn=%d  max err %.3e (|ref|max %.2f)" % (M, N, K, bn, err, scale))
