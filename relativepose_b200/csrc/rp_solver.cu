@@ -367,6 +367,17 @@ __device__ bool horn_eig_fast(const double N[4][4], double q[4], double lam_hint
                     rq += v[i] * sx;
                 }
                 lam = rq;
+                if (polish == 0) {               // usually already converged: skip the second adjugate
+                    double res0 = 0.0;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        double sx = -lam * v[i];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) sx += N[i][j] * v[j];
+                        res0 += sx * sx;
+                    }
+                    if (res0 <= 1e-29 * fro) break;
+                }
             }
             if (good) {
                 double res = 0.0;
@@ -929,6 +940,9 @@ __device__ void residual_to_h(const PairView& pv) {
     __syncthreads();
 }
 
+template <bool NARROW> struct MaskOf { typedef unsigned type; };
+template <> struct MaskOf<false> { typedef unsigned long long type; };
+
 // Phase C: conservative float32 pre-test of the distance-consistency condition (rpmodule.py:399-404).
 // The source distance depends only on the source keypoint pair (i1,i2) and is shared by the KK*KK correspondence pairs
 // built on it.  The n_s(n_s-1)/2 source pairs are enumerated in row-major triangular order, one per lane (every lane of
@@ -937,6 +951,7 @@ __device__ void residual_to_h(const PairView& pv) {
 // which is flushed 32 entries at a time into the candidate list.
 template <int KK>
 __device__ void pretest_pairs(Shared& sh, const PairView& pv, float tau, float sep2, long long edge_cap) {
+    typedef typename MaskOf<(KK * KK <= 32)>::type MaskT;             // one bit per (k1, k2)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int ns = pv.ns;
     const float4* sp4 = pv.sp4; const float4* tq4 = pv.tq4;
@@ -960,7 +975,10 @@ __device__ void pretest_pairs(Shared& sh, const PairView& pv, float tau, float s
             float S = ax * ax + ay * ay + az * az;
             float ds = S * rsqrt_approx(S + 1e-30f);
             const bool vs = vs0 && (S > sep2);                      // min(ds,dt) > sep  =>  ds > sep
-            unsigned long long keepm = 0ull;
+            // |ds - dt| < tau and dt > sep as bounds on the SQUARED target distance (no square root per test)
+            const float hi2 = (ds + tau) * (ds + tau);
+            const float lo2 = fmaxf(ds > tau ? (ds - tau) * (ds - tau) : -1.f, sep2);
+            MaskT keepm = 0;
 #pragma unroll
             for (int k1 = 0; k1 < KK; ++k1) {
                 const float4 q1 = tq4[i1 * KK + k1];
@@ -968,13 +986,12 @@ __device__ void pretest_pairs(Shared& sh, const PairView& pv, float tau, float s
                 for (int k2 = 0; k2 < KK; ++k2) {
                     float bx = q1.x - q2[k2].x, by = q1.y - q2[k2].y, bz = q1.z - q2[k2].z;
                     float Tq = bx * bx + by * by + bz * bz;
-                    float dt = Tq * rsqrt_approx(Tq + 1e-30f);
-                    bool keep = (fabsf(ds - dt) < tau) && (Tq > sep2);
-                    keepm |= keep ? (1ull << (k1 * KK + k2)) : 0ull;
+                    bool keep = (Tq > lo2) && (Tq < hi2);
+                    keepm |= keep ? ((MaskT)1 << (k1 * KK + k2)) : (MaskT)0;
                 }
             }
-            if (!vs) keepm = 0ull;
-            const int cntl = __popcll(keepm);
+            if (!vs) keepm = 0;
+            const int cntl = __popcll((unsigned long long)keepm);
             if (__any_sync(0xffffffffu, cntl != 0)) {
                 int inc = cntl;                                      // inclusive warp scan of the per-lane counts
 #pragma unroll
@@ -993,7 +1010,7 @@ __device__ void pretest_pairs(Shared& sh, const PairView& pv, float tau, float s
                 }
                 if (total <= STAGE) {
                     while (keepm) {
-                        int bit = __ffsll((long long)keepm) - 1; keepm &= keepm - 1;
+                        int bit = __ffsll((long long)(unsigned long long)keepm) - 1; keepm &= keepm - 1;
                         int k1 = bit / KK, k2 = bit - k1 * KK;
                         stg[pos++] = ((unsigned)(i1 * KK + k1) << 16) | (unsigned)(i2 * KK + k2);
                     }
@@ -1019,7 +1036,7 @@ __device__ void pretest_pairs(Shared& sh, const PairView& pv, float tau, float s
                     base = __shfl_sync(0xffffffffu, base, 0);
                     long long o = (long long)base + (pos - nst);
                     while (keepm) {
-                        int bit = __ffsll((long long)keepm) - 1; keepm &= keepm - 1;
+                        int bit = __ffsll((long long)(unsigned long long)keepm) - 1; keepm &= keepm - 1;
                         int k1 = bit / KK, k2 = bit - k1 * KK;
                         if (o < edge_cap) pv.edges[o] = ((unsigned)(i1 * KK + k1) << 16) | (unsigned)(i2 * KK + k2);
                         ++o;
@@ -1152,7 +1169,9 @@ __global__ void __launch_bounds__(T, RP_MIN_BLOCKS) rp_solve_kernel(const SolveA
                         if (A.has_dbg && A.dbg.dij && act) A.dbg.dij[A.dbg.dij_off[b] + (int64_t)i * nt + j] = dij;
                         const bool obs = __dmul_rn(wsi, __ldg(A.w_t + t0 + j)) == 1.0;                     // :354
                         const double qk = (double)dij * (obs ? rden_obs : rden_any);                       // ranks like -key
-                        if (qk < 372.6000001) {                // below -372.6 exp(key)^2 < 2^-1075 rounds to +0: a no-op in the norm
+                        // norm terms: below -372.6 exp(key)^2 < 2^-1075 rounds to +0; a term more than 22 below the best key seen
+                        // so far is < e^-44 of a term already in the sum (n_t of them stay under 1e-17 relative): both are no-ops
+                        if (qk < 372.6000001 && qk < lk[0] + 22.0) {
                             const double key = (double)(-dij) / (obs ? par.feat_den_obs : par.feat_den);   // :356-358
                             if (key > -372.6) { const double e = exp(key); ss += e * e; }
                         }
@@ -1370,15 +1389,28 @@ __global__ void __launch_bounds__(T, RP_MIN_BLOCKS) rp_solve_kernel(const SolveA
             double wloc = 0.0;
             const double th = sqrt(par.angle_thre_sq);
             const bool cheap = th > 0.0 && th < 3.14159;                // otherwise everything goes to stage 2
-            const double cth = cheap ? cos(th) - 1e-9 : -4.0;
+            // the rejection runs in float32 on float32 copies of the unit normals: rounding of the dot products and of
+            // sqrt((1-x^2)(1-y^2)) near |x| = 1 stays below 6e-4, hence the 2e-3 margin (0.16 degrees at th = 45 degrees)
+            const float cth = cheap ? (float)cos(th) - 2e-3f : -4.0f;
+            // stage-1 operands in shared memory (the per-pair vectors are not live yet; 72 N bytes always fit their region)
+            double* sP = reinterpret_cast<double*>(dyn);                // [6][N] source / target position
+            float* sN = reinterpret_cast<float*>(sP + 6 * (size_t)N);   // [6][N] source / target normal
+            for (int c = tid; c < N; c += T) {
+#pragma unroll
+                for (int a = 0; a < 6; ++a) {
+                    sP[(size_t)a * N + c] = geo[(size_t)(G_PX + a) * gs + c];
+                    sN[(size_t)a * N + c] = (float)geo[(size_t)(G_NX + a) * gs + c];
+                }
+            }
+            __syncthreads();
             for (int e0 = 0; e0 < MC; e0 += T) {
                 const int e = e0 + tid;
                 bool maybe = false;
                 if (e < MC) {
                     unsigned rc = pv.edges[e];
                     int r = rc >> 16, c = rc & 0xffffu;
-                    double ax = geo[G_PX * gs + r] - geo[G_PX * gs + c], ay = geo[G_PY * gs + r] - geo[G_PY * gs + c], az = geo[G_PZ * gs + r] - geo[G_PZ * gs + c];
-                    double bx = geo[G_QX * gs + r] - geo[G_QX * gs + c], by = geo[G_QY * gs + r] - geo[G_QY * gs + c], bz = geo[G_QZ * gs + r] - geo[G_QZ * gs + c];
+                    double ax = sP[r] - sP[c], ay = sP[N + r] - sP[N + c], az = sP[2 * N + r] - sP[2 * N + c];
+                    double bx = sP[3 * N + r] - sP[3 * N + c], by = sP[4 * N + r] - sP[4 * N + c], bz = sP[5 * N + r] - sP[5 * N + c];
                     double dis_s = sqrt(dot3_np(ax, ay, az, ax, ay, az));                // :399
                     double dis_t = sqrt(dot3_np(bx, by, bz, bx, by, bz));                // :400
                     double df = dis_s - dis_t;
@@ -1386,22 +1418,19 @@ __global__ void __launch_bounds__(T, RP_MIN_BLOCKS) rp_solve_kernel(const SolveA
                     if ((dd < par.dist_thre_sq) && (fmin(dis_s, dis_t) > par.sep_thre)) {   // :404
                         ++m1;
                         maybe = true;
-                        double n1x = geo[G_NX * gs + r], n1y = geo[G_NY * gs + r], n1z = geo[G_NZ * gs + r];
-                        double n2x = geo[G_NX * gs + c], n2y = geo[G_NY * gs + c], n2z = geo[G_NZ * gs + c];
-                        double m1x = geo[G_MX * gs + r], m1y = geo[G_MY * gs + r], m1z = geo[G_MZ * gs + r];
-                        double m2x = geo[G_MX * gs + c], m2y = geo[G_MY * gs + c], m2z = geo[G_MZ * gs + c];
-                        double x = clip1(dot3_np(n1x, n1y, n1z, n2x, n2y, n2z)), y = clip1(dot3_np(m1x, m1y, m1z, m2x, m2y, m2z));
-                        if (x * y + sqrt((1.0 - x * x) * (1.0 - y * y)) < cth) maybe = false;
+                        const float n1x = sN[r], n1y = sN[N + r], n1z = sN[2 * N + r], n2x = sN[c], n2y = sN[N + c], n2z = sN[2 * N + c];
+                        const float m1x = sN[3 * N + r], m1y = sN[4 * N + r], m1z = sN[5 * N + r], m2x = sN[3 * N + c], m2y = sN[4 * N + c], m2z = sN[5 * N + c];
+                        auto cosdiff = [](float x, float y) {          // cos(acos x - acos y)
+                            x = fminf(fmaxf(x, -1.f), 1.f); y = fminf(fmaxf(y, -1.f), 1.f);
+                            return x * y + sqrtf((1.f - x * x) * (1.f - y * y));
+                        };
+                        if (cosdiff(n1x * n2x + n1y * n2y + n1z * n2z, m1x * m2x + m1y * m2y + m1z * m2z) < cth) maybe = false;
                         else {
-                            const double is = 1.0 / dis_s, it = 1.0 / dis_t;
-                            double e1x = ax * is, e1y = ay * is, e1z = az * is;
-                            double e2x = bx * it, e2y = by * it, e2z = bz * it;
-                            x = clip1(dot3_np(n1x, n1y, n1z, e1x, e1y, e1z)); y = clip1(dot3_np(m1x, m1y, m1z, e2x, e2y, e2z));
-                            if (x * y + sqrt((1.0 - x * x) * (1.0 - y * y)) < cth) maybe = false;
-                            else {
-                                x = clip1(dot3_np(n2x, n2y, n2z, e1x, e1y, e1z)); y = clip1(dot3_np(m2x, m2y, m2z, e2x, e2y, e2z));
-                                if (x * y + sqrt((1.0 - x * x) * (1.0 - y * y)) < cth) maybe = false;
-                            }
+                            const float is = 1.0f / (float)dis_s, it = 1.0f / (float)dis_t;
+                            const float e1x = (float)ax * is, e1y = (float)ay * is, e1z = (float)az * is;
+                            const float e2x = (float)bx * it, e2y = (float)by * it, e2z = (float)bz * it;
+                            if (cosdiff(n1x * e1x + n1y * e1y + n1z * e1z, m1x * e2x + m1y * e2y + m1z * e2z) < cth) maybe = false;
+                            else if (cosdiff(n2x * e1x + n2y * e1y + n2z * e1z, m2x * e2x + m2y * e2y + m2z * e2z) < cth) maybe = false;
                         }
                     }
                     if (!maybe) pv.ew[e] = -1.0;

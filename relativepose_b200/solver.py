@@ -58,12 +58,36 @@ def zero_row_topk(n_t, K):
     return _ZERO_ROW_CACHE[key]
 
 
+class PinnedArena(object):
+    """One growing block of page-locked host memory handed out in 256-byte aligned slices (reset per batch): packing a
+    list of records costs the copies only, not a cudaHostAlloc per array."""
+
+    def __init__(self):
+        self.buf, self.used = None, 0
+
+    def reset(self, nbytes):
+        import torch
+        if self.buf is None or self.buf.numel() < nbytes:
+            self.buf = None
+            self.buf = torch.empty((max(int(nbytes * 1.25), 1 << 20),), dtype=torch.uint8).pin_memory()
+        self.used = 0
+
+    def take(self, nbytes):
+        lo = self.used
+        self.used = (lo + nbytes + 255) // 256 * 256
+        if self.used > self.buf.numel():
+            raise RuntimeError("PinnedArena overflow")
+        return self.buf[lo:lo + nbytes]
+
+
 class PackedBatch(object):
     """A ragged batch of scan pairs as concatenated host arrays (pinned torch tensors)."""
 
     FIELDS = ("pc_s", "nrm_s", "feat_s", "w_s", "pc_t", "nrm_t", "feat_t", "w_t")
 
-    def __init__(self, records=None, pin=True):
+    def __init__(self, records=None, pin=True, arena=None):
+        """``arena``: a PinnedArena the concatenated arrays are written into directly (no per-call cudaHostAlloc: the
+        arrays are views valid until the arena is reset).  Without one every array is pinned on its own."""
         import torch
         self.B = 0
         if records is None:
@@ -80,36 +104,62 @@ class PackedBatch(object):
         self.max_nt = int(nt.max()) if B else 0
         D = records[0]["feat_src"].shape[1] if B and records[0]["feat_src"].ndim == 2 else FEAT_DIM_DEFAULT
         self.feat_dim = int(D)
+        cuda = pin and torch.cuda.is_available()
+        tdt = {np.dtype(np.int32): torch.int32, np.dtype(np.float64): torch.float64, np.dtype(np.float32): torch.float32}
 
-        def cat(key, dtype, cols):
-            parts = [np.asarray(r[key], dtype=dtype).reshape(-1, cols) if cols else np.asarray(r[key], dtype=dtype).reshape(-1)
-                     for r in records]
-            a = np.ascontiguousarray(np.concatenate(parts, 0)) if parts else np.zeros((0,), dtype)
+        def host(shape, dtype):
+            """(numpy view, torch tensor) of a host array of this shape: arena slice, own pinned block, or plain memory."""
+            dtype = np.dtype(dtype)
+            n = int(np.prod(shape))
+            if arena is not None and cuda:
+                u8 = arena.take(n * dtype.itemsize)
+                t = u8.view(tdt[dtype]).view(*shape)
+                return t.numpy(), t
+            a = np.empty(shape, dtype)
             t = torch.from_numpy(a)
-            return t.pin_memory() if (pin and torch.cuda.is_available()) else t
+            if cuda:
+                t = t.pin_memory()
+                return t.numpy(), t
+            return a, t
 
-        self.pc_s = cat("pc_src", np.float64, 3)
-        self.nrm_s = cat("normal_src", np.float64, 3)
-        self.feat_s = cat("feat_src", np.float32, D)
-        self.w_s = cat("weight_src", np.float64, 0)
-        self.pc_t = cat("pc_tgt", np.float64, 3)
-        self.nrm_t = cat("normal_tgt", np.float64, 3)
-        self.feat_t = cat("feat_tgt", np.float32, D)
-        self.w_t = cat("weight_tgt", np.float64, 0)
-        self.off_s_t = torch.from_numpy(self.off_s)
-        self.off_t_t = torch.from_numpy(self.off_t)
+        Ns, Nt = int(self.off_s[-1]), int(self.off_t[-1])
+        jobs = (("pc_s", "pc_src", np.float64, 3, Ns), ("nrm_s", "normal_src", np.float64, 3, Ns), ("feat_s", "feat_src", np.float32, D, Ns),
+                ("w_s", "weight_src", np.float64, 0, Ns), ("pc_t", "pc_tgt", np.float64, 3, Nt), ("nrm_t", "normal_tgt", np.float64, 3, Nt),
+                ("feat_t", "feat_tgt", np.float32, D, Nt), ("w_t", "weight_tgt", np.float64, 0, Nt))
+        dst = {name: host((total, cols) if cols else (total,), dtype) for name, _, dtype, cols, total in jobs}   # arena slices: in order
+
+        def fill(job):
+            name, key, dtype, cols, total = job
+            a = dst[name][0]
+            parts = [np.asarray(r[key]) for r in records]
+            parts = [q if q.ndim == (2 if cols else 1) else (q.reshape(-1, cols) if cols else q.reshape(-1)) for q in parts]
+            if parts:
+                np.concatenate(parts, 0, out=a, casting='unsafe')
+        if B >= 256:                                        # the copies release the GIL: the eight arrays fill concurrently
+            from concurrent.futures import ThreadPoolExecutor
+            with ThreadPoolExecutor(max_workers=4) as ex:
+                list(ex.map(fill, jobs))
+        else:
+            for job in jobs:
+                fill(job)
+        for name, _, _, _, _ in jobs:
+            setattr(self, name, dst[name][1])
+
+        def small(arr):
+            a, t = host(arr.shape, arr.dtype)
+            a[...] = arr
+            return t
+        self.off_s_t = small(self.off_s)
+        self.off_t_t = small(self.off_t)
         # NumPy's float32 summation order for the descriptor distance depends on the layout of the caller's 'feat'
         # arrays (see include/rp_b200.h: feat_sum_order): sequential unless both are C-contiguous
-        order = np.array([0 if (np.asarray(r["feat_src"]).flags["C_CONTIGUOUS"] and np.asarray(r["feat_tgt"]).flags["C_CONTIGUOUS"])
-                          else 1 for r in records], dtype=np.int32)
-        self.sum_order_t = torch.from_numpy(order)
-        if pin and torch.cuda.is_available():
-            self.sum_order_t = self.sum_order_t.pin_memory()
+        order = np.fromiter((0 if (r["feat_src"].flags.c_contiguous and r["feat_tgt"].flags.c_contiguous) else 1
+                             for r in records), dtype=np.int32, count=B) if all(isinstance(r["feat_src"], np.ndarray) and isinstance(r["feat_tgt"], np.ndarray) for r in records[:1]) \
+            else np.array([0 if (np.asarray(r["feat_src"]).flags["C_CONTIGUOUS"] and np.asarray(r["feat_tgt"]).flags["C_CONTIGUOUS"])
+                           else 1 for r in records], dtype=np.int32)
+        self.sum_order_t = small(order)
         self.nt_list = nt
         self._zero_rows = {}
-        if pin and torch.cuda.is_available():
-            self.off_s_t = self.off_s_t.pin_memory()
-            self.off_t_t = self.off_t_t.pin_memory()
 
     def zero_rows(self, topk, stride):
         """[B, stride] int32 table of numpy tie-order candidate sets (see zero_row_topk)."""
@@ -475,7 +525,13 @@ class PoseSolver(object):
     def solve_records(self, records, para, return_stats=False):
         if 0 < len(records) <= self.SMALL_BATCH:
             return self._solve_small(records, para, return_stats)
-        return self.solve_packed(PackedBatch(records), para, return_stats=return_stats)
+        if getattr(self, "_arena", None) is None:
+            self._arena = PinnedArena()
+        ns = sum(int(np.asarray(r["pc_src"]).shape[0]) for r in records)
+        nt = sum(int(np.asarray(r["pc_tgt"]).shape[0]) for r in records)
+        D = int(np.asarray(records[0]["feat_src"]).shape[1]) if np.asarray(records[0]["feat_src"]).ndim == 2 else FEAT_DIM_DEFAULT
+        self._arena.reset((ns + nt) * (7 * 8 + 4 * D) + 12 * (len(records) + 1) + 256 * 16)
+        return self.solve_packed(PackedBatch(records, arena=self._arena), para, return_stats=return_stats)
 
     def _solve_small(self, records, para, return_stats):
         """Latency path for a few pairs (RelativePoseEstimation_helper is B = 1): every input goes through ONE pinned

@@ -1,22 +1,11 @@
 #!/bin/bash
-# One GPU visit: tests, bench.  Usage: gpurun --timeout 1500 -- 'bash scripts/gpu_round.sh <tag>'
 TAG=${1:-r2a}
 mkdir -p gpurun_out
 {
-echo "=== all gpu tests"; timeout 1200 python -m pytest tests -m gpu -q 2>&1 | tail -25
-echo "=== via-completion numbers"; python - <<'PY'
-import json
-try:
-    R = json.load(open('gpurun_out/via_completion_parity.json'))
-    for k, rows in R.items():
-        if isinstance(rows, list):
-            for r in rows:
-                print(k, {a: (round(b, 6) if isinstance(b, float) else b) for a, b in r.items()})
-        else:
-            print(k, rows)
-except Exception as e:
-    print("no report", e)
-PY
-echo "=== bench"; timeout 1200 python bench.py --steps 5 --warmup 3 2>&1 | tail -3
+echo "=== solver tests"; timeout 1200 python -m pytest tests/test_gpu_solver.py tests/test_gpu_fitters.py tests/test_gpu_plan.py tests/test_gpu_via_completion.py tests/test_gpu_pipeline.py tests/test_gpu_pipeline_batch.py tests/test_gpu_fd_objective.py -m gpu -q -x 2>&1 | tail -8
+echo "=== bench (no extras)"; timeout 600 python bench.py --steps 5 --warmup 3 --no-extra --no-cpu-baseline 2>&1 | tail -1 | python -c "
+import json,sys
+d=json.loads(sys.stdin.read()); print({k:d[k] for k in ('value','ms_per_step','per_pair_p50_ms')}, d['e2e']['value'], d['e2e_records']['value'], d['parity'])"
+echo "=== diag"; timeout 600 python scripts/diag_alternation_solve.py 2>&1 | tail -30
 } > gpurun_out/round_$TAG.log 2>&1
-tail -5 gpurun_out/round_$TAG.log
+tail -50 gpurun_out/round_$TAG.log
