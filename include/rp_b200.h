@@ -89,7 +89,10 @@ typedef struct rp_params {
 #define RP_STATS_STRIDE 8
 /* stats[b*8 + k]: 0 N (=n_s*K), 1 pairs after distance test, 2 pairs after angle test,
  * 3 pairs with non-zero weight, 4 power iterations (sum over alternations),
- * 5 max power iterations in one alternation, 6 1 if some alternation hit max_power_iters, 7 K */
+ * 5 max power iterations in one alternation, 6 bit 0: some alternation hit max_power_iters; bits 8..: number of source
+ * rows whose top-k index SET the keys alone do not determine (the K-th and (K+1)-th candidate tie exactly, or selected
+ * entries underflowed to weight 0 in a row that is not all zero): there the reference's numpy.argpartition order decides and
+ * the sets may differ from it (all-zero rows follow numpy through zero_row_topk; counted on the 32-channel path), 7 K */
 
 /* Optional stage-boundary outputs (device pointers; any may be NULL).  Used by the parity tests. */
 typedef struct rp_debug {

@@ -88,6 +88,8 @@ struct SolveArgs {
     size_t sm_mask_off;     // byte offset of the bit mask in dynamic shared memory (when mask_in_smem)
     int dyn_in_global;      // scan pairs too large for shared memory: the per-pair vectors live in the slot (o_dyn)
     size_t o_dyn;
+    int csr_smem_cap;       // small batches (fewer CTAs than fit an SM): CSR entries that fit the idle shared memory, else 0
+    size_t sm_csr_off;
 };
 
 // ----------------------------------------------------------------------------------------------
@@ -417,6 +419,7 @@ struct Shared {
     double scal[8];      // 0: lambda warm start, 1: prefilter margin, 2: CSR weight threshold
     unsigned long long wmax_bits;   // largest pair weight (non-negative doubles order like their bit patterns)
     int cnt[8];          // 0 candidate count, 1 M1, 2 M2, 3 scan carry, 4 pair id, 5 nnz
+    int ties;            // source rows whose top-k SET is not determined by the keys (see stats[6])
     int warp_tot[NWARP];
     int warp_tot2[NWARP];
     int crow0[T];        // merge-path: compact (non-empty) row index of the first non-zero of thread t's chunk
@@ -439,6 +442,7 @@ struct PairView {
     unsigned* edges; double* ew;
     int* rowstart;       // [N+1] shared memory
     uint16_t* cols; double* vals;   // lane-interleaved: logical entry k lives at (k % E) * T + k / E
+    uint16_t* cols_s; double* vals_s; int ism;   // shared-memory copy of the entries with k % E < ism (same indexing)
                          // cols word: column (14 bits) | bit 15 = first entry of its row | bit 14 = last entry
     int E, nnz, nrows;   // non-zeros per thread chunk, total directed non-zeros, rows with non-zeros
     unsigned* rowmap;    // [nrows] shared: row id | first chunk << 16 | last chunk << 24
@@ -649,11 +653,12 @@ __device__ void block_sum(Shared& sh, double (&v)[NV], int& red_buf) {
 
 // Merge-path walk over the CSR of W: every thread owns E consecutive logical non-zeros (perfect balance no
 // matter how skewed the row lengths are -- inlier correspondences have ~10x the degree of outliers).
-// The chunk loop is branch-free (row boundaries are flag bits in the column word: reset / store are selects and
-// predicated stores), so it unrolls and its loads batch.  F::term(c, w, s1, s2) accumulates one non-zero;
+// Row boundaries are flag bits in the column word (reset / store are selects and predicated stores).  F::term(c, w, s1, s2) accumulates one non-zero;
 // after a barrier F::fin(row, s1, s2) runs once per non-empty row, one thread per row.  A row split across
 // chunks is summed trailing piece + leading pieces in chunk order, so the summation order is fixed.
 // Rows without non-zeros are never visited.  Contains one __syncthreads.
+constexpr int CSR_PB = 8;           // non-zeros fetched per batch by csr_walk
+
 template <class F>
 __device__ __forceinline__ void csr_walk(Shared& sh, const PairView& pv, F& f) {
     const int t = threadIdx.x;
@@ -661,24 +666,39 @@ __device__ __forceinline__ void csr_walk(Shared& sh, const PairView& pv, F& f) {
     int n = pv.nnz - t * E;
     n = n < 0 ? 0 : (n > E ? E : n);                      // non-zeros in this thread's chunk
     if (n > 0) {
-        const uint16_t* __restrict__ cp = pv.cols + t;
-        const double* __restrict__ vp = pv.vals + t;
         double* __restrict__ S = pv.S;
         double* mypart = sh.part[t];
         int cr = sh.crow0[t];
         bool headless = true;                             // current row began in an earlier chunk
         double s1 = 0.0, s2 = 0.0;
         unsigned cw = 0;
-#pragma unroll 4
-        for (int i = 0; i < n; ++i) {
-            cw = cp[(size_t)i * T];
-            const double w = vp[(size_t)i * T];
-            const bool st = (cw & 0x8000u) != 0, en = (cw & 0x4000u) != 0;
-            s1 = st ? 0.0 : s1; s2 = st ? 0.0 : s2;
-            cr += (st && i > 0) ? 1 : 0;
-            headless = headless && !st;
-            f.term((int)(cw & 0x3fffu), w, s1, s2);
-            if (en) { double* d = headless ? mypart : (S + 2 * cr); d[0] = s1; d[1] = s2; }
+        // The non-zeros are fetched in batches of CSR_PB independent loads before any of them is used (the loop-carried
+        // row state otherwise serialises one memory round trip per non-zero); the leading pv.ism entries of every chunk
+        // come from shared memory when the launch had room for them (make_launch_plan), the rest from the slot.
+        for (int i0 = 0; i0 < n; i0 += CSR_PB) {
+            const bool from_s = i0 + CSR_PB <= pv.ism;
+            const uint16_t* __restrict__ cp = (from_s ? pv.cols_s : pv.cols) + t + (size_t)i0 * T;
+            const double* __restrict__ vp = (from_s ? pv.vals_s : pv.vals) + t + (size_t)i0 * T;
+            unsigned cwb[CSR_PB]; double wb[CSR_PB];
+#pragma unroll
+            for (int u = 0; u < CSR_PB; ++u) {
+                const bool ok = i0 + u < n;
+                cwb[u] = ok ? (unsigned)cp[(size_t)u * T] : 0u;
+                wb[u] = ok ? vp[(size_t)u * T] : 0.0;
+            }
+#pragma unroll
+            for (int u = 0; u < CSR_PB; ++u) {
+                if (i0 + u < n) {
+                    cw = cwb[u];
+                    const double w = wb[u];
+                    const bool st = (cw & 0x8000u) != 0, en = (cw & 0x4000u) != 0;
+                    s1 = st ? 0.0 : s1; s2 = st ? 0.0 : s2;
+                    cr += (st && (i0 + u) > 0) ? 1 : 0;
+                    headless = headless && !st;
+                    f.term((int)(cw & 0x3fffu), w, s1, s2);
+                    if (en) { double* d = headless ? mypart : (S + 2 * cr); d[0] = s1; d[1] = s2; }
+                }
+            }
         }
         if (!(cw & 0x4000u)) { double* d = headless ? mypart : (mypart + 2); d[0] = s1; d[1] = s2; }
     }
@@ -744,7 +764,8 @@ struct MatVecStep {           // out = S (diag(h) W + W diag(h)) S in
 };
 
 constexpr int PI_SWITCH = 48;       // ROBUST variant: plain power steps before the accelerated iteration takes over
-constexpr int PI_FAST_CAP = 64;     // fast variant: power steps after which a pair is handed to the ROBUST variant
+constexpr int PI_FAST_CAP = 192;    // fast variant: power steps after which a pair is handed to the ROBUST variant (which redoes the
+                                    // whole pair: dense, flat-weighted graphs need 50-90 steps per alternation and must not pay that)
 constexpr int RP_STATUS_RETRY = -100;   // internal: pair waits for the ROBUST pass (never visible to the caller)
 
 // Continuation of the power iteration for graphs whose two leading eigenvalues nearly coincide (two weakly coupled
@@ -1073,7 +1094,7 @@ __global__ void __launch_bounds__(T, RP_MIN_BLOCKS) rp_solve_kernel(const SolveA
 
     for (;;) {
         __syncthreads();
-        if (tid == 0) sh.cnt[4] = atomicAdd(work_counter, 1);
+        if (tid == 0) { sh.cnt[4] = atomicAdd(work_counter, 1); sh.ties = 0; }
         __syncthreads();
         const int b = sh.cnt[4];
         if (b >= A.B) break;
@@ -1115,6 +1136,7 @@ __global__ void __launch_bounds__(T, RP_MIN_BLOCKS) rp_solve_kernel(const SolveA
             pv.rowstart = reinterpret_cast<int*>(v + 8 * A.Nmax);    // Nmax+1 ints
             pv.rowmap = reinterpret_cast<unsigned*>(pv.rowstart + (A.Nmax + 1));   // Nmax words
             pv.E = 1; pv.nnz = 0; pv.nrows = 0;
+            pv.cols_s = pv.cols; pv.vals_s = pv.vals; pv.ism = 0;
             pv.sp4 = reinterpret_cast<float4*>(dyn);
             pv.tq4 = pv.sp4 + ns;
             pv.mask = A.mask_in_smem ? reinterpret_cast<unsigned*>(dyn + A.sm_mask_off)
@@ -1185,6 +1207,17 @@ __global__ void __launch_bounds__(T, RP_MIN_BLOCKS) rp_solve_kernel(const SolveA
                     }
                     if (act) {
                         const double nm = sqrt(ss);                                                        // :359
+                        // The index SET is decided by the keys unless the K-th and (K+1)-th candidate tie exactly, or selected
+                        // entries have underflowed to wij = 0 in a row that is not all zero (exp(key) = 0 below -745.1): there
+                        // numpy's introselect order decides, which is not reproduced (all-zero rows are: zero_row_topk).
+                        if (nm != 0.0) {
+                            bool amb = false;
+#pragma unroll
+                            for (int k = 1; k < KMAX; ++k) if (k == K && lk[k] == lk[k - 1] && li[k] != 0x7fffffff) amb = true;
+#pragma unroll
+                            for (int k = 0; k < KMAX; ++k) if (k == K - 1 && lk[k] > 745.13 && li[k] != 0x7fffffff) amb = true;
+                            if (amb) atomicAdd(&sh.ties, 1);
+                        }
 #pragma unroll
                         for (int k = 0; k < KMAX; ++k) {
                             if (k < K) {
@@ -1384,7 +1417,7 @@ __global__ void __launch_bounds__(T, RP_MIN_BLOCKS) rp_solve_kernel(const SolveA
         // all lanes busy: the reference's own arithmetic (six acos, the filters exactly as :430-436, the pair weight).
         if (!A.solve_only) {
             const int gs = pv.gstride; const double* geo = pv.geo;
-            unsigned* surv = reinterpret_cast<unsigned*>(pv.cols);      // the CSR arrays are not built yet
+            unsigned* surv = reinterpret_cast<unsigned*>(slot + A.o_cols);   // the CSR arrays are not built yet
             int m1 = 0, m2 = 0, nz = 0;
             double wloc = 0.0;
             const double th = sqrt(par.angle_thre_sq);
@@ -1577,6 +1610,12 @@ __global__ void __launch_bounds__(T, RP_MIN_BLOCKS) rp_solve_kernel(const SolveA
             pv.nrows = sh.cnt[6];
             pv.E = (pv.nnz + T - 1) / T; if (pv.E < 1) pv.E = 1;
             const int E = pv.E;
+            if (A.csr_smem_cap >= T * CSR_PB) {                     // shared memory an idle SM has left (small batches): the leading
+                const int rows_s = A.csr_smem_cap / T;               // entries of every thread's chunk live there, whole batches only
+                pv.ism = rows_s >= E ? E + CSR_PB : rows_s / CSR_PB * CSR_PB;
+                pv.cols_s = reinterpret_cast<uint16_t*>(dyn_smem + A.sm_csr_off);
+                pv.vals_s = reinterpret_cast<double*>(dyn_smem + A.sm_csr_off + (size_t)A.csr_smem_cap * sizeof(uint16_t));
+            }
             {   // compact row of this thread's first logical non-zero (upper_bound - 1 over rowstart)
                 int k0 = tid * E, lo_r = 0, hi_r = N;                 // invariant: rowstart[lo_r] <= k0 < rowstart[hi_r]
                 if (k0 < pv.nnz) {
@@ -1600,9 +1639,10 @@ __global__ void __launch_bounds__(T, RP_MIN_BLOCKS) rp_solve_kernel(const SolveA
                 const int pc = rs_c + wpre[(size_t)c * NW + (r >> 5)] + __popc(pv.mask[(size_t)c * NW + (r >> 5)] & ((1u << (r & 31)) - 1u));
                 unsigned fr_flags = (pr == rs_r ? 0x8000u : 0u) | (pr == pv.rowstart[r + 1] - 1 ? 0x4000u : 0u);
                 unsigned fc_flags = (pc == rs_c ? 0x8000u : 0u) | (pc == pv.rowstart[c + 1] - 1 ? 0x4000u : 0u);
-                size_t fr = (size_t)(pr % E) * T + pr / E, fc = (size_t)(pc % E) * T + pc / E;   // lane-interleaved layout
-                pv.cols[fr] = (uint16_t)((unsigned)c | fr_flags); pv.vals[fr] = w;
-                pv.cols[fc] = (uint16_t)((unsigned)r | fc_flags); pv.vals[fc] = w;
+                const int ir = pr % E, ic = pc % E;
+                size_t fr = (size_t)ir * T + pr / E, fc = (size_t)ic * T + pc / E;   // lane-interleaved layout
+                (ir < pv.ism ? pv.cols_s : pv.cols)[fr] = (uint16_t)((unsigned)c | fr_flags); (ir < pv.ism ? pv.vals_s : pv.vals)[fr] = w;
+                (ic < pv.ism ? pv.cols_s : pv.cols)[fc] = (uint16_t)((unsigned)r | fc_flags); (ic < pv.ism ? pv.vals_s : pv.vals)[fc] = w;
             }
             __syncthreads();
             { DegStep dg; dg.deg = pv.geo + (size_t)G_DEG * pv.gstride; csr_walk(sh, pv, dg); }   // row degrees of W
@@ -1676,7 +1716,7 @@ __global__ void __launch_bounds__(T, RP_MIN_BLOCKS) rp_solve_kernel(const SolveA
         }
         if (tid == 0) {
             A.status[b] = RP_STATUS_OK;
-            if (st) { st[4] = tot_it; st[5] = max_it_seen; st[6] = not_conv; }
+            if (st) { st[4] = tot_it; st[5] = max_it_seen; st[6] = not_conv | (sh.ties << 8); }
         }
     }
 }
@@ -1711,6 +1751,23 @@ bool make_layout(int max_ns, int max_topk, long long edge_cap, size_t dyn_bytes,
     return true;
 }
 
+int default_slots_uncached(size_t smem_bytes);
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize of both kernel variants, raised on demand and never lowered (launches with
+// different plans may be in flight on several streams; the attribute only has to cover the largest of them)
+template <bool ROBUST> __global__ void rp_solve_kernel(const SolveArgs A);
+bool ensure_smem_attr(size_t bytes) {
+    static size_t have = 48 * 1024;
+    if (bytes <= have) return true;
+    if (cudaFuncSetAttribute(rp_solve_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess ||
+        cudaFuncSetAttribute(rp_solve_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    have = bytes;
+    return true;
+}
+
 struct SmemPlan { size_t bytes; int mask_in_smem; int tfeat_stride; size_t mask_off; int dyn_in_global; size_t dyn_bytes; };
 
 bool make_smem_plan(long long Nmax_, int max_nt, int feat_dim, SmemPlan* S) {
@@ -1736,12 +1793,58 @@ bool make_smem_plan(long long Nmax_, int max_nt, int feat_dim, SmemPlan* S) {
     return true;
 }
 
+int sm_count() {
+    static int n_sm = 0;
+    if (n_sm == 0) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n_sm < 1) {
+            cudaGetLastError();
+            n_sm = 148;
+        }
+    }
+    return n_sm;
+}
+
+// Launch-time shared-memory plan.  With fewer CTAs than an SM can hold (small batches: B < 4 x 148) the idle shared memory
+// goes to the resident pairs: first the symmetric bit mask, then as much of the CSR of W as fits (cols uint16 + vals
+// float64, 10 bytes per directed non-zero).  The fitters make ~250 passes over that CSR per pair; from shared memory a pass
+// costs a few microseconds instead of an L2 round trip per batch of loads (the L1 of a CTA with a 200 KB carve-out is tiny).
+struct LaunchPlan { size_t bytes; int mask_in_smem; int csr_cap; size_t csr_off; };
+LaunchPlan make_launch_plan(const SmemPlan& S, const Layout& L, int grid) {
+    LaunchPlan P = {S.bytes, S.mask_in_smem, 0, 0};
+    if (S.dyn_in_global) return P;
+    const int per_sm = (grid + sm_count() - 1) / sm_count();
+    if (per_sm >= RP_MIN_BLOCKS) return P;
+    size_t avail = (size_t)(227 * 1024) / (size_t)per_sm - 13 * 1024;           // static part ~10.6 KB + 1 KB reserved per CTA
+    if (avail > (size_t)212 * 1024) avail = (size_t)212 * 1024;
+    // the CSR first (read ~250 times per pair), the bit mask (written in D, read once in E) only if both fit
+    const size_t mask = (size_t)L.Nmax * L.NWmax * sizeof(unsigned);
+    const long long want = (2 * L.edge_cap + 2 * T + 7) & ~7ll;
+    if (!P.mask_in_smem && align_up(S.mask_off + mask, 16) + (size_t)want * 10 <= avail) { P.mask_in_smem = 1; P.bytes = S.mask_off + mask; }
+    const size_t cur = align_up(P.bytes, 16);
+    if (avail > cur + 4096) {
+        long long entries = (long long)((avail - cur) / 10) & ~7ll;               // vals start 16-byte aligned
+        if (entries > want) entries = want;
+        P.csr_cap = (int)entries; P.csr_off = cur; P.bytes = cur + (size_t)entries * 10;
+    }
+    return P;
+}
+
 int default_slots(size_t smem_bytes) {
+    static size_t cached_bytes = (size_t)-1;
+    static int cached_slots = 0;
+    if (smem_bytes == cached_bytes && cached_slots > 0) return cached_slots;
+    int slots = default_slots_uncached(smem_bytes);
+    if (slots > 0) { cached_bytes = smem_bytes; cached_slots = slots; }
+    return slots;
+}
+
+int default_slots_uncached(size_t smem_bytes) {
     int dev = 0, sms = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) return -1;
     if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return -1;
     int per = 0;
-    cudaFuncSetAttribute(rp_solve_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+    if (!ensure_smem_attr(smem_bytes)) return -1;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, rp_solve_kernel<false>, T, smem_bytes) != cudaSuccess) return -1;
     if (per < 1) per = 1;
     return sms * per;
@@ -1815,15 +1918,13 @@ int rp_solve_batch_ex(int B, const int32_t* off_s, const int32_t* off_t,
     if (!make_smem_plan((long long)max_ns * max_topk, max_nt, feat_dim, &S)) return RP_ERR_UNSUPPORTED;
     Layout L;
     if (!make_layout(max_ns, max_topk, edge_cap, S.dyn_bytes, &L)) return RP_ERR_UNSUPPORTED;
-    if (cudaFuncSetAttribute(rp_solve_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S.bytes) != cudaSuccess ||
-        cudaFuncSetAttribute(rp_solve_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S.bytes) != cudaSuccess) {
-        cudaGetLastError();
-        return RP_ERR_CUDA;
-    }
     if (n_slots <= 0) {
         n_slots = default_slots(S.bytes);
         if (n_slots < 0) { cudaGetLastError(); return RP_ERR_NO_DEVICE; }
     }
+    const int grid = B < n_slots ? B : n_slots;
+    const LaunchPlan P = make_launch_plan(S, L, grid);
+    if (!ensure_smem_attr(P.bytes)) return RP_ERR_CUDA;
     if (workspace_bytes < 256 + (size_t)n_slots * L.slot_bytes) return RP_ERR_WORKSPACE_TOO_SMALL;
     SolveArgs a;
     a.B = B; a.off_s = off_s; a.off_t = off_t;
@@ -1840,14 +1941,14 @@ int rp_solve_batch_ex(int B, const int32_t* off_s, const int32_t* off_t,
     a.stop_after = stop_after;
     a.has_dbg = dbg ? 1 : 0;
     if (dbg) a.dbg = *dbg; else { rp_debug z = {}; a.dbg = z; }
-    a.mask_in_smem = S.mask_in_smem; a.tfeat_stride = S.tfeat_stride; a.sm_mask_off = S.mask_off;
+    a.mask_in_smem = P.mask_in_smem; a.tfeat_stride = S.tfeat_stride; a.sm_mask_off = S.mask_off;
+    a.csr_smem_cap = P.csr_cap; a.sm_csr_off = P.csr_off;
     a.dyn_in_global = S.dyn_in_global; a.o_dyn = L.o_dyn;
     if (cudaMemsetAsync(workspace, 0, 256, stream) != cudaSuccess) { cudaGetLastError(); return RP_ERR_CUDA; }
-    int grid = B < n_slots ? B : n_slots;
-    rp_solve_kernel<false><<<grid, T, S.bytes, stream>>>(a);
+    rp_solve_kernel<false><<<grid, T, P.bytes, stream>>>(a);
     ++g_launches;
     if (a.stop_after == RP_STAGE_SOLVE) {                // pairs whose eigen iteration needs the accelerated method
-        rp_solve_kernel<true><<<grid, T, S.bytes, stream>>>(a);
+        rp_solve_kernel<true><<<grid, T, P.bytes, stream>>>(a);
         ++g_launches;
     }
     if (cudaGetLastError() != cudaSuccess) return RP_ERR_CUDA;
@@ -1921,15 +2022,13 @@ int rp_spectral_irls_solve(int B, const int32_t* node_off,
     if (!make_smem_plan(max_nodes, 1, 8, &S)) return RP_ERR_UNSUPPORTED;
     Layout L;
     if (!make_layout(max_nodes, 1, edge_cap, S.dyn_bytes, &L)) return RP_ERR_UNSUPPORTED;
-    if (cudaFuncSetAttribute(rp_solve_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S.bytes) != cudaSuccess ||
-        cudaFuncSetAttribute(rp_solve_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S.bytes) != cudaSuccess) {
-        cudaGetLastError();
-        return RP_ERR_CUDA;
-    }
     if (n_slots <= 0) {
         n_slots = default_slots(S.bytes);
         if (n_slots < 0) { cudaGetLastError(); return RP_ERR_NO_DEVICE; }
     }
+    const int grid = B < n_slots ? B : n_slots;
+    const LaunchPlan P = make_launch_plan(S, L, grid);
+    if (!ensure_smem_attr(P.bytes)) return RP_ERR_CUDA;
     if (workspace_bytes < 256 + (size_t)n_slots * L.slot_bytes) return RP_ERR_WORKSPACE_TOO_SMALL;
     SolveArgs a = {};
     a.B = B; a.off_s = node_off; a.off_t = node_off;
@@ -1943,14 +2042,14 @@ int rp_spectral_irls_solve(int B, const int32_t* node_off,
     a.Nmax = L.Nmax; a.NWmax = L.NWmax;
     a.T_out = T_out; a.status = status; a.stats = stats;
     a.stop_after = RP_STAGE_SOLVE; a.has_dbg = 0;
-    a.mask_in_smem = S.mask_in_smem; a.tfeat_stride = S.tfeat_stride; a.sm_mask_off = S.mask_off;
+    a.mask_in_smem = P.mask_in_smem; a.tfeat_stride = S.tfeat_stride; a.sm_mask_off = S.mask_off;
+    a.csr_smem_cap = P.csr_cap; a.sm_csr_off = P.csr_off;
     a.dyn_in_global = S.dyn_in_global; a.o_dyn = L.o_dyn;
     if (cudaMemsetAsync(workspace, 0, 256, stream) != cudaSuccess) { cudaGetLastError(); return RP_ERR_CUDA; }
-    int grid = B < n_slots ? B : n_slots;
-    rp_solve_kernel<false><<<grid, T, S.bytes, stream>>>(a);
+    rp_solve_kernel<false><<<grid, T, P.bytes, stream>>>(a);
     ++g_launches;
     if (a.stop_after == RP_STAGE_SOLVE) {                // pairs whose eigen iteration needs the accelerated method
-        rp_solve_kernel<true><<<grid, T, S.bytes, stream>>>(a);
+        rp_solve_kernel<true><<<grid, T, P.bytes, stream>>>(a);
         ++g_launches;
     }
     if (cudaGetLastError() != cudaSuccess) return RP_ERR_CUDA;

@@ -46,6 +46,18 @@ def gather_primitives(feat, depth, normal, pts, weights, dataset):
                                                   side(pc, 1), side(nn, 1), side(desc, 1), weights.view(B, 2, K)[:, 1].reshape(-1), B)
 
 
+def _net_forward(net, inp):
+    """SCNet forward without the defensive output copy when ``net`` is this package's SCNet: the engine's output buffer is
+    consumed (blend, gather) before the next forward.  Any other module is simply called."""
+    from .model.mymodel import SCNet
+    if isinstance(net, SCNet):
+        from . import scnet_engine
+        if net._engine is None:
+            net._engine = scnet_engine.ScnetEngine(net)
+        return net._engine.forward(inp, borrow=True)
+    return net(inp)
+
+
 def solve_from_maps(feat, depth, normal, pts, weights, para, dataset, solver=None):
     """Poses [B,4,4] float64 (numpy) for B pairs from descriptor / depth / normal maps and keypoints; one gather kernel +
     one fused solver launch."""
@@ -91,7 +103,7 @@ def RelativePoseEstimationViaCompletion_batch(net, rgb, norm, depth, pts, weight
             Rs[0::2] = np.linalg.inv(R_hat)
             Rs[1::2] = R_hat
             _util.warping_device(inp, Rs, args.dataset, out=inp[:, 8:], src_index=swap)       # reads channels 0..7, writes 8..15
-            f = net(inp)                                                                                         # :619-623
+            f = _net_forward(net, inp)                                                                           # :619-623
             nrm2, dep2 = _util.blend_completion_device(f, mask, norm_gt, depth_gt)                                # :628-634
             para_this = copy.copy(args.para)
             for name in ('sigmaAngle1', 'sigmaAngle2', 'sigmaDist', 'sigmaFeat'):

@@ -78,7 +78,7 @@ def main():
         chain, sass = lines.get(off, ([("?", 0)], r[1]))
         # outermost frame in the main source file
         key = None
-        for f, l in reversed(chain):
+        for f, l in (chain if "--inner" in sys.argv else reversed(chain)):
             if f.endswith(".cu"):
                 key = (os.path.basename(f), l)
                 break

@@ -123,3 +123,21 @@ def test_match_topk_stage_entry():
         wij = tr['wij']
         ref_f = np.take_along_axis(wij, got.astype(np.int64), axis=1)
         assert np.allclose(f[lo:hi], ref_f, rtol=1e-12, atol=1e-300)
+
+
+def test_ambiguous_topk_rows_are_counted():
+    """stats[6] >> 8 counts the source rows whose top-k set is not decided by the keys (include/rp_b200.h): zero on the
+    generic synthetic pairs, non-zero when target descriptors are exact duplicates that straddle the top-k boundary."""
+    from relativepose_b200 import synth
+    from relativepose_b200.solver import PoseSolver
+    para = _para()
+    sol = PoseSolver("cuda:0")
+    recs = [synth.make_pair(40 + i, 50, 60) for i in range(4)]
+    _, st, stats = sol.solve_records(recs, para, return_stats=True)
+    assert (st == 0).all() and ((stats[:, 6] >> 8) == 0).all()
+    r = dict(recs[0])
+    ft = r['feat_tgt'].copy()
+    ft[:] = r['feat_src'][0]                       # every target descriptor equals source row 0: all its keys tie at 0
+    r['feat_tgt'] = ft
+    _, st2, stats2 = sol.solve_records([r, recs[1]], para, return_stats=True)
+    assert (stats2[0, 6] >> 8) > 0 and (stats2[1, 6] >> 8) == 0
