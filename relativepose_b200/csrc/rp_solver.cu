@@ -1082,7 +1082,9 @@ __device__ __forceinline__ void write_identity(double* T_out) {
 // not converged by then is marked RP_STATUS_RETRY and left.  ROBUST = true: launched right behind it on the same
 // stream, redoes exactly those pairs with the accelerated eigen iteration (lopcg_continue) -- a few microseconds when
 // there is none, and the common path keeps its register allocation.
-template <bool ROBUST>
+// BIG = true: pairs whose vectors do not fit shared memory keep them in the slot's workspace.  A template parameter, not a
+// run-time select, so that in the common variant every access to the per-pair vectors is a known shared-memory access.
+template <bool ROBUST, bool BIG>
 __global__ void __launch_bounds__(T, RP_MIN_BLOCKS) rp_solve_kernel(const SolveArgs A) {
     extern __shared__ __align__(16) unsigned char dyn_smem[];
     __shared__ Shared sh;
@@ -1090,7 +1092,7 @@ __global__ void __launch_bounds__(T, RP_MIN_BLOCKS) rp_solve_kernel(const SolveA
     int* work_counter = reinterpret_cast<int*>(A.ws) + (ROBUST ? 1 : 0);
     char* slot = A.ws + 256 + (size_t)blockIdx.x * A.slot_bytes;
     // per-pair vectors / staging: dynamic shared memory, or (N too large for it) the same layout in the slot's workspace
-    unsigned char* const dyn = A.dyn_in_global ? reinterpret_cast<unsigned char*>(slot + A.o_dyn) : dyn_smem;
+    unsigned char* const dyn = BIG ? reinterpret_cast<unsigned char*>(slot + A.o_dyn) : dyn_smem;
 
     for (;;) {
         __syncthreads();
@@ -1755,12 +1757,12 @@ int default_slots_uncached(size_t smem_bytes);
 
 // cudaFuncAttributeMaxDynamicSharedMemorySize of both kernel variants, raised on demand and never lowered (launches with
 // different plans may be in flight on several streams; the attribute only has to cover the largest of them)
-template <bool ROBUST> __global__ void rp_solve_kernel(const SolveArgs A);
+template <bool ROBUST, bool BIG> __global__ void rp_solve_kernel(const SolveArgs A);
 bool ensure_smem_attr(size_t bytes) {
     static size_t have = 48 * 1024;
     if (bytes <= have) return true;
-    if (cudaFuncSetAttribute(rp_solve_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess ||
-        cudaFuncSetAttribute(rp_solve_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess) {
+    if (cudaFuncSetAttribute(rp_solve_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess ||
+        cudaFuncSetAttribute(rp_solve_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess) {
         cudaGetLastError();
         return false;
     }
@@ -1845,7 +1847,7 @@ int default_slots_uncached(size_t smem_bytes) {
     if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return -1;
     int per = 0;
     if (!ensure_smem_attr(smem_bytes)) return -1;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, rp_solve_kernel<false>, T, smem_bytes) != cudaSuccess) return -1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, rp_solve_kernel<false, false>, T, smem_bytes) != cudaSuccess) return -1;
     if (per < 1) per = 1;
     return sms * per;
 }
@@ -1945,10 +1947,12 @@ int rp_solve_batch_ex(int B, const int32_t* off_s, const int32_t* off_t,
     a.csr_smem_cap = P.csr_cap; a.sm_csr_off = P.csr_off;
     a.dyn_in_global = S.dyn_in_global; a.o_dyn = L.o_dyn;
     if (cudaMemsetAsync(workspace, 0, 256, stream) != cudaSuccess) { cudaGetLastError(); return RP_ERR_CUDA; }
-    rp_solve_kernel<false><<<grid, T, P.bytes, stream>>>(a);
+    if (S.dyn_in_global) rp_solve_kernel<false, true><<<grid, T, P.bytes, stream>>>(a);
+    else rp_solve_kernel<false, false><<<grid, T, P.bytes, stream>>>(a);
     ++g_launches;
     if (a.stop_after == RP_STAGE_SOLVE) {                // pairs whose eigen iteration needs the accelerated method
-        rp_solve_kernel<true><<<grid, T, P.bytes, stream>>>(a);
+        if (S.dyn_in_global) rp_solve_kernel<true, true><<<grid, T, P.bytes, stream>>>(a);
+        else rp_solve_kernel<true, false><<<grid, T, P.bytes, stream>>>(a);
         ++g_launches;
     }
     if (cudaGetLastError() != cudaSuccess) return RP_ERR_CUDA;
@@ -2046,10 +2050,12 @@ int rp_spectral_irls_solve(int B, const int32_t* node_off,
     a.csr_smem_cap = P.csr_cap; a.sm_csr_off = P.csr_off;
     a.dyn_in_global = S.dyn_in_global; a.o_dyn = L.o_dyn;
     if (cudaMemsetAsync(workspace, 0, 256, stream) != cudaSuccess) { cudaGetLastError(); return RP_ERR_CUDA; }
-    rp_solve_kernel<false><<<grid, T, P.bytes, stream>>>(a);
+    if (S.dyn_in_global) rp_solve_kernel<false, true><<<grid, T, P.bytes, stream>>>(a);
+    else rp_solve_kernel<false, false><<<grid, T, P.bytes, stream>>>(a);
     ++g_launches;
     if (a.stop_after == RP_STAGE_SOLVE) {                // pairs whose eigen iteration needs the accelerated method
-        rp_solve_kernel<true><<<grid, T, P.bytes, stream>>>(a);
+        if (S.dyn_in_global) rp_solve_kernel<true, true><<<grid, T, P.bytes, stream>>>(a);
+        else rp_solve_kernel<true, false><<<grid, T, P.bytes, stream>>>(a);
         ++g_launches;
     }
     if (cudaGetLastError() != cudaSuccess) return RP_ERR_CUDA;
