@@ -35,7 +35,16 @@ constexpr int EPI = 128, LOADERS = 256, CTA = EPI + LOADERS + 64;    // warps 0-
 constexpr int MAXT = 16;            // taps over all classes
 constexpr int MAXACC = 8;           // accumulator sets in TMEM (512 columns / (classes x BN), at most 8)
 constexpr int MAXNPX = 640;         // halo pixels (4 planes x 17 x 9 = 612 for 4x4 s2)
+constexpr int MAXNG = 8;            // loader groups = halo buffers in flight (2, 4 or 8)
+constexpr int PIXTAB = 2 * MAXNPX;  // ints of per-group pixel tables
 constexpr int EPI_SMEM = (4 * 32 * 33 + 16 * 4 * 64) * 4;            // per-warp transpose buffers + partial sums
+
+// Profiling only (flags bit 5): cycles per role, summed over CTAs -- [0] loader total, [1] loader wait a_empty, [2] loader copy wait,
+// [3] loader transform, [4] mma total, [5] mma wait acc_empty, [6] mma wait a_full, [7] mma wait w_full, [8] epilogue total,
+// [9] epilogue wait acc_full, [10] epilogue tmem_ld, [11] epilogue stats barriers, [12] loader table build
+__device__ unsigned long long g_halo_prof[16];
+#define HP_T0(var) long long var = 0; if (PROF) var = clock64();
+#define HP_ADD(idx, var) if (PROF) { prof_acc[idx] += clock64() - var; }
 
 struct Plane { int qy, qx, oy, ox; };      // input row = (a0 + oy + hy) * istr + qy (same for columns)
 struct HTap { int cls, a_off, first; };    // a_off: byte offset of the tap's first row inside one K core of the halo
@@ -57,6 +66,8 @@ struct HaloArgs {
     int ng;                                // loader groups = halo buffers (2 or 4): group i fills buffer i with chunks i, i+ng, ...
     float inv_nkt;
     int w_resident;                        // all weight blocks of a tile fit in the ring: loaded once per CTA, never freed
+    int dbg;                               // profiling only (flags >> 2): 1 no epilogue stores/stats, 2 no loader copy/transform, 4 no MMA
+    int h2math;                            // producer BatchNorm + LeakyReLU of 16-bit sources in packed half arithmetic (flags bit 1)
     void* out; int out_pitch, out_ch_off, out_bf16;
     float* psum; float* psq;
     const float* bias; int tanh_out;
@@ -116,12 +127,15 @@ __global__ void __launch_bounds__(CTA, 1) conv_halo_tc(const HaloArgs A, const u
     constexpr int KC = TK / 8;
     constexpr int B_BYTES = BN * TK * 2;
     constexpr int U = 4;                           // loads in flight per loader thread
-    __shared__ __align__(8) uint64_t a_full[4], a_empty[4], w_full[NB], w_empty[NB], acc_full[MAXACC], acc_empty[MAXACC];
+    __shared__ __align__(8) uint64_t a_full[MAXNG], a_empty[MAXNG], w_full[NB], w_empty[NB], acc_full[MAXACC], acc_empty[MAXACC];
     __shared__ uint32_t tmem_slot;
-    __shared__ int s_pix[2 * MAXNPX];              // one pixel table per loader group (ng x NPX <= 2 x MAXNPX)
+    __shared__ int s_pix[PIXTAB];                  // one pixel table per loader group (ng x NPX <= PIXTAB)
     __shared__ int s_lut[MAXNPX];                  // halo pixel -> (plane << 20 | row << 10 | column), tile independent
     __shared__ __align__(16) float s_bias[256];                  // bias of the 1x1 heads (Cout <= 256), zero padded to whole n-tiles
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const bool PROF = (A.dbg & 8) != 0;
+    long long prof_acc[13] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    const long long prof_start = clock64();
     const int a_bytes = ((KC * A.a_lbo + 127) / 128) * 128;
     unsigned char* sEpi = smem;                                  // [EPI_SMEM] epilogue scratch (never aliased)
     unsigned char* sA = smem + EPI_SMEM;                         // ng halo buffers
@@ -129,7 +143,7 @@ __global__ void __launch_bounds__(CTA, 1) conv_halo_tc(const HaloArgs A, const u
 
     if (tid == 0) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) { mbar_init(&a_full[i], (uint32_t)(LOADERS / A.ng)); mbar_init(&a_empty[i], 1); }
+        for (int i = 0; i < MAXNG; ++i) { mbar_init(&a_full[i], (uint32_t)(LOADERS / A.ng)); mbar_init(&a_empty[i], 1); }
 #pragma unroll
         for (int i = 0; i < NB; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
 #pragma unroll
@@ -169,6 +183,7 @@ __global__ void __launch_bounds__(CTA, 1) conv_halo_tc(const HaloArgs A, const u
             if (tseq != cur_seq) {
                 cur_seq = tseq;
                 tc_ = decode_tile(A, (int)blockIdx.x + tseq * (int)gridDim.x);
+                HP_T0(tb0)
                 named_bar_sync(2 + gi, GT);                      // the group is done with its previous table
                 for (int h = lt; h < A.NPX; h += GT) {           // global pixel index of every halo pixel (-1 = zero padding)
                     const int l = s_lut[h];
@@ -178,6 +193,7 @@ __global__ void __launch_bounds__(CTA, 1) conv_halo_tc(const HaloArgs A, const u
                     my_pix[h] = (iy >= 0 && iy < A.Hin && ix >= 0 && ix < A.Win) ? (tc_.img * A.Hin + iy) * A.Win + ix : -1;
                 }
                 named_bar_sync(2 + gi, GT);
+                HP_ADD(12, tb0)
             }
             {
                 const int g = tc_.g;
@@ -203,7 +219,9 @@ __global__ void __launch_bounds__(CTA, 1) conv_halo_tc(const HaloArgs A, const u
                 const size_t esz = in_bf16 ? 2 : 4;
                 const unsigned char* base = reinterpret_cast<const unsigned char*>(S.ptr) + (size_t)(S.ch_off + ch) * esz;
                 const size_t pstride = (size_t)S.pitch * esz;
+                HP_T0(w0)
                 mbar_wait_backoff(&a_empty[b], (use & 1u) ^ 1u); // the MMAs that read this buffer are done
+                HP_ADD(1, w0)
                 unsigned char* dst = sA + b * a_bytes + kc * A.a_lbo;
                 auto finish = [&](float (&v)[8], int h) {       // BatchNorm + LeakyReLU, bf16, one 16-byte core row
                     if (act) {
@@ -217,24 +235,59 @@ __global__ void __launch_bounds__(CTA, 1) conv_halo_tc(const HaloArgs A, const u
                     o.z = *reinterpret_cast<uint32_t*>(&p2); o.w = *reinterpret_cast<uint32_t*>(&p3);
                     *reinterpret_cast<uint4*>(dst + (size_t)h * 16) = o;
                 };
-                if (in_bf16) {
-                    constexpr int UB = 2 * U;                       // 8 x 16-byte loads in flight per thread
-                    for (int hb = h0; hb < A.NPX; hb += HSTEP * UB) {
-                        uint4 x[UB];
-                        int pix[UB];
+                long long x0 = 0;
+                if (A.dbg & 2) {
+                } else if (in_bf16) {
+                    // 16-bit sources: the raw halo goes global -> shared with cp.async (LDGSTS: no registers held per load),
+                    // so a loader group has its WHOLE K chunk in flight instead of 8 loads per thread -- these layers are
+                    // bound by memory-level parallelism.  Padding pixels are zero-filled by the copy itself.  Each thread then
+                    // normalises, in place, exactly the units it copied (no cross-thread hand-off); a source without a
+                    // producer BatchNorm (the split stem input) needs no second pass at all.
+                    for (int h = h0; h < A.NPX; h += HSTEP) {
+                        const int pix = my_pix[h];
+                        cp_async16(dst + (size_t)h * 16, base + (size_t)(pix < 0 ? 0 : pix) * pstride, pix < 0 ? 0u : 16u);
+                    }
+                    HP_T0(c0)
+                    cp_async_wait_all();
+                    HP_ADD(2, c0)
+                    if (PROF) x0 = clock64();
+                    if (act && A.h2math) {
+                        // packed half arithmetic: z = x * scale + shift is ONE rounding of the exact value for half inputs (the
+                        // float path rounds to half after the float FMA as well); what differs is scale / shift rounded to half.
+                        // LeakyReLU(z) = max(z, slope z) for 0 <= slope <= 1.  12 instructions per 8 channels instead of ~36.
+                        rp_h162 sc2[4], sh2[4];
 #pragma unroll
-                        for (int u = 0; u < UB; ++u) {
-                            const int h = hb + u * HSTEP;
-                            pix[u] = h < A.NPX ? my_pix[h] : -2;
-                            if (pix[u] >= 0) x[u] = __ldg(reinterpret_cast<const uint4*>(base + (size_t)pix[u] * pstride));
+                        for (int q = 0; q < 4; ++q) { sc2[q] = rp_f2_to_h2(sc[2 * q], sc[2 * q + 1]); sh2[q] = rp_f2_to_h2(sh[2 * q], sh[2 * q + 1]); }
+                        const rp_h162 sl2 = rp_f2_to_h2(slope, slope);
+                        // four units per step, straight-line (loads first, then the math, then the stores): padding units are
+                        // recomputed as zero through a select instead of a branch so that the four chains interleave
+                        for (int hb = h0; hb < A.NPX; hb += 4 * HSTEP) {
+                            uint4 x[4]; bool live[4];
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) {
+                                const int h = hb + u * HSTEP;
+                                live[u] = h < A.NPX && my_pix[h < A.NPX ? h : 0] >= 0;
+                                x[u] = *reinterpret_cast<const uint4*>(dst + (size_t)(h < A.NPX ? h : h0) * 16);
+                            }
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) {
+                                rp_h162* hp = reinterpret_cast<rp_h162*>(&x[u]);
+#pragma unroll
+                                for (int q = 0; q < 4; ++q) { const rp_h162 z = __hfma2(hp[q], sc2[q], sh2[q]); hp[q] = __hmax2(z, __hmul2(z, sl2)); }
+                            }
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) {
+                                const int h = hb + u * HSTEP;
+                                if (live[u]) *reinterpret_cast<uint4*>(dst + (size_t)h * 16) = x[u];
+                            }
                         }
-#pragma unroll
-                        for (int u = 0; u < UB; ++u) {
-                            if (pix[u] == -2) continue;
-                            const int h = hb + u * HSTEP;
-                            if (pix[u] < 0) { *reinterpret_cast<uint4*>(dst + (size_t)h * 16) = make_uint4(0u, 0u, 0u, 0u); continue; }
+                    } else if (act) {
+#pragma unroll 2
+                        for (int h = h0; h < A.NPX; h += HSTEP) {
+                            if (my_pix[h] < 0) continue;              // zero padding stays zero (the BatchNorm shift must not leak in)
+                            const uint4 x = *reinterpret_cast<const uint4*>(dst + (size_t)h * 16);
                             float v[8];
-                            const rp_h162* hp = reinterpret_cast<const rp_h162*>(&x[u]);
+                            const rp_h162* hp = reinterpret_cast<const rp_h162*>(&x);
 #pragma unroll
                             for (int q = 0; q < 4; ++q) { const float2 f = rp_h2_to_f2(hp[q]); v[2 * q] = f.x; v[2 * q + 1] = f.y; }
                             finish(v, h);
@@ -265,6 +318,7 @@ __global__ void __launch_bounds__(CTA, 1) conv_halo_tc(const HaloArgs A, const u
                         }
                     }
                 }
+                if (in_bf16 && !(A.dbg & 2)) { HP_ADD(3, x0) }
                 fence_async_smem();                // generic-proxy writes -> visible to the tensor core (async proxy)
                 mbar_arrive(&a_full[b]);
             }
@@ -325,7 +379,9 @@ __global__ void __launch_bounds__(CTA, 1) conv_halo_tc(const HaloArgs A, const u
         bool w_ready = false;
         for (int tile = blockIdx.x; tile < A.total_tiles; tile += gridDim.x, ++tl) {
             const uint32_t ab = tl % (uint32_t)A.nacc;
+            HP_T0(m0)
             mbar_wait(&acc_empty[ab], ((tl / (uint32_t)A.nacc) & 1u) ^ 1u);   // the epilogue has drained this accumulator set
+            HP_ADD(5, m0)
             tc_fence_after();
             const uint32_t acc0 = tmem_d + ab * (uint32_t)A.acc_cols;
             if (A.w_resident && !w_ready) {                               // resident weights: wait for them once
@@ -334,7 +390,9 @@ __global__ void __launch_bounds__(CTA, 1) conv_halo_tc(const HaloArgs A, const u
             }
             for (int c = 0; c < A.nkt; ++c, ++cc) {
                 const uint32_t b = cc % (uint32_t)A.ng;
+                HP_T0(m1)
                 mbar_wait(&a_full[b], (cc / (uint32_t)A.ng) & 1u);
+                HP_ADD(6, m1)
                 tc_fence_after();
                 const uint32_t a_lo_buf = a_lo_k | (sA16 + b * ((uint32_t)a_bytes >> 4));
                 const uint32_t fresh_mask = c == 0 ? first_mask : 0u;
@@ -345,7 +403,7 @@ __global__ void __launch_bounds__(CTA, 1) conv_halo_tc(const HaloArgs A, const u
                         if (t < A.ntap) {
                             const uint32_t a_lo = a_lo_buf + tap_a[t];
                             const uint32_t b_lo = b_lo0 + (uint32_t)t * (uint32_t)(B_BYTES >> 4);
-                            if (leader) {
+                            if (leader && !(A.dbg & 4)) {
 #pragma unroll
                                 for (int j = 0; j < TK / 16; ++j)
                                     umma_bf16(acc0 + tap_col[t], pack_desc(a_lo + j * a_step, a_hi), pack_desc(b_lo + j * b_step, b_hi), idesc,
@@ -358,14 +416,18 @@ __global__ void __launch_bounds__(CTA, 1) conv_halo_tc(const HaloArgs A, const u
                     for (int t = 0; t < MAXT; ++t) {
                         if (t < A.ntap) {
                             const uint32_t slot = wi % NB;
+                            HP_T0(m2)
                             mbar_wait(&w_full[slot], (uint32_t)((wi / NB) & 1));
+                            HP_ADD(7, m2)
                             const uint32_t a_lo = a_lo_buf + tap_a[t];
                             const uint32_t b_lo = b_lo_k | (sB16 + slot * (uint32_t)(B_BYTES >> 4));
                             if (leader) {
+                                if (!(A.dbg & 4)) {
 #pragma unroll
-                                for (int j = 0; j < TK / 16; ++j)
-                                    umma_bf16(acc0 + tap_col[t], pack_desc(a_lo + j * a_step, a_hi), pack_desc(b_lo + j * b_step, b_hi), idesc,
-                                              (j > 0 || !((fresh_mask >> t) & 1u)) ? 1u : 0u);
+                                    for (int j = 0; j < TK / 16; ++j)
+                                        umma_bf16(acc0 + tap_col[t], pack_desc(a_lo + j * a_step, a_hi), pack_desc(b_lo + j * b_step, b_hi), idesc,
+                                                  (j > 0 || !((fresh_mask >> t) & 1u)) ? 1u : 0u);
+                                }
                                 umma_commit(&w_empty[slot]);   // frees the weight slot once these MMAs have read it
                             }
                             ++wi;
@@ -390,12 +452,16 @@ __global__ void __launch_bounds__(CTA, 1) conv_halo_tc(const HaloArgs A, const u
             const TileCoord tc_ = decode_tile(A, tile);
             const uint32_t ab = tl % (uint32_t)A.nacc;
             const int a = tc_.a0 + (m >> 3), bcol = tc_.b0 + (m & 7);
+            HP_T0(e0)
             mbar_wait(&acc_full[ab], (tl / (uint32_t)A.nacc) & 1u);
+            HP_ADD(9, e0)
             tc_fence_after();
             for (int u = 0; u < nunit; ++u) {
                 const int cls = u / (BN / 32), c0 = (u - cls * (BN / 32)) * 32;
                 float v[32];
+                HP_T0(e1)
                 tmem_ld32(tmem_d + ((uint32_t)(q * 32) << 16) + ab * (uint32_t)A.acc_cols + (uint32_t)(cls * BN + c0), v);
+                HP_ADD(10, e1)
                 const bool valid = a < A.cls_Ha[cls] && bcol < A.cls_Wb[cls];
                 const int co0 = tc_.tile_n * BN + c0;
                 if (A.bias || A.tanh_out) {                 // (bias/tanh layers have Cout <= 256, checked on the host)
@@ -410,11 +476,16 @@ __global__ void __launch_bounds__(CTA, 1) conv_halo_tc(const HaloArgs A, const u
                         for (int j = 0; j < 32; ++j) v[j] = fast_tanh(v[j]);
                     }
                 }
+                rp_h162 pk[16];            // 16-bit output: packed once, stored as packed
                 if (A.out_bf16) {          // statistics describe what the consumer will read: the rounded values
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) v[j] = rp_h_to_f(rp_f_to_h(v[j]));
+                    for (int j = 0; j < 16; ++j) {
+                        pk[j] = rp_f2_to_h2(v[2 * j], v[2 * j + 1]);
+                        const float2 f = rp_h2_to_f2(pk[j]);
+                        v[2 * j] = f.x; v[2 * j + 1] = f.y;
+                    }
                 }
-                if (valid) {
+                if (valid && !(A.dbg & 1)) {
                     const int oy = a * A.ostr + A.cls_py[cls], ox = bcol * A.ostr + A.cls_px[cls];
                     const size_t opix = ((size_t)tc_.img * A.Hout + oy) * A.Wout + ox;
                     if (A.out_bf16) {
@@ -422,11 +493,9 @@ __global__ void __launch_bounds__(CTA, 1) conv_halo_tc(const HaloArgs A, const u
                         if (co0 + 31 < A.Cout) {
 #pragma unroll
                             for (int j = 0; j < 32; j += 8) {
-                                rp_h162 p0 = rp_f2_to_h2(v[j], v[j + 1]), p1 = rp_f2_to_h2(v[j + 2], v[j + 3]);
-                                rp_h162 p2 = rp_f2_to_h2(v[j + 4], v[j + 5]), p3 = rp_f2_to_h2(v[j + 6], v[j + 7]);
                                 uint4 o;
-                                o.x = *reinterpret_cast<uint32_t*>(&p0); o.y = *reinterpret_cast<uint32_t*>(&p1);
-                                o.z = *reinterpret_cast<uint32_t*>(&p2); o.w = *reinterpret_cast<uint32_t*>(&p3);
+                                o.x = *reinterpret_cast<uint32_t*>(&pk[j / 2]); o.y = *reinterpret_cast<uint32_t*>(&pk[j / 2 + 1]);
+                                o.z = *reinterpret_cast<uint32_t*>(&pk[j / 2 + 2]); o.w = *reinterpret_cast<uint32_t*>(&pk[j / 2 + 3]);
                                 *reinterpret_cast<uint4*>(op + j) = o;
                             }
                         } else {
@@ -444,7 +513,7 @@ __global__ void __launch_bounds__(CTA, 1) conv_halo_tc(const HaloArgs A, const u
                         }
                     }
                 }
-                if (A.psum) {
+                if (A.psum && !(A.dbg & 1)) {
 #pragma unroll
                     for (int j = 0; j < 32; ++j) Tt[lane * 33 + j] = valid ? v[j] : 0.f;
                     __syncwarp();
@@ -458,8 +527,9 @@ __global__ void __launch_bounds__(CTA, 1) conv_halo_tc(const HaloArgs A, const u
             }
             tc_fence_before();
             mbar_arrive(&acc_empty[ab]);               // this thread's tcgen05.ld of the set have completed (wait::ld)
+            HP_T0(e2)
             if (A.psum) {
-                named_bar_sync(6, EPI);
+                named_bar_sync(14, EPI);
                 for (int i = tid; i < nunit * 32; i += EPI) {
                     const int u = i >> 5, col = i & 31;
                     const int cls = u / (BN / 32), c0 = (u - cls * (BN / 32)) * 32;
@@ -473,9 +543,16 @@ __global__ void __launch_bounds__(CTA, 1) conv_halo_tc(const HaloArgs A, const u
                         A.psq[prow * A.Cout + co] = s2;
                     }
                 }
-                named_bar_sync(6, EPI);                // `red` is free for the next tile
+                named_bar_sync(14, EPI);               // `red` is free for the next tile
             }
+            HP_ADD(11, e2)
         }
+    }
+    if (PROF && lane == 0) {
+        const long long tot = clock64() - prof_start;
+        if (warp == 4) { atomicAdd(&g_halo_prof[0], (unsigned long long)tot); for (int i = 1; i <= 3; ++i) atomicAdd(&g_halo_prof[i], (unsigned long long)prof_acc[i]); atomicAdd(&g_halo_prof[12], (unsigned long long)prof_acc[12]); }
+        if (warp == 13) { atomicAdd(&g_halo_prof[4], (unsigned long long)tot); for (int i = 5; i <= 7; ++i) atomicAdd(&g_halo_prof[i], (unsigned long long)prof_acc[i]); }
+        if (warp == 0) { atomicAdd(&g_halo_prof[8], (unsigned long long)tot); for (int i = 9; i <= 11; ++i) atomicAdd(&g_halo_prof[i], (unsigned long long)prof_acc[i]); }
     }
     tc_fence_before();
     __syncthreads();
@@ -577,17 +654,26 @@ static bool build_halo_args(const rp_conv_desc* d, HaloArgs* H, int bn, int tk, 
 }
 
 template <int BN, int TK, int NB>
-static int launch_halo(const HaloArgs& H0, const void* wp, cudaStream_t stream) {
+static int launch_halo(const HaloArgs& H0, const void* wp, int h2math, cudaStream_t stream) {
     constexpr int KC = TK / 8;
     HaloArgs H = H0;
     const size_t a_bytes = (size_t)((KC * H.a_lbo + 127) / 128) * 128;
     const size_t fixed = (size_t)EPI_SMEM + (size_t)NB * BN * TK * 2;
-    // four gathers in flight when the halo is small (stem, 3x3 / transposed layers, 1x1 heads), two otherwise
-    H.ng = (H.NPX * 4 <= 2 * MAXNPX && fixed + 4 * a_bytes <= 220 * 1024) ? 4 : 2;
-    H.w_resident = (H.ntn == 1 && H.nkt * H.ntap <= NB) ? 1 : 0;
-    const size_t smem = fixed + H.ng * a_bytes;
-    if (smem > 220 * 1024) return RP_ERR_UNSUPPORTED;
     auto kern = conv_halo_tc<BN, TK, NB>;
+    static size_t limit = 0;                                    // dynamic bytes a CTA of this instantiation may take
+    if (limit == 0) {
+        cudaFuncAttributes fa;
+        if (cudaFuncGetAttributes(&fa, kern) != cudaSuccess) { cudaGetLastError(); return RP_ERR_CUDA; }
+        limit = (size_t)227 * 1024 - fa.sharedSizeBytes - 1024;
+    }
+    // eight / four K chunks in flight (one per loader group) when the halo is small enough, two otherwise
+    H.ng = 2;
+    for (int ng = MAXNG; ng > 2; ng >>= 1)
+        if (H.NPX * ng <= PIXTAB && fixed + (size_t)ng * a_bytes <= limit) { H.ng = ng; break; }
+    H.w_resident = (H.ntn == 1 && H.nkt * H.ntap <= NB) ? 1 : 0;
+    H.h2math = h2math & 1; H.dbg = h2math >> 1;
+    const size_t smem = fixed + H.ng * a_bytes;
+    if (smem > limit) return RP_ERR_UNSUPPORTED;
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { cudaGetLastError(); return RP_ERR_CUDA; }
     static int n_sm = 0;
     if (n_sm == 0) {
@@ -630,12 +716,21 @@ int rp_conv_halo_debug(const rp_conv_desc* d, int bn, int tk, int flags, int* ou
     return RP_OK;
 }
 
+// Profiling only: read and clear the per-role cycle counters (see g_halo_prof); flags bit 5 enables them.
+int rp_conv_halo_prof(unsigned long long* out16) {
+    if (!out16) return RP_ERR_INVALID_ARG;
+    if (cudaMemcpyFromSymbol(out16, halo::g_halo_prof, sizeof(unsigned long long) * 16) != cudaSuccess) { cudaGetLastError(); return RP_ERR_CUDA; }
+    unsigned long long z[16] = {0};
+    cudaMemcpyToSymbol(halo::g_halo_prof, z, sizeof(z));
+    return RP_OK;
+}
+
 int rp_conv_layer_halo(const rp_conv_desc* d, const void* w_packed, int bn, int tk, int flags, void* stream_) {
     halo::HaloArgs H;
     if (!d || !w_packed || !d->out || !d->src[0].ptr) return RP_ERR_INVALID_ARG;
     if (!halo::build_halo_args(d, &H, bn, tk, nullptr, (flags & 1) != 0)) return RP_ERR_UNSUPPORTED;
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
-#define RP_HALO_CASE(BN_, TK_, NB_) if (bn == BN_ && tk == TK_) return halo::launch_halo<BN_, TK_, NB_>(H, w_packed, stream);
+#define RP_HALO_CASE(BN_, TK_, NB_) if (bn == BN_ && tk == TK_) return halo::launch_halo<BN_, TK_, NB_>(H, w_packed, (flags >> 1), stream);
     RP_HALO_CASE(32, 64, 32) RP_HALO_CASE(64, 64, 12) RP_HALO_CASE(128, 64, 6)
     RP_HALO_CASE(32, 32, 16) RP_HALO_CASE(64, 32, 16) RP_HALO_CASE(128, 32, 8)
     RP_HALO_CASE(32, 16, 16) RP_HALO_CASE(256, 32, 4)

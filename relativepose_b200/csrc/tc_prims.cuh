@@ -31,13 +31,16 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    // try_wait with a suspend-time hint: a waiting warp sleeps in hardware until the phase completes (or ~1 us passes) instead
+    // of spinning -- the MMA and epilogue warps wait half of the time on the small-N layers and their polling loops would
+    // otherwise take issue slots from the loader warps on the same scheduler
     uint32_t done = 0;
     const uint32_t a = smem_u32(bar);
     while (!done) {
         asm volatile("{\n\t.reg .pred p;\n\t"
-                     "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                     "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
                      "selp.u32 %0, 1, 0, p;\n\t}"
-                     : "=r"(done) : "r"(a), "r"(parity) : "memory");
+                     : "=r"(done) : "r"(a), "r"(parity), "r"(1000u) : "memory");
     }
 }
 // Same, for a producer that runs ahead of its consumer (halo loaders waiting for a free buffer, the TMA warp waiting for a
@@ -47,11 +50,11 @@ __device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity
     const uint32_t a = smem_u32(bar);
     for (;;) {
         asm volatile("{\n\t.reg .pred p;\n\t"
-                     "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                     "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
                      "selp.u32 %0, 1, 0, p;\n\t}"
-                     : "=r"(done) : "r"(a), "r"(parity) : "memory");
+                     : "=r"(done) : "r"(a), "r"(parity), "r"(20000u) : "memory");   // suspend-time hint: poll rarely
         if (done) break;
-        __nanosleep(64);
+        __nanosleep(128);
     }
 }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -102,6 +105,14 @@ __device__ __forceinline__ void store_core_row(unsigned char* tile, int rows, in
     *reinterpret_cast<uint4*>(tile + off) = u;
 }
 
+
+// 16-byte asynchronous global -> shared copy (LDGSTS); src_bytes = 0 zero-fills the destination
+__device__ __forceinline__ void cp_async16(void* dst_smem, const void* src_gmem, uint32_t src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+    asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+}
 
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");

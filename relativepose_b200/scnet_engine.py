@@ -90,7 +90,9 @@ class ScnetEngine(object):
         self.use_graph = os.environ.get("RP_SCNET_GRAPH", "1") == "1"
         # halo-tile tcgen05 kernel for the 3x3 / 4x4 layers with a large enough spatial extent (csrc/scnet_halo.cu)
         self.halo = os.environ.get("RP_SCNET_HALO", "1") == "1"
-        self.halo_flags = int(os.environ.get("RP_SCNET_HALO_FLAGS", "0"))
+        # bit 0: 16-pixel halo pitch (debugging aid); bit 1: producer BatchNorm + LeakyReLU of 16-bit sources in packed half
+        # arithmetic (default: as accurate as the float form on the reference goldens, a third of the loader instructions)
+        self.halo_flags = int(os.environ.get("RP_SCNET_HALO_FLAGS", "2"))
         self.halo_min = int(os.environ.get("RP_SCNET_HALO_MIN", "1"))     # smallest base-grid extent that takes the halo kernel
         act = os.environ.get("RP_SCNET_ACT", self._act_default)
         self.act_bf16 = self.mode == 'tc' and act == 'bf16'

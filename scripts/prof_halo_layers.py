@@ -18,6 +18,7 @@ LAYERS = [
     ("head_f", 0, 1, 1, 0, 224, [64], 32, False),
 ]
 eng = ScnetEngine(None, mode='tc')
+print('halo flags', eng.halo_flags)
 eng._P, eng._dev, eng._bufs = G, dev, {'partials': None}
 n = 2 * G
 todo = []
@@ -50,4 +51,17 @@ for it in range(1 + reps):
             e1.record(); torch.cuda.synchronize()
             if it > 0 or reps == 1:
                 print("%-8s %8.1f us (incl. bn_finalize)" % (name, e0.elapsed_time(e1) * 1e3))
+                if eng.halo_flags & 32 and it == reps:
+                    import ctypes
+                    buf = (ctypes.c_ulonglong * 16)()
+                    eng.lib.rp_conv_halo_prof(buf)
+                    v = [float(x) for x in buf]
+                    pc = lambda a, b: 100.0 * a / max(b, 1.0)
+                    print("   loader: wait a_empty %.0f%%, copy wait %.0f%%, transform %.0f%%, table %.0f%% | mma: wait acc_empty %.0f%%, a_full %.0f%%, w_full %.0f%% | "
+                          "epilogue: wait acc_full %.0f%%, tmem_ld %.0f%%, stats barriers+psum %.0f%%" % (
+                              pc(v[1], v[0]), pc(v[2], v[0]), pc(v[3], v[0]), pc(v[12], v[0]), pc(v[5], v[4]), pc(v[6], v[4]), pc(v[7], v[4]),
+                              pc(v[9], v[8]), pc(v[10], v[8]), pc(v[11], v[8])))
+                elif eng.halo_flags & 32:
+                    import ctypes
+                    eng.lib.rp_conv_halo_prof((ctypes.c_ulonglong * 16)())
 torch.cuda.synchronize(); torch.cuda.profiler.stop()

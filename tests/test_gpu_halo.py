@@ -116,6 +116,15 @@ def test_halo_layer_matches_torch(case, storage):
         assert e_sc <= 1e-3 and e_sh <= 5e-3
 
 
+@pytest.mark.parametrize("case", [CASES[i] for i in (0, 3, 4, 11)], ids=[CASES[i][0] for i in (0, 3, 4, 11)])
+def test_halo_layer_packed_half_batchnorm(case):
+    """flags bit 1 (the engine's default for 16-bit sources): producer BatchNorm + LeakyReLU in packed half arithmetic.  The
+    reference here applies them in float32 and rounds once, so scale / shift rounded to half show up: 2^-10 of the range more."""
+    err, tol, rng, e_sc, e_sh = _run(case, "bf16", flags=2)
+    print("%s/packed-half BN: max err %.3e (tol %.3e, range %.2f)" % (case[0], err, tol + 2.0 ** -10 * rng, rng))
+    assert err <= tol + 2.0 ** -10 * rng and e_sc <= 2e-3
+
+
 def test_halo_layer_pitch16_variant():
     err, tol, rng, e_sc, e_sh = _run(CASES[0], "fp32", flags=1)
     assert err <= tol and e_sc <= 1e-3
