@@ -550,7 +550,7 @@ def run_cuda_arm(args):
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": {
-            "bound": "issue", "kernel": "rp_solve_kernel<0>", "kernel_ms": float(np.mean(kern_ms)),
+            "bound": "issue", "kernel": "rp_solve_kernel<false,false>", "kernel_ms": float(np.mean(kern_ms)),
             "achieved": issue_ach, "peak": issue_peak, "unit": "Gwarp-inst/s", "frac": issue_ach / issue_peak,
             "peak_source": "148 SMs x 4 schedulers x 1 warp-instruction/clk x %.0f MHz (max SM clock, %s)" % (peaks["sm_max_mhz"], peaks["source"]),
             "model": "warp-instructions executed per pair (ncu smsp__inst_executed.sum / pairs, %s) x pairs per launch / CUDA-event "

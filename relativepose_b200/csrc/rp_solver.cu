@@ -1759,7 +1759,11 @@ int default_slots_uncached(size_t smem_bytes);
 // different plans may be in flight on several streams; the attribute only has to cover the largest of them)
 template <bool ROBUST, bool BIG> __global__ void rp_solve_kernel(const SolveArgs A);
 bool ensure_smem_attr(size_t bytes) {
-    static size_t have = 48 * 1024;
+    static size_t have_dev[64];                         // per device: function attributes are per-device state
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) { cudaGetLastError(); dev = 63; have_dev[63] = 0; }
+    size_t& have = have_dev[dev];
+    if (have == 0) have = 48 * 1024;
     if (bytes <= have) return true;
     if (cudaFuncSetAttribute(rp_solve_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess ||
         cudaFuncSetAttribute(rp_solve_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess) {

@@ -2,16 +2,10 @@
 TAG=${1:-r2a}
 mkdir -p gpurun_out
 {
-echo "=== all gpu tests"; timeout 1500 python -m pytest tests -m gpu -q 2>&1 | tail -8
-echo "=== scnet timing"; timeout 600 python scripts/time_scnet.py 1 8 32 2>&1 | tail -3
-echo "=== bench"; timeout 1200 python bench.py --steps 5 --warmup 3 2>&1 | tail -1 > gpurun_out/bench_line_$TAG.json; python - <<PY
-import json
-d = json.load(open('gpurun_out/bench_line_$TAG.json'))
-print({k: d[k] for k in ('value', 'ms_per_step', 'per_pair_p50_ms')}, 'e2e', d['e2e']['value'], 'records', d['e2e_records']['value'])
-print('roofline', {k: d['roofline'][k] for k in ('achieved', 'peak', 'frac')}, d['parity'])
-for k, v in d['extra'].items():
-    print(k, {a: b for a, b in v.items() if a not in ('workload', 'rows', 'ncu', 'peak_source')})
-print(d.get('cpu_baseline'))
-PY
+echo "=== solver tests"; timeout 1200 python -m pytest tests/test_gpu_solver.py tests/test_gpu_fitters.py tests/test_gpu_plan.py tests/test_gpu_properties.py tests/test_gpu_via_completion.py tests/test_gpu_pipeline.py tests/test_gpu_pipeline_batch.py tests/test_gpu_fd_objective.py -m gpu -q -x 2>&1 | tail -6
+echo "=== bench (no extras)"; timeout 600 python bench.py --steps 5 --warmup 3 --no-extra --no-cpu-baseline 2>&1 | tail -1 | python -c "
+import json,sys
+d=json.loads(sys.stdin.read()); print({k:d[k] for k in ('value','ms_per_step','per_pair_p50_ms')}, d['e2e']['value'], d['e2e_records']['value'], d['parity'])"
+echo "=== diag"; timeout 600 python scripts/diag_alternation_solve.py 2>&1 | grep -E "solve|stop after"
 } > gpurun_out/round_$TAG.log 2>&1
-tail -40 gpurun_out/round_$TAG.log
+tail -30 gpurun_out/round_$TAG.log
