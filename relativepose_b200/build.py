@@ -47,7 +47,7 @@ def build_all(force=False, verbose=False):
             obj = os.path.join(objdir, sname[:-3] + ".o")
             objs.append(obj)
             if force or _stale(obj, [src] + headers):
-                cmd = [_nvcc()] + [f for f in NVCC_FLAGS if f != "-shared"] + ["-I", INCLUDE, "-c", "-o", obj, src]
+                cmd = [_nvcc()] + [f for f in NVCC_FLAGS if f != "-shared"] + os.environ.get("RP_NVCC_EXTRA", "").split() + ["-I", INCLUDE, "-c", "-o", obj, src]
                 if verbose:
                     cmd[1:1] = ["-Xptxas", "-v"]
                 jobs.append((sname, cmd))

@@ -1,0 +1,115 @@
+"""Host-side logic added in round 2 (no GPU needed): util.apply_mask against the reference's own, the reference install used
+by bench.py's CPU arm, the rendered room scenes, the solver's status policy and workspace sizing rules."""
+import os
+import sys
+import types
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _reference_util():
+    from oracle import ref_loader
+    if not ref_loader.reference_available():
+        pytest.skip("reference tree not present")
+    import torch
+    ref = ref_loader.load_reference_rpmodule()
+    keep = lambda var, cuda=True, volatile=False: (torch.from_numpy(var).float() if isinstance(var, np.ndarray) else var.float())  # noqa: E731
+    ref.util.torch_op.v = keep
+    return ref.util
+
+
+@pytest.mark.parametrize("method", ["second", "kinect", "something-else"])
+def test_apply_mask_matches_reference(method):
+    """util.apply_mask (util.py:209-232): same 3-tuple (masked x, mask, geow) as the reference, for both shipped mask
+    methods and for an unknown one (mask and geow stay zero)."""
+    import torch
+    from relativepose_b200.util import apply_mask
+    util = _reference_util()
+    x = torch.rand(2, 8, 160, 640)
+    xr, mr, gr = util.apply_mask(x.clone(), method)
+    xm, mm, gm = apply_mask(x.clone(), method, "extra-positional-arguments-are-accepted")
+    assert torch.equal(xm, xr.float()) and torch.equal(mm, mr.float())
+    gr = torch.as_tensor(np.asarray(gr), dtype=torch.float32) if not torch.is_tensor(gr) else gr.float()
+    assert gm.shape == gr.shape and torch.allclose(gm, gr, atol=1e-7)
+
+
+def test_reference_install_is_the_unmodified_tree():
+    """oracle/install_reference.py: the files under baseline/_ref are byte-identical to /root/reference (when both exist)."""
+    src, dst = "/root/reference", os.path.join(ROOT, "baseline", "_ref")
+    if not os.path.isdir(src):
+        pytest.skip("reference tree not present")
+    sys.path.insert(0, ROOT)
+    from oracle import install_reference
+    assert install_reference.install() in ("present", "installed")
+    for rel in ("RPModule/rpmodule.py", "RPModule/rputil.py", "util.py", "config.py", "utils/torch_op.py", "model/mymodel.py"):
+        assert open(os.path.join(src, rel), "rb").read() == open(os.path.join(dst, rel), "rb").read(), rel
+
+
+def test_room_scan_pair_is_geometrically_consistent():
+    """synth.make_room_scan_pair: the two skybox scans see the same walls -- source points moved by R_gt land on the target's
+    point cloud (oracle Pano2PointCloud, util.py:751-773) within the pixel spacing."""
+    from scipy.spatial import cKDTree
+    from oracle import warp_oracle
+    from relativepose_b200 import synth
+    s, t, R = synth.make_room_scan_pair(4, tex_res=12)
+    assert s['rgb'].shape == (160, 640, 3) and s['depth'].min() > 0.5
+    assert np.allclose(np.linalg.norm(s['norm'], axis=2), 1.0, atol=1e-12)
+    assert np.allclose(R[:3, :3] @ R[:3, :3].T, np.eye(3), atol=1e-12)
+    ps = warp_oracle.pano2pointcloud(s['depth'], 'suncg')
+    pt = warp_oracle.pano2pointcloud(t['depth'], 'suncg')
+    moved = (R[:3, :3] @ ps + R[:3, 3:4]).T[::97]
+    d, _ = cKDTree(pt.T).query(moved)
+    assert np.median(d) < 0.03           # pixel spacing at 3 m is ~4 cm
+
+
+def test_status_policy():
+    """PoseSolver.check_status: overflow of the bounded candidate list -> one redo at full capacity; unsupported -> raise."""
+    from relativepose_b200 import _lib
+    from relativepose_b200.solver import PoseSolver
+    chk = PoseSolver.check_status
+    calls = []
+
+    def redo_ok():
+        calls.append(1)
+        return np.zeros(3, np.int32)
+    assert chk(None, np.array([0, 1, 5], np.int32), redo_ok) is False and not calls
+    assert chk(None, np.array([0, _lib.STATUS_EDGE_OVERFLOW, 0], np.int32), redo_ok) is True and len(calls) == 1
+    with pytest.raises(RuntimeError):
+        chk(None, np.array([_lib.STATUS_UNSUPPORTED], np.int32), redo_ok)
+    with pytest.raises(RuntimeError):
+        chk(None, np.array([_lib.STATUS_EDGE_OVERFLOW], np.int32), lambda: np.array([_lib.STATUS_EDGE_OVERFLOW], np.int32))
+
+
+def test_bounded_edge_capacity_rule():
+    from relativepose_b200.solver import PoseSolver
+    s = types.SimpleNamespace(edge_frac=None, AUTO_EDGE_FRAC=PoseSolver.AUTO_EDGE_FRAC, AUTO_EDGE_FLOOR=PoseSolver.AUTO_EDGE_FLOOR)
+    cap = lambda n_s: PoseSolver._edge_cap(s, n_s, 5)                                       # noqa: E731
+    assert cap(20) == 0                                   # tiny pair: the worst case is below the floor -> full capacity
+    P515 = 515 * 514 // 2
+    assert cap(103) == 65536 < P515                       # N = 515: the 64 Ki floor
+    N = 625 * 5
+    assert cap(625) == int(N * (N - 1) // 2 * 0.25)       # N = 3125: a quarter of the worst case
+    s.edge_frac = 1.0
+    assert cap(103) == 0
+
+
+def test_packed_batch_layouts_and_sum_order():
+    """PackedBatch: concatenation is exact for C-ordered, F-ordered and list inputs; the per-pair float32 summation-order
+    flag follows the memory layout of the descriptor arrays (rpmodule.py:531-532 hands over transposed views)."""
+    from relativepose_b200 import synth
+    from relativepose_b200.solver import PackedBatch
+    recs = [synth.make_pair(i, 10 + i, 12 + i) for i in range(300)]          # >= 256: the threaded fill path
+    r1 = dict(recs[1])
+    r1['feat_src'] = np.asfortranarray(r1['feat_src'])
+    r1['weight_tgt'] = list(r1['weight_tgt'])
+    recs[1] = r1
+    pk = PackedBatch(recs, pin=False)
+    assert pk.B == 300 and pk.sum_order_t.tolist()[:3] == [0, 1, 0]
+    for b in (0, 1, 150, 299):
+        lo, hi = int(pk.off_s[b]), int(pk.off_s[b + 1])
+        assert np.array_equal(pk.pc_s.numpy()[lo:hi], recs[b]['pc_src']) and np.array_equal(pk.feat_s.numpy()[lo:hi], recs[b]['feat_src'])
+        lo, hi = int(pk.off_t[b]), int(pk.off_t[b + 1])
+        assert np.array_equal(pk.w_t.numpy()[lo:hi], np.asarray(recs[b]['weight_tgt'])) and np.array_equal(pk.nrm_t.numpy()[lo:hi], recs[b]['normal_tgt'])
