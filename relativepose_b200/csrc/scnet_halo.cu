@@ -41,7 +41,8 @@ constexpr int EPI_SMEM = (4 * 32 * 33 + 16 * 4 * 64) * 4;            // per-warp
 
 // Profiling only (flags bit 5): cycles per role, summed over CTAs -- [0] loader total, [1] loader wait a_empty, [2] loader copy wait,
 // [3] loader transform, [4] mma total, [5] mma wait acc_empty, [6] mma wait a_full, [7] mma wait w_full, [8] epilogue total,
-// [9] epilogue wait acc_full, [10] epilogue tmem_ld, [11] epilogue stats barriers, [12] loader table build
+// [9] epilogue wait acc_full, [10] epilogue tmem_ld, [11] epilogue stats barriers, [12] loader table build,
+// [13] loader copy issue, [14] loader fence + arrive
 __device__ unsigned long long g_halo_prof[16];
 #define HP_T0(var) long long var = 0; if (PROF) var = clock64();
 #define HP_ADD(idx, var) if (PROF) { prof_acc[idx] += clock64() - var; }
@@ -134,7 +135,7 @@ __global__ void __launch_bounds__(CTA, 1) conv_halo_tc(const HaloArgs A, const u
     __shared__ __align__(16) float s_bias[256];                  // bias of the 1x1 heads (Cout <= 256), zero padded to whole n-tiles
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const bool PROF = (A.dbg & 8) != 0;
-    long long prof_acc[13] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    long long prof_acc[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     const long long prof_start = clock64();
     const int a_bytes = ((KC * A.a_lbo + 127) / 128) * 128;
     unsigned char* sEpi = smem;                                  // [EPI_SMEM] epilogue scratch (never aliased)
@@ -243,10 +244,12 @@ __global__ void __launch_bounds__(CTA, 1) conv_halo_tc(const HaloArgs A, const u
                     // bound by memory-level parallelism.  Padding pixels are zero-filled by the copy itself.  Each thread then
                     // normalises, in place, exactly the units it copied (no cross-thread hand-off); a source without a
                     // producer BatchNorm (the split stem input) needs no second pass at all.
+                    HP_T0(i0)
                     for (int h = h0; h < A.NPX; h += HSTEP) {
                         const int pix = my_pix[h];
                         cp_async16(dst + (size_t)h * 16, base + (size_t)(pix < 0 ? 0 : pix) * pstride, pix < 0 ? 0u : 16u);
                     }
+                    HP_ADD(13, i0)
                     HP_T0(c0)
                     cp_async_wait_all();
                     HP_ADD(2, c0)
@@ -319,8 +322,10 @@ __global__ void __launch_bounds__(CTA, 1) conv_halo_tc(const HaloArgs A, const u
                     }
                 }
                 if (in_bf16 && !(A.dbg & 2)) { HP_ADD(3, x0) }
+                HP_T0(f0)
                 fence_async_smem();                // generic-proxy writes -> visible to the tensor core (async proxy)
                 mbar_arrive(&a_full[b]);
+                HP_ADD(14, f0)
             }
         }
     } else if (warp == 12) {
@@ -550,7 +555,7 @@ __global__ void __launch_bounds__(CTA, 1) conv_halo_tc(const HaloArgs A, const u
     }
     if (PROF && lane == 0) {
         const long long tot = clock64() - prof_start;
-        if (warp == 4) { atomicAdd(&g_halo_prof[0], (unsigned long long)tot); for (int i = 1; i <= 3; ++i) atomicAdd(&g_halo_prof[i], (unsigned long long)prof_acc[i]); atomicAdd(&g_halo_prof[12], (unsigned long long)prof_acc[12]); }
+        if (warp == 4) { atomicAdd(&g_halo_prof[0], (unsigned long long)tot); for (int i = 1; i <= 3; ++i) atomicAdd(&g_halo_prof[i], (unsigned long long)prof_acc[i]); atomicAdd(&g_halo_prof[12], (unsigned long long)prof_acc[12]); atomicAdd(&g_halo_prof[13], (unsigned long long)prof_acc[13]); atomicAdd(&g_halo_prof[14], (unsigned long long)prof_acc[14]); }
         if (warp == 13) { atomicAdd(&g_halo_prof[4], (unsigned long long)tot); for (int i = 5; i <= 7; ++i) atomicAdd(&g_halo_prof[i], (unsigned long long)prof_acc[i]); }
         if (warp == 0) { atomicAdd(&g_halo_prof[8], (unsigned long long)tot); for (int i = 9; i <= 11; ++i) atomicAdd(&g_halo_prof[i], (unsigned long long)prof_acc[i]); }
     }

@@ -57,9 +57,9 @@ for it in range(1 + reps):
                     eng.lib.rp_conv_halo_prof(buf)
                     v = [float(x) for x in buf]
                     pc = lambda a, b: 100.0 * a / max(b, 1.0)
-                    print("   loader: wait a_empty %.0f%%, copy wait %.0f%%, transform %.0f%%, table %.0f%% | mma: wait acc_empty %.0f%%, a_full %.0f%%, w_full %.0f%% | "
+                    print("   loader: wait a_empty %.0f%%, copy issue %.0f%%, copy wait %.0f%%, transform %.0f%%, table %.0f%%, fence+arrive %.0f%% | mma: wait acc_empty %.0f%%, a_full %.0f%%, w_full %.0f%% | "
                           "epilogue: wait acc_full %.0f%%, tmem_ld %.0f%%, stats barriers+psum %.0f%%" % (
-                              pc(v[1], v[0]), pc(v[2], v[0]), pc(v[3], v[0]), pc(v[12], v[0]), pc(v[5], v[4]), pc(v[6], v[4]), pc(v[7], v[4]),
+                              pc(v[1], v[0]), pc(v[13], v[0]), pc(v[2], v[0]), pc(v[3], v[0]), pc(v[12], v[0]), pc(v[14], v[0]), pc(v[5], v[4]), pc(v[6], v[4]), pc(v[7], v[4]),
                               pc(v[9], v[8]), pc(v[10], v[8]), pc(v[11], v[8])))
                 elif eng.halo_flags & 32:
                     import ctypes
