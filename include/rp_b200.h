@@ -369,6 +369,10 @@ int rp_conv_layer_tc(const rp_conv_desc* d, const void* w_packed, int bn, int tk
  * K chunk and their order (tap_widx[i] = ky*k+kx, room for 16); w_packed is bf16
  * [n-tile][K chunk][block][tk/8][bn/8][8 co][8 ci] (relativepose_b200/scnet_engine.py:pack_halo). */
 int rp_conv_halo_plan(const rp_conv_desc* d, int bn, int tk, int flags, int* nparts, int* ntap, int* tap_widx);
+/* Launches of the halo kernel so far whose input halo was fetched by tiled TMA (16-bit sources; float32 sources use cp.async /
+ * thread gathers). */
+long long rp_conv_halo_tma_count(void);
+
 /* Profiling aid: per-role cycle counters of the halo kernel (enabled by flags bit 5 of rp_conv_layer_halo), read and cleared. */
 int rp_conv_halo_prof(unsigned long long* out16);
 

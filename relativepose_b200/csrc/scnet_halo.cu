@@ -20,8 +20,10 @@
 // meanwhile (tcgen05.ld, bias/tanh, raw output fp32 or bf16 NHWC, deterministic per-tile partial batch statistics).
 // mbarriers only; no __syncthreads in the steady state.
 #include "rp_h16.cuh"
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <string.h>
 
 #include "../../include/rp_b200.h"
 #include "scnet_common.cuh"
@@ -67,6 +69,9 @@ struct HaloArgs {
     int ng;                                // loader groups = halo buffers (2 or 4): group i fills buffer i with chunks i, i+ng, ...
     float inv_nkt;
     int w_resident;                        // all weight blocks of a tile fit in the ring: loaded once per CTA, never freed
+    float inv_ppl;                         // 1 / (PH * PW)
+    int use_tma;                           // 16-bit sources: the raw halo arrives by tiled TMA (one 5-D box per parity plane and K chunk)
+    int plane_bytes, a_bytes;              // TMA layout: [plane][K core][row][pixel] 16-byte units, planes 128-byte aligned; bytes of one buffer
     int dbg;                               // profiling only (flags >> 2): 1 no epilogue stores/stats, 2 no loader copy/transform, 4 no MMA
     int h2math;                            // producer BatchNorm + LeakyReLU of 16-bit sources in packed half arithmetic (flags bit 1)
     void* out; int out_pitch, out_ch_off, out_bf16;
@@ -123,11 +128,13 @@ __device__ __forceinline__ uint64_t pack_desc(uint32_t lo, uint32_t hi) { return
 //   epilogue (128 thr)  accumulator set tile % nacc -> global + statistics          acc_full -> acc_empty
 // so the gathers of the next tiles, the MMAs of tile i and the epilogue of earlier tiles overlap.
 template <int BN, int TK, int NB>
-__global__ void __launch_bounds__(CTA, 1) conv_halo_tc(const HaloArgs A, const unsigned char* __restrict__ Wp) {
+__global__ void __launch_bounds__(CTA, 1) conv_halo_tc(const HaloArgs A, const unsigned char* __restrict__ Wp,
+                                                        const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CUtensorMap tm1) {
     extern __shared__ __align__(128) unsigned char smem[];
     constexpr int KC = TK / 8;
     constexpr int B_BYTES = BN * TK * 2;
     constexpr int U = 4;                           // loads in flight per loader thread
+    __shared__ __align__(8) uint64_t raw_full[MAXNG];            // TMA path: the raw halo of a chunk has landed (byte count)
     __shared__ __align__(8) uint64_t a_full[MAXNG], a_empty[MAXNG], w_full[NB], w_empty[NB], acc_full[MAXACC], acc_empty[MAXACC];
     __shared__ uint32_t tmem_slot;
     __shared__ int s_pix[PIXTAB];                  // one pixel table per loader group (ng x NPX <= PIXTAB)
@@ -137,14 +144,15 @@ __global__ void __launch_bounds__(CTA, 1) conv_halo_tc(const HaloArgs A, const u
     const bool PROF = (A.dbg & 8) != 0;
     long long prof_acc[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     const long long prof_start = clock64();
-    const int a_bytes = ((KC * A.a_lbo + 127) / 128) * 128;
+    const int a_bytes = A.a_bytes;
     unsigned char* sEpi = smem;                                  // [EPI_SMEM] epilogue scratch (never aliased)
     unsigned char* sA = smem + EPI_SMEM;                         // ng halo buffers
     unsigned char* sB = sA + A.ng * a_bytes;                     // NB weight slots
 
     if (tid == 0) {
 #pragma unroll
-        for (int i = 0; i < MAXNG; ++i) { mbar_init(&a_full[i], (uint32_t)(LOADERS / A.ng)); mbar_init(&a_empty[i], 1); }
+        for (int i = 0; i < MAXNG; ++i) { mbar_init(&a_full[i], (uint32_t)(LOADERS / A.ng)); mbar_init(&a_empty[i], 1); mbar_init(&raw_full[i], 1); }
+        if (A.use_tma) { tma_prefetch_desc(&tm0); if (A.nsrc > 1) tma_prefetch_desc(&tm1); }
 #pragma unroll
         for (int i = 0; i < NB; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
 #pragma unroll
@@ -176,6 +184,103 @@ __global__ void __launch_bounds__(CTA, 1) conv_halo_tc(const HaloArgs A, const u
         int* my_pix = s_pix + gi * A.NPX;
         const int my_tiles = (A.total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
         const int total_chunks = my_tiles * A.nkt;
+        if (A.use_tma) {
+            // ---- tiled TMA: lane 0 of the group issues one 5-D box per parity plane (8 channels x PW pixels x PH rows x KC cores,
+            // element strides = the convolution stride, zero fill outside the image); the group's threads then normalise the
+            // landed data in place (nothing to do for a source without a producer BatchNorm) and hand the buffer to the MMA warp
+            const int ppl = A.PH * A.PW;
+            int cur_seq = -1;
+            TileCoord tc_ = decode_tile(A, blockIdx.x);
+            bool interior = true;
+            for (int cc = gi; cc < total_chunks; cc += A.ng) {
+                const int tseq = fdiv(cc, A.nkt, A.inv_nkt);
+                const int c = cc - tseq * A.nkt;
+                if (tseq != cur_seq) {
+                    cur_seq = tseq;
+                    tc_ = decode_tile(A, (int)blockIdx.x + tseq * (int)gridDim.x);
+                    interior = true;
+                    for (int p = 0; p < A.nplane; ++p) {
+                        const int y0 = (tc_.a0 + A.plane[p].oy) * A.istr + A.plane[p].qy, x0 = (tc_.b0 + A.plane[p].ox) * A.istr + A.plane[p].qx;
+                        interior = interior && y0 >= 0 && x0 >= 0 && y0 + (A.PH - 1) * A.istr < A.Hin && x0 + (A.PW - 1) * A.istr < A.Win;
+                    }
+                }
+                const int g = tc_.g;
+                const int b = gi;
+                const uint32_t use = (uint32_t)(cc / A.ng);
+                const int si = c < A.nkt0 ? 0 : 1;
+                const rp_conv_src& S = A.src[si];
+                const int ch = (c - (si ? A.nkt0 : 0)) * TK;
+                const bool act = S.act != 0;
+                rp_h162 sc2[4], sh2[4];
+                if (act) {                                   // issued before the waits below: their latency is hidden
+                    const int kc_ = lt / (GT / KC);
+                    const float4* ps = reinterpret_cast<const float4*>(S.scale + (size_t)g * S.sstride + S.s_off + ch + kc_ * 8);
+                    const float4* ph = reinterpret_cast<const float4*>(S.shift + (size_t)g * S.sstride + S.s_off + ch + kc_ * 8);
+                    const float4 s0 = __ldg(ps), s1 = __ldg(ps + 1), q0 = __ldg(ph), q1 = __ldg(ph + 1);
+                    sc2[0] = rp_f2_to_h2(s0.x, s0.y); sc2[1] = rp_f2_to_h2(s0.z, s0.w); sc2[2] = rp_f2_to_h2(s1.x, s1.y); sc2[3] = rp_f2_to_h2(s1.z, s1.w);
+                    sh2[0] = rp_f2_to_h2(q0.x, q0.y); sh2[1] = rp_f2_to_h2(q0.z, q0.w); sh2[2] = rp_f2_to_h2(q1.x, q1.y); sh2[3] = rp_f2_to_h2(q1.z, q1.w);
+                }
+                HP_T0(w0)
+                mbar_wait_backoff(&a_empty[b], (use & 1u) ^ 1u);
+                HP_ADD(1, w0)
+                unsigned char* buf = sA + b * a_bytes;
+                HP_T0(i0)
+                if (lt == 0) {
+                    mbar_expect_tx(&raw_full[b], (uint32_t)(A.nplane * KC * ppl * 16));
+                    for (int p = 0; p < A.nplane; ++p) {
+                        const int y0 = (tc_.a0 + A.plane[p].oy) * A.istr + A.plane[p].qy, x0 = (tc_.b0 + A.plane[p].ox) * A.istr + A.plane[p].qx;
+                        tma_load_5d(buf + p * A.plane_bytes, si ? (const void*)&tm1 : (const void*)&tm0, 0, x0, y0, ch >> 3, tc_.img, &raw_full[b]);
+                    }
+                }
+                HP_ADD(13, i0)
+                HP_T0(c0)
+                mbar_wait(&raw_full[b], use & 1u);
+                HP_ADD(2, c0)
+                HP_T0(x0t)
+                if (act && !(A.dbg & 2)) {
+                    // thread -> one K core kc (scale / shift of its 8 channels stay in registers) and the plane pixels
+                    // h = j, j + TPK, ... (TPK = GT / KC threads per core).  The TMA box is dense, so the K cores cannot be skewed
+                    // against the banks the way the gather layout is: with only four threads per core the two cores that share
+                    // a quarter-warp take alternating halves of every 8-pixel run instead, which keeps LDS.128 / STS.128 conflict-free
+                    const int TPK = GT / KC, kc = lt / TPK, j = lt - kc * TPK;
+                    const rp_h162 sl2 = rp_f2_to_h2(S.slope, S.slope);
+                    for (int p = 0; p < A.nplane; ++p) {
+                        unsigned char* base = buf + p * A.plane_bytes + (size_t)kc * ppl * 16;
+                        const int py0 = (tc_.a0 + A.plane[p].oy) * A.istr + A.plane[p].qy, px0 = (tc_.b0 + A.plane[p].ox) * A.istr + A.plane[p].qx;
+                        const int nit = TPK >= 8 ? (ppl - j + TPK - 1) / TPK : 2 * ((ppl + 7) / 8);
+                        for (int ib = 0; ib < nit; ib += 4) {
+                            uint4 x[4]; bool live[4]; int hs[4];
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) {
+                                const int i = ib + u;
+                                const int h = TPK >= 8 ? j + TPK * i : j + 4 * ((kc + i) & 1) + 8 * (i >> 1);
+                                live[u] = i < nit && h < ppl;
+                                hs[u] = live[u] ? h : 0;
+                                if (live[u] && !interior) {          // zero padding stays zero (the BatchNorm shift must not leak in)
+                                    const int l = s_lut[h];
+                                    const int iy = py0 + ((l >> 10) & 1023) * A.istr, ix = px0 + (l & 1023) * A.istr;
+                                    live[u] = iy >= 0 && iy < A.Hin && ix >= 0 && ix < A.Win;
+                                }
+                                x[u] = *reinterpret_cast<const uint4*>(base + (size_t)hs[u] * 16);
+                            }
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) {
+                                rp_h162* hp = reinterpret_cast<rp_h162*>(&x[u]);
+#pragma unroll
+                                for (int q = 0; q < 4; ++q) { const rp_h162 z = __hfma2(hp[q], sc2[q], sh2[q]); hp[q] = __hmax2(z, __hmul2(z, sl2)); }
+                            }
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) {
+                                if (live[u]) *reinterpret_cast<uint4*>(base + (size_t)hs[u] * 16) = x[u];
+                            }
+                        }
+                    }
+                    fence_async_smem();            // generic-proxy writes -> visible to the tensor core (async proxy)
+                }
+                HP_ADD(3, x0t)
+                mbar_arrive(&a_full[b]);
+            }
+        } else {
         int cur_seq = -1;
         TileCoord tc_ = decode_tile(A, blockIdx.x);
         for (int cc = gi; cc < total_chunks; cc += A.ng) {
@@ -327,6 +432,7 @@ __global__ void __launch_bounds__(CTA, 1) conv_halo_tc(const HaloArgs A, const u
                 mbar_arrive(&a_full[b]);
                 HP_ADD(14, f0)
             }
+        }
         }
     } else if (warp == 12) {
         // ------------------------------------------------------------------ weight stream (bulk TMA)
@@ -658,11 +764,73 @@ static bool build_halo_args(const rp_conv_desc* d, HaloArgs* H, int bn, int tk, 
     return true;
 }
 
+static long long g_tma_launches = 0;    // launches whose halo arrived by tiled TMA (rp_conv_halo_tma_count)
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link against libcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+        else cudaGetLastError();
+    }
+    return fn;
+}
+
+// Tensor map of one 16-bit NHWC source seen as [8 channels][x][y][K core][image]: a box of 8 x PW x PH x KC x 1 elements lands in
+// shared memory as [K core][row][pixel] 16-byte units -- the canonical K-major UMMA layout of the halo -- and element strides
+// (istr, istr) in x / y pick one parity plane of a stride-2 convolution.  Out-of-image coordinates are zero filled.
+static bool make_src_tmap(const rp_conv_src& S, const HaloArgs& H, int KC, CUtensorMap* tm) {
+    EncodeTiledFn enc = encode_tiled_fn();
+    if (!enc) return false;
+    const cuuint64_t pitchB = (cuuint64_t)S.pitch * 2;
+    cuuint64_t gdim[5] = {8, (cuuint64_t)H.Win, (cuuint64_t)H.Hin, (cuuint64_t)(S.C / 8), (cuuint64_t)H.G * (cuuint64_t)H.gsz};
+    cuuint64_t gstr[4] = {pitchB, (cuuint64_t)H.Win * pitchB, 16, (cuuint64_t)H.Hin * (cuuint64_t)H.Win * pitchB};
+    cuuint32_t box[5] = {8, (cuuint32_t)(H.PW * H.istr), (cuuint32_t)(H.PH * H.istr), (cuuint32_t)KC, 1};
+    cuuint32_t estr[5] = {1, (cuuint32_t)H.istr, (cuuint32_t)H.istr, 1, 1};
+    void* base = const_cast<unsigned char*>(reinterpret_cast<const unsigned char*>(S.ptr)) + (size_t)S.ch_off * 2;
+    if (box[1] > 256 || box[2] > 256 || (reinterpret_cast<uintptr_t>(base) & 15) || (pitchB & 15)) return false;
+    return enc(tm, RP_H16_FP16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, base, gdim, gstr, box, estr,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 template <int BN, int TK, int NB>
 static int launch_halo(const HaloArgs& H0, const void* wp, int h2math, cudaStream_t stream) {
     constexpr int KC = TK / 8;
     HaloArgs H = H0;
-    const size_t a_bytes = (size_t)((KC * H.a_lbo + 127) / 128) * 128;
+    // 16-bit sources can take the tiled-TMA loader: halo layout [plane][K core][row][pixel] with 128-byte aligned planes.  In the
+    // K-major / no-swizzle UMMA layout a TMA element is one 16-byte (pixel, K core) granule, and measured on B200 (32 scan pairs,
+    // profiles/r2_scnet_halo_ncu_summary.txt) that only pays for the single-tap layers (1x1 heads: -8 %); 3x3 / transposed layers
+    // are even and the stride-2 convolutions, whose parity planes need element strides of 2, lose 6-20 % against the per-thread
+    // cp.async gather.  Default: TMA for single-tap layers; flags bit 7 forces it everywhere, bit 6 disables it (float32
+    // sources always use the gather and its [K core][plane,row,pixel] layout).
+    CUtensorMap tm[2];
+    memset(tm, 0, sizeof(tm));
+    H.use_tma = ((h2math >> 5) & 1) ? 0 : (((h2math >> 6) & 1) || H.ntap == 1) ? 1 : 0;
+    for (int i = 0; i < H.nsrc; ++i) if (H.src[i].dtype != 1) H.use_tma = 0;
+    if (H.use_tma) {
+        const int ppl = H.PH * H.PW;
+        for (int i = 0; i < H.nsrc && H.use_tma; ++i) if (!make_src_tmap(H.src[i], H, KC, &tm[i])) H.use_tma = 0;
+        if (H.use_tma) {
+            H.plane_bytes = ((KC * ppl * 16 + 127) / 128) * 128;
+            for (int t = 0; t < H.ntap; ++t) {
+                const int u = H.tap[t].a_off / 16, p = u / ppl, rem = u - p * ppl;
+                H.tap[t].a_off = p * H.plane_bytes + rem * 16;
+            }
+            H.a_lbo = ppl * 16;
+            H.a_bytes = H.nplane * H.plane_bytes;
+            H.inv_ppl = 1.f / (float)ppl;
+        }
+    }
+    if (!H.use_tma) { H.plane_bytes = 0; H.a_bytes = ((KC * H.a_lbo + 127) / 128) * 128; }
+    const size_t a_bytes = (size_t)H.a_bytes;
     const size_t fixed = (size_t)EPI_SMEM + (size_t)NB * BN * TK * 2;
     auto kern = conv_halo_tc<BN, TK, NB>;
     static size_t limit = 0;                                    // dynamic bytes a CTA of this instantiation may take
@@ -686,7 +854,8 @@ static int launch_halo(const HaloArgs& H0, const void* wp, int h2math, cudaStrea
         if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n_sm < 1) { cudaGetLastError(); n_sm = 148; }
     }
     const int grid = H.total_tiles < n_sm ? H.total_tiles : n_sm;       // persistent: one CTA per SM
-    kern<<<grid, CTA, smem, stream>>>(H, static_cast<const unsigned char*>(wp));
+    kern<<<grid, CTA, smem, stream>>>(H, static_cast<const unsigned char*>(wp), tm[0], tm[1]);
+    if (H.use_tma) ++g_tma_launches;
     ++scnet::g_conv_launches;
     return cudaGetLastError() == cudaSuccess ? RP_OK : RP_ERR_CUDA;
 }
@@ -720,6 +889,9 @@ int rp_conv_halo_debug(const rp_conv_desc* d, int bn, int tk, int flags, int* ou
     for (int c = 0; c < 4; ++c) { *o++ = H.cls_py[c]; *o++ = H.cls_px[c]; *o++ = H.cls_Ha[c]; *o++ = H.cls_Wb[c]; }
     return RP_OK;
 }
+
+// Number of halo-kernel launches so far whose input halo was fetched by tiled TMA (cp.async.bulk.tensor).
+long long rp_conv_halo_tma_count(void) { return halo::g_tma_launches; }
 
 // Profiling only: read and clear the per-role cycle counters (see g_halo_prof); flags bit 5 enables them.
 int rp_conv_halo_prof(unsigned long long* out16) {

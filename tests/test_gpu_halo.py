@@ -125,6 +125,23 @@ def test_halo_layer_packed_half_batchnorm(case):
     assert err <= tol + 2.0 ** -10 * rng and e_sc <= 2e-3
 
 
+def test_halo_16bit_sources_arrive_by_tiled_tma():
+    """16-bit sources can take the tiled-TMA loader (cp.async.bulk.tensor, one 5-D box per parity plane and K chunk; default
+    for the single-tap layers, forced by flags bit 7); flags bit 6 selects the per-thread cp.async gather.  Both must give the
+    same bits (same operands, same MMA order) -- stride-1, stride-2 (four parity planes) and transposed layers."""
+    import torch
+    from relativepose_b200 import _lib
+    lib = _lib.load()
+    n0 = lib.rp_conv_halo_tma_count()
+    for case in (CASES[0], CASES[3], CASES[4]):
+        a = _run(case, "bf16", flags=2 | 128)
+        assert lib.rp_conv_halo_tma_count() > n0, "tensor-map encode failed: the layer fell back to the cp.async gather"
+        n0 = lib.rp_conv_halo_tma_count()
+        b = _run(case, "bf16", flags=2 | 64)
+        assert lib.rp_conv_halo_tma_count() == n0
+        assert a[0] == b[0], (case[0], a[0], b[0])       # identical max error against torch = identical output
+
+
 def test_halo_layer_pitch16_variant():
     err, tol, rng, e_sc, e_sh = _run(CASES[0], "fp32", flags=1)
     assert err <= tol and e_sc <= 1e-3
