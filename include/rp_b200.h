@@ -341,7 +341,7 @@ int rp_gather_primitives(const float* feat, int C, long long feat_img_stride, co
  * entry points above (`kind`) with its rp_conv_desc and/or up to 16 scalar arguments in call order (pointers and integers as
  * 64-bit words).  rp_scnet_forward (model/mymodel.py:259-380) / rp_resnet18_8s_forward (:82-122) issue every launch on
  * `stream`; the buffers the ops point to must stay allocated (relativepose_b200/scnet_engine.py keeps them per shape). */
-enum { RP_OP_CONV = 1, RP_OP_CONV_TC, RP_OP_CONV_HALO, RP_OP_BN_FINALIZE, RP_OP_BN_FINALIZE_SPLIT, RP_OP_RESIZE_IN,
+enum { RP_OP_CONV = 1, RP_OP_CONV_TC_REMOVED /* 2: per-tap tcgen05 kernel, removed */, RP_OP_CONV_HALO, RP_OP_BN_FINALIZE, RP_OP_BN_FINALIZE_SPLIT, RP_OP_RESIZE_IN,
        RP_OP_RESIZE_IN_SPLIT, RP_OP_RESIZE_OUT_MAP, RP_OP_IM2COL, RP_OP_BN_RELU_MAXPOOL, RP_OP_BN_ADD_RELU, RP_OP_RESIZE_NHWC,
        RP_OP_RESIZE_TO_NCHW };
 typedef struct rp_net_op {
@@ -355,11 +355,6 @@ int rp_resnet18_8s_forward(const rp_net_op* ops, int n_ops, void* stream);
 
 int64_t rp_launch_count(void);
 int64_t rp_conv_launch_count(void);
-
-/* rp_conv_layer on the 5th-gen tensor cores (tcgen05.mma, bf16 operands, fp32 accumulators in TMEM).  `w_packed` is the
- * layer's weight tensor as bf16 blocks in the UMMA shared-memory image; see csrc/scnet_tc.cu. */
-int rp_conv_nparts_tc(const rp_conv_desc* d, int* nparts);
-int rp_conv_layer_tc(const rp_conv_desc* d, const void* w_packed, int bn, int tk, void* stream);
 
 /* Halo-tile variant (csrc/scnet_halo.cu): a CTA stages the input halo of a 16x8 block of output positions once per
  * K chunk and every (sub-pixel class, tap) MMA reads it through a shifted shared-memory descriptor, so a 4x4 kernel no

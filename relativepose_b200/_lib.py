@@ -61,14 +61,14 @@ class RpNetOp(ctypes.Structure):
 
 
 # op kinds of rp_scnet_forward / rp_resnet18_8s_forward (include/rp_b200.h: RP_OP_*), keyed by the layer entry point
-NET_OPS = {"rp_conv_layer": 1, "rp_conv_layer_tc": 2, "rp_conv_layer_halo": 3, "rp_bn_finalize": 4, "rp_bn_finalize_split": 5,
+NET_OPS = {"rp_conv_layer": 1, "rp_conv_layer_halo": 3, "rp_bn_finalize": 4, "rp_bn_finalize_split": 5,
            "rp_scnet_resize_in": 6, "rp_scnet_resize_in_split": 7, "rp_scnet_resize_out_map": 8, "rp_im2col_bf16": 9,
            "rp_bn_relu_maxpool": 10, "rp_bn_add_relu": 11, "rp_resize_nhwc": 12, "rp_resize_to_nchw": 13}
 
 EXPORTS = ("rp_abi_version", "rp_device_info", "rp_solve_workspace_bytes", "rp_solve_batch",
            "rp_solve_batch_ex", "rp_solve_default_slots", "rp_h16_format", "rp_match_topk", "rp_launch_count", "rp_spectral_irls_solve", "rp_spectral_irls_workspace_bytes",
            "rp_conv_nparts", "rp_conv_layer", "rp_bn_finalize", "rp_bn_finalize_split", "rp_im2col_bf16", "rp_scnet_resize_in", "rp_scnet_resize_in_split", "rp_scnet_resize_out", "rp_scnet_resize_out_map",
-           "rp_conv_launch_count", "rp_tc_gemm_test", "rp_conv_nparts_tc", "rp_conv_layer_tc",
+           "rp_conv_launch_count", "rp_tc_gemm_test",
            "rp_conv_halo_plan", "rp_conv_layer_halo", "rp_conv_halo_debug", "rp_conv_halo_prof", "rp_conv_halo_tma_count",
            "rp_affinity_build", "rp_scnet_forward", "rp_resnet18_8s_forward", "rp_gather_primitives", "rp_match_sample_workspace_bytes", "rp_match_sample", "rp_heat_sample", "rp_warp_workspace_bytes", "rp_warp_views", "rp_warp_views_ex", "rp_pano2pc", "rp_blend_completion",
            "rp_bn_relu_maxpool", "rp_bn_add_relu", "rp_resize_nhwc", "rp_resize_to_nchw", "rp_interpolate")
@@ -138,10 +138,6 @@ def load():
     lib.rp_scnet_resize_out_map.restype = i32
     lib.rp_scnet_resize_out_map.argtypes = [vp, i32, i32, vp, i32, i32, i32, vp, vp]
     lib.rp_conv_launch_count.restype = i64
-    lib.rp_conv_nparts_tc.restype = i32
-    lib.rp_conv_nparts_tc.argtypes = [ctypes.POINTER(RpConvDesc), ctypes.POINTER(ctypes.c_int)]
-    lib.rp_conv_layer_tc.restype = i32
-    lib.rp_conv_layer_tc.argtypes = [ctypes.POINTER(RpConvDesc), vp, i32, i32, vp]
     lib.rp_conv_halo_plan.restype = i32
     lib.rp_conv_halo_plan.argtypes = [ctypes.POINTER(RpConvDesc), i32, i32, i32, ctypes.POINTER(ctypes.c_int),
                                       ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int)]

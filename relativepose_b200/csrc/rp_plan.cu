@@ -23,7 +23,6 @@ int run_plan(const rp_net_op* ops, int n_ops, void* stream) {
         int rc = RP_ERR_INVALID_ARG;
         switch (o.kind) {
         case RP_OP_CONV: rc = rp_conv_layer(&o.conv, stream); break;
-        case RP_OP_CONV_TC: rc = rp_conv_layer_tc(&o.conv, as_ptr<const void*>(a[0]), as_int(a[1]), as_int(a[2]), stream); break;
         case RP_OP_CONV_HALO: rc = rp_conv_layer_halo(&o.conv, as_ptr<const void*>(a[0]), as_int(a[1]), as_int(a[2]), as_int(a[3]), stream); break;
         case RP_OP_BN_FINALIZE:
             rc = rp_bn_finalize(as_ptr<const float*>(a[0]), as_ptr<const float*>(a[1]), as_int(a[2]), as_int(a[3]), as_int(a[4]), as_int(a[5]),

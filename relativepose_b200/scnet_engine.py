@@ -30,27 +30,6 @@ class _Act(object):
         return _Act(self.buf, self.H, self.W, self.pitch, self.ch_off + ch_off, C, self.scale, self.shift)
 
 
-def pack_tc(w_taps, src_channels, cout, bn, tk):
-    """Weights [taps, Cin_total, Cout] fp32 -> bf16 blocks [tap][k-tile][n-tile][tk/8][bn/8][8 (co)][8 (ci)]: each
-    (tap, k-tile, n-tile) block is the UMMA K-major / no-swizzle shared-memory image of a [bn x tk] B operand, so
-    the kernel copies it verbatim.  K tiles run source by source (the kernel's loop order); Cout is zero padded."""
-    import torch
-    taps = w_taps.shape[0]
-    ntn = -(-cout // bn)
-    cpad = ntn * bn
-    W = torch.zeros((taps, w_taps.shape[1], cpad), dtype=torch.float32, device=w_taps.device)
-    W[:, :, :cout] = w_taps
-    k0s, base = [], 0
-    for c in src_channels:
-        assert c % tk == 0
-        k0s += [base + c0 for c0 in range(0, c, tk)]
-        base += c
-    Wt = torch.stack([W[:, k0:k0 + tk, :] for k0 in k0s], 1)                   # [t, kt, tk, cpad]
-    Wt = Wt.reshape(taps, len(k0s), tk // 8, 8, ntn, bn // 8, 8)               # [t, kt, kc, kk, nt, nc, r]
-    Wt = Wt.permute(0, 1, 4, 2, 5, 6, 3).contiguous()                          # [t, kt, nt, kc, nc, r, kk]
-    return Wt.to(h16()).contiguous()
-
-
 def pack_halo(w_taps, tap_widx, src_channels, cout, bn, tk):
     import torch
     return _pack_halo_f32(w_taps, tap_widx, src_channels, cout, bn, tk).to(h16()).contiguous()
@@ -88,8 +67,8 @@ class ScnetEngine(object):
         self.mode = mode or os.environ.get("RP_SCNET_MODE", "tc")
         # replay the ~87 layer launches of a forward as one CUDA graph once a shape has been seen twice
         self.use_graph = os.environ.get("RP_SCNET_GRAPH", "1") == "1"
-        # halo-tile tcgen05 kernel for the 3x3 / 4x4 layers with a large enough spatial extent (csrc/scnet_halo.cu)
-        self.halo = os.environ.get("RP_SCNET_HALO", "1") == "1"
+        # tcgen05 halo-tile kernel (csrc/scnet_halo.cu) for every layer with >= 16 channels per source in 'tc' mode
+        self.halo = True
         # bit 0: 16-pixel halo pitch (debugging aid); bit 1: producer BatchNorm + LeakyReLU of 16-bit sources in packed half
         # arithmetic (default: as accurate as the float form on the reference goldens, a third of the loader instructions)
         self.halo_flags = int(os.environ.get("RP_SCNET_HALO_FLAGS", "2"))
@@ -236,7 +215,7 @@ class ScnetEngine(object):
                                              # fallback for the wider heads when the halo kernel is off)
         use_halo = False
         nparts = ctypes.c_int(0)
-        if use_tc and self.halo and ((bn and k in (3, 4)) or (k == 1 and s == 1)) and \
+        if use_tc and self.halo and ((bn and k in (3, 4)) or (k == 1 and s in (1, 2) and not transposed)) and \
                 min(out.H, out.W) // (s if transposed else 1) >= self.halo_min:
             # halo-tile kernel: stride-2 convolutions keep 4 parity planes of the halo, so their K chunk is 32
             tk = 32 if (s == 2 and not transposed) else (64 if all(a.C % 64 == 0 for a in srcs) else 32)
@@ -257,25 +236,11 @@ class ScnetEngine(object):
                     self._packed_tc[key] = pack_halo(w.reshape(k * k, w.shape[2], w.shape[3]), list(widx[:ntap.value]),
                                                      [a.C for a in srcs], out.C, bn_tile, tk)
                 wtc = self._packed_tc[key]
-        if use_tc and not use_halo and any(a.C % 32 for a in srcs):
-            raise RuntimeError("layer %s: %r input channels need the halo kernel" % (name, [a.C for a in srcs]))
         if use_tc and not use_halo:
-            tk = 64 if all(a.C % 64 == 0 for a in srcs) else 32
-            bn_tile = 128 if out.C >= 128 else (64 if out.C >= 64 else 32)
-            # small-spatial layers (the 7x7 ... 1x1 bottleneck) have one M tile per pair: narrower N tiles put more
-            # CTAs on the 148 SMs (each streams its own slice of the weights; the A gather is tiny there)
-            m_tiles = -(-(self._gsz * out.H * out.W // (s * s if transposed else 1)) // 128) * (s * s if transposed else 1)
-            while bn_tile > 32 and m_tiles * -(-out.C // bn_tile) * self._P < 296:
-                bn_tile //= 2
-            key = (name, bn_tile, tk)
-            if key not in self._packed_tc:
-                w = self._packed[name]
-                self._packed_tc[key] = pack_tc(w.reshape(k * k, w.shape[2], w.shape[3]), [a.C for a in srcs], out.C, bn_tile, tk)
-            wtc = self._packed_tc[key]
+            use_tc = False                  # no tile plan for this shape: the float32 CUDA-core kernel (reads / writes 16-bit storage too)
         if bn:
             if not use_halo:
-                _lib.check((self.lib.rp_conv_nparts_tc if use_tc else self.lib.rp_conv_nparts)(ctypes.byref(d), ctypes.byref(nparts)),
-                           "rp_conv_nparts")
+                _lib.check(self.lib.rp_conv_nparts(ctypes.byref(d), ctypes.byref(nparts)), "rp_conv_nparts")
             need = self._P * nparts.value * out.C
             pt = self._bufs['partials']
             if pt is None or pt.numel() < 2 * need:
@@ -286,8 +251,6 @@ class ScnetEngine(object):
             d.psum, d.psq = None, None
         if use_halo:
             self._run("rp_conv_layer_halo", d, wtc.data_ptr(), bn_tile, tk, self.halo_flags, stream)
-        elif use_tc:
-            self._run("rp_conv_layer_tc", d, wtc.data_ptr(), bn_tile, tk, stream)
         else:
             self._run("rp_conv_layer", d, stream)
         if bn:
