@@ -23,13 +23,17 @@ LEAKY = 0.1          # mymodel.py:20,33
 
 def _block(sd, name, x, transposed, stride, padding, trace=None, tag=None):
     w = sd[name + '.0.weight']
+    b = sd.get(name + '.0.bias')                     # batchnorm=0 blocks: biased convolution, no BatchNorm (mymodel.py:23-27,35-39)
     if transposed:
         y = F.conv_transpose2d(x, w, None, stride=stride, padding=padding)
     else:
         y = F.conv2d(x, w, None, stride=stride, padding=padding)
     if trace is not None:
         trace[(tag or name) + ':raw'] = y
-    y = F.batch_norm(y, None, None, sd[name + '.1.weight'], sd[name + '.1.bias'], True, 0.0, BN_EPS)
+    if b is not None:
+        y = y + b.view(1, -1, 1, 1)
+    else:
+        y = F.batch_norm(y, None, None, sd[name + '.1.weight'], sd[name + '.1.bias'], True, 0.0, BN_EPS)
     y = F.leaky_relu(y, LEAKY)
     if trace is not None:
         trace[(tag or name) + ':act'] = y
@@ -44,8 +48,10 @@ def deconv(sd, name, x, k, s, p, trace=None, tag=None):
     return _block(sd, name, x, True, s, p, trace, tag)
 
 
-def forward_pair(sd, x, snumclass, use_tanh=True, trace=None):
-    """x: [2,16,H,W] one scan pair -> [2, 7+snumclass+32, H, W].  mymodel.py:259-380 (skipLayer=1, 'rgbdnsf')."""
+def forward_pair(sd, x, snumclass, use_tanh=True, trace=None, skip=True, heads=('rgb', 'n', 'd', 's', 'f')):
+    """x: [2,16,H,W] one scan pair -> [2, sum of head channels, H, W].  mymodel.py:259-380; ``skip`` = args.skipLayer (:302 /
+    :333 branches), ``heads`` = the output heads args.outputType selects, in the reference's order; a batchnorm=0 network is
+    recognised by its ``.0.bias`` keys."""
     in_shape = x.shape[2:]
     x = F.interpolate(x, size=[224, 224], mode='bilinear', align_corners=False)          # :261
     if trace is not None:
@@ -68,20 +74,21 @@ def forward_pair(sd, x, snumclass, use_tanh=True, trace=None):
     x7 = conv(sd, 'conv7', x6, 3, 2, 0, trace)
     x8 = conv(sd, 'conv8', x7, 3, 1, 1, trace)
     x9 = conv(sd, 'conv9', x8, 3, 1, 0, trace)
-    dx9 = deconv(sd, 'deconv9', x9, 3, 1, 0, trace)                                      # :302-307
-    dx8 = deconv(sd, 'deconv8', torch.cat((dx9, x8), 1), 3, 1, 1, trace)
-    dx7 = deconv(sd, 'deconv7', torch.cat((dx8, x7), 1), 3, 2, 0, trace)
-    dx6 = deconv(sd, 'deconv6', torch.cat((dx7, x6), 1), 4, 2, 1, trace)
-    dx5 = deconv(sd, 'deconv5', torch.cat((dx6, x5), 1), 4, 2, 1, trace)
-    dx4 = deconv(sd, 'deconv4', torch.cat((dx5, x4), 1), 4, 2, 1, trace)
+    cat = (lambda a, b: torch.cat((a, b), 1)) if skip else (lambda a, b: a)
+    dx9 = deconv(sd, 'deconv9', x9, 3, 1, 0, trace)                                      # :302-307 / :333-339
+    dx8 = deconv(sd, 'deconv8', cat(dx9, x8), 3, 1, 1, trace)
+    dx7 = deconv(sd, 'deconv7', cat(dx8, x7), 3, 2, 0, trace)
+    dx6 = deconv(sd, 'deconv6', cat(dx7, x6), 4, 2, 1, trace)
+    dx5 = deconv(sd, 'deconv5', cat(dx6, x5), 4, 2, 1, trace)
+    dx4 = deconv(sd, 'deconv4', cat(dx5, x4), 4, 2, 1, trace)
     outs = []
-    for st in ('rgb', 'n', 'd'):                                                          # :309-325
+    for st in [h for h in ('rgb', 'n', 'd') if h in heads]:                               # :309-325 / :341-357
         e1, e2, e3 = enc[st]
-        d3 = deconv(sd, 'deconv3' + st, torch.cat((dx4, e3), 1), 4, 2, 1, trace)
-        d2 = deconv(sd, 'deconv2' + st, torch.cat((d3, e2), 1), 4, 2, 1, trace)
-        d1 = F.conv2d(torch.cat((d2, e1), 1), sd['deconv1' + st + '.weight'], sd['deconv1' + st + '.bias'])
+        d3 = deconv(sd, 'deconv3' + st, cat(dx4, e3), 4, 2, 1, trace)
+        d2 = deconv(sd, 'deconv2' + st, cat(d3, e2), 4, 2, 1, trace)
+        d1 = F.conv2d(cat(d2, e1), sd['deconv1' + st + '.weight'], sd['deconv1' + st + '.bias'])
         outs.append(d1)
-    for st in ('s', 'f'):                                                                 # :364-376
+    for st in [h for h in ('s', 'f') if h in heads]:                                      # :364-376
         d3 = deconv(sd, 'deconv3' + st, dx4, 4, 2, 1, trace)
         d2 = deconv(sd, 'deconv2' + st, d3, 4, 2, 1, trace)
         d1 = F.conv2d(d2, sd['deconv1' + st + '.weight'], sd['deconv1' + st + '.bias'])
@@ -94,8 +101,8 @@ def forward_pair(sd, x, snumclass, use_tanh=True, trace=None):
     return F.interpolate(out224, size=list(in_shape), mode='bilinear', align_corners=False)   # :379
 
 
-def forward(sd, x, snumclass, use_tanh=True):
+def forward(sd, x, snumclass, use_tanh=True, skip=True, heads=('rgb', 'n', 'd', 's', 'f')):
     """x: [2P,16,H,W]; consecutive image pairs are independent forward calls of the reference."""
     assert x.shape[0] % 2 == 0
     with torch.no_grad():
-        return torch.cat([forward_pair(sd, x[i:i + 2], snumclass, use_tanh) for i in range(0, x.shape[0], 2)], 0)
+        return torch.cat([forward_pair(sd, x[i:i + 2], snumclass, use_tanh, None, skip, heads) for i in range(0, x.shape[0], 2)], 0)

@@ -24,9 +24,13 @@ def weights_init(m):
         m.bias.data.fill_(0)
 
 
-def _block(transposed, cin, cout, k, s, p):
-    conv = (nn.ConvTranspose2d if transposed else nn.Conv2d)(cin, cout, kernel_size=k, stride=s, padding=p, bias=False)
-    return nn.Sequential(conv, nn.BatchNorm2d(cout, track_running_stats=False), nn.LeakyReLU(0.1, inplace=True))
+def _block(transposed, cin, cout, k, s, p, batchnorm=True):
+    """conv2d / deconv2d of mymodel.py:15-39: conv (no bias) + BatchNorm (batch statistics) + LeakyReLU(0.1), or -- batchnorm=0 --
+    conv with bias + LeakyReLU(0.1).  Same Sequential indices as the reference, hence the same state_dict keys."""
+    conv = (nn.ConvTranspose2d if transposed else nn.Conv2d)(cin, cout, kernel_size=k, stride=s, padding=p, bias=not batchnorm)
+    if batchnorm:
+        return nn.Sequential(conv, nn.BatchNorm2d(cout, track_running_stats=False), nn.LeakyReLU(0.1, inplace=True))
+    return nn.Sequential(conv, nn.LeakyReLU(0.1, inplace=True))
 
 
 # (name, transposed, cin, cout, k, s, p) in the reference's registration order (mymodel.py:151-231)
@@ -44,38 +48,48 @@ def _layer_table(snumclass, skip):
     return t
 
 
+HEAD_CHANNELS = {'rgb': 3, 'n': 3, 'd': 1, 's': None, 'f': 32}      # 's': args.snumclass
+HEAD_ORDER = ('rgb', 'n', 'd', 's', 'f')                             # order of the output channels (mymodel.py:309-377)
+
+
 class SCNet(nn.Module):
     def __init__(self, args):
         super(SCNet, self).__init__()
-        if not args.batchnorm:
-            raise NotImplementedError("relativepose_b200.SCNet implements the batchnorm=1 configuration the reference ships")
         if 'k' in args.outputType:
             raise NotImplementedError("outputType 'k' is dead code in the reference (mymodel.py:327-331 reads undefined tensors)")
-        for need in ('rgb', 'n', 'd', 's', 'f'):
-            if need not in args.outputType:
-                raise NotImplementedError("relativepose_b200.SCNet implements outputType 'rgbdnsf' (evaluation.py:52)")
-        if not args.skipLayer:
-            raise NotImplementedError("relativepose_b200.SCNet implements skipLayer=1 (opts.py:28 default)")
+        self.heads = [h for h in HEAD_ORDER if (h in args.outputType if h != 'rgb' else 'rgb' in args.outputType)]
+        if not self.heads:
+            raise ValueError("outputType %r selects no output head" % (args.outputType,))
+        if not args.skipLayer and any(h in ('rgb', 'n', 'd') for h in self.heads):
+            # the reference's own forward fails there: deconv1rgb/n/d are built for 64 input channels (mymodel.py:190,198,206)
+            # but the skipLayer=0 branch feeds them the 32 channels of deconv2* alone (:341,347,353)
+            raise NotImplementedError("skipLayer=0 works in the reference only with outputType drawn from 's', 'f'")
+        self.batchnorm = int(bool(args.batchnorm))
         self.useTanh = args.useTanh
         self.skipLayer = args.skipLayer
         self.outputType = args.outputType
         self.snumclass = args.snumclass
-        ngf, m = 64, 2
-        for name, tr, cin, cout, k, s, p in _layer_table(args.snumclass, True):
-            setattr(self, name, _block(bool(tr), cin, cout, k, s, p))
-        for st, nout in (('rgb', 3), ('n', 3), ('d', 1)):
-            setattr(self, 'deconv3' + st, _block(True, ngf * 2 * m, ngf, 4, 2, 1))
-            setattr(self, 'deconv2' + st, _block(True, ngf * m, ngf // 2, 4, 2, 1))
-            setattr(self, 'deconv1' + st, nn.Conv2d(ngf, nout, 1, 1, 0))
-        for st, nout in (('s', args.snumclass), ('f', 32)):
-            setattr(self, 'deconv3' + st, _block(True, ngf * 2, ngf, 4, 2, 1))
-            setattr(self, 'deconv2' + st, _block(True, ngf, ngf, 4, 2, 1))
+        ngf, m, bnf = 64, (2 if args.skipLayer else 1), bool(args.batchnorm)
+        for name, tr, cin, cout, k, s, p in _layer_table(args.snumclass, bool(args.skipLayer)):
+            setattr(self, name, _block(bool(tr), cin, cout, k, s, p, bnf))
+        for st in self.heads:                                   # registration order of the reference: rgb, n, d, s, f
+            nout = args.snumclass if st == 's' else HEAD_CHANNELS[st]
+            if st in ('rgb', 'n', 'd'):
+                setattr(self, 'deconv3' + st, _block(True, ngf * 2 * m, ngf, 4, 2, 1, bnf))
+                setattr(self, 'deconv2' + st, _block(True, ngf * m, ngf // 2, 4, 2, 1, bnf))
+            else:
+                setattr(self, 'deconv3' + st, _block(True, ngf * 2, ngf, 4, 2, 1, bnf))
+                setattr(self, 'deconv2' + st, _block(True, ngf, ngf, 4, 2, 1, bnf))
             setattr(self, 'deconv1' + st, nn.Conv2d(ngf, nout, 1, 1, 0))
         self.apply(weights_init)
         self._engine = None
 
+    def head_channels(self):
+        """[(head, channels)] in output order; the descriptor head 'f' is last (evaluation.py:137-138 computes its offset)."""
+        return [(h, self.snumclass if h == 's' else HEAD_CHANNELS[h]) for h in self.heads]
+
     def forward(self, x):
-        """x: [2P,16,H,W] float32 CUDA (NCHW, as evaluation.py:242 builds it) -> [2P, 7+snumclass+32, H, W].
+        """x: [2P,16,H,W] float32 CUDA (NCHW, as evaluation.py:242 builds it) -> [2P, sum of head channels, H, W].
         Consecutive image pairs are independent BN groups, exactly like P separate calls of the reference."""
         from .. import scnet_engine
         if self._engine is None:

@@ -136,9 +136,11 @@ class ScnetEngine(object):
         self._packed_key = key
 
     # ---------------------------------------------------------------- buffers
-    def _alloc(self, P, device, cout_total):
+    def _alloc(self, P, device, heads):
+        """heads: [(name, channels)] in output order (SCNet.head_channels())."""
         torch = self.torch
-        if self._P == P and self._dev == device and self._bufs.get('ctot') == cout_total:
+        cout_total = sum(c for _, c in heads)
+        if self._P == P and self._dev == device and self._bufs.get('heads') == tuple(heads):
             return
         n = 2 * P
         self._plans, self._graphs, self._seen = {}, {}, {}          # they hold pointers into the buffers replaced below
@@ -164,18 +166,21 @@ class ScnetEngine(object):
         act('x7', 3, 3, 512); act('x8', 3, 3, 512); act('x9', 1, 1, 1024)
         act('dx9', 3, 3, 512); act('dx8', 3, 3, 512); act('dx7', 7, 7, 512)
         act('dx6', 14, 14, 512); act('dx5', 28, 28, 256); act('dx4', 56, 56, 128)
-        for st in ('rgb', 'n', 'd', 's', 'f'):
+        for st, _ in heads:
             act('d3' + st, 112, 112, 64)
             act('d2' + st, 224, 224, 32 if st in ('rgb', 'n', 'd') else 64)
-        # 224x224 output of the five heads, each at a 16-byte aligned channel offset (float4 stores in the head kernels)
-        snum = cout_total - 39
-        offs = {'rgb': 0, 'n': 4, 'd': 8, 's': 12, 'f': 12 + 4 * ((snum + 3) // 4)}
-        pitch = offs['f'] + 32
+        # 224x224 output of the heads, each at a 16-byte aligned channel offset (float4 stores in the head kernels)
+        offs, cmap, o = {}, [], 0
+        for st, c in heads:
+            offs[st] = o
+            cmap += list(range(o, o + c))
+            o += 4 * ((c + 3) // 4)
+        pitch = o
         B['out224'] = _Act(torch.zeros((n, 224, 224, pitch), **f), 224, 224, pitch, 0, pitch)
-        cmap = list(range(0, 3)) + list(range(4, 7)) + [8] + list(range(12, 12 + snum)) + list(range(offs['f'], offs['f'] + 32))
         B['head_off'] = offs
         B['cmap'] = torch.tensor(cmap, dtype=torch.int32, device=device)
         B['ctot'] = cout_total
+        B['heads'] = tuple(heads)
         B['partials'] = None
         self._bufs, self._P, self._dev = B, P, device
 
@@ -183,8 +188,17 @@ class ScnetEngine(object):
     _slope = 0.1          # LeakyReLU(0.1) of the SCNet blocks; ResnetEngine overrides with 0 (ReLU)
     _gsz = 2              # images per BatchNorm batch (one scan pair)
 
-    def _conv(self, name, srcs, out, transposed, k, s, p, bn=True, bias=None, tanh=False, stream=None, bn_params=None, wkey=None):
+    def _conv(self, name, srcs, out, transposed, k, s, p, bn=True, bias=None, tanh=False, stream=None, bn_params=None, wkey=None,
+              block_bias=None):
+        """block_bias: the layer is a batchnorm=0 block (mymodel.py:23-27,35-39: biased convolution + LeakyReLU).  The raw
+        convolution is stored and the consumer's load-time transform gets scale = 1, shift = bias -- the same mechanism that
+        applies a BatchNorm, so no kernel knows the difference."""
         torch = self.torch
+        if block_bias is not None:
+            bn = False
+            sl = slice(out.ch_off, out.ch_off + out.C)
+            out.scale[:, sl] = 1.0                       # (eager runs only; a frozen plan / graph replays the kernels, the
+            out.shift[:, sl] = block_bias.detach().float()   #  two small tensors keep their values)
         wkey = wkey or name                  # entry of self._packed holding this layer's [k,k,Cin,Cout] weights
         d = _lib.RpConvDesc()
         d.imgs_per_group = self._gsz
@@ -215,7 +229,7 @@ class ScnetEngine(object):
                                              # fallback for the wider heads when the halo kernel is off)
         use_halo = False
         nparts = ctypes.c_int(0)
-        if use_tc and self.halo and ((bn and k in (3, 4)) or (k == 1 and s in (1, 2) and not transposed)) and \
+        if use_tc and self.halo and (k in (3, 4) or (k == 1 and s in (1, 2) and not transposed)) and \
                 min(out.H, out.W) // (s if transposed else 1) >= self.halo_min:
             # halo-tile kernel: stride-2 convolutions keep 4 parity planes of the halo, so their K chunk is 32
             tk = 32 if (s == 2 and not transposed) else (64 if all(a.C % 64 == 0 for a in srcs) else 32)
@@ -336,14 +350,25 @@ class ScnetEngine(object):
         n, _, H, W = x.shape
         P = n // 2
         net = self.net
-        snum = net.snumclass
-        ctot = 7 + snum + 32
+        heads = net.head_channels()                      # [(name, channels)] of the heads args.outputType selected, output order
+        ctot = sum(c for _, c in heads)
+        skip = bool(net.skipLayer)
+        nobn = not bool(getattr(net, 'batchnorm', 1))    # batchnorm=0: biased convolutions, no BatchNorm (mymodel.py:23-27,35-39)
         with torch.cuda.device(x.device), torch.no_grad():
             self._pack()
-            self._alloc(P, x.device, ctot)
+            self._alloc(P, x.device, heads)
             B = self._bufs
             stream = torch.cuda.current_stream().cuda_stream
-            split_stem = self.act_bf16 and self.halo     # conv1* on tcgen05 from the bf16 hi/lo split input
+
+            def block(name, srcs, out, transposed, k, s, p, **kw):
+                """One conv2d / deconv2d block of the reference (mymodel.py:15-39)."""
+                if nobn:
+                    kw['block_bias'] = getattr(net, name)[0].bias
+                self._conv(name, srcs, out, transposed, k, s, p, stream=stream, **kw)
+
+            def cat(a, b):
+                return [a, b] if skip else [a]           # skipLayer=0: the decoder sees no encoder tensors (:333-357)
+            split_stem = self.act_bf16 and self.halo     # conv1* on tcgen05 from the 16-bit hi/lo split input
             if split_stem:
                 self._run("rp_scnet_resize_in_split", x.data_ptr(), n, H, W, B['in96'].buf.data_ptr(), stream)
                 for st in ('rgb', 'n', 'd'):
@@ -364,37 +389,35 @@ class ScnetEngine(object):
                     off, c = chan[st]
                     if split_stem:
                         grp = {'rgb': 0, 'n': 1, 'd': 2}[st] + (3 if wh else 0)
-                        self._conv('conv1' + st, [B['in96'].view(16 * grp, 16)], B['e1' + st + wh], False, 3, 1, 1, stream=stream,
-                                   wkey='conv1' + st + '#split')
+                        block('conv1' + st, [B['in96'].view(16 * grp, 16)], B['e1' + st + wh], False, 3, 1, 1, wkey='conv1' + st + '#split')
                     else:
-                        self._conv('conv1' + st, [B['in20'].view(base + off, c)], B['e1' + st + wh], False, 3, 1, 1, stream=stream)
-                    self._conv('conv2' + st, [B['e1' + st + wh]], B['e2' + st + wh], False, 4, 2, 1, stream=stream)
-                    self._conv('conv3' + st, [B['e2' + st + wh]], B['xin'].view(xin_slot[st + wh], 128), False, 4, 2, 1, stream=stream)
-            self._conv('conv4', [B['xin']], B['x4'], False, 4, 2, 1, stream=stream)
-            self._conv('conv5', [B['x4']], B['x5'], False, 4, 2, 1, stream=stream)
-            self._conv('conv6', [B['x5']], B['x6'], False, 4, 2, 1, stream=stream)
-            self._conv('conv7', [B['x6']], B['x7'], False, 3, 2, 0, stream=stream)
-            self._conv('conv8', [B['x7']], B['x8'], False, 3, 1, 1, stream=stream)
-            self._conv('conv9', [B['x8']], B['x9'], False, 3, 1, 0, stream=stream)
-            self._conv('deconv9', [B['x9']], B['dx9'], True, 3, 1, 0, stream=stream)
-            self._conv('deconv8', [B['dx9'], B['x8']], B['dx8'], True, 3, 1, 1, stream=stream)
-            self._conv('deconv7', [B['dx8'], B['x7']], B['dx7'], True, 3, 2, 0, stream=stream)
-            self._conv('deconv6', [B['dx7'], B['x6']], B['dx6'], True, 4, 2, 1, stream=stream)
-            self._conv('deconv5', [B['dx6'], B['x5']], B['dx5'], True, 4, 2, 1, stream=stream)
-            self._conv('deconv4', [B['dx5'], B['x4']], B['dx4'], True, 4, 2, 1, stream=stream)
-            head_off = {k: (B['head_off'][k], c) for k, c in (('rgb', 3), ('n', 3), ('d', 1), ('s', snum), ('f', 32))}
-            for st in ('rgb', 'n', 'd'):
-                self._conv('deconv3' + st, [B['dx4'], B['xin'].view(xin_slot[st], 128)], B['d3' + st], True, 4, 2, 1, stream=stream)
-                self._conv('deconv2' + st, [B['d3' + st], B['e2' + st]], B['d2' + st], True, 4, 2, 1, stream=stream)
-                o, c = head_off[st]
-                self._conv('deconv1' + st, [B['d2' + st], B['e1' + st]], B['out224'].view(o, c), False, 1, 1, 0, bn=False,
-                           bias=getattr(net, 'deconv1' + st).bias, stream=stream)
-            for st in ('s', 'f'):
-                self._conv('deconv3' + st, [B['dx4']], B['d3' + st], True, 4, 2, 1, stream=stream)
-                self._conv('deconv2' + st, [B['d3' + st]], B['d2' + st], True, 4, 2, 1, stream=stream)
-                o, c = head_off[st]
-                self._conv('deconv1' + st, [B['d2' + st]], B['out224'].view(o, c), False, 1, 1, 0, bn=False,
-                           bias=getattr(net, 'deconv1' + st).bias, tanh=(st == 'f' and bool(net.useTanh)), stream=stream)
+                        block('conv1' + st, [B['in20'].view(base + off, c)], B['e1' + st + wh], False, 3, 1, 1)
+                    block('conv2' + st, [B['e1' + st + wh]], B['e2' + st + wh], False, 4, 2, 1)
+                    block('conv3' + st, [B['e2' + st + wh]], B['xin'].view(xin_slot[st + wh], 128), False, 4, 2, 1)
+            block('conv4', [B['xin']], B['x4'], False, 4, 2, 1)
+            block('conv5', [B['x4']], B['x5'], False, 4, 2, 1)
+            block('conv6', [B['x5']], B['x6'], False, 4, 2, 1)
+            block('conv7', [B['x6']], B['x7'], False, 3, 2, 0)
+            block('conv8', [B['x7']], B['x8'], False, 3, 1, 1)
+            block('conv9', [B['x8']], B['x9'], False, 3, 1, 0)
+            block('deconv9', [B['x9']], B['dx9'], True, 3, 1, 0)
+            block('deconv8', cat(B['dx9'], B['x8']), B['dx8'], True, 3, 1, 1)
+            block('deconv7', cat(B['dx8'], B['x7']), B['dx7'], True, 3, 2, 0)
+            block('deconv6', cat(B['dx7'], B['x6']), B['dx6'], True, 4, 2, 1)
+            block('deconv5', cat(B['dx6'], B['x5']), B['dx5'], True, 4, 2, 1)
+            block('deconv4', cat(B['dx5'], B['x4']), B['dx4'], True, 4, 2, 1)
+            for st, c in heads:
+                o = B['head_off'][st]
+                if st in ('rgb', 'n', 'd'):                                    # mymodel.py:309-325 (skipLayer=1 only, see SCNet.__init__)
+                    block('deconv3' + st, [B['dx4'], B['xin'].view(xin_slot[st], 128)], B['d3' + st], True, 4, 2, 1)
+                    block('deconv2' + st, [B['d3' + st], B['e2' + st]], B['d2' + st], True, 4, 2, 1)
+                    self._conv('deconv1' + st, [B['d2' + st], B['e1' + st]], B['out224'].view(o, c), False, 1, 1, 0, bn=False,
+                               bias=getattr(net, 'deconv1' + st).bias, stream=stream)
+                else:                                                          # :364-376
+                    block('deconv3' + st, [B['dx4']], B['d3' + st], True, 4, 2, 1)
+                    block('deconv2' + st, [B['d3' + st]], B['d2' + st], True, 4, 2, 1)
+                    self._conv('deconv1' + st, [B['d2' + st]], B['out224'].view(o, c), False, 1, 1, 0, bn=False,
+                               bias=getattr(net, 'deconv1' + st).bias, tanh=(st == 'f' and bool(net.useTanh)), stream=stream)
             out = torch.empty((n, ctot, H, W), dtype=torch.float32, device=x.device)
             self._run("rp_scnet_resize_out_map", B['out224'].buf.data_ptr(), n, B['out224'].pitch, B['cmap'].data_ptr(), ctot, H, W,
                                                         out.data_ptr(), stream)
@@ -427,7 +450,7 @@ class ScnetEngine(object):
                      ('deconv9', 'dx9'), ('deconv8', 'dx8'), ('deconv7', 'dx7'), ('deconv6', 'dx6'), ('deconv5', 'dx5'),
                      ('deconv4', 'dx4')):
             names[a] = B[b]
-        for st in ('rgb', 'n', 'd', 's', 'f'):
+        for st, _ in B['heads']:
             names['deconv3' + st] = B['d3' + st]
             names['deconv2' + st] = B['d2' + st]
         for k, a in names.items():

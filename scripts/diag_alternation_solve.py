@@ -42,7 +42,8 @@ for label, R_hat in (("identity pose (step 0)", np.tile(np.eye(4), (B, 1, 1))), 
     torch.cuda.synchronize(); ms = (time.perf_counter() - t0) * 1e3
     s = stats.cpu().numpy(); stt = st.cpu().numpy()
     print(label, ": solve %.2f ms; status" % ms, np.bincount(stt - stt.min()), "min", stt.min())
-    print("  columns N, M1, M2, NZ, tot_it, max_it, not_conv, K; first 6 pairs:\n", s[:6])
+    np.set_printoptions(linewidth=200)
+    print("  columns N, M1, M2, NZ, tot_it, max_it, not_conv, K; all pairs:\n", s)
     print("  mean:", s.mean(0))
     from relativepose_b200 import _lib
     for stage, nm in ((_lib.STAGE_TOPK, 'A only'), (_lib.STAGE_AFFINITY, 'A-D'), (_lib.STAGE_SOLVE, 'A-F')):

@@ -136,3 +136,48 @@ def test_scnet_module_surface():
     assert len(keys) == 103 and keys[0] == 'conv1rgb.0.weight' and 'deconv1f.bias' in keys
     with pytest.raises(RuntimeError):
         net(torch.zeros(2, 16, 32, 128))          # CPU tensor: no fallback
+
+
+def _variants():
+    import os
+    return np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "scnet_variants_golden.npz"))
+
+
+@pytest.mark.parametrize("name", ["nobn", "noskip_sf", "partial_df", "nobn_noskip_f"])
+@pytest.mark.parametrize("mode", ["fp32", "tc"])
+def test_scnet_constructor_variants(name, mode):
+    """batchnorm=0 (mymodel.py:23-27,35-39), skipLayer=0 (:333-357) and partial outputType against goldens from the
+    unmodified reference class (tests/golden/make_scnet_variants_golden.py).  float32 path: 5e-4 of the output range
+    (a batchnorm=0 network is not re-normalised, its outputs grow to O(100), hence relative); tensor-core path: the
+    documented 16-bit tolerance (0.25 max-abs / 0.03 rms per unit of output range)."""
+    import torch
+    from relativepose_b200 import synth
+    from relativepose_b200.model.mymodel import SCNet
+    from relativepose_b200.scnet_engine import ScnetEngine
+    G = _variants()
+    bn, skip, snum, tanh, seed, chk = G[name + '/meta']
+    a = types.SimpleNamespace(batchnorm=int(bn), useTanh=int(tanh), skipLayer=int(skip), outputType=str(G[name + '/otype']),
+                              snumclass=int(snum))
+    torch.manual_seed(0)
+    net = SCNet(a)
+    got_chk = float(sum(v.double().abs().sum().item() for v in net.state_dict().values()))
+    assert abs(got_chk - chk) <= 1e-6 * chk
+    x = torch.from_numpy(synth.make_panorama_pair(int(seed), str(G[name + '/dataset'])))
+    net = net.cuda()
+    eng = ScnetEngine(net, mode=mode)
+    ys = [eng.forward(x.cuda()) for _ in range(4)]            # eager, eager (recorded), plan replay, graph replay
+    torch.cuda.synchronize()
+    for y in ys[1:]:
+        assert torch.equal(y, ys[0])
+    yc = ys[0].cpu().numpy()
+    assert yc.shape[1] == G[name + '/mean'].shape[1]
+    sub = G[name + '/sub']
+    rng_ = max(1.0, float(np.abs(sub).max()))
+    d = yc[:, :, ::8, ::16] - sub
+    emax, erms = float(np.abs(d).max()) / rng_, float(np.sqrt((d ** 2).mean())) / rng_
+    emean = float(np.abs(yc.mean(axis=(2, 3)) - G[name + '/mean']).max()) / rng_
+    print("%s %s: max %.3e rms %.3e mean %.3e (relative to |y|max %.2f)" % (name, mode, emax, erms, emean, rng_))
+    if mode == 'fp32':
+        assert emax <= TOL and emean <= TOL
+    else:
+        assert emax <= 0.25 and erms <= 0.03

@@ -113,3 +113,38 @@ def test_packed_batch_layouts_and_sum_order():
         assert np.array_equal(pk.pc_s.numpy()[lo:hi], recs[b]['pc_src']) and np.array_equal(pk.feat_s.numpy()[lo:hi], recs[b]['feat_src'])
         lo, hi = int(pk.off_t[b]), int(pk.off_t[b + 1])
         assert np.array_equal(pk.w_t.numpy()[lo:hi], np.asarray(recs[b]['weight_tgt'])) and np.array_equal(pk.nrm_t.numpy()[lo:hi], recs[b]['normal_tgt'])
+
+
+def test_scnet_constructor_variants_state_dict_and_oracle():
+    """SCNet(batchnorm=0 / skipLayer=0 / partial outputType): parameter names follow the reference's layer table
+    (mymodel.py:151-231) and the oracle restatement reproduces the reference's golden for one variant."""
+    import os
+    import types
+    import numpy as np
+    import torch
+    from oracle import scnet_oracle
+    from relativepose_b200 import synth
+    from relativepose_b200.model.mymodel import SCNet
+    G = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "scnet_variants_golden.npz"))
+    a = types.SimpleNamespace(batchnorm=0, useTanh=1, skipLayer=1, outputType='rgbdnsf', snumclass=15)
+    keys = list(SCNet(a).state_dict().keys())
+    assert 'conv4.0.bias' in keys and not any('.1.' in k for k in keys)
+    a = types.SimpleNamespace(batchnorm=1, useTanh=0, skipLayer=0, outputType='sf', snumclass=21)
+    net = SCNet(a)
+    assert net.deconv8[0].weight.shape[0] == 512 and not hasattr(net, 'deconv3rgb')
+    assert [h for h, _ in net.head_channels()] == ['s', 'f'] and net.head_channels()[0][1] == 21
+    import pytest
+    with pytest.raises(NotImplementedError):
+        SCNet(types.SimpleNamespace(batchnorm=1, useTanh=1, skipLayer=0, outputType='rgbdnsf', snumclass=15))
+    name = 'nobn_noskip_f'
+    bn, skip, snum, tanh, seed, chk = G[name + '/meta']
+    a = types.SimpleNamespace(batchnorm=int(bn), useTanh=int(tanh), skipLayer=int(skip), outputType=str(G[name + '/otype']),
+                              snumclass=int(snum))
+    torch.manual_seed(0)
+    net = SCNet(a)
+    sd = {k: v.detach().clone() for k, v in net.state_dict().items()}
+    x = torch.from_numpy(synth.make_panorama_pair(int(seed), str(G[name + '/dataset'])))
+    torch.set_num_threads(8)
+    y = scnet_oracle.forward(sd, x, int(snum), bool(tanh), skip=bool(skip), heads=tuple(net.heads)).numpy()
+    sub = G[name + '/sub']
+    assert np.abs(y[:, :, ::8, ::16] - sub).max() <= 1e-4 * max(1.0, np.abs(sub).max())
