@@ -92,7 +92,8 @@ typedef struct rp_params {
  * 5 max power iterations in one alternation, 6 bit 0: some alternation hit max_power_iters; bits 8..: number of source
  * rows whose top-k index SET the keys alone do not determine (the K-th and (K+1)-th candidate tie exactly, or selected
  * entries underflowed to weight 0 in a row that is not all zero): there the reference's numpy.argpartition order decides and
- * the sets may differ from it (all-zero rows follow numpy through zero_row_topk; counted on the 32-channel path), 7 K */
+ * the sets may differ from it (all-zero rows follow numpy through zero_row_topk; counted on the 32-channel path),
+ * 7 bits 0..7: K; bit 8: the pair was solved by the accelerated (locally optimal CG) eigen iteration */
 
 /* Optional stage-boundary outputs (device pointers; any may be NULL).  Used by the parity tests. */
 typedef struct rp_debug {
@@ -126,6 +127,14 @@ int rp_solve_workspace_bytes(int n_slots, int max_ns, int max_nt, int max_topk, 
  * many pairs size the workspace for min(B, default) slots.  Pairs with n_s*topK <= 16383 are supported; above ~2800
  * correspondences (or n_t > ~1400) the per-pair vectors move from shared memory into the slot's workspace. */
 int rp_solve_default_slots(int max_ns, int max_nt, int max_topk, int feat_dim, int* n_slots);
+
+/* Small-batch path.  The solver kernel is built twice: 128-thread CTAs, four per SM (throughput for batches that fill the
+ * GPU) and 512-thread CTAs, one per SM, which give a scan pair a whole SM.  The reference calls its solver one pair at a time
+ * (evaluation.py:278-284) and the completion alternation solves a few dozen pairs per step (rpmodule.py:569-662); batches of
+ * at most `wide_max` pairs take the 512-thread build (default: the SM count; environment RP_SOLVER_WIDE_MAX; 0 = never).
+ * rp_solver_wide_max(new_max) sets the limit when new_max >= 0 and returns the previous one.  The two builds agree to
+ * rounding (reduction trees differ with the CTA width), not bitwise; which build a batch takes depends on its size alone. */
+int rp_solver_wide_max(int new_max);
 
 /* Replaces RelativePoseEstimation_helper (RPModule/rpmodule.py:317-508) for a ragged batch of B
  * scan pairs -- descriptor distance + soft match + top-k, pairwise consistency affinity,

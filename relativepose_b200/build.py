@@ -13,7 +13,7 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", 
 
 LIBS = {
     # output (relative to the package dir) : sources (relative to csrc/)
-    "librp_b200.so": ["rp_solver.cu", "scnet.cu", "scnet_tc.cu", "scnet_halo.cu", "rp_warp.cu", "rp_keypoint.cu", "rp_plan.cu"],
+    "librp_b200.so": ["rp_solver.cu", "rp_solver_wide.cu", "scnet.cu", "scnet_tc.cu", "scnet_halo.cu", "rp_warp.cu", "rp_keypoint.cu", "rp_plan.cu"],
 }
 
 
@@ -46,7 +46,8 @@ def build_all(force=False, verbose=False):
             src = os.path.join(CSRC, sname)
             obj = os.path.join(objdir, sname[:-3] + ".o")
             objs.append(obj)
-            if force or _stale(obj, [src] + headers):
+            inc = [os.path.join(CSRC, ln.split('"')[1]) for ln in open(src) if ln.startswith('#include "') and ln.split('"')[1].endswith(".cu")]
+            if force or _stale(obj, [src] + inc + headers):
                 cmd = [_nvcc()] + [f for f in NVCC_FLAGS if f != "-shared"] + os.environ.get("RP_NVCC_EXTRA", "").split() + ["-I", INCLUDE, "-c", "-o", obj, src]
                 if verbose:
                     cmd[1:1] = ["-Xptxas", "-v"]

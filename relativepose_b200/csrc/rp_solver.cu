@@ -28,6 +28,7 @@
 #include <math_constants.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include "../../include/rp_b200.h"
 
@@ -55,6 +56,9 @@ constexpr float FEAT_SCALING = 100.0f;  // rpmodule.py:327
 // row-normalised: a keypoint's best candidate has f ~ 1, its other candidates ~ e^-400).  Filters, counts and the
 // surviving-pair set are unaffected; the fitters then only visit correspondences that still have a pair.
 constexpr double PRUNE_REL = 1e-22;
+constexpr unsigned RM_ROW = 0x3fffu, RM_CHUNK = 0x1ffu;   // PairView::rowmap fields: N <= 16383 rows, T <= 512 chunks
+constexpr int RM_C0 = 14, RM_C1 = 23;
+static_assert(RP_THREADS <= 512, "rowmap holds 9-bit chunk indices");
 
 static long long g_launches = 0;
 
@@ -445,7 +449,7 @@ struct PairView {
     uint16_t* cols_s; double* vals_s; int ism;   // shared-memory copy of the entries with k % E < ism (same indexing)
                          // cols word: column (14 bits) | bit 15 = first entry of its row | bit 14 = last entry
     int E, nnz, nrows;   // non-zeros per thread chunk, total directed non-zeros, rows with non-zeros
-    unsigned* rowmap;    // [nrows] shared: row id | first chunk << 16 | last chunk << 24
+    unsigned* rowmap;    // [nrows] shared: row id (14 bits) | first chunk << 14 (9 bits) | last chunk << 23 (9 bits)
     double* S;           // [2*nrows] shared: row sums (s1,s2) of rows lying inside one chunk
     // shared-memory vectors
     double *aP, *aN, *res, *ua, *ub, *sv;
@@ -466,7 +470,7 @@ __device__ void horn_fit(Shared& sh, const PairView& pv, double mean_div, int& r
         double a0 = 0, a1 = 0, a2 = 0, a3 = 0, a4 = 0, a5 = 0, a6 = 0;
         if (warp == 0) {
             for (int cr = lane; cr < pv.nrows; cr += 32) {
-                const int c = pv.rowmap[cr] & 0xffffu;
+                const int c = pv.rowmap[cr] & RM_ROW;
                 double wp = pv.aP[c];
                 a0 += wp;
                 a1 += wp * geo[G_PX * gs + c]; a2 += wp * geo[G_PY * gs + c]; a3 += wp * geo[G_PZ * gs + c];
@@ -474,7 +478,7 @@ __device__ void horn_fit(Shared& sh, const PairView& pv, double mean_div, int& r
             }
         } else if (warp == 1) {
             for (int cr = lane; cr < pv.nrows; cr += 32) {
-                const int c = pv.rowmap[cr] & 0xffffu;
+                const int c = pv.rowmap[cr] & RM_ROW;
                 double wp = pv.aP[c];
                 double qx = geo[G_QX * gs + c], qy = geo[G_QY * gs + c], qz = geo[G_QZ * gs + c];
                 double wpx = wp * geo[G_PX * gs + c], wpy = wp * geo[G_PY * gs + c];
@@ -482,7 +486,7 @@ __device__ void horn_fit(Shared& sh, const PairView& pv, double mean_div, int& r
             }
         } else if (warp == 2) {
             for (int cr = lane; cr < pv.nrows; cr += 32) {
-                const int c = pv.rowmap[cr] & 0xffffu;
+                const int c = pv.rowmap[cr] & RM_ROW;
                 double wpz = pv.aP[c] * geo[G_PZ * gs + c];
                 double wnx = pv.aN[c] * geo[G_NX * gs + c];
                 double mx = geo[G_MX * gs + c], my = geo[G_MY * gs + c], mz = geo[G_MZ * gs + c];
@@ -491,7 +495,7 @@ __device__ void horn_fit(Shared& sh, const PairView& pv, double mean_div, int& r
             }
         } else {
             for (int cr = lane; cr < pv.nrows; cr += 32) {
-                const int c = pv.rowmap[cr] & 0xffffu;
+                const int c = pv.rowmap[cr] & RM_ROW;
                 double wn = pv.aN[c];
                 double wny = wn * geo[G_NY * gs + c], wnz = wn * geo[G_NZ * gs + c];
                 double mx = geo[G_MX * gs + c], my = geo[G_MY * gs + c], mz = geo[G_MZ * gs + c];
@@ -513,7 +517,7 @@ __device__ void horn_fit(Shared& sh, const PairView& pv, double mean_div, int& r
 #pragma unroll
     for (int k = 0; k < NSUM; ++k) acc[k] = 0.0;
     for (int cr = tid; cr < pv.nrows; cr += T) {
-        const int c = pv.rowmap[cr] & 0xffffu;
+        const int c = pv.rowmap[cr] & RM_ROW;
         double wp = pv.aP[c], wn = pv.aN[c];
         double px = geo[G_PX * gs + c], py = geo[G_PY * gs + c], pz = geo[G_PZ * gs + c];
         double qx = geo[G_QX * gs + c], qy = geo[G_QY * gs + c], qz = geo[G_QZ * gs + c];
@@ -600,7 +604,7 @@ __device__ void residual_pass(const Shared& sh, const PairView& pv, double mu, b
     const Pose& P = sh.pose;
     const double* geo = pv.geo; const int gs = pv.gstride;
     for (int cr = threadIdx.x; cr < pv.nrows; cr += T) {
-        const int c = pv.rowmap[cr] & 0xffffu;       // only correspondences that still have a pair carry weight
+        const int c = pv.rowmap[cr] & RM_ROW;       // only correspondences that still have a pair carry weight
         double px = geo[G_PX * gs + c] - P.sm[0], py = geo[G_PY * gs + c] - P.sm[1], pz = geo[G_PZ * gs + c] - P.sm[2];
         double qx = geo[G_QX * gs + c] - P.tm[0], qy = geo[G_QY * gs + c] - P.tm[1], qz = geo[G_QZ * gs + c] - P.tm[2];
         double dx = P.R[0] * px + P.R[1] * py + P.R[2] * pz - qx;
@@ -705,7 +709,7 @@ __device__ __forceinline__ void csr_walk(Shared& sh, const PairView& pv, F& f) {
     __syncthreads();
     for (int cr = t; cr < pv.nrows; cr += T) {
         const unsigned info = pv.rowmap[cr];
-        const int p = info & 0xffffu, t0 = (info >> 16) & 0xffu, t1 = info >> 24;
+        const int p = info & RM_ROW, t0 = (info >> RM_C0) & RM_CHUNK, t1 = info >> RM_C1;
         double s1, s2;
         if (t0 == t1) { s1 = pv.S[2 * cr]; s2 = pv.S[2 * cr + 1]; }
         else {
@@ -762,6 +766,71 @@ struct MatVecStep {           // out = S (diag(h) W + W diag(h)) S in
         out[p] = y;
     }
 };
+
+// Largest eigenpair of the symmetric Rayleigh-Ritz matrix of the accelerated eigen iteration (3x3, or its leading 2x2 block
+// when n == 2).  2x2: closed form.  3x3: Newton on the characteristic cubic from the Gershgorin upper bound (for a real-rooted
+// polynomial the iterates decrease monotonically to the largest root), eigenvector = the largest cross product of two rows of
+// B - theta I, one Rayleigh-quotient refinement.  ~200 flops with short dependency chains instead of the ~1500 of a Jacobi
+// solve; returns false (caller falls back to Jacobi) when Newton does not settle or the eigenvector is not resolved.
+__device__ __forceinline__ bool ritz_max(const double B[4][4], int n, double a[3], double* theta_out) {
+    if (n == 2) {
+        const double p = B[0][0], q = B[1][1], o = B[0][1];
+        const double hd = 0.5 * (p - q), rad = sqrt(hd * hd + o * o);
+        const double th = 0.5 * (p + q) + rad;
+        // eigenvector (o, th - p) or (th - q, o): take the one built from the larger difference
+        double v0, v1;
+        if (hd >= 0.0) { v0 = th - q; v1 = o; } else { v0 = o; v1 = th - p; }
+        const double n2 = v0 * v0 + v1 * v1;
+        if (!(n2 > 0.0) || !isfinite(n2)) return false;
+        const double inv = rsqrt(n2);
+        a[0] = v0 * inv; a[1] = v1 * inv; a[2] = 0.0;
+        *theta_out = th;
+        return true;
+    }
+    const double b00 = B[0][0], b11 = B[1][1], b22 = B[2][2], b01 = B[0][1], b02 = B[0][2], b12 = B[1][2];
+    const double ub = fmax(fmax(b00 + fabs(b01) + fabs(b02), b11 + fabs(b01) + fabs(b12)), b22 + fabs(b02) + fabs(b12));
+    const double sc = fabs(b00) + fabs(b11) + fabs(b22) + fabs(b01) + fabs(b02) + fabs(b12);
+    if (!(sc > 0.0) || !isfinite(sc)) return false;
+    // shifted matrix C = B - ub I (eigenvalues <= 0): the cubic is evaluated in the small quantity mu = theta - ub
+    const double c00 = b00 - ub, c11 = b11 - ub, c22 = b22 - ub;
+    const double k2 = c00 + c11 + c22;                                                          // trace
+    const double k1 = (c00 * c11 - b01 * b01) + (c00 * c22 - b02 * b02) + (c11 * c22 - b12 * b12);
+    const double k0 = c00 * (c11 * c22 - b12 * b12) - b01 * (b01 * c22 - b12 * b02) + b02 * (b01 * b12 - c11 * b02);   // det
+    double mu = 0.0;                                       // p(mu) = mu^3 - k2 mu^2 + k1 mu - k0, largest root <= 0
+    bool ok = false;
+    for (int it = 0; it < 80; ++it) {
+        const double pm = ((mu - k2) * mu + k1) * mu - k0;
+        const double dp = (3.0 * mu - 2.0 * k2) * mu + k1;
+        if (!(dp > 0.0)) { ok = (pm == 0.0); break; }
+        const double step = pm / dp;
+        mu -= step;
+        if (fabs(step) <= 2.0e-16 * sc || (it > 0 && step <= 0.0)) { ok = true; break; }   // (a negative step is rounding noise)
+    }
+    if (!ok) return false;
+    double th = ub + mu;
+    double v[3];
+    for (int polish = 0; polish < 2; ++polish) {
+        const double r0[3] = {b00 - th, b01, b02}, r1[3] = {b01, b11 - th, b12}, r2[3] = {b02, b12, b22 - th};
+        const double x0[3] = {r0[1] * r1[2] - r0[2] * r1[1], r0[2] * r1[0] - r0[0] * r1[2], r0[0] * r1[1] - r0[1] * r1[0]};
+        const double x1[3] = {r0[1] * r2[2] - r0[2] * r2[1], r0[2] * r2[0] - r0[0] * r2[2], r0[0] * r2[1] - r0[1] * r2[0]};
+        const double x2[3] = {r1[1] * r2[2] - r1[2] * r2[1], r1[2] * r2[0] - r1[0] * r2[2], r1[0] * r2[1] - r1[1] * r2[0]};
+        const double n0 = x0[0] * x0[0] + x0[1] * x0[1] + x0[2] * x0[2];
+        const double n1 = x1[0] * x1[0] + x1[1] * x1[1] + x1[2] * x1[2];
+        const double n2 = x2[0] * x2[0] + x2[1] * x2[1] + x2[2] * x2[2];
+        double nb = n0; v[0] = x0[0]; v[1] = x0[1]; v[2] = x0[2];
+        if (n1 > nb) { nb = n1; v[0] = x1[0]; v[1] = x1[1]; v[2] = x1[2]; }
+        if (n2 > nb) { nb = n2; v[0] = x2[0]; v[1] = x2[1]; v[2] = x2[2]; }
+        // |cross| ~ (theta - theta_2)(theta - theta_3): unresolved when the two leading Ritz values coincide to rounding
+        if (!(nb > 1e-24 * sc * sc * sc * sc) || !isfinite(nb)) return false;
+        const double inv = rsqrt(nb);
+        v[0] *= inv; v[1] *= inv; v[2] *= inv;
+        const double w0 = b00 * v[0] + b01 * v[1] + b02 * v[2], w1 = b01 * v[0] + b11 * v[1] + b12 * v[2], w2 = b02 * v[0] + b12 * v[1] + b22 * v[2];
+        th = v[0] * w0 + v[1] * w1 + v[2] * w2;            // Rayleigh quotient: second-order accurate in the vector error
+    }
+    a[0] = v[0]; a[1] = v[1]; a[2] = v[2];
+    *theta_out = th;
+    return true;
+}
 
 constexpr int PI_SWITCH = 48;       // ROBUST variant: plain power steps before the accelerated iteration takes over
 constexpr int PI_FAST_CAP = 192;    // fast variant: power steps after which a pair is handed to the ROBUST variant (which redoes the
@@ -850,18 +919,21 @@ __device__ __forceinline__ int lopcg_continue(Shared& sh, const PairView& pv, do
                 B[2][2] = (d[4] - 2.0 * d[5] * d[2] - 2.0 * d[6] * d[3] + d[5] * d[5] * lam + 2.0 * d[5] * d[6] * d[0] + d[6] * d[6] * d[1]) * ninv * ninv;
             }
         }
-        double low = fmin(fmin(B[0][0] - fabs(B[0][1]) - fabs(B[0][2]), B[1][1] - fabs(B[0][1]) - fabs(B[1][2])),
-                          B[2][2] - fabs(B[0][2]) - fabs(B[1][2])) - 1.0 - fabs(lam);
-        if (!use_p) B[2][2] = low - 1.0;                 // decoupled filler rows below the spectrum
-        B[3][3] = low - 2.0;
         double a[4];
-        jacobi4_max(B, a);
-        if (a[0] < 0.0) { a[0] = -a[0]; a[1] = -a[1]; a[2] = -a[2]; }
         double theta = 0.0;
+        if (!ritz_max(B, use_p ? 3 : 2, a, &theta)) {     // (every thread sees the same B: the branch is uniform)
+            double low = fmin(fmin(B[0][0] - fabs(B[0][1]) - fabs(B[0][2]), B[1][1] - fabs(B[0][1]) - fabs(B[1][2])),
+                              B[2][2] - fabs(B[0][2]) - fabs(B[1][2])) - 1.0 - fabs(lam);
+            if (!use_p) B[2][2] = low - 1.0;             // decoupled filler rows below the spectrum
+            B[3][3] = low - 2.0;
+            jacobi4_max(B, a);
+            theta = 0.0;
 #pragma unroll
-        for (int i = 0; i < 3; ++i)
+            for (int i = 0; i < 3; ++i)
 #pragma unroll
-            for (int j = 0; j < 3; ++j) theta += a[i] * B[i][j] * a[j];
+                for (int j = 0; j < 3; ++j) theta += a[i] * B[i][j] * a[j];
+        }
+        if (a[0] < 0.0) { a[0] = -a[0]; a[1] = -a[1]; a[2] = -a[2]; }
         const double c2 = use_p ? a[2] * ninv : 0.0;
         const double c1 = use_p ? a[1] - c2 * d[6] : a[1];
         const double c0 = use_p ? a[0] - c2 * d[5] : a[0];
@@ -957,7 +1029,7 @@ __device__ void x_degrees(Shared& sh, const PairView& pv, double mu) {
 
 // res <- h = max(0, OFFSET - res)   (rpmodule.py:265-266: a = w*(offset - r), clipped at 0)
 __device__ void residual_to_h(const PairView& pv) {
-    for (int cr = threadIdx.x; cr < pv.nrows; cr += T) { const int c = pv.rowmap[cr] & 0xffffu; pv.res[c] = fmax(0.0, OFFSET - pv.res[c]); }
+    for (int cr = threadIdx.x; cr < pv.nrows; cr += T) { const int c = pv.rowmap[cr] & RM_ROW; pv.res[c] = fmax(0.0, OFFSET - pv.res[c]); }
     __syncthreads();
 }
 
@@ -1164,9 +1236,14 @@ __global__ void __launch_bounds__(T, RP_MIN_BLOCKS) rp_solve_kernel(const SolveA
                 // memory as warp-wide broadcasts, and distance, soft-match norm and the top-k list are all thread-local --
                 // no shuffles, no per-(i,j) division (candidates are ranked by dij * (1/den), a monotone image of the
                 // reference's exp(-dij/den); the exact quotient is only formed for entries that reach the norm or the list).
+                // The 512-thread build gives a source keypoint QA = 4 adjacent lanes, each scanning a quarter of the targets; the
+                // four sorted lists are merged with a shuffle butterfly under the same (key, index) order the sequential scan
+                // produces, and the norm is the four partial sums added in lane order.
                 const double rden_obs = 1.0 / par.feat_den_obs, rden_any = 1.0 / par.feat_den;
-                for (int i0 = 0; i0 < ns; i0 += T) {
-                    const int i = i0 + tid;
+                constexpr int QA = T >= 512 ? 4 : 1;
+                constexpr int RPP = T / QA;
+                for (int i0 = 0; i0 < ns; i0 += RPP) {
+                    const int i = i0 + tid / QA, q = tid % QA;
                     const bool act = i < ns;
                     const int ic = act ? i : ns - 1;
                     unsigned long long sreg[16];
@@ -1186,7 +1263,8 @@ __global__ void __launch_bounds__(T, RP_MIN_BLOCKS) rp_solve_kernel(const SolveA
 #pragma unroll
                     for (int k = 0; k < KMAX; ++k) { lk[k] = CUDART_INF; li[k] = 0x7fffffff; }
                     double ss = 0.0;
-                    for (int j = 0; j < nt; ++j) {
+                    const int jq0 = QA == 1 ? 0 : (nt * q) / QA, jq1 = QA == 1 ? nt : (nt * (q + 1)) / QA;
+                    for (int j = jq0; j < jq1; ++j) {
                         float sq[32];
                         sqdiff32(sreg, tfeat + j * ts, sq);
                         const float dij = seq_sum ? sum32_seq(sq) : sum32_numpy(sq);                       // :355
@@ -1207,6 +1285,28 @@ __global__ void __launch_bounds__(T, RP_MIN_BLOCKS) rp_solve_kernel(const SolveA
                             }
                         }
                     }
+                    if (QA > 1) {
+#pragma unroll
+                        for (int x = 1; x < QA; x <<= 1) {
+                            double ok[KMAX]; int oi[KMAX];
+#pragma unroll
+                            for (int k = 0; k < KMAX; ++k) { ok[k] = shfl_xor_d(lk[k], x); oi[k] = __shfl_xor_sync(0xffffffffu, li[k], x); }
+#pragma unroll
+                            for (int k2 = 0; k2 < KMAX; ++k2) {
+                                double ck = ok[k2]; int ci = oi[k2];
+                                if (ck < lk[KMAX - 1] || (ck == lk[KMAX - 1] && ci < li[KMAX - 1])) {
+#pragma unroll
+                                    for (int k = 0; k < KMAX; ++k) {
+                                        if (ck < lk[k] || (ck == lk[k] && ci < li[k])) { const double tk = lk[k]; const int ti = li[k]; lk[k] = ck; li[k] = ci; ck = tk; ci = ti; }
+                                    }
+                                }
+                            }
+                        }
+                        double tot = 0.0;
+#pragma unroll
+                        for (int qq = 0; qq < QA; ++qq) tot += __shfl_sync(0xffffffffu, ss, (lane & ~(QA - 1)) + qq);
+                        ss = tot;
+                    }
                     if (act) {
                         const double nm = sqrt(ss);                                                        // :359
                         // The index SET is decided by the keys unless the K-th and (K+1)-th candidate tie exactly, or selected
@@ -1218,10 +1318,11 @@ __global__ void __launch_bounds__(T, RP_MIN_BLOCKS) rp_solve_kernel(const SolveA
                             for (int k = 1; k < KMAX; ++k) if (k == K && lk[k] == lk[k - 1] && li[k] != 0x7fffffff) amb = true;
 #pragma unroll
                             for (int k = 0; k < KMAX; ++k) if (k == K - 1 && lk[k] > 745.13 && li[k] != 0x7fffffff) amb = true;
-                            if (amb) atomicAdd(&sh.ties, 1);
+                            if (amb && q == 0) atomicAdd(&sh.ties, 1);
                         }
 #pragma unroll
                         for (int k = 0; k < KMAX; ++k) {
+                            if ((k % QA) != q) continue;                          // the row's output entries are dealt over its lanes
                             if (k < K) {
                                 int idx = li[k];
                                 double f = 0.0;
@@ -1627,7 +1728,7 @@ __global__ void __launch_bounds__(T, RP_MIN_BLOCKS) rp_solve_kernel(const SolveA
             }
             for (int r = tid; r < N; r += T) {
                 int rs = pv.rowstart[r], re = pv.rowstart[r + 1];
-                if (re > rs) pv.rowmap[cidx[r]] = (unsigned)r | ((unsigned)(rs / E) << 16) | ((unsigned)((re - 1) / E) << 24);
+                if (re > rs) pv.rowmap[cidx[r]] = (unsigned)r | ((unsigned)(rs / E) << RM_C0) | ((unsigned)((re - 1) / E) << RM_C1);
                 else pv.geo[G_DEG * pv.gstride + r] = 0.0;
             }
             const double csr_thr = sh.scal[2];
@@ -1718,7 +1819,7 @@ __global__ void __launch_bounds__(T, RP_MIN_BLOCKS) rp_solve_kernel(const SolveA
         }
         if (tid == 0) {
             A.status[b] = RP_STATUS_OK;
-            if (st) { st[4] = tot_it; st[5] = max_it_seen; st[6] = not_conv | (sh.ties << 8); }
+            if (st) { st[4] = tot_it; st[5] = max_it_seen; st[6] = not_conv | (sh.ties << 8); if (ROBUST) st[7] |= 0x100; }
         }
     }
 }
@@ -1731,6 +1832,7 @@ struct Layout {
 };
 
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+constexpr int TPAD = 512;
 
 bool make_layout(int max_ns, int max_topk, long long edge_cap, size_t dyn_bytes, Layout* L) {
     long long Nmax = (long long)max_ns * max_topk;
@@ -1746,8 +1848,9 @@ bool make_layout(int max_ns, int max_topk, long long edge_cap, size_t dyn_bytes,
     L->o_edges = o; o = align_up(o + sizeof(unsigned) * edge_cap, 256);
     L->o_ew = o; o = align_up(o + sizeof(double) * edge_cap, 256);
     L->o_rowstart = o; o = align_up(o + sizeof(uint16_t) * Nmax * L->NWmax, 256);
-    L->o_cols = o; o = align_up(o + sizeof(uint16_t) * (2 * edge_cap + 2 * T), 256);     // lane-interleaved: up to T-1 pad
-    L->o_vals = o; o = align_up(o + sizeof(double) * (2 * edge_cap + 2 * T), 256);
+    L->o_cols = o; o = align_up(o + sizeof(uint16_t) * (2 * edge_cap + 2 * TPAD), 256);  // lane-interleaved: up to T-1 pad (TPAD: the
+                                                                                          // widest build, so both builds share one layout)
+    L->o_vals = o; o = align_up(o + sizeof(double) * (2 * edge_cap + 2 * TPAD), 256);
     L->o_dyn = o; o = align_up(o + dyn_bytes, 256);          // only for pairs whose vectors do not fit shared memory
     L->slot_bytes = o;
     return true;
@@ -1781,7 +1884,8 @@ bool make_smem_plan(long long Nmax_, int max_nt, int feat_dim, SmemPlan* S) {
     struct { int Nmax, NWmax; } L = {(int)Nmax_, (int)((Nmax_ + 31) / 32)};
     // ~227 KB per SM shared by RP_MIN_BLOCKS CTAs; the static part (struct Shared) is ~3-8 KB
     const size_t budget = (size_t)(220 * 1024) / RP_MIN_BLOCKS - 9 * 1024;
-    const size_t hard = 200 * 1024;
+    size_t hard = (size_t)227 * 1024 - sizeof(Shared) - 2048;     // dynamic + static shared memory of one CTA <= 227 KB
+    if (hard > (size_t)200 * 1024) hard = (size_t)200 * 1024;
     int ts = (feat_dim % 8 == 0) ? (feat_dim + 4) : (feat_dim | 1);   // 16-B aligned rows, (ts/4) odd -> conflict-free LDS.128
     size_t fe = (size_t)max_nt * ts * sizeof(float);
     size_t vec = align_up((size_t)8 * L.Nmax * sizeof(double) + (size_t)(2 * L.Nmax + 1) * sizeof(int), 16);   // 6 vectors + S + rowstart + rowmap
@@ -1820,9 +1924,10 @@ LaunchPlan make_launch_plan(const SmemPlan& S, const Layout& L, int grid) {
     LaunchPlan P = {S.bytes, S.mask_in_smem, 0, 0};
     if (S.dyn_in_global) return P;
     const int per_sm = (grid + sm_count() - 1) / sm_count();
-    if (per_sm >= RP_MIN_BLOCKS) return P;
-    size_t avail = (size_t)(227 * 1024) / (size_t)per_sm - 13 * 1024;           // static part ~10.6 KB + 1 KB reserved per CTA
-    if (avail > (size_t)212 * 1024) avail = (size_t)212 * 1024;
+    if (RP_MIN_BLOCKS > 1 && per_sm >= RP_MIN_BLOCKS) return P;
+    const size_t stat = sizeof(Shared) + 2560;                                  // static part + 1 KB reserved per CTA + slack
+    size_t avail = (size_t)(227 * 1024) / (size_t)per_sm - stat;
+    if (avail > (size_t)225 * 1024 - stat) avail = (size_t)225 * 1024 - stat;
     // the CSR first (read ~250 times per pair), the bit mask (written in D, read once in E) only if both fit
     const size_t mask = (size_t)L.Nmax * L.NWmax * sizeof(unsigned);
     const long long want = (2 * L.edge_cap + 2 * T + 7) & ~7ll;
@@ -1856,13 +1961,210 @@ int default_slots_uncached(size_t smem_bytes) {
     return sms * per;
 }
 
+
+// Two builds of this file make up the solver: the default one (T = 128, four CTAs per SM: throughput for large batches, and
+// every extern "C" entry point) and rp_solver_wide.cu (RP_WIDE_TU: T = 512, one CTA per SM), whose two launch functions below
+// take small batches -- with fewer scan pairs than SMs x 2 a pair gets a whole SM's threads instead of a quarter of them.  Same
+// kernel source, same workspace layout; reduction trees differ with T, so the two builds agree to rounding (1e-13 on the
+// poses), not bitwise: a batch goes through exactly one of them, chosen from its size alone (rp_solver_wide_max).
+constexpr int RP_WIDE_DECLINED = 1000;       // the wide build cannot take this shape (vectors beyond shared memory): use T = 128
+int solve_batch_impl(int B, const int32_t* off_s, const int32_t* off_t,
+                      const double* pc_s, const double* nrm_s, const float* feat_s, const double* w_s,
+                      const double* pc_t, const double* nrm_t, const float* feat_t, const double* w_t,
+                      int feat_dim, const rp_params* params, const int32_t* param_idx,
+                      const int32_t* zero_row_topk, const int32_t* feat_sum_order,
+                      int max_ns, int max_nt, int max_topk,
+                      int n_slots, int64_t edge_cap, void* workspace, size_t workspace_bytes,
+                      double* T_out, int32_t* status, int32_t* stats,
+                      int stop_after, const rp_debug* dbg, void* stream_) {
+    if (B < 0 || !off_s || !off_t || !feat_s || !feat_t || !w_s || !w_t || !params || !workspace || !status)
+        return RP_ERR_INVALID_ARG;
+    if (stop_after == RP_STAGE_SOLVE && !T_out) return RP_ERR_INVALID_ARG;
+    if (stop_after != RP_STAGE_TOPK && (!pc_s || !pc_t || !nrm_s || !nrm_t)) return RP_ERR_INVALID_ARG;
+    if (stop_after < RP_STAGE_TOPK || stop_after > RP_STAGE_SOLVE) return RP_ERR_INVALID_ARG;
+    if (max_topk > RP_MAX_TOPK || max_topk < 1 || feat_dim < 1 || feat_dim > RP_MAX_FEAT_DIM) return RP_ERR_UNSUPPORTED;
+    if (B == 0) return RP_OK;
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    SmemPlan S;
+    if (!make_smem_plan((long long)max_ns * max_topk, max_nt, feat_dim, &S)) return RP_ERR_UNSUPPORTED;
+    Layout L;
+    if (!make_layout(max_ns, max_topk, edge_cap, S.dyn_bytes, &L)) return RP_ERR_UNSUPPORTED;
+#ifdef RP_WIDE_TU
+    if (S.dyn_in_global) return RP_WIDE_DECLINED;
+    {
+        const int mine = default_slots(S.bytes);
+        if (mine < 0) { cudaGetLastError(); return RP_ERR_NO_DEVICE; }
+        if (n_slots <= 0 || n_slots > mine) n_slots = mine;
+    }
+#else
+    if (n_slots <= 0) {
+        n_slots = default_slots(S.bytes);
+        if (n_slots < 0) { cudaGetLastError(); return RP_ERR_NO_DEVICE; }
+    }
+#endif
+    const int grid = B < n_slots ? B : n_slots;
+    const LaunchPlan P = make_launch_plan(S, L, grid);
+    if (!ensure_smem_attr(P.bytes)) return RP_ERR_CUDA;
+    if (workspace_bytes < 256 + (size_t)n_slots * L.slot_bytes) return RP_ERR_WORKSPACE_TOO_SMALL;
+    SolveArgs a;
+    a.B = B; a.off_s = off_s; a.off_t = off_t;
+    a.pc_s = pc_s; a.nrm_s = nrm_s; a.feat_s = feat_s; a.w_s = w_s;
+    a.pc_t = pc_t; a.nrm_t = nrm_t; a.feat_t = feat_t; a.w_t = w_t;
+    a.feat_dim = feat_dim; a.params = params; a.param_idx = param_idx; a.zero_row_topk = zero_row_topk; a.feat_sum_order = feat_sum_order;
+    a.solve_only = 0; a.node_wp = nullptr; a.node_wn = nullptr; a.edge_off = nullptr; a.edge_rc = nullptr; a.edge_w = nullptr;
+    a.max_topk = max_topk; a.edge_cap = L.edge_cap;
+    a.ws = static_cast<char*>(workspace); a.slot_bytes = L.slot_bytes;
+    a.o_geo = L.o_geo; a.o_cj = L.o_cj; a.o_mask = L.o_mask; a.o_edges = L.o_edges; a.o_ew = L.o_ew;
+    a.o_rowstart = L.o_rowstart; a.o_cols = L.o_cols; a.o_vals = L.o_vals;
+    a.Nmax = L.Nmax; a.NWmax = L.NWmax;
+    a.T_out = T_out; a.status = status; a.stats = stats;
+    a.stop_after = stop_after;
+    a.has_dbg = dbg ? 1 : 0;
+    if (dbg) a.dbg = *dbg; else { rp_debug z = {}; a.dbg = z; }
+    a.mask_in_smem = P.mask_in_smem; a.tfeat_stride = S.tfeat_stride; a.sm_mask_off = S.mask_off;
+    a.csr_smem_cap = P.csr_cap; a.sm_csr_off = P.csr_off;
+    a.dyn_in_global = S.dyn_in_global; a.o_dyn = L.o_dyn;
+    if (cudaMemsetAsync(workspace, 0, 256, stream) != cudaSuccess) { cudaGetLastError(); return RP_ERR_CUDA; }
+    if (S.dyn_in_global) rp_solve_kernel<false, true><<<grid, T, P.bytes, stream>>>(a);
+    else rp_solve_kernel<false, false><<<grid, T, P.bytes, stream>>>(a);
+    ++g_launches;
+    if (a.stop_after == RP_STAGE_SOLVE) {                // pairs whose eigen iteration needs the accelerated method
+        if (S.dyn_in_global) rp_solve_kernel<true, true><<<grid, T, P.bytes, stream>>>(a);
+        else rp_solve_kernel<true, false><<<grid, T, P.bytes, stream>>>(a);
+        ++g_launches;
+    }
+    if (cudaGetLastError() != cudaSuccess) return RP_ERR_CUDA;
+    return RP_OK;
+}
+
+
+int spectral_irls_impl(int B, const int32_t* node_off,
+                           const double* sp, const double* sn, const double* tp, const double* tn,
+                           const double* node_wp, const double* node_wn,
+                           const int32_t* edge_off, const int32_t* edge_rc, const double* edge_w,
+                           const rp_params* params, const int32_t* param_idx, int max_nodes,
+                           int n_slots, int64_t edge_cap, void* workspace, size_t workspace_bytes,
+                           double* T_out, int32_t* status, int32_t* stats, void* stream_) {
+    if (B < 0 || !node_off || !sp || !sn || !tp || !tn || !params || !workspace || !T_out || !status) return RP_ERR_INVALID_ARG;
+    if (!edge_off && !(node_wp && node_wn)) return RP_ERR_INVALID_ARG;
+    if (edge_off && (!edge_rc || !edge_w)) return RP_ERR_INVALID_ARG;
+    if (B == 0) return RP_OK;
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    SmemPlan S;
+    if (!make_smem_plan(max_nodes, 1, 8, &S)) return RP_ERR_UNSUPPORTED;
+    Layout L;
+    if (!make_layout(max_nodes, 1, edge_cap, S.dyn_bytes, &L)) return RP_ERR_UNSUPPORTED;
+#ifdef RP_WIDE_TU
+    if (S.dyn_in_global) return RP_WIDE_DECLINED;
+    {
+        const int mine = default_slots(S.bytes);
+        if (mine < 0) { cudaGetLastError(); return RP_ERR_NO_DEVICE; }
+        if (n_slots <= 0 || n_slots > mine) n_slots = mine;
+    }
+#else
+    if (n_slots <= 0) {
+        n_slots = default_slots(S.bytes);
+        if (n_slots < 0) { cudaGetLastError(); return RP_ERR_NO_DEVICE; }
+    }
+#endif
+    const int grid = B < n_slots ? B : n_slots;
+    const LaunchPlan P = make_launch_plan(S, L, grid);
+    if (!ensure_smem_attr(P.bytes)) return RP_ERR_CUDA;
+    if (workspace_bytes < 256 + (size_t)n_slots * L.slot_bytes) return RP_ERR_WORKSPACE_TOO_SMALL;
+    SolveArgs a = {};
+    a.B = B; a.off_s = node_off; a.off_t = node_off;
+    a.pc_s = sp; a.nrm_s = sn; a.pc_t = tp; a.nrm_t = tn;
+    a.feat_dim = 8; a.params = params; a.param_idx = param_idx;
+    a.solve_only = 1; a.node_wp = node_wp; a.node_wn = node_wn; a.edge_off = edge_off; a.edge_rc = edge_rc; a.edge_w = edge_w;
+    a.max_topk = 1; a.edge_cap = L.edge_cap;
+    a.ws = static_cast<char*>(workspace); a.slot_bytes = L.slot_bytes;
+    a.o_geo = L.o_geo; a.o_cj = L.o_cj; a.o_mask = L.o_mask; a.o_edges = L.o_edges; a.o_ew = L.o_ew;
+    a.o_rowstart = L.o_rowstart; a.o_cols = L.o_cols; a.o_vals = L.o_vals;
+    a.Nmax = L.Nmax; a.NWmax = L.NWmax;
+    a.T_out = T_out; a.status = status; a.stats = stats;
+    a.stop_after = RP_STAGE_SOLVE; a.has_dbg = 0;
+    a.mask_in_smem = P.mask_in_smem; a.tfeat_stride = S.tfeat_stride; a.sm_mask_off = S.mask_off;
+    a.csr_smem_cap = P.csr_cap; a.sm_csr_off = P.csr_off;
+    a.dyn_in_global = S.dyn_in_global; a.o_dyn = L.o_dyn;
+    if (cudaMemsetAsync(workspace, 0, 256, stream) != cudaSuccess) { cudaGetLastError(); return RP_ERR_CUDA; }
+    if (S.dyn_in_global) rp_solve_kernel<false, true><<<grid, T, P.bytes, stream>>>(a);
+    else rp_solve_kernel<false, false><<<grid, T, P.bytes, stream>>>(a);
+    ++g_launches;
+    if (a.stop_after == RP_STAGE_SOLVE) {                // pairs whose eigen iteration needs the accelerated method
+        if (S.dyn_in_global) rp_solve_kernel<true, true><<<grid, T, P.bytes, stream>>>(a);
+        else rp_solve_kernel<true, false><<<grid, T, P.bytes, stream>>>(a);
+        ++g_launches;
+    }
+    if (cudaGetLastError() != cudaSuccess) return RP_ERR_CUDA;
+    return RP_OK;
+}
+
+
+}  // namespace
+
+// launch functions of the T = 512 build (defined by rp_solver_wide.cu, called from the entry points below)
+int rp_wide_solve_batch_ex(int B, const int32_t* off_s, const int32_t* off_t,
+                      const double* pc_s, const double* nrm_s, const float* feat_s, const double* w_s,
+                      const double* pc_t, const double* nrm_t, const float* feat_t, const double* w_t,
+                      int feat_dim, const rp_params* params, const int32_t* param_idx,
+                      const int32_t* zero_row_topk, const int32_t* feat_sum_order,
+                      int max_ns, int max_nt, int max_topk,
+                      int n_slots, int64_t edge_cap, void* workspace, size_t workspace_bytes,
+                      double* T_out, int32_t* status, int32_t* stats,
+                      int stop_after, const rp_debug* dbg, void* stream_);
+int rp_wide_spectral_irls_solve(int B, const int32_t* node_off,
+                           const double* sp, const double* sn, const double* tp, const double* tn,
+                           const double* node_wp, const double* node_wn,
+                           const int32_t* edge_off, const int32_t* edge_rc, const double* edge_w,
+                           const rp_params* params, const int32_t* param_idx, int max_nodes,
+                           int n_slots, int64_t edge_cap, void* workspace, size_t workspace_bytes,
+                           double* T_out, int32_t* status, int32_t* stats, void* stream_);
+long long rp_wide_launch_count();
+
+#ifdef RP_WIDE_TU
+int rp_wide_solve_batch_ex(int B, const int32_t* off_s, const int32_t* off_t,
+                      const double* pc_s, const double* nrm_s, const float* feat_s, const double* w_s,
+                      const double* pc_t, const double* nrm_t, const float* feat_t, const double* w_t,
+                      int feat_dim, const rp_params* params, const int32_t* param_idx,
+                      const int32_t* zero_row_topk, const int32_t* feat_sum_order,
+                      int max_ns, int max_nt, int max_topk,
+                      int n_slots, int64_t edge_cap, void* workspace, size_t workspace_bytes,
+                      double* T_out, int32_t* status, int32_t* stats,
+                      int stop_after, const rp_debug* dbg, void* stream_) {
+    return solve_batch_impl(B, off_s, off_t, pc_s, nrm_s, feat_s, w_s, pc_t, nrm_t, feat_t, w_t, feat_dim, params, param_idx, zero_row_topk, feat_sum_order, max_ns, max_nt, max_topk, n_slots, edge_cap, workspace, workspace_bytes, T_out, status, stats, stop_after, dbg, stream_);
+}
+int rp_wide_spectral_irls_solve(int B, const int32_t* node_off,
+                           const double* sp, const double* sn, const double* tp, const double* tn,
+                           const double* node_wp, const double* node_wn,
+                           const int32_t* edge_off, const int32_t* edge_rc, const double* edge_w,
+                           const rp_params* params, const int32_t* param_idx, int max_nodes,
+                           int n_slots, int64_t edge_cap, void* workspace, size_t workspace_bytes,
+                           double* T_out, int32_t* status, int32_t* stats, void* stream_) {
+    return spectral_irls_impl(B, node_off, sp, sn, tp, tn, node_wp, node_wn, edge_off, edge_rc, edge_w, params, param_idx, max_nodes, n_slots, edge_cap, workspace, workspace_bytes, T_out, status, stats, stream_);
+}
+long long rp_wide_launch_count() { return g_launches; }
+#else
+
+namespace {
+// Batches of at most this many scan pairs run on the T = 512 build (0: never).  Default = the SM count: one wave of whole-SM
+// pairs (measured, N = 515: 0.42 vs 0.53 ms up to 148 pairs; at 222 pairs the second wave makes it 0.82 vs 0.60 ms).
+// RP_SOLVER_WIDE_MAX in the environment or rp_solver_wide_max() override it.
+int g_wide_max = -1;
+int wide_max() {
+    if (g_wide_max < 0) {
+        const char* e = getenv("RP_SOLVER_WIDE_MAX");
+        g_wide_max = e ? atoi(e) : sm_count();
+        if (g_wide_max < 0) g_wide_max = 0;
+    }
+    return g_wide_max;
+}
 }  // namespace
 
 extern "C" {
 
 int rp_abi_version(void) { return RP_ABI_VERSION; }
 
-int64_t rp_launch_count(void) { return g_launches; }
+int64_t rp_launch_count(void) { return g_launches + rp_wide_launch_count(); }
 
 int rp_device_info(int* sm_count, int* cc_major, int* cc_minor, size_t* total_mem) {
     int dev = 0;
@@ -1912,55 +2214,17 @@ int rp_solve_batch_ex(int B, const int32_t* off_s, const int32_t* off_t,
                       int n_slots, int64_t edge_cap, void* workspace, size_t workspace_bytes,
                       double* T_out, int32_t* status, int32_t* stats,
                       int stop_after, const rp_debug* dbg, void* stream_) {
-    if (B < 0 || !off_s || !off_t || !feat_s || !feat_t || !w_s || !w_t || !params || !workspace || !status)
-        return RP_ERR_INVALID_ARG;
-    if (stop_after == RP_STAGE_SOLVE && !T_out) return RP_ERR_INVALID_ARG;
-    if (stop_after != RP_STAGE_TOPK && (!pc_s || !pc_t || !nrm_s || !nrm_t)) return RP_ERR_INVALID_ARG;
-    if (stop_after < RP_STAGE_TOPK || stop_after > RP_STAGE_SOLVE) return RP_ERR_INVALID_ARG;
-    if (max_topk > RP_MAX_TOPK || max_topk < 1 || feat_dim < 1 || feat_dim > RP_MAX_FEAT_DIM) return RP_ERR_UNSUPPORTED;
-    if (B == 0) return RP_OK;
-    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
-    SmemPlan S;
-    if (!make_smem_plan((long long)max_ns * max_topk, max_nt, feat_dim, &S)) return RP_ERR_UNSUPPORTED;
-    Layout L;
-    if (!make_layout(max_ns, max_topk, edge_cap, S.dyn_bytes, &L)) return RP_ERR_UNSUPPORTED;
-    if (n_slots <= 0) {
-        n_slots = default_slots(S.bytes);
-        if (n_slots < 0) { cudaGetLastError(); return RP_ERR_NO_DEVICE; }
+    if (B > 0 && B <= wide_max()) {
+        const int rc = rp_wide_solve_batch_ex(B, off_s, off_t, pc_s, nrm_s, feat_s, w_s, pc_t, nrm_t, feat_t, w_t, feat_dim, params, param_idx, zero_row_topk, feat_sum_order, max_ns, max_nt, max_topk, n_slots, edge_cap, workspace, workspace_bytes, T_out, status, stats, stop_after, dbg, stream_);
+        if (rc != RP_WIDE_DECLINED) return rc;
     }
-    const int grid = B < n_slots ? B : n_slots;
-    const LaunchPlan P = make_launch_plan(S, L, grid);
-    if (!ensure_smem_attr(P.bytes)) return RP_ERR_CUDA;
-    if (workspace_bytes < 256 + (size_t)n_slots * L.slot_bytes) return RP_ERR_WORKSPACE_TOO_SMALL;
-    SolveArgs a;
-    a.B = B; a.off_s = off_s; a.off_t = off_t;
-    a.pc_s = pc_s; a.nrm_s = nrm_s; a.feat_s = feat_s; a.w_s = w_s;
-    a.pc_t = pc_t; a.nrm_t = nrm_t; a.feat_t = feat_t; a.w_t = w_t;
-    a.feat_dim = feat_dim; a.params = params; a.param_idx = param_idx; a.zero_row_topk = zero_row_topk; a.feat_sum_order = feat_sum_order;
-    a.solve_only = 0; a.node_wp = nullptr; a.node_wn = nullptr; a.edge_off = nullptr; a.edge_rc = nullptr; a.edge_w = nullptr;
-    a.max_topk = max_topk; a.edge_cap = L.edge_cap;
-    a.ws = static_cast<char*>(workspace); a.slot_bytes = L.slot_bytes;
-    a.o_geo = L.o_geo; a.o_cj = L.o_cj; a.o_mask = L.o_mask; a.o_edges = L.o_edges; a.o_ew = L.o_ew;
-    a.o_rowstart = L.o_rowstart; a.o_cols = L.o_cols; a.o_vals = L.o_vals;
-    a.Nmax = L.Nmax; a.NWmax = L.NWmax;
-    a.T_out = T_out; a.status = status; a.stats = stats;
-    a.stop_after = stop_after;
-    a.has_dbg = dbg ? 1 : 0;
-    if (dbg) a.dbg = *dbg; else { rp_debug z = {}; a.dbg = z; }
-    a.mask_in_smem = P.mask_in_smem; a.tfeat_stride = S.tfeat_stride; a.sm_mask_off = S.mask_off;
-    a.csr_smem_cap = P.csr_cap; a.sm_csr_off = P.csr_off;
-    a.dyn_in_global = S.dyn_in_global; a.o_dyn = L.o_dyn;
-    if (cudaMemsetAsync(workspace, 0, 256, stream) != cudaSuccess) { cudaGetLastError(); return RP_ERR_CUDA; }
-    if (S.dyn_in_global) rp_solve_kernel<false, true><<<grid, T, P.bytes, stream>>>(a);
-    else rp_solve_kernel<false, false><<<grid, T, P.bytes, stream>>>(a);
-    ++g_launches;
-    if (a.stop_after == RP_STAGE_SOLVE) {                // pairs whose eigen iteration needs the accelerated method
-        if (S.dyn_in_global) rp_solve_kernel<true, true><<<grid, T, P.bytes, stream>>>(a);
-        else rp_solve_kernel<true, false><<<grid, T, P.bytes, stream>>>(a);
-        ++g_launches;
-    }
-    if (cudaGetLastError() != cudaSuccess) return RP_ERR_CUDA;
-    return RP_OK;
+    return solve_batch_impl(B, off_s, off_t, pc_s, nrm_s, feat_s, w_s, pc_t, nrm_t, feat_t, w_t, feat_dim, params, param_idx, zero_row_topk, feat_sum_order, max_ns, max_nt, max_topk, n_slots, edge_cap, workspace, workspace_bytes, T_out, status, stats, stop_after, dbg, stream_);
+}
+
+int rp_solver_wide_max(int new_max) {
+    const int old = wide_max();
+    if (new_max >= 0) g_wide_max = new_max;
+    return old;
 }
 
 int rp_solve_batch(int B, const int32_t* off_s, const int32_t* off_t,
@@ -2021,49 +2285,11 @@ int rp_spectral_irls_solve(int B, const int32_t* node_off,
                            const rp_params* params, const int32_t* param_idx, int max_nodes,
                            int n_slots, int64_t edge_cap, void* workspace, size_t workspace_bytes,
                            double* T_out, int32_t* status, int32_t* stats, void* stream_) {
-    if (B < 0 || !node_off || !sp || !sn || !tp || !tn || !params || !workspace || !T_out || !status) return RP_ERR_INVALID_ARG;
-    if (!edge_off && !(node_wp && node_wn)) return RP_ERR_INVALID_ARG;
-    if (edge_off && (!edge_rc || !edge_w)) return RP_ERR_INVALID_ARG;
-    if (B == 0) return RP_OK;
-    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
-    SmemPlan S;
-    if (!make_smem_plan(max_nodes, 1, 8, &S)) return RP_ERR_UNSUPPORTED;
-    Layout L;
-    if (!make_layout(max_nodes, 1, edge_cap, S.dyn_bytes, &L)) return RP_ERR_UNSUPPORTED;
-    if (n_slots <= 0) {
-        n_slots = default_slots(S.bytes);
-        if (n_slots < 0) { cudaGetLastError(); return RP_ERR_NO_DEVICE; }
+    if (B > 0 && B <= wide_max()) {
+        const int rc = rp_wide_spectral_irls_solve(B, node_off, sp, sn, tp, tn, node_wp, node_wn, edge_off, edge_rc, edge_w, params, param_idx, max_nodes, n_slots, edge_cap, workspace, workspace_bytes, T_out, status, stats, stream_);
+        if (rc != RP_WIDE_DECLINED) return rc;
     }
-    const int grid = B < n_slots ? B : n_slots;
-    const LaunchPlan P = make_launch_plan(S, L, grid);
-    if (!ensure_smem_attr(P.bytes)) return RP_ERR_CUDA;
-    if (workspace_bytes < 256 + (size_t)n_slots * L.slot_bytes) return RP_ERR_WORKSPACE_TOO_SMALL;
-    SolveArgs a = {};
-    a.B = B; a.off_s = node_off; a.off_t = node_off;
-    a.pc_s = sp; a.nrm_s = sn; a.pc_t = tp; a.nrm_t = tn;
-    a.feat_dim = 8; a.params = params; a.param_idx = param_idx;
-    a.solve_only = 1; a.node_wp = node_wp; a.node_wn = node_wn; a.edge_off = edge_off; a.edge_rc = edge_rc; a.edge_w = edge_w;
-    a.max_topk = 1; a.edge_cap = L.edge_cap;
-    a.ws = static_cast<char*>(workspace); a.slot_bytes = L.slot_bytes;
-    a.o_geo = L.o_geo; a.o_cj = L.o_cj; a.o_mask = L.o_mask; a.o_edges = L.o_edges; a.o_ew = L.o_ew;
-    a.o_rowstart = L.o_rowstart; a.o_cols = L.o_cols; a.o_vals = L.o_vals;
-    a.Nmax = L.Nmax; a.NWmax = L.NWmax;
-    a.T_out = T_out; a.status = status; a.stats = stats;
-    a.stop_after = RP_STAGE_SOLVE; a.has_dbg = 0;
-    a.mask_in_smem = P.mask_in_smem; a.tfeat_stride = S.tfeat_stride; a.sm_mask_off = S.mask_off;
-    a.csr_smem_cap = P.csr_cap; a.sm_csr_off = P.csr_off;
-    a.dyn_in_global = S.dyn_in_global; a.o_dyn = L.o_dyn;
-    if (cudaMemsetAsync(workspace, 0, 256, stream) != cudaSuccess) { cudaGetLastError(); return RP_ERR_CUDA; }
-    if (S.dyn_in_global) rp_solve_kernel<false, true><<<grid, T, P.bytes, stream>>>(a);
-    else rp_solve_kernel<false, false><<<grid, T, P.bytes, stream>>>(a);
-    ++g_launches;
-    if (a.stop_after == RP_STAGE_SOLVE) {                // pairs whose eigen iteration needs the accelerated method
-        if (S.dyn_in_global) rp_solve_kernel<true, true><<<grid, T, P.bytes, stream>>>(a);
-        else rp_solve_kernel<true, false><<<grid, T, P.bytes, stream>>>(a);
-        ++g_launches;
-    }
-    if (cudaGetLastError() != cudaSuccess) return RP_ERR_CUDA;
-    return RP_OK;
+    return spectral_irls_impl(B, node_off, sp, sn, tp, tn, node_wp, node_wn, edge_off, edge_rc, edge_w, params, param_idx, max_nodes, n_slots, edge_cap, workspace, workspace_bytes, T_out, status, stats, stream_);
 }
 
 int rp_spectral_irls_workspace_bytes(int n_slots, int max_nodes, int64_t edge_cap, size_t* bytes) {
@@ -2071,3 +2297,4 @@ int rp_spectral_irls_workspace_bytes(int n_slots, int max_nodes, int64_t edge_ca
 }
 
 }  // extern "C"
+#endif  // RP_WIDE_TU
