@@ -26,8 +26,9 @@ class _Stager(object):
     def __init__(self):
         self.buf, self.event, self.pool = None, None, None
 
-    def upload(self, arrays, dev):
-        """arrays: numpy arrays / torch tensors; returns device tensors of the same shapes and dtypes (CUDA tensors pass through)."""
+    def upload(self, arrays, dev, stream=None):
+        """arrays: numpy arrays / torch tensors; returns device tensors of the same shapes and dtypes (CUDA tensors pass through).
+        ``stream``: a side stream for the copies (the caller makes its compute stream wait on ``self.event``)."""
         import torch
         from concurrent.futures import ThreadPoolExecutor
         out, jobs, total = [None] * len(arrays), [], 0
@@ -59,21 +60,27 @@ class _Stager(object):
                 hi = min(flat.size, lo + self.PIECE)
                 futs.append((self.pool.submit(np.copyto, hostv[off + lo:off + hi], flat[lo:hi]), dflat, off, lo, hi))
         with torch.cuda.device(dev):
-            for fut, dflat, off, lo, hi in futs:
-                fut.result()
-                dflat[lo:hi].copy_(self.buf[off + lo:off + hi], non_blocking=True)
-            self.event = torch.cuda.Event()
-            self.event.record()
+            cur = torch.cuda.current_stream()
+            st = stream or cur
+            if stream is not None:
+                stream.wait_stream(cur)                    # the destination tensors were allocated on the compute stream
+            with torch.cuda.stream(st):
+                for fut, dflat, off, lo, hi in futs:
+                    fut.result()
+                    dflat[lo:hi].copy_(self.buf[off + lo:off + hi], non_blocking=True)
+                self.event = torch.cuda.Event()
+                self.event.record(st)
         return out
 
 
-_stager = _Stager()
+_stagers = [_Stager(), _Stager()]      # two, so that filling one pinned buffer overlaps the DMA out of the other
+_copy_streams = {}
 
 
-def gather_primitives(feat, depth, normal, pts, weights, dataset):
+def gather_primitives(feat, depth, normal, pts, weights, dataset, raw=False):
     """feat: CUDA float32 [2B,C,160,640] (may be a channel slice of the network output); depth [2B,160,640], normal
     [2B,160,640,3] (CUDA, converted to float64); pts [2B,K,2] pixel (x,y) float64; weights [2B,K] (1.0 observed / 0.99).
-    -> DeviceBatch for PoseSolver.solve_device."""
+    -> DeviceBatch for PoseSolver.solve_device (``raw``: the gathered arrays themselves, [2B,K,.] in image order)."""
     import torch
     lib = _lib.load()
     n_img, C = feat.shape[0], feat.shape[1]
@@ -93,6 +100,16 @@ def gather_primitives(feat, depth, normal, pts, weights, dataset):
         _lib.check(lib.rp_gather_primitives(feat.data_ptr(), C, feat.stride(0), depth.data_ptr(), normal.data_ptr(), pts.data_ptr(),
                                             n_img, K, _util.dataset_id(dataset), pc.data_ptr(), nn.data_ptr(), desc.data_ptr(),
                                             torch.cuda.current_stream().cuda_stream), "rp_gather_primitives")
+    if raw:
+        return pc, nn, desc, weights
+
+    return _batch_from_gathered(pc, nn, desc, weights)
+
+
+def _batch_from_gathered(pc, nn, desc, weights):
+    """[2B,K,3] positions / normals, [2B,K,C] descriptors, [2B,K] weights in image order -> DeviceBatch of B pairs."""
+    n_img, K = pc.shape[0], pc.shape[1]
+    B = n_img // 2
 
     def side(a, k):
         return a.view(B, 2, K, -1)[:, k].reshape(B * K, -1)
@@ -121,47 +138,69 @@ def solve_from_maps(feat, depth, normal, pts, weights, para, dataset, solver=Non
     return T.cpu().numpy()
 
 
-def RelativePoseEstimationViaCompletion_batch(net, rgb, norm, depth, pts, weights, args):
+def RelativePoseEstimationViaCompletion_batch(net, rgb, norm, depth, pts, weights, args, chunk=None):
     """Batched rpmodule.RelativePoseEstimationViaCompletion (rpmodule.py:569-662) for B pairs with given keypoints.
 
     rgb [2B,160,640,3], norm [2B,160,640,3], depth [2B,160,640] (numpy or tensors; the complete scans), pts [2B,K,2],
     weights [2B,K]; args as in the reference (snumclass, featureDim, outputType, maskMethod, alterStep, dataset, para with
-    per-step sigma arrays).  Per alternation: one batched warp of all 2B views, one SCNet forward over all pairs, one blend,
-    one gather, one solve.  Returns [B,4,4] float64."""
+    per-step sigma arrays).  Per alternation: a batched warp of the 2B views, the SCNet forward, the blend and the gather run
+    over ``chunk`` pairs at a time (default: all B; the network's activation buffers are sized by it), then ONE solve over all B
+    pairs -- the solver's cost per pair falls with the batch (a pair alone occupies one SM).  Scans are uploaded once, chunk by
+    chunk on a copy stream, so the upload of chunk c+1 overlaps the first network pass of chunk c.  Returns [B,4,4] float64."""
     import copy
     import torch
     dev = next(net.parameters()).device
-    rgb, norm_gt, depth_gt, pts, weights = _stager.upload([rgb, norm, depth, np.asarray(pts, dtype=np.float64) if not torch.is_tensor(pts) else pts,
-                                                           np.asarray(weights, dtype=np.float64) if not torch.is_tensor(weights) else weights], dev)
     idx_f = 0
     for key, n in (('rgb', 3), ('n', 3), ('d', 1), ('s', args.snumclass)):
         if key in args.outputType:
             idx_f += n
     n_img = len(rgb)
     B = n_img // 2
-    with torch.no_grad():
-        full = torch.cat((rgb.float(), norm_gt.float(), depth_gt.float().unsqueeze(3)), 3).permute(0, 3, 1, 2).contiguous()   # [2B,7,h,w]
+    chunk = B if not chunk else max(1, min(int(chunk), B))
+    bounds = [(c0, min(B, c0 + chunk)) for c0 in range(0, B, chunk)]
+    as64 = lambda a: a if torch.is_tensor(a) else np.asarray(a, dtype=np.float64)
+    pts, weights = as64(pts), as64(weights)
+    solver = _solver.default_solver(dev)
+    state = {}
+
+    def prepare(ci, lo, hi):
+        """Upload the scans of pairs lo..hi and build their static network input (own view in channels 0..7)."""
+        sl = slice(2 * lo, 2 * hi)
+        with torch.cuda.device(dev):
+            cs = _copy_streams.setdefault(str(dev), torch.cuda.Stream(device=dev)) if len(bounds) > 1 else None
+            stg = _stagers[ci % 2]
+            rgb_d, norm_gt, depth_gt, pts_d, w_d = stg.upload([rgb[sl], norm[sl], depth[sl], pts[sl], weights[sl]], dev, stream=cs)
+            if cs is not None and stg.event is not None:
+                torch.cuda.current_stream().wait_event(stg.event)
+        full = torch.cat((rgb_d.float(), norm_gt.float(), depth_gt.float().unsqueeze(3)), 3).permute(0, 3, 1, 2).contiguous()   # [2b,7,h,w]
         vw, m, _geow = _util.apply_mask(full, args.maskMethod)
-        views = torch.cat((vw, (vw[:, 6:7] != 0).float()), 1)                                                    # [2B,8,h,w]
-        mask = m[:, 0].contiguous()
-        swap = (torch.arange(n_img, device=dev) ^ 1).to(torch.int32)   # the other scan of the pair
-        inp = torch.empty((n_img, 16, 160, 640), dtype=torch.float32, device=dev)
-        inp[:, :8] = views                                            # network input: own view | partner warped into this frame
+        inp = torch.empty((2 * (hi - lo), 16, 160, 640), dtype=torch.float32, device=dev)
+        inp[:, :7] = vw                                               # network input: own view | partner warped into this frame
+        inp[:, 7] = (vw[:, 6] != 0).float()
+        swap = (torch.arange(2 * (hi - lo), device=dev) ^ 1).to(torch.int32)   # the other scan of the pair
+        return dict(inp=inp, mask=m[:, 0].contiguous(), norm_gt=norm_gt, depth_gt=depth_gt, pts=pts_d.double(), w=w_d.double(), swap=swap)
+
+    with torch.no_grad():
         R_hat = np.tile(np.eye(4), (B, 1, 1))
-        solver = _solver.default_solver(dev)
         for alter_ in range(args.alterStep):
-            # view i receives the other scan warped into its frame: sources get the target moved by inv(R), targets the
-            # source moved by R (rpmodule.py:616-617); identity -> zeros inside the kernel
-            Rs = np.empty((n_img, 4, 4))
-            Rs[0::2] = np.linalg.inv(R_hat)
-            Rs[1::2] = R_hat
-            _util.warping_device(inp, Rs, args.dataset, out=inp[:, 8:], src_index=swap)       # reads channels 0..7, writes 8..15
-            f = _net_forward(net, inp)                                                                           # :619-623
-            nrm2, dep2 = _util.blend_completion_device(f, mask, norm_gt, depth_gt)                                # :628-634
             para_this = copy.copy(args.para)
             for name in ('sigmaAngle1', 'sigmaAngle2', 'sigmaDist', 'sigmaFeat'):
                 setattr(para_this, name, getattr(args.para, name)[alter_])
-            d = gather_primitives(f[:, idx_f:idx_f + args.featureDim], dep2, nrm2, pts, weights, args.dataset)
+            parts = []
+            for ci, (lo, hi) in enumerate(bounds):
+                if alter_ == 0:
+                    state[ci] = prepare(ci, lo, hi)
+                S = state[ci]
+                # view i receives the other scan warped into its frame: sources get the target moved by inv(R), targets the
+                # source moved by R (rpmodule.py:616-617); identity -> zeros inside the kernel
+                Rs = np.empty((2 * (hi - lo), 4, 4))
+                Rs[0::2] = np.linalg.inv(R_hat[lo:hi])
+                Rs[1::2] = R_hat[lo:hi]
+                _util.warping_device(S['inp'], Rs, args.dataset, out=S['inp'][:, 8:], src_index=S['swap'])   # reads channels 0..7, writes 8..15
+                f = _net_forward(net, S['inp'])                                                               # :619-623
+                nrm2, dep2 = _util.blend_completion_device(f, S['mask'], S['norm_gt'], S['depth_gt'])          # :628-634
+                parts.append(gather_primitives(f[:, idx_f:idx_f + args.featureDim], dep2, nrm2, S['pts'], S['w'], args.dataset, raw=True))
+            d = _batch_from_gathered(*[torch.cat([p[k] for p in parts], 0) if len(parts) > 1 else parts[0][k] for k in range(4)])
             T, status, _ = solver.solve_device_checked(d, [_solver.params_from_opts(para_this)])
             R_hat = T.cpu().numpy()
     return R_hat

@@ -89,6 +89,9 @@ def test_via_completion_batch_equals_pairwise():
                                  dataset='suncg', para=para, representation='skybox', completion=True)
     T = pipeline.RelativePoseEstimationViaCompletion_batch(net, rgb, nrm, depth, pts, w, args)
     assert T.shape == (B, 4, 4)
+    # network one pair at a time (scans uploaded chunk by chunk on the copy stream), one solve per step over both pairs: the same bits
+    Tc = pipeline.RelativePoseEstimationViaCompletion_batch(net, rgb, nrm, depth, pts, w, args, chunk=1)
+    assert np.array_equal(T, Tc)
     for b in range(B):
         def kp(dS, dT, ds, b=b):
             return (pts[2 * b], pts[2 * b] / np.array([640.0, 160.0]), w[2 * b], pts[2 * b + 1], pts[2 * b + 1] / np.array([640.0, 160.0]), w[2 * b + 1])
