@@ -128,6 +128,20 @@ int rp_solve_workspace_bytes(int n_slots, int max_ns, int max_nt, int max_topk, 
  * correspondences (or n_t > ~1400) the per-pair vectors move from shared memory into the slot's workspace. */
 int rp_solve_default_slots(int max_ns, int max_nt, int max_topk, int feat_dim, int* n_slots);
 
+/* One scan pair from HOST arrays (the reference's call pattern: evaluation.py:278-284 calls RelativePoseEstimation_helper,
+ * RPModule/rpmodule.py:317-508, once per pair).  All pointers are host pointers: pc / nrm [n,3] float64, feat [n,feat_dim]
+ * float32 (C order), w [n] float64; params: one rp_params; zero_row_topk: max_topk ints (numpy's tie order for all-zero rows)
+ * or NULL; feat_sum_order as in rp_solve_batch; edge_cap: candidate capacity (0 = worst case).  Packs the inputs into one
+ * page-locked block, ONE host-to-device copy, the fused launch, ONE device-to-host copy of T_out[16], status[1], stats[8]
+ * (stats may be NULL), and synchronises `stream`.  Device staging and workspace are cached per device inside the library.
+ * RP_STATUS_EDGE_OVERFLOW in *status: call again with edge_cap = 0. */
+int rp_solve_pair_host(int ns, int nt,
+                       const double* pc_s, const double* nrm_s, const float* feat_s, const double* w_s,
+                       const double* pc_t, const double* nrm_t, const float* feat_t, const double* w_t,
+                       int feat_dim, const rp_params* params, const int32_t* zero_row_topk, int max_topk,
+                       int feat_sum_order, int64_t edge_cap,
+                       double* T_out, int32_t* status, int32_t* stats, void* stream);
+
 /* Small-batch path.  The solver kernel is built twice: 128-thread CTAs, four per SM (throughput for batches that fill the
  * GPU) and 512-thread CTAs, one per SM, which give a scan pair a whole SM.  The reference calls its solver one pair at a time
  * (evaluation.py:278-284) and the completion alternation solves a few dozen pairs per step (rpmodule.py:569-662); batches of

@@ -66,7 +66,7 @@ NET_OPS = {"rp_conv_layer": 1, "rp_conv_layer_halo": 3, "rp_bn_finalize": 4, "rp
            "rp_bn_relu_maxpool": 10, "rp_bn_add_relu": 11, "rp_resize_nhwc": 12, "rp_resize_to_nchw": 13}
 
 EXPORTS = ("rp_abi_version", "rp_device_info", "rp_solve_workspace_bytes", "rp_solve_batch",
-           "rp_solve_batch_ex", "rp_solve_default_slots", "rp_solver_wide_max", "rp_h16_format", "rp_match_topk", "rp_launch_count", "rp_spectral_irls_solve", "rp_spectral_irls_workspace_bytes",
+           "rp_solve_batch_ex", "rp_solve_default_slots", "rp_solver_wide_max", "rp_solve_pair_host", "rp_h16_format", "rp_match_topk", "rp_launch_count", "rp_spectral_irls_solve", "rp_spectral_irls_workspace_bytes",
            "rp_conv_nparts", "rp_conv_layer", "rp_bn_finalize", "rp_bn_finalize_split", "rp_im2col_bf16", "rp_scnet_resize_in", "rp_scnet_resize_in_split", "rp_scnet_resize_out", "rp_scnet_resize_out_map",
            "rp_conv_launch_count", "rp_tc_gemm_test",
            "rp_conv_halo_plan", "rp_conv_layer_halo", "rp_conv_halo_debug", "rp_conv_halo_prof", "rp_conv_halo_tma_count",
@@ -105,6 +105,8 @@ def load():
     lib.rp_conv_halo_tma_count.restype = i64
     lib.rp_solve_default_slots.restype = i32
     lib.rp_solver_wide_max.restype = i32
+    lib.rp_solve_pair_host.restype = i32
+    lib.rp_solve_pair_host.argtypes = [i32, i32] + [vp] * 8 + [i32, vp, vp, i32, i32, i64, vp, vp, vp, vp]
     lib.rp_solver_wide_max.argtypes = [i32]
     lib.rp_solve_default_slots.argtypes = [i32, i32, i32, i32, ctypes.POINTER(ctypes.c_int)]
     lib.rp_solve_workspace_bytes.argtypes = [i32, i32, i32, i32, i32, i64, ctypes.POINTER(ctypes.c_size_t)]

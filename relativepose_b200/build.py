@@ -13,7 +13,7 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", 
 
 LIBS = {
     # output (relative to the package dir) : sources (relative to csrc/)
-    "librp_b200.so": ["rp_solver.cu", "rp_solver_wide.cu", "scnet.cu", "scnet_tc.cu", "scnet_halo.cu", "rp_warp.cu", "rp_keypoint.cu", "rp_plan.cu"],
+    "librp_b200.so": ["rp_solver.cu", "rp_solver_wide.cu", "rp_host.cu", "scnet.cu", "scnet_tc.cu", "scnet_halo.cu", "rp_warp.cu", "rp_keypoint.cu", "rp_plan.cu"],
 }
 
 

@@ -533,6 +533,8 @@ class PoseSolver(object):
     SMALL_BATCH = 16
 
     def solve_records(self, records, para, return_stats=False):
+        if len(records) == 1:
+            return self._solve_one(records[0], para, return_stats)
         if 0 < len(records) <= self.SMALL_BATCH:
             return self._solve_small(records, para, return_stats)
         if getattr(self, "_arena", None) is None:
@@ -542,6 +544,64 @@ class PoseSolver(object):
         D = int(np.asarray(records[0]["feat_src"]).shape[1]) if np.asarray(records[0]["feat_src"]).ndim == 2 else FEAT_DIM_DEFAULT
         self._arena.reset((ns + nt) * (7 * 8 + 4 * D) + 12 * (len(records) + 1) + 256 * 16)
         return self.solve_packed(PackedBatch(records, arena=self._arena), para, return_stats=return_stats)
+
+    _PARAM_FIELDS = ('method', 'topK', 'sigmaFeat', 'distThre', 'distSepThre', 'angleThre', 'sigmaDist', 'sigmaAngle1', 'sigmaAngle2', 'mu')
+
+    def _solve_one(self, rec, para, return_stats):
+        """B = 1 (RelativePoseEstimation_helper, the reference's one-pair-per-call pattern): the record's host arrays go to
+        rp_solve_pair_host as they are -- staging, the two copies, the launch and the wait all happen inside that one native
+        call; this function only checks dtypes / layout and passes pointers."""
+        try:
+            pkey = tuple(getattr(para, f) for f in self._PARAM_FIELDS)
+            cache = self.__dict__.setdefault('_one_params', {})
+            p = cache.get(pkey)
+        except TypeError:                                   # unhashable field (an array-valued sigma): no caching
+            pkey, p = None, None
+        if p is None:
+            p = params_from_opts(para)
+            if pkey is not None:
+                if len(cache) > 64:
+                    cache.clear()
+                cache[pkey] = p
+        fs, ft = np.asarray(rec["feat_src"]), np.asarray(rec["feat_tgt"])
+        order = 0 if (fs.flags["C_CONTIGUOUS"] and ft.flags["C_CONTIGUOUS"]) else 1
+        c = np.ascontiguousarray
+        pcs, nrs, ws = c(rec["pc_src"], dtype=np.float64), c(rec["normal_src"], dtype=np.float64), c(rec["weight_src"], dtype=np.float64)
+        pct, nrt, wt = c(rec["pc_tgt"], dtype=np.float64), c(rec["normal_tgt"], dtype=np.float64), c(rec["weight_tgt"], dtype=np.float64)
+        fs, ft = c(fs, dtype=np.float32), c(ft, dtype=np.float32)
+        ns, nt = pcs.shape[0], pct.shape[0]
+        D = fs.shape[1] if fs.ndim == 2 else FEAT_DIM_DEFAULT
+        if ns < 1 or nt < 1 or pcs.size != 3 * ns or nrs.size != 3 * ns or ws.size != ns or pct.size != 3 * nt or nrt.size != 3 * nt \
+                or wt.size != nt or fs.size != ns * D or ft.size != nt * D:
+            return self._solve_small([rec], para, return_stats)              # odd shapes: the general small-batch path sorts it out
+        topk_raw = int(p.topk)
+        stride = max(1, min(min(topk_raw, _lib.MAX_TOPK + 1), max(nt - 1, 1)))
+        if stride > _lib.MAX_TOPK:
+            raise RuntimeError("topK=%d > %d is not supported by the CUDA solver" % (stride, _lib.MAX_TOPK))
+        ztab = np.full([stride], -1, dtype=np.int32)
+        K = min(topk_raw, nt - 1)
+        if 1 <= K <= stride:
+            ztab[:K] = zero_row_topk(nt, K)
+        out = np.empty(16 + 1 + _lib.STATS_STRIDE // 2 + 1, dtype=np.float64)   # T | status | stats in one allocation
+        T = out[:16]
+        status = out[16:17].view(np.int32)
+        stats = out[17:17 + _lib.STATS_STRIDE // 2].view(np.int32)
+        ptr = lambda a: a.ctypes.data
+        edge_cap = self._edge_cap(ns, stride)
+        torch = self.torch
+        with torch.cuda.device(self.device):
+            stream = torch.cuda.current_stream().cuda_stream
+            for cap in (edge_cap, 0):
+                rc = self.lib.rp_solve_pair_host(ns, nt, ptr(pcs), ptr(nrs), ptr(fs), ptr(ws), ptr(pct), ptr(nrt), ptr(ft), ptr(wt), D,
+                                                 ctypes.byref(p), ptr(ztab), stride, order, cap, ptr(T), ptr(status), ptr(stats), stream)
+                _lib.check(rc, "rp_solve_pair_host")
+                if status[0] != _lib.STATUS_EDGE_OVERFLOW or cap == 0:
+                    break
+        self.check_status(status[:1], lambda: status[:1])
+        Th = T.reshape(1, 4, 4).copy()
+        if return_stats:
+            return Th, status[:1].copy(), stats.reshape(1, _lib.STATS_STRIDE).copy()
+        return Th
 
     def _solve_small(self, records, para, return_stats):
         """Latency path for a few pairs (RelativePoseEstimation_helper is B = 1): every input goes through ONE pinned
