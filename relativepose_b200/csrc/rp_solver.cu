@@ -92,6 +92,7 @@ struct SolveArgs {
     size_t sm_mask_off;     // byte offset of the bit mask in dynamic shared memory (when mask_in_smem)
     int dyn_in_global;      // scan pairs too large for shared memory: the per-pair vectors live in the slot (o_dyn)
     size_t o_dyn;
+    size_t sm_geo_off;      // 512-thread build: byte offset of the fitters' geometry copy in dynamic shared memory (0: none)
     int csr_smem_cap;       // small batches (fewer CTAs than fit an SM): CSR entries that fit the idle shared memory, else 0
     size_t sm_csr_off;
 };
@@ -441,6 +442,7 @@ enum { G_PX = 0, G_PY, G_PZ, G_QX, G_QY, G_QZ, G_NX, G_NY, G_NZ, G_MX, G_MY, G_M
 struct PairView {
     int ns, nt, K, N, NW;
     double* geo; int gstride;
+    const double* hgeo; int hgs;   // the 12 position / normal vectors the fitters read (G_PX..G_MZ): pv.geo, or a shared-memory copy
     int* cj;
     unsigned* mask;
     unsigned* edges; double* ew;
@@ -463,7 +465,7 @@ struct PairView {
 // un-scaled pair weights for the centroids, rpmodule.py:72-75,107-110).
 __device__ void horn_fit(Shared& sh, const PairView& pv, double mean_div, int& red_buf) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const double* geo = pv.geo; const int gs = pv.gstride;
+    const double* geo = pv.hgeo; const int gs = pv.hgs;
     if (NWARP == 4) {
         // warp-specialised: each warp owns 6-7 of the 25 sums over ALL correspondences, so the only
         // cross-lane traffic is one butterfly per owned sum and there is no cross-warp combine.
@@ -602,7 +604,7 @@ __device__ void horn_fit(Shared& sh, const PairView& pv, double mean_div, int& r
 // res[c] = mu*||R(p-sm)-(q-tm)||^2 + ||R n - m||^2  (the r of :262-263).
 __device__ void residual_pass(const Shared& sh, const PairView& pv, double mu, bool reweight) {
     const Pose& P = sh.pose;
-    const double* geo = pv.geo; const int gs = pv.gstride;
+    const double* geo = pv.hgeo; const int gs = pv.hgs;
     for (int cr = threadIdx.x; cr < pv.nrows; cr += T) {
         const int c = pv.rowmap[cr] & RM_ROW;       // only correspondences that still have a pair carry weight
         double px = geo[G_PX * gs + c] - P.sm[0], py = geo[G_PY * gs + c] - P.sm[1], pz = geo[G_PZ * gs + c] - P.sm[2];
@@ -1197,6 +1199,7 @@ __global__ void __launch_bounds__(T, RP_MIN_BLOCKS) rp_solve_kernel(const SolveA
         PairView pv;
         pv.ns = ns; pv.nt = nt; pv.K = K; pv.N = ns * K; pv.NW = (pv.N + 31) >> 5;
         pv.geo = reinterpret_cast<double*>(slot + A.o_geo); pv.gstride = A.Nmax;
+        pv.hgeo = pv.geo; pv.hgs = A.Nmax;
         pv.cj = reinterpret_cast<int*>(slot + A.o_cj);
         pv.edges = reinterpret_cast<unsigned*>(slot + A.o_edges);
         pv.ew = reinterpret_cast<double*>(slot + A.o_ew);
@@ -1759,6 +1762,12 @@ __global__ void __launch_bounds__(T, RP_MIN_BLOCKS) rp_solve_kernel(const SolveA
         }
 
         // ------------------------------------------------------------------ F. fitters
+        if (A.sm_geo_off) {          // a whole SM per pair: the 60 fit / residual passes read their geometry from shared memory
+            double* hg = reinterpret_cast<double*>(dyn_smem + A.sm_geo_off);
+            for (int e = tid; e < 12 * N; e += T) { const int a = e / N, c = e - a * N; hg[(size_t)a * N + c] = pv.geo[(size_t)a * pv.gstride + c]; }
+            pv.hgeo = hg; pv.hgs = N;
+            __syncthreads();
+        }
         const double mu = par.mu;
         int tot_it = 0, max_it_seen = 0, not_conv = 0;
         bool retry = false;                              // fast variant: the eigen iteration needs the ROBUST pass
@@ -1919,9 +1928,9 @@ int sm_count() {
 // goes to the resident pairs: first the symmetric bit mask, then as much of the CSR of W as fits (cols uint16 + vals
 // float64, 10 bytes per directed non-zero).  The fitters make ~250 passes over that CSR per pair; from shared memory a pass
 // costs a few microseconds instead of an L2 round trip per batch of loads (the L1 of a CTA with a 200 KB carve-out is tiny).
-struct LaunchPlan { size_t bytes; int mask_in_smem; int csr_cap; size_t csr_off; };
+struct LaunchPlan { size_t bytes; int mask_in_smem; int csr_cap; size_t csr_off; size_t geo_off; };
 LaunchPlan make_launch_plan(const SmemPlan& S, const Layout& L, int grid) {
-    LaunchPlan P = {S.bytes, S.mask_in_smem, 0, 0};
+    LaunchPlan P = {S.bytes, S.mask_in_smem, 0, 0, 0};
     if (S.dyn_in_global) return P;
     const int per_sm = (grid + sm_count() - 1) / sm_count();
     if (RP_MIN_BLOCKS > 1 && per_sm >= RP_MIN_BLOCKS) return P;
@@ -1932,6 +1941,10 @@ LaunchPlan make_launch_plan(const SmemPlan& S, const Layout& L, int grid) {
     const size_t mask = (size_t)L.Nmax * L.NWmax * sizeof(unsigned);
     const long long want = (2 * L.edge_cap + 2 * T + 7) & ~7ll;
     if (!P.mask_in_smem && align_up(S.mask_off + mask, 16) + (size_t)want * 10 <= avail) { P.mask_in_smem = 1; P.bytes = S.mask_off + mask; }
+    if (RP_MIN_BLOCKS == 1) {                              // one CTA per SM: room for the fitters' geometry (12 N float64)
+        const size_t g0 = align_up(P.bytes, 16), gb = (size_t)12 * L.Nmax * sizeof(double);
+        if (g0 > 0 && g0 + gb + 8192 <= avail) { P.geo_off = g0; P.bytes = g0 + gb; }
+    }
     const size_t cur = align_up(P.bytes, 16);
     if (avail > cur + 4096) {
         long long entries = (long long)((avail - cur) / 10) & ~7ll;               // vals start 16-byte aligned
@@ -2022,7 +2035,7 @@ int solve_batch_impl(int B, const int32_t* off_s, const int32_t* off_t,
     a.has_dbg = dbg ? 1 : 0;
     if (dbg) a.dbg = *dbg; else { rp_debug z = {}; a.dbg = z; }
     a.mask_in_smem = P.mask_in_smem; a.tfeat_stride = S.tfeat_stride; a.sm_mask_off = S.mask_off;
-    a.csr_smem_cap = P.csr_cap; a.sm_csr_off = P.csr_off;
+    a.csr_smem_cap = P.csr_cap; a.sm_csr_off = P.csr_off; a.sm_geo_off = P.geo_off;
     a.dyn_in_global = S.dyn_in_global; a.o_dyn = L.o_dyn;
     if (cudaMemsetAsync(workspace, 0, 256, stream) != cudaSuccess) { cudaGetLastError(); return RP_ERR_CUDA; }
     if (S.dyn_in_global) rp_solve_kernel<false, true><<<grid, T, P.bytes, stream>>>(a);
@@ -2084,7 +2097,7 @@ int spectral_irls_impl(int B, const int32_t* node_off,
     a.T_out = T_out; a.status = status; a.stats = stats;
     a.stop_after = RP_STAGE_SOLVE; a.has_dbg = 0;
     a.mask_in_smem = P.mask_in_smem; a.tfeat_stride = S.tfeat_stride; a.sm_mask_off = S.mask_off;
-    a.csr_smem_cap = P.csr_cap; a.sm_csr_off = P.csr_off;
+    a.csr_smem_cap = P.csr_cap; a.sm_csr_off = P.csr_off; a.sm_geo_off = P.geo_off;
     a.dyn_in_global = S.dyn_in_global; a.o_dyn = L.o_dyn;
     if (cudaMemsetAsync(workspace, 0, 256, stream) != cudaSuccess) { cudaGetLastError(); return RP_ERR_CUDA; }
     if (S.dyn_in_global) rp_solve_kernel<false, true><<<grid, T, P.bytes, stream>>>(a);

@@ -578,7 +578,7 @@ constexpr int RS_PX = 64, RS_MAXSRC = 40, RS_MAXFL = 2 * RS_MAXSRC * 72;
 __global__ void __launch_bounds__(256) resize_up_nchw_kernel(const float* __restrict__ src, int n, int Hs, int Ws, int pitch,
                                                              const int* __restrict__ cmap, int C, float* __restrict__ out, int H, int W,
                                                              int tanh_out) {
-    __shared__ float rows[RS_MAXFL];
+    __shared__ __align__(16) float rows[RS_MAXFL];
     __shared__ int s_x0[RS_PX], s_x1[RS_PX], s_map[256];
     __shared__ float s_l0[RS_PX], s_l1[RS_PX];
     const int tid = threadIdx.x;
@@ -598,24 +598,41 @@ __global__ void __launch_bounds__(256) resize_up_nchw_kernel(const float* __rest
     const int xs0 = s_x0[0], nsrc = s_x1[last] - xs0 + 1;       // source columns of the segment (<= RS_MAXSRC, checked on the host)
     const float* b = src + (size_t)im * Hs * Ws * pitch;
     const int run = nsrc * pitch;
-    for (int i = tid; i < run; i += 256) {
-        rows[i] = __ldg(b + ((size_t)y0 * Ws + xs0) * pitch + i);
-        rows[run + i] = __ldg(b + ((size_t)y1 * Ws + xs0) * pitch + i);
+    const float* g0 = b + ((size_t)y0 * Ws + xs0) * pitch;
+    const float* g1 = b + ((size_t)y1 * Ws + xs0) * pitch;
+    if ((pitch & 3) == 0 && ((reinterpret_cast<uintptr_t>(src) & 15) == 0)) {      // rows start 16-byte aligned: float4 staging
+        const int run4 = run >> 2;
+        float4* d0 = reinterpret_cast<float4*>(rows); float4* d1 = reinterpret_cast<float4*>(rows + run);
+        for (int i = tid; i < run4; i += 256) {
+            d0[i] = __ldg(reinterpret_cast<const float4*>(g0) + i);
+            d1[i] = __ldg(reinterpret_cast<const float4*>(g1) + i);
+        }
+    } else {
+        for (int i = tid; i < run; i += 256) {
+            rows[i] = __ldg(g0 + i);
+            rows[run + i] = __ldg(g1 + i);
+        }
     }
     __syncthreads();
     const size_t plane = (size_t)H * W;
     float* o = out + (size_t)im * C * plane + (size_t)oy * W + ox0;
-    for (int i = tid; i < RS_PX * C; i += 256) {
-        const int px = i & (RS_PX - 1), c = i / RS_PX;
-        if (ox0 + px >= W) continue;
+    // a thread keeps ONE output pixel (its column offsets and weights stay in registers) and walks the channels: a warp
+    // writes 32 consecutive pixels of one channel, and the inner loop is 4 shared-memory reads + the channel map per output
+    const int px = tid & (RS_PX - 1);
+    if (ox0 + px >= W) return;
+    const int a0 = (s_x0[px] - xs0) * pitch, a1 = (s_x1[px] - xs0) * pitch;
+    const float lx0 = s_l0[px], lx1 = s_l1[px];
+    const float* r0a = rows + a0; const float* r0b = rows + a1;
+    const float* r1a = rows + run + a0; const float* r1b = rows + run + a1;
+    o += px;
+#pragma unroll 4
+    for (int c = tid / RS_PX; c < C; c += 256 / RS_PX) {
         const int sc = s_map[c];
-        const int a0 = (s_x0[px] - xs0) * pitch + sc, a1 = (s_x1[px] - xs0) * pitch + sc;
-        const float lx0 = s_l0[px], lx1 = s_l1[px];
-        const float v = ly0 * (lx0 * rows[a0] + lx1 * rows[a1]) + ly1 * (lx0 * rows[run + a0] + lx1 * rows[run + a1]);
+        const float v = ly0 * (lx0 * r0a[sc] + lx1 * r0b[sc]) + ly1 * (lx0 * r1a[sc] + lx1 * r1b[sc]);
         float y = v;
         if (tanh_out == 1) y = tanhf(v);
         else if (tanh_out == 2) asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(v));
-        o[(size_t)c * plane + px] = y;
+        __stcs(o + (size_t)c * plane, y);
     }
 }
 
