@@ -106,6 +106,9 @@ typedef struct rp_debug {
     int64_t edge_cap;
     double* u;           /* [B, 5, u_stride] leading eigenvector per alternation (irls+sm / spectral) */
     int64_t u_stride;
+    int64_t* phase_clk;  /* [B, 8] SM clock (clock64) of the pair's CTA at: 0 start, 1 after the descriptor front end, 2 after the
+                          * pre-test, 3 after the exact tests, 4 after the CSR build, 5 end; 6 cycles inside the eigen iterations,
+                          * 7 cycles inside the Horn fits + residual passes (profiling aid) */
 } rp_debug;
 
 int rp_abi_version(void);

@@ -36,7 +36,7 @@ class RpDebug(ctypes.Structure):
     _fields_ = [("topk_idx", ctypes.c_void_p), ("topk_f", ctypes.c_void_p),
                 ("dij", ctypes.c_void_p), ("dij_off", ctypes.c_void_p),
                 ("edge_rc", ctypes.c_void_p), ("edge_w", ctypes.c_void_p), ("edge_cap", ctypes.c_int64),
-                ("u", ctypes.c_void_p), ("u_stride", ctypes.c_int64)]
+                ("u", ctypes.c_void_p), ("u_stride", ctypes.c_int64), ("phase_clk", ctypes.c_void_p)]
 
 
 class RpConvSrc(ctypes.Structure):

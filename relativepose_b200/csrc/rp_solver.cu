@@ -514,6 +514,40 @@ __device__ void horn_fit(Shared& sh, const PairView& pv, double mean_div, int& r
             if (warp == 0) sh.fin[6] = a6;
         }
         __syncthreads();
+    } else if (NWARP >= 13) {
+        // 512-thread build: every one of the 25 sums is sum_c w[c] X[c] Y[c] with w in {aP, aN}, X in {1, p_a, n_a}, Y in {1, q_b,
+        // m_b}; warp k takes sums k and k + NWARP over ALL correspondences (operands in shared memory), so a fit costs two short
+        // loops and two butterflies per warp instead of 25 butterflies per warp and a cross-warp combine.
+        static_assert(NWARP < 13 || (NWARP <= 16 && 2 * NWARP >= NSUM), "sum k < NWARP weighs with aP, its partner k + NWARP >= 16 with aN");
+        auto rows_of = [&](int k, const double*& xv, const double*& yv, bool& hx, bool& hy) {
+            int xa = -1, ya = -1;
+            if (k >= 1 && k <= 3) xa = G_PX + (k - 1);
+            else if (k >= 4 && k <= 6) ya = G_QX + (k - 4);
+            else if (k >= 7 && k <= 15) { xa = G_PX + (k - 7) / 3; ya = G_QX + (k - 7) % 3; }
+            else if (k >= 16) { xa = G_NX + (k - 16) / 3; ya = G_MX + (k - 16) % 3; }
+            hx = xa >= 0; hy = ya >= 0;
+            xv = geo + (size_t)(hx ? xa : 0) * gs; yv = geo + (size_t)(hy ? ya : 0) * gs;
+        };
+        const int k0 = warp, k1 = warp + NWARP;                // both sums of the warp in ONE loop: independent loads overlap
+        const bool two = k1 < NSUM;
+        const double *x0, *y0, *x1, *y1; bool hx0, hy0, hx1, hy1;
+        rows_of(k0, x0, y0, hx0, hy0);
+        rows_of(two ? k1 : 16, x1, y1, hx1, hy1);
+        const double* w0 = k0 < 16 ? pv.aP : pv.aN;
+        double acc0 = 0.0, acc1 = 0.0;
+#pragma unroll 4
+        for (int cr = lane; cr < pv.nrows; cr += 32) {
+            const int c = pv.rowmap[cr] & RM_ROW;
+            double t0 = w0[c];
+            if (hx0) t0 *= x0[c];
+            if (hy0) t0 *= y0[c];
+            acc0 += t0;
+            if (two) acc1 += (pv.aN[c] * x1[c]) * y1[c];
+        }
+        acc0 = warp_sum(acc0);
+        if (two) acc1 = warp_sum(acc1);
+        if (lane == 0) { sh.fin[k0] = acc0; if (two) sh.fin[k1] = acc1; }
+        __syncthreads();
     } else {
     double acc[NSUM];
 #pragma unroll
@@ -1158,6 +1192,8 @@ __device__ __forceinline__ void write_identity(double* T_out) {
 // there is none, and the common path keeps its register allocation.
 // BIG = true: pairs whose vectors do not fit shared memory keep them in the slot's workspace.  A template parameter, not a
 // run-time select, so that in the common variant every access to the per-pair vectors is a known shared-memory access.
+#define RP_PHASE_CLK(k) do { if (A.has_dbg && A.dbg.phase_clk && tid == 0) A.dbg.phase_clk[(size_t)b * 8 + (k)] = clock64(); } while (0)
+
 template <bool ROBUST, bool BIG>
 __global__ void __launch_bounds__(T, RP_MIN_BLOCKS) rp_solve_kernel(const SolveArgs A) {
     extern __shared__ __align__(16) unsigned char dyn_smem[];
@@ -1183,6 +1219,7 @@ __global__ void __launch_bounds__(T, RP_MIN_BLOCKS) rp_solve_kernel(const SolveA
         int* st = A.stats ? A.stats + (size_t)b * RP_STATS_STRIDE : nullptr;
         if (st && tid < RP_STATS_STRIDE) st[tid] = 0;
         const int D = A.feat_dim;
+        RP_PHASE_CLK(0);
 
         if (!A.solve_only && (ns < 3 || nt < 3)) {                // rpmodule.py:346-348
             write_identity(Tout);
@@ -1420,6 +1457,7 @@ __global__ void __launch_bounds__(T, RP_MIN_BLOCKS) rp_solve_kernel(const SolveA
             }
             __syncthreads();
         }
+        RP_PHASE_CLK(1);
         if (A.stop_after == RP_STAGE_TOPK) {
             write_identity(Tout);
             if (tid == 0) A.status[b] = RP_STATUS_OK;
@@ -1509,6 +1547,7 @@ __global__ void __launch_bounds__(T, RP_MIN_BLOCKS) rp_solve_kernel(const SolveA
             __syncthreads();
         }
         const int MC = sh.cnt[0];
+        RP_PHASE_CLK(2);
         if ((long long)MC > A.edge_cap) {
             write_identity(Tout);
             if (tid == 0) A.status[b] = RP_STATUS_EDGE_OVERFLOW;
@@ -1641,6 +1680,7 @@ __global__ void __launch_bounds__(T, RP_MIN_BLOCKS) rp_solve_kernel(const SolveA
             __syncthreads();
         }
         const int M1 = sh.cnt[1], M2 = sh.cnt[2], NZ = sh.cnt[5];
+        RP_PHASE_CLK(3);
         if (st && tid == 0) { st[1] = M1; st[2] = M2; st[3] = NZ; }
         if (A.has_dbg && A.dbg.edge_rc) {
             // compacted dump of the surviving pairs (test hook; order follows the candidate list)
@@ -1761,6 +1801,7 @@ __global__ void __launch_bounds__(T, RP_MIN_BLOCKS) rp_solve_kernel(const SolveA
             __syncthreads();
         }
 
+        RP_PHASE_CLK(4);
         // ------------------------------------------------------------------ F. fitters
         if (A.sm_geo_off) {          // a whole SM per pair: the 60 fit / residual passes read their geometry from shared memory
             double* hg = reinterpret_cast<double*>(dyn_smem + A.sm_geo_off);
@@ -1782,11 +1823,15 @@ __global__ void __launch_bounds__(T, RP_MIN_BLOCKS) rp_solve_kernel(const SolveA
         } else if (par.method == RP_METHOD_IRLS) {                    // rpmodule.py:169-210
             irls_rounds(sh, pv, mu, red_buf);
         } else if (par.method == RP_METHOD_IRLS_SM) {                 // rpmodule.py:212-315
+            long long clk_pi = 0, clk0 = 0;
+            const bool prof = A.has_dbg && A.dbg.phase_clk;
             irls_rounds(sh, pv, mu, red_buf);
             for (int alt = 0; alt < NUM_ALTER; ++alt) {
                 residual_to_h(pv);
                 int conv = 0;
+                if (prof) clk0 = clock64();
                 int it = power_iteration<false, ROBUST>(sh, pv, par.power_tol, par.max_power_iters, alt > 0, red_buf, &conv);
+                if (prof) { clk_pi += clock64() - clk0; if (tid == 0) A.dbg.phase_clk[(size_t)b * 8 + 6] = clk_pi; }
                 tot_it += it; max_it_seen = it > max_it_seen ? it : max_it_seen; not_conv |= !conv;
                 if (!ROBUST && !conv && par.max_power_iters > PI_FAST_CAP) { retry = true; break; }
                 if (A.has_dbg && A.dbg.u) for (int c = tid; c < N; c += T) A.dbg.u[((size_t)b * NUM_ALTER + alt) * A.dbg.u_stride + c] = pv.ua[c];
@@ -1815,6 +1860,7 @@ __global__ void __launch_bounds__(T, RP_MIN_BLOCKS) rp_solve_kernel(const SolveA
             if (tid == 0) A.status[b] = RP_STATUS_UNSUPPORTED;
             continue;
         }
+        RP_PHASE_CLK(5);
         if (retry) {                                     // uniform: decided from block-wide reductions
             if (tid == 0) A.status[b] = RP_STATUS_RETRY;
             continue;

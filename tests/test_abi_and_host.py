@@ -32,7 +32,7 @@ def test_struct_layouts_match_header():
     from relativepose_b200 import _lib
     assert ctypes.sizeof(_lib.RpParams) == 10 * 8 + 4 * 4
     assert _lib.RpParams.topk.offset == 80 and _lib.RpParams.method.offset == 84
-    assert ctypes.sizeof(_lib.RpDebug) == 9 * 8
+    assert ctypes.sizeof(_lib.RpDebug) == 10 * 8
 
 
 def test_params_follow_reference_expressions():
