@@ -284,7 +284,15 @@ def run_extras(torch, dev, peaks, steps):
                    "ms": ms, "pair_steps_per_s": B / ms * 1e3, "tflops": tf, "peak_tflops": sus, "frac": tf / sus,
                    "peak_source": peaks["source"] + " bf16_tflops_sustained", "gflop_per_pair_step": SCNET_GFLOP_PER_PAIR,
                    "ncu": "profiles/r2_scnet_halo_ncu_summary.txt (sm__pipe_tensor_cycles_active per layer)"}
-    del x16
+    # the same forward in the split-precision tensor-core mode (three tcgen05 launches per layer, float32 storage): the parity mode
+    from relativepose_b200.scnet_engine import ScnetEngine
+    eng3 = ScnetEngine(cnet, mode='tc3')
+    ms3 = device_time_ms(torch, lambda: eng3.forward(x16, borrow=True), n, 5)
+    ex["scnet_tc3"] = {"workload": "SCNet.forward, %d scan pairs, RP_SCNET_MODE=tc3: half(x) w_hi + lo(x) w_hi + half(x) lo(w) on tcgen05, "
+                                   "float32 storage (descriptors within 1.7e-4 of the reference's, poses within 2e-4 per step)" % B,
+                       "ms": ms3, "pair_steps_per_s": B / ms3 * 1e3, "useful_tflops": SCNET_GFLOP_PER_PAIR * B / ms3,
+                       "issued_tflops": 3 * SCNET_GFLOP_PER_PAIR * B / ms3}
+    del x16, eng3
 
     # ---- M2: Resnet18_8s forward, 64 images
     torch.manual_seed(0)

@@ -74,6 +74,10 @@ struct HaloArgs {
     int plane_bytes, a_bytes;              // TMA layout: [plane][K core][row][pixel] 16-byte units, planes 128-byte aligned; bytes of one buffer
     int dbg;                               // profiling only (flags >> 2): 1 no epilogue stores/stats, 2 no loader copy/transform, 4 no MMA
     int h2math;                            // producer BatchNorm + LeakyReLU of 16-bit sources in packed half arithmetic (flags bit 1)
+    int split_lo;                          // flags bit 8: the loader emits the LOW half of the activation, (x - half(x)) * 2^11, instead of half(x)
+    int accum;                             // flags bit 9: out = out + 2^-11 * (this launch's accumulators)   (float32 output only)
+                                           // -- the three launches of the split-precision mode: half(x) w_hi, then lo(x) w_hi and
+                                           //    half(x) lo(w) accumulated on top: x w to ~2^-22 on tensor cores (scnet_engine.py 'tc3')
     void* out; int out_pitch, out_ch_off, out_bf16;
     float* psum; float* psq;
     const float* bias; int tanh_out;
@@ -334,6 +338,13 @@ __global__ void __launch_bounds__(CTA, 1) conv_halo_tc(const HaloArgs A, const u
 #pragma unroll
                         for (int q = 0; q < 8; ++q) { const float z = fmaf(v[q], sc[q], sh[q]); v[q] = z > 0.f ? z : slope * z; }
                     }
+                    if (A.split_lo) {                           // low half, scaled into the normal range of the 16-bit format
+#pragma unroll
+                        for (int q = 0; q < 8; q += 2) {
+                            const float2 hi = rp_h2_to_f2(rp_f2_to_h2(v[q], v[q + 1]));
+                            v[q] = (v[q] - hi.x) * 2048.f; v[q + 1] = (v[q + 1] - hi.y) * 2048.f;
+                        }
+                    }
                     rp_h162 p0 = rp_f2_to_h2(v[0], v[1]), p1 = rp_f2_to_h2(v[2], v[3]);
                     rp_h162 p2 = rp_f2_to_h2(v[4], v[5]), p3 = rp_f2_to_h2(v[6], v[7]);
                     uint4 o;
@@ -359,7 +370,7 @@ __global__ void __launch_bounds__(CTA, 1) conv_halo_tc(const HaloArgs A, const u
                     cp_async_wait_all();
                     HP_ADD(2, c0)
                     if (PROF) x0 = clock64();
-                    if (act && A.h2math) {
+                    if (act && A.h2math && !A.split_lo) {
                         // packed half arithmetic: z = x * scale + shift is ONE rounding of the exact value for half inputs (the
                         // float path rounds to half after the float FMA as well); what differs is scale / shift rounded to half.
                         // LeakyReLU(z) = max(z, slope z) for 0 <= slope <= 1.  12 instructions per 8 channels instead of ~36.
@@ -389,7 +400,7 @@ __global__ void __launch_bounds__(CTA, 1) conv_halo_tc(const HaloArgs A, const u
                                 if (live[u]) *reinterpret_cast<uint4*>(dst + (size_t)h * 16) = x[u];
                             }
                         }
-                    } else if (act) {
+                    } else if (act || A.split_lo) {
 #pragma unroll 2
                         for (int h = h0; h < A.NPX; h += HSTEP) {
                             if (my_pix[h] < 0) continue;              // zero padding stays zero (the BatchNorm shift must not leak in)
@@ -575,6 +586,21 @@ __global__ void __launch_bounds__(CTA, 1) conv_halo_tc(const HaloArgs A, const u
                 HP_ADD(10, e1)
                 const bool valid = a < A.cls_Ha[cls] && bcol < A.cls_Wb[cls];
                 const int co0 = tc_.tile_n * BN + c0;
+                if (A.accum && valid) {                     // a later launch of the split-precision mode: add onto what is stored
+                    const int oy_ = a * A.ostr + A.cls_py[cls], ox_ = bcol * A.ostr + A.cls_px[cls];
+                    const float* pp = reinterpret_cast<const float*>(A.out) + (((size_t)tc_.img * A.Hout + oy_) * A.Wout + ox_) * A.out_pitch + A.out_ch_off + co0;
+                    constexpr float S11 = 4.8828125e-4f;    // 2^-11
+                    if (co0 + 31 < A.Cout && ((((size_t)pp) & 15) == 0)) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) {
+                            const float4 p4 = *reinterpret_cast<const float4*>(pp + j);
+                            v[j] = fmaf(v[j], S11, p4.x); v[j + 1] = fmaf(v[j + 1], S11, p4.y); v[j + 2] = fmaf(v[j + 2], S11, p4.z); v[j + 3] = fmaf(v[j + 3], S11, p4.w);
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) if (co0 + j < A.Cout) v[j] = fmaf(v[j], S11, pp[j]);
+                    }
+                }
                 if (A.bias || A.tanh_out) {                 // (bias/tanh layers have Cout <= 256, checked on the host)
                     const float4* bp = reinterpret_cast<const float4*>(s_bias + co0);
 #pragma unroll
@@ -583,8 +609,13 @@ __global__ void __launch_bounds__(CTA, 1) conv_halo_tc(const HaloArgs A, const u
                         v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
                     }
                     if (A.tanh_out) {
+                        if (A.accum) {                      // split-precision mode: float32-class output, so the exact function
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) v[j] = fast_tanh(v[j]);
+                            for (int j = 0; j < 32; ++j) v[j] = tanhf(v[j]);
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) v[j] = fast_tanh(v[j]);
+                        }
                     }
                 }
                 rp_h162 pk[16];            // 16-bit output: packed once, stored as packed
@@ -813,7 +844,9 @@ static int launch_halo(const HaloArgs& H0, const void* wp, int h2math, cudaStrea
     // sources always use the gather and its [K core][plane,row,pixel] layout).
     CUtensorMap tm[2];
     memset(tm, 0, sizeof(tm));
-    H.use_tma = ((h2math >> 5) & 1) ? 0 : (((h2math >> 6) & 1) || H.ntap == 1) ? 1 : 0;
+    H.split_lo = (h2math >> 7) & 1; H.accum = (h2math >> 8) & 1;
+    if (H.accum && H.out_bf16) return RP_ERR_UNSUPPORTED;                     // accumulation passes need float32 storage
+    H.use_tma = (((h2math >> 5) & 1) || H.split_lo) ? 0 : (((h2math >> 6) & 1) || H.ntap == 1) ? 1 : 0;
     for (int i = 0; i < H.nsrc; ++i) if (H.src[i].dtype != 1) H.use_tma = 0;
     if (H.use_tma) {
         const int ppl = H.PH * H.PW;
@@ -844,7 +877,8 @@ static int launch_halo(const HaloArgs& H0, const void* wp, int h2math, cudaStrea
     for (int ng = MAXNG; ng > 2; ng >>= 1)
         if (H.NPX * ng <= PIXTAB && fixed + (size_t)ng * a_bytes <= limit) { H.ng = ng; break; }
     H.w_resident = (H.ntn == 1 && H.nkt * H.ntap <= NB) ? 1 : 0;
-    H.h2math = h2math & 1; H.dbg = h2math >> 1;
+    H.h2math = h2math & 1; H.dbg = (h2math >> 1) & 15;
+
     const size_t smem = fixed + H.ng * a_bytes;
     if (smem > limit) return RP_ERR_UNSUPPORTED;
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { cudaGetLastError(); return RP_ERR_CUDA; }

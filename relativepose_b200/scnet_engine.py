@@ -63,8 +63,15 @@ class ScnetEngine(object):
     def __init__(self, net, mode=None):
         import os
         import torch
-        # 'tc': tcgen05 bf16 tensor-core kernels wherever a layer qualifies (default); 'fp32': CUDA-core float32 only
+        # 'tc': tcgen05 tensor-core kernels with 16-bit operands wherever a layer qualifies (default, the throughput mode);
+        # 'tc3': the same kernels in split precision -- float32 activation storage, every tensor-core layer as three launches
+        #        half(x) w_hi + lo(x) w_hi + half(x) lo(w) (x w to ~2^-22, float32 accumulation): float32-class output at
+        #        tensor-core speed, the parity mode for the descriptors that drive the solver;
+        # 'fp32': CUDA-core float32 only (the exact-parity reference path of the tests)
         self.mode = mode or os.environ.get("RP_SCNET_MODE", "tc")
+        self.split3 = self.mode == 'tc3'
+        if self.split3 and not _lib.h16_is_fp16():
+            raise RuntimeError("RP_SCNET_MODE=tc3 needs the IEEE-half build of the library (csrc/rp_h16.cuh)")
         # replay the ~87 layer launches of a forward as one CUDA graph once a shape has been seen twice
         self.use_graph = os.environ.get("RP_SCNET_GRAPH", "1") == "1"
         # tcgen05 halo-tile kernel (csrc/scnet_halo.cu) for every layer with >= 16 channels per source in 'tc' mode
@@ -74,7 +81,7 @@ class ScnetEngine(object):
         self.halo_flags = int(os.environ.get("RP_SCNET_HALO_FLAGS", "2"))
         self.halo_min = int(os.environ.get("RP_SCNET_HALO_MIN", "1"))     # smallest base-grid extent that takes the halo kernel
         act = os.environ.get("RP_SCNET_ACT", self._act_default)
-        self.act_bf16 = self.mode == 'tc' and act == 'bf16'
+        self.act_bf16 = self.mode == 'tc' and act == 'bf16'      # (tc3 accumulates its three launches in float32 storage)
         # the forward as ONE native call: after a warm-up run the layer calls of a forward are frozen into an op list
         # (rp_net_op) that rp_scnet_forward / rp_resnet18_8s_forward replays (and that the CUDA graph captures)
         self.use_plan = os.environ.get("RP_SCNET_PLAN", "1") == "1"
@@ -223,7 +230,7 @@ class ScnetEngine(object):
         d.out_dtype = out.dtype
         d.bias = bias.data_ptr() if bias is not None else None
         d.tanh_out = int(tanh)
-        use_tc = self.mode == 'tc' and all(a.C % 16 == 0 for a in srcs)
+        use_tc = self.mode in ('tc', 'tc3') and all(a.C % 16 == 0 for a in srcs)
         if k == 1 and not bn and sum(a.C for a in srcs) <= 128 and (out.C <= 4 or (out.C <= 32 and not self.halo)):
             use_tc = False                   # 3-channel heads are HBM-bound: CUDA-core kernel inside rp_conv_layer (also the
                                              # fallback for the wider heads when the halo kernel is off)
@@ -250,6 +257,14 @@ class ScnetEngine(object):
                     self._packed_tc[key] = pack_halo(w.reshape(k * k, w.shape[2], w.shape[3]), list(widx[:ntap.value]),
                                                      [a.C for a in srcs], out.C, bn_tile, tk)
                 wtc = self._packed_tc[key]
+                if self.split3:
+                    key_lo = key + ('lo',)
+                    if key_lo not in self._packed_tc:
+                        w = self._packed[wkey]
+                        w_lo = (w - w.to(h16()).float()) * 2048.0
+                        self._packed_tc[key_lo] = pack_halo(w_lo.reshape(k * k, w.shape[2], w.shape[3]), list(widx[:ntap.value]),
+                                                            [a.C for a in srcs], out.C, bn_tile, tk)
+                    wtc_lo = self._packed_tc[key_lo]
         if use_tc and not use_halo:
             use_tc = False                  # no tile plan for this shape: the float32 CUDA-core kernel (reads / writes 16-bit storage too)
         if bn:
@@ -263,7 +278,16 @@ class ScnetEngine(object):
             d.psum, d.psq = pt.data_ptr(), pt.data_ptr() + 4 * need
         else:
             d.psum, d.psq = None, None
-        if use_halo:
+        if use_halo and self.split3:
+            # x w = half(x) w_hi + [lo(x) w_hi + half(x) lo(w)] 2^-11 with lo(.) = (. - half(.)) 2^11: the first launch stores, the
+            # other two add onto the float32 output (flags bit 9), the second with the loader emitting lo(x) (bit 8); bias / tanh
+            # / batch statistics belong to the last launch, which sees the complete sum
+            d0 = _lib.RpConvDesc.from_buffer_copy(d)
+            d0.bias, d0.tanh_out, d0.psum, d0.psq = None, 0, None, None
+            self._run("rp_conv_layer_halo", d0, wtc.data_ptr(), bn_tile, tk, self.halo_flags, stream)
+            self._run("rp_conv_layer_halo", d0, wtc.data_ptr(), bn_tile, tk, self.halo_flags | (1 << 8) | (1 << 9), stream)
+            self._run("rp_conv_layer_halo", d, wtc_lo.data_ptr(), bn_tile, tk, self.halo_flags | (1 << 9), stream)
+        elif use_halo:
             self._run("rp_conv_layer_halo", d, wtc.data_ptr(), bn_tile, tk, self.halo_flags, stream)
         else:
             self._run("rp_conv_layer", d, stream)
