@@ -329,6 +329,12 @@ def run_extras(torch, dev, peaks, steps):
         ms = wall_ms(torch, lambda: pipeline.RelativePoseEstimationViaCompletion_batch(snet, rgb, nrm, depth, pts, w, a), 3, 3)
         ex["config3_%dstep" % st_] = {"workload": "configs[3] per GPU: 32 ScanNet-shape pairs, %d x (warp -> SCNet -> blend -> gather -> "
                                                   "RPModule N=515), host scans in, poses out" % st_, "ms": ms, "pairs_per_s": B / ms * 1e3}
+    # the same 3-step alternation with the network in its split-precision (parity) mode
+    from relativepose_b200.scnet_engine import ScnetEngine
+    snet._engine = ScnetEngine(snet, mode='tc3')
+    ms = wall_ms(torch, lambda: pipeline.RelativePoseEstimationViaCompletion_batch(snet, rgb, nrm, depth, pts, w, a), 3, 3)
+    ex["config3_3step_tc3"] = {"workload": "configs[3] per GPU, 3 steps, network in RP_SCNET_MODE=tc3 (split-precision tcgen05, the parity mode)",
+                               "ms": ms, "pairs_per_s": B / ms * 1e3}
     del snet, cnet
     torch.cuda.empty_cache()
 

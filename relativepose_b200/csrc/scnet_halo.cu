@@ -131,7 +131,7 @@ __device__ __forceinline__ uint64_t pack_desc(uint32_t lo, uint32_t hi) { return
 //   MMA      (1 thr)    ntap x TK/16 tcgen05.mma per chunk into accumulator set tile % nacc; commits free slots / buffers
 //   epilogue (128 thr)  accumulator set tile % nacc -> global + statistics          acc_full -> acc_empty
 // so the gathers of the next tiles, the MMAs of tile i and the epilogue of earlier tiles overlap.
-template <int BN, int TK, int NB>
+template <int BN, int TK, int NB, bool SPLIT>      // SPLIT: the launches of the split-precision mode (HaloArgs::split_lo / accum)
 __global__ void __launch_bounds__(CTA, 1) conv_halo_tc(const HaloArgs A, const unsigned char* __restrict__ Wp,
                                                         const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CUtensorMap tm1) {
     extern __shared__ __align__(128) unsigned char smem[];
@@ -338,7 +338,7 @@ __global__ void __launch_bounds__(CTA, 1) conv_halo_tc(const HaloArgs A, const u
 #pragma unroll
                         for (int q = 0; q < 8; ++q) { const float z = fmaf(v[q], sc[q], sh[q]); v[q] = z > 0.f ? z : slope * z; }
                     }
-                    if (A.split_lo) {                           // low half, scaled into the normal range of the 16-bit format
+                    if (SPLIT && A.split_lo) {                  // low half, scaled into the normal range of the 16-bit format
 #pragma unroll
                         for (int q = 0; q < 8; q += 2) {
                             const float2 hi = rp_h2_to_f2(rp_f2_to_h2(v[q], v[q + 1]));
@@ -370,7 +370,7 @@ __global__ void __launch_bounds__(CTA, 1) conv_halo_tc(const HaloArgs A, const u
                     cp_async_wait_all();
                     HP_ADD(2, c0)
                     if (PROF) x0 = clock64();
-                    if (act && A.h2math && !A.split_lo) {
+                    if (act && A.h2math && !(SPLIT && A.split_lo)) {
                         // packed half arithmetic: z = x * scale + shift is ONE rounding of the exact value for half inputs (the
                         // float path rounds to half after the float FMA as well); what differs is scale / shift rounded to half.
                         // LeakyReLU(z) = max(z, slope z) for 0 <= slope <= 1.  12 instructions per 8 channels instead of ~36.
@@ -400,7 +400,7 @@ __global__ void __launch_bounds__(CTA, 1) conv_halo_tc(const HaloArgs A, const u
                                 if (live[u]) *reinterpret_cast<uint4*>(dst + (size_t)h * 16) = x[u];
                             }
                         }
-                    } else if (act || A.split_lo) {
+                    } else if (act || (SPLIT && A.split_lo)) {
 #pragma unroll 2
                         for (int h = h0; h < A.NPX; h += HSTEP) {
                             if (my_pix[h] < 0) continue;              // zero padding stays zero (the BatchNorm shift must not leak in)
@@ -586,7 +586,7 @@ __global__ void __launch_bounds__(CTA, 1) conv_halo_tc(const HaloArgs A, const u
                 HP_ADD(10, e1)
                 const bool valid = a < A.cls_Ha[cls] && bcol < A.cls_Wb[cls];
                 const int co0 = tc_.tile_n * BN + c0;
-                if (A.accum && valid) {                     // a later launch of the split-precision mode: add onto what is stored
+                if (SPLIT && A.accum && valid) {            // a later launch of the split-precision mode: add onto what is stored
                     const int oy_ = a * A.ostr + A.cls_py[cls], ox_ = bcol * A.ostr + A.cls_px[cls];
                     const float* pp = reinterpret_cast<const float*>(A.out) + (((size_t)tc_.img * A.Hout + oy_) * A.Wout + ox_) * A.out_pitch + A.out_ch_off + co0;
                     constexpr float S11 = 4.8828125e-4f;    // 2^-11
@@ -609,7 +609,7 @@ __global__ void __launch_bounds__(CTA, 1) conv_halo_tc(const HaloArgs A, const u
                         v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
                     }
                     if (A.tanh_out) {
-                        if (A.accum) {                      // split-precision mode: float32-class output, so the exact function
+                        if (SPLIT && A.accum) {             // split-precision mode: float32-class output, so the exact function
 #pragma unroll
                             for (int j = 0; j < 32; ++j) v[j] = tanhf(v[j]);
                         } else {
@@ -832,8 +832,8 @@ static bool make_src_tmap(const rp_conv_src& S, const HaloArgs& H, int KC, CUten
                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-template <int BN, int TK, int NB>
-static int launch_halo(const HaloArgs& H0, const void* wp, int h2math, cudaStream_t stream) {
+template <int BN, int TK, int NB, bool SPLIT>
+static int launch_halo_impl(const HaloArgs& H0, const void* wp, int h2math, cudaStream_t stream) {
     constexpr int KC = TK / 8;
     HaloArgs H = H0;
     // 16-bit sources can take the tiled-TMA loader: halo layout [plane][K core][row][pixel] with 128-byte aligned planes.  In the
@@ -865,7 +865,7 @@ static int launch_halo(const HaloArgs& H0, const void* wp, int h2math, cudaStrea
     if (!H.use_tma) { H.plane_bytes = 0; H.a_bytes = ((KC * H.a_lbo + 127) / 128) * 128; }
     const size_t a_bytes = (size_t)H.a_bytes;
     const size_t fixed = (size_t)EPI_SMEM + (size_t)NB * BN * TK * 2;
-    auto kern = conv_halo_tc<BN, TK, NB>;
+    auto kern = conv_halo_tc<BN, TK, NB, SPLIT>;
     static size_t limit = 0;                                    // dynamic bytes a CTA of this instantiation may take
     if (limit == 0) {
         cudaFuncAttributes fa;
@@ -892,6 +892,14 @@ static int launch_halo(const HaloArgs& H0, const void* wp, int h2math, cudaStrea
     if (H.use_tma) ++g_tma_launches;
     ++scnet::g_conv_launches;
     return cudaGetLastError() == cudaSuccess ? RP_OK : RP_ERR_CUDA;
+}
+
+// the split-precision launches (flags bit 8 / 9) run their own instantiation: compiled into the common one, the extra paths cost
+// the 16-bit layers registers (spills in three of the eight tile shapes, stem +20 %)
+template <int BN, int TK, int NB>
+static int launch_halo(const HaloArgs& H0, const void* wp, int h2math, cudaStream_t stream) {
+    return ((h2math >> 7) & 3) ? launch_halo_impl<BN, TK, NB, true>(H0, wp, h2math, stream)
+                               : launch_halo_impl<BN, TK, NB, false>(H0, wp, h2math, stream);
 }
 
 }  // namespace halo

@@ -12,5 +12,9 @@ echo "=== launch list of the bench"; timeout 900 ncu --metrics gpu__time_duratio
 echo "=== scnet launch list P=32"; timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv --log-file gpurun_out/${TAG}_scnet_launches_P32.csv python scripts/prof_scnet.py 32 > /dev/null 2>&1; python scripts/ncu_launch_table.py gpurun_out/${TAG}_scnet_launches_P32.csv | head -14
 echo "=== halo roles"; RP_SCNET_HALO_FLAGS=34 timeout 300 python scripts/prof_halo_layers.py 32 3 2>&1 | tail -16
 echo "=== ncu halo layers"; timeout 900 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:conv_halo_tc -o gpurun_out/${TAG}_halo_layers python scripts/prof_halo_layers.py 32 1 > /dev/null 2>&1; ls -la gpurun_out/${TAG}_halo_layers.ncu-rep
+echo "=== ncu wide solver kernel, one pair"; timeout 600 ncu --set full --clock-control none --import-source on -k regex:rp_solve_kernel -s 8 -c 1 -o gpurun_out/${TAG}_solver_wide_one_pair python scripts/phase_clk.py > /dev/null 2>&1; ls -la gpurun_out/${TAG}_solver_wide_one_pair.ncu-rep
+echo "=== phase clocks"; timeout 300 python scripts/phase_clk.py 2>&1 | tail -4
+echo "=== wide vs narrow"; timeout 600 python scripts/time_wide.py 2>&1 | tail -16
+echo "=== launch list of one alternation call (no graph)"; RP_SCNET_GRAPH=0 timeout 900 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/${TAG}_alternation_launches.csv python scripts/prof_alternation.py > /dev/null 2>&1; python scripts/ncu_launch_table.py gpurun_out/${TAG}_alternation_launches.csv | head -24
 } > gpurun_out/round_final_$TAG.log 2>&1
 tail -60 gpurun_out/round_final_$TAG.log
