@@ -397,6 +397,16 @@ long long rp_conv_halo_tma_count(void);
 /* Profiling aid: per-role cycle counters of the halo kernel (enabled by flags bit 5 of rp_conv_layer_halo), read and cleared. */
 int rp_conv_halo_prof(unsigned long long* out16);
 
+/* RP_OK when the tile plan of this layer fits one CTA's shared memory under `flags` (the fused split-precision launch, flags bit
+ * 10, keeps a hi and a lo halo per buffer), RP_ERR_UNSUPPORTED otherwise.  Launches nothing. */
+int rp_conv_halo_fits(const rp_conv_desc* d, int bn, int tk, int flags);
+
+/* flags of rp_conv_layer_halo: bit 0 16-pixel halo pitch; bit 1 packed-half BatchNorm of 16-bit sources; bits 2-5 profiling /
+ * debugging; bit 6 / 7 never / always tiled TMA for 16-bit sources.  Split-precision launches (float32 sources and output; the
+ * network mode RP_SCNET_MODE=tc3): bit 8 the loader emits lo(x) = (x - half(x)) 2^11 instead of half(x); bit 9 the epilogue adds
+ * 2^-11 x (this launch) onto the stored float32 output -- three launches half(x) w_hi, lo(x) w_hi, half(x) lo(w) give x w to
+ * 2^-22; bit 10 the same sum in ONE launch: w_packed holds (hi, lo) block pairs of 2^8 w, the loader fills a hi and a lo halo of
+ * 2^4 x, three tcgen05.mma per K step accumulate into one TMEM accumulator and the epilogue scales by 2^-12. */
 int rp_conv_layer_halo(const rp_conv_desc* d, const void* w_packed, int bn, int tk, int flags, void* stream);
 /* test hook: the tile plan as 96 integers (layout in csrc/scnet_halo.cu) for the CPU emulation in tests/test_halo_plan.py */
 int rp_conv_halo_debug(const rp_conv_desc* d, int bn, int tk, int flags, int* out96);

@@ -69,7 +69,7 @@ EXPORTS = ("rp_abi_version", "rp_device_info", "rp_solve_workspace_bytes", "rp_s
            "rp_solve_batch_ex", "rp_solve_default_slots", "rp_solver_wide_max", "rp_solve_pair_host", "rp_h16_format", "rp_match_topk", "rp_launch_count", "rp_spectral_irls_solve", "rp_spectral_irls_workspace_bytes",
            "rp_conv_nparts", "rp_conv_layer", "rp_bn_finalize", "rp_bn_finalize_split", "rp_im2col_bf16", "rp_scnet_resize_in", "rp_scnet_resize_in_split", "rp_scnet_resize_out", "rp_scnet_resize_out_map",
            "rp_conv_launch_count", "rp_tc_gemm_test",
-           "rp_conv_halo_plan", "rp_conv_layer_halo", "rp_conv_halo_debug", "rp_conv_halo_prof", "rp_conv_halo_tma_count",
+           "rp_conv_halo_plan", "rp_conv_halo_fits", "rp_conv_layer_halo", "rp_conv_halo_debug", "rp_conv_halo_prof", "rp_conv_halo_tma_count",
            "rp_affinity_build", "rp_scnet_forward", "rp_resnet18_8s_forward", "rp_gather_primitives", "rp_match_sample_workspace_bytes", "rp_match_sample", "rp_heat_sample", "rp_warp_workspace_bytes", "rp_warp_views", "rp_warp_views_ex", "rp_pano2pc", "rp_blend_completion",
            "rp_bn_relu_maxpool", "rp_bn_add_relu", "rp_resize_nhwc", "rp_resize_to_nchw", "rp_interpolate")
 

@@ -75,6 +75,9 @@ struct HaloArgs {
     int dbg;                               // profiling only (flags >> 2): 1 no epilogue stores/stats, 2 no loader copy/transform, 4 no MMA
     int h2math;                            // producer BatchNorm + LeakyReLU of 16-bit sources in packed half arithmetic (flags bit 1)
     int split_lo;                          // flags bit 8: the loader emits the LOW half of the activation, (x - half(x)) * 2^11, instead of half(x)
+    int fused3;                            // flags bit 10: ONE launch computes half(x) w_hi + lo(x) w_hi + half(x) lo(w): the loader fills a hi and a
+    int a_half;                            //   lo halo (a_half bytes apart, unscaled lo), weight blocks come as (hi, lo) pairs of the weights scaled by
+    float out_scale;                       //   2^8 and the activations by 2^4 (low halves in the normal range of IEEE half), the epilogue multiplies by out_scale = 2^-12
     int accum;                             // flags bit 9: out = out + 2^-11 * (this launch's accumulators)   (float32 output only)
                                            // -- the three launches of the split-precision mode: half(x) w_hi, then lo(x) w_hi and
                                            //    half(x) lo(w) accumulated on top: x w to ~2^-22 on tensor cores (scnet_engine.py 'tc3')
@@ -338,6 +341,21 @@ __global__ void __launch_bounds__(CTA, 1) conv_halo_tc(const HaloArgs A, const u
 #pragma unroll
                         for (int q = 0; q < 8; ++q) { const float z = fmaf(v[q], sc[q], sh[q]); v[q] = z > 0.f ? z : slope * z; }
                     }
+                    if (SPLIT && A.fused3) {                    // fused split precision: the low halves go to the second halo of the buffer
+                        float l[8];
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) v[q] *= 16.f;             // 2^4: the low halves of |x| > 0.008 stay normal numbers
+#pragma unroll
+                        for (int q = 0; q < 8; q += 2) {
+                            const float2 hi = rp_h2_to_f2(rp_f2_to_h2(v[q], v[q + 1]));
+                            l[q] = v[q] - hi.x; l[q + 1] = v[q + 1] - hi.y;
+                        }
+                        rp_h162 l0 = rp_f2_to_h2(l[0], l[1]), l1 = rp_f2_to_h2(l[2], l[3]), l2 = rp_f2_to_h2(l[4], l[5]), l3 = rp_f2_to_h2(l[6], l[7]);
+                        uint4 ol;
+                        ol.x = *reinterpret_cast<uint32_t*>(&l0); ol.y = *reinterpret_cast<uint32_t*>(&l1);
+                        ol.z = *reinterpret_cast<uint32_t*>(&l2); ol.w = *reinterpret_cast<uint32_t*>(&l3);
+                        *reinterpret_cast<uint4*>(dst + A.a_half + (size_t)h * 16) = ol;
+                    }
                     if (SPLIT && A.split_lo) {                  // low half, scaled into the normal range of the 16-bit format
 #pragma unroll
                         for (int q = 0; q < 8; q += 2) {
@@ -430,7 +448,11 @@ __global__ void __launch_bounds__(CTA, 1) conv_halo_tc(const HaloArgs A, const u
                         for (int u = 0; u < U; ++u) {
                             if (pix[u] == -2) continue;
                             const int h = hb + u * HSTEP;
-                            if (pix[u] < 0) { *reinterpret_cast<uint4*>(dst + (size_t)h * 16) = make_uint4(0u, 0u, 0u, 0u); continue; }
+                            if (pix[u] < 0) {
+                                *reinterpret_cast<uint4*>(dst + (size_t)h * 16) = make_uint4(0u, 0u, 0u, 0u);
+                                if (SPLIT && A.fused3) *reinterpret_cast<uint4*>(dst + A.a_half + (size_t)h * 16) = make_uint4(0u, 0u, 0u, 0u);
+                                continue;
+                            }
                             float v[8] = {__uint_as_float(x[u][0].x), __uint_as_float(x[u][0].y), __uint_as_float(x[u][0].z), __uint_as_float(x[u][0].w),
                                           __uint_as_float(x[u][1].x), __uint_as_float(x[u][1].y), __uint_as_float(x[u][1].z), __uint_as_float(x[u][1].w)};
                             finish(v, h);
@@ -449,7 +471,7 @@ __global__ void __launch_bounds__(CTA, 1) conv_halo_tc(const HaloArgs A, const u
         // ------------------------------------------------------------------ weight stream (bulk TMA)
         // (the whole warp runs the loop so that its control values stay warp-uniform; one elected lane issues)
         const bool leader = elect_one();
-        const int per_tile = A.nkt * A.ntap;
+        const int per_tile = A.nkt * A.ntap * ((SPLIT && A.fused3) ? 2 : 1);    // fused split precision: (hi, lo) block pairs
         uint32_t wi = 0;
         if (A.w_resident) {
             // small layers (stem, heads, 32/64-channel 4x4 layers with one n-tile): the whole weight set sits in the ring
@@ -506,8 +528,9 @@ __global__ void __launch_bounds__(CTA, 1) conv_halo_tc(const HaloArgs A, const u
             HP_ADD(5, m0)
             tc_fence_after();
             const uint32_t acc0 = tmem_d + ab * (uint32_t)A.acc_cols;
+            const bool F3 = SPLIT && A.fused3;
             if (A.w_resident && !w_ready) {                               // resident weights: wait for them once
-                for (int i = 0; i < A.nkt * A.ntap; ++i) mbar_wait(&w_full[i], 0u);
+                for (int i = 0; i < A.nkt * A.ntap * (F3 ? 2 : 1); ++i) mbar_wait(&w_full[i], 0u);
                 w_ready = true;
             }
             for (int c = 0; c < A.nkt; ++c, ++cc) {
@@ -518,7 +541,38 @@ __global__ void __launch_bounds__(CTA, 1) conv_halo_tc(const HaloArgs A, const u
                 tc_fence_after();
                 const uint32_t a_lo_buf = a_lo_k | (sA16 + b * ((uint32_t)a_bytes >> 4));
                 const uint32_t fresh_mask = c == 0 ? first_mask : 0u;
-                if (A.w_resident) {
+                if (F3) {
+                    // fused split precision: per tap the weight blocks (hi, lo); A_hi B_hi + A_lo B_hi + A_hi B_lo into ONE accumulator
+                    const uint32_t a_lo_buf2 = a_lo_buf + ((uint32_t)A.a_half >> 4);
+#pragma unroll
+                    for (int t = 0; t < MAXT; ++t) {
+                        if (t < A.ntap) {
+                            const uint32_t a_h = a_lo_buf + tap_a[t], a_l = a_lo_buf2 + tap_a[t];
+                            uint32_t slot_h, slot_l;
+                            if (A.w_resident) { slot_h = (uint32_t)(c * A.ntap + t) * 2u; slot_l = slot_h + 1u; }
+                            else {
+                                slot_h = wi % NB; slot_l = (wi + 1) % NB;
+                                HP_T0(m2)
+                                mbar_wait(&w_full[slot_h], (uint32_t)((wi / NB) & 1));
+                                mbar_wait(&w_full[slot_l], (uint32_t)(((wi + 1) / NB) & 1));
+                                HP_ADD(7, m2)
+                            }
+                            const uint32_t b_h = b_lo_k | (sB16 + slot_h * (uint32_t)(B_BYTES >> 4));
+                            const uint32_t b_l = b_lo_k | (sB16 + slot_l * (uint32_t)(B_BYTES >> 4));
+                            if (leader) {
+#pragma unroll
+                                for (int j = 0; j < TK / 16; ++j) {
+                                    umma_bf16(acc0 + tap_col[t], pack_desc(a_h + j * a_step, a_hi), pack_desc(b_h + j * b_step, b_hi), idesc,
+                                              (j > 0 || !((fresh_mask >> t) & 1u)) ? 1u : 0u);
+                                    umma_bf16(acc0 + tap_col[t], pack_desc(a_l + j * a_step, a_hi), pack_desc(b_h + j * b_step, b_hi), idesc, 1u);
+                                    umma_bf16(acc0 + tap_col[t], pack_desc(a_h + j * a_step, a_hi), pack_desc(b_l + j * b_step, b_hi), idesc, 1u);
+                                }
+                                if (!A.w_resident) { umma_commit(&w_empty[slot_h]); umma_commit(&w_empty[slot_l]); }
+                            }
+                            if (!A.w_resident) wi += 2;
+                        }
+                    }
+                } else if (A.w_resident) {
                     const uint32_t b_lo0 = b_lo_k | (sB16 + (uint32_t)(c * A.ntap) * (uint32_t)(B_BYTES >> 4));
 #pragma unroll
                     for (int t = 0; t < MAXT; ++t) {
@@ -586,6 +640,11 @@ __global__ void __launch_bounds__(CTA, 1) conv_halo_tc(const HaloArgs A, const u
                 HP_ADD(10, e1)
                 const bool valid = a < A.cls_Ha[cls] && bcol < A.cls_Wb[cls];
                 const int co0 = tc_.tile_n * BN + c0;
+                if (SPLIT && A.fused3) {                    // the weights went in scaled by 2^8
+                    const float os = A.out_scale;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] *= os;
+                }
                 if (SPLIT && A.accum && valid) {            // a later launch of the split-precision mode: add onto what is stored
                     const int oy_ = a * A.ostr + A.cls_py[cls], ox_ = bcol * A.ostr + A.cls_px[cls];
                     const float* pp = reinterpret_cast<const float*>(A.out) + (((size_t)tc_.img * A.Hout + oy_) * A.Wout + ox_) * A.out_pitch + A.out_ch_off + co0;
@@ -609,7 +668,7 @@ __global__ void __launch_bounds__(CTA, 1) conv_halo_tc(const HaloArgs A, const u
                         v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
                     }
                     if (A.tanh_out) {
-                        if (SPLIT && A.accum) {             // split-precision mode: float32-class output, so the exact function
+                        if (SPLIT && (A.accum || A.fused3)) {   // split-precision modes: float32-class output, so the exact function
 #pragma unroll
                             for (int j = 0; j < 32; ++j) v[j] = tanhf(v[j]);
                         } else {
@@ -833,7 +892,7 @@ static bool make_src_tmap(const rp_conv_src& S, const HaloArgs& H, int KC, CUten
 }
 
 template <int BN, int TK, int NB, bool SPLIT>
-static int launch_halo_impl(const HaloArgs& H0, const void* wp, int h2math, cudaStream_t stream) {
+static int launch_halo_impl(const HaloArgs& H0, const void* wp, int h2math, cudaStream_t stream, bool dry_run) {
     constexpr int KC = TK / 8;
     HaloArgs H = H0;
     // 16-bit sources can take the tiled-TMA loader: halo layout [plane][K core][row][pixel] with 128-byte aligned planes.  In the
@@ -844,9 +903,10 @@ static int launch_halo_impl(const HaloArgs& H0, const void* wp, int h2math, cuda
     // sources always use the gather and its [K core][plane,row,pixel] layout).
     CUtensorMap tm[2];
     memset(tm, 0, sizeof(tm));
-    H.split_lo = (h2math >> 7) & 1; H.accum = (h2math >> 8) & 1;
+    H.split_lo = (h2math >> 7) & 1; H.accum = (h2math >> 8) & 1; H.fused3 = (h2math >> 9) & 1; H.a_half = 0; H.out_scale = 1.f;
+    if (H.fused3) { H.split_lo = 0; H.accum = 0; for (int i = 0; i < H.nsrc; ++i) if (H.src[i].dtype == 1) return RP_ERR_UNSUPPORTED; }   // float32 sources only
     if (H.accum && H.out_bf16) return RP_ERR_UNSUPPORTED;                     // accumulation passes need float32 storage
-    H.use_tma = (((h2math >> 5) & 1) || H.split_lo) ? 0 : (((h2math >> 6) & 1) || H.ntap == 1) ? 1 : 0;
+    H.use_tma = (((h2math >> 5) & 1) || H.split_lo || H.fused3) ? 0 : (((h2math >> 6) & 1) || H.ntap == 1) ? 1 : 0;
     for (int i = 0; i < H.nsrc; ++i) if (H.src[i].dtype != 1) H.use_tma = 0;
     if (H.use_tma) {
         const int ppl = H.PH * H.PW;
@@ -863,6 +923,7 @@ static int launch_halo_impl(const HaloArgs& H0, const void* wp, int h2math, cuda
         }
     }
     if (!H.use_tma) { H.plane_bytes = 0; H.a_bytes = ((KC * H.a_lbo + 127) / 128) * 128; }
+    if (H.fused3) { H.a_half = H.a_bytes; H.a_bytes *= 2; H.out_scale = 1.f / 4096.f; }
     const size_t a_bytes = (size_t)H.a_bytes;
     const size_t fixed = (size_t)EPI_SMEM + (size_t)NB * BN * TK * 2;
     auto kern = conv_halo_tc<BN, TK, NB, SPLIT>;
@@ -876,11 +937,13 @@ static int launch_halo_impl(const HaloArgs& H0, const void* wp, int h2math, cuda
     H.ng = 2;
     for (int ng = MAXNG; ng > 2; ng >>= 1)
         if (H.NPX * ng <= PIXTAB && fixed + (size_t)ng * a_bytes <= limit) { H.ng = ng; break; }
-    H.w_resident = (H.ntn == 1 && H.nkt * H.ntap <= NB) ? 1 : 0;
+    H.w_resident = (H.ntn == 1 && H.nkt * H.ntap * (H.fused3 ? 2 : 1) <= NB) ? 1 : 0;
+    if (H.fused3 && NB < 2) return RP_ERR_UNSUPPORTED;
     H.h2math = h2math & 1; H.dbg = (h2math >> 1) & 15;
 
     const size_t smem = fixed + H.ng * a_bytes;
     if (smem > limit) return RP_ERR_UNSUPPORTED;
+    if (dry_run) return RP_OK;
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { cudaGetLastError(); return RP_ERR_CUDA; }
     static int n_sm = 0;
     if (n_sm == 0) {
@@ -897,9 +960,9 @@ static int launch_halo_impl(const HaloArgs& H0, const void* wp, int h2math, cuda
 // the split-precision launches (flags bit 8 / 9) run their own instantiation: compiled into the common one, the extra paths cost
 // the 16-bit layers registers (spills in three of the eight tile shapes, stem +20 %)
 template <int BN, int TK, int NB>
-static int launch_halo(const HaloArgs& H0, const void* wp, int h2math, cudaStream_t stream) {
-    return ((h2math >> 7) & 3) ? launch_halo_impl<BN, TK, NB, true>(H0, wp, h2math, stream)
-                               : launch_halo_impl<BN, TK, NB, false>(H0, wp, h2math, stream);
+static int launch_halo(const HaloArgs& H0, const void* wp, int h2math, cudaStream_t stream, bool dry_run = false) {
+    return ((h2math >> 7) & 7) ? launch_halo_impl<BN, TK, NB, true>(H0, wp, h2math, stream, dry_run)
+                               : launch_halo_impl<BN, TK, NB, false>(H0, wp, h2math, stream, dry_run);
 }
 
 }  // namespace halo
@@ -942,6 +1005,20 @@ int rp_conv_halo_prof(unsigned long long* out16) {
     unsigned long long z[16] = {0};
     cudaMemcpyToSymbol(halo::g_halo_prof, z, sizeof(z));
     return RP_OK;
+}
+
+// Does the tile plan of this layer fit one CTA's shared memory with these flags (the fused split-precision launch, flags bit
+// 10, keeps two halos per buffer)?  RP_OK / RP_ERR_UNSUPPORTED; launches nothing.
+int rp_conv_halo_fits(const rp_conv_desc* d, int bn, int tk, int flags) {
+    halo::HaloArgs H;
+    if (!d) return RP_ERR_INVALID_ARG;
+    if (!halo::build_halo_args(d, &H, bn, tk, nullptr, (flags & 1) != 0)) return RP_ERR_UNSUPPORTED;
+#define RP_HALO_CASE(BN_, TK_, NB_) if (bn == BN_ && tk == TK_) return halo::launch_halo<BN_, TK_, NB_>(H, nullptr, (flags >> 1), nullptr, true);
+    RP_HALO_CASE(32, 64, 32) RP_HALO_CASE(64, 64, 12) RP_HALO_CASE(128, 64, 6)
+    RP_HALO_CASE(32, 32, 16) RP_HALO_CASE(64, 32, 16) RP_HALO_CASE(128, 32, 8)
+    RP_HALO_CASE(32, 16, 16) RP_HALO_CASE(256, 32, 4)
+#undef RP_HALO_CASE
+    return RP_ERR_UNSUPPORTED;
 }
 
 int rp_conv_layer_halo(const rp_conv_desc* d, const void* w_packed, int bn, int tk, int flags, void* stream_) {

@@ -64,12 +64,15 @@ class ScnetEngine(object):
         import os
         import torch
         # 'tc': tcgen05 tensor-core kernels with 16-bit operands wherever a layer qualifies (default, the throughput mode);
-        # 'tc3': the same kernels in split precision -- float32 activation storage, every tensor-core layer as three launches
-        #        half(x) w_hi + lo(x) w_hi + half(x) lo(w) (x w to ~2^-22, float32 accumulation): float32-class output at
-        #        tensor-core speed, the parity mode for the descriptors that drive the solver;
+        # 'tc3': the same kernels in split precision -- float32 activation storage, every tensor-core layer computed as
+        #        half(x) w_hi + lo(x) w_hi + half(x) lo(w) (x w to ~2^-22, float32 accumulation): ONE launch with a hi and a lo halo
+        #        and three MMAs per K step where that fits shared memory, three accumulating launches otherwise (stride-2
+        #        convolutions).  float32-class output at tensor-core speed: the parity mode for the descriptors that drive the solver;
         # 'fp32': CUDA-core float32 only (the exact-parity reference path of the tests)
         self.mode = mode or os.environ.get("RP_SCNET_MODE", "tc")
         self.split3 = self.mode == 'tc3'
+        # tc3: layers whose doubled halo fits shared memory take ONE fused launch, the others three (RP_SCNET_TC3=passes: always three)
+        self.tc3_fused = os.environ.get("RP_SCNET_TC3", "fused") != "passes"
         if self.split3 and not _lib.h16_is_fp16():
             raise RuntimeError("RP_SCNET_MODE=tc3 needs the IEEE-half build of the library (csrc/rp_h16.cuh)")
         # replay the ~87 layer launches of a forward as one CUDA graph once a shape has been seen twice
@@ -162,7 +165,7 @@ class ScnetEngine(object):
                            torch.empty((P, C), **f), torch.empty((P, C), **f))
 
         B['in20'] = _Act(torch.empty((n, 224, 224, 20), **f), 224, 224, 20, 0, 20)
-        if self.act_bf16:
+        if self.act_bf16 or self.split3:
             B['in96'] = _Act(torch.empty((n, 224, 224, 96), dtype=h16(), device=device), 224, 224, 96, 0, 96)
         for st in ('rgb', 'n', 'd'):
             for wh in ('', '_t2s'):
@@ -248,6 +251,15 @@ class ScnetEngine(object):
             bn_tile = next((b for b in (256, 128, 64, 32) if b <= cap and out.C % b == 0), 32)   # 32: Cout zero-padded (heads)
             ntap = ctypes.c_int(0)
             widx = (ctypes.c_int * 16)()
+            split3 = self.split3 and not wkey.endswith('#split')      # the stem input is already a hi/lo split: one plain launch
+            fused_ok = False
+            if split3 and self.tc3_fused:
+                # the fused split-precision launch keeps a hi and a lo halo per buffer: take the largest K chunk whose doubled
+                # halo still fits next to the weight ring (else the layer runs as three launches at its usual K chunk)
+                for tk_try in ([64, 32] if tk == 64 else [tk]):
+                    if self.lib.rp_conv_halo_fits(ctypes.byref(d), bn_tile, tk_try, self.halo_flags | (1 << 10)) == _lib.RP_OK:
+                        tk, fused_ok = tk_try, True
+                        break
             if bn_tile and self.lib.rp_conv_halo_plan(ctypes.byref(d), bn_tile, tk, self.halo_flags, ctypes.byref(nparts),
                                                       ctypes.byref(ntap), widx) == _lib.RP_OK:
                 use_halo = True
@@ -257,7 +269,19 @@ class ScnetEngine(object):
                     self._packed_tc[key] = pack_halo(w.reshape(k * k, w.shape[2], w.shape[3]), list(widx[:ntap.value]),
                                                      [a.C for a in srcs], out.C, bn_tile, tk)
                 wtc = self._packed_tc[key]
-                if self.split3:
+                fused3 = fused_ok
+                if fused3:
+                    # ONE launch: (hi, lo) block pairs of 2^8 w (both halves in the normal range of IEEE half)
+                    key_f = key + ('f3',)
+                    if key_f not in self._packed_tc:
+                        w = self._packed[wkey].reshape(k * k, self._packed[wkey].shape[2], self._packed[wkey].shape[3]) * 256.0
+                        w_hi = w.to(h16()).float()
+                        taps = list(widx[:ntap.value])
+                        both = torch.cat((w_hi, w - w_hi), 0)                                       # [2 k k, Cin, Cout]
+                        order = [i for t in taps for i in (t, k * k + t)]
+                        self._packed_tc[key_f] = pack_halo(both, order, [a.C for a in srcs], out.C, bn_tile, tk)
+                    wtc = self._packed_tc[key_f]
+                elif split3:
                     key_lo = key + ('lo',)
                     if key_lo not in self._packed_tc:
                         w = self._packed[wkey]
@@ -278,7 +302,9 @@ class ScnetEngine(object):
             d.psum, d.psq = pt.data_ptr(), pt.data_ptr() + 4 * need
         else:
             d.psum, d.psq = None, None
-        if use_halo and self.split3:
+        if use_halo and fused3:
+            self._run("rp_conv_layer_halo", d, wtc.data_ptr(), bn_tile, tk, self.halo_flags | (1 << 10), stream)
+        elif use_halo and split3:
             # x w = half(x) w_hi + [lo(x) w_hi + half(x) lo(w)] 2^-11 with lo(.) = (. - half(.)) 2^11: the first launch stores, the
             # other two add onto the float32 output (flags bit 9), the second with the loader emitting lo(x) (bit 8); bias / tanh
             # / batch statistics belong to the last launch, which sees the complete sum
@@ -392,7 +418,7 @@ class ScnetEngine(object):
 
             def cat(a, b):
                 return [a, b] if skip else [a]           # skipLayer=0: the decoder sees no encoder tensors (:333-357)
-            split_stem = self.act_bf16 and self.halo     # conv1* on tcgen05 from the 16-bit hi/lo split input
+            split_stem = (self.act_bf16 or self.split3) and self.halo     # conv1* on tcgen05 from the 16-bit hi/lo split input
             if split_stem:
                 self._run("rp_scnet_resize_in_split", x.data_ptr(), n, H, W, B['in96'].buf.data_ptr(), stream)
                 for st in ('rgb', 'n', 'd'):

@@ -185,8 +185,8 @@ def test_scnet_constructor_variants(name, mode):
 
 @pytest.mark.parametrize("name", ["suncg", "scannet"])
 def test_scnet_split_precision_tensor_core_mode(name):
-    """mode='tc3': the tcgen05 kernels in split precision (three launches per layer: half(x) w_hi, lo(x) w_hi, half(x) lo(w);
-    float32 storage) against the reference module's golden.  Stated tolerance: 1e-3 max-abs on outputs of magnitude ~10
+    """mode='tc3': the tcgen05 kernels in split precision (half(x) w_hi + lo(x) w_hi + half(x) lo(w): one fused launch where the
+    doubled halo fits shared memory, three launches for the stride-2 layers; float32 storage) against the reference module's golden.  Stated tolerance: 1e-3 max-abs on outputs of magnitude ~10
     (the float32 CUDA-core path is asserted at 5e-4, the 16-bit mode at 0.25); plan / graph replay bit-identical to eager."""
     import torch
     from oracle import scnet_oracle
