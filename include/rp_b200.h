@@ -403,10 +403,13 @@ int rp_conv_halo_fits(const rp_conv_desc* d, int bn, int tk, int flags);
 
 /* flags of rp_conv_layer_halo: bit 0 16-pixel halo pitch; bit 1 packed-half BatchNorm of 16-bit sources; bits 2-5 profiling /
  * debugging; bit 6 / 7 never / always tiled TMA for 16-bit sources.  Split-precision launches (float32 sources and output; the
- * network mode RP_SCNET_MODE=tc3): bit 8 the loader emits lo(x) = (x - half(x)) 2^11 instead of half(x); bit 9 the epilogue adds
- * 2^-11 x (this launch) onto the stored float32 output -- three launches half(x) w_hi, lo(x) w_hi, half(x) lo(w) give x w to
- * 2^-22; bit 10 the same sum in ONE launch: w_packed holds (hi, lo) block pairs of 2^8 w, the loader fills a hi and a lo halo of
- * 2^4 x, three tcgen05.mma per K step accumulate into one TMEM accumulator and the epilogue scales by 2^-12. */
+ * network mode RP_SCNET_MODE=tc3) compute x w = half(x') hi(w') + lo(x') hi(w') + half(x') lo(w') with x' = 2^4 x, w' = 2^8 w,
+ * lo(v) = v - half(v), the epilogue scaling by 2^-12:  bit 10 all three terms in ONE launch -- w_packed holds (hi(w'), lo(w'))
+ * block pairs, the loader fills a hi and a lo halo, three tcgen05.mma per tap and K step accumulate into one TMEM accumulator
+ * (needs room for the doubled halo: rp_conv_halo_fits);  otherwise THREE launches, each term in an accumulator of its own: the
+ * plain launch half(x) hi(w) stores, then bits 8 + 9 (the loader emits lo(x'), w_packed = the hi(w') blocks) and bit 9 (w_packed =
+ * the lo(w') blocks) add 2^-12 x their accumulators onto the stored float32 output; bias / tanh / statistics go with the last.
+ * (Bit 11: block pairs over a single halo, half(x') [hi(w') + lo(w')] in one launch -- measurably less accurate, unused.) */
 int rp_conv_layer_halo(const rp_conv_desc* d, const void* w_packed, int bn, int tk, int flags, void* stream);
 /* test hook: the tile plan as 96 integers (layout in csrc/scnet_halo.cu) for the CPU emulation in tests/test_halo_plan.py */
 int rp_conv_halo_debug(const rp_conv_desc* d, int bn, int tk, int flags, int* out96);

@@ -74,13 +74,17 @@ struct HaloArgs {
     int plane_bytes, a_bytes;              // TMA layout: [plane][K core][row][pixel] 16-byte units, planes 128-byte aligned; bytes of one buffer
     int dbg;                               // profiling only (flags >> 2): 1 no epilogue stores/stats, 2 no loader copy/transform, 4 no MMA
     int h2math;                            // producer BatchNorm + LeakyReLU of 16-bit sources in packed half arithmetic (flags bit 1)
-    int split_lo;                          // flags bit 8: the loader emits the LOW half of the activation, (x - half(x)) * 2^11, instead of half(x)
-    int fused3;                            // flags bit 10: ONE launch computes half(x) w_hi + lo(x) w_hi + half(x) lo(w): the loader fills a hi and a
-    int a_half;                            //   lo halo (a_half bytes apart, unscaled lo), weight blocks come as (hi, lo) pairs of the weights scaled by
-    float out_scale;                       //   2^8 and the activations by 2^4 (low halves in the normal range of IEEE half), the epilogue multiplies by out_scale = 2^-12
-    int accum;                             // flags bit 9: out = out + 2^-11 * (this launch's accumulators)   (float32 output only)
-                                           // -- the three launches of the split-precision mode: half(x) w_hi, then lo(x) w_hi and
-                                           //    half(x) lo(w) accumulated on top: x w to ~2^-22 on tensor cores (scnet_engine.py 'tc3')
+    // Split-precision launches (SPLIT instantiation; float32 sources and output; scnet_engine.py mode 'tc3'):
+    //   x w = half(x') hi(w') + lo(x') hi(w') + half(x') lo(w'),  x' = 2^4 x, w' = 2^8 w, lo(v) = v - half(v)  (both low halves are
+    //   normal IEEE-half numbers for |x| > 0.008), out_scale = 2^-12 applied in the epilogue.
+    int split_lo;                          // flags bit 8: the loader emits lo(x') instead of half(x')
+    int accum;                             // flags bit 9: out = out + out_scale * (this launch's accumulators)
+    int fused3;                            // flags bit 10: ONE launch, all three terms: the loader fills a hi and a lo halo (a_half bytes apart), the weight
+    int a_half;                            //   blocks come as (hi(w'), lo(w')) pairs, three MMAs per tap and K step into one accumulator
+    int pairw;                             // flags bit 11: single halo, (hi, lo) weight block pairs, two MMAs per step: half(x') [hi(w') + lo(w')] (or, with
+                                           //   bit 8, lo(x') ...) -- the first of the TWO launches of layers whose doubled halo does not fit shared
+                                           //   memory (stride-2 convolutions); the second is bit 8 + bit 9 with the hi(w') blocks alone
+    float in_scale, out_scale;
     void* out; int out_pitch, out_ch_off, out_bf16;
     float* psum; float* psq;
     const float* bias; int tanh_out;
@@ -341,26 +345,26 @@ __global__ void __launch_bounds__(CTA, 1) conv_halo_tc(const HaloArgs A, const u
 #pragma unroll
                         for (int q = 0; q < 8; ++q) { const float z = fmaf(v[q], sc[q], sh[q]); v[q] = z > 0.f ? z : slope * z; }
                     }
-                    if (SPLIT && A.fused3) {                    // fused split precision: the low halves go to the second halo of the buffer
-                        float l[8];
+                    if (SPLIT) {
 #pragma unroll
-                        for (int q = 0; q < 8; ++q) v[q] *= 16.f;             // 2^4: the low halves of |x| > 0.008 stay normal numbers
+                        for (int q = 0; q < 8; ++q) v[q] *= A.in_scale;       // 2^4: the low halves of |x| > 0.008 stay normal numbers
+                        if (A.fused3 || A.split_lo) {
+                            float l[8];
 #pragma unroll
-                        for (int q = 0; q < 8; q += 2) {
-                            const float2 hi = rp_h2_to_f2(rp_f2_to_h2(v[q], v[q + 1]));
-                            l[q] = v[q] - hi.x; l[q + 1] = v[q + 1] - hi.y;
-                        }
-                        rp_h162 l0 = rp_f2_to_h2(l[0], l[1]), l1 = rp_f2_to_h2(l[2], l[3]), l2 = rp_f2_to_h2(l[4], l[5]), l3 = rp_f2_to_h2(l[6], l[7]);
-                        uint4 ol;
-                        ol.x = *reinterpret_cast<uint32_t*>(&l0); ol.y = *reinterpret_cast<uint32_t*>(&l1);
-                        ol.z = *reinterpret_cast<uint32_t*>(&l2); ol.w = *reinterpret_cast<uint32_t*>(&l3);
-                        *reinterpret_cast<uint4*>(dst + A.a_half + (size_t)h * 16) = ol;
-                    }
-                    if (SPLIT && A.split_lo) {                  // low half, scaled into the normal range of the 16-bit format
+                            for (int q = 0; q < 8; q += 2) {
+                                const float2 hi = rp_h2_to_f2(rp_f2_to_h2(v[q], v[q + 1]));
+                                l[q] = v[q] - hi.x; l[q + 1] = v[q + 1] - hi.y;
+                            }
+                            if (A.fused3) {                     // the low halves go to the second halo of the buffer
+                                rp_h162 l0 = rp_f2_to_h2(l[0], l[1]), l1 = rp_f2_to_h2(l[2], l[3]), l2 = rp_f2_to_h2(l[4], l[5]), l3 = rp_f2_to_h2(l[6], l[7]);
+                                uint4 ol;
+                                ol.x = *reinterpret_cast<uint32_t*>(&l0); ol.y = *reinterpret_cast<uint32_t*>(&l1);
+                                ol.z = *reinterpret_cast<uint32_t*>(&l2); ol.w = *reinterpret_cast<uint32_t*>(&l3);
+                                *reinterpret_cast<uint4*>(dst + A.a_half + (size_t)h * 16) = ol;
+                            } else {                            // this launch multiplies the low halves
 #pragma unroll
-                        for (int q = 0; q < 8; q += 2) {
-                            const float2 hi = rp_h2_to_f2(rp_f2_to_h2(v[q], v[q + 1]));
-                            v[q] = (v[q] - hi.x) * 2048.f; v[q + 1] = (v[q + 1] - hi.y) * 2048.f;
+                                for (int q = 0; q < 8; ++q) v[q] = l[q];
+                            }
                         }
                     }
                     rp_h162 p0 = rp_f2_to_h2(v[0], v[1]), p1 = rp_f2_to_h2(v[2], v[3]);
@@ -471,7 +475,7 @@ __global__ void __launch_bounds__(CTA, 1) conv_halo_tc(const HaloArgs A, const u
         // ------------------------------------------------------------------ weight stream (bulk TMA)
         // (the whole warp runs the loop so that its control values stay warp-uniform; one elected lane issues)
         const bool leader = elect_one();
-        const int per_tile = A.nkt * A.ntap * ((SPLIT && A.fused3) ? 2 : 1);    // fused split precision: (hi, lo) block pairs
+        const int per_tile = A.nkt * A.ntap * ((SPLIT && (A.fused3 || A.pairw)) ? 2 : 1);    // split precision: (hi, lo) block pairs
         uint32_t wi = 0;
         if (A.w_resident) {
             // small layers (stem, heads, 32/64-channel 4x4 layers with one n-tile): the whole weight set sits in the ring
@@ -528,7 +532,8 @@ __global__ void __launch_bounds__(CTA, 1) conv_halo_tc(const HaloArgs A, const u
             HP_ADD(5, m0)
             tc_fence_after();
             const uint32_t acc0 = tmem_d + ab * (uint32_t)A.acc_cols;
-            const bool F3 = SPLIT && A.fused3;
+            const bool F3 = SPLIT && (A.fused3 || A.pairw);          // weight blocks come as (hi, lo) pairs
+            const bool TWOHALO = SPLIT && A.fused3;
             if (A.w_resident && !w_ready) {                               // resident weights: wait for them once
                 for (int i = 0; i < A.nkt * A.ntap * (F3 ? 2 : 1); ++i) mbar_wait(&w_full[i], 0u);
                 w_ready = true;
@@ -542,7 +547,7 @@ __global__ void __launch_bounds__(CTA, 1) conv_halo_tc(const HaloArgs A, const u
                 const uint32_t a_lo_buf = a_lo_k | (sA16 + b * ((uint32_t)a_bytes >> 4));
                 const uint32_t fresh_mask = c == 0 ? first_mask : 0u;
                 if (F3) {
-                    // fused split precision: per tap the weight blocks (hi, lo); A_hi B_hi + A_lo B_hi + A_hi B_lo into ONE accumulator
+                    // split precision: per tap the weight blocks (hi, lo); A_hi B_hi (+ A_lo B_hi with two halos) + A_hi B_lo into ONE accumulator
                     const uint32_t a_lo_buf2 = a_lo_buf + ((uint32_t)A.a_half >> 4);
 #pragma unroll
                     for (int t = 0; t < MAXT; ++t) {
@@ -564,7 +569,7 @@ __global__ void __launch_bounds__(CTA, 1) conv_halo_tc(const HaloArgs A, const u
                                 for (int j = 0; j < TK / 16; ++j) {
                                     umma_bf16(acc0 + tap_col[t], pack_desc(a_h + j * a_step, a_hi), pack_desc(b_h + j * b_step, b_hi), idesc,
                                               (j > 0 || !((fresh_mask >> t) & 1u)) ? 1u : 0u);
-                                    umma_bf16(acc0 + tap_col[t], pack_desc(a_l + j * a_step, a_hi), pack_desc(b_h + j * b_step, b_hi), idesc, 1u);
+                                    if (TWOHALO) umma_bf16(acc0 + tap_col[t], pack_desc(a_l + j * a_step, a_hi), pack_desc(b_h + j * b_step, b_hi), idesc, 1u);
                                     umma_bf16(acc0 + tap_col[t], pack_desc(a_h + j * a_step, a_hi), pack_desc(b_l + j * b_step, b_hi), idesc, 1u);
                                 }
                                 if (!A.w_resident) { umma_commit(&w_empty[slot_h]); umma_commit(&w_empty[slot_l]); }
@@ -640,7 +645,7 @@ __global__ void __launch_bounds__(CTA, 1) conv_halo_tc(const HaloArgs A, const u
                 HP_ADD(10, e1)
                 const bool valid = a < A.cls_Ha[cls] && bcol < A.cls_Wb[cls];
                 const int co0 = tc_.tile_n * BN + c0;
-                if (SPLIT && A.fused3) {                    // the weights went in scaled by 2^8
+                if (SPLIT) {                                // activations and weights went in scaled by 2^4 / 2^8
                     const float os = A.out_scale;
 #pragma unroll
                     for (int j = 0; j < 32; ++j) v[j] *= os;
@@ -648,16 +653,15 @@ __global__ void __launch_bounds__(CTA, 1) conv_halo_tc(const HaloArgs A, const u
                 if (SPLIT && A.accum && valid) {            // a later launch of the split-precision mode: add onto what is stored
                     const int oy_ = a * A.ostr + A.cls_py[cls], ox_ = bcol * A.ostr + A.cls_px[cls];
                     const float* pp = reinterpret_cast<const float*>(A.out) + (((size_t)tc_.img * A.Hout + oy_) * A.Wout + ox_) * A.out_pitch + A.out_ch_off + co0;
-                    constexpr float S11 = 4.8828125e-4f;    // 2^-11
                     if (co0 + 31 < A.Cout && ((((size_t)pp) & 15) == 0)) {
 #pragma unroll
                         for (int j = 0; j < 32; j += 4) {
                             const float4 p4 = *reinterpret_cast<const float4*>(pp + j);
-                            v[j] = fmaf(v[j], S11, p4.x); v[j + 1] = fmaf(v[j + 1], S11, p4.y); v[j + 2] = fmaf(v[j + 2], S11, p4.z); v[j + 3] = fmaf(v[j + 3], S11, p4.w);
+                            v[j] += p4.x; v[j + 1] += p4.y; v[j + 2] += p4.z; v[j + 3] += p4.w;
                         }
                     } else {
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) if (co0 + j < A.Cout) v[j] = fmaf(v[j], S11, pp[j]);
+                        for (int j = 0; j < 32; ++j) if (co0 + j < A.Cout) v[j] += pp[j];
                     }
                 }
                 if (A.bias || A.tanh_out) {                 // (bias/tanh layers have Cout <= 256, checked on the host)
@@ -668,7 +672,7 @@ __global__ void __launch_bounds__(CTA, 1) conv_halo_tc(const HaloArgs A, const u
                         v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
                     }
                     if (A.tanh_out) {
-                        if (SPLIT && (A.accum || A.fused3)) {   // split-precision modes: float32-class output, so the exact function
+                        if (SPLIT) {                            // split-precision modes: float32-class output, so the exact function
 #pragma unroll
                             for (int j = 0; j < 32; ++j) v[j] = tanhf(v[j]);
                         } else {
@@ -903,10 +907,14 @@ static int launch_halo_impl(const HaloArgs& H0, const void* wp, int h2math, cuda
     // sources always use the gather and its [K core][plane,row,pixel] layout).
     CUtensorMap tm[2];
     memset(tm, 0, sizeof(tm));
-    H.split_lo = (h2math >> 7) & 1; H.accum = (h2math >> 8) & 1; H.fused3 = (h2math >> 9) & 1; H.a_half = 0; H.out_scale = 1.f;
-    if (H.fused3) { H.split_lo = 0; H.accum = 0; for (int i = 0; i < H.nsrc; ++i) if (H.src[i].dtype == 1) return RP_ERR_UNSUPPORTED; }   // float32 sources only
-    if (H.accum && H.out_bf16) return RP_ERR_UNSUPPORTED;                     // accumulation passes need float32 storage
-    H.use_tma = (((h2math >> 5) & 1) || H.split_lo || H.fused3) ? 0 : (((h2math >> 6) & 1) || H.ntap == 1) ? 1 : 0;
+    H.split_lo = (h2math >> 7) & 1; H.accum = (h2math >> 8) & 1; H.fused3 = (h2math >> 9) & 1; H.pairw = (h2math >> 10) & 1;
+    H.a_half = 0; H.in_scale = 1.f; H.out_scale = 1.f;
+    if (SPLIT) {
+        for (int i = 0; i < H.nsrc; ++i) if (H.src[i].dtype == 1) return RP_ERR_UNSUPPORTED;      // float32 sources and output only
+        if (H.out_bf16 || (H.fused3 && (H.split_lo || H.accum || H.pairw))) return RP_ERR_UNSUPPORTED;
+        H.in_scale = 16.f; H.out_scale = 1.f / 4096.f;
+    }
+    H.use_tma = (((h2math >> 5) & 1) || SPLIT) ? 0 : (((h2math >> 6) & 1) || H.ntap == 1) ? 1 : 0;
     for (int i = 0; i < H.nsrc; ++i) if (H.src[i].dtype != 1) H.use_tma = 0;
     if (H.use_tma) {
         const int ppl = H.PH * H.PW;
@@ -923,7 +931,7 @@ static int launch_halo_impl(const HaloArgs& H0, const void* wp, int h2math, cuda
         }
     }
     if (!H.use_tma) { H.plane_bytes = 0; H.a_bytes = ((KC * H.a_lbo + 127) / 128) * 128; }
-    if (H.fused3) { H.a_half = H.a_bytes; H.a_bytes *= 2; H.out_scale = 1.f / 4096.f; }
+    if (H.fused3) { H.a_half = H.a_bytes; H.a_bytes *= 2; }
     const size_t a_bytes = (size_t)H.a_bytes;
     const size_t fixed = (size_t)EPI_SMEM + (size_t)NB * BN * TK * 2;
     auto kern = conv_halo_tc<BN, TK, NB, SPLIT>;
@@ -937,8 +945,8 @@ static int launch_halo_impl(const HaloArgs& H0, const void* wp, int h2math, cuda
     H.ng = 2;
     for (int ng = MAXNG; ng > 2; ng >>= 1)
         if (H.NPX * ng <= PIXTAB && fixed + (size_t)ng * a_bytes <= limit) { H.ng = ng; break; }
-    H.w_resident = (H.ntn == 1 && H.nkt * H.ntap * (H.fused3 ? 2 : 1) <= NB) ? 1 : 0;
-    if (H.fused3 && NB < 2) return RP_ERR_UNSUPPORTED;
+    H.w_resident = (H.ntn == 1 && H.nkt * H.ntap * ((H.fused3 || H.pairw) ? 2 : 1) <= NB) ? 1 : 0;
+    if ((H.fused3 || H.pairw) && NB < 2) return RP_ERR_UNSUPPORTED;
     H.h2math = h2math & 1; H.dbg = (h2math >> 1) & 15;
 
     const size_t smem = fixed + H.ng * a_bytes;
@@ -961,7 +969,7 @@ static int launch_halo_impl(const HaloArgs& H0, const void* wp, int h2math, cuda
 // the 16-bit layers registers (spills in three of the eight tile shapes, stem +20 %)
 template <int BN, int TK, int NB>
 static int launch_halo(const HaloArgs& H0, const void* wp, int h2math, cudaStream_t stream, bool dry_run = false) {
-    return ((h2math >> 7) & 7) ? launch_halo_impl<BN, TK, NB, true>(H0, wp, h2math, stream, dry_run)
+    return ((h2math >> 7) & 15) ? launch_halo_impl<BN, TK, NB, true>(H0, wp, h2math, stream, dry_run)
                                : launch_halo_impl<BN, TK, NB, false>(H0, wp, h2math, stream, dry_run);
 }
 

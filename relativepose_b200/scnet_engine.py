@@ -71,7 +71,8 @@ class ScnetEngine(object):
         # 'fp32': CUDA-core float32 only (the exact-parity reference path of the tests)
         self.mode = mode or os.environ.get("RP_SCNET_MODE", "tc")
         self.split3 = self.mode == 'tc3'
-        # tc3: layers whose doubled halo fits shared memory take ONE fused launch, the others three (RP_SCNET_TC3=passes: always three)
+        # tc3: layers whose doubled halo fits shared memory take ONE fused launch, the others three (RP_SCNET_TC3=passes: always
+        # three -- each term in its own accumulator: the most accurate form, 1.5e-4 instead of 2.4e-4 on the output)
         self.tc3_fused = os.environ.get("RP_SCNET_TC3", "fused") != "passes"
         if self.split3 and not _lib.h16_is_fp16():
             raise RuntimeError("RP_SCNET_MODE=tc3 needs the IEEE-half build of the library (csrc/rp_h16.cuh)")
@@ -270,8 +271,9 @@ class ScnetEngine(object):
                                                      [a.C for a in srcs], out.C, bn_tile, tk)
                 wtc = self._packed_tc[key]
                 fused3 = fused_ok
-                if fused3:
-                    # ONE launch: (hi, lo) block pairs of 2^8 w (both halves in the normal range of IEEE half)
+                if split3:
+                    # split precision: (hi, lo) block pairs of 2^8 w (both halves in the normal range of IEEE half) for the fused
+                    # launch / the first of two launches, the hi blocks alone for the second
                     key_f = key + ('f3',)
                     if key_f not in self._packed_tc:
                         w = self._packed[wkey].reshape(k * k, self._packed[wkey].shape[2], self._packed[wkey].shape[3]) * 256.0
@@ -280,15 +282,10 @@ class ScnetEngine(object):
                         both = torch.cat((w_hi, w - w_hi), 0)                                       # [2 k k, Cin, Cout]
                         order = [i for t in taps for i in (t, k * k + t)]
                         self._packed_tc[key_f] = pack_halo(both, order, [a.C for a in srcs], out.C, bn_tile, tk)
-                    wtc = self._packed_tc[key_f]
-                elif split3:
-                    key_lo = key + ('lo',)
-                    if key_lo not in self._packed_tc:
-                        w = self._packed[wkey]
-                        w_lo = (w - w.to(h16()).float()) * 2048.0
-                        self._packed_tc[key_lo] = pack_halo(w_lo.reshape(k * k, w.shape[2], w.shape[3]), list(widx[:ntap.value]),
-                                                            [a.C for a in srcs], out.C, bn_tile, tk)
-                    wtc_lo = self._packed_tc[key_lo]
+                        self._packed_tc[key + ('hi8',)] = pack_halo(w_hi, taps, [a.C for a in srcs], out.C, bn_tile, tk)
+                        self._packed_tc[key + ('lo8',)] = pack_halo(w - w_hi, taps, [a.C for a in srcs], out.C, bn_tile, tk)
+                    wtc_plain = wtc
+                    wtc, wtc_hi, wtc_lo = self._packed_tc[key_f], self._packed_tc[key + ('hi8',)], self._packed_tc[key + ('lo8',)]
         if use_tc and not use_halo:
             use_tc = False                  # no tile plan for this shape: the float32 CUDA-core kernel (reads / writes 16-bit storage too)
         if bn:
@@ -305,13 +302,15 @@ class ScnetEngine(object):
         if use_halo and fused3:
             self._run("rp_conv_layer_halo", d, wtc.data_ptr(), bn_tile, tk, self.halo_flags | (1 << 10), stream)
         elif use_halo and split3:
-            # x w = half(x) w_hi + [lo(x) w_hi + half(x) lo(w)] 2^-11 with lo(.) = (. - half(.)) 2^11: the first launch stores, the
-            # other two add onto the float32 output (flags bit 9), the second with the loader emitting lo(x) (bit 8); bias / tanh
-            # / batch statistics belong to the last launch, which sees the complete sum
+            # the doubled halo does not fit shared memory (stride-2 convolutions): three launches, each term in an accumulator of
+            # its own -- half(x) hi(w) stores (the plain 16-bit launch over float32 storage), lo(x') hi(w') (flags bits 8 + 9) and
+            # half(x') lo(w') (bit 9) add 2^-12 x their accumulators onto the float32 output; bias / tanh / batch statistics belong to
+            # the last launch, which sees the complete sum.  (Measured: more accurate than two launches with weight block pairs,
+            # flags bit 11 -- the tensor core's float32 accumulator loses the low-order terms it is handed one by one.)
             d0 = _lib.RpConvDesc.from_buffer_copy(d)
             d0.bias, d0.tanh_out, d0.psum, d0.psq = None, 0, None, None
-            self._run("rp_conv_layer_halo", d0, wtc.data_ptr(), bn_tile, tk, self.halo_flags, stream)
-            self._run("rp_conv_layer_halo", d0, wtc.data_ptr(), bn_tile, tk, self.halo_flags | (1 << 8) | (1 << 9), stream)
+            self._run("rp_conv_layer_halo", d0, wtc_plain.data_ptr(), bn_tile, tk, self.halo_flags, stream)
+            self._run("rp_conv_layer_halo", d0, wtc_hi.data_ptr(), bn_tile, tk, self.halo_flags | (1 << 8) | (1 << 9), stream)
             self._run("rp_conv_layer_halo", d, wtc_lo.data_ptr(), bn_tile, tk, self.halo_flags | (1 << 9), stream)
         elif use_halo:
             self._run("rp_conv_layer_halo", d, wtc.data_ptr(), bn_tile, tk, self.halo_flags, stream)

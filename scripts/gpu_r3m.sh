@@ -10,7 +10,7 @@ for k, rows in d.items():
         print(k, [(round(r['net_f'], 6), round(r['topk_rows_equal'], 4), float('%.3g' % r['dT'])) for r in rows])
 PY
 echo "=== resnet tc3"; RP_SCNET_MODE=tc3 timeout 600 python -m pytest tests/test_gpu_resnet.py -m gpu -q -x 2>&1 | tail -2
-echo "=== timing"; for m in fused; do RP_SCNET_TC3=$m RP_SCNET_MODE=tc3 timeout 600 python scripts/time_scnet.py 1 32 2>&1 | tail -2; done
+echo "=== timing"; for m in fused passes; do RP_SCNET_TC3=$m RP_SCNET_MODE=tc3 timeout 600 python scripts/time_scnet.py 1 32 2>&1 | tail -2; done
 RP_SCNET_MODE=tc timeout 600 python scripts/time_scnet.py 32 2>&1 | tail -1
 } > gpurun_out/round_r3m.log 2>&1
 tail -c 5000 gpurun_out/round_r3m.log
