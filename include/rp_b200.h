@@ -272,6 +272,12 @@ int rp_bn_finalize_split(const float* psum, const float* psq, int G, int nparts,
 /* im2col of NHWC float32 [n,H,W,C] into bfloat16 rows [n,Hout,Wout,Kpad] (K = (ky*k+kx)*C + c, zero padded): the 7x7/s2
  * stem of Resnet18_8s (mymodel.py:51-54,85) becomes a 1x1 convolution with K = 352 on the tensor cores */
 int rp_im2col_bf16(const float* x, int n, int H, int W, int C, int k, int s, int p, int Hout, int Wout, int Kpad, void* out, void* stream);
+/* Space-to-depth of an NCHW float32 input [n,C,H,W] (H, W even, 4 C <= Cpad, Cpad % 8 == 0) into 16-bit NHWC [n,H/2,W/2,Cpad]:
+ * channel (dy*2+dx)*C + c of pixel (sy,sx) = x[c, 2 sy + dy, 2 sx + dx], the rest zero.  A k = 7, stride 2, padding 3 convolution
+ * (the Resnet18_8s stem, mymodel.py:51-54,85) is then a 4x4 stride-1 convolution with padding 2 over this tensor (weights
+ * W4[by,bx,(dy*2+dx)*C+c] = W7[2 by + dy - 1, 2 bx + dx - 1, c], zero where the index leaves the 7x7 kernel) -- 16 taps over 32
+ * channels on the halo kernel instead of an im2col matrix 10x the size of the input. */
+int rp_space_to_depth_h16(const float* x, int n, int C, int H, int W, int Cpad, void* out, void* stream);
 /* F.upsample(x,[224,224],'bilinear',align_corners=False) (mymodel.py:261) fused with the channel regrouping of
  * mymodel.py:264-286: in [n,16,H,W] NCHW -> out [n,224,224,20] NHWC = (rgb,mask | normal,mask | depth,mask) x (own, warped) */
 int rp_scnet_resize_in(const float* x, int n, int H, int W, float* out, void* stream);
@@ -369,7 +375,7 @@ int rp_gather_primitives(const float* feat, int C, long long feat_img_stride, co
  * `stream`; the buffers the ops point to must stay allocated (relativepose_b200/scnet_engine.py keeps them per shape). */
 enum { RP_OP_CONV = 1, RP_OP_CONV_TC_REMOVED /* 2: per-tap tcgen05 kernel, removed */, RP_OP_CONV_HALO, RP_OP_BN_FINALIZE, RP_OP_BN_FINALIZE_SPLIT, RP_OP_RESIZE_IN,
        RP_OP_RESIZE_IN_SPLIT, RP_OP_RESIZE_OUT_MAP, RP_OP_IM2COL, RP_OP_BN_RELU_MAXPOOL, RP_OP_BN_ADD_RELU, RP_OP_RESIZE_NHWC,
-       RP_OP_RESIZE_TO_NCHW };
+       RP_OP_RESIZE_TO_NCHW, RP_OP_SPACE_TO_DEPTH };
 typedef struct rp_net_op {
     int32_t kind;         /* RP_OP_* */
     int32_t reserved;

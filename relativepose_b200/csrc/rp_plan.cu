@@ -61,6 +61,10 @@ int run_plan(const rp_net_op* ops, int n_ops, void* stream) {
             rc = rp_resize_to_nchw(as_ptr<const float*>(a[0]), as_int(a[1]), as_int(a[2]), as_int(a[3]), as_int(a[4]), as_ptr<float*>(a[5]),
                                    as_int(a[6]), as_int(a[7]), as_int(a[8]), stream);
             break;
+        case RP_OP_SPACE_TO_DEPTH:
+            rc = rp_space_to_depth_h16(as_ptr<const float*>(a[0]), as_int(a[1]), as_int(a[2]), as_int(a[3]), as_int(a[4]), as_int(a[5]),
+                                       as_ptr<void*>(a[6]), stream);
+            break;
         default: return RP_ERR_UNSUPPORTED;
         }
         if (rc != RP_OK) return rc;

@@ -237,6 +237,36 @@ __global__ void bn_combine_kernel(const double* __restrict__ scratch, int nsplit
 // im2col of an NHWC float32 image batch into bf16 rows [n, Hout, Wout, Kpad], K index = (ky*k + kx)*C + c, zero padded to
 // Kpad (multiple of 32) and outside the image: turns the 7x7/s2 stem of Resnet18_8s (Cin = 7, 49 taps -- too many taps
 // and too few channels for the halo kernel's per-tap K chunks) into a 1x1 convolution with K = 352 on tcgen05.
+// Space-to-depth, NCHW float32 -> NHWC 16-bit (rp_space_to_depth_h16): one thread per output pixel; its 2x2 input pixels are
+// one float2 per (channel, row) -- a warp reads 256 contiguous bytes per (channel, row) -- and it writes Cpad/8 16-byte units.
+template <int CT>            // CT > 0: channel count known at compile time (everything stays in registers); 0: runtime C
+__global__ void __launch_bounds__(256) space_to_depth_kernel(const float* __restrict__ x, int n, int C_, int H, int W, int Cpad,
+                                                             rp_h16* __restrict__ out) {
+    const int C = CT > 0 ? CT : C_;
+    const int Hs = H >> 1, Ws = W >> 1;
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (size_t)n * Hs * Ws) return;
+    const int sx = (int)(idx % Ws), sy = (int)((idx / Ws) % Hs), im = (int)(idx / ((size_t)Ws * Hs));
+    constexpr int NV = CT > 0 ? ((4 * CT + 7) / 8) * 8 : 64;
+    rp_h16 v[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) v[i] = rp_f_to_h(0.f);
+    const float* xb = x + (size_t)im * C * H * W + (size_t)(2 * sy) * W + 2 * sx;
+#pragma unroll
+    for (int c = 0; c < (CT > 0 ? CT : 16); ++c) {
+        if (c < C) {
+            const float2 r0 = __ldg(reinterpret_cast<const float2*>(xb + (size_t)c * H * W));
+            const float2 r1 = __ldg(reinterpret_cast<const float2*>(xb + (size_t)c * H * W + W));
+            v[c] = rp_f_to_h(r0.x); v[C + c] = rp_f_to_h(r0.y); v[2 * C + c] = rp_f_to_h(r1.x); v[3 * C + c] = rp_f_to_h(r1.y);
+        }
+    }
+    uint4* o = reinterpret_cast<uint4*>(out + idx * Cpad);
+    const uint4* vv = reinterpret_cast<const uint4*>(v);
+    const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+    for (int u = 0; u < 8; ++u) if (u < Cpad / 8) o[u] = u < NV / 8 ? vv[u] : z;
+}
+
 constexpr int IC_PX = 32;                          // output pixels (one row segment) per block
 constexpr int IC_ROW = 512;                        // floats per staged input row: (IC_PX*s + k - s) * C <= IC_ROW
 __global__ void __launch_bounds__(256) im2col_bf16_kernel(const float* __restrict__ x, int n, int H, int W, int C, int k, int s, int p,
@@ -871,6 +901,19 @@ int rp_im2col_bf16(const float* x, int n, int H, int W, int C, int k, int s, int
     if (k > 7 || (IC_PX * s + k - s) * C > IC_ROW) return RP_ERR_UNSUPPORTED;
     const size_t blocks = (size_t)n * Hout * ((Wout + IC_PX - 1) / IC_PX);
     im2col_bf16_kernel<<<(unsigned)blocks, 256, 0, stream>>>(x, n, H, W, C, k, s, p, Hout, Wout, Kpad, static_cast<rp_h16*>(out));
+    ++g_conv_launches;
+    return cudaGetLastError() == cudaSuccess ? RP_OK : RP_ERR_CUDA;
+}
+
+int rp_space_to_depth_h16(const float* x, int n, int C, int H, int W, int Cpad, void* out, void* stream_) {
+    if (!x || !out || n < 1 || C < 1) return RP_ERR_INVALID_ARG;
+    if ((H & 1) || (W & 1) || C > 16 || 4 * C > Cpad || (Cpad & 7) || Cpad > 64) return RP_ERR_UNSUPPORTED;
+    if ((reinterpret_cast<uintptr_t>(x) & 7) != 0) return RP_ERR_INVALID_ARG;                 // float2 loads
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    const size_t total = (size_t)n * (H / 2) * (W / 2);
+    const unsigned nb = (unsigned)((total + 255) / 256);
+    if (C == 7) space_to_depth_kernel<7><<<nb, 256, 0, stream>>>(x, n, C, H, W, Cpad, static_cast<rp_h16*>(out));
+    else space_to_depth_kernel<0><<<nb, 256, 0, stream>>>(x, n, C, H, W, Cpad, static_cast<rp_h16*>(out));
     ++g_conv_launches;
     return cudaGetLastError() == cudaSuccess ? RP_OK : RP_ERR_CUDA;
 }

@@ -51,7 +51,13 @@ class ResnetEngine(ScnetEngine):
             if ent is not None:                                        # one native call (rp_resnet18_8s_forward)
                 xs, ys, plan = ent
                 with torch.cuda.device(x.device):
-                    xs.copy_(x.permute(0, 2, 3, 1))
+                    if xs is None:                                     # op 0 (space-to-depth) reads the caller's tensor in place
+                        xc = x.contiguous().float()
+                        if xc.data_ptr() % 8:
+                            xc = xc.clone()
+                        plan[0][0].arg[0] = xc.data_ptr()
+                    else:
+                        xs.copy_(x.permute(0, 2, 3, 1))
                     self._run_plan(plan)
                 return ys.clone()
             self._seen[key] = self._seen.get(key, 0) + 1
@@ -62,7 +68,7 @@ class ResnetEngine(ScnetEngine):
                     rec = self._rec
                 finally:
                     self._rec = None
-                self._plans = {key: (self._xin_buf, ys, ((_lib.RpNetOp * len(rec))(*rec), len(rec)))}
+                self._plans = {key: (None if self._x_direct else self._xin_buf, ys, ((_lib.RpNetOp * len(rec))(*rec), len(rec)))}
                 return ys.clone()
         return self._forward_impl(x, trace)
 
@@ -92,12 +98,41 @@ class ResnetEngine(ScnetEngine):
             def co(h, k, s, p):
                 return (h + 2 * p - k) // s + 1
 
-            self._xin_buf = self._take((n, H, W, cin), torch.float32)
-            self._xin_buf.copy_(x.permute(0, 2, 3, 1))                             # NCHW -> NHWC copy of the input (plumbing)
-            xin = _Act(self._xin_buf, H, W, cin, 0, cin)
             H1, W1 = co(H, 7, 2, 3), co(W, 7, 2, 3)
             c1 = act(H1, W1, 64)
-            if self.mode == 'tc' and self.halo:
+            s2d = self.mode == 'tc' and self.halo and H % 2 == 0 and W % 2 == 0 and 4 * cin <= 32 and x.data_ptr() % 8 == 0
+            self._x_direct = s2d                           # the first op of the forward reads the caller's NCHW tensor itself
+            if s2d:
+                # 7x7/s2 stem (Cin = num_input) as a 4x4 stride-1 convolution over the 2x2 space-to-depth input: one kernel turns the
+                # caller's NCHW float32 tensor into 16-bit NHWC [n,H/2,W/2,32] (no NCHW->NHWC copy, no im2col matrix -- that was
+                # 1.15 GB written and read back per 64 images), then 16 taps x 32 channels on the halo kernel
+                sd = self._take((n, H // 2, W // 2, 32), h16())
+                self._run("rp_space_to_depth_h16", x.data_ptr(), n, cin, H, W, 32, sd.data_ptr(), stream)
+                if 'resnet18_32s.conv1#s2d' not in self._packed:
+                    w = self._packed['resnet18_32s.conv1']                                   # [7,7,cin,64]
+                    w4 = torch.zeros((4, 4, 32, w.shape[3]), dtype=torch.float32, device=w.device)
+                    for by in range(4):
+                        for dy in range(2):
+                            ky = 2 * by + dy - 1
+                            if not 0 <= ky < 7:
+                                continue
+                            for bx in range(4):
+                                for dx in range(2):
+                                    kx = 2 * bx + dx - 1
+                                    if 0 <= kx < 7:
+                                        q = dy * 2 + dx
+                                        w4[by, bx, q * cin:(q + 1) * cin] = w[ky, kx]
+                    self._packed['resnet18_32s.conv1#s2d'] = w4.contiguous()
+                self._conv('resnet18_32s.conv1', [_Act(sd, H // 2, W // 2, 32, 0, 32)], c1, False, 4, 1, 2, stream=stream,
+                           bn_params=(tr.bn1.weight, tr.bn1.bias), wkey='resnet18_32s.conv1#s2d')
+                xin = None
+            else:
+                self._xin_buf = self._take((n, H, W, cin), torch.float32)
+                self._xin_buf.copy_(x.permute(0, 2, 3, 1))                             # NCHW -> NHWC copy of the input (plumbing)
+                xin = _Act(self._xin_buf, H, W, cin, 0, cin)
+            if s2d:
+                pass
+            elif self.mode == 'tc' and self.halo:
                 # 7x7/s2 stem (Cin = num_input): im2col into bf16 rows of K = 49*Cin padded to a multiple of 32, then a 1x1
                 # convolution on the halo kernel (the CUDA-core implicit GEMM took 58 % of the forward)
                 Kp = -(-(49 * cin) // 32) * 32
