@@ -413,6 +413,39 @@ def run_c4(torch, dev, rank, world, total_pairs, barrier, max_over_ranks):
 
 
 # --------------------------------------------------------------------------------------------- CUDA arm
+def pin_to_gpu_numa_node(torch, local_rank):
+    """Multi-GPU runs: keep this rank's threads (and therefore the pages of its pinned staging buffers, first touch) on the NUMA
+    node its GPU hangs off -- eight ranks each streaming 155 MB per step out of host memory otherwise cross the socket link.
+    Best effort: returns a description, or None when the topology is not exposed (single node, container without sysfs)."""
+    try:
+        bdf = torch.cuda.get_device_properties(local_rank).pci_bus_id if hasattr(torch.cuda.get_device_properties(local_rank), "pci_bus_id") else None
+        if bdf is None:
+            import subprocess
+            out = subprocess.run(["nvidia-smi", "--query-gpu=pci.bus_id", "--format=csv,noheader", "-i", str(local_rank)],
+                                 stdout=subprocess.PIPE, text=True, timeout=10).stdout.strip()
+            bdf = out.splitlines()[0].strip() if out else None
+        if not bdf:
+            return None
+        bdf = bdf.lower()
+        if len(bdf.split(":")[0]) == 8:                    # nvidia-smi prints an 8-digit domain, sysfs uses 4
+            bdf = bdf[4:]
+        node = int(open("/sys/bus/pci/devices/%s/numa_node" % bdf).read().strip())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = os.sched_getaffinity(0)
+        cpus &= allowed
+        if len(cpus) < 2 or cpus == allowed:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return {"numa_node": node, "cpus": len(cpus)}
+    except Exception:
+        return None
+
+
 def run_cuda_arm(args):
     import torch
     from relativepose_b200 import _lib, synth
@@ -424,6 +457,7 @@ def run_cuda_arm(args):
         raise RuntimeError("bench.py (impl=cuda) needs a CUDA device; there is no CPU fallback")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa = pin_to_gpu_numa_node(torch, local_rank) if world > 1 else None
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
@@ -560,6 +594,7 @@ def run_cuda_arm(args):
         "e2e_records": {"value": e2e_records, "unit": UNIT, "api": "RPModule.rpmodule.RelativePoseEstimation_batch(list of record "
                         "dicts): concatenation + pinning + H2D + solve + D2H timed"},
         "gpu_launches": int(launches),
+        "host_affinity": numa if numa else ("not pinned (single GPU)" if world == 1 else "not pinned (no NUMA topology exposed)"),
         "clocks": clocks,
         "roofline": {
             "bound": "issue", "kernel": "rp_solve_kernel<false,false>", "kernel_ms": float(np.mean(kern_ms)),

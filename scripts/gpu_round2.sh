@@ -7,7 +7,7 @@ import json
 txt = open('gpurun_out/bench_line_N2.txt').read().strip().splitlines()
 try:
     d = json.loads(txt[-1])
-    print({k: d[k] for k in ('value', 'n_gpus', 'ms_per_step')}, 'e2e', d['e2e']['value'], d['parity'], {k: (v.get('pairs_per_s'), v.get('ms')) for k, v in d['extra'].items()})
+    print(d.get('host_affinity'), {k: d[k] for k in ('value', 'n_gpus', 'ms_per_step')}, 'e2e', d['e2e']['value'], d['parity'], {k: (v.get('pairs_per_s'), v.get('ms')) for k, v in d['extra'].items()})
 except Exception as e:
     print("parse failed", e, txt[-3:])
 PY
