@@ -5,6 +5,28 @@ from . import _lib
 from .scnet_engine import ScnetEngine, _Act, h16
 
 
+def stem_weights_s2d(w, cpad):
+    """Weights [7,7,Cin,Cout] of a k = 7, stride 2, padding 3 convolution -> [4,4,cpad,Cout] of the equivalent 4x4 stride-1,
+    padding-2 convolution over the 2x2 space-to-depth input (channel (dy*2+dx)*Cin + c of pixel (sy,sx) = x[c, 2 sy + dy,
+    2 sx + dx], csrc/scnet.cu: space_to_depth_kernel): input row 2 oy + ky - 3 = 2 (oy + by - 2) + dy  <=>  ky = 2 by + dy - 1,
+    and the one (by = 0, dy = 0) combination that leaves the 7x7 kernel gets zero weights."""
+    import torch
+    cin = w.shape[2]
+    w4 = torch.zeros((4, 4, cpad, w.shape[3]), dtype=torch.float32, device=w.device)
+    for by in range(4):
+        for dy in range(2):
+            ky = 2 * by + dy - 1
+            if not 0 <= ky < 7:
+                continue
+            for bx in range(4):
+                for dx in range(2):
+                    kx = 2 * bx + dx - 1
+                    if 0 <= kx < 7:
+                        q = dy * 2 + dx
+                        w4[by, bx, q * cin:(q + 1) * cin] = w[ky, kx]
+    return w4.contiguous()
+
+
 class ResnetEngine(ScnetEngine):
     _slope = 0.0          # ReLU
     _act_default = 'fp32' # the pooling / residual / resize kernels of the trunk are float32
@@ -109,20 +131,7 @@ class ResnetEngine(ScnetEngine):
                 sd = self._take((n, H // 2, W // 2, 32), h16())
                 self._run("rp_space_to_depth_h16", x.data_ptr(), n, cin, H, W, 32, sd.data_ptr(), stream)
                 if 'resnet18_32s.conv1#s2d' not in self._packed:
-                    w = self._packed['resnet18_32s.conv1']                                   # [7,7,cin,64]
-                    w4 = torch.zeros((4, 4, 32, w.shape[3]), dtype=torch.float32, device=w.device)
-                    for by in range(4):
-                        for dy in range(2):
-                            ky = 2 * by + dy - 1
-                            if not 0 <= ky < 7:
-                                continue
-                            for bx in range(4):
-                                for dx in range(2):
-                                    kx = 2 * bx + dx - 1
-                                    if 0 <= kx < 7:
-                                        q = dy * 2 + dx
-                                        w4[by, bx, q * cin:(q + 1) * cin] = w[ky, kx]
-                    self._packed['resnet18_32s.conv1#s2d'] = w4.contiguous()
+                    self._packed['resnet18_32s.conv1#s2d'] = stem_weights_s2d(self._packed['resnet18_32s.conv1'], 32)
                 self._conv('resnet18_32s.conv1', [_Act(sd, H // 2, W // 2, 32, 0, 32)], c1, False, 4, 1, 2, stream=stream,
                            bn_params=(tr.bn1.weight, tr.bn1.bias), wkey='resnet18_32s.conv1#s2d')
                 xin = None

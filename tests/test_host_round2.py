@@ -148,3 +148,26 @@ def test_scnet_constructor_variants_state_dict_and_oracle():
     y = scnet_oracle.forward(sd, x, int(snum), bool(tanh), skip=bool(skip), heads=tuple(net.heads)).numpy()
     sub = G[name + '/sub']
     assert np.abs(y[:, :, ::8, ::16] - sub).max() <= 1e-4 * max(1.0, np.abs(sub).max())
+
+
+def test_resnet_stem_space_to_depth_weights():
+    """The Resnet18_8s stem (mymodel.py:51-54,85: conv 7x7, stride 2, padding 3) as a 4x4 stride-1 convolution over the 2x2
+    space-to-depth input: the weight rearrangement of resnet_engine.stem_weights_s2d against torch's conv2d on the CPU."""
+    import torch
+    import torch.nn.functional as F
+    from relativepose_b200.resnet_engine import stem_weights_s2d
+    torch.manual_seed(3)
+    n, C, H, W, Co = 2, 7, 20, 36, 5
+    x = torch.randn(n, C, H, W, dtype=torch.float64)
+    w = torch.randn(Co, C, 7, 7, dtype=torch.float64)
+    ref = F.conv2d(x, w, None, stride=2, padding=3)                                   # [n,Co,10,18]
+    w4 = stem_weights_s2d(w.permute(2, 3, 1, 0).float(), 32).double()                 # [4,4,32,Co]
+    # space-to-depth exactly as the kernel lays it out: channel (dy*2+dx)*C + c
+    sd = torch.zeros(n, 32, H // 2, W // 2, dtype=torch.float64)
+    for dy in range(2):
+        for dx in range(2):
+            q = dy * 2 + dx
+            sd[:, q * C:(q + 1) * C] = x[:, :, dy::2, dx::2]
+    out = F.conv2d(F.pad(sd, (2, 1, 2, 1)), w4.permute(3, 2, 0, 1), None, stride=1)   # padding 2 before, 1 after = rows 0..H/2-1 of p = 2
+    assert out.shape == ref.shape
+    assert (out - ref).abs().max() <= 1e-5 * ref.abs().max()
