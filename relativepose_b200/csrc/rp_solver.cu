@@ -92,6 +92,8 @@ struct SolveArgs {
     size_t sm_mask_off;     // byte offset of the bit mask in dynamic shared memory (when mask_in_smem)
     int dyn_in_global;      // scan pairs too large for shared memory: the per-pair vectors live in the slot (o_dyn)
     size_t o_dyn;
+    int pi_switch;          // ROBUST variant: plain power steps before the accelerated iteration takes over
+    int pi_fast_cap;        // fast variant: power steps per alternation after which a pair is handed to the ROBUST variant
     size_t sm_geo_off;      // 512-thread build: byte offset of the fitters' geometry copy in dynamic shared memory (0: none)
     int csr_smem_cap;       // small batches (fewer CTAs than fit an SM): CSR entries that fit the idle shared memory, else 0
     size_t sm_csr_off;
@@ -868,9 +870,13 @@ __device__ __forceinline__ bool ritz_max(const double B[4][4], int n, double a[3
     return true;
 }
 
-constexpr int PI_SWITCH = 48;       // ROBUST variant: plain power steps before the accelerated iteration takes over
-constexpr int PI_FAST_CAP = 192;    // fast variant: power steps after which a pair is handed to the ROBUST variant (which redoes the
-                                    // whole pair: dense, flat-weighted graphs need 50-90 steps per alternation and must not pay that)
+constexpr int PI_SWITCH = 16;       // ROBUST variant: plain power steps before the accelerated iteration takes over
+constexpr int PI_FAST_CAP = 48;     // fast variant: power steps per alternation after which a pair is handed to the ROBUST variant (which
+                                    // redoes the whole pair).  Measured on B200 (32 dense 9 k-edge pairs / the 4 096-pair headline batch,
+                                    // whose pairs need <= 13 steps): cap 192, switch 48 -> 6.9 ms / 720 k pairs/s; 96, 48 -> 5.3 ms; 48, 48
+                                    // -> 3.5 ms; 48, 16 -> 2.8 ms / 719 k; 32, 16 -> 2.6 ms.  A pair that needs ~70 steps per alternation
+                                    // costs the same either way (the redo is worth ~60 steps); beyond that the accelerated iteration wins.
+                                    // RP_PI_FAST_CAP / RP_PI_SWITCH in the environment override both (tuning aid).
 constexpr int RP_STATUS_RETRY = -100;   // internal: pair waits for the ROBUST pass (never visible to the caller)
 
 // Continuation of the power iteration for graphs whose two leading eigenvalues nearly coincide (two weakly coupled
@@ -1003,7 +1009,7 @@ __device__ __forceinline__ int lopcg_continue(Shared& sh, const PairView& pv, do
 // one-step-stale lambda.  On return pv.ua holds the unit eigenvector (non-negative).
 template <bool USE_SV, bool ROBUST>
 __device__ int power_iteration(Shared& sh, const PairView& pv, double tol, int max_it, bool warm,
-                               int& red_buf, int* converged) {
+                               int& red_buf, int* converged, int fast_cap, int pi_switch) {
     const int tid = threadIdx.x;
     const int N = pv.N;
     for (int c = tid; c < N; c += T) pv.ub[c] = 0.0;     // rows without non-zeros stay 0 in both buffers
@@ -1021,7 +1027,7 @@ __device__ int power_iteration(Shared& sh, const PairView& pv, double tol, int m
     int it = 0;
     *converged = 0;
     double res_prev = CUDART_INF;
-    const int cap = ROBUST ? PI_SWITCH : PI_FAST_CAP;
+    const int cap = ROBUST ? pi_switch : fast_cap;
     const int max_pi = max_it < cap ? max_it : cap;
     bool dead = false;
     for (it = 0; it < max_pi; ++it) {
@@ -1046,7 +1052,7 @@ __device__ int power_iteration(Shared& sh, const PairView& pv, double tol, int m
       for (int p = tid; p < N; p += T) pv.ua[p] = cur[p] * inv; }   // leave the unit vector in pv.ua
     __syncthreads();
     if (ROBUST) {
-        if (!*converged && !dead && it >= PI_SWITCH && max_it > PI_SWITCH)
+        if (!*converged && !dead && it >= pi_switch && max_it > pi_switch)
             it += lopcg_continue<USE_SV>(sh, pv, tol, max_it - it, red_buf, converged);
     } else if (dead) {
         *converged = 1;                                  // zero matrix: nothing a second pass could improve
@@ -1830,10 +1836,10 @@ __global__ void __launch_bounds__(T, RP_MIN_BLOCKS) rp_solve_kernel(const SolveA
                 residual_to_h(pv);
                 int conv = 0;
                 if (prof) clk0 = clock64();
-                int it = power_iteration<false, ROBUST>(sh, pv, par.power_tol, par.max_power_iters, alt > 0, red_buf, &conv);
+                int it = power_iteration<false, ROBUST>(sh, pv, par.power_tol, par.max_power_iters, alt > 0, red_buf, &conv, A.pi_fast_cap, A.pi_switch);
                 if (prof) { clk_pi += clock64() - clk0; if (tid == 0) A.dbg.phase_clk[(size_t)b * 8 + 6] = clk_pi; }
                 tot_it += it; max_it_seen = it > max_it_seen ? it : max_it_seen; not_conv |= !conv;
-                if (!ROBUST && !conv && par.max_power_iters > PI_FAST_CAP) { retry = true; break; }
+                if (!ROBUST && !conv && par.max_power_iters > A.pi_fast_cap) { retry = true; break; }
                 if (A.has_dbg && A.dbg.u) for (int c = tid; c < N; c += T) A.dbg.u[((size_t)b * NUM_ALTER + alt) * A.dbg.u_stride + c] = pv.ua[c];
                 x_degrees(sh, pv, mu);
                 irls_rounds(sh, pv, mu, red_buf);
@@ -1846,9 +1852,9 @@ __global__ void __launch_bounds__(T, RP_MIN_BLOCKS) rp_solve_kernel(const SolveA
                 residual_pass(sh, pv, mu, false);
                 residual_to_h(pv);
                 int conv = 0;
-                int it = power_iteration<true, ROBUST>(sh, pv, par.power_tol, par.max_power_iters, false, red_buf, &conv);
+                int it = power_iteration<true, ROBUST>(sh, pv, par.power_tol, par.max_power_iters, false, red_buf, &conv, A.pi_fast_cap, A.pi_switch);
                 tot_it += it; max_it_seen = it > max_it_seen ? it : max_it_seen; not_conv |= !conv;
-                if (!ROBUST && !conv && par.max_power_iters > PI_FAST_CAP) { retry = true; break; }
+                if (!ROBUST && !conv && par.max_power_iters > A.pi_fast_cap) { retry = true; break; }
                 if (A.has_dbg && A.dbg.u) for (int c = tid; c < N; c += T) A.dbg.u[((size_t)b * NUM_ALTER + alt) * A.dbg.u_stride + c] = pv.ua[c];
                 x_degrees(sh, pv, mu);
                 for (int c = tid; c < N; c += T) pv.sv[c] = pv.ua[c];     // next affinity uses allWP = mu*x (:126,148)
@@ -1912,6 +1918,18 @@ bool make_layout(int max_ns, int max_topk, long long edge_cap, size_t dyn_bytes,
 }
 
 int default_slots_uncached(size_t smem_bytes);
+
+int pi_switch() {
+    static int v = 0;
+    if (v == 0) { const char* e = getenv("RP_PI_SWITCH"); v = e ? atoi(e) : PI_SWITCH; if (v < 4) v = 4; }
+    return v;
+}
+
+int pi_fast_cap() {                 // PI_FAST_CAP, or RP_PI_FAST_CAP from the environment (tuning aid)
+    static int v = 0;
+    if (v == 0) { const char* e = getenv("RP_PI_FAST_CAP"); v = e ? atoi(e) : PI_FAST_CAP; if (v < 8) v = 8; }
+    return v;
+}
 
 // cudaFuncAttributeMaxDynamicSharedMemorySize of both kernel variants, raised on demand and never lowered (launches with
 // different plans may be in flight on several streams; the attribute only has to cover the largest of them)
@@ -2081,7 +2099,7 @@ int solve_batch_impl(int B, const int32_t* off_s, const int32_t* off_t,
     a.has_dbg = dbg ? 1 : 0;
     if (dbg) a.dbg = *dbg; else { rp_debug z = {}; a.dbg = z; }
     a.mask_in_smem = P.mask_in_smem; a.tfeat_stride = S.tfeat_stride; a.sm_mask_off = S.mask_off;
-    a.csr_smem_cap = P.csr_cap; a.sm_csr_off = P.csr_off; a.sm_geo_off = P.geo_off;
+    a.csr_smem_cap = P.csr_cap; a.sm_csr_off = P.csr_off; a.sm_geo_off = P.geo_off; a.pi_fast_cap = pi_fast_cap(); a.pi_switch = pi_switch();
     a.dyn_in_global = S.dyn_in_global; a.o_dyn = L.o_dyn;
     if (cudaMemsetAsync(workspace, 0, 256, stream) != cudaSuccess) { cudaGetLastError(); return RP_ERR_CUDA; }
     if (S.dyn_in_global) rp_solve_kernel<false, true><<<grid, T, P.bytes, stream>>>(a);
@@ -2143,7 +2161,7 @@ int spectral_irls_impl(int B, const int32_t* node_off,
     a.T_out = T_out; a.status = status; a.stats = stats;
     a.stop_after = RP_STAGE_SOLVE; a.has_dbg = 0;
     a.mask_in_smem = P.mask_in_smem; a.tfeat_stride = S.tfeat_stride; a.sm_mask_off = S.mask_off;
-    a.csr_smem_cap = P.csr_cap; a.sm_csr_off = P.csr_off; a.sm_geo_off = P.geo_off;
+    a.csr_smem_cap = P.csr_cap; a.sm_csr_off = P.csr_off; a.sm_geo_off = P.geo_off; a.pi_fast_cap = pi_fast_cap(); a.pi_switch = pi_switch();
     a.dyn_in_global = S.dyn_in_global; a.o_dyn = L.o_dyn;
     if (cudaMemsetAsync(workspace, 0, 256, stream) != cudaSuccess) { cudaGetLastError(); return RP_ERR_CUDA; }
     if (S.dyn_in_global) rp_solve_kernel<false, true><<<grid, T, P.bytes, stream>>>(a);
