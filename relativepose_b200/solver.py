@@ -58,6 +58,16 @@ def zero_row_topk(n_t, K):
     return _ZERO_ROW_CACHE[key]
 
 
+def wave_chunks(B, slots):
+    """Chunk boundaries [0, ..., B] of the pipelined host path: every chunk is the pairs one wave of `slots` resident CTAs takes,
+    a tail shorter than a quarter wave joins the chunk before it."""
+    per = max(1, int(slots))
+    bounds = list(range(0, B, per)) + [B]
+    if len(bounds) > 2 and bounds[-1] - bounds[-2] < per // 4:
+        del bounds[-2]
+    return bounds
+
+
 class PinnedArena(object):
     """One growing block of page-locked host memory handed out in 256-byte aligned slices (reset per batch): packing a
     list of records costs the copies only, not a cudaHostAlloc per array."""
@@ -443,10 +453,7 @@ class PoseSolver(object):
                 # chunk = the pairs one wave of resident CTAs takes (key[5] slots): a launch over a whole number of waves wastes
                 # no SM time on a ragged last wave, and the copy of wave c+1 hides behind the kernel of wave c.  Measured on
                 # B200, 4096 pairs: 7 chunks of 585 -> 6.26 ms, 4 chunks of 1024 (1.7 waves each) -> 6.93 ms, 6 chunks -> 8.75 ms.
-                per = max(1, int(key[5]))
-                bounds = list(range(0, B, per)) + [B]
-                if len(bounds) > 2 and bounds[-1] - bounds[-2] < per // 4:
-                    del bounds[-2]                     # a short tail joins the previous chunk
+                bounds = wave_chunks(B, int(key[5]))
                 chunks = len(bounds) - 1
             else:
                 bounds = [B * c // chunks for c in range(chunks + 1)]

@@ -171,3 +171,17 @@ def test_resnet_stem_space_to_depth_weights():
     out = F.conv2d(F.pad(sd, (2, 1, 2, 1)), w4.permute(3, 2, 0, 1), None, stride=1)   # padding 2 before, 1 after = rows 0..H/2-1 of p = 2
     assert out.shape == ref.shape
     assert (out - ref).abs().max() <= 1e-5 * ref.abs().max()
+
+
+def test_wave_aligned_chunks():
+    """PoseSolver._solve_pipelined cuts a batch into waves of resident CTAs (solver.wave_chunks): whole waves, in order, covering
+    every pair exactly once; a short tail joins the previous chunk."""
+    from relativepose_b200.solver import wave_chunks
+    assert wave_chunks(4096, 592) == [0, 592, 1184, 1776, 2368, 2960, 3552, 4096]
+    assert wave_chunks(592, 592) == [0, 592]
+    assert wave_chunks(100, 592) == [0, 100]
+    assert wave_chunks(1200, 592) == [0, 592, 1200]                # 16-pair tail joins the second wave
+    assert wave_chunks(1400, 592) == [0, 592, 1184, 1400]
+    for B, per in ((1, 1), (7, 3), (5000, 148), (2048, 592)):
+        b = wave_chunks(B, per)
+        assert b[0] == 0 and b[-1] == B and all(lo < hi for lo, hi in zip(b, b[1:]))
