@@ -289,6 +289,12 @@ int rp_scnet_resize_out(const float* in, int n, int C, int H, int W, float* out,
 /* same with `pitch` floats per pixel in memory and a device channel map (output channel c reads cmap[c]): the engine keeps
  * every head at a 16-byte aligned channel offset of the 224x224 tensor */
 int rp_scnet_resize_out_map(const float* in, int n, int pitch, const int* cmap, int C, int H, int W, float* out, void* stream);
+/* the same for a subset of the channels of an output tensor [n, out_channels, H, W]: item i reads source channel cmap[i] and writes
+ * output channel omap[i] (device arrays of C ints); the other output channels are not touched.  The batched alternation
+ * (relativepose_b200/pipeline.py) only reads the normal / depth / descriptor heads of the completion network, so the other heads
+ * are neither computed nor resized there */
+int rp_scnet_resize_out_sub(const float* in, int n, int pitch, const int* cmap, const int* omap, int C, int H, int W, float* out,
+                            int out_channels, void* stream);
 
 /* Stage entry: the fitters only (rpmodule.py:484-508; fit_horn87 :60, fit_spectral :86, fit_irls :169, fit_irls_sm :212,
  * horn87_np :17).  Problem b owns nodes [node_off[b], node_off[b+1]) = candidate correspondences with source/target
@@ -375,7 +381,7 @@ int rp_gather_primitives(const float* feat, int C, long long feat_img_stride, co
  * `stream`; the buffers the ops point to must stay allocated (relativepose_b200/scnet_engine.py keeps them per shape). */
 enum { RP_OP_CONV = 1, RP_OP_CONV_TC_REMOVED /* 2: per-tap tcgen05 kernel, removed */, RP_OP_CONV_HALO, RP_OP_BN_FINALIZE, RP_OP_BN_FINALIZE_SPLIT, RP_OP_RESIZE_IN,
        RP_OP_RESIZE_IN_SPLIT, RP_OP_RESIZE_OUT_MAP, RP_OP_IM2COL, RP_OP_BN_RELU_MAXPOOL, RP_OP_BN_ADD_RELU, RP_OP_RESIZE_NHWC,
-       RP_OP_RESIZE_TO_NCHW, RP_OP_SPACE_TO_DEPTH };
+       RP_OP_RESIZE_TO_NCHW, RP_OP_SPACE_TO_DEPTH, RP_OP_RESIZE_OUT_SUB };
 typedef struct rp_net_op {
     int32_t kind;         /* RP_OP_* */
     int32_t reserved;

@@ -63,11 +63,11 @@ class RpNetOp(ctypes.Structure):
 # op kinds of rp_scnet_forward / rp_resnet18_8s_forward (include/rp_b200.h: RP_OP_*), keyed by the layer entry point
 NET_OPS = {"rp_conv_layer": 1, "rp_conv_layer_halo": 3, "rp_bn_finalize": 4, "rp_bn_finalize_split": 5,
            "rp_scnet_resize_in": 6, "rp_scnet_resize_in_split": 7, "rp_scnet_resize_out_map": 8, "rp_im2col_bf16": 9,
-           "rp_bn_relu_maxpool": 10, "rp_bn_add_relu": 11, "rp_resize_nhwc": 12, "rp_resize_to_nchw": 13, "rp_space_to_depth_h16": 14}
+           "rp_bn_relu_maxpool": 10, "rp_bn_add_relu": 11, "rp_resize_nhwc": 12, "rp_resize_to_nchw": 13, "rp_space_to_depth_h16": 14, "rp_scnet_resize_out_sub": 15}
 
 EXPORTS = ("rp_abi_version", "rp_device_info", "rp_solve_workspace_bytes", "rp_solve_batch",
            "rp_solve_batch_ex", "rp_solve_default_slots", "rp_solver_wide_max", "rp_solve_pair_host", "rp_h16_format", "rp_match_topk", "rp_launch_count", "rp_spectral_irls_solve", "rp_spectral_irls_workspace_bytes",
-           "rp_conv_nparts", "rp_conv_layer", "rp_bn_finalize", "rp_bn_finalize_split", "rp_im2col_bf16", "rp_space_to_depth_h16", "rp_scnet_resize_in", "rp_scnet_resize_in_split", "rp_scnet_resize_out", "rp_scnet_resize_out_map",
+           "rp_conv_nparts", "rp_conv_layer", "rp_bn_finalize", "rp_bn_finalize_split", "rp_im2col_bf16", "rp_space_to_depth_h16", "rp_scnet_resize_in", "rp_scnet_resize_in_split", "rp_scnet_resize_out", "rp_scnet_resize_out_map", "rp_scnet_resize_out_sub",
            "rp_conv_launch_count", "rp_tc_gemm_test",
            "rp_conv_halo_plan", "rp_conv_halo_fits", "rp_conv_layer_halo", "rp_conv_halo_debug", "rp_conv_halo_prof", "rp_conv_halo_tma_count",
            "rp_affinity_build", "rp_scnet_forward", "rp_resnet18_8s_forward", "rp_gather_primitives", "rp_match_sample_workspace_bytes", "rp_match_sample", "rp_heat_sample", "rp_warp_workspace_bytes", "rp_warp_views", "rp_warp_views_ex", "rp_pano2pc", "rp_blend_completion",
@@ -143,6 +143,8 @@ def load():
     lib.rp_scnet_resize_in_split.argtypes = [vp, i32, i32, i32, vp, vp]
     lib.rp_scnet_resize_out.restype = i32
     lib.rp_scnet_resize_out.argtypes = [vp, i32, i32, i32, i32, vp, vp]
+    lib.rp_scnet_resize_out_sub.restype = i32
+    lib.rp_scnet_resize_out_sub.argtypes = [vp, i32, i32, vp, vp, i32, i32, i32, vp, i32, vp]
     lib.rp_scnet_resize_out_map.restype = i32
     lib.rp_scnet_resize_out_map.argtypes = [vp, i32, i32, vp, i32, i32, i32, vp, vp]
     lib.rp_conv_launch_count.restype = i64

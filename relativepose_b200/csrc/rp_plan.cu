@@ -65,6 +65,10 @@ int run_plan(const rp_net_op* ops, int n_ops, void* stream) {
             rc = rp_space_to_depth_h16(as_ptr<const float*>(a[0]), as_int(a[1]), as_int(a[2]), as_int(a[3]), as_int(a[4]), as_int(a[5]),
                                        as_ptr<void*>(a[6]), stream);
             break;
+        case RP_OP_RESIZE_OUT_SUB:
+            rc = rp_scnet_resize_out_sub(as_ptr<const float*>(a[0]), as_int(a[1]), as_int(a[2]), as_ptr<const int*>(a[3]), as_ptr<const int*>(a[4]),
+                                         as_int(a[5]), as_int(a[6]), as_int(a[7]), as_ptr<float*>(a[8]), as_int(a[9]), stream);
+            break;
         default: return RP_ERR_UNSUPPORTED;
         }
         if (rc != RP_OK) return rc;

@@ -394,11 +394,11 @@ __global__ void scnet_resize_in_split_kernel(const float* __restrict__ x, int n,
 // `pitch` floats per pixel in memory; output channel c reads channel cmap[c] (cmap == nullptr: identity) -- the engine
 // keeps each head at a 16-byte aligned channel offset so that the head kernels store float4s.
 __global__ void scnet_resize_out_kernel(const float* __restrict__ in, int n, int C, int H, int W, float* __restrict__ out,
-                                        int pitch, const int* __restrict__ cmap) {
+                                        int pitch, const int* __restrict__ cmap, int out_cs, const int* __restrict__ omap) {
     // in [n,224,224,pitch] NHWC -> out [n,C,H,W]: one thread per output pixel; the four corner pixels are contiguous
     // channel vectors, the per-channel stores are coalesced across the warp (consecutive ox); 4 channels in flight
-    __shared__ int s_map[256];
-    for (int i = threadIdx.x; i < C && i < 256; i += blockDim.x) s_map[i] = cmap ? cmap[i] : i;
+    __shared__ int s_map[256], s_omap[256];
+    for (int i = threadIdx.x; i < C && i < 256; i += blockDim.x) { s_map[i] = cmap ? cmap[i] : i; s_omap[i] = omap ? omap[i] : i; }
     __syncthreads();
     const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const size_t total = (size_t)n * H * W;
@@ -410,7 +410,7 @@ __global__ void scnet_resize_out_kernel(const float* __restrict__ in, int n, int
     const float* b = in + (size_t)im * 224 * 224 * pitch;
     const float* p00 = b + ((size_t)y0 * 224 + x0) * pitch; const float* p01 = b + ((size_t)y0 * 224 + x1) * pitch;
     const float* p10 = b + ((size_t)y1 * 224 + x0) * pitch; const float* p11 = b + ((size_t)y1 * 224 + x1) * pitch;
-    float* o = out + (size_t)im * C * H * W + (size_t)oy * W + ox;
+    float* o = out + (size_t)im * out_cs * H * W + (size_t)oy * W + ox;      // out_cs: channels per image of the output tensor (>= C)
     int c = 0;
     for (; c + 4 <= C; c += 4) {
         float v[4];
@@ -420,11 +420,11 @@ __global__ void scnet_resize_out_kernel(const float* __restrict__ in, int n, int
             v[u] = ly0 * (lx0 * __ldg(p00 + s) + lx1 * __ldg(p01 + s)) + ly1 * (lx0 * __ldg(p10 + s) + lx1 * __ldg(p11 + s));
         }
 #pragma unroll
-        for (int u = 0; u < 4; ++u) o[(size_t)(c + u) * H * W] = v[u];
+        for (int u = 0; u < 4; ++u) o[(size_t)s_omap[c + u] * H * W] = v[u];
     }
     for (; c < C; ++c) {
         const int s = s_map[c];
-        o[(size_t)c * H * W] = ly0 * (lx0 * p00[s] + lx1 * p01[s]) + ly1 * (lx0 * p10[s] + lx1 * p11[s]);
+        o[(size_t)s_omap[c] * H * W] = ly0 * (lx0 * p00[s] + lx1 * p01[s]) + ly1 * (lx0 * p10[s] + lx1 * p11[s]);
     }
 }
 
@@ -607,9 +607,9 @@ __global__ void resize_to_nchw_kernel(const float* __restrict__ src, int n, int 
 constexpr int RS_PX = 64, RS_MAXSRC = 40, RS_MAXFL = 2 * RS_MAXSRC * 72;
 __global__ void __launch_bounds__(256) resize_up_nchw_kernel(const float* __restrict__ src, int n, int Hs, int Ws, int pitch,
                                                              const int* __restrict__ cmap, int C, float* __restrict__ out, int H, int W,
-                                                             int tanh_out) {
+                                                             int tanh_out, int out_cs, const int* __restrict__ omap) {
     __shared__ __align__(16) float rows[RS_MAXFL];
-    __shared__ int s_x0[RS_PX], s_x1[RS_PX], s_map[256];
+    __shared__ int s_x0[RS_PX], s_x1[RS_PX], s_map[256], s_omap[256];
     __shared__ float s_l0[RS_PX], s_l1[RS_PX];
     const int tid = threadIdx.x;
     const int segs = (W + RS_PX - 1) / RS_PX;
@@ -622,7 +622,7 @@ __global__ void __launch_bounds__(256) resize_up_nchw_kernel(const float* __rest
         if (ox0 + tid < W) bilin_coord(ox0 + tid, (float)Ws / (float)W, Ws, x0, x1, l0, l1);
         s_x0[tid] = x0; s_x1[tid] = x1; s_l0[tid] = l0; s_l1[tid] = l1;
     }
-    for (int i = tid; i < C; i += 256) s_map[i] = cmap ? cmap[i] : i;
+    for (int i = tid; i < C; i += 256) { s_map[i] = cmap ? cmap[i] : i; s_omap[i] = omap ? omap[i] : i; }   // item i: source / output channel
     __syncthreads();
     const int last = min(W - 1, ox0 + RS_PX - 1) - ox0;
     const int xs0 = s_x0[0], nsrc = s_x1[last] - xs0 + 1;       // source columns of the segment (<= RS_MAXSRC, checked on the host)
@@ -645,7 +645,7 @@ __global__ void __launch_bounds__(256) resize_up_nchw_kernel(const float* __rest
     }
     __syncthreads();
     const size_t plane = (size_t)H * W;
-    float* o = out + (size_t)im * C * plane + (size_t)oy * W + ox0;
+    float* o = out + (size_t)im * out_cs * plane + (size_t)oy * W + ox0;     // out_cs: channels per image of the output tensor (>= C)
     // a thread keeps ONE output pixel (its column offsets and weights stay in registers) and walks the channels: a warp
     // writes 32 consecutive pixels of one channel, and the inner loop is 4 shared-memory reads + the channel map per output
     const int px = tid & (RS_PX - 1);
@@ -662,7 +662,7 @@ __global__ void __launch_bounds__(256) resize_up_nchw_kernel(const float* __rest
         float y = v;
         if (tanh_out == 1) y = tanhf(v);
         else if (tanh_out == 2) asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(v));
-        __stcs(o + (size_t)c * plane, y);
+        __stcs(o + (size_t)s_omap[c] * plane, y);
     }
 }
 
@@ -940,8 +940,8 @@ int rp_scnet_resize_out(const float* in, int n, int C, int H, int W, float* out,
     if (!in || !out || n < 1) return RP_ERR_INVALID_ARG;
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
     size_t total = (size_t)n * H * W;
-    if (resize_up_ok(224, W, C, C) && H >= 1) resize_up_nchw_kernel<<<(unsigned)((size_t)n * H * ((W + RS_PX - 1) / RS_PX)), 256, 0, stream>>>(in, n, 224, 224, C, nullptr, C, out, H, W, 0);
-    else scnet_resize_out_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(in, n, C, H, W, out, C, nullptr);
+    if (resize_up_ok(224, W, C, C) && H >= 1) resize_up_nchw_kernel<<<(unsigned)((size_t)n * H * ((W + RS_PX - 1) / RS_PX)), 256, 0, stream>>>(in, n, 224, 224, C, nullptr, C, out, H, W, 0, C, nullptr);
+    else scnet_resize_out_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(in, n, C, H, W, out, C, nullptr, C, nullptr);
     ++g_conv_launches;
     return cudaGetLastError() == cudaSuccess ? RP_OK : RP_ERR_CUDA;
 }
@@ -950,8 +950,19 @@ int rp_scnet_resize_out_map(const float* in, int n, int pitch, const int* cmap, 
     if (!in || !out || !cmap || n < 1 || pitch < 1) return RP_ERR_INVALID_ARG;
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
     size_t total = (size_t)n * H * W;
-    if (resize_up_ok(224, W, pitch, C)) resize_up_nchw_kernel<<<(unsigned)((size_t)n * H * ((W + RS_PX - 1) / RS_PX)), 256, 0, stream>>>(in, n, 224, 224, pitch, cmap, C, out, H, W, 0);
-    else scnet_resize_out_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(in, n, C, H, W, out, pitch, cmap);
+    if (resize_up_ok(224, W, pitch, C)) resize_up_nchw_kernel<<<(unsigned)((size_t)n * H * ((W + RS_PX - 1) / RS_PX)), 256, 0, stream>>>(in, n, 224, 224, pitch, cmap, C, out, H, W, 0, C, nullptr);
+    else scnet_resize_out_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(in, n, C, H, W, out, pitch, cmap, C, nullptr);
+    ++g_conv_launches;
+    return cudaGetLastError() == cudaSuccess ? RP_OK : RP_ERR_CUDA;
+}
+
+int rp_scnet_resize_out_sub(const float* in, int n, int pitch, const int* cmap, const int* omap, int C, int H, int W, float* out,
+                            int out_channels, void* stream_) {
+    if (!in || !out || !cmap || !omap || n < 1 || pitch < 1 || C < 1 || C > 256 || C > out_channels) return RP_ERR_INVALID_ARG;
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    size_t total = (size_t)n * H * W;
+    if (resize_up_ok(224, W, pitch, C)) resize_up_nchw_kernel<<<(unsigned)((size_t)n * H * ((W + RS_PX - 1) / RS_PX)), 256, 0, stream>>>(in, n, 224, 224, pitch, cmap, C, out, H, W, 0, out_channels, omap);
+    else scnet_resize_out_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(in, n, C, H, W, out, pitch, cmap, out_channels, omap);
     ++g_conv_launches;
     return cudaGetLastError() == cudaSuccess ? RP_OK : RP_ERR_CUDA;
 }
@@ -991,7 +1002,7 @@ int rp_resize_to_nchw(const float* src, int n, int Hs, int Ws, int C, float* out
     if (!src || !out || n < 1) return RP_ERR_INVALID_ARG;
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
     size_t total = (size_t)n * H * W;
-    if (resize_up_ok(Ws, W, C, C)) resize_up_nchw_kernel<<<(unsigned)((size_t)n * H * ((W + RS_PX - 1) / RS_PX)), 256, 0, stream>>>(src, n, Hs, Ws, C, nullptr, C, out, H, W, tanh_out);
+    if (resize_up_ok(Ws, W, C, C)) resize_up_nchw_kernel<<<(unsigned)((size_t)n * H * ((W + RS_PX - 1) / RS_PX)), 256, 0, stream>>>(src, n, Hs, Ws, C, nullptr, C, out, H, W, tanh_out, C, nullptr);
     else resize_to_nchw_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(src, n, Hs, Ws, C, out, H, W, tanh_out);
     ++g_conv_launches;
     return cudaGetLastError() == cudaSuccess ? RP_OK : RP_ERR_CUDA;

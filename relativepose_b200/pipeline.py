@@ -117,15 +117,16 @@ def _batch_from_gathered(pc, nn, desc, weights):
                                                   side(pc, 1), side(nn, 1), side(desc, 1), weights.view(B, 2, K)[:, 1].reshape(-1), B)
 
 
-def _net_forward(net, inp):
+def _net_forward(net, inp, heads=None):
     """SCNet forward without the defensive output copy when ``net`` is this package's SCNet: the engine's output buffer is
-    consumed (blend, gather) before the next forward.  Any other module is simply called."""
+    consumed (blend, gather) before the next forward, and only the output heads the caller reads are computed (``heads``).  Any
+    other module is simply called."""
     from .model.mymodel import SCNet
     if isinstance(net, SCNet):
         from . import scnet_engine
         if net._engine is None:
             net._engine = scnet_engine.ScnetEngine(net)
-        return net._engine.forward(inp, borrow=True)
+        return net._engine.forward(inp, borrow=True, heads=heads)
     return net(inp)
 
 
@@ -197,7 +198,7 @@ def RelativePoseEstimationViaCompletion_batch(net, rgb, norm, depth, pts, weight
                 Rs[0::2] = np.linalg.inv(R_hat[lo:hi])
                 Rs[1::2] = R_hat[lo:hi]
                 _util.warping_device(S['inp'], Rs, args.dataset, out=S['inp'][:, 8:], src_index=S['swap'])   # reads channels 0..7, writes 8..15
-                f = _net_forward(net, S['inp'])                                                               # :619-623
+                f = _net_forward(net, S['inp'], heads=('n', 'd', 'f'))    # :619-623; the alternation reads f[3:7] (:628-634) and the descriptors
                 nrm2, dep2 = _util.blend_completion_device(f, S['mask'], S['norm_gt'], S['depth_gt'])          # :628-634
                 parts.append(gather_primitives(f[:, idx_f:idx_f + args.featureDim], dep2, nrm2, S['pts'], S['w'], args.dataset, raw=True))
             d = _batch_from_gathered(*[torch.cat([p[k] for p in parts], 0) if len(parts) > 1 else parts[0][k] for k in range(4)])

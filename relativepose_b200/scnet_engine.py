@@ -335,13 +335,19 @@ class ScnetEngine(object):
                                                    out.scale.data_ptr(), out.shift.data_ptr(), out.pitch, out.ch_off, stream)
 
     # ---------------------------------------------------------------- forward
-    def forward(self, x, trace=None, borrow=False):
+    def forward(self, x, trace=None, borrow=False, heads=None):
         """``borrow=True`` returns the engine's own output buffer (valid until the next forward of this engine) instead of a
         fresh copy -- the batched pipeline consumes the output before it calls the network again, and the copy of a
-        [64,54,160,640] float32 tensor is 2.8 GB of HBM traffic per call."""
+        [64,54,160,640] float32 tensor is 2.8 GB of HBM traffic per call.  ``heads``: compute only these output heads (their
+        decoder branches, 1x1 heads and the resize of their channels); the channels of the other heads in the returned tensor
+        are then undefined -- the alternation reads normals, depth and descriptors only, the rgb and semantic branches are a
+        fifth of the forward."""
         torch = self.torch
+        heads = tuple(heads) if heads else None
+        if heads is not None and set(heads) >= set(h for h, _ in self.net.head_channels()):
+            heads = None
         if (self.use_plan or self.use_graph) and trace is None and x.is_cuda and x.dim() == 4:
-            key = (tuple(x.shape), str(x.device), self.mode, tuple((p.data_ptr(), p._version) for p in self.net.parameters()))
+            key = (tuple(x.shape), str(x.device), self.mode, heads, tuple((p.data_ptr(), p._version) for p in self.net.parameters()))
             ent = self._graphs.get(key)
             if ent is not None:                       # CUDA-graph replay of the native forward
                 gph, xs, ys = ent
@@ -373,13 +379,13 @@ class ScnetEngine(object):
                 xs = x.contiguous().float().clone()
                 self._rec = []
                 try:
-                    ys = self._forward_eager(xs, None)
+                    ys = self._forward_eager(xs, None, heads)
                     rec = self._rec
                 finally:
                     self._rec = None
                 self._plans = {key: (xs, ys, ((_lib.RpNetOp * len(rec))(*rec), len(rec)))}     # one plan: buffers are shared between shapes
                 return ys if borrow else ys.clone()
-        return self._forward_eager(x, trace)
+        return self._forward_eager(x, trace, heads)
 
     def input_buffer(self, shape, device):
         """The static input tensor of the frozen plan for this shape (None before the plan exists): a caller that assembles
@@ -389,7 +395,7 @@ class ScnetEngine(object):
                 return ent[1] if key in self._graphs else ent[0]
         return None
 
-    def _forward_eager(self, x, trace=None):
+    def _forward_eager(self, x, trace=None, only=None):
         torch = self.torch
         if not x.is_cuda:
             raise RuntimeError("relativepose_b200.SCNet.forward needs a CUDA tensor (no CPU fallback)")
@@ -456,6 +462,8 @@ class ScnetEngine(object):
             block('deconv5', cat(B['dx6'], B['x5']), B['dx5'], True, 4, 2, 1)
             block('deconv4', cat(B['dx5'], B['x4']), B['dx4'], True, 4, 2, 1)
             for st, c in heads:
+                if only is not None and st not in only:
+                    continue                                                   # this head's decoder branch is not wanted
                 o = B['head_off'][st]
                 if st in ('rgb', 'n', 'd'):                                    # mymodel.py:309-325 (skipLayer=1 only, see SCNet.__init__)
                     block('deconv3' + st, [B['dx4'], B['xin'].view(xin_slot[st], 128)], B['d3' + st], True, 4, 2, 1)
@@ -468,8 +476,24 @@ class ScnetEngine(object):
                     self._conv('deconv1' + st, [B['d2' + st]], B['out224'].view(o, c), False, 1, 1, 0, bn=False,
                                bias=getattr(net, 'deconv1' + st).bias, tanh=(st == 'f' and bool(net.useTanh)), stream=stream)
             out = torch.empty((n, ctot, H, W), dtype=torch.float32, device=x.device)
-            self._run("rp_scnet_resize_out_map", B['out224'].buf.data_ptr(), n, B['out224'].pitch, B['cmap'].data_ptr(), ctot, H, W,
-                                                        out.data_ptr(), stream)
+            if only is None:
+                self._run("rp_scnet_resize_out_map", B['out224'].buf.data_ptr(), n, B['out224'].pitch, B['cmap'].data_ptr(), ctot, H, W,
+                                                            out.data_ptr(), stream)
+            else:
+                c0, items = 0, []                          # (source channel of out224, output channel) of every wanted channel
+                cm = B['cmap'].tolist() if 'cmap_list' not in B else B['cmap_list']
+                B['cmap_list'] = cm
+                for st, c in heads:
+                    if st in only:
+                        items += [(cm[c0 + j], c0 + j) for j in range(c)]
+                    c0 += c
+                skey = ('submap', tuple(only))
+                if skey not in B:
+                    B[skey] = (torch.tensor([a for a, _ in items], dtype=torch.int32, device=x.device),
+                               torch.tensor([b for _, b in items], dtype=torch.int32, device=x.device))
+                sm, om = B[skey]
+                self._run("rp_scnet_resize_out_sub", B['out224'].buf.data_ptr(), n, B['out224'].pitch, sm.data_ptr(), om.data_ptr(), len(items),
+                                                            H, W, out.data_ptr(), ctot, stream)
             if trace is not None:
                 self._dump(trace)
         return out

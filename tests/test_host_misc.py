@@ -33,7 +33,7 @@ def test_net_op_struct_matches_the_header_layout():
     assert ctypes.sizeof(_lib.RpNetOp) == 8 + ctypes.sizeof(_lib.RpConvDesc) + 16 * 8
     assert _lib.RpNetOp.conv.offset == 8 and _lib.RpNetOp.arg.offset == 8 + ctypes.sizeof(_lib.RpConvDesc)
     assert ctypes.sizeof(_lib.RpConvDesc) % 8 == 0
-    assert sorted(_lib.NET_OPS.values()) == [1] + list(range(3, 15))      # 2 was the per-tap tensor-core kernel (removed in round 2)
+    assert sorted(_lib.NET_OPS.values()) == [1] + list(range(3, 16))      # 2 was the per-tap tensor-core kernel (removed in round 2)
 
 
 def test_small_batch_constants():
