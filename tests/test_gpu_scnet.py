@@ -221,3 +221,27 @@ def test_scnet_split_precision_tensor_core_mode(name):
     gsub = float(np.abs(y.cpu().numpy()[:, :, ::4, ::8] - G[name + '/sub']).max())
     print("tc3 final: max %.3e rms %.3e (f head max %.3e), vs reference golden (subsampled) max %.3e, |y|max %.2f" % (emax, erms, ef, gsub, yo.abs().max().item()))
     assert emax <= 1e-3 and gsub <= 1e-3 and ef <= 4e-4
+
+
+def test_scnet_head_subset_forward():
+    """ScnetEngine.forward(heads=...) (what the batched alternation asks for: normals, depth, descriptors) computes the wanted
+    heads bit-identically to the full forward and leaves the other decoder branches out (fewer launches)."""
+    import torch
+    from relativepose_b200 import _lib, synth
+    from relativepose_b200.model.mymodel import SCNet
+    from relativepose_b200.scnet_engine import ScnetEngine
+    torch.manual_seed(0)
+    net = SCNet(_args(15, 1)).cuda()
+    x = torch.from_numpy(synth.make_panorama_pair(3, "suncg", 64, 256)).cuda()
+    lib = _lib.load()
+    full_eng, sub_eng = ScnetEngine(net), ScnetEngine(net)
+    n0 = lib.rp_conv_launch_count()
+    full = full_eng.forward(x)
+    n1 = lib.rp_conv_launch_count()
+    subs = [sub_eng.forward(x, heads=('n', 'd', 'f')) for _ in range(4)]          # eager, recorded, plan replay, graph replay
+    torch.cuda.synchronize()
+    n2 = lib.rp_conv_launch_count()
+    want = list(range(3, 7)) + list(range(7 + 15, 7 + 15 + 32))                   # n (3), d (1), f (32) of 'rgbdnsf'
+    for sub in subs:
+        assert torch.equal(sub[:, want], full[:, want])
+    assert (n2 - n1) < 4 * (n1 - n0)                                              # the rgb / s branches were not launched
