@@ -31,6 +31,23 @@ def _stale(out, deps):
     return any(os.path.getmtime(d) > t for d in deps)
 
 
+def build_host_ext(force=False):
+    """The CPython extension _rp_pack (csrc/rp_pack.c: host-side packing of record lists; pure C, no CUDA) with gcc, in-tree."""
+    import sysconfig
+    src = os.path.join(CSRC, "rp_pack.c")
+    out = os.path.join(HERE, "_rp_pack.so")
+    if not (force or _stale(out, [src])):
+        return []
+    cc = os.environ.get("CC") or shutil.which("gcc") or shutil.which("cc")
+    if not cc:
+        raise RuntimeError("no C compiler for _rp_pack")
+    cmd = [cc, "-O2", "-fPIC", "-shared", "-Wall", "-I", sysconfig.get_paths()["include"], "-o", out, src]
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("building _rp_pack failed:\n%s" % r.stdout)
+    return ["_rp_pack.so"]
+
+
 def build_all(force=False, verbose=False):
     """Each .cu is compiled to an object (only when stale, in parallel), then linked into the one shared library."""
     from concurrent.futures import ThreadPoolExecutor
@@ -68,6 +85,7 @@ def build_all(force=False, verbose=False):
             if r.returncode != 0:
                 raise RuntimeError("link failed for %s:\n%s" % (out, r.stdout))
             built.append(out)
+    built += build_host_ext(force)
     return built
 
 

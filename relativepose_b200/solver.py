@@ -68,6 +68,22 @@ def wave_chunks(B, slots):
     return bounds
 
 
+_PACK_EXT = [None, False]
+
+
+def _pack_ext():
+    """The host packing extension (csrc/rp_pack.c, built by relativepose_b200.build), or None when it is not built: the numpy
+    packing path is then used -- this is host-side data marshalling, not a compute fallback."""
+    if not _PACK_EXT[1]:
+        _PACK_EXT[1] = True
+        try:
+            from . import _rp_pack
+            _PACK_EXT[0] = _rp_pack
+        except ImportError:
+            _PACK_EXT[0] = None
+    return _PACK_EXT[0]
+
+
 class PinnedArena(object):
     """One growing block of page-locked host memory handed out in 256-byte aligned slices (reset per batch): packing a
     list of records costs the copies only, not a cudaHostAlloc per array."""
@@ -138,9 +154,15 @@ class PackedBatch(object):
                 ("feat_t", "feat_tgt", np.float32, D, Nt), ("w_t", "weight_tgt", np.float64, 0, Nt))
         dst = {name: host((total, cols) if cols else (total,), dtype) for name, _, dtype, cols, total in jobs}   # arena slices: in order
 
+        fast = _pack_ext() if isinstance(records, list) else None
+
         def fill(job):
             name, key, dtype, cols, total = job
             a = dst[name][0]
+            if fast is not None:            # C loop over the records (buffer protocol, copies with the GIL released); None = a
+                dt = np.dtype(dtype)        # record needs a dtype conversion or is not an array: numpy handles that below
+                if fast.pack_field(records, key, a, dt.char, dt.itemsize, int(cols)) is not None:
+                    return
             parts = [np.asarray(r[key]) for r in records]
             parts = [q if q.ndim == (2 if cols else 1) else (q.reshape(-1, cols) if cols else q.reshape(-1)) for q in parts]
             if parts:

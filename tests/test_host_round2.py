@@ -185,3 +185,33 @@ def test_wave_aligned_chunks():
     for B, per in ((1, 1), (7, 3), (5000, 148), (2048, 592)):
         b = wave_chunks(B, per)
         assert b[0] == 0 and b[-1] == B and all(lo < hi for lo, hi in zip(b, b[1:]))
+
+
+def test_record_packing_extension_matches_numpy():
+    """PackedBatch through the C packing extension (csrc/rp_pack.c: buffer protocol + memcpy with the GIL released) equals the
+    numpy.concatenate path array for array -- incl. a Fortran-ordered descriptor array, a negative-stride view and a record that
+    needs a dtype conversion (the extension declines that field, numpy converts)."""
+    from relativepose_b200 import solver, synth
+    from relativepose_b200.solver import PackedBatch
+    ext = solver._pack_ext()
+    assert ext is not None, "relativepose_b200/_rp_pack.so is missing: python -m relativepose_b200.build"
+    recs = [dict(r) for r in synth.make_batch(77, 300, 40)]
+    recs[5]['feat_src'] = np.asfortranarray(recs[5]['feat_src'])
+    recs[7]['pc_tgt'] = recs[7]['pc_tgt'][::-1]
+    recs[9]['normal_src'] = recs[9]['normal_src'].astype(np.float32)
+    a = PackedBatch(recs, pin=False)
+    try:
+        solver._PACK_EXT[0] = None                                   # numpy path
+        b = PackedBatch(recs, pin=False)
+    finally:
+        solver._PACK_EXT[0], solver._PACK_EXT[1] = None, False       # re-probe on next use
+    for f in PackedBatch.FIELDS + ("off_s_t", "off_t_t", "sum_order_t"):
+        assert np.array_equal(getattr(a, f).numpy(), getattr(b, f).numpy()), f
+    assert int(a.sum_order_t.numpy()[5]) == 1 and int(a.sum_order_t.numpy()[6]) == 0
+    # direct calls: row counts, declined cases
+    dst = np.empty((300 * 40, 3), np.float64)
+    cnt = np.frombuffer(ext.pack_field(recs, 'pc_src', dst, 'd', 8, 3), dtype=np.int64)
+    assert cnt.tolist() == [40] * 300 and np.array_equal(dst, np.concatenate([r['pc_src'] for r in recs], 0))
+    assert ext.pack_field(recs, 'normal_src', dst, 'd', 8, 3) is None            # record 9 is float32
+    assert ext.pack_field(recs, 'no_such_key', dst, 'd', 8, 3) is None
+    assert ext.pack_field(recs, 'pc_src', np.empty((10, 3)), 'd', 8, 3) is None   # destination too small
