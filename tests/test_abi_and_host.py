@@ -101,3 +101,28 @@ def test_product_never_imports_oracle():
                 if re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M):
                     bad.append(f)
     assert not bad, "product modules import the oracle: %s" % bad
+
+
+def test_round2_entry_points_validate_their_arguments_without_a_gpu():
+    """rp_solve_pair_host rejects null / out-of-range arguments before it touches the device; rp_solver_wide_max is a plain
+    get / set (default: the SM count, 148 when no device can be asked)."""
+    import ctypes
+    from relativepose_b200 import _lib
+    lib = _lib.load()
+    p = _lib.RpParams()
+    T = (ctypes.c_double * 16)()
+    st = (ctypes.c_int32 * 1)()
+    z = ctypes.c_void_p(0)
+    buf = (ctypes.c_double * 64)()
+    b = ctypes.cast(buf, ctypes.c_void_p)
+    rc = lib.rp_solve_pair_host(10, 10, z, z, z, z, z, z, z, z, 32, ctypes.byref(p), z, 5, 0, 0, ctypes.cast(T, ctypes.c_void_p),
+                                ctypes.cast(st, ctypes.c_void_p), z, z)
+    assert rc == -1          # RP_ERR_INVALID_ARG
+    rc = lib.rp_solve_pair_host(10, 10, b, b, b, b, b, b, b, b, 32, ctypes.byref(p), z, _lib.MAX_TOPK + 1, 0, 0,
+                                ctypes.cast(T, ctypes.c_void_p), ctypes.cast(st, ctypes.c_void_p), z, z)
+    assert rc == -3          # RP_ERR_UNSUPPORTED
+    old = lib.rp_solver_wide_max(-1)
+    assert old >= 0
+    assert lib.rp_solver_wide_max(7) == old and lib.rp_solver_wide_max(-1) == 7
+    lib.rp_solver_wide_max(old)
+    assert lib.rp_solver_wide_max(-1) == old
